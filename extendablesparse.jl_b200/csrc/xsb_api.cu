@@ -1,0 +1,1051 @@
+// xsb_api.cu -- the C ABI of libxsparse_b200 (include/xsparse_b200.h): handle, device
+// memory, staging buffers and the flush pipeline that strings the kernels together.
+#include "../../include/xsparse_b200.h"
+#include "xsb_internal.h"
+
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace xsb;
+
+namespace {
+
+struct ApiError : std::runtime_error
+{
+    int32_t code;
+    ApiError(int32_t c, const std::string &w) : std::runtime_error(w), code(c) {}
+};
+
+thread_local std::string g_err;
+
+int ceil_log2(i64 x)
+{
+    int b = 0;
+    while (((i64)1 << b) < x)
+        ++b;
+    return b < 1 ? 1 : b;
+}
+
+bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct Stage
+{
+    Rec *buf = nullptr;
+    i64 cap = 0;   // records the allocation holds (front included)
+    i64 front = 0; // slots reserved ahead of the staged records for the old CSC (single-partition handles)
+    i64 count = 0; // staged records
+};
+
+} // namespace
+
+struct xsb_matrix
+{
+    i64 m = 0, n = 0;
+    int idx64 = 1, base = 1, n_tid = 1, device = 0;
+    KeyLayout L{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // resident CSC, in the caller's index type and base
+    void *colptr = nullptr;
+    void *csc_store = nullptr; // holds rowval then nzval
+    size_t csc_store_bytes = 0;
+    void *rowval = nullptr;
+    double *nzval = nullptr;
+    i64 nnz = 0;
+
+    std::vector<Stage> stage;
+    bool has_assign = false;
+
+    // frozen pattern
+    bool frozen = false;
+    i64 f_count = 0;
+    i64 *f_slot = nullptr;
+    u32 *f_perm = nullptr;
+    i64 *f_segstart = nullptr;
+
+    u64 *d_scal = nullptr; // 8 device scalars
+    u64 *h_scal = nullptr; // pinned mirror
+
+    LaunchCounter lc;
+    bool profiling = false;
+    xsb_flush_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    size_t isz() const { return idx64 ? 8 : 4; }
+    void *dalloc(size_t bytes)
+    {
+        void *p = nullptr;
+        if (bytes == 0)
+            bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        if (e != cudaSuccess)
+        {
+            cudaGetLastError();
+            throw ApiError(e == cudaErrorMemoryAllocation ? XSB_ENOMEM : XSB_ECUDA,
+                           std::string("device allocation of ") + std::to_string(bytes) +
+                               " bytes failed: " + cudaGetErrorString(e));
+        }
+        return p;
+    }
+    void dfree(void *p)
+    {
+        if (p)
+            cudaFreeAsync(p, stream);
+    }
+    void sync() { XSB_CUDA(cudaStreamSynchronize(stream)); }
+    i64 pending() const
+    {
+        i64 s = 0;
+        for (auto &st : stage)
+            s += st.count;
+        return s;
+    }
+    CscView view() const { return CscView{colptr, rowval, nzval, nnz}; }
+    void drop_frozen()
+    {
+        dfree(f_slot);
+        dfree(f_perm);
+        dfree(f_segstart);
+        f_slot = nullptr;
+        f_perm = nullptr;
+        f_segstart = nullptr;
+        frozen = false;
+        f_count = 0;
+    }
+    void clear_staging(bool release)
+    {
+        for (auto &st : stage)
+        {
+            st.count = 0;
+            st.front = 0;
+            if (release)
+            {
+                dfree(st.buf);
+                st.buf = nullptr;
+                st.cap = 0;
+            }
+        }
+        has_assign = false;
+    }
+    void set_empty_csc()
+    {
+        dfree(colptr);
+        dfree(csc_store);
+        colptr = dalloc(isz() * (size_t)(n + 1));
+        fill_index(stream, colptr, n + 1, idx64, base, lc); // spzeros: colptr[:] = base
+        csc_store = nullptr;
+        csc_store_bytes = 0;
+        rowval = nullptr;
+        nzval = nullptr;
+        nnz = 0;
+    }
+    // make room for `extra` more records in partition t
+    void ensure_stage(int t, i64 extra)
+    {
+        Stage &st = stage[t];
+        if (st.count == 0)
+            st.front = (n_tid == 1) ? nnz : 0;
+        const i64 need = st.front + st.count + extra;
+        if (need <= st.cap)
+            return;
+        i64 cap = std::max<i64>(need, st.cap + st.cap / 2);
+        cap = std::max<i64>(cap, 1024);
+        Rec *nb = static_cast<Rec *>(dalloc(sizeof(Rec) * (size_t)cap));
+        if (st.buf && st.count > 0)
+            XSB_CUDA(cudaMemcpyAsync(nb + st.front, st.buf + st.front, sizeof(Rec) * (size_t)st.count,
+                                     cudaMemcpyDeviceToDevice, stream));
+        dfree(st.buf);
+        st.buf = nb;
+        st.cap = cap;
+    }
+};
+
+namespace {
+
+void set_err(xsb_matrix *h, const std::string &s)
+{
+    if (h)
+        h->err = s;
+    else
+        g_err = s;
+}
+
+template <class F> int32_t guard(xsb_matrix *h, F &&f)
+{
+    try
+    {
+        if (h)
+            XSB_CUDA(cudaSetDevice(h->device));
+        return f();
+    }
+    catch (const ApiError &e)
+    {
+        set_err(h, e.what());
+        return e.code;
+    }
+    catch (const CudaError &e)
+    {
+        set_err(h, e.what());
+        cudaGetLastError();
+        return e.code == cudaErrorMemoryAllocation ? XSB_ENOMEM : XSB_ECUDA;
+    }
+    catch (const std::bad_alloc &)
+    {
+        set_err(h, "host allocation failed");
+        return XSB_ENOMEM;
+    }
+    catch (const std::exception &e)
+    {
+        set_err(h, e.what());
+        return XSB_EINVAL;
+    }
+    catch (...)
+    {
+        set_err(h, "unknown failure");
+        return XSB_EINVAL;
+    }
+}
+
+#define REQUIRE(cond, code, msg)                                                                   \
+    do                                                                                             \
+    {                                                                                              \
+        if (!(cond))                                                                               \
+            throw ApiError((code), (msg));                                                         \
+    } while (0)
+
+// A caller array made visible to the device: device pointers pass through,
+// host pointers are staged through a stream-ordered temporary.
+struct DevIn
+{
+    xsb_matrix *h;
+    const void *ptr = nullptr;
+    void *tmp = nullptr;
+    DevIn(xsb_matrix *h_, const void *p, size_t bytes) : h(h_)
+    {
+        if (bytes == 0 || p == nullptr)
+        {
+            ptr = p;
+            return;
+        }
+        if (is_device_ptr(p))
+            ptr = p;
+        else
+        {
+            tmp = h->dalloc(bytes);
+            XSB_CUDA(cudaMemcpyAsync(tmp, p, bytes, cudaMemcpyHostToDevice, h->stream));
+            ptr = tmp;
+        }
+    }
+    ~DevIn() { h->dfree(tmp); }
+};
+
+struct DevOut
+{
+    xsb_matrix *h;
+    void *user;
+    void *ptr = nullptr;
+    void *tmp = nullptr;
+    size_t bytes;
+    DevOut(xsb_matrix *h_, void *p, size_t b) : h(h_), user(p), bytes(b)
+    {
+        if (p == nullptr || b == 0)
+            return;
+        if (is_device_ptr(p))
+            ptr = p;
+        else
+        {
+            tmp = h->dalloc(b);
+            ptr = tmp;
+        }
+    }
+    void finish()
+    { // enqueue the copy back; caller synchronises
+        if (tmp)
+            XSB_CUDA(cudaMemcpyAsync(user, tmp, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ~DevOut() { h->dfree(tmp); }
+};
+
+u64 read_scalar(xsb_matrix *h, int slot)
+{
+    XSB_CUDA(cudaMemcpyAsync(h->h_scal + slot, h->d_scal + slot, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    h->sync();
+    return h->h_scal[slot];
+}
+
+void write_scalar(xsb_matrix *h, int slot, u64 v)
+{
+    h->h_scal[slot] = v;
+    XSB_CUDA(cudaMemcpyAsync(h->d_scal + slot, h->h_scal + slot, sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+}
+
+void check_tid_flavour(xsb_matrix *h, int32_t tid, int32_t flavour)
+{
+    REQUIRE(tid >= 0 && tid < h->n_tid, XSB_EINVAL, "tid out of range");
+    REQUIRE(flavour >= XSB_UPDATE && flavour <= XSB_ASSIGN, XSB_EINVAL, "unknown insertion flavour");
+}
+
+int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out, int32_t *pattern_changed)
+{
+    REQUIRE(mode == XSB_DETERMINISTIC || mode == XSB_FAST, XSB_EINVAL, "unknown summation mode");
+    REQUIRE(combine == XSB_COMBINE_SEED || combine == XSB_COMBINE_ADD, XSB_EINVAL, "unknown combine mode");
+    const i64 n_ins = h->pending();
+    h->lc.in_flush = 0;
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    h->stats.nnz_old = h->nnz;
+    h->stats.nnz_new = h->nnz;
+    if (n_ins == 0)
+    { // flush! is a no-op without new entries: extendable.jl:249
+        if (nnz_out)
+            *nnz_out = h->nnz;
+        if (pattern_changed)
+            *pattern_changed = 0;
+        return XSB_OK;
+    }
+    cudaStream_t s = h->stream;
+    StageTimer timer;
+    StageTimer *tp = h->profiling ? &timer : nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (tp)
+    {
+        XSB_CUDA(cudaEventCreate(&e0));
+        XSB_CUDA(cudaEventCreate(&e1));
+        XSB_CUDA(cudaEventRecord(e0, s));
+    }
+
+    const i64 nnz_old = h->nnz;
+    const i64 total = nnz_old + n_ins;
+    REQUIRE((u64)total < (1ull << 40), XSB_EINVAL, "too many staged entries");
+
+    // ---- input buffer A = [old CSC as records | staged records in tid order]
+    Rec *A = nullptr;
+    bool a_is_stage0 = false;
+    if (tp)
+        tp->begin(s);
+    if (h->n_tid == 1)
+    {
+        A = h->stage[0].buf; // front was reserved when staging began
+        REQUIRE(h->stage[0].front == nnz_old && h->stage[0].cap >= total, XSB_ESTATE, "staging buffer out of step");
+        a_is_stage0 = true;
+    }
+    else
+    {
+        A = static_cast<Rec *>(h->dalloc(sizeof(Rec) * (size_t)total));
+        i64 off = nnz_old;
+        for (auto &st : h->stage)
+        {
+            if (st.count)
+                XSB_CUDA(cudaMemcpyAsync(A + off, st.buf + st.front, sizeof(Rec) * (size_t)st.count,
+                                         cudaMemcpyDeviceToDevice, s));
+            off += st.count;
+        }
+    }
+    if (tp)
+        tp->end(s, &StageTimes::other);
+    if (tp)
+        tp->begin(s);
+    expand_csc_records(s, h->view(), h->n, h->idx64, h->base, h->L, A, h->lc);
+    if (tp)
+        tp->end(s, &StageTimes::expand);
+
+    Rec *B = static_cast<Rec *>(h->dalloc(sizeof(Rec) * (size_t)total));
+    const size_t ws_bytes = std::max(sort_workspace_bytes((u64)total), reduce_workspace_bytes((u64)total, h->n));
+    void *ws = h->dalloc(ws_bytes);
+
+    // ---- sort by (col,row)
+    const SortPlan plan = make_sort_plan(h->L.low, h->L.sortbits());
+    Rec *sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
+    Rec *spare = (sorted == A) ? B : A;
+
+    // ---- reduce duplicates, emit CSC into the spare ping-pong buffer
+    void *new_colptr = h->dalloc(h->isz() * (size_t)(h->n + 1));
+    void *new_rowval = spare;
+    double *new_nzval = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spare) + 8 * (size_t)total);
+    reduce_emit_csc(s, sorted, (u64)total, h->L, combine, mode, !h->has_assign, h->n, h->idx64, h->base, new_rowval,
+                    new_nzval, new_colptr, ws, h->d_scal + 0, h->lc, tp);
+    const i64 nnz_new = (i64)read_scalar(h, 0);
+
+    if (tp)
+        tp->begin(s);
+    h->dfree(ws);
+    h->dfree(h->colptr);
+    h->dfree(h->csc_store);
+    h->colptr = new_colptr;
+    h->csc_store = spare;
+    h->csc_store_bytes = sizeof(Rec) * (size_t)total;
+    h->rowval = new_rowval;
+    h->nzval = new_nzval;
+    h->nnz = nnz_new;
+
+    // shrink an oversized store (duplicate-heavy streams) so HBM is not held hostage
+    const size_t exact = (h->isz() + 8) * (size_t)nnz_new;
+    if (h->csc_store_bytes > (32u << 20) && h->csc_store_bytes > 2 * exact)
+    {
+        const size_t rv_bytes = (h->isz() * (size_t)nnz_new + 15) & ~(size_t)15;
+        unsigned char *st = static_cast<unsigned char *>(h->dalloc(rv_bytes + 8 * (size_t)nnz_new));
+        XSB_CUDA(cudaMemcpyAsync(st, h->rowval, h->isz() * (size_t)nnz_new, cudaMemcpyDeviceToDevice, s));
+        XSB_CUDA(cudaMemcpyAsync(st + rv_bytes, h->nzval, 8 * (size_t)nnz_new, cudaMemcpyDeviceToDevice, s));
+        h->dfree(h->csc_store);
+        h->csc_store = st;
+        h->csc_store_bytes = rv_bytes + 8 * (size_t)nnz_new;
+        h->rowval = st;
+        h->nzval = reinterpret_cast<double *>(st + rv_bytes);
+    }
+
+    // the buffer that held the sorted records is recycled as the next staging buffer
+    if (a_is_stage0)
+    {
+        h->stage[0].buf = sorted;
+        h->stage[0].cap = total;
+    }
+    else
+        h->dfree(sorted);
+    h->clear_staging(false);
+    if (nnz_new != nnz_old)
+        h->drop_frozen();
+    if (tp)
+        tp->end(s, &StageTimes::other);
+
+    h->stats.n_inserted = n_ins;
+    h->stats.nnz_old = nnz_old;
+    h->stats.nnz_new = nnz_new;
+    h->stats.sort_passes = plan.npasses;
+    h->stats.sort_bits = h->L.sortbits();
+    h->stats.kernel_launches = h->lc.in_flush;
+    if (tp)
+    {
+        XSB_CUDA(cudaEventRecord(e1, s));
+        h->sync();
+        StageTimes t;
+        timer.collect(t);
+        cudaEventElapsedTime(&t.total, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        h->stats.ms_total = t.total;
+        h->stats.ms_expand = t.expand;
+        h->stats.ms_histogram = t.histogram;
+        h->stats.ms_sort = t.sort;
+        h->stats.ms_reduce = t.reduce;
+        h->stats.ms_colptr = t.colptr;
+        h->stats.ms_other = t.other;
+    }
+    if (nnz_out)
+        *nnz_out = nnz_new;
+    if (pattern_changed)
+        *pattern_changed = (nnz_new != nnz_old) ? 1 : 0; // the pattern only ever grows
+    return XSB_OK;
+}
+
+// room for `count` generated records in partition tid; returns where to write them
+Rec *begin_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
+{
+    check_tid_flavour(h, tid, flavour);
+    REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+    h->ensure_stage(tid, count);
+    Stage &st = h->stage[tid];
+    return st.buf + st.front + st.count;
+}
+
+void end_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
+{
+    h->stage[tid].count += count;
+    if (flavour == XSB_ASSIGN)
+        h->has_assign = true;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t xsb_version(void) { return XSB_VERSION; }
+
+int32_t xsb_device_count(int32_t *count)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        if (count)
+            *count = 0;
+        return XSB_ECUDA;
+    }
+    if (count)
+        *count = c;
+    return XSB_OK;
+}
+
+int32_t xsb_create(int64_t m, int64_t n, int32_t val_type, int32_t idx_type, int32_t index_base, int32_t n_tid,
+                   int32_t device, xsb_matrix **out)
+{
+    if (out)
+        *out = nullptr;
+    xsb_matrix *h = nullptr;
+    int32_t rc = guard(nullptr, [&]() -> int32_t {
+        REQUIRE(out != nullptr, XSB_EINVAL, "out is NULL");
+        REQUIRE(m >= 1 && n >= 1, XSB_EINVAL, "matrix dimensions must be >= 1");
+        REQUIRE(val_type == XSB_F64, XSB_EINVAL, "only Float64 values are supported");
+        REQUIRE(idx_type == XSB_I32 || idx_type == XSB_I64, XSB_EINVAL, "idx_type must be XSB_I32 or XSB_I64");
+        REQUIRE(index_base == 0 || index_base == 1, XSB_EINVAL, "index_base must be 0 or 1");
+        REQUIRE(n_tid >= 1 && n_tid <= (1 << 16), XSB_EINVAL, "n_tid must be in 1..65536");
+        if (idx_type == XSB_I32)
+            REQUIRE(m < (1ll << 31) - 1 && n < (1ll << 31) - 1, XSB_EINVAL, "dimensions exceed Int32");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+        {
+            cudaGetLastError();
+            throw ApiError(XSB_ECUDA, "no CUDA device: libxsparse_b200 has no CPU fallback");
+        }
+        REQUIRE(device >= 0 && device < ndev, XSB_EINVAL, "device ordinal out of range");
+        KeyLayout L;
+        L.tidbits = n_tid > 1 ? ceil_log2(n_tid) : 0;
+        L.low = 2 + L.tidbits;
+        L.rowbits = ceil_log2(m);
+        L.colbits = ceil_log2(n);
+        REQUIRE(L.low + L.rowbits + L.colbits <= 64, XSB_EINVAL, "m*n*n_tid does not fit the 64-bit packed key");
+        REQUIRE(L.rowbits <= 32 && L.colbits <= 32, XSB_EINVAL, "dimensions above 2^32 are not supported");
+        XSB_CUDA(cudaSetDevice(device));
+        h = new xsb_matrix();
+        h->m = m;
+        h->n = n;
+        h->idx64 = idx_type == XSB_I64;
+        h->base = index_base;
+        h->n_tid = n_tid;
+        h->device = device;
+        h->L = L;
+        h->stage.resize((size_t)n_tid);
+        XSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        XSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long thr = ~0ull; // keep freed blocks cached: flush allocates and frees large buffers
+        XSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        h->d_scal = static_cast<u64 *>(h->dalloc(sizeof(u64) * 8));
+        XSB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_scal), sizeof(u64) * 8));
+        XSB_CUDA(cudaEventCreate(&h->ev0));
+        XSB_CUDA(cudaEventCreate(&h->ev1));
+        h->set_empty_csc();
+        *out = h;
+        return XSB_OK;
+    });
+    if (rc != XSB_OK && h)
+    {
+        xsb_destroy(h);
+        if (out)
+            *out = nullptr;
+    }
+    return rc;
+}
+
+int32_t xsb_destroy(xsb_matrix *h)
+{
+    if (!h)
+        return XSB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream)
+        cudaStreamSynchronize(h->stream);
+    h->drop_frozen();
+    h->clear_staging(true);
+    h->dfree(h->colptr);
+    h->dfree(h->csc_store);
+    h->dfree(h->d_scal);
+    if (h->h_scal)
+        cudaFreeHost(h->h_scal);
+    if (h->ev0)
+        cudaEventDestroy(h->ev0);
+    if (h->ev1)
+        cudaEventDestroy(h->ev1);
+    if (h->stream)
+    {
+        cudaStreamSynchronize(h->stream);
+        cudaStreamDestroy(h->stream);
+    }
+    cudaGetLastError();
+    delete h;
+    return XSB_OK;
+}
+
+const char *xsb_last_error(const xsb_matrix *h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int32_t xsb_reset(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        h->drop_frozen();
+        h->clear_staging(false);
+        h->set_empty_csc();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_set_csc(xsb_matrix *h, const void *colptr, const void *rowval, const void *nzval)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && colptr, XSB_EINVAL, "NULL argument");
+        const size_t isz = h->isz();
+        // nnz = colptr[n] - base
+        unsigned char last[8];
+        XSB_CUDA(cudaMemcpy(last, static_cast<const unsigned char *>(colptr) + isz * (size_t)h->n, isz,
+                            cudaMemcpyDefault));
+        i64 nnz;
+        if (h->idx64)
+        {
+            int64_t v;
+            std::memcpy(&v, last, 8);
+            nnz = v - h->base;
+        }
+        else
+        {
+            int32_t v;
+            std::memcpy(&v, last, 4);
+            nnz = v - h->base;
+        }
+        REQUIRE(nnz >= 0, XSB_EINVAL, "colptr[n] is smaller than the index base");
+        REQUIRE(nnz == 0 || (rowval && nzval), XSB_EINVAL, "NULL rowval/nzval");
+        h->drop_frozen();
+        h->clear_staging(false);
+        h->dfree(h->colptr);
+        h->dfree(h->csc_store);
+        h->colptr = h->dalloc(isz * (size_t)(h->n + 1));
+        XSB_CUDA(cudaMemcpyAsync(h->colptr, colptr, isz * (size_t)(h->n + 1), cudaMemcpyDefault, h->stream));
+        const size_t rv_bytes = (isz * (size_t)nnz + 15) & ~(size_t)15;
+        unsigned char *st = static_cast<unsigned char *>(h->dalloc(rv_bytes + 8 * (size_t)nnz));
+        if (nnz)
+        {
+            XSB_CUDA(cudaMemcpyAsync(st, rowval, isz * (size_t)nnz, cudaMemcpyDefault, h->stream));
+            XSB_CUDA(cudaMemcpyAsync(st + rv_bytes, nzval, 8 * (size_t)nnz, cudaMemcpyDefault, h->stream));
+        }
+        h->csc_store = st;
+        h->csc_store_bytes = rv_bytes + 8 * (size_t)nnz;
+        h->rowval = st;
+        h->nzval = reinterpret_cast<double *>(st + rv_bytes);
+        h->nnz = nnz;
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_size(const xsb_matrix *h, int64_t *m, int64_t *n)
+{
+    if (!h)
+        return XSB_EINVAL;
+    if (m)
+        *m = h->m;
+    if (n)
+        *n = h->n;
+    return XSB_OK;
+}
+
+int32_t xsb_nnz(const xsb_matrix *h, int64_t *nnz)
+{
+    if (!h || !nnz)
+        return XSB_EINVAL;
+    *nnz = h->nnz;
+    return XSB_OK;
+}
+
+int32_t xsb_reserve(xsb_matrix *h, int32_t tid, int64_t count)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(tid >= 0 && tid < h->n_tid, XSB_EINVAL, "tid out of range");
+        REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+        h->ensure_stage(tid, count);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *J, const void *V, int64_t count,
+                         int32_t flavour)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        check_tid_flavour(h, tid, flavour);
+        REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+        if (count == 0)
+            return XSB_OK;
+        REQUIRE(I && J && V, XSB_EINVAL, "NULL array");
+        Rec *dst = begin_emit(h, tid, flavour, count);
+        DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count), dV(h, V, 8 * (size_t)count);
+        write_scalar(h, 1, ~0ull);
+        pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
+                     h->n, h->L, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc);
+        const u64 bad = read_scalar(h, 1);
+        if (bad != ~0ull)
+            throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
+                                            " of the batch is outside the matrix; batch rejected");
+        end_emit(h, tid, flavour, count);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_pending(const xsb_matrix *h, int64_t *count)
+{
+    if (!h || !count)
+        return XSB_EINVAL;
+    *count = h->pending();
+    return XSB_OK;
+}
+
+int32_t xsb_flush(xsb_matrix *h, int32_t mode, int64_t *nnz_out, int32_t *pattern_changed)
+{
+    return xsb_flush_ex(h, mode, XSB_COMBINE_SEED, nnz_out, pattern_changed);
+}
+
+int32_t xsb_flush_ex(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out, int32_t *pattern_changed)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        return do_flush(h, mode, combine, nnz_out, pattern_changed);
+    });
+}
+
+int32_t xsb_fetch_csc(xsb_matrix *h, void *colptr_out, void *rowval_out, void *nzval_out)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        if (colptr_out)
+            XSB_CUDA(cudaMemcpyAsync(colptr_out, h->colptr, h->isz() * (size_t)(h->n + 1), cudaMemcpyDefault,
+                                     h->stream));
+        if (rowval_out && h->nnz)
+            XSB_CUDA(cudaMemcpyAsync(rowval_out, h->rowval, h->isz() * (size_t)h->nnz, cudaMemcpyDefault, h->stream));
+        if (nzval_out && h->nnz)
+            XSB_CUDA(cudaMemcpyAsync(nzval_out, h->nzval, 8 * (size_t)h->nnz, cudaMemcpyDefault, h->stream));
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_get_values(xsb_matrix *h, const void *I, const void *J, void *V_out, int64_t count)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+        REQUIRE(h->pending() == 0, XSB_ESTATE, "flush! before reading entries");
+        if (count == 0)
+            return XSB_OK;
+        REQUIRE(I && J && V_out, XSB_EINVAL, "NULL array");
+        DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count);
+        DevOut dV(h, V_out, 8 * (size_t)count);
+        i64 *slot = static_cast<i64 *>(h->dalloc(8 * (size_t)count));
+        write_scalar(h, 2, 0);
+        write_scalar(h, 3, ~0ull);
+        lookup_slots(h->stream, h->view(), h->m, h->n, h->idx64, h->base, dI.ptr, dJ.ptr, count, slot, h->d_scal + 2,
+                     h->d_scal + 3, h->lc);
+        gather_values(h->stream, h->nzval, slot, count, static_cast<double *>(dV.ptr), h->lc);
+        dV.finish();
+        h->dfree(slot);
+        const u64 oob = read_scalar(h, 3);
+        REQUIRE(oob == ~0ull, XSB_EBOUNDS, "BoundsError: position " + std::to_string(oob) + " is outside the matrix");
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_zero_values(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        zero_values(h->stream, h->nzval, h->nnz, h->lc);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_freeze_pattern(xsb_matrix *h, const void *I, const void *J, int64_t count)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(count >= 0 && (u64)count < (1ull << 32), XSB_EINVAL, "count must be below 2^32");
+        REQUIRE(h->pending() == 0, XSB_ESTATE, "flush! before freezing the pattern");
+        REQUIRE(count == 0 || (I && J), XSB_EINVAL, "NULL array");
+        h->drop_frozen();
+        cudaStream_t s = h->stream;
+        DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count);
+        i64 *slot = static_cast<i64 *>(h->dalloc(8 * (size_t)count));
+        write_scalar(h, 2, 0);
+        write_scalar(h, 3, ~0ull);
+        lookup_slots(s, h->view(), h->m, h->n, h->idx64, h->base, dI.ptr, dJ.ptr, count, slot, h->d_scal + 2,
+                     h->d_scal + 3, h->lc);
+        const u64 oob = read_scalar(h, 3);
+        const u64 missing = read_scalar(h, 2);
+        if (oob != ~0ull || missing != 0)
+        {
+            h->dfree(slot);
+            if (oob != ~0ull)
+                throw ApiError(XSB_EBOUNDS, "BoundsError: position " + std::to_string(oob) + " is outside the matrix");
+            throw ApiError(XSB_EILLEGAL, std::to_string(missing) + " positions are not in the frozen pattern");
+        }
+        Rec *A = static_cast<Rec *>(h->dalloc(sizeof(Rec) * (size_t)count));
+        Rec *B = static_cast<Rec *>(h->dalloc(sizeof(Rec) * (size_t)count));
+        void *ws = h->dalloc(sort_workspace_bytes((u64)count));
+        slots_to_records(s, slot, count, A, h->lc);
+        const SortPlan plan = make_sort_plan(0, ceil_log2(std::max<i64>(h->nnz, 2)));
+        Rec *sorted = radix_sort_records(s, A, B, (u64)count, plan, ws, h->lc, nullptr);
+        h->f_perm = static_cast<u32 *>(h->dalloc(4 * (size_t)count));
+        h->f_segstart = static_cast<i64 *>(h->dalloc(8 * (size_t)(h->nnz + 1)));
+        build_frozen_map(s, sorted, count, h->nnz, h->f_perm, h->f_segstart, h->lc);
+        h->dfree(A);
+        h->dfree(B);
+        h->dfree(ws);
+        h->f_slot = slot;
+        h->f_count = count;
+        h->frozen = true;
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32_t mode)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(h->frozen, XSB_ESTATE, "no frozen pattern");
+        REQUIRE(count == h->f_count, XSB_ESIZE, "value count differs from the frozen stream");
+        REQUIRE(mode == XSB_DETERMINISTIC || mode == XSB_FAST, XSB_EINVAL, "unknown summation mode");
+        if (count == 0)
+            return XSB_OK;
+        REQUIRE(V, XSB_EINVAL, "NULL array");
+        DevIn dV(h, V, 8 * (size_t)count);
+        if (mode == XSB_DETERMINISTIC)
+            reassemble_deterministic(h->stream, static_cast<const double *>(dV.ptr), h->f_perm, h->f_segstart, h->nnz,
+                                     h->nzval, h->lc);
+        else
+            reassemble_fast(h->stream, static_cast<const double *>(dV.ptr), h->f_slot, count, h->nzval, h->lc);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_unfreeze(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        h->drop_frozen();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_mark_dirichlet(xsb_matrix *h, double penalty, uint8_t *marker_out)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && marker_out, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->m == h->n, XSB_ESIZE, "Dirichlet passes need a square matrix");
+        REQUIRE(h->pending() == 0, XSB_ESTATE, "flush! first");
+        DevOut dM(h, marker_out, (size_t)h->n);
+        mark_dirichlet(h->stream, h->view(), h->n, h->idx64, h->base, penalty, static_cast<unsigned char *>(dM.ptr),
+                       h->lc);
+        dM.finish();
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_eliminate_dirichlet(xsb_matrix *h, const uint8_t *marker)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && marker, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->m == h->n, XSB_ESIZE, "Dirichlet passes need a square matrix");
+        REQUIRE(h->pending() == 0, XSB_ESTATE, "flush! first");
+        DevIn dM(h, marker, (size_t)h->n);
+        eliminate_dirichlet(h->stream, h->view(), h->n, h->idx64, h->base, static_cast<const unsigned char *>(dM.ptr),
+                            h->lc);
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_pattern_hash(xsb_matrix *h, uint64_t *hash_out)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && hash_out, XSB_EINVAL, "NULL argument");
+        pattern_hash(h->stream, h->view(), h->n, h->idx64, h->d_scal + 4, h->lc);
+        *hash_out = read_scalar(h, 4);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_stream_count_fdrand(int64_t nx, int64_t ny, int64_t nz, int64_t *count)
+{
+    if (!count || nx < 1 || ny < 1 || nz < 1)
+        return XSB_EINVAL;
+    *count = fdrand_prefix(nx, ny, nz, nx * ny * nz);
+    return XSB_OK;
+}
+
+int32_t xsb_stream_count_p1fem(int64_t nxn, int64_t nyn, int64_t nzn, int64_t *count)
+{
+    if (!count || nxn < 2 || nyn < 2 || nzn < 2)
+        return XSB_EINVAL;
+    *count = 20 * 6 * (nxn - 1) * (nyn - 1) * (nzn - 1);
+    return XSB_OK;
+}
+
+int32_t xsb_stream_count_blockrd(int64_t nx, int64_t ny, int64_t nz, int32_t ns, int64_t *count)
+{
+    if (!count || nx < 1 || ny < 1 || nz < 1 || ns < 1)
+        return XSB_EINVAL;
+    *count = blockrd_count(nx, ny, nz, ns);
+    return XSB_OK;
+}
+
+int32_t xsb_emit_fdrand_range(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int64_t nz, uint64_t seed,
+                              int32_t ones, int32_t flavour, int64_t l_begin, int64_t l_end)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, XSB_EINVAL, "grid dimensions must be >= 1");
+        const i64 N = nx * ny * nz;
+        REQUIRE(h->m == N && h->n == N, XSB_ESIZE, "Matrix size mismatch"); // sprand.jl:66-68
+        REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= N, XSB_EINVAL, "bad node range");
+        const i64 count = fdrand_prefix(nx, ny, nz, l_end) - fdrand_prefix(nx, ny, nz, l_begin);
+        Rec *dst = begin_emit(h, tid, flavour, count);
+        emit_fdrand(h->stream, nx, ny, nz, seed, ones, h->L, (u32)tid, (u32)flavour, l_begin, l_end, dst, h->lc);
+        end_emit(h, tid, flavour, count);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_emit_fdrand(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int64_t nz, uint64_t seed, int32_t ones,
+                        int32_t flavour)
+{
+    return xsb_emit_fdrand_range(h, tid, nx, ny, nz, seed, ones, flavour, 0, nx * ny * nz);
+}
+
+int32_t xsb_emit_p1fem_range(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t nyn, int64_t nzn, int32_t flavour,
+                             int64_t cz_begin, int64_t cz_end)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(nxn >= 2 && nyn >= 2 && nzn >= 2, XSB_EINVAL, "mesh needs at least 2 nodes per direction");
+        const i64 N = nxn * nyn * nzn;
+        REQUIRE(h->m == N && h->n == N, XSB_ESIZE, "Matrix size mismatch");
+        REQUIRE(0 <= cz_begin && cz_begin <= cz_end && cz_end <= nzn - 1, XSB_EINVAL, "bad cube-layer range");
+        const i64 count = 20 * 6 * (nxn - 1) * (nyn - 1) * (cz_end - cz_begin);
+        Rec *dst = begin_emit(h, tid, flavour, count);
+        emit_p1fem(h->stream, nxn, nyn, nzn, h->L, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc);
+        end_emit(h, tid, flavour, count);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_emit_p1fem(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t nyn, int64_t nzn, int32_t flavour)
+{
+    return xsb_emit_p1fem_range(h, tid, nxn, nyn, nzn, flavour, 0, nzn - 1);
+}
+
+int32_t xsb_emit_blockrd(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int64_t nz, int32_t ns, uint64_t seed,
+                         int32_t flavour)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && ns >= 1 && ns <= 16, XSB_EINVAL, "bad grid or species count");
+        const i64 N = nx * ny * nz * ns;
+        REQUIRE(h->m == N && h->n == N, XSB_ESIZE, "Matrix size mismatch");
+        const i64 count = blockrd_count(nx, ny, nz, ns);
+        Rec *dst = begin_emit(h, tid, flavour, count);
+        emit_blockrd(h->stream, nx, ny, nz, ns, seed, h->L, (u32)tid, (u32)flavour, dst, h->lc);
+        end_emit(h, tid, flavour, count);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_debug_fetch_staged(xsb_matrix *h, int32_t tid, void *I, void *J, void *V, int32_t *flavour,
+                               int64_t capacity, int64_t *count)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && count, XSB_EINVAL, "NULL argument");
+        REQUIRE(tid >= 0 && tid < h->n_tid, XSB_EINVAL, "tid out of range");
+        const Stage &st = h->stage[tid];
+        *count = st.count;
+        if (!I || !J || !V)
+            return XSB_OK;
+        REQUIRE(capacity >= st.count, XSB_EINVAL, "capacity too small");
+        if (st.count == 0)
+            return XSB_OK;
+        const size_t c = (size_t)st.count;
+        DevOut dI(h, I, h->isz() * c), dJ(h, J, h->isz() * c), dV(h, V, 8 * c), dF(h, flavour, 4 * c);
+        unpack_records(h->stream, st.buf + st.front, st.count, h->idx64, h->base, h->L, dI.ptr, dJ.ptr,
+                       static_cast<double *>(dV.ptr), static_cast<int *>(dF.ptr), h->lc);
+        dI.finish();
+        dJ.finish();
+        dV.finish();
+        dF.finish();
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_synchronize(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_get_stream(xsb_matrix *h, void **stream_out)
+{
+    if (!h || !stream_out)
+        return XSB_EINVAL;
+    *stream_out = h->stream;
+    return XSB_OK;
+}
+
+int32_t xsb_timer_start(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        XSB_CUDA(cudaEventRecord(h->ev0, h->stream));
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_timer_stop(xsb_matrix *h, float *ms_out)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && ms_out, XSB_EINVAL, "NULL argument");
+        XSB_CUDA(cudaEventRecord(h->ev1, h->stream));
+        XSB_CUDA(cudaEventSynchronize(h->ev1));
+        XSB_CUDA(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_set_profiling(xsb_matrix *h, int32_t enable)
+{
+    if (!h)
+        return XSB_EINVAL;
+    h->profiling = enable != 0;
+    return XSB_OK;
+}
+
+int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out)
+{
+    if (!h || !out)
+        return XSB_EINVAL;
+    *out = h->stats;
+    return XSB_OK;
+}
+
+int32_t xsb_kernel_launches(const xsb_matrix *h, int64_t *count)
+{
+    if (!h || !count)
+        return XSB_EINVAL;
+    *count = h->lc.total;
+    return XSB_OK;
+}
+
+} // extern "C"

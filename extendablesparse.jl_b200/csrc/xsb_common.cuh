@@ -1,0 +1,119 @@
+// xsb_common.cuh -- shared device/host definitions of libxsparse_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace xsb {
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+
+// One staged insertion: packed key + Float64 value = one 16-byte vector load/store.
+//
+// key bits, low to high:  [flavour:2][tid:tidbits][row:rowbits][col:colbits]
+// The radix sort covers only [low, low+rowbits+colbits): flavour and tid ride
+// along unsorted, so a STABLE sort keeps the insertion order inside a run of
+// equal (col,row) -- which is what the deterministic left fold needs.
+struct __align__(16) Rec
+{
+    u64 key;
+    double val;
+};
+
+enum : u32
+{
+    FL_UPDATE = 0,
+    FL_RAW = 1,
+    FL_ASSIGN = 2,
+    FL_OLD = 3 // entry of the resident CSC, placed ahead of all staged entries
+};
+
+struct KeyLayout
+{
+    int low;     // 2 + tidbits
+    int tidbits; // bits of the partition id
+    int rowbits;
+    int colbits;
+    __host__ __device__ __forceinline__ u64 pack(u64 col, u64 row, u32 tid, u32 fl) const
+    {
+        return (col << (rowbits + low)) | (row << low) | ((u64)tid << 2) | (u64)fl;
+    }
+    __host__ __device__ __forceinline__ u64 colrow(u64 key) const { return key >> low; }
+    __host__ __device__ __forceinline__ u64 col(u64 key) const { return key >> (rowbits + low); }
+    __host__ __device__ __forceinline__ u64 row(u64 key) const
+    {
+        return (key >> low) & ((1ull << rowbits) - 1ull);
+    }
+    __host__ __device__ __forceinline__ u32 tid(u64 key) const
+    {
+        return (u32)((key >> 2) & ((1ull << tidbits) - 1ull));
+    }
+    __host__ __device__ __forceinline__ u32 flavour(u64 key) const { return (u32)(key & 3ull); }
+    __host__ __device__ int sortbits() const { return rowbits + colbits; }
+};
+
+struct CudaError : std::runtime_error
+{
+    cudaError_t code;
+    CudaError(cudaError_t c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+
+#define XSB_CUDA(expr)                                                                             \
+    do                                                                                             \
+    {                                                                                              \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            throw ::xsb::CudaError(_e, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+// number of SMs of a B200; grids are sized as multiples of it
+constexpr int kNumSM = 148;
+
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// streaming 16-byte record load / store (data touched once: keep it out of L1)
+__device__ __forceinline__ Rec ld_rec_stream(const Rec *p)
+{
+    Rec r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(r.key), "=l"(*reinterpret_cast<u64 *>(&r.val))
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_rec(Rec *p, const Rec &r)
+{
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(r.key),
+                 "l"(*reinterpret_cast<const u64 *>(&r.val))
+                 : "memory");
+}
+
+} // namespace xsb

@@ -1,0 +1,461 @@
+// xsb_insert.cu -- producers of staged records:
+//   pack_records   : caller (I,J,V) arrays -> 16-byte records, bounds-checked on device
+//   emit_fdrand    : fdrand! call stream           (reference: src/matrix/sprand.jl:58-126)
+//   emit_p1fem     : testassemble! call stream     (reference: test/femtools.jl:45-72)
+//   emit_blockrd   : block reaction-diffusion stream (SURVEY.md 8d cfg 4, build-defined)
+// The emitters batch whole elements/nodes per thread block, stage their records in
+// shared memory and write them out as coalesced 16-byte vector stores, in exactly the
+// order the reference's sequential loop would issue the insert calls.
+//
+// Compiled with -fmad=false: the element arithmetic must round like the CPU oracle's.
+#include "xsb_internal.h"
+
+namespace xsb {
+
+// ------------------------------------------------------------------------
+// pack / unpack
+// ------------------------------------------------------------------------
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+pack_kernel(const Ti *__restrict__ I, const Ti *__restrict__ J, const double *__restrict__ V, i64 count, Ti base,
+            i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out, u64 *__restrict__ d_err)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const i64 i = (i64)I[k] - base, j = (i64)J[k] - base;
+        if (i < 0 || i >= m || j < 0 || j >= n)
+        { // BoundsError: sparsematrixcsc.jl:8-10
+            atomicMin(d_err, (u64)k);
+            continue;
+        }
+        Rec r;
+        r.key = L.pack((u64)j, (u64)i, tid, flavour);
+        r.val = V[k];
+        st_rec(out + k, r);
+    }
+}
+
+void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
+                  int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
+                  LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    const int threads = 256;
+    const int blocks = (int)std::min<i64>((count + threads - 1) / threads, (i64)kNumSM * 16);
+    if (idx64)
+        pack_kernel<int64_t><<<blocks, threads, 0, stream>>>((const int64_t *)I, (const int64_t *)J, V, count,
+                                                             (int64_t)base, m, n, L, tid, flavour, out, d_err);
+    else
+        pack_kernel<int32_t><<<blocks, threads, 0, stream>>>((const int32_t *)I, (const int32_t *)J, V, count,
+                                                             (int32_t)base, m, n, L, tid, flavour, out, d_err);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+unpack_kernel(const Rec *__restrict__ in, i64 count, Ti base, KeyLayout L, Ti *__restrict__ I, Ti *__restrict__ J,
+              double *__restrict__ V, int *__restrict__ flavour)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const Rec r = in[k];
+        I[k] = (Ti)L.row(r.key) + base;
+        J[k] = (Ti)L.col(r.key) + base;
+        V[k] = r.val;
+        if (flavour)
+            flavour[k] = (int)L.flavour(r.key);
+    }
+}
+
+void unpack_records(cudaStream_t stream, const Rec *in, i64 count, int idx64, int base, KeyLayout L, void *I,
+                    void *J, double *V, int *flavour, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    const int threads = 256;
+    const int blocks = (int)std::min<i64>((count + threads - 1) / threads, (i64)kNumSM * 16);
+    if (idx64)
+        unpack_kernel<int64_t><<<blocks, threads, 0, stream>>>(in, count, (int64_t)base, L, (int64_t *)I,
+                                                               (int64_t *)J, V, flavour);
+    else
+        unpack_kernel<int32_t><<<blocks, threads, 0, stream>>>(in, count, (int32_t)base, L, (int32_t *)I,
+                                                               (int32_t *)J, V, flavour);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------
+// counter-based random numbers: Philox4x32-10, u = (w1:w0 >> 11) * 2^-53
+// ------------------------------------------------------------------------
+__host__ __device__ __forceinline__ double philox_uniform(u64 seed, u64 counter)
+{
+    u32 c0 = (u32)counter, c1 = (u32)(counter >> 32), c2 = 0u, c3 = 0u;
+    u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+    {
+        const u64 p0 = (u64)0xD2511F53u * c0;
+        const u64 p1 = (u64)0xCD9E8D57u * c2;
+        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0;
+        const u32 n1 = (u32)p1;
+        const u32 n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
+        const u32 n3 = (u32)p0;
+        c0 = n0;
+        c1 = n1;
+        c2 = n2;
+        c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const u64 bits = ((u64)c1 << 32) | (u64)c0;
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------
+// fdrand! stream.  Per node (i,j,k), in this order (sprand.jl:100-124):
+//   x-edge pair (4 records, if i<nx), x-boundary (1, if i==1||i==nx),
+//   y-edge pair (if j<ny), y-boundary (if ny>2 && (j==1||j==ny)),
+//   z-edge pair (if k<nz), z-boundary (if nz>2 && (k==1||k==nz)).
+// Record and rand() counts before a node have a closed form, so every node
+// can be emitted independently at its exact stream position.
+// ------------------------------------------------------------------------
+struct FdGeom
+{
+    i64 nx, ny, nz;
+    __host__ __device__ i64 bx(i64 i) const { return (i == 1 || i == nx) ? 1 : 0; }
+    __host__ __device__ i64 by(i64 j) const { return (ny > 2 && (j == 1 || j == ny)) ? 1 : 0; }
+    __host__ __device__ i64 bz(i64 k) const { return (nz > 2 && (k == 1 || k == nz)) ? 1 : 0; }
+    // number of boundary hits / edges among indices 1..i-1
+    __host__ __device__ i64 pbx(i64 i) const { return (i > 1 ? 1 : 0) + ((nx > 1 && i > nx) ? 1 : 0); }
+    __host__ __device__ i64 pby(i64 j) const
+    {
+        return ny > 2 ? (j > 1 ? 1 : 0) + (j > ny ? 1 : 0) : 0;
+    }
+    __host__ __device__ i64 pbz(i64 k) const
+    {
+        return nz > 2 ? (k > 1 ? 1 : 0) + (k > nz ? 1 : 0) : 0;
+    }
+    __host__ __device__ static i64 pe(i64 i, i64 n) { return (i - 1) < (n - 1) ? (i - 1) : (n - 1); } // edges among 1..i-1
+
+    // W = 4 for records, 1 for rand() calls (an edge pair is 4 records but one rand())
+    template <int W> __host__ __device__ i64 cx(i64 i) const { return (i < nx ? W : 0) + bx(i); }
+    template <int W> __host__ __device__ i64 cy(i64 j) const { return (j < ny ? W : 0) + by(j); }
+    template <int W> __host__ __device__ i64 cz(i64 k) const { return (k < nz ? W : 0) + bz(k); }
+    template <int W> __host__ __device__ i64 PX(i64 i) const { return W * pe(i, nx) + pbx(i); }
+    template <int W> __host__ __device__ i64 PY(i64 j) const { return W * pe(j, ny) + pby(j); }
+    template <int W> __host__ __device__ i64 PZ(i64 k) const { return W * pe(k, nz) + pbz(k); }
+    // count over all nodes that precede (i,j,k) in the sweep (x fastest)
+    template <int W> __host__ __device__ i64 before(i64 i, i64 j, i64 k) const
+    {
+        const i64 RX = PX<W>(nx + 1), RY = PY<W>(ny + 1);
+        i64 s = (k - 1) * (ny * RX + nx * RY) + nx * ny * PZ<W>(k);
+        s += (j - 1) * RX + nx * PY<W>(j) + (j - 1) * nx * cz<W>(k);
+        s += PX<W>(i) + (i - 1) * (cy<W>(j) + cz<W>(k));
+        return s;
+    }
+    template <int W> __host__ __device__ i64 before_node(i64 l0) const
+    { // l0 = 0-based node index; l0 == nx*ny*nz gives the stream total
+        if (l0 >= nx * ny * nz)
+            return before<W>(1, 1, nz + 1);
+        const i64 i = l0 % nx + 1, j = (l0 / nx) % ny + 1, k = l0 / (nx * ny) + 1;
+        return before<W>(i, j, k);
+    }
+};
+
+i64 fdrand_prefix(i64 nx, i64 ny, i64 nz, i64 l)
+{
+    FdGeom g{nx, ny, nz};
+    return g.before_node<4>(l);
+}
+
+constexpr int FD_THREADS = 128; // nodes per block
+constexpr int FD_MAXREC = 15;   // records per node upper bound
+
+__global__ void __launch_bounds__(FD_THREADS)
+emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour, i64 l_begin, i64 l_end,
+                   i64 rec_begin, Rec *__restrict__ out)
+{
+    __shared__ Rec s_rec[FD_THREADS * FD_MAXREC];
+    const i64 l_first = l_begin + (i64)blockIdx.x * FD_THREADS;
+    const i64 l_last = min(l_first + FD_THREADS, l_end);
+    const i64 blk_rec0 = g.before_node<4>(l_first);
+    const i64 blk_rec1 = g.before_node<4>(l_last);
+    const i64 l0 = l_first + threadIdx.x;
+    if (l0 < l_last)
+    {
+        const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+        i64 pos = g.before<4>(i, j, k) - blk_rec0;
+        u64 call = (u64)g.before<1>(i, j, k);
+        const double hx = 1.0 / (double)g.nx, hy = 1.0 / (double)g.ny, hz = 1.0 / (double)g.nz;
+        const u64 l = (u64)l0; // 0-based unknown
+        auto rnd = [&]() -> double {
+            const double u = ones ? 1.0 : philox_uniform(seed, call);
+            ++call;
+            return u;
+        };
+        auto put = [&](double v, u64 row, u64 col) {
+            Rec r;
+            r.key = L.pack(col, row, tid, flavour);
+            r.val = v;
+            s_rec[pos++] = r;
+        };
+        auto pair = [&](double v, u64 a, u64 b) { // update_pair, sprand.jl:87-92
+            put(-v, a, b);
+            put(-v, b, a);
+            put(v, a, a);
+            put(v, b, b);
+        };
+        if (i < g.nx)
+            pair(rnd() * hy * hz / hx, l, l + 1);
+        if (i == 1 || i == g.nx)
+            put(rnd() * hy * hz, l, l);
+        if (j < g.ny)
+            pair(rnd() * hx * hz / hy, l, l + (u64)g.nx);
+        if (g.ny > 2 && (j == 1 || j == g.ny))
+            put(rnd() * hx * hz, l, l);
+        if (k < g.nz)
+            pair(rnd() * hx * hy / hz, l, l + (u64)(g.nx * g.ny));
+        if (g.nz > 2 && (k == 1 || k == g.nz))
+            put(rnd() * hx * hy, l, l);
+    }
+    __syncthreads();
+    const i64 nrec = blk_rec1 - blk_rec0;
+    Rec *dst = out + (blk_rec0 - rec_begin);
+    for (i64 q = threadIdx.x; q < nrec; q += FD_THREADS)
+        st_rec(dst + q, s_rec[q]);
+}
+
+void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid,
+                 u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc)
+{
+    if (l_end <= l_begin)
+        return;
+    FdGeom g{nx, ny, nz};
+    const i64 blocks = (l_end - l_begin + FD_THREADS - 1) / FD_THREADS;
+    emit_fdrand_kernel<<<(unsigned)blocks, FD_THREADS, 0, stream>>>(g, seed, ones, L, tid, flavour, l_begin, l_end,
+                                                                    g.before_node<4>(l_begin), out);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------
+// P1 FEM stream on the Kuhn tensor mesh: 20 rawupdateindex! calls per tetrahedron
+// (test/femtools.jl:62-69).  One thread per tetrahedron, 128 tetrahedra per block.
+// ------------------------------------------------------------------------
+__constant__ int c_kuhn[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+
+constexpr int FEM_THREADS = 128;
+constexpr int FEM_REC = 20;
+
+__global__ void __launch_bounds__(FEM_THREADS)
+emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
+                  Rec *__restrict__ out)
+{
+    __shared__ Rec s_rec[FEM_THREADS * FEM_REC];
+    const i64 t_first = tet_begin + (i64)blockIdx.x * FEM_THREADS;
+    const i64 t_last = min(t_first + FEM_THREADS, tet_end);
+    const i64 t = t_first + threadIdx.x;
+    if (t < t_last)
+    {
+        const i64 cube = t / 6;
+        const int perm = (int)(t % 6);
+        const i64 cxn = nxn - 1, cyn = nyn - 1;
+        i64 idx[4][3];
+        idx[0][0] = cube % cxn;
+        idx[0][1] = (cube / cxn) % cyn;
+        idx[0][2] = cube / (cxn * cyn);
+#pragma unroll
+        for (int v = 1; v < 4; ++v)
+        {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                idx[v][d] = idx[v - 1][d] + (c_kuhn[perm][v - 1] == d ? 1 : 0);
+        }
+        const double dx = (double)(nxn - 1), dy = (double)(nyn - 1), dz = (double)(nzn - 1);
+        double p[4][3];
+        u64 node[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+        {
+            p[v][0] = (double)idx[v][0] / dx;
+            p[v][1] = (double)idx[v][1] / dy;
+            p[v][2] = (double)idx[v][2] / dz;
+            node[v] = (u64)(idx[v][0] + nxn * idx[v][1] + nxn * nyn * idx[v][2]);
+        }
+        // P1 gradients from the inverse edge matrix; operation order mirrors the CPU oracle
+        double a[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                a[r][c] = p[c + 1][r] - p[0][r];
+        const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+        const double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+        const double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+        const double c10 = a[0][2] * a[2][1] - a[0][1] * a[2][2];
+        const double c11 = a[0][0] * a[2][2] - a[0][2] * a[2][0];
+        const double c12 = a[0][1] * a[2][0] - a[0][0] * a[2][1];
+        const double c20 = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+        const double c21 = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+        const double c22 = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+        const double det = (a[0][0] * c00 + a[0][1] * c01) + a[0][2] * c02;
+        double gr[4][3];
+        gr[1][0] = c00 / det;
+        gr[1][1] = c10 / det;
+        gr[1][2] = c20 / det;
+        gr[2][0] = c01 / det;
+        gr[2][1] = c11 / det;
+        gr[2][2] = c21 / det;
+        gr[3][0] = c02 / det;
+        gr[3][1] = c12 / det;
+        gr[3][2] = c22 / det;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            gr[0][d] = -((gr[1][d] + gr[2][d]) + gr[3][d]);
+        const double vol = fabs(det) / 6.0;
+        double S[4][4];
+#pragma unroll
+        for (int il = 0; il < 4; ++il)
+#pragma unroll
+            for (int jl = il; jl < 4; ++jl)
+            {
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    s += gr[jl][d] * gr[il][d];
+                S[il][jl] = s;
+                S[jl][il] = s;
+            }
+        Rec *dst = s_rec + threadIdx.x * FEM_REC;
+        int q = 0;
+#pragma unroll
+        for (int il = 0; il < 4; ++il)
+        {
+            Rec r;
+            r.key = L.pack(node[il], node[il], tid, flavour);
+            r.val = 0.1 * vol / 4.0;
+            dst[q++] = r;
+#pragma unroll
+            for (int jl = 0; jl < 4; ++jl)
+            {
+                r.key = L.pack(node[jl], node[il], tid, flavour); // A[i,j]: row = node[il], col = node[jl]
+                r.val = vol * S[il][jl];
+                dst[q++] = r;
+            }
+        }
+    }
+    __syncthreads();
+    const i64 nrec = (t_last - t_first) * FEM_REC;
+    Rec *dst = out + (t_first - tet_begin) * FEM_REC;
+    for (i64 q = threadIdx.x; q < nrec; q += FEM_THREADS)
+        st_rec(dst + q, s_rec[q]);
+}
+
+void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc)
+{
+    const i64 per_layer = 6 * (nxn - 1) * (nyn - 1);
+    const i64 tet_begin = cz_begin * per_layer, tet_end = cz_end * per_layer;
+    if (tet_end <= tet_begin)
+        return;
+    const i64 blocks = (tet_end - tet_begin + FEM_THREADS - 1) / FEM_THREADS;
+    emit_p1fem_kernel<<<(unsigned)blocks, FEM_THREADS, 0, stream>>>(nxn, nyn, nzn, L, tid, flavour, tet_begin,
+                                                                    tet_end, out);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------
+// block reaction-diffusion stream: per node, per outgoing edge a dense ns x ns
+// block applied as update_pair per block entry, then an ns x ns reaction block.
+// One thread per (node, block entry): it writes 4 consecutive records per edge.
+// ------------------------------------------------------------------------
+struct RdGeom
+{
+    i64 nx, ny, nz, ns;
+    __host__ __device__ i64 edges_before(i64 i, i64 j, i64 k) const
+    { // edges leaving the nodes that precede (i,j,k)
+        const i64 ex_row = nx - 1;
+        auto ey = [&](i64 jj) { return jj < ny ? 1 : 0; };
+        auto ez = [&](i64 kk) { return kk < nz ? 1 : 0; };
+        const i64 pey = (j - 1) < (ny - 1) ? (j - 1) : (ny - 1);
+        const i64 pez = (k - 1) < (nz - 1) ? (k - 1) : (nz - 1);
+        const i64 pex = (i - 1) < (nx - 1) ? (i - 1) : (nx - 1);
+        i64 s = (k - 1) * (ny * ex_row + nx * (ny - 1)) + nx * ny * pez;
+        s += (j - 1) * ex_row + nx * pey + (j - 1) * nx * ez(k);
+        s += pex + (i - 1) * (ey(j) + ez(k));
+        return s;
+    }
+};
+
+i64 blockrd_count(i64 nx, i64 ny, i64 nz, i64 ns)
+{
+    const i64 edges = (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1);
+    return edges * 4 * ns * ns + nx * ny * nz * ns * ns;
+}
+
+__global__ void __launch_bounds__(256)
+emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out)
+{
+    const i64 ns2 = g.ns * g.ns;
+    const i64 total = g.nx * g.ny * g.nz * ns2;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride)
+    {
+        const i64 l0 = w / ns2;
+        const i64 ab = w % ns2;
+        const u64 a = (u64)(ab / g.ns), b = (u64)(ab % g.ns);
+        const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+        const i64 eb = g.edges_before(i, j, k);
+        i64 rec = eb * 4 * ns2 + l0 * ns2;      // records before this node
+        u64 call = (u64)(eb * ns2 + l0 * ns2);  // rand() calls before this node
+        const i64 step[3] = {1, g.nx, g.nx * g.ny};
+        const bool has[3] = {i < g.nx, j < g.ny, k < g.nz};
+        const u64 ia = (u64)(g.ns * l0) + a, ib = (u64)(g.ns * l0) + b;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            if (!has[d])
+                continue;
+            const double v = philox_uniform(seed, call + (u64)ab);
+            const u64 l2 = (u64)(l0 + step[d]);
+            const u64 ja = (u64)g.ns * l2 + a, jb = (u64)g.ns * l2 + b;
+            Rec *dst = out + rec + ab * 4;
+            Rec r;
+            r.val = -v;
+            r.key = L.pack(jb, ia, tid, flavour); // (-v, i_a, j_b)
+            st_rec(dst + 0, r);
+            r.key = L.pack(ib, ja, tid, flavour); // (-v, j_a, i_b)
+            st_rec(dst + 1, r);
+            r.val = v;
+            r.key = L.pack(ib, ia, tid, flavour); // ( v, i_a, i_b)
+            st_rec(dst + 2, r);
+            r.key = L.pack(jb, ja, tid, flavour); // ( v, j_a, j_b)
+            st_rec(dst + 3, r);
+            rec += 4 * ns2;
+            call += (u64)ns2;
+        }
+        Rec r;
+        r.val = philox_uniform(seed, call + (u64)ab);
+        r.key = L.pack(ib, ia, tid, flavour);
+        st_rec(out + rec + ab, r);
+    }
+}
+
+void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,
+                  u32 flavour, Rec *out, LaunchCounter &lc)
+{
+    RdGeom g{nx, ny, nz, (i64)ns};
+    const i64 total = nx * ny * nz * ns * ns;
+    const int threads = 256;
+    const int blocks = (int)std::min<i64>((total + threads - 1) / threads, (i64)kNumSM * 32);
+    emit_blockrd_kernel<<<blocks, threads, 0, stream>>>(g, seed, L, tid, flavour, out);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+} // namespace xsb

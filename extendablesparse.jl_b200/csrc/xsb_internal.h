@@ -1,0 +1,134 @@
+// xsb_internal.h -- host-side declarations shared by the translation units of libxsparse_b200.
+#pragma once
+#include "xsb_common.cuh"
+#include <algorithm>
+#include <cstddef>
+#include <vector>
+
+namespace xsb {
+
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 8;
+
+struct SortPlan
+{
+    int npasses;
+    int shift[kMaxPasses];
+    int bits[kMaxPasses];
+};
+
+struct LaunchCounter
+{
+    long long total = 0;
+    int in_flush = 0;
+    void add(int k = 1)
+    {
+        total += k;
+        in_flush += k;
+    }
+};
+
+struct StageTimes
+{
+    float expand = 0, histogram = 0, sort = 0, reduce = 0, colptr = 0, other = 0, total = 0;
+};
+
+// Optional CUDA-event bracket around pipeline stages (profiling mode only).
+struct StageTimer
+{
+    struct Span
+    {
+        cudaEvent_t a, b;
+        float StageTimes::*slot;
+    };
+    std::vector<Span> spans;
+    cudaEvent_t cur = nullptr;
+    void begin(cudaStream_t s)
+    {
+        XSB_CUDA(cudaEventCreate(&cur));
+        XSB_CUDA(cudaEventRecord(cur, s));
+    }
+    void end(cudaStream_t s, float StageTimes::*slot)
+    {
+        cudaEvent_t b;
+        XSB_CUDA(cudaEventCreate(&b));
+        XSB_CUDA(cudaEventRecord(b, s));
+        spans.push_back({cur, b, slot});
+        cur = nullptr;
+    }
+    // call after the stream has been synchronised
+    void collect(StageTimes &t)
+    {
+        for (auto &sp : spans)
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, sp.a, sp.b);
+            t.*(sp.slot) += ms;
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        spans.clear();
+    }
+};
+
+// ---- xsb_sort.cu
+SortPlan make_sort_plan(int begin_bit, int nbits);
+size_t sort_workspace_bytes(u64 n);
+Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPlan &plan, void *workspace,
+                        LaunchCounter &lc, StageTimer *timer);
+
+// ---- xsb_flush.cu
+struct CscView
+{
+    void *colptr; // Ti[n+1]
+    void *rowval; // Ti[nnz]
+    double *nzval;
+    i64 nnz;
+};
+// old CSC -> FL_OLD records at out[0..nnz)
+void expand_csc_records(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, KeyLayout L,
+                        Rec *out, LaunchCounter &lc);
+size_t reduce_workspace_bytes(u64 nrec, i64 ncols);
+// sorted records -> rowval/nzval (compacted, user index type/base) + colptr; returns nnz via *d_nnz (device)
+void reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine, int mode,
+                     bool plain_adds, i64 ncols, int idx64, int base, void *rowval_out, double *nzval_out,
+                     void *colptr_out, void *workspace, u64 *d_nnz, LaunchCounter &lc, StageTimer *timer);
+
+// ---- xsb_insert.cu
+// (I,J,V) -> records; *d_err receives the smallest offending index (or ~0)
+void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
+                  int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
+                  LaunchCounter &lc);
+void unpack_records(cudaStream_t stream, const Rec *in, i64 count, int idx64, int base, KeyLayout L, void *I,
+                    void *J, double *V, int *flavour, LaunchCounter &lc);
+i64 fdrand_prefix(i64 nx, i64 ny, i64 nz, i64 l); // records emitted by nodes [0,l)
+void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid,
+                 u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc);
+void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc);
+i64 blockrd_count(i64 nx, i64 ny, i64 nz, i64 ns);
+void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,
+                  u32 flavour, Rec *out, LaunchCounter &lc);
+
+// ---- xsb_values.cu
+void zero_values(cudaStream_t stream, double *nzval, i64 nnz, LaunchCounter &lc);
+void fill_index(cudaStream_t stream, void *x, i64 count, int idx64, i64 value, LaunchCounter &lc);
+// slot[k] = nz index of (I[k],J[k]) or -1; *d_missing counts the absent ones
+void lookup_slots(cudaStream_t stream, const CscView &csc, i64 m, i64 n, int idx64, int base, const void *I,
+                  const void *J, i64 count, i64 *slot, u64 *d_missing, u64 *d_oob, LaunchCounter &lc);
+void gather_values(cudaStream_t stream, const double *nzval, const i64 *slot, i64 count, double *out,
+                   LaunchCounter &lc);
+void slots_to_records(cudaStream_t stream, const i64 *slot, i64 count, Rec *out, LaunchCounter &lc);
+void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, i64 *segstart,
+                      LaunchCounter &lc);
+void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *perm, const i64 *segstart,
+                              i64 nnz, double *nzval, LaunchCounter &lc);
+void reassemble_fast(cudaStream_t stream, const double *V, const i64 *slot, i64 count, double *nzval,
+                     LaunchCounter &lc);
+void mark_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, double penalty,
+                    unsigned char *marker, LaunchCounter &lc);
+void eliminate_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base,
+                         const unsigned char *marker, LaunchCounter &lc);
+void pattern_hash(cudaStream_t stream, const CscView &csc, i64 n, int idx64, u64 *d_hash, LaunchCounter &lc);
+
+} // namespace xsb

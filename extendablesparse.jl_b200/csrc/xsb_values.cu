@@ -1,0 +1,354 @@
+// xsb_values.cu -- values-only work on the resident CSC:
+//   lookup_slots / gather_values : findindex + getindex    (src/matrix/sparsematrixcsc.jl:7-23,
+//                                                           src/matrix/extendable.jl:226-238)
+//   frozen-pattern re-assembly   : the CSC-hit branch of updateindex! (extendable.jl:164-166)
+//                                  resolved once into an entry->nzval map
+//   Dirichlet passes             : mark_dirichlet / eliminate_dirichlet! (sparsematrixcsc.jl:97-148)
+//   pattern fingerprint          : stands in for phash (sparsematrixcsc.jl:74)
+#include "xsb_internal.h"
+
+namespace xsb {
+
+__global__ void __launch_bounds__(256) zero_kernel(double *__restrict__ x, i64 n)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        x[k] = 0.0;
+}
+
+static inline int grid_for(i64 n, int threads, int waves = 16)
+{
+    return (int)std::min<i64>(std::max<i64>((n + threads - 1) / threads, 1), (i64)kNumSM * waves);
+}
+
+template <typename Ti> __global__ void __launch_bounds__(256) fill_index_kernel(Ti *__restrict__ x, i64 n, Ti v)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        x[k] = v;
+}
+
+void fill_index(cudaStream_t stream, void *x, i64 count, int idx64, i64 value, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    if (idx64)
+        fill_index_kernel<int64_t><<<grid_for(count, 256), 256, 0, stream>>>((int64_t *)x, count, (int64_t)value);
+    else
+        fill_index_kernel<int32_t><<<grid_for(count, 256), 256, 0, stream>>>((int32_t *)x, count, (int32_t)value);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+void zero_values(cudaStream_t stream, double *nzval, i64 nnz, LaunchCounter &lc)
+{
+    if (nnz <= 0)
+        return;
+    zero_kernel<<<grid_for(nnz, 256), 256, 0, stream>>>(nzval, nnz);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// searchsortedfirst over one CSC column, sparsematrixcsc.jl:11-22
+template <typename Ti>
+__device__ __forceinline__ i64 find_slot(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval, Ti base,
+                                         i64 i, i64 j)
+{
+    i64 lo = (i64)colptr[j] - base, hi = (i64)colptr[j + 1] - base;
+    const i64 end = hi;
+    const Ti want = (Ti)i + base;
+    while (lo < hi)
+    {
+        const i64 mid = lo + ((hi - lo) >> 1);
+        if (rowval[mid] < want)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (lo < end && rowval[lo] == want) ? lo : -1;
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+lookup_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval, Ti base, i64 m, i64 n,
+              const Ti *__restrict__ I, const Ti *__restrict__ J, i64 count, i64 *__restrict__ slot,
+              u64 *__restrict__ d_missing, u64 *__restrict__ d_oob)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const i64 i = (i64)I[k] - base, j = (i64)J[k] - base;
+        i64 s = -1;
+        if (i < 0 || i >= m || j < 0 || j >= n)
+            atomicMin(d_oob, (u64)k);
+        else
+        {
+            s = find_slot<Ti>(colptr, rowval, base, i, j);
+            if (s < 0)
+                atomicAdd(d_missing, 1ull);
+        }
+        slot[k] = s;
+    }
+}
+
+void lookup_slots(cudaStream_t stream, const CscView &csc, i64 m, i64 n, int idx64, int base, const void *I,
+                  const void *J, i64 count, i64 *slot, u64 *d_missing, u64 *d_oob, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    const int blocks = grid_for(count, 256);
+    if (idx64)
+        lookup_kernel<int64_t><<<blocks, 256, 0, stream>>>((const int64_t *)csc.colptr, (const int64_t *)csc.rowval,
+                                                           (int64_t)base, m, n, (const int64_t *)I,
+                                                           (const int64_t *)J, count, slot, d_missing, d_oob);
+    else
+        lookup_kernel<int32_t><<<blocks, 256, 0, stream>>>((const int32_t *)csc.colptr, (const int32_t *)csc.rowval,
+                                                           (int32_t)base, m, n, (const int32_t *)I,
+                                                           (const int32_t *)J, count, slot, d_missing, d_oob);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const double *__restrict__ nzval, const i64 *__restrict__ slot, i64 count, double *__restrict__ out)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const i64 s = slot[k];
+        out[k] = s >= 0 ? nzval[s] : 0.0;
+    }
+}
+
+void gather_values(cudaStream_t stream, const double *nzval, const i64 *slot, i64 count, double *out,
+                   LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    gather_kernel<<<grid_for(count, 256), 256, 0, stream>>>(nzval, slot, count, out);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// ---- frozen pattern: sort (slot, stream index) pairs by slot (stable) ----
+__global__ void __launch_bounds__(256)
+slots_to_records_kernel(const i64 *__restrict__ slot, i64 count, Rec *__restrict__ out)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        Rec r;
+        r.key = (u64)slot[k];
+        *reinterpret_cast<u64 *>(&r.val) = (u64)k;
+        st_rec(out + k, r);
+    }
+}
+
+void slots_to_records(cudaStream_t stream, const i64 *slot, i64 count, Rec *out, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    slots_to_records_kernel<<<grid_for(count, 256), 256, 0, stream>>>(slot, count, out);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// sorted (slot,index) records -> perm[] and segstart[0..nnz]
+__global__ void __launch_bounds__(256)
+frozen_map_kernel(const Rec *__restrict__ sorted, i64 count, i64 nnz, u32 *__restrict__ perm,
+                  i64 *__restrict__ segstart)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride)
+    {
+        const Rec r = sorted[s];
+        perm[s] = (u32) * reinterpret_cast<const u64 *>(&r.val);
+        const i64 z = (i64)r.key;
+        const i64 zprev = s > 0 ? (i64)sorted[s - 1].key : -1;
+        // slots zprev+1 .. z start at s (slots without entries get an empty range)
+        for (i64 q = zprev + 1; q <= z; ++q)
+            segstart[q] = s;
+        if (s == count - 1)
+            for (i64 q = z + 1; q <= nnz; ++q)
+                segstart[q] = count;
+    }
+}
+
+void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, i64 *segstart,
+                      LaunchCounter &lc)
+{
+    if (count <= 0)
+    {
+        XSB_CUDA(cudaMemsetAsync(segstart, 0, sizeof(i64) * (size_t)(nnz + 1), stream));
+        return;
+    }
+    frozen_map_kernel<<<grid_for(count, 256), 256, 0, stream>>>(sorted, count, nnz, perm, segstart);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// nzval[z] = ((nzval[z] + V[p0]) + V[p1]) + ...  in stream order: bit-exact with the
+// reference's in-place CSC-hit updates (extendable.jl:164-166)
+__global__ void __launch_bounds__(256)
+reassemble_det_kernel(const double *__restrict__ V, const u32 *__restrict__ perm,
+                      const i64 *__restrict__ segstart, i64 nnz, double *__restrict__ nzval)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 z = (i64)blockIdx.x * blockDim.x + threadIdx.x; z < nnz; z += stride)
+    {
+        const i64 s0 = segstart[z], s1 = segstart[z + 1];
+        if (s1 == s0)
+            continue;
+        double acc = nzval[z];
+        for (i64 s = s0; s < s1; ++s)
+            acc = acc + __ldg(V + perm[s]);
+        nzval[z] = acc;
+    }
+}
+
+void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *perm, const i64 *segstart,
+                              i64 nnz, double *nzval, LaunchCounter &lc)
+{
+    if (nnz <= 0)
+        return;
+    reassemble_det_kernel<<<grid_for(nnz, 256, 32), 256, 0, stream>>>(V, perm, segstart, nnz, nzval);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+reassemble_fast_kernel(const double *__restrict__ V, const i64 *__restrict__ slot, i64 count,
+                       double *__restrict__ nzval)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+        atomicAdd(nzval + slot[k], V[k]);
+}
+
+void reassemble_fast(cudaStream_t stream, const double *V, const i64 *slot, i64 count, double *nzval,
+                     LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    reassemble_fast_kernel<<<grid_for(count, 256, 32), 256, 0, stream>>>(V, slot, count, nzval);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// ---- Dirichlet passes (square matrices; sparsematrixcsc.jl:97-148) ----
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+mark_dirichlet_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval,
+                      const double *__restrict__ nzval, i64 n, Ti base, double penalty,
+                      unsigned char *__restrict__ marker)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        unsigned char mk = 0;
+        const i64 s = (i64)colptr[i] - base, e = (i64)colptr[i + 1] - base;
+        for (i64 k = s; k < e; ++k)
+            if ((i64)rowval[k] - base == i && nzval[k] >= penalty)
+                mk = 1;
+        marker[i] = mk;
+    }
+}
+
+void mark_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, double penalty,
+                    unsigned char *marker, LaunchCounter &lc)
+{
+    const int blocks = grid_for(n, 256);
+    if (idx64)
+        mark_dirichlet_kernel<int64_t><<<blocks, 256, 0, stream>>>(
+            (const int64_t *)csc.colptr, (const int64_t *)csc.rowval, csc.nzval, n, (int64_t)base, penalty, marker);
+    else
+        mark_dirichlet_kernel<int32_t><<<blocks, 256, 0, stream>>>(
+            (const int32_t *)csc.colptr, (const int32_t *)csc.rowval, csc.nzval, n, (int32_t)base, penalty, marker);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// The reference sweeps columns sequentially, but each nzval[k] is decided by
+// (marker[col], marker[row], row==col) alone, so one thread per column is exact:
+//   marked column: diagonal -> 1, rest -> 0;  then any off-diagonal in a marked row -> 0.
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+eliminate_dirichlet_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval,
+                           double *__restrict__ nzval, i64 n, Ti base, const unsigned char *__restrict__ marker)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const bool mi = marker[i] != 0;
+        const i64 s = (i64)colptr[i] - base, e = (i64)colptr[i + 1] - base;
+        for (i64 k = s; k < e; ++k)
+        {
+            const i64 r = (i64)rowval[k] - base;
+            if (mi)
+                nzval[k] = (r == i) ? 1.0 : 0.0;
+            if (r != i && marker[r] != 0)
+                nzval[k] = 0.0;
+        }
+    }
+}
+
+void eliminate_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base,
+                         const unsigned char *marker, LaunchCounter &lc)
+{
+    const int blocks = grid_for(n, 256);
+    if (idx64)
+        eliminate_dirichlet_kernel<int64_t><<<blocks, 256, 0, stream>>>(
+            (const int64_t *)csc.colptr, (const int64_t *)csc.rowval, csc.nzval, n, (int64_t)base, marker);
+    else
+        eliminate_dirichlet_kernel<int32_t><<<blocks, 256, 0, stream>>>(
+            (const int32_t *)csc.colptr, (const int32_t *)csc.rowval, csc.nzval, n, (int32_t)base, marker);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// ---- pattern fingerprint: order-sensitive polynomial hash, combined with atomics ----
+__device__ __forceinline__ u64 mix64(u64 x)
+{ // splitmix64 finaliser
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+pattern_hash_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval, i64 n, i64 nnz,
+                    u64 *__restrict__ d_hash)
+{
+    // sum over positions of mix(position, value) is order sensitive and associative
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    u64 acc = 0;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n + 1 + nnz; k += stride)
+    {
+        const u64 v = k <= n ? (u64)colptr[k] : (u64)rowval[k - n - 1];
+        acc += mix64(mix64((u64)k + 0x9e3779b97f4a7c15ull) ^ v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc)
+        atomicAdd(d_hash, acc);
+}
+
+void pattern_hash(cudaStream_t stream, const CscView &csc, i64 n, int idx64, u64 *d_hash, LaunchCounter &lc)
+{
+    XSB_CUDA(cudaMemsetAsync(d_hash, 0, sizeof(u64), stream));
+    const int blocks = grid_for(n + 1 + csc.nnz, 256);
+    if (idx64)
+        pattern_hash_kernel<int64_t><<<blocks, 256, 0, stream>>>((const int64_t *)csc.colptr,
+                                                                 (const int64_t *)csc.rowval, n, csc.nnz, d_hash);
+    else
+        pattern_hash_kernel<int32_t><<<blocks, 256, 0, stream>>>((const int32_t *)csc.colptr,
+                                                                 (const int32_t *)csc.rowval, n, csc.nnz, d_hash);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+} // namespace xsb

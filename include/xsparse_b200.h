@@ -1,0 +1,223 @@
+/*
+ * xsparse_b200.h -- C ABI of libxsparse_b200.so
+ *
+ * A B200 (sm_100a) implementation of the assembly hot path of
+ * ExtendableSparse.jl: batched insertion/accumulation of possibly duplicate
+ * (i,j,v) entries and the flush! that merges them with the resident CSC matrix
+ * into a new sorted CSC matrix; a values-only path for frozen patterns; and the
+ * synthetic stencil/FEM emitters the benchmarks are defined on.
+ *
+ * The entry points are what a Julia `ccall` (or any FFI) binding of the
+ * reference's extension plug-in interface needs
+ * (reference: src/matrix/abstractsparsematrixextension.jl:1-19).  Each entry
+ * point cites the reference interface it stands in for; paths are relative to
+ * the ExtendableSparse.jl v1.5.1 source tree.
+ *
+ * Conventions
+ *  - Plain C: opaque handle, plain pointers and sizes, no C++/torch types.
+ *  - Every function returns an int32 status (XSB_OK == 0).  No exception ever
+ *    crosses the boundary.  xsb_last_error(h) returns the message of the last
+ *    failing call on that handle (h == NULL: last failure of a call that had no
+ *    handle, per thread).
+ *  - Array arguments may be HOST or DEVICE pointers (resolved through unified
+ *    virtual addressing).  The library never frees, keeps or reallocates a
+ *    caller pointer: outputs are written into caller-allocated buffers, hence
+ *    the two-phase flush (xsb_flush returns nnz; the caller allocates; then
+ *    xsb_fetch_csc).
+ *  - Index arrays have the element type `idx_type` and the base `index_base`
+ *    chosen at creation (Julia: XSB_I64, base 1).  Values are Float64.
+ *  - Calls on one handle must not overlap, except xsb_insert_batch /
+ *    xsb_emit_* with DISTINCT `tid` (the reference's threading contract,
+ *    test/femtools.jl:88-105).
+ *  - There is no CPU fallback: without a CUDA device xsb_create fails with
+ *    XSB_ECUDA.
+ */
+#ifndef XSPARSE_B200_H
+#define XSPARSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XSB_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define XSB_OK 0
+#define XSB_EBOUNDS 1  /* Julia BoundsError: sparsematrixcsc.jl:8-10, sparsematrixlnk.jl:121-123 */
+#define XSB_ESIZE 2    /* size-mismatch @assert: sparsematrixlnk.jl:296-297 */
+#define XSB_EILLEGAL 3 /* error(...) of the MT wrapper: genericmtextendablesparsematrixcsc.jl:67,80 */
+#define XSB_EINVAL 4   /* bad argument */
+#define XSB_ECUDA 5    /* CUDA runtime failure, or no device */
+#define XSB_ENOMEM 6   /* device allocation failed */
+#define XSB_ESTATE 7   /* call not valid in the current state (e.g. pending inserts) */
+
+/* value / index element types */
+#define XSB_F64 0
+#define XSB_I32 0
+#define XSB_I64 1
+
+/* insertion flavours */
+#define XSB_UPDATE 0 /* updateindex!(A,+,v,i,j): no new entry if v==0   extendable.jl:159-174, sparsematrixlnk.jl:210-228 */
+#define XSB_RAW 1    /* rawupdateindex!(A,+,v,i,j): always creates      extendable.jl:181-197, sparsematrixlnk.jl:237-253 */
+#define XSB_ASSIGN 2 /* A[i,j]=v: overwrite; creates only if v!=0       extendable.jl:205-218, sparsematrixlnk.jl:178-201 */
+
+/* summation modes */
+#define XSB_DETERMINISTIC 0 /* left fold in insertion order: bit-exact with the reference   */
+#define XSB_FAST 1          /* warp-shuffle tree per duplicate run: <= 1e-14 relative (f64) */
+
+/* how resident CSC values combine with new duplicates */
+#define XSB_COMBINE_SEED 0 /* ((old + v1) + v2)...  the wrapper's CSC-hit branch, extendable.jl:164-166 */
+#define XSB_COMBINE_ADD 1  /* old + ((0 + v1) + v2)  stand-alone `lnk + csc`, sparsematrixlnk.jl:359-366 */
+
+typedef struct xsb_matrix xsb_matrix;
+
+/* Timings and traffic of the most recent xsb_flush, for roofline reporting. */
+typedef struct xsb_flush_stats
+{
+    int64_t n_inserted;       /* staged insertions consumed            */
+    int64_t nnz_old;          /* entries of the CSC before the flush   */
+    int64_t nnz_new;          /* entries of the CSC after the flush    */
+    int32_t sort_passes;      /* onesweep passes executed              */
+    int32_t sort_bits;        /* key bits sorted                       */
+    int32_t kernel_launches;  /* kernels launched by the flush         */
+    int32_t reserved;
+    float ms_total;           /* device time of the whole flush (CUDA events; 0 unless profiling on) */
+    float ms_expand;          /* old CSC -> records                    */
+    float ms_histogram;       /* digit histogram + scan                */
+    float ms_sort;            /* all onesweep passes                   */
+    float ms_reduce;          /* segmented duplicate reduction + CSC emit */
+    float ms_colptr;          /* colptr scan                           */
+    float ms_other;           /* buffer management, shrink copy        */
+} xsb_flush_stats;
+
+/* ------------------------------------------------------------------ */
+/* life cycle                                                          */
+/* ------------------------------------------------------------------ */
+int32_t xsb_version(void);
+int32_t xsb_device_count(int32_t *count);
+
+/* T_ext(m,n) constructor of the plug-in contract (abstractsparsematrixextension.jl:10)
+ * together with the wrapper's empty CSC (extendable.jl:39-41, genericmt...:16-22).
+ * n_tid = number of partition buffers (length(xmatrices)); device = CUDA ordinal. */
+int32_t xsb_create(int64_t m, int64_t n, int32_t val_type, int32_t idx_type, int32_t index_base,
+                   int32_t n_tid, int32_t device, xsb_matrix **out);
+int32_t xsb_destroy(xsb_matrix *h);
+const char *xsb_last_error(const xsb_matrix *h);
+
+/* reset!(A): extendable.jl:269-272, genericmt...:31-42 */
+int32_t xsb_reset(xsb_matrix *h);
+
+/* ExtendableSparseMatrixCSC(csc) constructor: extendable.jl:61-67.  Replaces the
+ * resident CSC (colptr[n+1], rowval[nnz], nzval[nnz]); pending inserts are dropped. */
+int32_t xsb_set_csc(xsb_matrix *h, const void *colptr, const void *rowval, const void *nzval);
+
+/* Base.size(ext), SparseArrays.nnz(csc part) */
+int32_t xsb_size(const xsb_matrix *h, int64_t *m, int64_t *n);
+int32_t xsb_nnz(const xsb_matrix *h, int64_t *nnz);
+
+/* ------------------------------------------------------------------ */
+/* insertion                                                           */
+/* ------------------------------------------------------------------ */
+/* Pre-size the staging buffer of partition `tid` (0-based) for `count` more entries. */
+int32_t xsb_reserve(xsb_matrix *h, int32_t tid, int64_t count);
+
+/* `count` calls of updateindex!/rawupdateindex!/setindex!(A,[+,]V[k],I[k],J[k][,tid])
+ * in the order k = 0..count-1 (genericmt...:87-114, extendable.jl:159-218).
+ * Out-of-range indices reject the whole batch with XSB_EBOUNDS. */
+int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *J, const void *V,
+                         int64_t count, int32_t flavour);
+
+/* Number of staged insertions (an upper bound of nnznew(A), genericextendable...:21). */
+int32_t xsb_pending(const xsb_matrix *h, int64_t *count);
+
+/* ------------------------------------------------------------------ */
+/* flush! / sparse(A)                                                  */
+/* ------------------------------------------------------------------ */
+/* flush!(A): extendable.jl:248-255 = Base.:+(lnk,csc) sparsematrixlnk.jl:294-383;
+ * multi-partition: Base.sum(xmatrices,csc) sparsematrixdilnkc.jl:397-435.
+ * pattern_changed != 0 iff colptr/rowval changed (the phash contract, extendable.jl:252). */
+int32_t xsb_flush(xsb_matrix *h, int32_t mode, int64_t *nnz_out, int32_t *pattern_changed);
+int32_t xsb_flush_ex(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
+                     int32_t *pattern_changed);
+
+/* sparse(A) after flush!: copy the resident CSC out.  Any pointer may be NULL. */
+int32_t xsb_fetch_csc(xsb_matrix *h, void *colptr_out, void *rowval_out, void *nzval_out);
+
+/* getindex(A,i,j) for `count` positions on the flushed CSC (extendable.jl:226-238,
+ * findindex sparsematrixcsc.jl:7-23); absent entries read 0. XSB_ESTATE if inserts are pending. */
+int32_t xsb_get_values(xsb_matrix *h, const void *I, const void *J, void *V_out, int64_t count);
+
+/* nonzeros(A) .= 0 (sprand.jl:80-85, test_parallel.jl:55) */
+int32_t xsb_zero_values(xsb_matrix *h);
+
+/* ------------------------------------------------------------------ */
+/* values-only re-assembly into a frozen pattern (Newton / transient loops) */
+/* ------------------------------------------------------------------ */
+/* Records, for an insertion stream (I[k],J[k]), the nzval slot of every entry
+ * (the CSC-hit branch extendable.jl:164-166 resolved once instead of per insert).
+ * Every (i,j) must already be in the pattern, else XSB_EILLEGAL. */
+int32_t xsb_freeze_pattern(xsb_matrix *h, const void *I, const void *J, int64_t count);
+/* nzval[slot(k)] += V[k] for the frozen stream; deterministic mode folds in stream order. */
+int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32_t mode);
+int32_t xsb_unfreeze(xsb_matrix *h);
+
+/* ------------------------------------------------------------------ */
+/* values-only passes over the resident CSC                            */
+/* ------------------------------------------------------------------ */
+/* mark_dirichlet / eliminate_dirichlet!: sparsematrixcsc.jl:97-148 (square matrices) */
+int32_t xsb_mark_dirichlet(xsb_matrix *h, double penalty, uint8_t *marker_out);
+int32_t xsb_eliminate_dirichlet(xsb_matrix *h, const uint8_t *marker);
+/* 64-bit fingerprint of (colptr,rowval): stands in for phash (sparsematrixcsc.jl:74);
+ * equal patterns give equal values, it is NOT Julia's hash(). */
+int32_t xsb_pattern_hash(xsb_matrix *h, uint64_t *hash_out);
+
+/* ------------------------------------------------------------------ */
+/* on-device emitters of the benchmark insertion streams               */
+/* ------------------------------------------------------------------ */
+/* fdrand!(A,nx,ny,nz) call stream: sprand.jl:58-126.  ones != 0: rand = ()->1. */
+int32_t xsb_emit_fdrand(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int64_t nz,
+                        uint64_t seed, int32_t ones, int32_t flavour);
+/* Same stream restricted to nodes l in [l_begin, l_end) (0-based), for sharded generation. */
+int32_t xsb_emit_fdrand_range(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int64_t nz,
+                              uint64_t seed, int32_t ones, int32_t flavour, int64_t l_begin,
+                              int64_t l_end);
+/* testassemble!(A,grid) call stream on the Kuhn tensor mesh: test/femtools.jl:45-72 */
+int32_t xsb_emit_p1fem(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t nyn, int64_t nzn,
+                       int32_t flavour);
+/* Same, cubes cz in [cz_begin, cz_end) only; node numbering stays global. */
+int32_t xsb_emit_p1fem_range(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t nyn, int64_t nzn,
+                             int32_t flavour, int64_t cz_begin, int64_t cz_end);
+/* block reaction-diffusion stream (SURVEY.md 8d cfg 4) */
+int32_t xsb_emit_blockrd(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int64_t nz,
+                         int32_t ns, uint64_t seed, int32_t flavour);
+
+/* Lengths of those streams (host arithmetic, no device needed). */
+int32_t xsb_stream_count_fdrand(int64_t nx, int64_t ny, int64_t nz, int64_t *count);
+int32_t xsb_stream_count_p1fem(int64_t nxn, int64_t nyn, int64_t nzn, int64_t *count);
+int32_t xsb_stream_count_blockrd(int64_t nx, int64_t ny, int64_t nz, int32_t ns, int64_t *count);
+
+/* Copy staged records of partition `tid` back as (I,J,V,flavour) in stream order (testing aid). */
+int32_t xsb_debug_fetch_staged(xsb_matrix *h, int32_t tid, void *I, void *J, void *V,
+                               int32_t *flavour, int64_t capacity, int64_t *count);
+
+/* ------------------------------------------------------------------ */
+/* streams, timing                                                     */
+/* ------------------------------------------------------------------ */
+int32_t xsb_synchronize(xsb_matrix *h);
+/* The CUDA stream (cudaStream_t) all kernels of this handle are launched on. */
+int32_t xsb_get_stream(xsb_matrix *h, void **stream_out);
+/* CUDA-event timer on that stream. */
+int32_t xsb_timer_start(xsb_matrix *h);
+int32_t xsb_timer_stop(xsb_matrix *h, float *ms_out);
+/* Per-stage CUDA-event timing inside xsb_flush (off by default). */
+int32_t xsb_set_profiling(xsb_matrix *h, int32_t enable);
+int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
+/* Total kernels launched by this handle since creation. */
+int32_t xsb_kernel_launches(const xsb_matrix *h, int64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSPARSE_B200_H */

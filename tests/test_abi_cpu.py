@@ -1,0 +1,67 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares,
+and its host-side stream arithmetic agrees with the oracle.  No compute call needs a GPU here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def xsb():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import xsparse_b200
+
+    return xsparse_b200
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "xsparse_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(xsb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(xsb):
+    names = header_functions()
+    assert len(names) >= 35
+    lib = ctypes.CDLL(xsb.capi.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/xsparse_b200.h but not exported"
+    # and the Python binding covers exactly the declared surface
+    assert sorted(xsb.capi.SIGNATURES) == names
+
+
+def test_version(xsb):
+    assert xsb.capi.lib().xsb_version() == 100
+
+
+def test_stream_counts_match_oracle(xsb, oracle):
+    for dims in [(1, 1, 1), (2, 1, 1), (3, 1, 1), (100, 1, 1), (10, 10, 1), (2, 2, 1), (3, 3, 1), (5, 5, 5), (7, 6, 5),
+                 (2, 3, 4), (1, 5, 1), (1, 1, 7), (3, 1, 4), (100, 100, 1), (33, 17, 9)]:
+        assert xsb.capi.stream_count_fdrand(*dims) == oracle.fdrand_count(*dims), dims
+    assert xsb.capi.stream_count_p1fem(128, 128, 128) == oracle.fem_count(128, 128, 128)
+    assert xsb.capi.stream_count_blockrd(96, 96, 96, 4) == oracle.blockrd_count(96, 96, 96, 4)
+    assert xsb.capi.stream_count_blockrd(3, 4, 5, 2) == oracle.blockrd_count(3, 4, 5, 2)
+
+
+def test_no_cpu_fallback(xsb):
+    """Without a CUDA device the product fails loudly instead of computing on the host."""
+    if xsb.capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(xsb.XsbError) as e:
+        xsb.Handle(10, 10)
+    assert e.value.code == xsb.capi.ECUDA
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "extendablesparse.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                src = open(os.path.join(dirpath, f)).read()
+                for needle in ("import oracle", "from oracle", "xsb_oracle", "libxsb_oracle", "ora_"):
+                    assert needle not in src, f"{f} references the oracle ({needle})"

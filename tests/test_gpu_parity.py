@@ -1,0 +1,508 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bar: colptr/rowval bit-exact; nzval bit-exact in deterministic mode and
+within 1e-14 relative in fast mode.  Cases follow the reference's own tests."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xsb():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import xsparse_b200
+
+    assert xsparse_b200.capi.device_count() > 0, "no CUDA device: GPU tests need the real extension on a GPU"
+    return xsparse_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def assert_csc_equal(got, ref, exact=True, rtol=1e-14):
+    cp, rv, nz = got
+    ocp, orv, onz = ref
+    assert np.array_equal(cp, ocp), "colptr differs"
+    assert np.array_equal(rv, orv), "rowval differs"
+    if exact:
+        bad = np.nonzero(bits(nz) != bits(onz))[0]
+        assert bad.size == 0, f"{bad.size} nzval entries not bit-exact, first at {bad[:5]}: {nz[bad[:5]]} vs {onz[bad[:5]]}"
+    else:
+        assert np.allclose(nz, onz, rtol=rtol, atol=0.0)
+
+
+# ---------------------------------------------------------------- known-answer tests
+def test_micro_vector(xsb):
+    """SURVEY.md 8(c')."""
+    h = xsb.Handle(3, 3)
+    I = np.array([2, 3, 2, 1], np.int64)
+    J = np.array([1, 1, 1, 2], np.int64)
+    V = np.array([1.0, 2.0, 0.5, 0.0])
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    h.insert_batch(np.array([1], np.int64), np.array([3], np.int64), np.array([0.0]), xsb.RAW)
+    nnz, changed = h.flush()
+    assert (nnz, changed) == (3, True)
+    cp, rv, nz = h.fetch_csc_numpy()
+    assert cp.tolist() == [1, 3, 3, 4] and rv.tolist() == [2, 3, 1] and nz.tolist() == [1.5, 2.0, 0.0]
+    h.insert_batch(np.array([2, 1], np.int64), np.array([1, 1], np.int64), np.array([-1.5, 4.0]), xsb.UPDATE)
+    nnz, changed = h.flush()
+    assert (nnz, changed) == (4, True)
+    cp, rv, nz = h.fetch_csc_numpy()
+    assert cp.tolist() == [1, 4, 4, 5] and rv.tolist() == [1, 2, 3, 1] and nz.tolist() == [4.0, 0.0, 2.0, 0.0]
+    # values-only update: pattern (phash) unchanged
+    h.insert_batch(np.array([1], np.int64), np.array([1], np.int64), np.array([1.0]), xsb.UPDATE)
+    assert h.flush() == (4, False)
+    assert h.flush() == (4, False)  # nothing pending: no-op
+
+
+def test_updates_zero_semantics(xsb):
+    """test/test_updates.jl:10-25 through the host mirror."""
+    import operator
+
+    A = xsb.ExtendableSparseMatrix(10, 10)
+    assert A.nnz == 0
+    A[1, 3] = 5
+    A.updateindex(operator.add, 6.0, 4, 5)
+    A.updateindex(operator.add, 0.0, 2, 3)
+    assert A.nnz == 2
+    A.rawupdateindex(operator.add, 0.0, 2, 3)
+    assert A.nnz == 3
+    A.dropzeros()
+    assert A.nnz == 2
+    A.rawupdateindex(operator.add, 0.1, 2, 3)
+    assert A.nnz == 3
+    A.dropzeros()
+    assert A.nnz == 3
+    assert A[1, 3] == 5.0 and A[4, 5] == 6.0 and A[2, 3] == 0.1 and A[7, 7] == 0.0
+
+
+def test_readme_example(xsb):
+    """README.md:15-27 with A[i,j] += v spelled through getindex/setindex!."""
+    A = xsb.ExtendableSparseMatrix(10, 10)
+    A[1, 1] = 1
+    for i in range(1, 10):
+        A[i + 1, i] = A[i + 1, i] - 1
+        A[i, i + 1] = A[i, i + 1] - 1
+        A[i + 1, i + 1] = A[i + 1, i + 1] + 1
+        A[i, i] = A[i, i] + 1
+    S = A.sparse().toarray()
+    T = 2 * np.eye(10) - np.eye(10, k=1) - np.eye(10, k=-1)
+    T[9, 9] = 1
+    assert A.nnz == 28 and np.array_equal(S, T)
+
+
+def test_bounds_error_rejects_batch(xsb):
+    h = xsb.Handle(4, 5)
+    I = np.array([1, 2, 5, 1], np.int64)
+    J = np.array([1, 1, 1, 1], np.int64)
+    with pytest.raises(IndexError) as e:
+        h.insert_batch(I, J, np.ones(4), xsb.UPDATE)
+    assert "entry 2" in str(e.value) and h.pending == 0
+    for i, j in [(0, 1), (1, 0), (1, 6)]:
+        with pytest.raises(IndexError):
+            h.insert_batch(np.array([i], np.int64), np.array([j], np.int64), np.ones(1), xsb.RAW)
+    h.insert_batch(np.array([4], np.int64), np.array([5], np.int64), np.ones(1), xsb.RAW)
+    assert h.flush() == (1, True)
+
+
+# ---------------------------------------------------------------- random streams
+@pytest.mark.parametrize(
+    "m,n,xnnz,nsplice",
+    [(10, 10, 5, 1), (100, 100, 500, 2), (1000, 1000, 5000, 3), (20, 10, 5, 1), (200, 100, 500, 2),
+     (2000, 1000, 5000, 3), (10, 20, 5, 1), (100, 200, 500, 2), (1000, 2000, 5000, 3), (37, 9001, 7000, 5),
+     (1, 1, 10, 2), (1, 50, 200, 2), (50, 1, 200, 2), (5000, 7000, 200000, 3)],
+)
+def test_assembly_random_splices(xsb, oracle, m, n, xnnz, nsplice):
+    """test/test_assembly.jl:6-35: sorted columns, equal nnz, exactly equal values, after every splice."""
+    rng = np.random.default_rng(1000 * m + n)
+    h = xsb.Handle(m, n)
+    A = oracle.OracleExt(m, n)
+    for _ in range(nsplice):
+        I = rng.integers(1, m + 1, xnnz)
+        J = rng.integers(1, n + 1, xnnz)
+        V = 1.0 + rng.random(xnnz)
+        h.insert_batch(I, J, V, xsb.UPDATE)
+        A.insert_batch(I, J, V, oracle.UPDATE)
+        nnz_before = h.nnz
+        nnz, changed = h.flush()
+        got = h.fetch_csc_numpy()
+        ref = A.csc()
+        assert nnz == len(ref[2]) and changed == (nnz != nnz_before)
+        assert_csc_equal(got, ref)
+        cols = np.repeat(np.arange(n), np.diff(got[0]))
+        order = np.lexsort((got[1], cols))
+        assert np.array_equal(order, np.arange(len(order)))  # rows strictly sorted per column
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mixed_flavours_and_zeros(xsb, oracle, seed):
+    """All three insert flavours interleaved, with +0.0/-0.0 values, cancellations and splices."""
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(5, 60)), int(rng.integers(5, 60))
+    h = xsb.Handle(m, n)
+    A = oracle.OracleExt(m, n)
+    for _ in range(4):
+        for _ in range(int(rng.integers(1, 12))):
+            cnt = int(rng.integers(1, 400))
+            I = rng.integers(1, m + 1, cnt)
+            J = rng.integers(1, n + 1, cnt)
+            V = rng.choice([0.0, -0.0, 1.0, -1.0, 0.5, 1e-3, 1e30, -1e30], cnt) * rng.choice([1.0, rng.random()], cnt)
+            fl = int(rng.integers(0, 3))
+            h.insert_batch(I, J, V, fl)
+            A.insert_batch(I, J, V, fl)
+        h.flush()
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+def test_cancellation_keeps_entry(xsb, oracle):
+    h = xsb.Handle(3, 3)
+    A = oracle.OracleExt(3, 3)
+    I, J, V = np.array([2, 2], np.int64), np.array([2, 2], np.int64), np.array([1.5, -1.5])
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    assert h.flush() == (1, True)
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+@pytest.mark.parametrize("idx,base", [(0, 0), (0, 1), (1, 0)])
+def test_index_types_and_bases(xsb, oracle, idx, base):
+    rng = np.random.default_rng(5)
+    m, n, cnt = 300, 200, 5000
+    dt = np.int64 if idx == 1 else np.int32
+    h = xsb.Handle(m, n, idx_type=idx, index_base=base)
+    A = oracle.OracleExt(m, n)
+    for _ in range(2):
+        I = rng.integers(1, m + 1, cnt)
+        J = rng.integers(1, n + 1, cnt)
+        V = rng.standard_normal(cnt)
+        h.insert_batch((I - 1 + base).astype(dt), (J - 1 + base).astype(dt), V, xsb.RAW)
+        A.insert_batch(I, J, V, oracle.RAW)
+        h.flush()
+        cp, rv, nz = h.fetch_csc_numpy()
+        assert cp.dtype == dt and rv.dtype == dt
+        assert_csc_equal((cp.astype(np.int64) + 1 - base, rv.astype(np.int64) + 1 - base, nz), A.csc())
+
+
+def test_device_pointers(xsb, oracle):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(9)
+    m = n = 4000
+    cnt = 300000
+    I = rng.integers(1, m + 1, cnt)
+    J = rng.integers(1, n + 1, cnt)
+    V = rng.standard_normal(cnt)
+    h = xsb.Handle(m, n)
+    dI, dJ, dV = (torch.from_numpy(x).cuda() for x in (I, J, V))
+    torch.cuda.synchronize()
+    h.insert_batch(dI, dJ, dV, xsb.UPDATE, count=cnt)
+    nnz, _ = h.flush()
+    cp = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    rv = torch.empty(nnz, dtype=torch.int64, device="cuda")
+    nz = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    h.fetch_csc(cp, rv, nz)
+    A = oracle.OracleExt(m, n)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    assert_csc_equal((cp.cpu().numpy(), rv.cpu().numpy(), nz.cpu().numpy()), A.csc())
+
+
+# ---------------------------------------------------------------- reference constructors / operations
+@pytest.mark.parametrize("seed", range(4))
+def test_csc_plus_lnk_is_twice(xsb, seed):
+    """test/test_operations.jl:8-13: csc + SparseMatrixLNK(csc) == 2*csc (COMBINE_ADD)."""
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+    S = sp.random(m, n, density=0.3 * rng.random(), format="csc", random_state=seed)
+    S.sort_indices()
+    cp, rv, nz = S.indptr.astype(np.int64) + 1, S.indices.astype(np.int64) + 1, S.data.copy()
+    h = xsb.Handle(m, n)
+    h.set_csc(cp, rv, nz)
+    cols = np.repeat(np.arange(1, n + 1), np.diff(cp)).astype(np.int64)
+    h.insert_batch(rv, cols, nz, xsb.ASSIGN)  # SparseMatrixLNK(csc): setindex! per entry, sparsematrixlnk.jl:109-118
+    h.flush(xsb.DETERMINISTIC, xsb.COMBINE_ADD)
+    cp2, rv2, nz2 = h.fetch_csc_numpy()
+    assert np.array_equal(cp2, cp) and np.array_equal(rv2, rv) and np.array_equal(nz2, 2 * nz)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_csc_roundtrip(xsb, seed):
+    """test/test_constructors.jl:26-31, :44: CSC -> extension -> CSC is exact."""
+    rng = np.random.default_rng(50 + seed)
+    m, n = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+    S = sp.random(m, n, density=0.3 * rng.random(), format="csc", random_state=seed)
+    S.sort_indices()
+    cp, rv, nz = S.indptr.astype(np.int64) + 1, S.indices.astype(np.int64) + 1, S.data.copy()
+    cols = np.repeat(np.arange(1, n + 1), np.diff(cp)).astype(np.int64)
+    h = xsb.Handle(m, n)
+    perm = rng.permutation(len(nz))
+    h.insert_batch(rv[perm], cols[perm], nz[perm], xsb.ASSIGN)
+    h.flush()
+    cp2, rv2, nz2 = h.fetch_csc_numpy()
+    assert np.array_equal(cp2, cp) and np.array_equal(rv2, rv) and np.array_equal(nz2, nz)
+    h2 = xsb.Handle(m, n)
+    h2.set_csc(cp, rv, nz)
+    cp3, rv3, nz3 = h2.fetch_csc_numpy()
+    assert np.array_equal(cp3, cp) and np.array_equal(rv3, rv) and np.array_equal(nz3, nz)
+
+
+# ---------------------------------------------------------------- generated streams
+@pytest.mark.parametrize("dims", [(100, 100, 1), (100, 1, 1), (10, 10, 1), (5, 5, 5), (2, 2, 2), (3, 1, 1), (1, 1, 1),
+                                  (2, 1, 1), (1, 4, 1), (1, 1, 3), (17, 33, 9), (40, 40, 40)])
+@pytest.mark.parametrize("ones", [False, True])
+def test_emit_fdrand_stream_and_matrix(xsb, oracle, dims, ones):
+    """cfg 1 (fdrand 2D 100x100 via updateindex! + flush!, test_fdrand.jl) and friends."""
+    nx, ny, nz_ = dims
+    N = nx * ny * nz_
+    h = xsb.Handle(N, N)
+    h.emit_fdrand(nx, ny, nz_, seed=20240717, ones=ones, flavour=xsb.UPDATE)
+    I, J, V = oracle.fdrand_stream(nx, ny, nz_, seed=20240717, ones=ones)
+    gI, gJ, gV, gF = h.debug_fetch_staged()
+    assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
+    assert np.all(gF == xsb.UPDATE)
+    A = oracle.OracleExt(N, N)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    h.flush()
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+def test_fdrand_ones_analytic(xsb):
+    """fdrand(100,100; rand=()->1) is analytic."""
+    nx = ny = 100
+    h = xsb.Handle(nx * ny, nx * ny)
+    h.emit_fdrand(nx, ny, 1, ones=True)
+    assert h.pending == 79600
+    assert h.flush() == (49600, True)
+    cp, rv, nz = h.fetch_csc_numpy()
+    cols = np.repeat(np.arange(1, nx * ny + 1), np.diff(cp))
+    off = rv != cols
+    assert np.all(nz[off] == -1.0)
+    ix, iy = (cols[~off] - 1) % nx + 1, (cols[~off] - 1) // nx + 1
+    interior = (ix > 1) & (ix < nx) & (iy > 1) & (iy < ny)
+    assert np.all(nz[~off][interior] == 4.0)
+    assert np.array_equal(np.diff(cp), 1 + (ix > 1) + (ix < nx) + (iy > 1) + (iy < ny))
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2), (3, 4, 5), (9, 9, 9), (17, 5, 3)])
+def test_emit_p1fem(xsb, oracle, dims):
+    """cfg 2 at oracle-sized meshes: testassemble! stream (femtools.jl:45-72), rawupdateindex!."""
+    N = dims[0] * dims[1] * dims[2]
+    h = xsb.Handle(N, N)
+    h.emit_p1fem(*dims, flavour=xsb.RAW)
+    I, J, V = oracle.fem_stream(*dims)
+    gI, gJ, gV, gF = h.debug_fetch_staged()
+    assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
+    A = oracle.OracleExt(N, N)
+    A.insert_batch(I, J, V, oracle.RAW)
+    h.flush()
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2, 4), (5, 4, 3, 4), (6, 6, 6, 2), (3, 1, 1, 3)])
+def test_emit_blockrd_with_dirichlet(xsb, oracle, dims):
+    """cfg 4 at oracle size: block system, then Dirichlet penalty rows (A[d,d]=1e30) and elimination."""
+    nx, ny, nz_, ns = dims
+    N = nx * ny * nz_ * ns
+    h = xsb.Handle(N, N)
+    h.emit_blockrd(nx, ny, nz_, ns, seed=7, flavour=xsb.UPDATE)
+    I, J, V = oracle.blockrd_stream(nx, ny, nz_, ns, seed=7)
+    gI, gJ, gV, _ = h.debug_fetch_staged()
+    assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
+    A = oracle.OracleExt(N, N)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    # Dirichlet on the two x-faces: test/test_dirichlet.jl:9-11
+    node = np.arange(nx * ny * nz_)
+    face = (node % nx == 0) | (node % nx == nx - 1)
+    d = (ns * node[face][:, None] + np.arange(1, ns + 1)[None, :]).ravel().astype(np.int64)
+    pen = np.full(len(d), 1.0e30)
+    h.insert_batch(d, d, pen, xsb.ASSIGN)
+    A.insert_batch(d, d, pen, oracle.ASSIGN)
+    h.flush()
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    mk = h.mark_dirichlet()
+    omk = A.mark_dirichlet()
+    assert np.array_equal(mk, omk) and mk.sum() == len(d)
+    h.eliminate_dirichlet(mk)
+    A.eliminate_dirichlet(omk)
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+# ---------------------------------------------------------------- multi-partition
+@pytest.mark.parametrize("nparts", [1, 3, 8])
+def test_mt_partitions(xsb, oracle, nparts):
+    """MTExtendableSparseMatrixCSC: per-partition buffers summed in partition order
+    (sparsematrixdilnkc.jl:397-435), then a second assembly that only hits the CSC."""
+    I, J, V = oracle.fem_stream(5, 5, 5)
+    N = 125
+    h = xsb.Handle(N, N, n_tid=nparts)
+    A = oracle.OracleMT(N, N, nparts)
+    rng = np.random.default_rng(nparts)
+    chunks = np.array_split(np.arange(len(V)), nparts)
+    order = rng.permutation(nparts)  # partitions deliver their batches in arbitrary order
+    for t in order:
+        c = chunks[t]
+        for part in np.array_split(c, 3):
+            h.insert_batch(I[part], J[part], V[part], xsb.RAW, tid=int(t))
+    for t in range(nparts):
+        A.insert_batch(I[chunks[t]], J[chunks[t]], V[chunks[t]], t + 1, oracle.RAW)
+    h.flush()
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    h.zero_values()
+    A.zero_values()
+    for t in range(nparts):
+        c = chunks[t]
+        h.insert_batch(I[c], J[c], V[c], xsb.RAW, tid=t)
+        A.insert_batch(I[c], J[c], V[c], t + 1, oracle.RAW)
+    assert h.flush()[1] is False
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+# ---------------------------------------------------------------- values-only path
+@pytest.mark.parametrize("dims", [(20, 20, 1), (12, 11, 10)])
+def test_frozen_reassembly(xsb, oracle, dims):
+    """cfg 3 at oracle size: build, then re-assemblies into the frozen pattern (Newton loop)."""
+    nx, ny, nz_ = dims
+    N = nx * ny * nz_
+    h = xsb.Handle(N, N)
+    h.emit_fdrand(nx, ny, nz_, seed=1)
+    h.flush()
+    A = oracle.OracleExt(N, N)
+    I, J, V = oracle.fdrand_stream(nx, ny, nz_, seed=1)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    A.flush()
+    hash0 = h.pattern_hash()
+    h.freeze_pattern(I, J)
+    for it in range(3):
+        _, _, Vn = oracle.fdrand_stream(nx, ny, nz_, seed=2 + it)
+        h.zero_values()
+        h.reassemble_values(Vn, xsb.DETERMINISTIC)
+        A.zero_values()
+        A.insert_batch(I, J, Vn, oracle.UPDATE)
+        assert A.nflush == 1
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        # accumulate on top without zeroing: ((old + v1) + v2) order
+        h.reassemble_values(Vn, xsb.DETERMINISTIC)
+        A.insert_batch(I, J, Vn, oracle.UPDATE)
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        h.zero_values()
+        h.reassemble_values(Vn, xsb.FAST)
+        A.zero_values()
+        A.insert_batch(I, J, Vn, oracle.UPDATE)
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc(), exact=False, rtol=1e-14)
+    assert h.pattern_hash() == hash0
+    # the same re-assembly through the general path (keys re-searched) gives the same bits
+    h.zero_values()
+    h.insert_batch(I, J, Vn, xsb.UPDATE)
+    assert h.flush()[1] is False
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    # a position outside the pattern is refused
+    with pytest.raises(xsb.XsbIllegalError):
+        h.freeze_pattern(np.array([1], np.int64), np.array([N], np.int64))
+    with pytest.raises(xsb.XsbSizeError):
+        h.freeze_pattern(I, J)
+        h.reassemble_values(Vn[:-1])
+
+
+def test_fast_mode_flush(xsb, oracle):
+    I, J, V = oracle.fem_stream(7, 7, 7)
+    N = 343
+    h = xsb.Handle(N, N)
+    h.insert_batch(I, J, V, xsb.RAW)
+    h.flush(xsb.FAST)
+    A = oracle.OracleExt(N, N)
+    A.insert_batch(I, J, V, oracle.RAW)
+    cp, rv, nz = h.fetch_csc_numpy()
+    ocp, orv, onz = A.csc()
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+    scale = np.abs(onz).max()
+    assert np.max(np.abs(nz - onz)) <= 1e-14 * scale
+
+
+def test_get_values_and_pattern_hash(xsb, oracle):
+    rng = np.random.default_rng(3)
+    m, n, cnt = 500, 400, 20000
+    I = rng.integers(1, m + 1, cnt)
+    J = rng.integers(1, n + 1, cnt)
+    V = rng.standard_normal(cnt)
+    h = xsb.Handle(m, n)
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    with pytest.raises(xsb.XsbError):
+        h.get_values(I[:3], J[:3])  # pending inserts: flush first
+    h.flush()
+    A = oracle.OracleExt(m, n)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    qI = rng.integers(1, m + 1, 1000)
+    qJ = rng.integers(1, n + 1, 1000)
+    got = h.get_values(qI, qJ)
+    ref = np.array([A[int(i), int(j)] for i, j in zip(qI, qJ)])
+    assert np.array_equal(bits(got), bits(ref))
+    h0 = h.pattern_hash()
+    h.insert_batch(I[:100], J[:100], V[:100], xsb.UPDATE)
+    h.flush()
+    assert h.pattern_hash() == h0  # values-only update keeps the fingerprint (test_lu.jl:7-31)
+    free = np.setdiff1d(np.arange(1, m + 1), I[J == 1])[:1]
+    h.insert_batch(free, np.array([1], np.int64), np.array([1.0]), xsb.UPDATE)
+    assert h.flush()[1] is True and h.pattern_hash() != h0  # new entry changes it (test_lu.jl:33-45)
+
+
+def test_reset_and_reuse(xsb, oracle):
+    h = xsb.Handle(50, 50)
+    I, J, V = oracle.fdrand_stream(50, 1, 1, seed=4)
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    h.flush()
+    h.reset()
+    assert h.nnz == 0 and h.pending == 0
+    cp, rv, nz = h.fetch_csc_numpy()
+    assert np.all(cp == 1) and len(rv) == 0
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    h.flush()
+    A = oracle.OracleExt(50, 50)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+def test_host_mirror_fdrand(xsb, oracle):
+    """test/test_fdrand.jl:29-53: A[i,j]+=v vs rawupdateindex! vs updateindex! with rand=()->1."""
+    import operator
+
+    def run(update):
+        A = xsb.ExtendableSparseMatrix(25, 25)
+        xsb.fdrand(A, 5, 5, 1, update=update, rand=lambda: 1.0)
+        return A.csc()
+
+    a2 = run(lambda A, v, i, j: A.rawupdateindex(operator.add, v, i, j))
+    a3 = run(lambda A, v, i, j: A.updateindex(operator.add, v, i, j))
+    I, J, V = oracle.fdrand_stream(5, 5, 1, ones=True)
+    O = oracle.OracleExt(25, 25)
+    O.insert_batch(I, J, V, oracle.UPDATE)
+    assert_csc_equal(a2, O.csc())
+    assert_csc_equal(a3, O.csc())
+
+
+# ---------------------------------------------------------------- full-size properties (no oracle)
+def test_full_size_fd_properties(xsb):
+    """fdrand 3D 128^3 (25 M insertions): size-independent properties of the result."""
+    nx = 128
+    N = nx ** 3
+    h = xsb.Handle(N, N)
+    h.emit_fdrand(nx, nx, nx, seed=11)
+    n_ins = h.pending
+    nnz, changed = h.flush()
+    assert changed and nnz == 7 * N - 6 * nx * nx
+    cp, rv, nz = h.fetch_csc_numpy()
+    assert cp[0] == 1 and cp[-1] == nnz + 1 and np.all(np.diff(cp) >= 4) and np.all(np.diff(cp) <= 7)
+    cols = np.repeat(np.arange(1, N + 1), np.diff(cp))
+    assert np.all((np.diff(rv) > 0) | (np.diff(cols) > 0))  # strictly sorted rows inside each column
+    S = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(N, N))
+    assert abs(S - S.T).max() == 0.0  # update_pair inserts -v at (i,j) and (j,i)
+    rs = np.asarray(S.sum(axis=0)).ravel()
+    assert rs.min() > -1e-12  # weakly diagonally dominant M-matrix
+    # idempotence: flushing the same stream on top doubles every value, pattern unchanged
+    h.emit_fdrand(nx, nx, nx, seed=11)
+    assert h.pending == n_ins
+    assert h.flush() == (nnz, False)
+    _, _, nz2 = h.fetch_csc_numpy()
+    assert np.array_equal(nz2[rv != cols], 2 * nz[rv != cols])  # one contribution each: exact
+    assert np.allclose(nz2, 2 * nz, rtol=1e-14, atol=0.0)
