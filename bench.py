@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- assembled entries/s of insert + flush! on B200, with roofline and CPU baseline.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            our arm (libxsparse_b200 through the C ABI)
+  python bench.py --impl reference --gpus N ...            the reference's CPU algorithm (oracle port)
+
+A step = one full assembly of the workload: reset!, insertion of the whole (i,j,v) stream,
+flush! into a fresh CSC.  N=1 workload: BASELINE.json configs[1], the 3-D P1-FEM Laplacian on
+a 128^3-node Kuhn mesh (245 805 960 rawupdateindex! calls, 31 065 598 nnz, Float64/Int64).
+N>1: weak scaling -- every rank assembles its own 128x128x128-node slab of a 128x128x(127N+1)
+mesh; columns are owned by z-slab and the interface plane is routed with an NCCL all-to-all.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "assembled entries/sec (insert+flush!)"
+UNIT = "entries/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+# ---------------------------------------------------------------------------------- workloads
+def workload(args):
+    n = args.mesh
+    return {"workload": f"P1-FEM Laplacian+mass, {n}^3-node Kuhn 6-tet mesh, rawupdateindex! stream + flush! "
+                        f"(BASELINE.json configs[1])",
+            "nodes": n ** 3, "mesh": n, "Tv": "Float64", "Ti": "Int64", "mode": args.mode,
+            "l2_policy": "inputs (3.9 GB of records) far exceed the 126 MB L2; no explicit flush"}
+
+
+def flush_bytes(n_ins, nnz_old, nnz_new, ncols):
+    """Algorithmic bytes of one flush!, SURVEY.md 8(d): 16 B per triplet (packed key + Float64),
+    16 B per CSC entry (Int64 row + Float64), 8 B per colptr entry; old CSC read, new CSC written."""
+    return 16 * n_ins + 16 * nnz_old + 8 * (ncols + 1) + 16 * nnz_new + 8 * (ncols + 1)
+
+
+# ---------------------------------------------------------------------------------- CPU legs
+def cpu_reference_leg(mesh, steps, warmup):
+    """Times the oracle port of the reference's serial path (ExtendableSparseMatrix +
+    rawupdateindex! + flush!) on one host core; returns entries/s (best step) and seconds/step."""
+    from oracle import oracle as ora
+
+    ora.build()
+    I, J, V = ora.fem_stream(mesh, mesh, mesh)
+    n = mesh ** 3
+    times = []
+    for it in range(warmup + steps):
+        A = ora.OracleExt(n, n)
+        t0 = time.perf_counter()
+        A.insert_batch(I, J, V, ora.RAW)
+        A.flush()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        del A
+    return len(V), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mesh = args.ref_mesh
+    n_ins, times = cpu_reference_leg(mesh, args.steps, args.warmup)
+    total = sum(times)
+    value = n_ins * len(times) / total
+    sample = (f"P1-FEM {mesh}^3-node Kuhn mesh ({n_ins} insertions per step), same generator and flavour as the "
+              f"GPU workload; C port of the reference's serial algorithm (gcc -O3), 1 thread: "
+              f"ExtendableSparseMatrix insertion and flush! are single-threaded in the reference")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as ge
+
+    ge.build()
+    import xsparse_b200 as xsb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus != 1 and world == 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import bench_dist
+
+        return bench_dist.run(args, xsb, rank, world, local)
+
+    mesh = args.mesh
+    n = mesh ** 3
+    mode = xsb.DETERMINISTIC if args.mode == "deterministic" else xsb.FAST
+    h = xsb.Handle(n, n, device=local)
+    h.set_profiling(True)
+    n_ins = xsb.capi.stream_count_p1fem(mesh, mesh, mesh)
+
+    def step():
+        h.reset()
+        h.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
+        return h.flush(mode)
+
+    for _ in range(args.warmup):
+        step()
+    h.synchronize()
+    torch.cuda.synchronize()
+    launches0 = h.kernel_launches
+    stage = {}
+    with ClockSampler(local) as clk:
+        h.timer_start()
+        for _ in range(args.steps):
+            nnz, _ = step()
+            st = h.flush_stats()
+            for k, v in st.items():
+                if k.startswith("ms_"):
+                    stage[k] = stage.get(k, 0.0) + v
+        ms = h.timer_stop()
+        launches_timed = h.kernel_launches - launches0
+        # keep the sampler alive for at least a few samples on very short runs
+        t_end = time.time() + max(0.0, 0.5 - ms / 1e3)
+        while time.time() < t_end:
+            step()
+    st = h.flush_stats()
+    ms_step = ms / args.steps
+    value = n_ins / (ms_step / 1e3)
+    peak, peak_src = peaks()
+
+    # dominant kernel: one onesweep pass reads and writes every 16-byte record once
+    passes = st["sort_passes"]
+    ms_pass = stage["ms_sort"] / args.steps / max(passes, 1)
+    rec = st["n_inserted"] + st["nnz_old"]
+    pass_bytes = 32 * rec
+    achieved = pass_bytes / (ms_pass / 1e3) / 1e9
+    b_flush = flush_bytes(st["n_inserted"], st["nnz_old"], st["nnz_new"], n)
+    ms_flush = stage["ms_total"] / args.steps
+    flush_gbs = b_flush / (ms_flush / 1e3) / 1e9
+
+
+    # ---- end-to-end through the C ABI with HOST buffers
+    e2e = measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch)
+
+    # ---- CPU baseline (rank 0, N=1): the oracle port on the same workload
+    cpu = None
+    if not args.no_cpu:
+        cmesh = args.cpu_mesh
+        c_ins, times = cpu_reference_leg(cmesh, 1, 0)
+        cpu = {"value": c_ins / times[0], "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"P1-FEM {cmesh}^3-node Kuhn mesh, {c_ins} insertions, one timed assembly "
+                         f"(oracle port of ExtendableSparseMatrix rawupdateindex!+flush!, gcc -O3, 1 thread)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload(args),
+        "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass over 16-B records)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": args.traffic, "peak_source": peak_src,
+                     "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass, "launches_per_step": passes,
+                     "flush": {"algorithmic_bytes": b_flush, "ms": ms_flush, "achieved": flush_gbs,
+                               "frac": flush_gbs / peak},
+                     "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stage.items())}},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed),
+        "clocks": clk.summary(), "nnz": int(nnz), "n_inserted": int(n_ins),
+    }
+    print(json.dumps(line))
+    h.close()
+
+
+def measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch):
+    """Same metric through the public C ABI with HOST buffers: every step copies the (I,J,V)
+    stream host->device from pinned memory (24 B per insertion), runs insert + flush!, and
+    reads the CSC (colptr, rowval, nzval) back to pinned host memory."""
+    emesh = args.e2e_mesh
+    en = emesh ** 3
+    g = xsb.Handle(en, en, device=h.device)
+    g.emit_p1fem(emesh, emesh, emesh, flavour=xsb.RAW)
+    cnt = g.pending
+    dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dJ = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dV = torch.empty(cnt, dtype=torch.float64, device="cuda")
+    c = xsb.capi
+    import ctypes as C
+
+    got = C.c_int64(0)
+    c.check(c.lib().xsb_debug_fetch_staged(g._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt,
+                                           C.byref(got)), g._h)
+    hI = torch.empty(cnt, dtype=torch.int64, pin_memory=True)
+    hJ = torch.empty(cnt, dtype=torch.int64, pin_memory=True)
+    hV = torch.empty(cnt, dtype=torch.float64, pin_memory=True)
+    hI.copy_(dI)
+    hJ.copy_(dJ)
+    hV.copy_(dV)
+    torch.cuda.synchronize()
+    del dI, dJ, dV
+    g.reset()
+    # result buffers (pinned), sized after one dry run
+    g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
+    nnz, _ = g.flush(mode)
+    ocp = torch.empty(en + 1, dtype=torch.int64, pin_memory=True)
+    orv = torch.empty(nnz, dtype=torch.int64, pin_memory=True)
+    onz = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
+
+    def step():
+        g.reset()
+        g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
+        g.flush(mode)
+        g.fetch_csc(ocp, orv, onz)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    g.synchronize()
+    steps = max(1, min(args.steps, 3))
+    g.timer_start()
+    for _ in range(steps):
+        step()
+    ms = g.timer_stop() / steps
+    g.close()
+    return {"value": cnt / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 24 * cnt,
+            "d2h_bytes_per_step": 8 * (en + 1) + 16 * int(nnz), "ms_per_step": ms,
+            "workload": f"P1-FEM {emesh}^3-node mesh, {cnt} insertions from pinned host (I,J,V), CSC read back to host"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mesh", type=int, default=128, help="nodes per direction of the FEM mesh (128 = configs[1])")
+    ap.add_argument("--e2e-mesh", type=int, default=128)
+    ap.add_argument("--cpu-mesh", type=int, default=128, help="mesh of the cpu_baseline sample")
+    ap.add_argument("--ref-mesh", type=int, default=64, help="mesh of one --impl reference step (bounded sample)")
+    ap.add_argument("--mode", default="deterministic", choices=["deterministic", "fast"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per onesweep launch, if known")
+    args = ap.parse_args()
+    args.steps = max(1, args.steps)
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else max(0, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
