@@ -97,6 +97,9 @@ SIGNATURES = {
     "xsb_stream_count_p1fem": (_i32, [_i64, _i64, _i64, C.POINTER(_i64)]),
     "xsb_stream_count_blockrd": (_i32, [_i64, _i64, _i64, _i32, C.POINTER(_i64)]),
     "xsb_debug_fetch_staged": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "xsb_debug_set_sort_variant": (_i32, [_i32]),
+    "xsb_debug_sort_selftest": (_i32, [_p, _i64, _i32, _i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                       C.POINTER(_i64), C.POINTER(_i32)]),
     "xsb_synchronize": (_i32, [_p]),
     "xsb_get_stream": (_i32, [_p, C.POINTER(_p)]),
     "xsb_timer_start": (_i32, [_p]),
@@ -311,6 +314,12 @@ class Handle:
         if n:
             self._c(lib().xsb_debug_fetch_staged(self._h, tid, ptr(I), ptr(J), ptr(V), ptr(F), n, C.byref(c)))
         return I, J, V, F
+
+    def sort_selftest(self, n, nbits, variant=0, reps=3):
+        mh, mp, v, npass = C.c_float(0), C.c_float(0), _i64(0), _i32(0)
+        self._c(lib().xsb_debug_sort_selftest(self._h, n, nbits, variant, reps, C.byref(mh), C.byref(mp), C.byref(v),
+                                              C.byref(npass)))
+        return {"ms_histogram": mh.value, "ms_per_pass": mp.value, "violations": v.value, "passes": npass.value}
 
     def synchronize(self):
         self._c(lib().xsb_synchronize(self._h))

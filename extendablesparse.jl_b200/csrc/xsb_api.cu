@@ -987,6 +987,27 @@ int32_t xsb_debug_fetch_staged(xsb_matrix *h, int32_t tid, void *I, void *J, voi
     });
 }
 
+int32_t xsb_debug_set_sort_variant(int32_t variant)
+{
+    set_sort_variant(variant);
+    return get_sort_variant() == variant ? XSB_OK : XSB_EINVAL;
+}
+
+int32_t xsb_debug_sort_selftest(xsb_matrix *h, int64_t n, int32_t nbits, int32_t variant, int32_t reps,
+                                float *ms_histogram, float *ms_per_pass, int64_t *violations, int32_t *npasses)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && ms_histogram && ms_per_pass && violations && npasses, XSB_EINVAL, "NULL argument");
+        REQUIRE(n >= 2 && nbits >= 1 && nbits <= 64 && reps >= 1, XSB_EINVAL, "bad self-test size");
+        u64 viol = 0;
+        int np = 0;
+        sort_selftest(h->stream, (u64)n, nbits, variant, reps, ms_histogram, ms_per_pass, &viol, &np);
+        *violations = (int64_t)viol;
+        *npasses = np;
+        return XSB_OK;
+    });
+}
+
 int32_t xsb_synchronize(xsb_matrix *h)
 {
     return guard(h, [&]() -> int32_t {

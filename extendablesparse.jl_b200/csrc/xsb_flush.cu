@@ -151,97 +151,20 @@ struct RunFold
     }
 };
 
-template <typename Ti>
-__global__ void __launch_bounds__(RD_THREADS)
-reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int combine, Ti base,
-                   Ti *__restrict__ rowval, double *__restrict__ nzval, u64 *__restrict__ colend,
-                   u64 *__restrict__ status, u32 *__restrict__ tile_counter, u64 *__restrict__ d_nnz, u32 ntiles)
+// Order-preserving compaction ranks for flags laid out as (step i, thread): returns the
+// exclusive rank of every set flag and the total.  s_cnt/s_off hold RD_IPT*RD_WARPS words.
+__device__ __forceinline__ u32 block_rank_flags(const bool (&flag)[RD_IPT], u32 (&rank)[RD_IPT], u32 *s_cnt,
+                                                u32 *s_off, u32 *s_total, int lane, int warp, u32 lt)
 {
-    __shared__ Rec s_rec[RD_TILE];
-    __shared__ u32 s_col[RD_TILE];
-    __shared__ u32 s_cnt[RD_IPT * RD_WARPS];
-    __shared__ u32 s_off[RD_IPT * RD_WARPS];
-    __shared__ u64 s_prev, s_tileoff;
-    __shared__ u32 s_tile, s_total;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0)
-        s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
-    const u64 tbase = (u64)tile * RD_TILE;
-    const u32 valid = (u32)min((u64)RD_TILE, nrec - tbase);
-
 #pragma unroll
     for (int i = 0; i < RD_IPT; ++i)
     {
-        const u32 e = i * RD_THREADS + tid;
-        if (e < valid)
-            s_rec[e] = ld_rec_stream(sorted + tbase + e);
-    }
-    if (tid == 0)
-        s_prev = tbase > 0 ? sorted[tbase - 1].key : 0ull;
-    __syncthreads();
-
-    const u32 lt = lanemask_lt();
-    double myval[RD_IPT];
-    u32 myrow[RD_IPT], mycol[RD_IPT], myrank[RD_IPT];
-    bool myflag[RD_IPT];
-#pragma unroll
-    for (int i = 0; i < RD_IPT; ++i)
-    {
-        const u32 e = i * RD_THREADS + tid;
-        bool flag = false;
-        double out = 0.0;
-        u32 row = 0, col = 0;
-        if (e < valid)
-        {
-            const u64 key = s_rec[e].key;
-            const u64 cr = L.colrow(key);
-            bool head;
-            if (e > 0)
-                head = cr != L.colrow(s_rec[e - 1].key);
-            else
-                head = (tbase == 0) || cr != L.colrow(s_prev);
-            if (head)
-            {
-                RunFold f;
-                u64 g = tbase + e;
-                u32 q = e;
-                for (;;)
-                {
-                    Rec r;
-                    if (q < valid)
-                        r = s_rec[q];
-                    else if (g < nrec)
-                        r = sorted[g]; // run continues into the next tile
-                    else
-                        break;
-                    if (L.colrow(r.key) != cr)
-                        break;
-                    f.apply(L.flavour(r.key), L.tid(r.key), r.val, combine);
-                    ++q;
-                    ++g;
-                }
-                f.finish();
-                flag = f.exists;
-                out = f.acc;
-                row = (u32)L.row(key);
-                col = (u32)L.col(key);
-            }
-        }
-        const u32 bal = __ballot_sync(0xffffffffu, flag);
+        const u32 bal = __ballot_sync(0xffffffffu, flag[i]);
         if (lane == 0)
             s_cnt[i * RD_WARPS + warp] = __popc(bal);
-        myrank[i] = __popc(bal & lt);
-        myflag[i] = flag;
-        myval[i] = out;
-        myrow[i] = row;
-        mycol[i] = col;
+        rank[i] = __popc(bal & lt);
     }
     __syncthreads();
-
-    // exclusive scan of the RD_IPT*RD_WARPS ballot counts (order: step major, warp minor)
     if (warp == 0)
     {
         constexpr int PER = RD_IPT * RD_WARPS / 32;
@@ -267,9 +190,155 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
             s_off[lane * PER + k] = run;
             run += c[k];
         }
-        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31)
+            *s_total = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RD_IPT; ++i)
+        rank[i] += s_off[i * RD_WARPS + warp];
+    return *s_total;
+}
 
-        // decoupled look-back over the tiles' output counts, 32 predecessors per step
+// One tile of RD_TILE sorted records: find the heads of the duplicate runs, compact them so that
+// every lane folds one run (a run is folded sequentially in insertion order, which is what makes
+// the result bit-exact), compact the created entries and write them at the tile's output offset
+// (decoupled look-back over the tiles' entry counts).
+// SIMPLE: single partition, no assign flavour, seed combine -- the fold is a plain running sum.
+template <typename Ti, bool SIMPLE>
+__global__ void __launch_bounds__(RD_THREADS)
+reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int combine, Ti base,
+                   Ti *__restrict__ rowval, double *__restrict__ nzval, u64 *__restrict__ colend,
+                   u64 *__restrict__ status, u32 *__restrict__ tile_counter, u64 *__restrict__ d_nnz, u32 ntiles)
+{
+    __shared__ Rec s_rec[RD_TILE];
+    __shared__ u32 s_col[RD_TILE]; // first the head positions, later the columns of the output entries
+    __shared__ u32 s_cnt[RD_IPT * RD_WARPS];
+    __shared__ u32 s_off[RD_IPT * RD_WARPS];
+    __shared__ u64 s_prev, s_tileoff;
+    __shared__ u32 s_tile, s_total;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 tbase = (u64)tile * RD_TILE;
+    const u32 valid = (u32)min((u64)RD_TILE, nrec - tbase);
+
+#pragma unroll
+    for (int i = 0; i < RD_IPT; ++i)
+    {
+        const u32 e = i * RD_THREADS + tid;
+        if (e < valid)
+            s_rec[e] = ld_rec_stream(sorted + tbase + e);
+    }
+    if (tid == 0)
+        s_prev = tbase > 0 ? sorted[tbase - 1].key : 0ull;
+    __syncthreads();
+
+    const u32 lt = lanemask_lt();
+    bool flag[RD_IPT];
+    u32 rank[RD_IPT];
+
+    // ---- heads of the runs of equal (col,row), compacted into s_col[0..nheads)
+#pragma unroll
+    for (int i = 0; i < RD_IPT; ++i)
+    {
+        const u32 e = i * RD_THREADS + tid;
+        bool head = false;
+        if (e < valid)
+        {
+            const u64 cr = L.colrow(s_rec[e].key);
+            if (e > 0)
+                head = cr != L.colrow(s_rec[e - 1].key);
+            else
+                head = (tbase == 0) || cr != L.colrow(s_prev);
+        }
+        flag[i] = head;
+    }
+    const u32 nheads = block_rank_flags(flag, rank, s_cnt, s_off, &s_total, lane, warp, lt);
+#pragma unroll
+    for (int i = 0; i < RD_IPT; ++i)
+        if (flag[i])
+            s_col[rank[i]] = i * RD_THREADS + tid;
+    __syncthreads();
+
+    // ---- one run per lane
+    double myval[RD_IPT];
+    u32 myrow[RD_IPT], mycol[RD_IPT];
+#pragma unroll
+    for (int i = 0; i < RD_IPT; ++i)
+    {
+        const u32 hidx = i * RD_THREADS + tid;
+        bool created = false;
+        double out = 0.0;
+        u32 row = 0, col = 0;
+        if (i * RD_THREADS < nheads) // uniform: rounds beyond the last head are skipped by the whole block
+        {
+            if (hidx < nheads)
+            {
+                const u32 e0 = s_col[hidx];
+                const bool last = hidx + 1 == nheads;
+                const u32 e1 = last ? valid : s_col[hidx + 1];
+                const u64 key = s_rec[e0].key;
+                const u64 cr = L.colrow(key);
+                row = (u32)L.row(key);
+                col = (u32)L.col(key);
+                if (SIMPLE)
+                {
+                    double acc = 0.0;
+                    for (u32 q = e0; q < e1; ++q)
+                    {
+                        const Rec r = s_rec[q];
+                        const u32 fl = L.flavour(r.key);
+                        acc = (fl == FL_OLD) ? r.val : acc + r.val;
+                        created |= (fl != FL_UPDATE) | (r.val != 0.0);
+                    }
+                    if (last)
+                        for (u64 g = tbase + valid; g < nrec; ++g)
+                        { // the tile's last run may continue into the following tiles
+                            const Rec r = sorted[g];
+                            if (L.colrow(r.key) != cr)
+                                break;
+                            acc = acc + r.val;
+                            created |= (L.flavour(r.key) != FL_UPDATE) | (r.val != 0.0);
+                        }
+                    out = acc;
+                }
+                else
+                {
+                    RunFold f;
+                    for (u32 q = e0; q < e1; ++q)
+                    {
+                        const Rec r = s_rec[q];
+                        f.apply(L.flavour(r.key), L.tid(r.key), r.val, combine);
+                    }
+                    if (last)
+                        for (u64 g = tbase + valid; g < nrec; ++g)
+                        {
+                            const Rec r = sorted[g];
+                            if (L.colrow(r.key) != cr)
+                                break;
+                            f.apply(L.flavour(r.key), L.tid(r.key), r.val, combine);
+                        }
+                    f.finish();
+                    created = f.exists;
+                    out = f.acc;
+                }
+            }
+        }
+        flag[i] = created;
+        myval[i] = out;
+        myrow[i] = row;
+        mycol[i] = col;
+    }
+    __syncthreads(); // s_col (head positions) is dead from here on
+    const u32 total = block_rank_flags(flag, rank, s_cnt, s_off, &s_total, lane, warp, lt);
+
+    // ---- decoupled look-back over the tiles' entry counts, 32 predecessors per step
+    if (warp == 0)
+    {
         u64 prefix = 0;
         if (tile == 0)
         {
@@ -314,7 +383,6 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
         if (lane == 0)
         {
             s_tileoff = prefix;
-            s_total = total;
             if (tile == ntiles - 1)
                 *d_nnz = prefix + total;
         }
@@ -322,17 +390,15 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
     __syncthreads();
 
     const u64 tileoff = s_tileoff;
-    const u32 total = s_total;
 #pragma unroll
     for (int i = 0; i < RD_IPT; ++i)
     {
-        if (myflag[i])
+        if (flag[i])
         {
-            const u32 local = s_off[i * RD_WARPS + warp] + myrank[i];
-            const u64 p = tileoff + local;
+            const u64 p = tileoff + rank[i];
             rowval[p] = (Ti)myrow[i] + base;
             nzval[p] = myval[i];
-            s_col[local] = mycol[i];
+            s_col[rank[i]] = mycol[i];
         }
     }
     __syncthreads();
@@ -474,7 +540,6 @@ void reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout
                      void *colptr_out, void *workspace, u64 *d_nnz, LaunchCounter &lc, StageTimer *timer)
 {
     (void)mode;
-    (void)plain_adds;
     const u64 ntiles = (nrec + RD_TILE - 1) / RD_TILE;
     const u64 ctiles = ((u64)ncols + CP_TILE - 1) / CP_TILE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -489,14 +554,25 @@ void reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout
     XSB_CUDA(cudaMemsetAsync(d_nnz, 0, sizeof(u64), stream));
     if (nrec > 0)
     {
+        const bool simple = plain_adds && L.tidbits == 0 && combine == 0;
+#define XSB_LAUNCH_REDUCE(TI, SIMPLE)                                                                            \
+    reduce_emit_kernel<TI, SIMPLE><<<(unsigned)ntiles, RD_THREADS, 0, stream>>>(                                 \
+        sorted, nrec, L, combine, (TI)base, (TI *)rowval_out, nzval_out, colend, status, counter, d_nnz, (u32)ntiles)
         if (idx64)
-            reduce_emit_kernel<int64_t><<<(unsigned)ntiles, RD_THREADS, 0, stream>>>(
-                sorted, nrec, L, combine, (int64_t)base, (int64_t *)rowval_out, nzval_out, colend, status,
-                counter, d_nnz, (u32)ntiles);
+        {
+            if (simple)
+                XSB_LAUNCH_REDUCE(int64_t, true);
+            else
+                XSB_LAUNCH_REDUCE(int64_t, false);
+        }
         else
-            reduce_emit_kernel<int32_t><<<(unsigned)ntiles, RD_THREADS, 0, stream>>>(
-                sorted, nrec, L, combine, (int32_t)base, (int32_t *)rowval_out, nzval_out, colend, status,
-                counter, d_nnz, (u32)ntiles);
+        {
+            if (simple)
+                XSB_LAUNCH_REDUCE(int32_t, true);
+            else
+                XSB_LAUNCH_REDUCE(int32_t, false);
+        }
+#undef XSB_LAUNCH_REDUCE
         lc.add();
         XSB_CUDA(cudaGetLastError());
     }

@@ -77,6 +77,11 @@ size_t sort_workspace_bytes(u64 n);
 Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPlan &plan, void *workspace,
                         LaunchCounter &lc, StageTimer *timer);
 
+void set_sort_variant(int v);
+int get_sort_variant();
+void sort_selftest(cudaStream_t stream, u64 n, int nbits, int variant, int reps, float *ms_hist, float *ms_pass,
+                   u64 *violations_out, int *npasses_out);
+
 // ---- xsb_flush.cu
 struct CscView
 {

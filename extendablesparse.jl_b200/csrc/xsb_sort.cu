@@ -72,50 +72,46 @@ __global__ void __launch_bounds__(kRadix) histogram_scan_kernel(u64 *__restrict_
 // ------------------------------------------------------------------------
 // one onesweep pass
 // ------------------------------------------------------------------------
-constexpr int OS_THREADS = 256;
-constexpr int OS_WARPS = OS_THREADS / 32;
-constexpr int OS_IPT = 16;
-constexpr int OS_TILE = OS_THREADS * OS_IPT; // 4096 records = 64 KB of shared memory
-static_assert(OS_THREADS == kRadix, "one thread per digit in the look-back");
-
 // look-back words carry 30-bit counts: longer inputs are sorted in portions
-constexpr u64 kSortPortion = ((1ull << 30) - 1ull) / OS_TILE * OS_TILE;
 constexpr u32 ST_LOCAL = 1u << 30;
 constexpr u32 ST_INCL = 2u << 30;
 constexpr u32 ST_VALUE = (1u << 30) - 1u;
 
-__global__ void __launch_bounds__(OS_THREADS, 2)
+template <int THREADS, int IPT, int MINBLK>
+__global__ void __launch_bounds__(THREADS, MINBLK)
 onesweep_kernel(const Rec *__restrict__ in, Rec *__restrict__ out, u32 n, u32 ntiles, int shift,
                 int bits, const u64 *__restrict__ gbase, u64 *__restrict__ gbase_next,
                 u32 *__restrict__ status, u32 *__restrict__ tile_counter)
 {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * IPT;
+    static_assert(THREADS >= kRadix, "one thread per digit in the look-back");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Rec *s_rec = reinterpret_cast<Rec *>(smem_raw);
-    __shared__ u32 s_whist[OS_WARPS][kRadix];
+    __shared__ u32 s_whist[WARPS][kRadix];
     __shared__ u32 s_binstart[kRadix];
     __shared__ i64 s_gofs[kRadix];
-    __shared__ u32 s_warpsum[OS_WARPS];
+    __shared__ u32 s_warpsum[kRadix / 32];
     __shared__ u32 s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0)
         s_tile = atomicAdd(tile_counter, 1u); // tiles are claimed in launch order: predecessors always run
-#pragma unroll
-    for (int w = 0; w < OS_WARPS; ++w)
-        s_whist[w][tid] = 0;
+    for (int i = tid; i < WARPS * kRadix; i += THREADS)
+        (&s_whist[0][0])[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
-    const u32 base = tile * OS_TILE;
-    const u32 valid = min((u32)OS_TILE, n - base);
+    const u32 base = tile * TILE;
+    const u32 valid = min((u32)TILE, n - base);
     const u32 mask = (1u << bits) - 1u;
     const u32 nbins = 1u << bits;
 
     // ---- load: warp-striped, one 16-byte vector per lane per step
-    u64 key[OS_IPT];
-    double val[OS_IPT];
-    const u32 wbase = warp * (32 * OS_IPT);
+    u64 key[IPT];
+    double val[IPT];
+    const u32 wbase = warp * (32 * IPT);
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k)
+    for (int k = 0; k < IPT; ++k)
     {
         const u32 idx = wbase + k * 32 + lane;
         if (idx < valid)
@@ -133,9 +129,9 @@ onesweep_kernel(const Rec *__restrict__ in, Rec *__restrict__ out, u32 n, u32 nt
 
     // ---- rank inside the warp with ballots (stable: lower lane, lower step first)
     const u32 lt = lanemask_lt();
-    u32 rank[OS_IPT];
+    u32 rank[IPT];
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k)
+    for (int k = 0; k < IPT; ++k)
     {
         const u32 d = (u32)(key[k] >> shift) & mask;
         u32 peers = 0xffffffffu;
@@ -162,71 +158,86 @@ onesweep_kernel(const Rec *__restrict__ in, Rec *__restrict__ out, u32 n, u32 nt
     }
     __syncthreads();
 
-    // ---- per digit: exclusive prefix over the warps, tile count
-    u32 total = 0;
-#pragma unroll
-    for (int w = 0; w < OS_WARPS; ++w)
+    // ---- per digit: exclusive prefix over the warps, tile count, exclusive scan over digits
+    u32 total = 0, incl = 0;
+    if (tid < kRadix)
     {
-        const u32 c = s_whist[w][tid];
-        s_whist[w][tid] = total;
-        total += c;
-    }
-    // exclusive scan of the tile counts over the digits
-    u32 incl = total;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o)
-            incl += t;
+        for (int w = 0; w < WARPS; ++w)
+        {
+            const u32 c = s_whist[w][tid];
+            s_whist[w][tid] = total;
+            total += c;
+        }
+        incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_warpsum[warp] = incl;
     }
-    if (lane == 31)
-        s_warpsum[warp] = incl;
     __syncthreads();
-    u32 wpre = 0;
-#pragma unroll
-    for (int w = 0; w < OS_WARPS; ++w)
-        if (w < warp)
-            wpre += s_warpsum[w];
-    const u32 excl = wpre + incl - total;
-    s_binstart[tid] = excl;
 
     // ---- decoupled look-back: one thread per digit
-    if ((u32)tid < nbins)
+    if (tid < kRadix)
     {
-        u32 *mine = status + (size_t)tile * nbins + tid;
-        u32 prefix = 0;
-        if (tile == 0)
+        u32 wpre = 0;
+#pragma unroll
+        for (int w = 0; w < kRadix / 32; ++w)
+            if (w < warp)
+                wpre += s_warpsum[w];
+        const u32 excl = wpre + incl - total;
+        s_binstart[tid] = excl;
+        if ((u32)tid < nbins)
         {
-            st_relaxed_u32(mine, ST_INCL | total);
-        }
-        else
-        {
-            st_relaxed_u32(mine, ST_LOCAL | total);
-            for (i64 t = (i64)tile - 1;; --t)
+            u32 *mine = status + (size_t)tile * nbins + tid;
+            u32 prefix = 0;
+            if (tile == 0)
             {
-                const u32 *p = status + (size_t)t * nbins + tid;
-                u32 v;
-                do
-                {
-                    v = ld_relaxed_u32(p);
-                } while ((v >> 30) == 0u);
-                prefix += v & ST_VALUE;
-                if ((v >> 30) == 2u)
-                    break;
+                st_relaxed_u32(mine, ST_INCL | total);
             }
-            st_relaxed_u32(mine, ST_INCL | (prefix + total));
+            else
+            {
+                st_relaxed_u32(mine, ST_LOCAL | total);
+                // LB predecessors are read per L2 round trip: the walk back to the nearest tile
+                // with an inclusive prefix is latency bound, so the loads must overlap
+                constexpr int LB = 8;
+                bool done = false;
+                for (i64 t = (i64)tile - 1; !done; t -= LB)
+                {
+                    u32 v[LB];
+#pragma unroll
+                    for (int j = 0; j < LB; ++j)
+                        v[j] = (t - j >= 0) ? ld_relaxed_u32(status + (size_t)(t - j) * nbins + tid) : ST_INCL;
+#pragma unroll
+                    for (int j = 0; j < LB; ++j)
+                    {
+                        if (!done)
+                        {
+                            while ((v[j] >> 30) == 0u)
+                                v[j] = ld_relaxed_u32(status + (size_t)(t - j) * nbins + tid);
+                            prefix += v[j] & ST_VALUE;
+                            done = (v[j] >> 30) == 2u;
+                        }
+                    }
+                }
+                st_relaxed_u32(mine, ST_INCL | (prefix + total));
+            }
+            const u64 g = gbase[tid];
+            s_gofs[tid] = (i64)(g + prefix) - (i64)excl;
+            if (gbase_next != nullptr && tile == ntiles - 1)
+                gbase_next[tid] = g + prefix + total;
         }
-        const u64 g = gbase[tid];
-        s_gofs[tid] = (i64)(g + prefix) - (i64)excl;
-        if (gbase_next != nullptr && tile == ntiles - 1)
-            gbase_next[tid] = g + prefix + total;
     }
     __syncthreads();
 
     // ---- reorder through shared memory
 #pragma unroll
-    for (int k = 0; k < OS_IPT; ++k)
+    for (int k = 0; k < IPT; ++k)
     {
         const u32 d = (u32)(key[k] >> shift) & mask;
         const u32 pos = s_binstart[d] + s_whist[warp][d] + rank[k];
@@ -239,9 +250,9 @@ onesweep_kernel(const Rec *__restrict__ in, Rec *__restrict__ out, u32 n, u32 nt
 
     // ---- scatter: consecutive threads hold consecutive ranks, so each digit's run is coalesced
 #pragma unroll
-    for (int i = 0; i < OS_IPT; ++i)
+    for (int i = 0; i < IPT; ++i)
     {
-        const u32 idx = i * OS_THREADS + tid;
+        const u32 idx = i * THREADS + tid;
         if (idx < valid)
         {
             const Rec r = s_rec[idx];
@@ -254,6 +265,38 @@ onesweep_kernel(const Rec *__restrict__ in, Rec *__restrict__ out, u32 n, u32 nt
 // ------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------
+typedef void (*OnesweepFn)(const Rec *, Rec *, u32, u32, int, int, const u64 *, u64 *, u32 *, u32 *);
+struct OnesweepVariant
+{
+    OnesweepFn fn;
+    int threads, tile;
+};
+template <int THREADS, int IPT, int MINBLK> static OnesweepVariant make_variant()
+{
+    return OnesweepVariant{onesweep_kernel<THREADS, IPT, MINBLK>, THREADS, THREADS * IPT};
+}
+static const OnesweepVariant kVariants[] = {
+    make_variant<256, 16, 2>(), // 0: 4096-record tiles, 2 CTAs/SM
+    make_variant<256, 8, 4>(),  // 1: 2048-record tiles, 4 CTAs/SM
+    make_variant<512, 8, 2>(),  // 2: 4096-record tiles, 2 x 16 warps
+    make_variant<256, 12, 3>(), // 3: 3072-record tiles, 3 CTAs/SM
+    make_variant<512, 6, 3>(),  // 4: 3072-record tiles, 3 x 16 warps
+    make_variant<256, 8, 3>(),  // 5
+    make_variant<512, 4, 4>(),  // 6: 2048-record tiles, 4 x 16 warps
+};
+constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+static int g_variant = 2; // 512 threads x 8 records: best of the measured tile shapes (tools/tune_sort.py)
+constexpr int kMinTile = 2048;
+
+void set_sort_variant(int v)
+{
+    if (v >= 0 && v < kNumVariants)
+        g_variant = v;
+}
+int get_sort_variant() { return g_variant; }
+
+static u64 sort_portion(int tile) { return ((1ull << 30) - 1ull) / (u64)tile * (u64)tile; }
+
 SortPlan make_sort_plan(int begin_bit, int nbits)
 {
     SortPlan p{};
@@ -278,8 +321,8 @@ SortPlan make_sort_plan(int begin_bit, int nbits)
 
 size_t sort_workspace_bytes(u64 n)
 {
-    const u64 portion = std::min<u64>(n, kSortPortion);
-    const u64 ntiles = (portion + OS_TILE - 1) / OS_TILE;
+    const u64 portion = std::min<u64>(n, sort_portion(kMinTile));
+    const u64 ntiles = (portion + kMinTile - 1) / kMinTile;
     // ghist [kMaxPasses][256] u64, gbase_next [256] u64 x2, counter u32 (padded), status [ntiles][256] u32
     return sizeof(u64) * kMaxPasses * kRadix + 2 * sizeof(u64) * kRadix + 256 +
            sizeof(u32) * ntiles * kRadix;
@@ -292,13 +335,15 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
 {
     if (n <= 1 || plan.npasses == 0)
         return a;
-    static bool attr_set = false;
-    if (!attr_set)
+    const OnesweepVariant &var = kVariants[g_variant];
+    static bool attr_set[kNumVariants] = {};
+    if (!attr_set[g_variant])
     {
-        XSB_CUDA(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(OS_TILE * sizeof(Rec))));
-        attr_set = true;
+        XSB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(var.fn),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var.tile * sizeof(Rec))));
+        attr_set[g_variant] = true;
     }
+    const u64 portion = sort_portion(var.tile);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     u64 *ghist = reinterpret_cast<u64 *>(ws);
     u64 *gnext0 = ghist + kMaxPasses * kRadix;
@@ -330,13 +375,13 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
         const u64 *gbase = ghist + p * kRadix;
         u64 *gn[2] = {gnext0, gnext1};
         int flip = 0;
-        for (u64 off = 0; off < n; off += kSortPortion)
+        for (u64 off = 0; off < n; off += portion)
         {
-            const u32 cnt = (u32)std::min<u64>(kSortPortion, n - off);
-            const u32 ntiles = (cnt + OS_TILE - 1) / OS_TILE;
-            const bool more = off + kSortPortion < n;
+            const u32 cnt = (u32)std::min<u64>(portion, n - off);
+            const u32 ntiles = (cnt + var.tile - 1) / var.tile;
+            const bool more = off + portion < n;
             XSB_CUDA(cudaMemsetAsync(counter, 0, 256 + sizeof(u32) * (size_t)ntiles * nbins, stream));
-            onesweep_kernel<<<ntiles, OS_THREADS, OS_TILE * sizeof(Rec), stream>>>(
+            var.fn<<<ntiles, var.threads, var.tile * sizeof(Rec), stream>>>(
                 src + off, dst, cnt, ntiles, plan.shift[p], plan.bits[p], gbase, more ? gn[flip] : nullptr,
                 status, counter);
             lc.add();
@@ -352,6 +397,86 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
     if (timer)
         timer->end(stream, &StageTimes::sort);
     return src;
+}
+
+// ------------------------------------------------------------------------
+// self test / micro benchmark of the sort (random keys, stability checked)
+// ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) selftest_fill_kernel(Rec *__restrict__ out, u64 n, int nbits, u64 seed)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 mask = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1ull);
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    {
+        u64 x = k + seed * 0x9e3779b97f4a7c15ull;
+        x ^= x >> 30;
+        x *= 0xbf58476d1ce4e5b9ull;
+        x ^= x >> 27;
+        x *= 0x94d049bb133111ebull;
+        x ^= x >> 31;
+        Rec r;
+        r.key = x & mask;
+        r.val = (double)k;
+        st_rec(out + k, r);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+selftest_check_kernel(const Rec *__restrict__ in, u64 n, u64 *__restrict__ violations)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1; k < n; k += stride)
+    {
+        const Rec a = in[k - 1], b = in[k];
+        if (a.key > b.key || (a.key == b.key && !(a.val < b.val)))
+            atomicAdd(violations, 1ull);
+    }
+}
+
+void sort_selftest(cudaStream_t stream, u64 n, int nbits, int variant, int reps, float *ms_hist, float *ms_pass,
+                   u64 *violations_out, int *npasses_out)
+{
+    const int saved = g_variant;
+    set_sort_variant(variant);
+    Rec *a = nullptr, *b = nullptr;
+    void *ws = nullptr;
+    u64 *d_viol = nullptr;
+    XSB_CUDA(cudaMallocAsync(&a, sizeof(Rec) * n, stream));
+    XSB_CUDA(cudaMallocAsync(&b, sizeof(Rec) * n, stream));
+    XSB_CUDA(cudaMallocAsync(&ws, sort_workspace_bytes(n), stream));
+    XSB_CUDA(cudaMallocAsync(&d_viol, sizeof(u64), stream));
+    XSB_CUDA(cudaMemsetAsync(d_viol, 0, sizeof(u64), stream));
+    const SortPlan plan = make_sort_plan(0, nbits);
+    LaunchCounter lc;
+    StageTimes acc;
+    Rec *res = nullptr;
+    for (int r = 0; r < reps + 1; ++r)
+    {
+        selftest_fill_kernel<<<kNumSM * 8, 256, 0, stream>>>(a, n, nbits, 12345);
+        StageTimer t;
+        res = radix_sort_records(stream, a, b, n, plan, ws, lc, &t);
+        XSB_CUDA(cudaStreamSynchronize(stream));
+        StageTimes st;
+        t.collect(st);
+        if (r > 0)
+        {
+            acc.histogram += st.histogram;
+            acc.sort += st.sort;
+        }
+    }
+    selftest_check_kernel<<<kNumSM * 8, 256, 0, stream>>>(res, n, d_viol);
+    u64 viol = 0;
+    XSB_CUDA(cudaMemcpyAsync(&viol, d_viol, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    XSB_CUDA(cudaStreamSynchronize(stream));
+    cudaFreeAsync(a, stream);
+    cudaFreeAsync(b, stream);
+    cudaFreeAsync(ws, stream);
+    cudaFreeAsync(d_viol, stream);
+    set_sort_variant(saved);
+    *ms_hist = acc.histogram / reps;
+    *ms_pass = acc.sort / reps / std::max(plan.npasses, 1);
+    *violations_out = viol;
+    *npasses_out = plan.npasses;
 }
 
 } // namespace xsb

@@ -202,6 +202,13 @@ int32_t xsb_stream_count_blockrd(int64_t nx, int64_t ny, int64_t nz, int32_t ns,
 int32_t xsb_debug_fetch_staged(xsb_matrix *h, int32_t tid, void *I, void *J, void *V,
                                int32_t *flavour, int64_t capacity, int64_t *count);
 
+/* Tuning/self-test aids: choose the onesweep tile shape; sort n random nbits-wide keys,
+ * report per-pass time and the number of order/stability violations (must be 0). */
+int32_t xsb_debug_set_sort_variant(int32_t variant);
+int32_t xsb_debug_sort_selftest(xsb_matrix *h, int64_t n, int32_t nbits, int32_t variant, int32_t reps,
+                                float *ms_histogram, float *ms_per_pass, int64_t *violations,
+                                int32_t *npasses);
+
 /* ------------------------------------------------------------------ */
 /* streams, timing                                                     */
 /* ------------------------------------------------------------------ */
