@@ -72,6 +72,7 @@ SIGNATURES = {
     "xsb_last_error": (C.c_char_p, [_p]),
     "xsb_reset": (_i32, [_p]),
     "xsb_set_csc": (_i32, [_p, _p, _p, _p]),
+    "xsb_shrink_to_fit": (_i32, [_p]),
     "xsb_size": (_i32, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "xsb_nnz": (_i32, [_p, C.POINTER(_i64)]),
     "xsb_reserve": (_i32, [_p, _i32, _i64]),
@@ -211,6 +212,9 @@ class Handle:
 
     def set_csc(self, colptr, rowval, nzval):
         self._c(lib().xsb_set_csc(self._h, ptr(colptr), ptr(rowval), ptr(nzval)))
+
+    def shrink_to_fit(self):
+        self._c(lib().xsb_shrink_to_fit(self._h))
 
     @property
     def nnz(self) -> int:

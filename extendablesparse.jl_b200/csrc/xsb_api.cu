@@ -152,6 +152,25 @@ struct xsb_matrix
         nzval = nullptr;
         nnz = 0;
     }
+    size_t shrink_surplus_bytes = (size_t)16 << 30;
+    // move rowval/nzval into an allocation of exactly nnz entries
+    void shrink_store()
+    {
+        const size_t rv_bytes = (isz() * (size_t)nnz + 15) & ~(size_t)15;
+        if (!csc_store || csc_store_bytes <= rv_bytes + 8 * (size_t)nnz)
+            return;
+        unsigned char *st = static_cast<unsigned char *>(dalloc(rv_bytes + 8 * (size_t)nnz));
+        if (nnz)
+        {
+            XSB_CUDA(cudaMemcpyAsync(st, rowval, isz() * (size_t)nnz, cudaMemcpyDeviceToDevice, stream));
+            XSB_CUDA(cudaMemcpyAsync(st + rv_bytes, nzval, 8 * (size_t)nnz, cudaMemcpyDeviceToDevice, stream));
+        }
+        dfree(csc_store);
+        csc_store = st;
+        csc_store_bytes = rv_bytes + 8 * (size_t)nnz;
+        rowval = st;
+        nzval = reinterpret_cast<double *>(st + rv_bytes);
+    }
     // make room for `extra` more records in partition t
     void ensure_stage(int t, i64 extra)
     {
@@ -390,20 +409,11 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->nzval = new_nzval;
     h->nnz = nnz_new;
 
-    // shrink an oversized store (duplicate-heavy streams) so HBM is not held hostage
+    // The CSC stays in the (duplicate-count sized) ping-pong buffer: copying it into an exact
+    // allocation costs 32 B per entry of HBM traffic.  Only a large surplus is given back.
     const size_t exact = (h->isz() + 8) * (size_t)nnz_new;
-    if (h->csc_store_bytes > (32u << 20) && h->csc_store_bytes > 2 * exact)
-    {
-        const size_t rv_bytes = (h->isz() * (size_t)nnz_new + 15) & ~(size_t)15;
-        unsigned char *st = static_cast<unsigned char *>(h->dalloc(rv_bytes + 8 * (size_t)nnz_new));
-        XSB_CUDA(cudaMemcpyAsync(st, h->rowval, h->isz() * (size_t)nnz_new, cudaMemcpyDeviceToDevice, s));
-        XSB_CUDA(cudaMemcpyAsync(st + rv_bytes, h->nzval, 8 * (size_t)nnz_new, cudaMemcpyDeviceToDevice, s));
-        h->dfree(h->csc_store);
-        h->csc_store = st;
-        h->csc_store_bytes = rv_bytes + 8 * (size_t)nnz_new;
-        h->rowval = st;
-        h->nzval = reinterpret_cast<double *>(st + rv_bytes);
-    }
+    if (h->csc_store_bytes > exact + h->shrink_surplus_bytes)
+        h->shrink_store();
 
     // the buffer that held the sorted records is recycled as the next staging buffer
     if (a_is_stage0)
@@ -635,6 +645,17 @@ int32_t xsb_set_csc(xsb_matrix *h, const void *colptr, const void *rowval, const
         h->nzval = reinterpret_cast<double *>(st + rv_bytes);
         h->nnz = nnz;
         h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_shrink_to_fit(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        h->shrink_store();
+        if (h->pending() == 0)
+            h->clear_staging(true);
         return XSB_OK;
     });
 }

@@ -58,6 +58,7 @@ constexpr int RD_THREADS = 256;
 constexpr int RD_WARPS = RD_THREADS / 32;
 constexpr int RD_IPT = 8;
 constexpr int RD_TILE = RD_THREADS * RD_IPT;
+constexpr int RD_OVER = 64;
 
 constexpr u64 RS_LOCAL = 1ull << 62;
 constexpr u64 RS_INCL = 2ull << 62;
@@ -211,7 +212,7 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
                    Ti *__restrict__ rowval, double *__restrict__ nzval, u64 *__restrict__ colend,
                    u64 *__restrict__ status, u32 *__restrict__ tile_counter, u64 *__restrict__ d_nnz, u32 ntiles)
 {
-    __shared__ Rec s_rec[RD_TILE];
+    __shared__ Rec s_rec[RD_TILE + RD_OVER]; // tile + look-ahead for the run that crosses the tile's end
     __shared__ u32 s_col[RD_TILE]; // first the head positions, later the columns of the output entries
     __shared__ u32 s_cnt[RD_IPT * RD_WARPS];
     __shared__ u32 s_off[RD_IPT * RD_WARPS];
@@ -233,6 +234,9 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
         if (e < valid)
             s_rec[e] = ld_rec_stream(sorted + tbase + e);
     }
+    const u32 avail = (u32)min((u64)(RD_TILE + RD_OVER), nrec - tbase);
+    if (tid < RD_OVER && RD_TILE + tid < avail)
+        s_rec[RD_TILE + tid] = ld_rec_stream(sorted + tbase + RD_TILE + tid);
     if (tid == 0)
         s_prev = tbase > 0 ? sorted[tbase - 1].key : 0ull;
     __syncthreads();
@@ -280,7 +284,7 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
             {
                 const u32 e0 = s_col[hidx];
                 const bool last = hidx + 1 == nheads;
-                const u32 e1 = last ? valid : s_col[hidx + 1];
+                const u32 e1 = last ? avail : s_col[hidx + 1]; // the last run ends where its key ends
                 const u64 key = s_rec[e0].key;
                 const u64 cr = L.colrow(key);
                 row = (u32)L.row(key);
@@ -288,15 +292,18 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
                 if (SIMPLE)
                 {
                     double acc = 0.0;
-                    for (u32 q = e0; q < e1; ++q)
+                    u32 q = e0;
+                    for (; q < e1; ++q)
                     {
                         const Rec r = s_rec[q];
+                        if (q >= valid && L.colrow(r.key) != cr)
+                            break;
                         const u32 fl = L.flavour(r.key);
                         acc = (fl == FL_OLD) ? r.val : acc + r.val;
                         created |= (fl != FL_UPDATE) | (r.val != 0.0);
                     }
-                    if (last)
-                        for (u64 g = tbase + valid; g < nrec; ++g)
+                    if (last && q == avail) // longer than the look-ahead: rare, walk global memory
+                        for (u64 g = tbase + avail; g < nrec; ++g)
                         { // the tile's last run may continue into the following tiles
                             const Rec r = sorted[g];
                             if (L.colrow(r.key) != cr)
@@ -309,13 +316,16 @@ reduce_emit_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int co
                 else
                 {
                     RunFold f;
-                    for (u32 q = e0; q < e1; ++q)
+                    u32 q = e0;
+                    for (; q < e1; ++q)
                     {
                         const Rec r = s_rec[q];
+                        if (q >= valid && L.colrow(r.key) != cr)
+                            break;
                         f.apply(L.flavour(r.key), L.tid(r.key), r.val, combine);
                     }
-                    if (last)
-                        for (u64 g = tbase + valid; g < nrec; ++g)
+                    if (last && q == avail)
+                        for (u64 g = tbase + avail; g < nrec; ++g)
                         {
                             const Rec r = sorted[g];
                             if (L.colrow(r.key) != cr)

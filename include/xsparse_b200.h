@@ -113,6 +113,11 @@ int32_t xsb_reset(xsb_matrix *h);
  * resident CSC (colptr[n+1], rowval[nnz], nzval[nnz]); pending inserts are dropped. */
 int32_t xsb_set_csc(xsb_matrix *h, const void *colptr, const void *rowval, const void *nzval);
 
+/* After a flush the CSC lives in a buffer sized for the staged insertions (no copy on the
+ * hot path); this moves it into exactly nnz entries and releases idle staging buffers
+ * (the resize! of sparsematrixlnk.jl:380-381). */
+int32_t xsb_shrink_to_fit(xsb_matrix *h);
+
 /* Base.size(ext), SparseArrays.nnz(csc part) */
 int32_t xsb_size(const xsb_matrix *h, int64_t *m, int64_t *n);
 int32_t xsb_nnz(const xsb_matrix *h, int64_t *nnz);
