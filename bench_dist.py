@@ -1,0 +1,175 @@
+"""N>1 arm of bench.py: weak scaling of the partitioned FEM assembly over column-owning ranks.
+
+Global mesh: 128 x 128 x (127*N + 1) nodes (Kuhn 6-tet).  Rank r emits the tetrahedra of its
+127 cube layers (245 805 960 rawupdateindex! calls, the same per-GPU work as the N=1 workload)
+and owns the columns of the z-planes [127 r, 127 (r+1)) (the last rank also owns the top plane).
+Records whose column lies on the interface plane travel to the rank above in one NCCL
+all-to-all-v; every rank then merges into its own CSC slab.  The assembled matrix is left
+sharded (slab-local colptr + global offset); that is what is timed.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+
+def run(args, xsb, rank, world, local):
+    import bench
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from xsparse_b200 import dist as xd
+
+    dev = torch.device("cuda", local)
+    nx = ny = args.mesh
+    layers = args.mesh - 1
+    nz_nodes = layers * world + 1
+    N = nx * ny * nz_nodes
+    plane = nx * ny
+    splits = [plane * layers * r for r in range(world)] + [N]
+    mode = xsb.DETERMINISTIC if args.mode == "deterministic" else xsb.FAST
+    D = xd.DistExtendableSparseMatrix(N, N, splits=splits, device=local)
+    h = D.h
+    h.set_profiling(True)
+    n_ins_rank = xsb.capi.stream_count_p1fem(nx, ny, layers + 1)
+
+    def step():
+        h.reset()
+        h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
+        return D.flush(mode)
+
+    for _ in range(args.warmup):
+        step()
+    h.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches0 = h.kernel_launches
+    stage = {}
+    with bench.ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        h.timer_start()  # CUDA events on the stream the library launches on
+        for _ in range(args.steps):
+            nnz, _ = step()
+            st = h.flush_stats()
+            for k, v in st.items():
+                if k.startswith("ms_"):
+                    stage[k] = stage.get(k, 0.0) + v
+        ms_local = h.timer_stop()
+        torch.cuda.synchronize()
+        dist.barrier()
+        launches_timed = h.kernel_launches - launches0
+        t_end = time.time() + max(0.0, 0.5 - ms_local / 1e3)
+        while time.time() < t_end:
+            step()
+    # max over ranks, on the device clock
+    tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    launches = torch.tensor([launches_timed], dtype=torch.int64, device=dev)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    st = h.flush_stats()
+    ms_step = ms / args.steps
+    value = world * n_ins_rank / (ms_step / 1e3)
+    peak, peak_src = bench.peaks()
+    passes = st["sort_passes"]
+    ms_pass = stage["ms_sort"] / args.steps / max(passes, 1)
+    rec = st["n_inserted"] + st["nnz_old"]
+    pass_bytes = 32 * rec
+    achieved = pass_bytes / (ms_pass / 1e3) / 1e9
+    b_flush = bench.flush_bytes(st["n_inserted"], st["nnz_old"], st["nnz_new"], h.n)
+    ms_flush = stage["ms_total"] / args.steps
+    flush_gbs = b_flush / (ms_flush / 1e3) / 1e9
+
+    e2e = measure_e2e(args, xsb, xd, rank, world, local, mode)
+    clocks = clk.summary()
+    if rank == 0:
+        cfg = bench.workload(args)
+        cfg["workload"] = (f"P1-FEM Laplacian+mass, {nx}x{ny}x{nz_nodes}-node Kuhn mesh sharded over {world} ranks "
+                           f"({layers} cube layers = {n_ins_rank} rawupdateindex! calls per rank), column-slab ownership, "
+                           f"NCCL all-to-all-v of the interface plane, CSC left sharded")
+        cfg["parallelism"] = f"column-slab x{world}"
+        cfg["exchange"] = dict(D.last_exchange)
+        line = {
+            "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass over 16-B records), rank 0",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic,
+                         "peak_source": peak_src, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
+                         "launches_per_step": passes,
+                         "flush": {"algorithmic_bytes": b_flush, "ms": ms_flush, "achieved": flush_gbs,
+                                   "frac": flush_gbs / peak},
+                         "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stage.items())}},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clocks,
+            "nnz_global": int(D.nnz_global), "n_inserted": int(world * n_ins_rank),
+        }
+        print(json.dumps(line))
+    h.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def measure_e2e(args, xsb, xd, rank, world, local, mode):
+    """End to end at N ranks with HOST buffers: every step each rank copies its (I,J,V) stream from
+    pinned host memory, inserts, routes, flushes and reads its CSC slab back to pinned host memory."""
+    import ctypes as C
+
+    emesh = args.e2e_mesh
+    layers = emesh - 1
+    nz_nodes = layers * world + 1
+    N = emesh * emesh * nz_nodes
+    splits = [emesh * emesh * layers * r for r in range(world)] + [N]
+    D = xd.DistExtendableSparseMatrix(N, N, splits=splits, device=local)
+    g = D.h
+    g.emit_p1fem(emesh, emesh, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
+    cnt = g.pending
+    dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dJ = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dV = torch.empty(cnt, dtype=torch.float64, device="cuda")
+    got = C.c_int64(0)
+    c = xsb.capi
+    c.check(c.lib().xsb_debug_fetch_staged(g._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt,
+                                           C.byref(got)), g._h)
+    hI = torch.empty(cnt, dtype=torch.int64, pin_memory=True).copy_(dI)
+    hJ = torch.empty(cnt, dtype=torch.int64, pin_memory=True).copy_(dJ)
+    hV = torch.empty(cnt, dtype=torch.float64, pin_memory=True).copy_(dV)
+    torch.cuda.synchronize()
+    del dI, dJ, dV
+    g.reset()
+    g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
+    nnz, _ = D.flush(mode)
+    ocp = torch.empty(g.n + 1, dtype=torch.int64, pin_memory=True)
+    orv = torch.empty(nnz, dtype=torch.int64, pin_memory=True)
+    onz = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
+
+    def step():
+        g.reset()
+        g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
+        D.flush(mode)
+        g.fetch_csc(ocp, orv, onz)
+
+    step()
+    steps = max(1, min(args.steps, 3))
+    torch.cuda.synchronize()
+    dist.barrier()
+    g.timer_start()
+    for _ in range(steps):
+        step()
+    ms_e2e = g.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ms_e2e / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([cnt, 24 * cnt, 8 * (g.n + 1) + 16 * int(nnz)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    g.close()
+    return {"value": int(tot[0].item()) / (ms / 1e3), "unit": "entries/s", "h2d_bytes_per_step": int(tot[1].item()),
+            "d2h_bytes_per_step": int(tot[2].item()), "ms_per_step": ms,
+            "workload": f"P1-FEM {emesh}x{emesh}x{nz_nodes}-node mesh over {world} ranks, (I,J,V) from pinned host, "
+                        f"CSC slabs read back to host"}

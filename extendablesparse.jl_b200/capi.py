@@ -68,6 +68,10 @@ SIGNATURES = {
     "xsb_version": (_i32, []),
     "xsb_device_count": (_i32, [C.POINTER(_i32)]),
     "xsb_create": (_i32, [_i64, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_p)]),
+    "xsb_create_slab": (_i32, [_i64, _i64, _i32, _i32, C.POINTER(_i64), _i32, _i32, _i32, _i32, C.POINTER(_p)]),
+    "xsb_slab_info": (_i32, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "xsb_route_prepare": (_i32, [_p, _p, _i64, C.POINTER(_i64)]),
+    "xsb_route_finish": (_i32, [_p, _p, _i64]),
     "xsb_destroy": (_i32, [_p]),
     "xsb_last_error": (C.c_char_p, [_p]),
     "xsb_reset": (_i32, [_p]),
@@ -184,10 +188,20 @@ def stream_count_blockrd(nx, ny, nz, ns=4) -> int:
 class Handle:
     """Thin object wrapper of an `xsb_matrix*`; method names follow the C entry points."""
 
-    def __init__(self, m, n, idx_type=I64, index_base=1, n_tid=1, device=0):
+    def __init__(self, m, n, idx_type=I64, index_base=1, n_tid=1, device=0, slab=None):
+        """slab=(n_ranks, rank, col_splits): own columns [col_splits[rank], col_splits[rank+1]) of an m x n matrix."""
         self._h = None
         h = _p()
-        check(lib().xsb_create(m, n, F64, idx_type, index_base, n_tid, device, C.byref(h)))
+        if slab is None:
+            check(lib().xsb_create(m, n, F64, idx_type, index_base, n_tid, device, C.byref(h)))
+            self.n_global, self.col_begin = int(n), 0
+        else:
+            n_ranks, rank, splits = slab
+            arr = (_i64 * (n_ranks + 1))(*[int(x) for x in splits])
+            check(lib().xsb_create_slab(m, n, n_ranks, rank, arr, F64, idx_type, index_base, device, C.byref(h)))
+            self.n_global, self.col_begin = int(n), int(splits[rank])
+            n = int(splits[rank + 1]) - int(splits[rank])
+            self.n_ranks, self.rank = n_ranks, rank
         self._h = h
         self.m, self.n = int(m), int(n)
         self.idx_type, self.index_base, self.n_tid, self.device = idx_type, index_base, n_tid, device
@@ -212,6 +226,15 @@ class Handle:
 
     def set_csc(self, colptr, rowval, nzval):
         self._c(lib().xsb_set_csc(self._h, ptr(colptr), ptr(rowval), ptr(nzval)))
+
+    def route_prepare(self, send_records, capacity):
+        """Bucket the staged records by owner into `send_records` (device int64 tensor, 2 words per record)."""
+        counts = (_i64 * self.n_ranks)()
+        self._c(lib().xsb_route_prepare(self._h, ptr(send_records), capacity, counts))
+        return [int(c) for c in counts]
+
+    def route_finish(self, recv_records, count):
+        self._c(lib().xsb_route_finish(self._h, ptr(recv_records), count))
 
     def shrink_to_fit(self):
         self._c(lib().xsb_shrink_to_fit(self._h))

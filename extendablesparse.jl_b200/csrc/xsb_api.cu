@@ -54,7 +54,11 @@ struct xsb_matrix
 {
     i64 m = 0, n = 0;
     int idx64 = 1, base = 1, n_tid = 1, device = 0;
-    KeyLayout L{};
+    KeyLayout L{};  // layout the flush sorts and reduces on (columns relative to the slab)
+    KeyLayout Ls{}; // layout of staged records before routing (global columns + owner bits); == L without ranks
+    i64 n_global = 0, col_begin = 0; // slab handles own columns [col_begin, col_begin + n) of an m x n_global matrix
+    int nranks = 0, rank = 0;        // nranks == 0: plain single-GPU handle
+    bool routed = false;             // staged records already went through xsb_route_finish
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -131,6 +135,7 @@ struct xsb_matrix
         {
             st.count = 0;
             st.front = 0;
+            routed = false;
             if (release)
             {
                 dfree(st.buf);
@@ -334,6 +339,8 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             *pattern_changed = 0;
         return XSB_OK;
     }
+    REQUIRE(h->nranks == 0 || h->routed, XSB_ESTATE,
+            "slab handle: route the staged records (xsb_route_prepare/xsb_route_finish) before flush");
     cudaStream_t s = h->stream;
     StageTimer timer;
     StageTimer *tp = h->profiling ? &timer : nullptr;
@@ -464,6 +471,7 @@ Rec *begin_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
 {
     check_tid_flavour(h, tid, flavour);
     REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+    REQUIRE(!h->routed, XSB_ESTATE, "routed records are pending: flush before inserting again");
     h->ensure_stage(tid, count);
     Stage &st = h->stage[tid];
     return st.buf + st.front + st.count;
@@ -499,21 +507,34 @@ int32_t xsb_device_count(int32_t *count)
     return XSB_OK;
 }
 
-int32_t xsb_create(int64_t m, int64_t n, int32_t val_type, int32_t idx_type, int32_t index_base, int32_t n_tid,
-                   int32_t device, xsb_matrix **out)
+static int32_t create_impl(int64_t m, int64_t n_global, int32_t nranks, int32_t rank, const int64_t *splits,
+                           int32_t val_type, int32_t idx_type, int32_t index_base, int32_t n_tid, int32_t device,
+                           xsb_matrix **out)
 {
     if (out)
         *out = nullptr;
     xsb_matrix *h = nullptr;
     int32_t rc = guard(nullptr, [&]() -> int32_t {
         REQUIRE(out != nullptr, XSB_EINVAL, "out is NULL");
-        REQUIRE(m >= 1 && n >= 1, XSB_EINVAL, "matrix dimensions must be >= 1");
+        REQUIRE(m >= 1 && n_global >= 1, XSB_EINVAL, "matrix dimensions must be >= 1");
         REQUIRE(val_type == XSB_F64, XSB_EINVAL, "only Float64 values are supported");
         REQUIRE(idx_type == XSB_I32 || idx_type == XSB_I64, XSB_EINVAL, "idx_type must be XSB_I32 or XSB_I64");
         REQUIRE(index_base == 0 || index_base == 1, XSB_EINVAL, "index_base must be 0 or 1");
         REQUIRE(n_tid >= 1 && n_tid <= (1 << 16), XSB_EINVAL, "n_tid must be in 1..65536");
         if (idx_type == XSB_I32)
-            REQUIRE(m < (1ll << 31) - 1 && n < (1ll << 31) - 1, XSB_EINVAL, "dimensions exceed Int32");
+            REQUIRE(m < (1ll << 31) - 1 && n_global < (1ll << 31) - 1, XSB_EINVAL, "dimensions exceed Int32");
+        i64 col_begin = 0, n = n_global;
+        if (nranks > 0)
+        {
+            REQUIRE(nranks <= kMaxRanks, XSB_EINVAL, "at most 16 ranks");
+            REQUIRE(rank >= 0 && rank < nranks && splits, XSB_EINVAL, "bad rank or NULL splits");
+            REQUIRE(n_tid == 1, XSB_EINVAL, "slab handles take one partition buffer per rank");
+            REQUIRE(splits[0] == 0 && splits[nranks] == n_global, XSB_EINVAL, "splits must cover [0, n)");
+            for (int r = 0; r < nranks; ++r)
+                REQUIRE(splits[r] < splits[r + 1], XSB_EINVAL, "every rank must own at least one column");
+            col_begin = splits[rank];
+            n = splits[rank + 1] - splits[rank];
+        }
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0)
@@ -522,22 +543,37 @@ int32_t xsb_create(int64_t m, int64_t n, int32_t val_type, int32_t idx_type, int
             throw ApiError(XSB_ECUDA, "no CUDA device: libxsparse_b200 has no CPU fallback");
         }
         REQUIRE(device >= 0 && device < ndev, XSB_EINVAL, "device ordinal out of range");
-        KeyLayout L;
+        KeyLayout L{};
         L.tidbits = n_tid > 1 ? ceil_log2(n_tid) : 0;
         L.low = 2 + L.tidbits;
         L.rowbits = ceil_log2(m);
         L.colbits = ceil_log2(n);
-        REQUIRE(L.low + L.rowbits + L.colbits <= 64, XSB_EINVAL, "m*n*n_tid does not fit the 64-bit packed key");
-        REQUIRE(L.rowbits <= 32 && L.colbits <= 32, XSB_EINVAL, "dimensions above 2^32 are not supported");
+        KeyLayout Ls = L;
+        if (nranks > 0)
+        {
+            Ls.colbits = ceil_log2(n_global);
+            Ls.ownerbits = ceil_log2(nranks);
+            Ls.nranks = nranks;
+            for (int r = 0; r <= nranks; ++r)
+                Ls.splits[r] = splits[r];
+        }
+        REQUIRE(Ls.low + Ls.rowbits + Ls.colbits + Ls.ownerbits <= 64, XSB_EINVAL,
+                "m*n*n_tid does not fit the 64-bit packed key");
+        REQUIRE(L.rowbits <= 32 && Ls.colbits <= 32, XSB_EINVAL, "dimensions above 2^32 are not supported");
         XSB_CUDA(cudaSetDevice(device));
         h = new xsb_matrix();
         h->m = m;
         h->n = n;
+        h->n_global = n_global;
+        h->col_begin = col_begin;
+        h->nranks = nranks;
+        h->rank = rank;
         h->idx64 = idx_type == XSB_I64;
         h->base = index_base;
         h->n_tid = n_tid;
         h->device = device;
         h->L = L;
+        h->Ls = Ls;
         h->stage.resize((size_t)n_tid);
         XSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
@@ -559,6 +595,92 @@ int32_t xsb_create(int64_t m, int64_t n, int32_t val_type, int32_t idx_type, int
             *out = nullptr;
     }
     return rc;
+}
+
+int32_t xsb_create(int64_t m, int64_t n, int32_t val_type, int32_t idx_type, int32_t index_base, int32_t n_tid,
+                   int32_t device, xsb_matrix **out)
+{
+    return create_impl(m, n, 0, 0, nullptr, val_type, idx_type, index_base, n_tid, device, out);
+}
+
+int32_t xsb_create_slab(int64_t m, int64_t n_global, int32_t n_ranks, int32_t rank, const int64_t *col_splits,
+                        int32_t val_type, int32_t idx_type, int32_t index_base, int32_t device, xsb_matrix **out)
+{
+    if (n_ranks < 1)
+    {
+        g_err = "n_ranks must be >= 1";
+        return XSB_EINVAL;
+    }
+    return create_impl(m, n_global, n_ranks, rank, col_splits, val_type, idx_type, index_base, 1, device, out);
+}
+
+int32_t xsb_slab_info(const xsb_matrix *h, int64_t *col_begin, int64_t *col_end, int64_t *n_global)
+{
+    if (!h)
+        return XSB_EINVAL;
+    if (col_begin)
+        *col_begin = h->col_begin;
+    if (col_end)
+        *col_end = h->col_begin + h->n;
+    if (n_global)
+        *n_global = h->n_global;
+    return XSB_OK;
+}
+
+// Buckets the staged records by owning rank (one stable radix pass on the owner bits) into the
+// caller's send buffer; send_counts[r] = records for rank r, laid out rank after rank.
+int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, int64_t *send_counts)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && send_counts, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(!h->routed, XSB_ESTATE, "staged records were already routed");
+        Stage &st = h->stage[0];
+        REQUIRE(capacity >= st.count, XSB_EINVAL, "send buffer too small");
+        REQUIRE(st.count == 0 || (send_records && is_device_ptr(send_records)), XSB_EINVAL,
+                "send buffer must be device memory");
+        u64 counts[kRadix] = {0};
+        if (st.count > 0)
+        {
+            void *ws = h->dalloc(sort_workspace_bytes((u64)st.count));
+            partition_records(h->stream, st.buf + st.front, static_cast<Rec *>(send_records), (u64)st.count,
+                              h->Ls.low + h->Ls.rowbits + h->Ls.colbits, h->Ls.ownerbits, ws, h->lc, counts);
+            h->dfree(ws);
+        }
+        for (int r = 0; r < h->nranks; ++r)
+            send_counts[r] = (int64_t)counts[r];
+        h->clear_staging(false);
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+// Takes the records this rank received (source rank after source rank, each in stream order),
+// rewrites them into the slab's key layout and stages them for xsb_flush.
+int32_t xsb_route_finish(xsb_matrix *h, const void *recv_records, int64_t count)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+        REQUIRE(h->pending() == 0 || h->routed, XSB_ESTATE, "unrouted records are still staged");
+        REQUIRE(count == 0 || (recv_records && is_device_ptr(recv_records)), XSB_EINVAL,
+                "receive buffer must be device memory");
+        if (count > 0)
+        {
+            h->ensure_stage(0, count);
+            Stage &st = h->stage[0];
+            write_scalar(h, 1, ~0ull);
+            relayout_records(h->stream, static_cast<const Rec *>(recv_records), count, h->Ls, h->L, h->col_begin,
+                             h->n, st.buf + st.front + st.count, h->d_scal + 1, h->lc);
+            const u64 bad = read_scalar(h, 1);
+            REQUIRE(bad == ~0ull, XSB_EBOUNDS,
+                    "record " + std::to_string(bad) + " of the received buffer is not owned by this rank");
+            st.count += count;
+        }
+        h->routed = true;
+        return XSB_OK;
+    });
 }
 
 int32_t xsb_destroy(xsb_matrix *h)
@@ -704,7 +826,7 @@ int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *
         DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count), dV(h, V, 8 * (size_t)count);
         write_scalar(h, 1, ~0ull);
         pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
-                     h->n, h->L, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc);
+                     h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc);
         const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
@@ -928,11 +1050,11 @@ int32_t xsb_emit_fdrand_range(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny
         REQUIRE(h, XSB_EINVAL, "NULL handle");
         REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, XSB_EINVAL, "grid dimensions must be >= 1");
         const i64 N = nx * ny * nz;
-        REQUIRE(h->m == N && h->n == N, XSB_ESIZE, "Matrix size mismatch"); // sprand.jl:66-68
+        REQUIRE(h->m == N && h->n_global == N, XSB_ESIZE, "Matrix size mismatch"); // sprand.jl:66-68
         REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= N, XSB_EINVAL, "bad node range");
         const i64 count = fdrand_prefix(nx, ny, nz, l_end) - fdrand_prefix(nx, ny, nz, l_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        emit_fdrand(h->stream, nx, ny, nz, seed, ones, h->L, (u32)tid, (u32)flavour, l_begin, l_end, dst, h->lc);
+        emit_fdrand(h->stream, nx, ny, nz, seed, ones, h->Ls, (u32)tid, (u32)flavour, l_begin, l_end, dst, h->lc);
         end_emit(h, tid, flavour, count);
         return XSB_OK;
     });
@@ -951,11 +1073,11 @@ int32_t xsb_emit_p1fem_range(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t ny
         REQUIRE(h, XSB_EINVAL, "NULL handle");
         REQUIRE(nxn >= 2 && nyn >= 2 && nzn >= 2, XSB_EINVAL, "mesh needs at least 2 nodes per direction");
         const i64 N = nxn * nyn * nzn;
-        REQUIRE(h->m == N && h->n == N, XSB_ESIZE, "Matrix size mismatch");
+        REQUIRE(h->m == N && h->n_global == N, XSB_ESIZE, "Matrix size mismatch");
         REQUIRE(0 <= cz_begin && cz_begin <= cz_end && cz_end <= nzn - 1, XSB_EINVAL, "bad cube-layer range");
         const i64 count = 20 * 6 * (nxn - 1) * (nyn - 1) * (cz_end - cz_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        emit_p1fem(h->stream, nxn, nyn, nzn, h->L, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc);
+        emit_p1fem(h->stream, nxn, nyn, nzn, h->Ls, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc);
         end_emit(h, tid, flavour, count);
         return XSB_OK;
     });
@@ -973,10 +1095,10 @@ int32_t xsb_emit_blockrd(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int
         REQUIRE(h, XSB_EINVAL, "NULL handle");
         REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && ns >= 1 && ns <= 16, XSB_EINVAL, "bad grid or species count");
         const i64 N = nx * ny * nz * ns;
-        REQUIRE(h->m == N && h->n == N, XSB_ESIZE, "Matrix size mismatch");
+        REQUIRE(h->m == N && h->n_global == N, XSB_ESIZE, "Matrix size mismatch");
         const i64 count = blockrd_count(nx, ny, nz, ns);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        emit_blockrd(h->stream, nx, ny, nz, ns, seed, h->L, (u32)tid, (u32)flavour, dst, h->lc);
+        emit_blockrd(h->stream, nx, ny, nz, ns, seed, h->Ls, (u32)tid, (u32)flavour, dst, h->lc);
         end_emit(h, tid, flavour, count);
         return XSB_OK;
     });
@@ -997,7 +1119,7 @@ int32_t xsb_debug_fetch_staged(xsb_matrix *h, int32_t tid, void *I, void *J, voi
             return XSB_OK;
         const size_t c = (size_t)st.count;
         DevOut dI(h, I, h->isz() * c), dJ(h, J, h->isz() * c), dV(h, V, 8 * c), dF(h, flavour, 4 * c);
-        unpack_records(h->stream, st.buf + st.front, st.count, h->idx64, h->base, h->L, dI.ptr, dJ.ptr,
+        unpack_records(h->stream, st.buf + st.front, st.count, h->idx64, h->base, h->routed ? h->L : h->Ls, dI.ptr, dJ.ptr,
                        static_cast<double *>(dV.ptr), static_cast<int *>(dF.ptr), h->lc);
         dI.finish();
         dJ.finish();

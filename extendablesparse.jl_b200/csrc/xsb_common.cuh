@@ -31,18 +31,36 @@ enum : u32
     FL_OLD = 3 // entry of the resident CSC, placed ahead of all staged entries
 };
 
+constexpr int kMaxRanks = 16;
+
 struct KeyLayout
 {
     int low;     // 2 + tidbits
     int tidbits; // bits of the partition id
     int rowbits;
     int colbits;
+    // Multi-GPU staging layout only: the rank that owns the column rides in the bits above
+    // the column ([owner:ownerbits] on top), so routing is one radix pass on those bits.
+    int ownerbits;
+    int nranks;
+    i64 splits[kMaxRanks + 1]; // rank r owns columns [splits[r], splits[r+1]), 0-based
     __host__ __device__ __forceinline__ u64 pack(u64 col, u64 row, u32 tid, u32 fl) const
     {
-        return (col << (rowbits + low)) | (row << low) | ((u64)tid << 2) | (u64)fl;
+        u64 k = (col << (rowbits + low)) | (row << low) | ((u64)tid << 2) | (u64)fl;
+        if (ownerbits)
+        {
+            int o = 0;
+            while (o + 1 < nranks && (i64)col >= splits[o + 1])
+                ++o;
+            k |= (u64)o << (low + rowbits + colbits);
+        }
+        return k;
     }
     __host__ __device__ __forceinline__ u64 colrow(u64 key) const { return key >> low; }
-    __host__ __device__ __forceinline__ u64 col(u64 key) const { return key >> (rowbits + low); }
+    __host__ __device__ __forceinline__ u64 col(u64 key) const
+    {
+        return (key >> (rowbits + low)) & ((1ull << colbits) - 1ull);
+    }
     __host__ __device__ __forceinline__ u64 row(u64 key) const
     {
         return (key >> low) & ((1ull << rowbits) - 1ull);

@@ -88,6 +88,39 @@ void unpack_records(cudaStream_t stream, const Rec *in, i64 count, int idx64, in
     XSB_CUDA(cudaGetLastError());
 }
 
+// Records that arrived from other ranks (staging layout, global column) -> this slab's layout
+// (column relative to the slab, owner bits dropped, fewer key bits to sort).
+__global__ void __launch_bounds__(256)
+relayout_kernel(const Rec *__restrict__ in, i64 count, KeyLayout src, KeyLayout dst, i64 col_begin, i64 ncols,
+                Rec *__restrict__ out, u64 *__restrict__ d_err)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        Rec r = ld_rec_stream(in + k);
+        const i64 c = (i64)src.col(r.key) - col_begin;
+        if (c < 0 || c >= ncols)
+        {
+            atomicMin(d_err, (u64)k); // a record routed to the wrong owner
+            continue;
+        }
+        r.key = dst.pack((u64)c, src.row(r.key), src.tid(r.key), src.flavour(r.key));
+        st_rec(out + k, r);
+    }
+}
+
+void relayout_records(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &src, const KeyLayout &dst,
+                      i64 col_begin, i64 ncols, Rec *out, u64 *d_err, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    const int threads = 256;
+    const int blocks = (int)std::min<i64>((count + threads - 1) / threads, (i64)kNumSM * 16);
+    relayout_kernel<<<blocks, threads, 0, stream>>>(in, count, src, dst, col_begin, ncols, out, d_err);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------
 // counter-based random numbers: Philox4x32-10, u = (w1:w0 >> 11) * 2^-53
 // ------------------------------------------------------------------------

@@ -399,6 +399,70 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
     return src;
 }
 
+// Stable partition of n records by key bits [shift, shift+bits) into `out` (one onesweep pass);
+// counts_host[d] receives the number of records of digit d.  Used to bucket staged records by
+// owning rank before the all-to-all (the digit histogram doubles as the send counts).
+void partition_records(cudaStream_t stream, const Rec *in, Rec *out, u64 n, int shift, int bits, void *workspace,
+                       LaunchCounter &lc, u64 *counts_host)
+{
+    const int nb = 1 << bits;
+    for (int d = 0; d < nb; ++d)
+        counts_host[d] = 0;
+    if (n == 0)
+        return;
+    SortPlan plan{};
+    plan.npasses = 1;
+    plan.shift[0] = shift;
+    plan.bits[0] = bits;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    u64 *ghist = reinterpret_cast<u64 *>(ws);
+    XSB_CUDA(cudaMemsetAsync(ghist, 0, sizeof(u64) * kMaxPasses * kRadix, stream));
+    const u64 want = (n + HIST_THREADS * 8 - 1) / (HIST_THREADS * 8);
+    const int blocks = (int)std::min<u64>(std::max<u64>(want, 1), (u64)kNumSM * 4);
+    histogram_kernel<<<blocks, HIST_THREADS, 0, stream>>>(in, n, plan, ghist);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+    std::vector<u64> h((size_t)nb);
+    XSB_CUDA(cudaMemcpyAsync(h.data(), ghist, sizeof(u64) * nb, cudaMemcpyDeviceToHost, stream));
+    XSB_CUDA(cudaStreamSynchronize(stream));
+    for (int d = 0; d < nb; ++d)
+        counts_host[d] = h[d];
+    histogram_scan_kernel<<<1, kRadix, 0, stream>>>(ghist, 1);
+    lc.add();
+    const OnesweepVariant &var = kVariants[g_variant];
+    static bool attr_set[kNumVariants] = {};
+    if (!attr_set[g_variant])
+    {
+        XSB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(var.fn),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var.tile * sizeof(Rec))));
+        attr_set[g_variant] = true;
+    }
+    const u64 portion = sort_portion(var.tile);
+    u64 *gnext0 = ghist + kMaxPasses * kRadix;
+    u64 *gnext1 = gnext0 + kRadix;
+    u32 *counter = reinterpret_cast<u32 *>(gnext1 + kRadix);
+    u32 *status = counter + 64;
+    const u64 *gbase = ghist;
+    u64 *gn[2] = {gnext0, gnext1};
+    int flip = 0;
+    for (u64 off = 0; off < n; off += portion)
+    {
+        const u32 cnt = (u32)std::min<u64>(portion, n - off);
+        const u32 ntiles = (cnt + var.tile - 1) / var.tile;
+        const bool more = off + portion < n;
+        XSB_CUDA(cudaMemsetAsync(counter, 0, 256 + sizeof(u32) * (size_t)ntiles * nb, stream));
+        var.fn<<<ntiles, var.threads, var.tile * sizeof(Rec), stream>>>(in + off, out, cnt, ntiles, shift, bits, gbase,
+                                                                        more ? gn[flip] : nullptr, status, counter);
+        lc.add();
+        if (more)
+        {
+            gbase = gn[flip];
+            flip ^= 1;
+        }
+    }
+    XSB_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------
 // self test / micro benchmark of the sort (random keys, stability checked)
 // ------------------------------------------------------------------------

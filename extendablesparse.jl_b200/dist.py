@@ -1,0 +1,108 @@
+"""Column-slab multi-GPU assembly: one process per GPU, torch.distributed for the exchange.
+
+Rank r owns the contiguous column slab [splits[r], splits[r+1]).  Every rank stages the
+insertions it generates (any column), buckets them by owner with one radix pass on the GPU
+(xsb_route_prepare), the buckets travel with ONE all-to-all-v (NCCL over NVLink), and every
+rank merges what it received into its own CSC slab (xsb_route_finish + xsb_flush).  Received
+buckets are concatenated in source-rank order and each bucket is in stream order, so the
+deterministic fold runs in (source rank, stream) order -- the distributed result equals the
+serial reference applied to the rank-ordered concatenation of the ranks' streams.
+
+Reference analogue: the per-partition buffers of GenericMTExtendableSparseMatrixCSC
+(genericmtextendablesparsematrixcsc.jl:45-51) summed in partition order
+(sparsematrixdilnkc.jl:416-426).  The reference itself is single-process.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def uniform_splits(n: int, world: int) -> List[int]:
+    """Contiguous column slabs of (almost) equal width."""
+    return [(n * r) // world for r in range(world)] + [n]
+
+
+def exchange_records(send: torch.Tensor, send_counts: Sequence[int], group=None) -> Tuple[torch.Tensor, List[int]]:
+    """All-to-all-v of 16-byte records (2 int64 words each).  `send` holds the buckets rank after
+    rank; returns the received records (source rank after source rank) and the per-source counts."""
+    world = dist.get_world_size(group)
+    assert len(send_counts) == world
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.cpu().tolist()]
+    recv = torch.empty(2 * sum(recv_counts), dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(recv, send[: 2 * sum(send_counts)], output_split_sizes=[2 * c for c in recv_counts],
+                           input_split_sizes=[2 * int(c) for c in send_counts], group=group)
+    return recv, recv_counts
+
+
+def slab_offsets(nnz_local: int, device, group=None) -> Tuple[int, int]:
+    """(entries owned by lower ranks, total entries): the shift that turns a slab's colptr into the
+    global colptr (8 bytes per rank on the wire)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = torch.tensor([nnz_local], dtype=torch.int64, device=device)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    counts = [int(t.item()) for t in allv]
+    return sum(counts[:rank]), sum(counts)
+
+
+class DistExtendableSparseMatrix:
+    """ExtendableSparseMatrix sharded by column ownership over the ranks of a process group.
+
+    `backend` is the per-rank slab object; the product backend is capi.Handle in slab mode
+    (libxsparse_b200).  It must offer: pending, route_prepare(send, capacity) -> counts,
+    route_finish(recv, count), flush(mode) -> (nnz, changed), synchronize().
+    """
+
+    def __init__(self, m: int, n: int, splits: Sequence[int] | None = None, group=None, device=None, backend=None,
+                 idx_type=None, index_base: int = 1):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.m, self.n = int(m), int(n)
+        self.splits = list(splits) if splits is not None else uniform_splits(self.n, self.world)
+        assert len(self.splits) == self.world + 1 and self.splits[0] == 0 and self.splits[-1] == self.n
+        if backend is None:
+            from . import capi
+
+            dev = torch.cuda.current_device() if device is None else int(device)
+            backend = capi.Handle(self.m, self.n, capi.I64 if idx_type is None else idx_type, index_base, 1, dev,
+                                  slab=(self.world, self.rank, self.splits))
+            self.device = torch.device("cuda", dev)
+        else:
+            self.device = torch.device("cpu") if device is None else device
+        self.h = backend
+        self.col_begin, self.col_end = self.splits[self.rank], self.splits[self.rank + 1]
+        self.nnz_offset = 0
+        self.nnz_global = 0
+        self.last_exchange = {"sent_off_rank": 0, "received": 0}
+
+    # insertion: global (i,j) on any rank
+    def insert_batch(self, I, J, V, flavour=0):
+        self.h.insert_batch(I, J, V, flavour)
+
+    def flush(self, mode=0):
+        """Route, exchange, merge.  Returns (local nnz, pattern changed anywhere)."""
+        cnt = int(self.h.pending)
+        send = torch.empty(2 * max(cnt, 1), dtype=torch.int64, device=self.device)
+        counts = self.h.route_prepare(send, cnt)
+        recv, rcounts = exchange_records(send, counts, self.group)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        self.h.route_finish(recv, sum(rcounts))
+        nnz, changed = self.h.flush(mode)
+        self.nnz_offset, self.nnz_global = slab_offsets(nnz, self.device, self.group)
+        flag = torch.tensor([int(changed)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received": sum(rcounts)}
+        return nnz, bool(flag.item())
+
+    def global_colptr(self, local_colptr):
+        """Slab colptr (slab_width+1 entries) shifted to index the global rowval/nzval arrays."""
+        return local_colptr + self.nnz_offset

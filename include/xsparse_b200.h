@@ -158,6 +158,26 @@ int32_t xsb_get_values(xsb_matrix *h, const void *I, const void *J, void *V_out,
 int32_t xsb_zero_values(xsb_matrix *h);
 
 /* ------------------------------------------------------------------ */
+/* multi-GPU: column-slab ownership, one process (and handle) per GPU  */
+/* ------------------------------------------------------------------ */
+/* Rank `rank` of `n_ranks` owns columns [col_splits[rank], col_splits[rank+1]) (0-based) of an
+ * m x n_global matrix.  Insertions and emitters take GLOBAL indices on any rank; the resident
+ * CSC, xsb_flush and xsb_fetch_csc work on the owned slab (colptr has slab_width+1 entries,
+ * row indices stay global).  The reference has no counterpart (single process); its
+ * per-partition analogue is genericmtextendablesparsematrixcsc.jl:45-51 /
+ * sparsematrixdilnkc.jl:416-426, whose partition order becomes the source-rank order here. */
+int32_t xsb_create_slab(int64_t m, int64_t n_global, int32_t n_ranks, int32_t rank,
+                        const int64_t *col_splits, int32_t val_type, int32_t idx_type,
+                        int32_t index_base, int32_t device, xsb_matrix **out);
+int32_t xsb_slab_info(const xsb_matrix *h, int64_t *col_begin, int64_t *col_end, int64_t *n_global);
+/* Step 1: bucket the staged records by owning rank into `send_records` (device, 16 B each,
+ * capacity >= xsb_pending); send_counts[n_ranks] (host) receives the bucket sizes.
+ * Step 2 (caller): all-to-all-v of the buckets (NCCL), received buffers concatenated in
+ * source-rank order.  Step 3: hand the received records over; then xsb_flush. */
+int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, int64_t *send_counts);
+int32_t xsb_route_finish(xsb_matrix *h, const void *recv_records, int64_t count);
+
+/* ------------------------------------------------------------------ */
 /* values-only re-assembly into a frozen pattern (Newton / transient loops) */
 /* ------------------------------------------------------------------ */
 /* Records, for an insertion stream (I[k],J[k]), the nzval slot of every entry
