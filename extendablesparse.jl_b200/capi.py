@@ -55,6 +55,7 @@ class FlushStats(C.Structure):
         ("ms_reduce", C.c_float),
         ("ms_colptr", C.c_float),
         ("ms_other", C.c_float),
+        ("ms_host_alloc", C.c_float),
     ]
 
     def as_dict(self):

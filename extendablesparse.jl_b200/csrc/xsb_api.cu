@@ -3,6 +3,7 @@
 #include "../../include/xsparse_b200.h"
 #include "xsb_internal.h"
 
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -88,13 +89,16 @@ struct xsb_matrix
     xsb_flush_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+    float alloc_ms = 0.f; // host time spent inside cudaMallocAsync (reset per flush)
     size_t isz() const { return idx64 ? 8 : 4; }
     void *dalloc(size_t bytes)
     {
         void *p = nullptr;
         if (bytes == 0)
             bytes = 16;
+        const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        alloc_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (e != cudaSuccess)
         {
             cudaGetLastError();
@@ -328,6 +332,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     REQUIRE(combine == XSB_COMBINE_SEED || combine == XSB_COMBINE_ADD, XSB_EINVAL, "unknown combine mode");
     const i64 n_ins = h->pending();
     h->lc.in_flush = 0;
+    h->alloc_ms = 0.f;
     std::memset(&h->stats, 0, sizeof(h->stats));
     h->stats.nnz_old = h->nnz;
     h->stats.nnz_new = h->nnz;
@@ -442,6 +447,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.sort_passes = plan.npasses;
     h->stats.sort_bits = h->L.sortbits();
     h->stats.kernel_launches = h->lc.in_flush;
+    h->stats.ms_host_alloc = h->alloc_ms;
     if (tp)
     {
         XSB_CUDA(cudaEventRecord(e1, s));
@@ -671,9 +677,15 @@ int32_t xsb_route_finish(xsb_matrix *h, const void *recv_records, int64_t count)
             h->ensure_stage(0, count);
             Stage &st = h->stage[0];
             write_scalar(h, 1, ~0ull);
+            write_scalar(h, 5, 0ull);
             relayout_records(h->stream, static_cast<const Rec *>(recv_records), count, h->Ls, h->L, h->col_begin,
-                             h->n, st.buf + st.front + st.count, h->d_scal + 1, h->lc);
+                             h->n, st.buf + st.front + st.count, h->d_scal + 1, h->d_scal + 5, h->lc);
             const u64 bad = read_scalar(h, 1);
+            if (h->h_scal[5] == 0ull)
+                XSB_CUDA(cudaMemcpyAsync(h->h_scal + 5, h->d_scal + 5, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+            h->sync();
+            if (h->h_scal[5] != 0ull)
+                h->has_assign = true; // the received stream holds A[i,j]=v records: ordered fold needed
             REQUIRE(bad == ~0ull, XSB_EBOUNDS,
                     "record " + std::to_string(bad) + " of the received buffer is not owned by this rank");
             st.count += count;

@@ -80,7 +80,7 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
 void partition_records(cudaStream_t stream, const Rec *in, Rec *out, u64 n, int shift, int bits, void *workspace,
                        LaunchCounter &lc, u64 *counts_host);
 void relayout_records(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &src, const KeyLayout &dst,
-                      i64 col_begin, i64 ncols, Rec *out, u64 *d_err, LaunchCounter &lc);
+                      i64 col_begin, i64 ncols, Rec *out, u64 *d_err, u64 *d_has_assign, LaunchCounter &lc);
 void set_sort_variant(int v);
 int get_sort_variant();
 void sort_selftest(cudaStream_t stream, u64 n, int nbits, int variant, int reps, float *ms_hist, float *ms_pass,

@@ -2,11 +2,12 @@
 
 Rank r owns the contiguous column slab [splits[r], splits[r+1]).  Every rank stages the
 insertions it generates (any column), buckets them by owner with one radix pass on the GPU
-(xsb_route_prepare), the buckets travel with ONE all-to-all-v (NCCL over NVLink), and every
-rank merges what it received into its own CSC slab (xsb_route_finish + xsb_flush).  Received
-buckets are concatenated in source-rank order and each bucket is in stream order, so the
-deterministic fold runs in (source rank, stream) order -- the distributed result equals the
-serial reference applied to the rank-ordered concatenation of the ranks' streams.
+(xsb_route_prepare), the off-rank buckets travel with ONE all-to-all-v (NCCL over NVLink; the
+rank's own bucket never leaves its HBM), and every rank merges what it holds into its own CSC
+slab (xsb_route_finish per source in rank order, then xsb_flush).  Buckets are ingested in
+source-rank order and each bucket is in stream order, so the deterministic fold runs in
+(source rank, stream) order -- the distributed result equals the serial reference applied to
+the rank-ordered concatenation of the ranks' streams.
 
 Reference analogue: the per-partition buffers of GenericMTExtendableSparseMatrixCSC
 (genericmtextendablesparsematrixcsc.jl:45-51) summed in partition order
@@ -25,18 +26,29 @@ def uniform_splits(n: int, world: int) -> List[int]:
     return [(n * r) // world for r in range(world)] + [n]
 
 
-def exchange_records(send: torch.Tensor, send_counts: Sequence[int], group=None) -> Tuple[torch.Tensor, List[int]]:
-    """All-to-all-v of 16-byte records (2 int64 words each).  `send` holds the buckets rank after
-    rank; returns the received records (source rank after source rank) and the per-source counts."""
+def exchange_off_rank(send: torch.Tensor, send_counts: Sequence[int], rank: int, group=None
+                      ) -> Tuple[torch.Tensor, List[int]]:
+    """All-to-all-v of the OFF-RANK buckets of 16-byte records (2 int64 words each).
+
+    `send` holds the buckets rank after rank (the own bucket included, it stays where it is).
+    Returns the received records, source rank after source rank (own rank: nothing), and the
+    per-source record counts (own rank: 0)."""
     world = dist.get_world_size(group)
     assert len(send_counts) == world
-    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
+    off = [int(c) if r != rank else 0 for r, c in enumerate(send_counts)]
+    sc = torch.tensor(off, dtype=torch.int64, device=send.device)
     rc = torch.empty(world, dtype=torch.int64, device=send.device)
     dist.all_to_all_single(rc, sc, group=group)
     recv_counts = [int(x) for x in rc.cpu().tolist()]
+    # the off-rank buckets, packed contiguously (they are the small part: interface entries)
+    starts = [0]
+    for c in send_counts:
+        starts.append(starts[-1] + int(c))
+    parts = [send[2 * starts[r]: 2 * starts[r + 1]] for r in range(world) if r != rank and send_counts[r] > 0]
+    packed = torch.cat(parts) if parts else send[:0]
     recv = torch.empty(2 * sum(recv_counts), dtype=torch.int64, device=send.device)
-    dist.all_to_all_single(recv, send[: 2 * sum(send_counts)], output_split_sizes=[2 * c for c in recv_counts],
-                           input_split_sizes=[2 * int(c) for c in send_counts], group=group)
+    dist.all_to_all_single(recv, packed, output_split_sizes=[2 * c for c in recv_counts],
+                           input_split_sizes=[2 * c for c in off], group=group)
     return recv, recv_counts
 
 
@@ -57,7 +69,7 @@ class DistExtendableSparseMatrix:
 
     `backend` is the per-rank slab object; the product backend is capi.Handle in slab mode
     (libxsparse_b200).  It must offer: pending, route_prepare(send, capacity) -> counts,
-    route_finish(recv, count), flush(mode) -> (nnz, changed), synchronize().
+    route_finish(records, count) (appending), flush(mode) -> (nnz, changed).
     """
 
     def __init__(self, m: int, n: int, splits: Sequence[int] | None = None, group=None, device=None, backend=None,
@@ -81,26 +93,42 @@ class DistExtendableSparseMatrix:
         self.col_begin, self.col_end = self.splits[self.rank], self.splits[self.rank + 1]
         self.nnz_offset = 0
         self.nnz_global = 0
-        self.last_exchange = {"sent_off_rank": 0, "received": 0}
+        self.last_exchange = {"sent_off_rank": 0, "received_off_rank": 0, "kept": 0}
+        self._send = None
 
     # insertion: global (i,j) on any rank
     def insert_batch(self, I, J, V, flavour=0):
         self.h.insert_batch(I, J, V, flavour)
 
+    def _send_buffer(self, records: int) -> torch.Tensor:
+        words = 2 * max(records, 1)
+        if self._send is None or self._send.numel() < words:
+            self._send = torch.empty(words, dtype=torch.int64, device=self.device)
+        return self._send
+
     def flush(self, mode=0):
-        """Route, exchange, merge.  Returns (local nnz, pattern changed anywhere)."""
+        """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank)."""
         cnt = int(self.h.pending)
-        send = torch.empty(2 * max(cnt, 1), dtype=torch.int64, device=self.device)
+        send = self._send_buffer(cnt)
         counts = self.h.route_prepare(send, cnt)
-        recv, rcounts = exchange_records(send, counts, self.group)
+        recv, rcounts = exchange_off_rank(send, counts, self.rank, self.group)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
-        self.h.route_finish(recv, sum(rcounts))
+        # ingest in source-rank order; the own bucket is read straight from the send buffer
+        own_start = sum(counts[: self.rank])
+        pos = 0
+        for src in range(self.world):
+            if src == self.rank:
+                self.h.route_finish(send[2 * own_start: 2 * (own_start + counts[src])], counts[src])
+            else:
+                self.h.route_finish(recv[2 * pos: 2 * (pos + rcounts[src])], rcounts[src])
+                pos += rcounts[src]
         nnz, changed = self.h.flush(mode)
         self.nnz_offset, self.nnz_global = slab_offsets(nnz, self.device, self.group)
         flag = torch.tensor([int(changed)], dtype=torch.int64, device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-        self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received": sum(rcounts)}
+        self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received_off_rank": sum(rcounts),
+                              "kept": counts[self.rank]}
         return nnz, bool(flag.item())
 
     def global_colptr(self, local_colptr):

@@ -90,6 +90,7 @@ typedef struct xsb_flush_stats
     float ms_reduce;          /* segmented duplicate reduction + CSC emit */
     float ms_colptr;          /* colptr scan                           */
     float ms_other;           /* buffer management, shrink copy        */
+    float ms_host_alloc;      /* host wall time spent in device allocations during the flush */
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */

@@ -54,7 +54,7 @@ class OracleSlabBackend:
             i, j = ij % self.m + 1, ij // self.m + 1
             assert self.col_begin < j <= self.col_begin + self.width, "record routed to the wrong owner"
             out.append((i, j - self.col_begin, float(np.int64(buf[2 * k + 1]).view(np.float64)), fl))
-        self.routed = out
+        self.routed = (self.routed or []) + out  # appends: one call per source rank, in rank order
 
     def flush(self, mode=0):
         before = self.A.nnz
@@ -158,7 +158,9 @@ def test_distributed_assembly_matches_serial(oracle, world, splits):
             assert changed is True
             off += nnz
             sent += ex["sent_off_rank"]
-            recv += ex["received"]
+            recv += ex["received_off_rank"]
+            kept = ex["kept"] + (0 if r else 0)
+            assert kept + ex["sent_off_rank"] == len(got[r][0][splice][2])
         assert off == len(nz)
         total = sum(len(got[r][0][splice][2]) for r in range(world))
-        assert recv == total and 0 < sent < total
+        assert recv == sent and 0 < sent < total  # the own bucket never travels
