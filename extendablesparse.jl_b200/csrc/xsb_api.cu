@@ -7,6 +7,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 using namespace xsb;
@@ -90,14 +92,40 @@ struct xsb_matrix
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     float alloc_ms = 0.f; // host time spent inside cudaMallocAsync (reset per flush)
+    static constexpr size_t kBigBytes = (size_t)32 << 20;
+    std::unordered_map<void *, size_t> big_live;         // large allocations currently handed out
+    std::vector<std::pair<void *, size_t>> big_cache;    // large allocations waiting for reuse
     size_t isz() const { return idx64 ? 8 : 4; }
     void *dalloc(size_t bytes)
     {
         void *p = nullptr;
         if (bytes == 0)
             bytes = 16;
+        if (bytes >= kBigBytes)
+        { // large buffers (staging, sort scratch, CSC store) rotate through a per-handle cache:
+          // in a steady assembly loop a flush allocates nothing (measured: the CUDA pool re-maps
+          // gigabytes per flush once small allocations have split its free blocks)
+            int best = -1;
+            for (int k = 0; k < (int)big_cache.size(); ++k)
+                if (big_cache[k].second >= bytes && big_cache[k].second <= 4 * bytes &&
+                    (best < 0 || big_cache[k].second < big_cache[best].second))
+                    best = k;
+            if (best >= 0)
+            {
+                p = big_cache[best].first;
+                big_live[p] = big_cache[best].second;
+                big_cache.erase(big_cache.begin() + best);
+                return p;
+            }
+        }
         const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        if (e == cudaErrorMemoryAllocation && !big_cache.empty())
+        { // give the cache back and retry once
+            cudaGetLastError();
+            release_cache();
+            e = cudaMallocAsync(&p, bytes, stream);
+        }
         alloc_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (e != cudaSuccess)
         {
@@ -106,12 +134,37 @@ struct xsb_matrix
                            std::string("device allocation of ") + std::to_string(bytes) +
                                " bytes failed: " + cudaGetErrorString(e));
         }
+        if (bytes >= kBigBytes)
+            big_live[p] = bytes;
         return p;
     }
     void dfree(void *p)
     {
-        if (p)
+        if (!p)
+            return;
+        auto it = big_live.find(p);
+        if (it == big_live.end())
+        {
             cudaFreeAsync(p, stream);
+            return;
+        }
+        big_cache.emplace_back(p, it->second);
+        big_live.erase(it);
+        if (big_cache.size() > 6)
+        { // keep the cache bounded: drop the smallest buffer
+            int k = 0;
+            for (int q = 1; q < (int)big_cache.size(); ++q)
+                if (big_cache[q].second < big_cache[k].second)
+                    k = q;
+            cudaFreeAsync(big_cache[k].first, stream);
+            big_cache.erase(big_cache.begin() + k);
+        }
+    }
+    void release_cache()
+    {
+        for (auto &b : big_cache)
+            cudaFreeAsync(b.first, stream);
+        big_cache.clear();
     }
     void sync() { XSB_CUDA(cudaStreamSynchronize(stream)); }
     i64 pending() const
@@ -707,6 +760,7 @@ int32_t xsb_destroy(xsb_matrix *h)
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
     h->dfree(h->d_scal);
+    h->release_cache();
     if (h->h_scal)
         cudaFreeHost(h->h_scal);
     if (h->ev0)
@@ -790,6 +844,7 @@ int32_t xsb_shrink_to_fit(xsb_matrix *h)
         h->shrink_store();
         if (h->pending() == 0)
             h->clear_staging(true);
+        h->release_cache();
         return XSB_OK;
     });
 }
