@@ -19,6 +19,7 @@ I32, I64 = 0, 1
 UPDATE, RAW, ASSIGN = 0, 1, 2
 DETERMINISTIC, FAST = 0, 1
 COMBINE_SEED, COMBINE_ADD = 0, 1
+STRATEGY_AUTO, STRATEGY_FULLSORT = 0, 1
 
 
 class XsbError(RuntimeError):
@@ -47,7 +48,7 @@ class FlushStats(C.Structure):
         ("sort_passes", C.c_int32),
         ("sort_bits", C.c_int32),
         ("kernel_launches", C.c_int32),
-        ("reserved", C.c_int32),
+        ("column_path", C.c_int32),
         ("ms_total", C.c_float),
         ("ms_expand", C.c_float),
         ("ms_histogram", C.c_float),
@@ -59,7 +60,7 @@ class FlushStats(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _i32, _i64, _u64, _p, _f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_double
@@ -111,6 +112,7 @@ SIGNATURES = {
     "xsb_timer_start": (_i32, [_p]),
     "xsb_timer_stop": (_i32, [_p, C.POINTER(C.c_float)]),
     "xsb_set_profiling": (_i32, [_p, _i32]),
+    "xsb_set_strategy": (_i32, [_p, _i32]),
     "xsb_get_flush_stats": (_i32, [_p, C.POINTER(FlushStats)]),
     "xsb_kernel_launches": (_i32, [_p, C.POINTER(_i64)]),
 }
@@ -204,6 +206,8 @@ class Handle:
             n = int(splits[rank + 1]) - int(splits[rank])
             self.n_ranks, self.rank = n_ranks, rank
         self._h = h
+        if os.environ.get("XSB_STRATEGY", "").lower() == "fullsort":  # test/bench switch
+            check(lib().xsb_set_strategy(h, STRATEGY_FULLSORT), h)
         self.m, self.n = int(m), int(n)
         self.idx_type, self.index_base, self.n_tid, self.device = idx_type, index_base, n_tid, device
         self.idx_dtype = np.int64 if idx_type == I64 else np.int32
@@ -365,6 +369,10 @@ class Handle:
         ms = C.c_float(0)
         self._c(lib().xsb_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def set_strategy(self, strategy):
+        """STRATEGY_AUTO (column sort + in-tile row ordering) or STRATEGY_FULLSORT ((col,row) sort)."""
+        self._c(lib().xsb_set_strategy(self._h, int(strategy)))
 
     def set_profiling(self, on=True):
         self._c(lib().xsb_set_profiling(self._h, int(bool(on))))

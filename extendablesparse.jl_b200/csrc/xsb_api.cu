@@ -215,6 +215,8 @@ struct xsb_matrix
         nnz = 0;
     }
     size_t shrink_surplus_bytes = (size_t)16 << 30;
+    int strategy = XSB_STRATEGY_AUTO;
+    bool last_column_path = false;
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
     {
@@ -446,21 +448,53 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         tp->end(s, &StageTimes::expand);
 
     Rec *B = static_cast<Rec *>(h->dalloc(sizeof(Rec) * (size_t)total));
-    const size_t ws_bytes = std::max(sort_workspace_bytes((u64)total), reduce_workspace_bytes((u64)total, h->n));
+    const size_t ws_bytes = std::max(std::max(sort_workspace_bytes((u64)total), reduce_workspace_bytes((u64)total, h->n)),
+                                     column_workspace_bytes((u64)total, h->n));
     void *ws = h->dalloc(ws_bytes);
 
-    // ---- sort by (col,row)
-    const SortPlan plan = make_sort_plan(h->L.low, h->L.sortbits());
-    Rec *sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
-    Rec *spare = (sorted == A) ? B : A;
-
-    // ---- reduce duplicates, emit CSC into the spare ping-pong buffer
     void *new_colptr = h->dalloc(h->isz() * (size_t)(h->n + 1));
-    void *new_rowval = spare;
-    double *new_nzval = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spare) + 8 * (size_t)total);
-    reduce_emit_csc(s, sorted, (u64)total, h->L, combine, mode, !h->has_assign, h->n, h->idx64, h->base, new_rowval,
-                    new_nzval, new_colptr, ws, h->d_scal + 0, h->lc, tp);
-    const i64 nnz_new = (i64)read_scalar(h, 0);
+    Rec *sorted = nullptr, *spare = nullptr;
+    void *new_rowval = nullptr;
+    double *new_nzval = nullptr;
+    i64 nnz_new = -1;
+    SortPlan plan{};
+    int passes_run = 0;
+    bool column_path = h->strategy != XSB_STRATEGY_FULLSORT && column_path_supported(h->L);
+    if (column_path)
+    {
+        // ---- sort by column only (half the passes); rows are ordered inside the reduce kernel
+        plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
+        sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
+        passes_run += plan.npasses;
+        spare = (sorted == A) ? B : A;
+        new_rowval = spare;
+        new_nzval = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spare) + 8 * (size_t)total);
+        column_reduce_emit_csc(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base,
+                               new_rowval, new_nzval, new_colptr, ws, h->d_scal + 0,
+                               reinterpret_cast<u32 *>(h->d_scal + 6), h->lc, tp);
+        XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, sizeof(u64), cudaMemcpyDeviceToHost, s));
+        nnz_new = (i64)read_scalar(h, 0);
+        if ((u32)h->h_scal[6] != 0u)
+        { // a column too long for the in-warp path: finish with the general sort (records are intact)
+            column_path = false;
+            A = sorted;
+            B = spare;
+        }
+    }
+    if (!column_path)
+    {
+        // ---- sort by (col,row), then a flat segmented reduction
+        plan = make_sort_plan(h->L.low, h->L.sortbits());
+        sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
+        passes_run += plan.npasses;
+        spare = (sorted == A) ? B : A;
+        new_rowval = spare;
+        new_nzval = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spare) + 8 * (size_t)total);
+        reduce_emit_csc(s, sorted, (u64)total, h->L, combine, mode, !h->has_assign, h->n, h->idx64, h->base,
+                        new_rowval, new_nzval, new_colptr, ws, h->d_scal + 0, h->lc, tp);
+        nnz_new = (i64)read_scalar(h, 0);
+    }
+    h->last_column_path = column_path;
 
     if (tp)
         tp->begin(s);
@@ -497,8 +531,9 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.n_inserted = n_ins;
     h->stats.nnz_old = nnz_old;
     h->stats.nnz_new = nnz_new;
-    h->stats.sort_passes = plan.npasses;
-    h->stats.sort_bits = h->L.sortbits();
+    h->stats.sort_passes = passes_run;
+    h->stats.sort_bits = column_path ? h->L.colbits : h->L.sortbits();
+    h->stats.column_path = column_path ? 1 : 0;
     h->stats.kernel_launches = h->lc.in_flush;
     h->stats.ms_host_alloc = h->alloc_ms;
     if (tp)
@@ -1253,6 +1288,14 @@ int32_t xsb_timer_stop(xsb_matrix *h, float *ms_out)
         XSB_CUDA(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
         return XSB_OK;
     });
+}
+
+int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy)
+{
+    if (!h || (strategy != XSB_STRATEGY_AUTO && strategy != XSB_STRATEGY_FULLSORT))
+        return XSB_EINVAL;
+    h->strategy = strategy;
+    return XSB_OK;
 }
 
 int32_t xsb_set_profiling(xsb_matrix *h, int32_t enable)

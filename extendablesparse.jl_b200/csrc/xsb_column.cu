@@ -1,0 +1,774 @@
+// xsb_column.cu -- flush! after a COLUMN-ONLY radix sort (half the passes of a (col,row) sort):
+//
+//   column_reduce_kernel : a tile owns the columns that start inside it.  It stages the tile
+//     (+ look-ahead) in shared memory, finds the column boundaries, and one warp per column
+//       * orders the column's records by (row, position in column) with a register bitonic
+//         sort on a packed 32-bit key -- position is the insertion order, so the order inside a
+//         run of equal rows is the stream order (what the stable global sort would have given),
+//       * folds every run of equal rows sequentially (bit-exact left fold, same RunFold state
+//         machine as the (col,row) path),
+//       * leaves the column's entries (sorted rows, values) and their count in shared memory.
+//     Tile output offsets come from a decoupled look-back over the tiles' entry counts; the
+//     entries are written to rowval/nzval and the per-column counts to colcount.
+//   colcount -> colptr   : exclusive sum scan.
+//
+// This is the reference's own per-column structure (gather column, sort by row, merge:
+// src/matrix/sparsematrixlnk.jl:328-377) with the column gather done by the radix sort.
+// Columns longer than the in-warp limit raise an overflow flag; the caller then finishes with
+// the general (col,row) sort path.
+#include "xsb_internal.h"
+
+namespace xsb {
+
+constexpr int CK_THREADS = 256;
+constexpr int CK_WARPS = CK_THREADS / 32;
+constexpr int CK_T = 2048;                 // nominal tile: columns starting in [tile*CK_T, (tile+1)*CK_T) are owned
+constexpr int CK_CAP = 3072;               // records staged per tile (tile + look-ahead for the last owned column)
+constexpr int CK_IPT = CK_CAP / CK_THREADS; // 12
+constexpr int CK_MAXE = 8;                 // up to 32*8 = 256 records per column in the warp sort
+
+constexpr u64 CS_LOCAL = 1ull << 62;
+constexpr u64 CS_INCL = 2ull << 62;
+constexpr u64 CS_VALUE = (1ull << 62) - 1ull;
+
+// exclusive rank of every element among the set flags, flags laid out as (round i, thread)
+template <int IPT, int WARPS>
+__device__ __forceinline__ u32 block_rank(const bool (&flag)[IPT], u32 (&excl)[IPT], u32 *s_cnt, u32 *s_total,
+                                          int lane, int warp, u32 lt)
+{
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+        const u32 bal = __ballot_sync(0xffffffffu, flag[i]);
+        if (lane == 0)
+            s_cnt[i * WARPS + warp] = __popc(bal);
+        excl[i] = __popc(bal & lt);
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        constexpr int N = IPT * WARPS;
+        constexpr int PER = (N + 31) / 32;
+        u32 c[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            const int idx = lane * PER + k;
+            c[k] = idx < N ? s_cnt[idx] : 0u;
+            sum += c[k];
+        }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        u32 run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            const int idx = lane * PER + k;
+            if (idx < N)
+                s_cnt[idx] = run;
+            run += c[k];
+        }
+        if (lane == 31)
+            *s_total = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        excl[i] += s_cnt[i * WARPS + warp];
+    const u32 total = *s_total;
+    __syncthreads(); // s_cnt / s_total may be reused right away
+    return total;
+}
+
+// bitonic sort of 32*E keys held E per lane (element index = lane*E + e), ascending
+template <int E> __device__ __forceinline__ void warp_bitonic(u32 (&k)[E], int lane)
+{
+    constexpr int N = 32 * E;
+#pragma unroll
+    for (int size = 2; size <= N; size <<= 1)
+    {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+        {
+            if (stride >= E)
+            { // partner in another lane, same register slot
+                const int lstride = stride / E;
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                {
+                    const int g = lane * E + e;
+                    const u32 other = __shfl_xor_sync(0xffffffffu, k[e], lstride);
+                    const bool up = (g & size) == 0;      // ascending block
+                    const bool lower = (g & stride) == 0; // this element is the lower index of the pair
+                    const u32 mn = min(k[e], other), mx = max(k[e], other);
+                    k[e] = (up == lower) ? mn : mx;
+                }
+            }
+            else
+            { // both elements in this lane
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                {
+                    if ((e & stride) == 0)
+                    {
+                        const int g = lane * E + e;
+                        const bool up = (g & size) == 0;
+                        const u32 a = k[e], b = k[e + stride];
+                        const u32 mn = min(a, b), mx = max(a, b);
+                        k[e] = up ? mn : mx;
+                        k[e + stride] = up ? mx : mn;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_column(const u32 *s_key, u32 *s_sorted, u32 len, int lane)
+{
+    u32 k[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+        const u32 i = e * 32 + lane; // any initial arrangement will do: the position is part of the key
+        k[e] = i < len ? s_key[i] : 0xffffffffu;
+    }
+    warp_bitonic<E>(k, lane);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+        const u32 r = lane * E + e;
+        if (r < len)
+            s_sorted[r] = k[e];
+    }
+}
+
+struct ColFold
+{ // same semantics as RunFold in xsb_flush.cu (kept separate: different translation unit)
+    bool seeded = false, has_old = false, exists = false, pexists = false;
+    double old = 0.0, acc = 0.0, pacc = 0.0;
+    u32 ptid = 0xffffffffu;
+    __device__ __forceinline__ void commit()
+    {
+        if (pexists)
+        {
+            if (exists)
+                acc = acc + pacc;
+            else
+            {
+                acc = pacc;
+                exists = true;
+            }
+            pexists = false;
+        }
+    }
+    __device__ __forceinline__ void apply(u32 fl, u32 tid, double v, int combine)
+    {
+        if (fl == FL_OLD)
+        {
+            if (combine == 0)
+            {
+                seeded = true;
+                exists = true;
+                acc = v;
+            }
+            else
+            {
+                has_old = true;
+                old = v;
+            }
+            return;
+        }
+        if (seeded)
+        {
+            acc = (fl == FL_ASSIGN) ? v : acc + v;
+            return;
+        }
+        if (tid != ptid)
+        {
+            commit();
+            ptid = tid;
+        }
+        if (fl == FL_RAW)
+        {
+            pacc = pexists ? pacc + v : 0.0 + v;
+            pexists = true;
+        }
+        else if (fl == FL_UPDATE)
+        {
+            if (pexists)
+                pacc = pacc + v;
+            else if (v != 0.0)
+            {
+                pexists = true;
+                pacc = 0.0 + v;
+            }
+        }
+        else
+        {
+            if (pexists)
+                pacc = v;
+            else if (v != 0.0)
+            {
+                pexists = true;
+                pacc = v;
+            }
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        commit();
+        if (has_old)
+        {
+            acc = exists ? old + acc : old;
+            exists = true;
+        }
+    }
+};
+
+template <typename Ti, bool SIMPLE>
+__global__ void __launch_bounds__(CK_THREADS)
+column_reduce_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int posbits, int combine, Ti base,
+                     Ti *__restrict__ rowval, double *__restrict__ nzval, u32 *__restrict__ colcount,
+                     u64 *__restrict__ status, u32 *__restrict__ tile_counter, u64 *__restrict__ d_nnz,
+                     u32 *__restrict__ d_overflow, u32 ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Rec *s_rec = reinterpret_cast<Rec *>(smem_raw);                 // CK_CAP records; later the columns' entries
+    u32 *s_key = reinterpret_cast<u32 *>(s_rec + CK_CAP);           // CK_CAP packed (row,pos) keys; later run heads
+    u32 *s_sorted = s_key + CK_CAP;                                 // CK_CAP sorted keys
+    unsigned short *s_cs = reinterpret_cast<unsigned short *>(s_sorted + CK_CAP); // column starts (padded to keep s_ccnt 16-byte aligned)
+    unsigned short *s_ccnt = s_cs + CK_CAP + 8;                     // entries per owned column (CK_T)
+    u32 *s_coff = reinterpret_cast<u32 *>(s_ccnt + CK_T);           // exclusive offsets per owned column (CK_T)
+    __shared__ u32 s_cnt[CK_IPT * CK_WARPS];
+    __shared__ u32 s_total, s_tile, s_next;
+    __shared__ u64 s_prev, s_tileoff;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+    {
+        s_tile = atomicAdd(tile_counter, 1u);
+        s_next = 0;
+    }
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 g0 = (u64)tile * CK_T;
+    const u32 avail = (u32)min((u64)CK_CAP, nrec - g0);
+    const bool at_end = g0 + avail == nrec;
+
+#pragma unroll
+    for (int i = 0; i < CK_IPT; ++i)
+    {
+        const u32 e = i * CK_THREADS + tid;
+        if (e < avail)
+            s_rec[e] = ld_rec_stream(sorted + g0 + e);
+    }
+    if (tid == 0)
+        s_prev = g0 > 0 ? sorted[g0 - 1].key : 0ull;
+    __syncthreads();
+
+    // ---- column starts
+    const u32 lt = lanemask_lt();
+    bool flag[CK_IPT];
+    u32 excl[CK_IPT];
+#pragma unroll
+    for (int i = 0; i < CK_IPT; ++i)
+    {
+        const u32 e = i * CK_THREADS + tid;
+        bool st = false;
+        if (e < avail)
+        {
+            const u64 c = L.col(s_rec[e].key);
+            st = e > 0 ? c != L.col(s_rec[e - 1].key) : (g0 == 0 || c != L.col(s_prev));
+        }
+        flag[i] = st;
+    }
+    const u32 nstarts = block_rank<CK_IPT, CK_WARPS>(flag, excl, s_cnt, &s_total, lane, warp, lt);
+#pragma unroll
+    for (int i = 0; i < CK_IPT; ++i)
+        if (flag[i])
+            s_cs[excl[i]] = (unsigned short)(i * CK_THREADS + tid);
+    __syncthreads();
+    // columns that start inside the nominal tile are owned; the column list is sorted, so the
+    // owned ones are the first `nown`
+    u32 nown = 0;
+    {
+        u32 lo = 0, hi = nstarts; // first start >= CK_T
+        while (lo < hi)
+        {
+            const u32 mid = (lo + hi) >> 1;
+            if (s_cs[mid] < CK_T)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        nown = lo;
+    }
+    // end of the last owned column: the next start, or the end of the data
+    u32 last_end = 0;
+    bool overflow = false;
+    if (nown > 0)
+    {
+        if (nown < nstarts)
+            last_end = s_cs[nown];
+        else if (at_end)
+            last_end = avail;
+        else
+            overflow = true; // the last owned column runs past the look-ahead
+    }
+    const u32 posmask = (1u << posbits) - 1u;
+    // packed (row, position-in-column) keys
+#pragma unroll
+    for (int i = 0; i < CK_IPT; ++i)
+    {
+        const u32 e = i * CK_THREADS + tid;
+        const int ci = (int)excl[i] + (flag[i] ? 1 : 0) - 1; // column of this record in the tile's list
+        if (e < avail && ci >= 0 && (u32)ci < nown)
+        {
+            const u32 pos = e - s_cs[ci];
+            s_key[e] = ((u32)L.row(s_rec[e].key) << posbits) | (pos & posmask);
+        }
+    }
+    if (tid < CK_T / 8) // zero the per-column counts (unsigned short x 8 per thread)
+        reinterpret_cast<uint4 *>(s_ccnt)[tid] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+
+    // ---- one warp per column (dynamic assignment)
+    const u32 maxlen = min(32u * CK_MAXE, 1u << posbits);
+    for (;;)
+    {
+        u32 k = 0;
+        if (lane == 0)
+            k = atomicAdd(&s_next, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nown || overflow)
+            break;
+        const u32 c0 = s_cs[k];
+        const u32 c1 = (k + 1 < nown) ? s_cs[k + 1] : last_end;
+        const u32 len = c1 - c0;
+        if (len > maxlen)
+        {
+            if (lane == 0)
+                atomicExch(d_overflow, 1u);
+            continue;
+        }
+        if (len <= 32)
+            sort_column<1>(s_key + c0, s_sorted + c0, len, lane);
+        else if (len <= 64)
+            sort_column<2>(s_key + c0, s_sorted + c0, len, lane);
+        else if (len <= 128)
+            sort_column<4>(s_key + c0, s_sorted + c0, len, lane);
+        else
+            sort_column<8>(s_key + c0, s_sorted + c0, len, lane);
+        __syncwarp();
+        // run heads (first record of every distinct row), compacted into s_key[c0..]
+        u32 nruns = 0;
+        for (u32 r0 = 0; r0 < len; r0 += 32)
+        {
+            const u32 r = r0 + lane;
+            bool head = false;
+            if (r < len)
+                head = r == 0 || (s_sorted[c0 + r] >> posbits) != (s_sorted[c0 + r - 1] >> posbits);
+            const u32 bal = __ballot_sync(0xffffffffu, head);
+            if (head)
+                s_key[c0 + nruns + __popc(bal & lt)] = r;
+            nruns += __popc(bal);
+        }
+        __syncwarp();
+        // fold: one run per lane per round; results stay in registers until the column is done
+        constexpr int MAXROUND = CK_MAXE;
+        double oval[MAXROUND];
+        u32 orow[MAXROUND];
+        u32 created_mask = 0; // bit r: this lane's run of round r created an entry
+#pragma unroll
+        for (int rd = 0; rd < MAXROUND; ++rd)
+        {
+            oval[rd] = 0.0;
+            orow[rd] = 0;
+            const u32 u = rd * 32 + lane;
+            if (rd * 32 < (int)nruns && u < nruns)
+            {
+                const u32 q0 = s_key[c0 + u];
+                const u32 q1 = (u + 1 < nruns) ? s_key[c0 + u + 1] : len;
+                orow[rd] = s_sorted[c0 + q0] >> posbits;
+                bool created = false;
+                if (SIMPLE)
+                {
+                    double acc = 0.0;
+                    for (u32 q = q0; q < q1; ++q)
+                    {
+                        const Rec r = s_rec[c0 + (s_sorted[c0 + q] & posmask)];
+                        const u32 fl = L.flavour(r.key);
+                        acc = (fl == FL_OLD) ? r.val : acc + r.val;
+                        created |= (fl != FL_UPDATE) | (r.val != 0.0);
+                    }
+                    oval[rd] = acc;
+                }
+                else
+                {
+                    ColFold f;
+                    for (u32 q = q0; q < q1; ++q)
+                    {
+                        const Rec r = s_rec[c0 + (s_sorted[c0 + q] & posmask)];
+                        f.apply(L.flavour(r.key), L.tid(r.key), r.val, combine);
+                    }
+                    f.finish();
+                    created = f.exists;
+                    oval[rd] = f.acc;
+                }
+                if (created)
+                    created_mask |= 1u << rd;
+            }
+        }
+        __syncwarp(); // every fold of this column is done: its records may now be overwritten
+        u32 cnt = 0;
+#pragma unroll
+        for (int rd = 0; rd < MAXROUND; ++rd)
+        {
+            if (rd * 32 < (int)nruns)
+            {
+                const bool cr = (created_mask >> rd) & 1u;
+                const u32 bal = __ballot_sync(0xffffffffu, cr);
+                if (cr)
+                {
+                    Rec o;
+                    o.key = (u64)orow[rd];
+                    o.val = oval[rd];
+                    s_rec[c0 + cnt + __popc(bal & lt)] = o;
+                }
+                cnt += __popc(bal);
+            }
+        }
+        if (lane == 0)
+            s_ccnt[k] = (unsigned short)cnt;
+    }
+    if (overflow && tid == 0)
+        atomicExch(d_overflow, 1u);
+    __syncthreads();
+
+    // ---- exclusive scan of the owned columns' entry counts (8 columns per thread)
+    {
+        constexpr int PER = CK_T / CK_THREADS;
+        u32 c[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+        {
+            const u32 k = tid * PER + j;
+            c[j] = k < nown ? (u32)s_ccnt[k] : 0u;
+            sum += c[j];
+        }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_cnt[warp] = incl;
+        __syncthreads();
+        u32 wpre = 0;
+#pragma unroll
+        for (int w = 0; w < CK_WARPS; ++w)
+            if (w < warp)
+                wpre += s_cnt[w];
+        u32 run = wpre + incl - sum;
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+        {
+            const u32 k = tid * PER + j;
+            if (k < nown)
+                s_coff[k] = run;
+            run += c[j];
+        }
+        if (tid == CK_THREADS - 1)
+            s_total = run;
+    }
+    __syncthreads();
+    const u32 total = s_total;
+
+    // ---- decoupled look-back over the tiles' entry counts
+    if (warp == 0)
+    {
+        u64 prefix = 0;
+        if (tile == 0)
+        {
+            if (lane == 0)
+                st_relaxed_u64(status, CS_INCL | (u64)total);
+        }
+        else
+        {
+            if (lane == 0)
+                st_relaxed_u64(status + tile, CS_LOCAL | (u64)total);
+            i64 t = (i64)tile - 1;
+            for (;;)
+            {
+                const i64 idx = t - lane;
+                u64 v = CS_INCL;
+                if (idx >= 0)
+                {
+                    do
+                    {
+                        v = ld_relaxed_u64(status + idx);
+                    } while ((v >> 62) == 0ull);
+                }
+                const u32 incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                u64 contrib = v & CS_VALUE;
+                if (incl_mask)
+                {
+                    const int first = __ffs(incl_mask) - 1;
+                    if (lane > first)
+                        contrib = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                prefix += contrib;
+                if (incl_mask)
+                    break;
+                t -= 32;
+            }
+            if (lane == 0)
+                st_relaxed_u64(status + tile, CS_INCL | (prefix + total));
+        }
+        if (lane == 0)
+        {
+            s_tileoff = prefix;
+            if (tile == ntiles - 1)
+                *d_nnz = prefix + total;
+        }
+    }
+    __syncthreads();
+    const u64 tileoff = s_tileoff;
+
+    // ---- write the entries and the per-column counts
+    for (u32 k = warp; k < nown; k += CK_WARPS)
+    {
+        const u32 c0 = s_cs[k];
+        const u32 cnt = s_ccnt[k];
+        const u64 o0 = tileoff + s_coff[k];
+        for (u32 j = lane; j < cnt; j += 32)
+        {
+            const Rec o = s_rec[c0 + j];
+            rowval[o0 + j] = (Ti)o.key + base;
+            nzval[o0 + j] = o.val;
+        }
+        if (lane == 0)
+            colcount[L.col(sorted[g0 + c0].key)] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------
+// colptr = base + exclusive sum of colcount
+// ------------------------------------------------------------------------
+constexpr int CS_THREADS = 256;
+constexpr int CS_IPT = 8;
+constexpr int CS_TILE = CS_THREADS * CS_IPT;
+
+__global__ void __launch_bounds__(CS_THREADS)
+colcount_tilesum_kernel(const u32 *__restrict__ colcount, i64 n, u64 *__restrict__ tsum)
+{
+    __shared__ u64 s_w[CS_THREADS / 32];
+    const i64 b0 = (i64)blockIdx.x * CS_TILE;
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < CS_IPT; ++i)
+    {
+        const i64 j = b0 + i * CS_THREADS + threadIdx.x;
+        if (j < n)
+            s += colcount[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0)
+        s_w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < CS_THREADS / 32; ++w)
+            s += s_w[w];
+        tsum[blockIdx.x] = s;
+    }
+}
+
+// single block: in-place exclusive scan of the tile sums
+__global__ void __launch_bounds__(1024) tilesum_scan_kernel(u64 *__restrict__ tsum, i64 nt)
+{
+    __shared__ u64 s_w[32];
+    __shared__ u64 s_carry;
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (i64 b0 = 0; b0 < nt; b0 += 1024)
+    {
+        const i64 j = b0 + threadIdx.x;
+        const u64 x = j < nt ? tsum[j] : 0;
+        u64 v = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u64 t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o)
+                v += t;
+        }
+        if (lane == 31)
+            s_w[warp] = v;
+        __syncthreads();
+        u64 pre = s_carry;
+        for (int w = 0; w < warp; ++w)
+            pre += s_w[w];
+        if (j < nt)
+            tsum[j] = pre + v - x;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            s_carry = pre + v;
+        __syncthreads();
+    }
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(CS_THREADS)
+colptr_from_counts_kernel(const u32 *__restrict__ colcount, const u64 *__restrict__ tsum, i64 n, Ti base,
+                          Ti *__restrict__ colptr)
+{
+    __shared__ u64 s_w[CS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 b0 = (i64)blockIdx.x * CS_TILE + (i64)threadIdx.x * CS_IPT; // blocked: thread owns CS_IPT columns
+    u64 c[CS_IPT], sum = 0;
+#pragma unroll
+    for (int i = 0; i < CS_IPT; ++i)
+    {
+        const i64 j = b0 + i;
+        c[i] = j < n ? (u64)colcount[j] : 0ull;
+        sum += c[i];
+    }
+    u64 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_w[warp] = incl;
+    __syncthreads();
+    u64 run = tsum[blockIdx.x];
+    for (int w = 0; w < warp; ++w)
+        run += s_w[w];
+    run += incl - sum;
+#pragma unroll
+    for (int i = 0; i < CS_IPT; ++i)
+    {
+        const i64 j = b0 + i;
+        if (j < n)
+            colptr[j] = (Ti)run + base; // entries before column j
+        run += c[i];
+        if (j == n - 1)
+            colptr[n] = (Ti)run + base;
+    }
+}
+
+size_t column_workspace_bytes(u64 nrec, i64 ncols)
+{
+    const u64 ntiles = (nrec + CK_T - 1) / CK_T;
+    const u64 ctiles = ((u64)ncols + CS_TILE - 1) / CS_TILE;
+    return 256 + sizeof(u32) * (((size_t)ncols + 1) & ~(size_t)1) + sizeof(u64) * (ntiles + 1) +
+           sizeof(u64) * (ctiles + 1) + 64;
+}
+
+size_t column_kernel_smem()
+{
+    return sizeof(Rec) * CK_CAP + 2 * sizeof(u32) * CK_CAP + sizeof(unsigned short) * (CK_CAP + 8 + CK_T) +
+           sizeof(u32) * CK_T + 16;
+}
+
+bool column_path_supported(const KeyLayout &L) { return L.rowbits <= 27 && L.colbits <= 32; }
+
+// records sorted by column (stable) -> CSC.  *h_overflow is set when a column was too long for the
+// in-warp path (outputs are then undefined and the caller falls back to the (col,row) sort).
+void column_reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine,
+                            bool plain_adds, i64 ncols, int idx64, int base, void *rowval_out, double *nzval_out,
+                            void *colptr_out, void *workspace, u64 *d_nnz, u32 *d_overflow, LaunchCounter &lc,
+                            StageTimer *timer)
+{
+    const u64 ntiles = (nrec + CK_T - 1) / CK_T;
+    const u64 ctiles = ((u64)ncols + CS_TILE - 1) / CS_TILE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    u32 *counter = reinterpret_cast<u32 *>(ws);
+    u32 *colcount = reinterpret_cast<u32 *>(ws + 256);
+    u64 *status = reinterpret_cast<u64 *>(colcount + (((size_t)ncols + 1) & ~(size_t)1));
+    u64 *tsum = status + ntiles + 1;
+    const int posbits = std::min(8, 32 - L.rowbits);
+    const size_t smem = column_kernel_smem();
+
+    if (timer)
+        timer->begin(stream);
+    XSB_CUDA(cudaMemsetAsync(ws, 0, 256 + sizeof(u32) * (((size_t)ncols + 1) & ~(size_t)1) + sizeof(u64) * (ntiles + 1),
+                             stream));
+    XSB_CUDA(cudaMemsetAsync(d_nnz, 0, sizeof(u64), stream));
+    XSB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(u32), stream));
+    const bool simple = plain_adds && L.tidbits == 0 && combine == 0;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+#define XSB_LAUNCH_COL(TI, SIMPLE)                                                                                 \
+    column_reduce_kernel<TI, SIMPLE><<<(unsigned)ntiles, CK_THREADS, smem, stream>>>(                              \
+        sorted, nrec, L, posbits, combine, (TI)base, (TI *)rowval_out, nzval_out, colcount, status, counter, d_nnz, \
+        d_overflow, (u32)ntiles)
+    if (nrec > 0)
+    {
+        if (idx64)
+        {
+            if (simple)
+                XSB_LAUNCH_COL(int64_t, true);
+            else
+                XSB_LAUNCH_COL(int64_t, false);
+        }
+        else
+        {
+            if (simple)
+                XSB_LAUNCH_COL(int32_t, true);
+            else
+                XSB_LAUNCH_COL(int32_t, false);
+        }
+        lc.add();
+        XSB_CUDA(cudaGetLastError());
+    }
+#undef XSB_LAUNCH_COL
+    if (timer)
+        timer->end(stream, &StageTimes::reduce);
+
+    if (timer)
+        timer->begin(stream);
+    colcount_tilesum_kernel<<<(unsigned)ctiles, CS_THREADS, 0, stream>>>(colcount, ncols, tsum);
+    tilesum_scan_kernel<<<1, 1024, 0, stream>>>(tsum, (i64)ctiles);
+    if (idx64)
+        colptr_from_counts_kernel<int64_t><<<(unsigned)ctiles, CS_THREADS, 0, stream>>>(colcount, tsum, ncols, (int64_t)base,
+                                                                                        (int64_t *)colptr_out);
+    else
+        colptr_from_counts_kernel<int32_t><<<(unsigned)ctiles, CS_THREADS, 0, stream>>>(colcount, tsum, ncols, (int32_t)base,
+                                                                                        (int32_t *)colptr_out);
+    lc.add(3);
+    XSB_CUDA(cudaGetLastError());
+    if (timer)
+        timer->end(stream, &StageTimes::colptr);
+}
+
+} // namespace xsb

@@ -103,6 +103,15 @@ void reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout
                      bool plain_adds, i64 ncols, int idx64, int base, void *rowval_out, double *nzval_out,
                      void *colptr_out, void *workspace, u64 *d_nnz, LaunchCounter &lc, StageTimer *timer);
 
+// ---- xsb_column.cu
+size_t column_workspace_bytes(u64 nrec, i64 ncols);
+bool column_path_supported(const KeyLayout &L);
+// records sorted by column only -> CSC (rows ordered per column in shared memory)
+void column_reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine,
+                            bool plain_adds, i64 ncols, int idx64, int base, void *rowval_out, double *nzval_out,
+                            void *colptr_out, void *workspace, u64 *d_nnz, u32 *d_overflow, LaunchCounter &lc,
+                            StageTimer *timer);
+
 // ---- xsb_insert.cu
 // (I,J,V) -> records; *d_err receives the smallest offending index (or ~0)
 void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,

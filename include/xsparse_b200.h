@@ -82,7 +82,7 @@ typedef struct xsb_flush_stats
     int32_t sort_passes;      /* onesweep passes executed              */
     int32_t sort_bits;        /* key bits sorted                       */
     int32_t kernel_launches;  /* kernels launched by the flush         */
-    int32_t reserved;
+    int32_t column_path;      /* 1: column-only sort + in-tile row ordering produced the result */
     float ms_total;           /* device time of the whole flush (CUDA events; 0 unless profiling on) */
     float ms_expand;          /* old CSC -> records                    */
     float ms_histogram;       /* digit histogram + scan                */
@@ -246,6 +246,12 @@ int32_t xsb_timer_start(xsb_matrix *h);
 int32_t xsb_timer_stop(xsb_matrix *h, float *ms_out);
 /* Per-stage CUDA-event timing inside xsb_flush (off by default). */
 int32_t xsb_set_profiling(xsb_matrix *h, int32_t enable);
+/* Flush algorithm.  AUTO: radix sort on the column bits only, rows ordered per column inside the
+ * reduce kernel (falls back by itself when a column exceeds the in-warp limit).
+ * FULLSORT: radix sort on the whole (col,row) key, flat segmented reduction.  Same results. */
+#define XSB_STRATEGY_AUTO 0
+#define XSB_STRATEGY_FULLSORT 1
+int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy);
 int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
 /* Total kernels launched by this handle since creation. */
 int32_t xsb_kernel_launches(const xsb_matrix *h, int64_t *count);

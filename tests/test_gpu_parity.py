@@ -506,3 +506,48 @@ def test_full_size_fd_properties(xsb):
     _, _, nz2 = h.fetch_csc_numpy()
     assert np.array_equal(nz2[rv != cols], 2 * nz[rv != cols])  # one contribution each: exact
     assert np.allclose(nz2, 2 * nz, rtol=1e-14, atol=0.0)
+
+
+# ---------------------------------------------------------------- flush strategies
+def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
+    """Column-only sort + in-tile row ordering (AUTO) and the (col,row) sort (FULLSORT) give the
+    same bits; a column longer than the in-warp limit makes AUTO finish with the general path."""
+    rng = np.random.default_rng(77)
+    m, n, cnt = 3000, 500, 60000
+    I = rng.integers(1, m + 1, cnt)
+    J = rng.integers(1, n + 1, cnt)
+    V = rng.standard_normal(cnt)
+    A = oracle.OracleExt(m, n)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    ref = A.csc()
+    for strat, expect_col in ((xsb.capi.STRATEGY_AUTO, 1), (xsb.capi.STRATEGY_FULLSORT, 0)):
+        h = xsb.Handle(m, n)
+        h.set_strategy(strat)
+        h.insert_batch(I, J, V, xsb.UPDATE)
+        h.flush()
+        assert h.flush_stats()["column_path"] == expect_col
+        assert_csc_equal(h.fetch_csc_numpy(), ref)
+    # one dense column (3000 records in column 7) -> overflow -> fallback, same result
+    J2 = J.copy()
+    J2[:3000] = 7
+    A = oracle.OracleExt(m, n)
+    A.insert_batch(I, J2, V, oracle.UPDATE)
+    h = xsb.Handle(m, n)
+    h.insert_batch(I, J2, V, xsb.UPDATE)
+    h.flush()
+    st = h.flush_stats()
+    assert st["column_path"] == 0 and st["sort_passes"] > 3
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    # columns of every length around the warp-sort sizes (31..257 records), duplicates included
+    lens = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256]
+    Jl = np.concatenate([np.full(L, k + 1) for k, L in enumerate(lens)])
+    Il = rng.integers(1, 40, len(Jl))
+    Vl = rng.standard_normal(len(Jl))
+    perm = rng.permutation(len(Jl))
+    A = oracle.OracleExt(50, len(lens))
+    A.insert_batch(Il[perm], Jl[perm], Vl[perm], oracle.RAW)
+    h = xsb.Handle(50, len(lens))
+    h.insert_batch(Il[perm], Jl[perm], Vl[perm], xsb.RAW)
+    h.flush()
+    assert h.flush_stats()["column_path"] == 1
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
