@@ -130,23 +130,35 @@ template <int E> __device__ __forceinline__ void warp_bitonic(u32 (&k)[E], int l
     }
 }
 
+// Sorts one column (len <= 32*E records at s_col[0..len)) by (row, position) and permutes the
+// records in place into that order: keys are sorted in registers, every lane then gathers the
+// records of its E ranks, and only after the whole warp has read are they written back.
 template <int E>
-__device__ __forceinline__ void sort_column(const u32 *s_key, u32 *s_sorted, u32 len, int lane)
+__device__ __forceinline__ void sort_column(const u32 *s_keycol, Rec *s_col, u32 len, u32 posmask, int lane)
 {
     u32 k[E];
 #pragma unroll
     for (int e = 0; e < E; ++e)
     {
         const u32 i = e * 32 + lane; // any initial arrangement will do: the position is part of the key
-        k[e] = i < len ? s_key[i] : 0xffffffffu;
+        k[e] = i < len ? s_keycol[i] : 0xffffffffu;
     }
     warp_bitonic<E>(k, lane);
+    Rec t[E];
 #pragma unroll
     for (int e = 0; e < E; ++e)
     {
         const u32 r = lane * E + e;
         if (r < len)
-            s_sorted[r] = k[e];
+            t[e] = s_col[k[e] & posmask];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+        const u32 r = lane * E + e;
+        if (r < len)
+            s_col[r] = t[e];
     }
 }
 
@@ -233,338 +245,8 @@ struct ColFold
     }
 };
 
-template <typename Ti, bool SIMPLE>
-__global__ void __launch_bounds__(CK_THREADS)
-column_reduce_kernel(const Rec *__restrict__ sorted, u64 nrec, KeyLayout L, int posbits, int combine, Ti base,
-                     Ti *__restrict__ rowval, double *__restrict__ nzval, u32 *__restrict__ colcount,
-                     u64 *__restrict__ status, u32 *__restrict__ tile_counter, u64 *__restrict__ d_nnz,
-                     u32 *__restrict__ d_overflow, u32 ntiles)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Rec *s_rec = reinterpret_cast<Rec *>(smem_raw);                 // CK_CAP records; later the columns' entries
-    u32 *s_key = reinterpret_cast<u32 *>(s_rec + CK_CAP);           // CK_CAP packed (row,pos) keys; later run heads
-    u32 *s_sorted = s_key + CK_CAP;                                 // CK_CAP sorted keys
-    unsigned short *s_cs = reinterpret_cast<unsigned short *>(s_sorted + CK_CAP); // column starts (padded to keep s_ccnt 16-byte aligned)
-    unsigned short *s_ccnt = s_cs + CK_CAP + 8;                     // entries per owned column (CK_T)
-    u32 *s_coff = reinterpret_cast<u32 *>(s_ccnt + CK_T);           // exclusive offsets per owned column (CK_T)
-    __shared__ u32 s_cnt[CK_IPT * CK_WARPS];
-    __shared__ u32 s_total, s_tile, s_next;
-    __shared__ u64 s_prev, s_tileoff;
+#include "xsb_column_kernel.cuh"
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0)
-    {
-        s_tile = atomicAdd(tile_counter, 1u);
-        s_next = 0;
-    }
-    __syncthreads();
-    const u32 tile = s_tile;
-    const u64 g0 = (u64)tile * CK_T;
-    const u32 avail = (u32)min((u64)CK_CAP, nrec - g0);
-    const bool at_end = g0 + avail == nrec;
-
-#pragma unroll
-    for (int i = 0; i < CK_IPT; ++i)
-    {
-        const u32 e = i * CK_THREADS + tid;
-        if (e < avail)
-            s_rec[e] = ld_rec_stream(sorted + g0 + e);
-    }
-    if (tid == 0)
-        s_prev = g0 > 0 ? sorted[g0 - 1].key : 0ull;
-    __syncthreads();
-
-    // ---- column starts
-    const u32 lt = lanemask_lt();
-    bool flag[CK_IPT];
-    u32 excl[CK_IPT];
-#pragma unroll
-    for (int i = 0; i < CK_IPT; ++i)
-    {
-        const u32 e = i * CK_THREADS + tid;
-        bool st = false;
-        if (e < avail)
-        {
-            const u64 c = L.col(s_rec[e].key);
-            st = e > 0 ? c != L.col(s_rec[e - 1].key) : (g0 == 0 || c != L.col(s_prev));
-        }
-        flag[i] = st;
-    }
-    const u32 nstarts = block_rank<CK_IPT, CK_WARPS>(flag, excl, s_cnt, &s_total, lane, warp, lt);
-#pragma unroll
-    for (int i = 0; i < CK_IPT; ++i)
-        if (flag[i])
-            s_cs[excl[i]] = (unsigned short)(i * CK_THREADS + tid);
-    __syncthreads();
-    // columns that start inside the nominal tile are owned; the column list is sorted, so the
-    // owned ones are the first `nown`
-    u32 nown = 0;
-    {
-        u32 lo = 0, hi = nstarts; // first start >= CK_T
-        while (lo < hi)
-        {
-            const u32 mid = (lo + hi) >> 1;
-            if (s_cs[mid] < CK_T)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        nown = lo;
-    }
-    // end of the last owned column: the next start, or the end of the data
-    u32 last_end = 0;
-    bool overflow = false;
-    if (nown > 0)
-    {
-        if (nown < nstarts)
-            last_end = s_cs[nown];
-        else if (at_end)
-            last_end = avail;
-        else
-            overflow = true; // the last owned column runs past the look-ahead
-    }
-    const u32 posmask = (1u << posbits) - 1u;
-    // packed (row, position-in-column) keys
-#pragma unroll
-    for (int i = 0; i < CK_IPT; ++i)
-    {
-        const u32 e = i * CK_THREADS + tid;
-        const int ci = (int)excl[i] + (flag[i] ? 1 : 0) - 1; // column of this record in the tile's list
-        if (e < avail && ci >= 0 && (u32)ci < nown)
-        {
-            const u32 pos = e - s_cs[ci];
-            s_key[e] = ((u32)L.row(s_rec[e].key) << posbits) | (pos & posmask);
-        }
-    }
-    if (tid < CK_T / 8) // zero the per-column counts (unsigned short x 8 per thread)
-        reinterpret_cast<uint4 *>(s_ccnt)[tid] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-
-    // ---- one warp per column (dynamic assignment)
-    const u32 maxlen = min(32u * CK_MAXE, 1u << posbits);
-    for (;;)
-    {
-        u32 k = 0;
-        if (lane == 0)
-            k = atomicAdd(&s_next, 1u);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= nown || overflow)
-            break;
-        const u32 c0 = s_cs[k];
-        const u32 c1 = (k + 1 < nown) ? s_cs[k + 1] : last_end;
-        const u32 len = c1 - c0;
-        if (len > maxlen)
-        {
-            if (lane == 0)
-                atomicExch(d_overflow, 1u);
-            continue;
-        }
-        if (len <= 32)
-            sort_column<1>(s_key + c0, s_sorted + c0, len, lane);
-        else if (len <= 64)
-            sort_column<2>(s_key + c0, s_sorted + c0, len, lane);
-        else if (len <= 128)
-            sort_column<4>(s_key + c0, s_sorted + c0, len, lane);
-        else
-            sort_column<8>(s_key + c0, s_sorted + c0, len, lane);
-        __syncwarp();
-        // run heads (first record of every distinct row), compacted into s_key[c0..]
-        u32 nruns = 0;
-        for (u32 r0 = 0; r0 < len; r0 += 32)
-        {
-            const u32 r = r0 + lane;
-            bool head = false;
-            if (r < len)
-                head = r == 0 || (s_sorted[c0 + r] >> posbits) != (s_sorted[c0 + r - 1] >> posbits);
-            const u32 bal = __ballot_sync(0xffffffffu, head);
-            if (head)
-                s_key[c0 + nruns + __popc(bal & lt)] = r;
-            nruns += __popc(bal);
-        }
-        __syncwarp();
-        // fold: one run per lane per round; results stay in registers until the column is done
-        constexpr int MAXROUND = CK_MAXE;
-        double oval[MAXROUND];
-        u32 orow[MAXROUND];
-        u32 created_mask = 0; // bit r: this lane's run of round r created an entry
-#pragma unroll
-        for (int rd = 0; rd < MAXROUND; ++rd)
-        {
-            oval[rd] = 0.0;
-            orow[rd] = 0;
-            const u32 u = rd * 32 + lane;
-            if (rd * 32 < (int)nruns && u < nruns)
-            {
-                const u32 q0 = s_key[c0 + u];
-                const u32 q1 = (u + 1 < nruns) ? s_key[c0 + u + 1] : len;
-                orow[rd] = s_sorted[c0 + q0] >> posbits;
-                bool created = false;
-                if (SIMPLE)
-                {
-                    double acc = 0.0;
-                    for (u32 q = q0; q < q1; ++q)
-                    {
-                        const Rec r = s_rec[c0 + (s_sorted[c0 + q] & posmask)];
-                        const u32 fl = L.flavour(r.key);
-                        acc = (fl == FL_OLD) ? r.val : acc + r.val;
-                        created |= (fl != FL_UPDATE) | (r.val != 0.0);
-                    }
-                    oval[rd] = acc;
-                }
-                else
-                {
-                    ColFold f;
-                    for (u32 q = q0; q < q1; ++q)
-                    {
-                        const Rec r = s_rec[c0 + (s_sorted[c0 + q] & posmask)];
-                        f.apply(L.flavour(r.key), L.tid(r.key), r.val, combine);
-                    }
-                    f.finish();
-                    created = f.exists;
-                    oval[rd] = f.acc;
-                }
-                if (created)
-                    created_mask |= 1u << rd;
-            }
-        }
-        __syncwarp(); // every fold of this column is done: its records may now be overwritten
-        u32 cnt = 0;
-#pragma unroll
-        for (int rd = 0; rd < MAXROUND; ++rd)
-        {
-            if (rd * 32 < (int)nruns)
-            {
-                const bool cr = (created_mask >> rd) & 1u;
-                const u32 bal = __ballot_sync(0xffffffffu, cr);
-                if (cr)
-                {
-                    Rec o;
-                    o.key = (u64)orow[rd];
-                    o.val = oval[rd];
-                    s_rec[c0 + cnt + __popc(bal & lt)] = o;
-                }
-                cnt += __popc(bal);
-            }
-        }
-        if (lane == 0)
-            s_ccnt[k] = (unsigned short)cnt;
-    }
-    if (overflow && tid == 0)
-        atomicExch(d_overflow, 1u);
-    __syncthreads();
-
-    // ---- exclusive scan of the owned columns' entry counts (8 columns per thread)
-    {
-        constexpr int PER = CK_T / CK_THREADS;
-        u32 c[PER], sum = 0;
-#pragma unroll
-        for (int j = 0; j < PER; ++j)
-        {
-            const u32 k = tid * PER + j;
-            c[j] = k < nown ? (u32)s_ccnt[k] : 0u;
-            sum += c[j];
-        }
-        u32 incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        if (lane == 31)
-            s_cnt[warp] = incl;
-        __syncthreads();
-        u32 wpre = 0;
-#pragma unroll
-        for (int w = 0; w < CK_WARPS; ++w)
-            if (w < warp)
-                wpre += s_cnt[w];
-        u32 run = wpre + incl - sum;
-#pragma unroll
-        for (int j = 0; j < PER; ++j)
-        {
-            const u32 k = tid * PER + j;
-            if (k < nown)
-                s_coff[k] = run;
-            run += c[j];
-        }
-        if (tid == CK_THREADS - 1)
-            s_total = run;
-    }
-    __syncthreads();
-    const u32 total = s_total;
-
-    // ---- decoupled look-back over the tiles' entry counts
-    if (warp == 0)
-    {
-        u64 prefix = 0;
-        if (tile == 0)
-        {
-            if (lane == 0)
-                st_relaxed_u64(status, CS_INCL | (u64)total);
-        }
-        else
-        {
-            if (lane == 0)
-                st_relaxed_u64(status + tile, CS_LOCAL | (u64)total);
-            i64 t = (i64)tile - 1;
-            for (;;)
-            {
-                const i64 idx = t - lane;
-                u64 v = CS_INCL;
-                if (idx >= 0)
-                {
-                    do
-                    {
-                        v = ld_relaxed_u64(status + idx);
-                    } while ((v >> 62) == 0ull);
-                }
-                const u32 incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-                u64 contrib = v & CS_VALUE;
-                if (incl_mask)
-                {
-                    const int first = __ffs(incl_mask) - 1;
-                    if (lane > first)
-                        contrib = 0;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                prefix += contrib;
-                if (incl_mask)
-                    break;
-                t -= 32;
-            }
-            if (lane == 0)
-                st_relaxed_u64(status + tile, CS_INCL | (prefix + total));
-        }
-        if (lane == 0)
-        {
-            s_tileoff = prefix;
-            if (tile == ntiles - 1)
-                *d_nnz = prefix + total;
-        }
-    }
-    __syncthreads();
-    const u64 tileoff = s_tileoff;
-
-    // ---- write the entries and the per-column counts
-    for (u32 k = warp; k < nown; k += CK_WARPS)
-    {
-        const u32 c0 = s_cs[k];
-        const u32 cnt = s_ccnt[k];
-        const u64 o0 = tileoff + s_coff[k];
-        for (u32 j = lane; j < cnt; j += 32)
-        {
-            const Rec o = s_rec[c0 + j];
-            rowval[o0 + j] = (Ti)o.key + base;
-            nzval[o0 + j] = o.val;
-        }
-        if (lane == 0)
-            colcount[L.col(sorted[g0 + c0].key)] = cnt;
-    }
-}
 
 // ------------------------------------------------------------------------
 // colptr = base + exclusive sum of colcount
@@ -689,8 +371,7 @@ size_t column_workspace_bytes(u64 nrec, i64 ncols)
 
 size_t column_kernel_smem()
 {
-    return sizeof(Rec) * CK_CAP + 2 * sizeof(u32) * CK_CAP + sizeof(unsigned short) * (CK_CAP + 8 + CK_T) +
-           sizeof(u32) * CK_T + 16;
+    return sizeof(Rec) * CK_CAP + sizeof(u32) * CK_CAP + sizeof(unsigned short) * (CK_CAP + 8 + CK_T) + 16;
 }
 
 bool column_path_supported(const KeyLayout &L) { return L.rowbits <= 27 && L.colbits <= 32; }

@@ -533,6 +533,7 @@ def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
     A = oracle.OracleExt(m, n)
     A.insert_batch(I, J2, V, oracle.UPDATE)
     h = xsb.Handle(m, n)
+    h.set_strategy(xsb.capi.STRATEGY_AUTO)
     h.insert_batch(I, J2, V, xsb.UPDATE)
     h.flush()
     st = h.flush_stats()
@@ -547,6 +548,7 @@ def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
     A = oracle.OracleExt(50, len(lens))
     A.insert_batch(Il[perm], Jl[perm], Vl[perm], oracle.RAW)
     h = xsb.Handle(50, len(lens))
+    h.set_strategy(xsb.capi.STRATEGY_AUTO)
     h.insert_batch(Il[perm], Jl[perm], Vl[perm], xsb.RAW)
     h.flush()
     assert h.flush_stats()["column_path"] == 1
