@@ -19,7 +19,7 @@ I32, I64 = 0, 1
 UPDATE, RAW, ASSIGN = 0, 1, 2
 DETERMINISTIC, FAST = 0, 1
 COMBINE_SEED, COMBINE_ADD = 0, 1
-STRATEGY_AUTO, STRATEGY_FULLSORT = 0, 1
+STRATEGY_AUTO, STRATEGY_FULLSORT, STRATEGY_COLSORT = 0, 1, 2
 
 
 class XsbError(RuntimeError):
@@ -206,8 +206,9 @@ class Handle:
             n = int(splits[rank + 1]) - int(splits[rank])
             self.n_ranks, self.rank = n_ranks, rank
         self._h = h
-        if os.environ.get("XSB_STRATEGY", "").lower() == "fullsort":  # test/bench switch
-            check(lib().xsb_set_strategy(h, STRATEGY_FULLSORT), h)
+        strat = os.environ.get("XSB_STRATEGY", "").lower()  # test/bench switch
+        if strat in ("fullsort", "colsort"):
+            check(lib().xsb_set_strategy(h, STRATEGY_FULLSORT if strat == "fullsort" else STRATEGY_COLSORT), h)
         self.m, self.n = int(m), int(n)
         self.idx_type, self.index_base, self.n_tid, self.device = idx_type, index_base, n_tid, device
         self.idx_dtype = np.int64 if idx_type == I64 else np.int32

@@ -456,13 +456,48 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     Rec *sorted = nullptr, *spare = nullptr;
     void *new_rowval = nullptr;
     double *new_nzval = nullptr;
+    void *new_store = nullptr; // allocation that holds rowval|nzval after the flush
+    size_t new_store_bytes = 0;
     i64 nnz_new = -1;
     SortPlan plan{};
     int passes_run = 0;
-    bool column_path = h->strategy != XSB_STRATEGY_FULLSORT && column_path_supported(h->L);
-    if (column_path)
+    int path = 0; // 0: (col,row) sort + flat reduction, 1: column sort + in-tile row ordering, 2: column sort + hash fold
+    if (h->strategy == XSB_STRATEGY_AUTO && colfold_supported(h->L, (u64)total, h->n))
     {
-        // ---- sort by column only (half the passes); rows are ordered inside the reduce kernel
+        // ---- sort by column only; the per-column kernel folds duplicates through a hash table
+        void *cws = h->dalloc(colfold_workspace_bytes((u64)total, h->n));
+        colfold_clear_counts(s, cws, (u64)total, h->n);
+        plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
+        sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp, colfold_counts(cws, (u64)total, h->n),
+                                    h->L.low + h->L.rowbits, h->L.colbits);
+        passes_run += plan.npasses;
+        spare = (sorted == A) ? B : A;
+        colfold_reduce(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
+                       new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), h->lc, tp);
+        XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, sizeof(u64), cudaMemcpyDeviceToHost, s));
+        nnz_new = (i64)read_scalar(h, 0);
+        if ((u32)h->h_scal[6] == 0u)
+        {
+            const size_t rv_bytes = (h->isz() * (size_t)nnz_new + 15) & ~(size_t)15;
+            new_store_bytes = rv_bytes + 8 * (size_t)nnz_new;
+            new_store = h->dalloc(new_store_bytes);
+            new_rowval = new_store;
+            new_nzval = reinterpret_cast<double *>(static_cast<unsigned char *>(new_store) + rv_bytes);
+            colfold_compact(s, spare, (u64)total, h->n, h->idx64, h->base, new_colptr, new_rowval, new_nzval, cws,
+                            h->lc, tp);
+            h->dfree(spare); // back to the buffer cache
+            path = 2;
+        }
+        else
+        { // a group of columns too rich for the in-warp table: finish with the general sort (records are intact)
+            A = sorted;
+            B = spare;
+        }
+        h->dfree(cws);
+    }
+    else if (h->strategy == XSB_STRATEGY_COLSORT && column_path_supported(h->L))
+    {
+        // ---- sort by column only; rows are ordered inside the reduce kernel (bitonic, per column)
         plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
         sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
         passes_run += plan.npasses;
@@ -474,14 +509,19 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
                                reinterpret_cast<u32 *>(h->d_scal + 6), h->lc, tp);
         XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, sizeof(u64), cudaMemcpyDeviceToHost, s));
         nnz_new = (i64)read_scalar(h, 0);
-        if ((u32)h->h_scal[6] != 0u)
+        if ((u32)h->h_scal[6] == 0u)
+        {
+            path = 1;
+            new_store = spare;
+            new_store_bytes = sizeof(Rec) * (size_t)total;
+        }
+        else
         { // a column too long for the in-warp path: finish with the general sort (records are intact)
-            column_path = false;
             A = sorted;
             B = spare;
         }
     }
-    if (!column_path)
+    if (path == 0)
     {
         // ---- sort by (col,row), then a flat segmented reduction
         plan = make_sort_plan(h->L.low, h->L.sortbits());
@@ -493,7 +533,10 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         reduce_emit_csc(s, sorted, (u64)total, h->L, combine, mode, !h->has_assign, h->n, h->idx64, h->base,
                         new_rowval, new_nzval, new_colptr, ws, h->d_scal + 0, h->lc, tp);
         nnz_new = (i64)read_scalar(h, 0);
+        new_store = spare;
+        new_store_bytes = sizeof(Rec) * (size_t)total;
     }
+    const bool column_path = path != 0;
     h->last_column_path = column_path;
 
     if (tp)
@@ -502,8 +545,8 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
     h->colptr = new_colptr;
-    h->csc_store = spare;
-    h->csc_store_bytes = sizeof(Rec) * (size_t)total;
+    h->csc_store = new_store;
+    h->csc_store_bytes = new_store_bytes;
     h->rowval = new_rowval;
     h->nzval = new_nzval;
     h->nnz = nnz_new;
@@ -533,7 +576,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.nnz_new = nnz_new;
     h->stats.sort_passes = passes_run;
     h->stats.sort_bits = column_path ? h->L.colbits : h->L.sortbits();
-    h->stats.column_path = column_path ? 1 : 0;
+    h->stats.column_path = path;
     h->stats.kernel_launches = h->lc.in_flush;
     h->stats.ms_host_alloc = h->alloc_ms;
     if (tp)
@@ -1292,7 +1335,7 @@ int32_t xsb_timer_stop(xsb_matrix *h, float *ms_out)
 
 int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy)
 {
-    if (!h || (strategy != XSB_STRATEGY_AUTO && strategy != XSB_STRATEGY_FULLSORT))
+    if (!h || strategy < XSB_STRATEGY_AUTO || strategy > XSB_STRATEGY_COLSORT)
         return XSB_EINVAL;
     h->strategy = strategy;
     return XSB_OK;

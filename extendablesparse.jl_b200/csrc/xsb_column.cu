@@ -17,6 +17,7 @@
 // Columns longer than the in-warp limit raise an overflow flag; the caller then finishes with
 // the general (col,row) sort path.
 #include "xsb_internal.h"
+#include "xsb_fold.cuh"
 
 namespace xsb {
 
@@ -86,50 +87,6 @@ __device__ __forceinline__ u32 block_rank(const bool (&flag)[IPT], u32 (&excl)[I
     return total;
 }
 
-// bitonic sort of 32*E keys held E per lane (element index = lane*E + e), ascending
-template <int E> __device__ __forceinline__ void warp_bitonic(u32 (&k)[E], int lane)
-{
-    constexpr int N = 32 * E;
-#pragma unroll
-    for (int size = 2; size <= N; size <<= 1)
-    {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1)
-        {
-            if (stride >= E)
-            { // partner in another lane, same register slot
-                const int lstride = stride / E;
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                {
-                    const int g = lane * E + e;
-                    const u32 other = __shfl_xor_sync(0xffffffffu, k[e], lstride);
-                    const bool up = (g & size) == 0;      // ascending block
-                    const bool lower = (g & stride) == 0; // this element is the lower index of the pair
-                    const u32 mn = min(k[e], other), mx = max(k[e], other);
-                    k[e] = (up == lower) ? mn : mx;
-                }
-            }
-            else
-            { // both elements in this lane
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                {
-                    if ((e & stride) == 0)
-                    {
-                        const int g = lane * E + e;
-                        const bool up = (g & size) == 0;
-                        const u32 a = k[e], b = k[e + stride];
-                        const u32 mn = min(a, b), mx = max(a, b);
-                        k[e] = up ? mn : mx;
-                        k[e + stride] = up ? mx : mn;
-                    }
-                }
-            }
-        }
-    }
-}
-
 // Sorts one column (len <= 32*E records at s_col[0..len)) by (row, position) and permutes the
 // records in place into that order: keys are sorted in registers, every lane then gathers the
 // records of its E ranks, and only after the whole warp has read are they written back.
@@ -161,89 +118,6 @@ __device__ __forceinline__ void sort_column(const u32 *s_keycol, Rec *s_col, u32
             s_col[r] = t[e];
     }
 }
-
-struct ColFold
-{ // same semantics as RunFold in xsb_flush.cu (kept separate: different translation unit)
-    bool seeded = false, has_old = false, exists = false, pexists = false;
-    double old = 0.0, acc = 0.0, pacc = 0.0;
-    u32 ptid = 0xffffffffu;
-    __device__ __forceinline__ void commit()
-    {
-        if (pexists)
-        {
-            if (exists)
-                acc = acc + pacc;
-            else
-            {
-                acc = pacc;
-                exists = true;
-            }
-            pexists = false;
-        }
-    }
-    __device__ __forceinline__ void apply(u32 fl, u32 tid, double v, int combine)
-    {
-        if (fl == FL_OLD)
-        {
-            if (combine == 0)
-            {
-                seeded = true;
-                exists = true;
-                acc = v;
-            }
-            else
-            {
-                has_old = true;
-                old = v;
-            }
-            return;
-        }
-        if (seeded)
-        {
-            acc = (fl == FL_ASSIGN) ? v : acc + v;
-            return;
-        }
-        if (tid != ptid)
-        {
-            commit();
-            ptid = tid;
-        }
-        if (fl == FL_RAW)
-        {
-            pacc = pexists ? pacc + v : 0.0 + v;
-            pexists = true;
-        }
-        else if (fl == FL_UPDATE)
-        {
-            if (pexists)
-                pacc = pacc + v;
-            else if (v != 0.0)
-            {
-                pexists = true;
-                pacc = 0.0 + v;
-            }
-        }
-        else
-        {
-            if (pexists)
-                pacc = v;
-            else if (v != 0.0)
-            {
-                pexists = true;
-                pacc = v;
-            }
-        }
-    }
-    __device__ __forceinline__ void finish()
-    {
-        commit();
-        if (has_old)
-        {
-            acc = exists ? old + acc : old;
-            exists = true;
-        }
-    }
-};
 
 #include "xsb_column_kernel.cuh"
 

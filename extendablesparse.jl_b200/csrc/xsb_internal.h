@@ -74,8 +74,11 @@ struct StageTimer
 // ---- xsb_sort.cu
 SortPlan make_sort_plan(int begin_bit, int nbits);
 size_t sort_workspace_bytes(u64 n);
+// colcnt != nullptr: the histogram kernel also counts the records per column (key field
+// [colshift, colshift+colbits)) into colcnt[], which the caller has zeroed
 Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPlan &plan, void *workspace,
-                        LaunchCounter &lc, StageTimer *timer);
+                        LaunchCounter &lc, StageTimer *timer, u32 *colcnt = nullptr, int colshift = 0,
+                        int colbits = 0);
 
 void partition_records(cudaStream_t stream, const Rec *in, Rec *out, u64 n, int shift, int bits, void *workspace,
                        LaunchCounter &lc, u64 *counts_host);
@@ -111,6 +114,20 @@ void column_reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, Ke
                             bool plain_adds, i64 ncols, int idx64, int base, void *rowval_out, double *nzval_out,
                             void *colptr_out, void *workspace, u64 *d_nnz, u32 *d_overflow, LaunchCounter &lc,
                             StageTimer *timer);
+
+// ---- xsb_colfold.cu
+size_t colfold_workspace_bytes(u64 nrec, i64 ncols);
+bool colfold_supported(const KeyLayout &L, u64 nrec, i64 ncols);
+u32 *colfold_counts(void *workspace, u64 nrec, i64 ncols);
+void colfold_clear_counts(cudaStream_t stream, void *workspace, u64 nrec, i64 ncols);
+// records sorted by column only (stable) + per-column record counts -> entries parked in tmp, colptr, nnz
+void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine, bool plain_adds,
+                    i64 ncols, int idx64, int base, Rec *tmp, void *colptr_out, void *workspace, u64 *d_nnz,
+                    u32 *d_overflow, LaunchCounter &lc, StageTimer *timer);
+// parked entries -> rowval / nzval
+void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, int idx64, int base,
+                     const void *colptr, void *rowval_out, double *nzval_out, void *workspace, LaunchCounter &lc,
+                     StageTimer *timer);
 
 // ---- xsb_insert.cu
 // (I,J,V) -> records; *d_err receives the smallest offending index (or ~0)

@@ -17,22 +17,45 @@ namespace xsb {
 // ------------------------------------------------------------------------
 constexpr int HIST_THREADS = 512;
 
+// With colcnt != nullptr the kernel also counts the records of every column (the field
+// [colshift, colshift+colbits) of the key): one global atomic per distinct column of a warp's 32
+// consecutive records.  The per-column kernels of xsb_colfold.cu take their column list from it.
 __global__ void __launch_bounds__(HIST_THREADS)
-histogram_kernel(const Rec *__restrict__ in, u64 n, SortPlan plan, u64 *__restrict__ ghist)
+histogram_kernel(const Rec *__restrict__ in, u64 n, SortPlan plan, u64 *__restrict__ ghist, u32 *__restrict__ colcnt,
+                 int colshift, int colbits)
 {
     __shared__ u32 s_hist[kMaxPasses][kRadix];
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += HIST_THREADS)
         (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * HIST_THREADS;
+    const int lane = threadIdx.x & 31;
+    const u32 lt = lanemask_lt();
+    const u64 colmask = (1ull << colbits) - 1ull;
     // 32-bit shared counters: one block sees n/gridDim.x < 2^32 keys for every n that fits in HBM
-    for (u64 k = (u64)blockIdx.x * HIST_THREADS + threadIdx.x; k < n; k += stride)
-    {
-        const u64 key = in[k].key;
+    for (u64 k0 = (u64)blockIdx.x * HIST_THREADS + (threadIdx.x - lane); k0 < n; k0 += stride)
+    { // k0 is warp-uniform
+        const u64 k = k0 + lane;
+        const bool valid = k < n;
+        const u64 key = valid ? in[k].key : 0ull;
+        if (valid)
+        {
 #pragma unroll
-        for (int p = 0; p < kMaxPasses; ++p)
-            if (p < plan.npasses)
-                atomicAdd(&s_hist[p][(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+            for (int p = 0; p < kMaxPasses; ++p)
+                if (p < plan.npasses)
+                    atomicAdd(&s_hist[p][(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+        }
+        if (colcnt != nullptr)
+        {
+            const u32 vm = __ballot_sync(0xffffffffu, valid);
+            if (valid)
+            {
+                const u32 col = (u32)((key >> colshift) & colmask);
+                const u32 peers = __match_any_sync(vm, col);
+                if ((peers & lt) == 0u)
+                    atomicAdd(&colcnt[col], (u32)__popc(peers));
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < plan.npasses * kRadix; i += HIST_THREADS)
@@ -331,9 +354,10 @@ size_t sort_workspace_bytes(u64 n)
 // Sorts n records by key bits [begin_bit, begin_bit+nbits).  `a` holds the input;
 // `b` is scratch of the same size.  Returns the buffer that holds the result.
 Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPlan &plan, void *workspace,
-                        LaunchCounter &lc, StageTimer *timer)
+                        LaunchCounter &lc, StageTimer *timer, u32 *colcnt, int colshift, int colbits)
 {
-    if (n <= 1 || plan.npasses == 0)
+    const bool nosort = n <= 1 || plan.npasses == 0;
+    if (nosort && (colcnt == nullptr || n == 0))
         return a;
     const OnesweepVariant &var = kVariants[g_variant];
     static bool attr_set[kNumVariants] = {};
@@ -357,14 +381,19 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
     {
         const u64 want = (n + HIST_THREADS * 8 - 1) / (HIST_THREADS * 8);
         const int blocks = (int)std::min<u64>(std::max<u64>(want, 1), (u64)kNumSM * 4);
-        histogram_kernel<<<blocks, HIST_THREADS, 0, stream>>>(a, n, plan, ghist);
+        histogram_kernel<<<blocks, HIST_THREADS, 0, stream>>>(a, n, plan, ghist, colcnt, colshift, colbits);
         lc.add();
-        histogram_scan_kernel<<<plan.npasses, kRadix, 0, stream>>>(ghist, plan.npasses);
-        lc.add();
+        if (plan.npasses > 0)
+        {
+            histogram_scan_kernel<<<plan.npasses, kRadix, 0, stream>>>(ghist, plan.npasses);
+            lc.add();
+        }
         XSB_CUDA(cudaGetLastError());
     }
     if (timer)
         timer->end(stream, &StageTimes::histogram);
+    if (nosort)
+        return a; // only the column counts were wanted
 
     if (timer)
         timer->begin(stream);
@@ -419,7 +448,7 @@ void partition_records(cudaStream_t stream, const Rec *in, Rec *out, u64 n, int 
     XSB_CUDA(cudaMemsetAsync(ghist, 0, sizeof(u64) * kMaxPasses * kRadix, stream));
     const u64 want = (n + HIST_THREADS * 8 - 1) / (HIST_THREADS * 8);
     const int blocks = (int)std::min<u64>(std::max<u64>(want, 1), (u64)kNumSM * 4);
-    histogram_kernel<<<blocks, HIST_THREADS, 0, stream>>>(in, n, plan, ghist);
+    histogram_kernel<<<blocks, HIST_THREADS, 0, stream>>>(in, n, plan, ghist, nullptr, 0, 0);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     std::vector<u64> h((size_t)nb);

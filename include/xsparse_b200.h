@@ -82,7 +82,7 @@ typedef struct xsb_flush_stats
     int32_t sort_passes;      /* onesweep passes executed              */
     int32_t sort_bits;        /* key bits sorted                       */
     int32_t kernel_launches;  /* kernels launched by the flush         */
-    int32_t column_path;      /* 1: column-only sort + in-tile row ordering produced the result */
+    int32_t column_path;      /* 0: (col,row) sort; 1: column sort + in-tile row ordering; 2: column sort + hash fold */
     float ms_total;           /* device time of the whole flush (CUDA events; 0 unless profiling on) */
     float ms_expand;          /* old CSC -> records                    */
     float ms_histogram;       /* digit histogram + scan                */
@@ -246,11 +246,13 @@ int32_t xsb_timer_start(xsb_matrix *h);
 int32_t xsb_timer_stop(xsb_matrix *h, float *ms_out);
 /* Per-stage CUDA-event timing inside xsb_flush (off by default). */
 int32_t xsb_set_profiling(xsb_matrix *h, int32_t enable);
-/* Flush algorithm.  AUTO: radix sort on the column bits only, rows ordered per column inside the
- * reduce kernel (falls back by itself when a column exceeds the in-warp limit).
- * FULLSORT: radix sort on the whole (col,row) key, flat segmented reduction.  Same results. */
+/* Flush algorithm.  AUTO: stable radix sort on the column bits only; a warp per group of columns
+ * folds duplicates through a shared-memory hash table in stream order and sorts only the distinct
+ * entries by row (falls back by itself when a group exceeds the table).  All strategies give the
+ * same bits. */
 #define XSB_STRATEGY_AUTO 0
-#define XSB_STRATEGY_FULLSORT 1
+#define XSB_STRATEGY_FULLSORT 1 /* (col,row) radix sort + flat segmented reduction */
+#define XSB_STRATEGY_COLSORT 2  /* column-only sort + per-column bitonic row ordering  */
 int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy);
 int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
 /* Total kernels launched by this handle since creation. */

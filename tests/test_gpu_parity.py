@@ -510,8 +510,9 @@ def test_full_size_fd_properties(xsb):
 
 # ---------------------------------------------------------------- flush strategies
 def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
-    """Column-only sort + in-tile row ordering (AUTO) and the (col,row) sort (FULLSORT) give the
-    same bits; a column longer than the in-warp limit makes AUTO finish with the general path."""
+    """Column sort + hash fold (AUTO), column sort + in-tile row ordering (COLSORT) and the (col,row)
+    sort (FULLSORT) give the same bits; a column too rich for the in-warp paths makes AUTO and
+    COLSORT finish with the general path."""
     rng = np.random.default_rng(77)
     m, n, cnt = 3000, 500, 60000
     I = rng.integers(1, m + 1, cnt)
@@ -520,7 +521,8 @@ def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
     A = oracle.OracleExt(m, n)
     A.insert_batch(I, J, V, oracle.UPDATE)
     ref = A.csc()
-    for strat, expect_col in ((xsb.capi.STRATEGY_AUTO, 1), (xsb.capi.STRATEGY_FULLSORT, 0)):
+    for strat, expect_col in ((xsb.capi.STRATEGY_AUTO, 2), (xsb.capi.STRATEGY_COLSORT, 1),
+                              (xsb.capi.STRATEGY_FULLSORT, 0)):
         h = xsb.Handle(m, n)
         h.set_strategy(strat)
         h.insert_batch(I, J, V, xsb.UPDATE)
@@ -532,13 +534,14 @@ def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
     J2[:3000] = 7
     A = oracle.OracleExt(m, n)
     A.insert_batch(I, J2, V, oracle.UPDATE)
-    h = xsb.Handle(m, n)
-    h.set_strategy(xsb.capi.STRATEGY_AUTO)
-    h.insert_batch(I, J2, V, xsb.UPDATE)
-    h.flush()
-    st = h.flush_stats()
-    assert st["column_path"] == 0 and st["sort_passes"] > 3
-    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    for strat in (xsb.capi.STRATEGY_AUTO, xsb.capi.STRATEGY_COLSORT):
+        h = xsb.Handle(m, n)
+        h.set_strategy(strat)
+        h.insert_batch(I, J2, V, xsb.UPDATE)
+        h.flush()
+        st = h.flush_stats()
+        assert st["column_path"] == 0 and st["sort_passes"] > 3
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
     # columns of every length around the warp-sort sizes (31..257 records), duplicates included
     lens = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256]
     Jl = np.concatenate([np.full(L, k + 1) for k, L in enumerate(lens)])
@@ -547,9 +550,49 @@ def test_strategies_agree_and_long_columns_fall_back(xsb, oracle):
     perm = rng.permutation(len(Jl))
     A = oracle.OracleExt(50, len(lens))
     A.insert_batch(Il[perm], Jl[perm], Vl[perm], oracle.RAW)
-    h = xsb.Handle(50, len(lens))
-    h.set_strategy(xsb.capi.STRATEGY_AUTO)
-    h.insert_batch(Il[perm], Jl[perm], Vl[perm], xsb.RAW)
-    h.flush()
-    assert h.flush_stats()["column_path"] == 1
-    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    for strat, expect_col in ((xsb.capi.STRATEGY_AUTO, 2), (xsb.capi.STRATEGY_COLSORT, 1)):
+        h = xsb.Handle(50, len(lens))
+        h.set_strategy(strat)
+        h.insert_batch(Il[perm], Jl[perm], Vl[perm], xsb.RAW)
+        h.flush()
+        assert h.flush_stats()["column_path"] == expect_col
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+def test_hash_fold_groups_of_columns(xsb, oracle):
+    """The hash-fold kernel on shapes that stress its grouping: many short columns per group, columns
+    around the group size, a long column with few distinct rows, empty columns in between, all three
+    flavours, several partitions and a second flush on top of the first (old entries seed the fold)."""
+    rng = np.random.default_rng(4242)
+    m, n = 5000, 4000
+    lens = np.concatenate([rng.integers(0, 6, 1500), rng.integers(100, 140, 40), [2000, 1, 0, 0, 700],
+                           rng.integers(20, 70, 300)])
+    cols = rng.permutation(n)[: len(lens)] + 1
+    J = np.repeat(cols, lens)
+    I = np.empty(len(J), dtype=np.int64)
+    pos = 0
+    for L in lens:
+        I[pos:pos + L] = rng.integers(1, min(150, max(3, int(L) // 3) + 8), L)  # plenty of duplicates
+        pos += L
+    V = rng.standard_normal(len(J))
+    V[rng.random(len(J)) < 0.05] = 0.0
+    perm = rng.permutation(len(J))
+    I, J, V = I[perm], J[perm], V[perm]
+    for n_tid in (1, 3):
+        A = oracle.OracleMT(m, n, n_tid) if n_tid > 1 else oracle.OracleExt(m, n)
+        h = xsb.Handle(m, n, n_tid=n_tid)
+        for rnd in range(2):
+            parts = np.array_split(np.arange(len(J)), 3 * n_tid)
+            for q, idx in enumerate(parts):
+                fl = (xsb.UPDATE, xsb.RAW, xsb.ASSIGN)[q % 3] if n_tid == 1 else (xsb.UPDATE, xsb.RAW)[q % 2]
+                ofl = {xsb.UPDATE: oracle.UPDATE, xsb.RAW: oracle.RAW, xsb.ASSIGN: oracle.ASSIGN}[fl]
+                if n_tid > 1:  # partitions deliver in tid order: CSC hits are applied in call order
+                    A.insert_batch(I[idx], J[idx], V[idx] * (rnd + 1), q // 3 + 1, ofl)
+                    h.insert_batch(I[idx], J[idx], V[idx] * (rnd + 1), fl, tid=q // 3)
+                else:
+                    A.insert_batch(I[idx], J[idx], V[idx] * (rnd + 1), ofl)
+                    h.insert_batch(I[idx], J[idx], V[idx] * (rnd + 1), fl)
+            A.flush()
+            h.flush()
+            assert h.flush_stats()["column_path"] == 2
+            assert_csc_equal(h.fetch_csc_numpy(), A.csc())
