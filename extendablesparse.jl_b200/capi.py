@@ -20,6 +20,7 @@ UPDATE, RAW, ASSIGN = 0, 1, 2
 DETERMINISTIC, FAST = 0, 1
 COMBINE_SEED, COMBINE_ADD = 0, 1
 STRATEGY_AUTO, STRATEGY_FULLSORT, STRATEGY_COLSORT = 0, 1, 2
+GROUPING_AUTO, GROUPING_OFF, GROUPING_ON = 0, 1, 2
 
 
 class XsbError(RuntimeError):
@@ -57,6 +58,7 @@ class FlushStats(C.Structure):
         ("ms_colptr", C.c_float),
         ("ms_other", C.c_float),
         ("ms_host_alloc", C.c_float),
+        ("group_pairs", C.c_int64),
     ]
 
     def as_dict(self):
@@ -113,6 +115,7 @@ SIGNATURES = {
     "xsb_timer_stop": (_i32, [_p, C.POINTER(C.c_float)]),
     "xsb_set_profiling": (_i32, [_p, _i32]),
     "xsb_set_strategy": (_i32, [_p, _i32]),
+    "xsb_set_grouping": (_i32, [_p, _i32]),
     "xsb_get_flush_stats": (_i32, [_p, C.POINTER(FlushStats)]),
     "xsb_kernel_launches": (_i32, [_p, C.POINTER(_i64)]),
 }
@@ -207,6 +210,8 @@ class Handle:
             self.n_ranks, self.rank = n_ranks, rank
         self._h = h
         strat = os.environ.get("XSB_STRATEGY", "").lower()  # test/bench switch
+        if os.environ.get("XSB_GROUPING", "").lower() in ("off", "on"):
+            check(lib().xsb_set_grouping(h, GROUPING_OFF if os.environ["XSB_GROUPING"].lower() == "off" else GROUPING_ON), h)
         if strat in ("fullsort", "colsort"):
             check(lib().xsb_set_strategy(h, STRATEGY_FULLSORT if strat == "fullsort" else STRATEGY_COLSORT), h)
         self.m, self.n = int(m), int(n)
@@ -370,6 +375,11 @@ class Handle:
         ms = C.c_float(0)
         self._c(lib().xsb_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def set_grouping(self, grouping):
+        """GROUPING_AUTO (two-pass grouping by column when the stream has column locality), GROUPING_OFF
+        (always the radix sort) or GROUPING_ON (always try)."""
+        self._c(lib().xsb_set_grouping(self._h, int(grouping)))
 
     def set_strategy(self, strategy):
         """STRATEGY_AUTO (column sort + in-tile row ordering) or STRATEGY_FULLSORT ((col,row) sort)."""

@@ -216,6 +216,9 @@ struct xsb_matrix
     }
     size_t shrink_surplus_bytes = (size_t)16 << 30;
     int strategy = XSB_STRATEGY_AUTO;
+    int grouping = XSB_GROUPING_AUTO; // two-pass grouping by column before the hash fold
+    int grouping_misses = 0;          // consecutive flushes whose stream had no column locality
+    i64 stats_pairs = 0;
     bool last_column_path = false;
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
@@ -414,6 +417,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
 
     const i64 nnz_old = h->nnz;
     const i64 total = nnz_old + n_ins;
+    h->stats_pairs = 0;
     REQUIRE((u64)total < (1ull << 40), XSB_EINVAL, "too many staged entries");
 
     // ---- input buffer A = [old CSC as records | staged records in tid order]
@@ -466,14 +470,42 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     {
         // ---- sort by column only; the per-column kernel folds duplicates through a hash table
         void *cws = h->dalloc(colfold_workspace_bytes((u64)total, h->n));
-        colfold_clear_counts(s, cws, (u64)total, h->n);
-        plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
-        sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp, colfold_counts(cws, (u64)total, h->n),
-                                    h->L.low + h->L.rowbits, h->L.colbits);
-        passes_run += plan.npasses;
-        spare = (sorted == A) ? B : A;
+        bool grouped = false;
+        if (h->grouping != XSB_GROUPING_OFF && (h->grouping == XSB_GROUPING_ON || h->grouping_misses < 2) &&
+            group_supported(h->L, (u64)total, h->n))
+        { // two-pass grouping through sparse per-chunk column histograms (streams with column locality)
+            void *gws = h->dalloc(group_workspace_bytes((u64)total));
+            u32 *nzcol, *nzstart;
+            u64 *totals;
+            colfold_lists(cws, (u64)total, h->n, &nzcol, &nzstart, &totals);
+            int pair_passes = 0;
+            u64 npairs = 0;
+            grouped = group_by_column(s, A, B, (u64)total, h->L, gws, ws, nzcol, nzstart, totals, h->h_scal + 4,
+                                      h->d_scal + 4, h->lc, tp, &pair_passes, &npairs);
+            h->dfree(gws);
+            h->stats_pairs = (i64)npairs;
+            if (grouped)
+            {
+                sorted = B;
+                spare = A;
+                passes_run += pair_passes;
+                h->grouping_misses = 0;
+            }
+            else if (h->grouping == XSB_GROUPING_AUTO)
+                h->grouping_misses++; // two misses in a row: stop trying on this handle
+        }
+        if (!grouped)
+        {
+            colfold_clear_counts(s, cws, (u64)total, h->n);
+            plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
+            sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp, colfold_counts(cws, (u64)total, h->n),
+                                        h->L.low + h->L.rowbits, h->L.colbits);
+            passes_run += plan.npasses;
+            spare = (sorted == A) ? B : A;
+        }
         colfold_reduce(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
-                       new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), h->lc, tp);
+                       new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), grouped, h->lc, tp);
+        path = grouped ? 3 : 2;
         XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, sizeof(u64), cudaMemcpyDeviceToHost, s));
         nnz_new = (i64)read_scalar(h, 0);
         if ((u32)h->h_scal[6] == 0u)
@@ -486,12 +518,12 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             colfold_compact(s, spare, (u64)total, h->n, h->idx64, h->base, new_colptr, new_rowval, new_nzval, cws,
                             h->lc, tp);
             h->dfree(spare); // back to the buffer cache
-            path = 2;
         }
         else
         { // a group of columns too rich for the in-warp table: finish with the general sort (records are intact)
             A = sorted;
             B = spare;
+            path = 0;
         }
         h->dfree(cws);
     }
@@ -579,6 +611,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.column_path = path;
     h->stats.kernel_launches = h->lc.in_flush;
     h->stats.ms_host_alloc = h->alloc_ms;
+    h->stats.group_pairs = h->stats_pairs;
     if (tp)
     {
         XSB_CUDA(cudaEventRecord(e1, s));
@@ -1338,6 +1371,15 @@ int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy)
     if (!h || strategy < XSB_STRATEGY_AUTO || strategy > XSB_STRATEGY_COLSORT)
         return XSB_EINVAL;
     h->strategy = strategy;
+    return XSB_OK;
+}
+
+int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping)
+{
+    if (!h || grouping < XSB_GROUPING_AUTO || grouping > XSB_GROUPING_ON)
+        return XSB_EINVAL;
+    h->grouping = grouping;
+    h->grouping_misses = 0;
     return XSB_OK;
 }
 

@@ -765,6 +765,20 @@ CfLayout cf_layout(u64 nrec, i64 ncols)
 
 size_t colfold_workspace_bytes(u64 nrec, i64 ncols) { return cf_layout(nrec, ncols).bytes; }
 
+void colscan_scan_launch(cudaStream_t stream, u64 *trec, u32 *tnz, i64 nt, u64 *totals, u32 *nzstart)
+{
+    colscan_scan_kernel<<<1, 1024, 0, stream>>>(trec, tnz, nt, totals, nzstart);
+}
+
+void colfold_lists(void *workspace, u64 nrec, i64 ncols, u32 **nzcol, u32 **nzstart, u64 **totals)
+{
+    const CfLayout l = cf_layout(nrec, ncols);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    *nzcol = reinterpret_cast<u32 *>(ws + l.off_nzcol);
+    *nzstart = reinterpret_cast<u32 *>(ws + l.off_nzstart);
+    *totals = reinterpret_cast<u64 *>(ws + l.off_tot);
+}
+
 bool colfold_supported(const KeyLayout &L, u64 nrec, i64 ncols)
 {
     return L.rowbits <= CF_MAXROWBITS && L.low <= 32 && nrec < (1ull << 32) - (u64)CF_SPAN &&
@@ -786,7 +800,7 @@ void colfold_clear_counts(cudaStream_t stream, void *workspace, u64 nrec, i64 nc
 // *d_overflow != 0 if a group of columns did not fit the in-warp table (outputs then undefined).
 void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine, bool plain_adds,
                     i64 ncols, int idx64, int base, Rec *tmp, void *colptr_out, void *workspace, u64 *d_nnz,
-                    u32 *d_overflow, LaunchCounter &lc, StageTimer *timer)
+                    u32 *d_overflow, bool lists_ready, LaunchCounter &lc, StageTimer *timer)
 {
     const CfLayout l = cf_layout(nrec, ncols);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -805,11 +819,17 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     if (timer)
         timer->begin(stream);
     XSB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(u32), stream));
-    colscan_tilesum_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, ncols, trec, tnz);
-    colscan_scan_kernel<<<1, 1024, 0, stream>>>(trec, tnz, (i64)ctiles, totals, nzstart);
-    colscan_emit_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, trec, tnz, ncols, nzcol, nzstart);
+    if (!lists_ready)
+    { // column list from the per-column record counts (taken by the sort's histogram kernel)
+        colscan_tilesum_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, ncols, trec, tnz);
+        colscan_scan_kernel<<<1, 1024, 0, stream>>>(trec, tnz, (i64)ctiles, totals, nzstart);
+        colscan_emit_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, trec, tnz, ncols, nzcol, nzstart);
+        lc.add(3);
+    }
+    else // the grouping pass made the list; cnt only receives the entry counts of non-empty columns
+        XSB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(u32) * ((size_t)ncols + 1), stream));
     tilemap_kernel<<<(unsigned)((kmax + 1 + 255) / 256), 256, 0, stream>>>(nzstart, totals, ntiles, tilek);
-    lc.add(4);
+    lc.add(1);
     XSB_CUDA(cudaGetLastError());
     if (timer)
         timer->end(stream, &StageTimes::colptr);

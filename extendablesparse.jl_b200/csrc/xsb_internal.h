@@ -123,7 +123,16 @@ void colfold_clear_counts(cudaStream_t stream, void *workspace, u64 nrec, i64 nc
 // records sorted by column only (stable) + per-column record counts -> entries parked in tmp, colptr, nnz
 void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine, bool plain_adds,
                     i64 ncols, int idx64, int base, Rec *tmp, void *colptr_out, void *workspace, u64 *d_nnz,
-                    u32 *d_overflow, LaunchCounter &lc, StageTimer *timer);
+                    u32 *d_overflow, bool lists_ready, LaunchCounter &lc, StageTimer *timer);
+void colfold_lists(void *workspace, u64 nrec, i64 ncols, u32 **nzcol, u32 **nzstart, u64 **totals);
+
+// ---- xsb_group.cu
+size_t group_workspace_bytes(u64 nrec);
+bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols);
+// stable grouping by column in two passes (sparse per-chunk histograms); false: no column locality
+bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
+                     void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
+                     LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out);
 // parked entries -> rowval / nzval
 void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, int idx64, int base,
                      const void *colptr, void *rowval_out, double *nzval_out, void *workspace, LaunchCounter &lc,

@@ -82,7 +82,8 @@ typedef struct xsb_flush_stats
     int32_t sort_passes;      /* onesweep passes executed              */
     int32_t sort_bits;        /* key bits sorted                       */
     int32_t kernel_launches;  /* kernels launched by the flush         */
-    int32_t column_path;      /* 0: (col,row) sort; 1: column sort + in-tile row ordering; 2: column sort + hash fold */
+    int32_t column_path;      /* 0: (col,row) sort + flat reduction; 1: column sort + in-tile row ordering;
+                                 2: column sort + hash fold; 3: two-pass grouping by column + hash fold */
     float ms_total;           /* device time of the whole flush (CUDA events; 0 unless profiling on) */
     float ms_expand;          /* old CSC -> records                    */
     float ms_histogram;       /* digit histogram + scan                */
@@ -91,6 +92,7 @@ typedef struct xsb_flush_stats
     float ms_colptr;          /* colptr scan                           */
     float ms_other;           /* buffer management, shrink copy        */
     float ms_host_alloc;      /* host wall time spent in device allocations during the flush */
+    int64_t group_pairs;      /* (chunk, column) pairs of the two-pass grouping; 0 when it was not tried */
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */
@@ -254,6 +256,15 @@ int32_t xsb_set_profiling(xsb_matrix *h, int32_t enable);
 #define XSB_STRATEGY_FULLSORT 1 /* (col,row) radix sort + flat segmented reduction */
 #define XSB_STRATEGY_COLSORT 2  /* column-only sort + per-column bitonic row ordering  */
 int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy);
+/* How STRATEGY_AUTO brings the records of a column together.  AUTO: try the two-pass grouping
+ * (sparse per-chunk column histograms; pays off when consecutive insertions touch few distinct
+ * columns, as element-by-element assembly does) and use the radix sort when the stream has no
+ * such locality; after two such misses in a row the handle stops trying.  OFF: always the radix
+ * sort.  ON: always try. */
+#define XSB_GROUPING_AUTO 0
+#define XSB_GROUPING_OFF 1
+#define XSB_GROUPING_ON 2
+int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping);
 int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
 /* Total kernels launched by this handle since creation. */
 int32_t xsb_kernel_launches(const xsb_matrix *h, int64_t *count);

@@ -596,3 +596,77 @@ def test_hash_fold_groups_of_columns(xsb, oracle):
             h.flush()
             assert h.flush_stats()["column_path"] == 2
             assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+# ---------------------------------------------------------------- two-pass grouping by column
+def test_grouping_by_column_fem_and_fallback(xsb, oracle):
+    """Streams with column locality take the two-pass grouping (sparse per-chunk column histograms);
+    a stream without locality is detected after the counting pass and takes the radix sort.  Same bits
+    either way, also on top of a resident CSC and with several partitions."""
+    I, J, V = oracle.fem_stream(12, 12, 12)
+    N = 12 ** 3
+    assert len(V) >= 32768
+    A = oracle.OracleExt(N, N)
+    A.insert_batch(I, J, V, oracle.RAW)
+    ref = A.csc()
+    got = {}
+    for grouping in (xsb.capi.GROUPING_AUTO, xsb.capi.GROUPING_OFF):
+        h = xsb.Handle(N, N)
+        h.set_grouping(grouping)
+        h.insert_batch(I, J, V, xsb.RAW)
+        h.flush()
+        st = h.flush_stats()
+        assert st["column_path"] == (3 if grouping == xsb.capi.GROUPING_AUTO else 2)
+        if grouping == xsb.capi.GROUPING_AUTO:
+            assert 0 < st["group_pairs"] < len(V) // 4
+        got[grouping] = h.fetch_csc_numpy()
+        assert_csc_equal(got[grouping], ref)
+        # second assembly on top of the resident CSC, scaled values, update flavour with some zeros
+        V2 = V * 0.5
+        V2[::7] = 0.0
+        h.insert_batch(I, J, V2, xsb.UPDATE)
+        h.flush()
+        A2 = oracle.OracleExt(N, N)
+        A2.insert_batch(I, J, V, oracle.RAW)
+        A2.flush()
+        A2.insert_batch(I, J, V2, oracle.UPDATE)
+        assert_csc_equal(h.fetch_csc_numpy(), A2.csc())
+    # no locality: random columns -> about one pair per record -> radix sort
+    rng = np.random.default_rng(5)
+    m, n, cnt = 30000, 30000, 80000
+    Ir = rng.integers(1, m + 1, cnt)
+    Jr = rng.integers(1, n + 1, cnt)
+    Vr = rng.standard_normal(cnt)
+    B = oracle.OracleExt(m, n)
+    B.insert_batch(Ir, Jr, Vr, oracle.UPDATE)
+    h = xsb.Handle(m, n)
+    h.set_grouping(xsb.capi.GROUPING_ON)
+    h.insert_batch(Ir, Jr, Vr, xsb.UPDATE)
+    h.flush()
+    st = h.flush_stats()
+    assert st["column_path"] == 2 and st["group_pairs"] > cnt // 4
+    assert_csc_equal(h.fetch_csc_numpy(), B.csc())
+    # several partitions (general fold) through the grouping
+    nparts = 3
+    hm = xsb.Handle(N, N, n_tid=nparts)
+    M = oracle.OracleMT(N, N, nparts)
+    for t, c in enumerate(np.array_split(np.arange(len(V)), nparts)):
+        hm.insert_batch(I[c], J[c], V[c], xsb.RAW, tid=t)
+        M.insert_batch(I[c], J[c], V[c], t + 1, oracle.RAW)
+    hm.flush()
+    assert hm.flush_stats()["column_path"] == 3
+    assert_csc_equal(hm.fetch_csc_numpy(), M.csc())
+
+
+def test_grouping_fdrand_large(xsb, oracle):
+    """fdrand 3-D 40^3 through the generator kernel: short columns, little duplication."""
+    nx = 40
+    N = nx ** 3
+    h = xsb.Handle(N, N)
+    h.emit_fdrand(nx, nx, nx, seed=3)
+    h.flush()
+    assert h.flush_stats()["column_path"] == 3
+    I, J, V = oracle.fdrand_stream(nx, nx, nx, seed=3)
+    A = oracle.OracleExt(N, N)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
