@@ -5,10 +5,10 @@
 //
 //   group_count_kernel   : a warp owns a chunk of GP_W consecutive records.  It finds the chunk's
 //                          distinct columns with a shared-memory hash table and counts the records
-//                          of each; the (column, count) pairs of all chunks are appended in chunk
-//                          order (decoupled look-back over the chunks' pair counts).
-//   radix sort of the PAIRS by column (xsb_sort.cu; stable, so pairs of one column stay in chunk
-//                          = stream order).  There are 4-12x fewer pairs than records.
+//                          of each; the (column, chunk, count) pairs of all chunks are appended to
+//                          one list (one atomic per chunk: no ordering between chunks is needed).
+//   radix sort of the PAIRS by (column, chunk) (xsb_sort.cu): pairs of one column end up in chunk
+//                          = stream order.  There are 4-12x fewer pairs than records.
 //   pair_scan kernels    : exclusive sum of the counts in sorted order = where the records of
 //                          (column, chunk) start in the output; column heads give the compact
 //                          column list (nzcol, nzstart) the per-column kernels need.
@@ -28,41 +28,34 @@ namespace xsb {
 
 constexpr int GP_W = 512;           // records per chunk (one warp)
 constexpr int GP_NB = GP_W / 32;    // batches per chunk
-constexpr int GP_HBITS = 10;
-constexpr int GP_H = 1 << GP_HBITS; // hash slots per warp (>= 2 * GP_W)
+constexpr int GP_HBITS = 9;
+constexpr int GP_H = 1 << GP_HBITS; // hash slots per warp
+constexpr int GP_DMAX = GP_H - 96;  // distinct columns a chunk may hold; more means "no locality" anyway
 constexpr int GP_WARPS = 8;
 constexpr u32 GP_EMPTY = 0xffffffffu;
-
-constexpr u64 GS_LOCAL = 1ull << 62;
-constexpr u64 GS_INCL = 2ull << 62;
-constexpr u64 GS_VALUE = (1ull << 62) - 1ull;
 
 __device__ __forceinline__ u32 gp_hash(u32 col) { return (col * 0x9E3779B1u) >> (32 - GP_HBITS); }
 
 struct CountSpace
 {
     u32 key[GP_H];
-    unsigned short cnt[GP_H];
-    unsigned short cand[GP_W];
+    u32 cnt[GP_H];
+    unsigned short cand[GP_H];
 };
 
 // ------------------------------------------------------------------------
 // pass 1: distinct columns of every chunk and their record counts
 // ------------------------------------------------------------------------
-__global__ void __launch_bounds__(GP_WARPS * 32, 3)
-group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks,
-                   u32 *__restrict__ ticket, u64 *__restrict__ status, Rec *__restrict__ pairs,
-                   u32 *__restrict__ chunkcols, u32 *__restrict__ chunkbase, u32 cap, u32 *__restrict__ d_flags)
+__global__ void __launch_bounds__(GP_WARPS * 32, 5)
+group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks, int chunkbits,
+                   u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
+                   uint2 *__restrict__ chunkinfo, u32 cap, u32 *__restrict__ d_flags)
 {
     constexpr u32 full = 0xffffffffu;
-    __shared__ u32 s_ticket;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CountSpace &ws = reinterpret_cast<CountSpace *>(smem_raw)[warp];
-    if (threadIdx.x == 0)
-        s_ticket = atomicAdd(ticket, 1u); // chunks are claimed in launch order: predecessors always run
-    __syncthreads();
-    const u32 chunk = s_ticket * GP_WARPS + warp;
+    const u32 chunk = blockIdx.x * GP_WARPS + warp;
     if (chunk >= nchunks)
         return;
     const u32 lt = lanemask_lt();
@@ -76,129 +69,103 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
             kq[i * 32 + lane] = make_uint4(GP_EMPTY, GP_EMPTY, GP_EMPTY, GP_EMPTY);
         uint4 *cq = reinterpret_cast<uint4 *>(ws.cnt);
 #pragma unroll
-        for (int i = 0; i < GP_H / 256; ++i)
+        for (int i = 0; i < GP_H / 128; ++i)
             cq[i * 32 + lane] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
 
     u32 d = 0;
-#pragma unroll 1
-    for (int g = 0; g < GP_NB; g += 4)
+    bool crowded = false;
+    u64 key[4], nkey[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
     {
-        u64 key[4];
+        const u32 p = i * 32 + lane;
+        nkey[i] = p < cnt_here ? in[r0 + p].key : 0ull;
+    }
+#pragma unroll 1
+    for (int g = 0; g < GP_NB && !crowded; g += 4)
+    {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            const u32 p = (g + i) * 32 + lane;
-            key[i] = p < cnt_here ? in[r0 + p].key : 0ull;
+            key[i] = nkey[i];
+            const u32 p = (g + 4 + i) * 32 + lane; // the next group's keys travel while this one is ranked
+            nkey[i] = p < cnt_here ? in[r0 + p].key : 0ull;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
             const u32 bb = (g + i) * 32;
-            if (bb < cnt_here) // warp-uniform
+            if (bb < cnt_here && !crowded) // warp-uniform
             {
-                const bool valid = bb + lane < cnt_here;
-                const u32 col = (u32)(key[i] >> colshift) & colmask;
-                u32 slot = gp_hash(col);
-                bool fresh = false;
-                if (valid)
+                if (d > (u32)GP_DMAX)
                 {
-                    for (;;)
-                    {
-                        const u32 prev = atomicCAS(&ws.key[slot], GP_EMPTY, col);
-                        if (prev == GP_EMPTY)
-                        {
-                            fresh = true;
-                            break;
-                        }
-                        if (prev == col)
-                            break;
-                        slot = (slot + 1) & (GP_H - 1);
-                    }
+                    crowded = true; // the table may not take another 32 columns
                 }
-                const u32 fb = __ballot_sync(full, fresh);
-                const u32 vm = __ballot_sync(full, valid);
-                u32 peers = 0;
-                if (valid)
-                    peers = __match_any_sync(vm, slot);
-                const bool leader = valid && (peers & lt) == 0u;
-                // a new column is registered by the FIRST lane that holds it: the order of the
-                // chunk's column list must not depend on which lane won the CAS
-                const bool reg = leader && (fb & peers) != 0u;
-                const u32 rb = __ballot_sync(full, reg);
-                if (reg)
-                    ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
-                d += __popc(rb);
-                if (leader)
-                    ws.cnt[slot] = (unsigned short)(ws.cnt[slot] + __popc(peers));
-                __syncwarp();
-            }
-        }
-    }
-
-    // ---- position of this chunk's pairs: exclusive sum of d over the preceding chunks
-    u64 prefix = 0;
-    if (chunk == 0)
-    {
-        if (lane == 0)
-            st_relaxed_u64(status, GS_INCL | (u64)d);
-    }
-    else
-    {
-        if (lane == 0)
-            st_relaxed_u64(status + chunk, GS_LOCAL | (u64)d);
-        i64 t = (i64)chunk - 1;
-        for (;;)
-        {
-            const i64 idx = t - lane;
-            u64 v = GS_INCL;
-            if (idx >= 0)
-            {
-                do
+                else
                 {
-                    v = ld_relaxed_u64(status + idx);
-                } while ((v >> 62) == 0ull);
+                    const bool valid = bb + lane < cnt_here;
+                    const u32 col = (u32)(key[i] >> colshift) & colmask;
+                    u32 slot = gp_hash(col);
+                    bool fresh = false;
+                    if (valid)
+                    {
+                        for (;;)
+                        {
+                            const u32 prev = atomicCAS(&ws.key[slot], GP_EMPTY, col);
+                            if (prev == GP_EMPTY)
+                            {
+                                fresh = true;
+                                break;
+                            }
+                            if (prev == col)
+                                break;
+                            slot = (slot + 1) & (GP_H - 1);
+                        }
+                    }
+                    const u32 fb = __ballot_sync(full, fresh);
+                    const u32 vm = __ballot_sync(full, valid);
+                    u32 peers = 0;
+                    if (valid)
+                        peers = __match_any_sync(vm, slot);
+                    const bool leader = valid && (peers & lt) == 0u;
+                    // a new column is registered by the FIRST lane that holds it: the order of the
+                    // chunk's column list must not depend on which lane won the CAS
+                    const bool reg = leader && (fb & peers) != 0u;
+                    const u32 rb = __ballot_sync(full, reg);
+                    if (reg)
+                        ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
+                    d += __popc(rb);
+                    if (leader)
+                        atomicAdd(&ws.cnt[slot], (u32)__popc(peers));
+                }
             }
-            const u32 incl_mask = __ballot_sync(full, (v >> 62) == 2ull);
-            u64 contrib = v & GS_VALUE;
-            if (incl_mask)
-            {
-                const int first = __ffs(incl_mask) - 1;
-                if (lane > first)
-                    contrib = 0;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                contrib += __shfl_xor_sync(full, contrib, o);
-            prefix += contrib;
-            if (incl_mask)
-                break;
-            t -= 32;
         }
-        if (lane == 0)
-            st_relaxed_u64(status + chunk, GS_INCL | (prefix + d));
     }
+    __syncwarp();
+
+    // ---- room for this chunk's pairs
+    u32 base = 0;
+    if (lane == 0)
+        base = atomicAdd(pair_total, d);
+    base = __shfl_sync(full, base, 0);
+    const bool room = !crowded && (u64)base + d <= (u64)cap;
     if (lane == 0)
     {
-        chunkbase[chunk] = (u32)min(prefix, (u64)0xffffffffu);
-        if (chunk == nchunks - 1)
-            chunkbase[nchunks] = (u32)min(prefix + d, (u64)0xffffffffu);
-    }
-    if (prefix + d > (u64)cap)
-    { // more pairs than the caller made room for: the stream has no column locality
-        if (lane == 0)
+        chunkinfo[chunk] = make_uint2(base, room ? d : 0u);
+        if (!room) // more pairs than the caller made room for: the stream has no column locality
             atomicExch(d_flags, 1u);
-        return;
     }
-    const u32 base = (u32)prefix;
+    if (!room)
+        return;
     for (u32 j = lane; j < d; j += 32)
     {
         const u32 slot = ws.cand[j];
         const u32 col = ws.key[slot];
         chunkcols[base + j] = col;
         Rec pr;
-        pr.key = (u64)col;
+        pr.key = ((u64)col << chunkbits) | (u64)chunk;
         const u64 payload = ((u64)(base + j) << 16) | (u64)ws.cnt[slot];
         pr.val = __longlong_as_double((long long)payload);
         st_rec(pairs + base + j, pr);
@@ -215,7 +182,8 @@ constexpr int PS_TILE = PS_THREADS * PS_IPT;
 __device__ __forceinline__ u64 pair_payload(const Rec &r) { return (u64)__double_as_longlong(r.val); }
 
 __global__ void __launch_bounds__(PS_THREADS)
-pair_tilesum_kernel(const Rec *__restrict__ sp, u32 npairs, u64 *__restrict__ trec, u32 *__restrict__ tnz)
+pair_tilesum_kernel(const Rec *__restrict__ sp, u32 npairs, int chunkbits, u64 *__restrict__ trec,
+                    u32 *__restrict__ tnz)
 {
     __shared__ u64 s_w[PS_THREADS / 32];
     const u32 b0 = blockIdx.x * PS_TILE;
@@ -228,7 +196,7 @@ pair_tilesum_kernel(const Rec *__restrict__ sp, u32 npairs, u64 *__restrict__ tr
         {
             const Rec r = sp[j];
             rec += pair_payload(r) & 0xffffull;
-            heads += (j == 0 || sp[j - 1].key != r.key) ? 1 : 0;
+            heads += (j == 0 || (sp[j - 1].key >> chunkbits) != (r.key >> chunkbits)) ? 1 : 0;
         }
     }
     // packed: records << 24 | heads (a tile holds at most 2048 heads)
@@ -249,8 +217,9 @@ pair_tilesum_kernel(const Rec *__restrict__ sp, u32 npairs, u64 *__restrict__ tr
 }
 
 __global__ void __launch_bounds__(PS_THREADS)
-pair_emit_kernel(const Rec *__restrict__ sp, u32 npairs, const u64 *__restrict__ trec, const u32 *__restrict__ tnz,
-                 u32 *__restrict__ offs, u32 *__restrict__ nzcol, u32 *__restrict__ nzstart)
+pair_emit_kernel(const Rec *__restrict__ sp, u32 npairs, int chunkbits, const u64 *__restrict__ trec,
+                 const u32 *__restrict__ tnz, u32 *__restrict__ offs, u32 *__restrict__ nzcol,
+                 u32 *__restrict__ nzstart)
 {
     __shared__ u64 s_w[PS_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -258,7 +227,7 @@ pair_emit_kernel(const Rec *__restrict__ sp, u32 npairs, const u64 *__restrict__
     u32 cnt[PS_IPT], col[PS_IPT], tidx[PS_IPT];
     bool head[PS_IPT];
     u64 sum = 0;
-    u32 prevcol = (b0 > 0 && b0 <= npairs) ? (u32)sp[b0 - 1].key : 0xffffffffu;
+    u32 prevcol = (b0 > 0 && b0 <= npairs) ? (u32)(sp[b0 - 1].key >> chunkbits) : 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < PS_IPT; ++i)
     {
@@ -273,7 +242,7 @@ pair_emit_kernel(const Rec *__restrict__ sp, u32 npairs, const u64 *__restrict__
             const u64 pl = pair_payload(r);
             cnt[i] = (u32)(pl & 0xffffull);
             tidx[i] = (u32)(pl >> 16);
-            col[i] = (u32)r.key;
+            col[i] = (u32)(r.key >> chunkbits);
             head[i] = j == 0 || col[i] != prevcol;
             prevcol = col[i];
         }
@@ -321,9 +290,9 @@ struct ScatterSpace
     u32 cur[GP_H];
 };
 
-__global__ void __launch_bounds__(GP_WARPS * 32, 3)
+__global__ void __launch_bounds__(GP_WARPS * 32, 5)
 group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks,
-                     const u32 *__restrict__ chunkcols, const u32 *__restrict__ chunkbase,
+                     const u32 *__restrict__ chunkcols, const uint2 *__restrict__ chunkinfo,
                      const u32 *__restrict__ offs, Rec *__restrict__ out)
 {
     constexpr u32 full = 0xffffffffu;
@@ -336,8 +305,8 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
     const u32 lt = lanemask_lt();
     const u64 r0 = (u64)chunk * GP_W;
     const u32 cnt_here = (u32)min((u64)GP_W, nrec - r0);
-    const u32 base = chunkbase[chunk];
-    const u32 d = chunkbase[chunk + 1] - base;
+    const uint2 info = chunkinfo[chunk];
+    const u32 base = info.x, d = info.y;
     {
         uint4 *kq = reinterpret_cast<uint4 *>(ws.key);
 #pragma unroll
@@ -391,14 +360,10 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
                 const int ldr = __ffs(peers) - 1;
                 u32 b = 0;
                 if (valid && lane == ldr)
-                {
-                    b = ws.cur[slot];
-                    ws.cur[slot] = b + __popc(peers);
-                }
+                    b = atomicAdd(&ws.cur[slot], (u32)__popc(peers));
                 b = __shfl_sync(full, b, ldr);
                 if (valid)
                     st_rec(out + (b + __popc(peers & lt)), r[i]);
-                __syncwarp();
             }
         }
     }
@@ -410,7 +375,7 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
 namespace {
 struct GpLayout
 {
-    size_t off_ticket, off_status, off_chunkbase, off_chunkcols, off_offs, off_trec, off_tnz, bytes;
+    size_t off_ticket, off_chunkinfo, off_chunkcols, off_offs, off_trec, off_tnz, bytes;
     u32 cap;
 };
 GpLayout gp_layout(u64 nrec)
@@ -423,10 +388,8 @@ GpLayout gp_layout(u64 nrec)
     size_t o = 0;
     l.off_ticket = o;
     o = up(o + 256);
-    l.off_status = o;
-    o = up(o + sizeof(u64) * (nchunks + 1));
-    l.off_chunkbase = o;
-    o = up(o + sizeof(u32) * (nchunks + 2));
+    l.off_chunkinfo = o;
+    o = up(o + sizeof(uint2) * (nchunks + 1));
     l.off_chunkcols = o;
     o = up(o + sizeof(u32) * ((size_t)l.cap + 1));
     l.off_offs = o;
@@ -444,7 +407,7 @@ size_t group_workspace_bytes(u64 nrec) { return gp_layout(nrec).bytes; }
 
 bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols)
 {
-    return L.colbits <= 32 && nrec >= 32768 && nrec < (1ull << 32) - (u64)GP_W && (u64)ncols < (1ull << 32) - 1ull;
+    return L.colbits <= 32 && L.colbits + 23 <= 8 * kMaxPasses && nrec >= 32768 && nrec < (1ull << 32) - (u64)GP_W && (u64)ncols < (1ull << 32) - 1ull;
 }
 
 // colscan_scan_kernel of xsb_colfold.cu (exclusive scan of the tile sums; totals; nzstart sentinel)
@@ -460,10 +423,9 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
 {
     const GpLayout l = gp_layout(nrec);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    u32 *ticket = reinterpret_cast<u32 *>(ws + l.off_ticket);
-    u32 *flags = ticket + 1;
-    u64 *status = reinterpret_cast<u64 *>(ws + l.off_status);
-    u32 *chunkbase = reinterpret_cast<u32 *>(ws + l.off_chunkbase);
+    u32 *pair_total = reinterpret_cast<u32 *>(ws + l.off_ticket);
+    u32 *flags = pair_total + 1;
+    uint2 *chunkinfo = reinterpret_cast<uint2 *>(ws + l.off_chunkinfo);
     u32 *chunkcols = reinterpret_cast<u32 *>(ws + l.off_chunkcols);
     u32 *offs = reinterpret_cast<u32 *>(ws + l.off_offs);
     u64 *trec = reinterpret_cast<u64 *>(ws + l.off_trec);
@@ -486,14 +448,17 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     // ---- pass 1
     if (timer)
         timer->begin(stream);
-    XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, l.off_chunkbase - l.off_ticket, stream)); // ticket, flags, status
+    XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair_total, flags
+    int chunkbits = 1;
+    while ((1ull << chunkbits) < (u64)nchunks)
+        ++chunkbits;
     const unsigned cblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;
     group_count_kernel<<<cblocks, GP_WARPS * 32, sizeof(CountSpace) * GP_WARPS, stream>>>(
-        in, nrec, colshift, colmask, nchunks, ticket, status, pairs_a, chunkcols, chunkbase, l.cap, flags);
+        in, nrec, colshift, colmask, nchunks, chunkbits, pair_total, pairs_a, chunkcols, chunkinfo, l.cap, flags);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     // pairs made, too-many flag
-    XSB_CUDA(cudaMemcpyAsync(h_scal_pinned, chunkbase + nchunks, sizeof(u32), cudaMemcpyDeviceToHost, stream));
+    XSB_CUDA(cudaMemcpyAsync(h_scal_pinned, pair_total, sizeof(u32), cudaMemcpyDeviceToHost, stream));
     XSB_CUDA(cudaMemcpyAsync(h_scal_pinned + 1, flags, sizeof(u32), cudaMemcpyDeviceToHost, stream));
     if (timer)
         timer->end(stream, &StageTimes::histogram);
@@ -505,7 +470,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
         return false;
 
     // ---- pairs sorted by column (stable: chunk order inside a column)
-    const SortPlan plan = make_sort_plan(0, L.colbits);
+    const SortPlan plan = make_sort_plan(0, L.colbits + chunkbits);
     *pair_passes = plan.npasses;
     Rec *sp = radix_sort_records(stream, pairs_a, pairs_b, npairs, plan, sort_workspace, lc, timer);
 
@@ -513,16 +478,16 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     if (timer)
         timer->begin(stream);
     const unsigned ptiles = (npairs + PS_TILE - 1) / PS_TILE;
-    pair_tilesum_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, trec, tnz);
+    pair_tilesum_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, chunkbits, trec, tnz);
     colscan_scan_launch(stream, trec, tnz, (i64)ptiles, totals, nzstart);
-    pair_emit_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, trec, tnz, offs, nzcol, nzstart);
+    pair_emit_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, chunkbits, trec, tnz, offs, nzcol, nzstart);
     lc.add(3);
     XSB_CUDA(cudaGetLastError());
     (void)d_scal;
     // ---- pass 2
     const unsigned sblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;
     group_scatter_kernel<<<sblocks, GP_WARPS * 32, sizeof(ScatterSpace) * GP_WARPS, stream>>>(
-        in, nrec, colshift, colmask, nchunks, chunkcols, chunkbase, offs, out);
+        in, nrec, colshift, colmask, nchunks, chunkcols, chunkinfo, offs, out);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     if (timer)
