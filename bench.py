@@ -96,6 +96,47 @@ def flush_bytes(n_ins, nnz_old, nnz_new, ncols):
     return 16 * n_ins + 16 * nnz_old + 8 * (ncols + 1) + 16 * nnz_new + 8 * (ncols + 1)
 
 
+
+def roofline(st, ms, ncols, peak, peak_src, traffic):
+    """Roofline of the DOMINANT kernel of the flush (largest device time per step, CUDA events on the
+    library's stream around that kernel) + the whole-flush fraction on SURVEY.md 8(d)'s bytes.
+    Algorithmic bytes per launch: records are 16 B, CSC entries 16 B."""
+    rec = st["n_inserted"] + st["nnz_old"]
+    nnz = st["nnz_new"]
+    pairs = st["group_pairs"]
+    path = st["column_path"]
+    cands = {}
+    if path == 3:
+        cands["group_count_kernel (read every record, write the (column, chunk) pairs)"] = (
+            ms["ms_group_count"], 16 * rec + 16 * pairs, 1)
+        cands["group_scatter_kernel (+ pair offsets: stable scatter of every record to its column)"] = (
+            ms["ms_group_scatter"], 32 * rec + 24 * pairs, 1)
+        cands["onesweep_kernel on the (column, chunk) pairs"] = (ms["ms_pair_sort"], 32 * pairs * st["sort_passes"],
+                                                                 st["sort_passes"])
+    else:
+        cands["onesweep_kernel (one radix pass over 16-B records)"] = (ms["ms_sort"], 32 * rec * st["sort_passes"],
+                                                                      st["sort_passes"])
+    if path >= 2:
+        cands["colthread_kernel (+ leftover colfold_kernel: per-column fold, read records, park entries)"] = (
+            ms["ms_fold"], 16 * rec + 16 * nnz, 1)
+        cands["compact_entries_kernel (parked entries -> rowval / nzval)"] = (ms["ms_compact"], 32 * nnz, 1)
+    else:
+        cands["reduce_emit_kernel"] = (ms["ms_reduce"], 16 * rec + 16 * nnz, 1)
+    name = max(cands, key=lambda k: cands[k][0])
+    t, byts, launches = cands[name]
+    achieved = byts / (t / 1e3) / 1e9
+    b_flush = flush_bytes(st["n_inserted"], st["nnz_old"], nnz, ncols)
+    flush_gbs = b_flush / (ms["ms_total"] / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "bytes_per_launch": byts / launches, "ms_per_launch": t / launches, "launches_per_step": launches,
+            "kernels": {k: {"ms": v[0], "GB/s": v[1] / (v[0] / 1e3) / 1e9 if v[0] > 0 else None,
+                            "frac": v[1] / (v[0] / 1e3) / 1e9 / peak if v[0] > 0 else None} for k, v in cands.items()},
+            "flush": {"algorithmic_bytes": b_flush, "ms": ms["ms_total"], "achieved": flush_gbs,
+                      "frac": flush_gbs / peak, "column_path": path},
+            "stage_ms_per_step": dict(sorted(ms.items()))}
+
+
 # ---------------------------------------------------------------------------------- CPU legs
 def cpu_reference_leg(mesh, steps, warmup):
     """Times the oracle port of the reference's serial path (ExtendableSparseMatrix +
@@ -199,16 +240,7 @@ def run_ours(args):
     value = n_ins / (ms_step / 1e3)
     peak, peak_src = peaks()
 
-    # dominant kernel: one onesweep pass reads and writes every 16-byte record once
-    passes = st["sort_passes"]
-    ms_pass = stage["ms_sort"] / args.steps / max(passes, 1)
-    rec = st["n_inserted"] + st["nnz_old"]
-    pass_bytes = 32 * rec
-    achieved = pass_bytes / (ms_pass / 1e3) / 1e9
-    b_flush = flush_bytes(st["n_inserted"], st["nnz_old"], st["nnz_new"], n)
-    ms_flush = stage["ms_total"] / args.steps
-    flush_gbs = b_flush / (ms_flush / 1e3) / 1e9
-
+    roof = roofline(st, {k: v / args.steps for k, v in stage.items()}, n, peak, peak_src, args.traffic)
 
     # ---- end-to-end through the C ABI with HOST buffers
     e2e = measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch)
@@ -226,13 +258,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload(args),
-        "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass over 16-B records)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": args.traffic, "peak_source": peak_src,
-                     "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass, "launches_per_step": passes,
-                     "flush": {"algorithmic_bytes": b_flush, "ms": ms_flush, "achieved": flush_gbs,
-                               "frac": flush_gbs / peak},
-                     "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stage.items())}},
+        "roofline": roof,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed),
         "clocks": clk.summary(), "nnz": int(nnz), "n_inserted": int(n_ins),
     }

@@ -59,6 +59,12 @@ class FlushStats(C.Structure):
         ("ms_other", C.c_float),
         ("ms_host_alloc", C.c_float),
         ("group_pairs", C.c_int64),
+        ("ms_group_count", C.c_float),
+        ("ms_pair_sort", C.c_float),
+        ("ms_group_scatter", C.c_float),
+        ("ms_fold", C.c_float),
+        ("ms_compact", C.c_float),
+        ("reserved_", C.c_float),
     ]
 
     def as_dict(self):

@@ -623,9 +623,14 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         cudaEventDestroy(e1);
         h->stats.ms_total = t.total;
         h->stats.ms_expand = t.expand;
-        h->stats.ms_histogram = t.histogram;
-        h->stats.ms_sort = t.sort;
-        h->stats.ms_reduce = t.reduce;
+        h->stats.ms_histogram = t.histogram + t.gcount;
+        h->stats.ms_sort = t.sort + t.gscatter;
+        h->stats.ms_reduce = t.reduce + t.fold + t.compact;
+        h->stats.ms_group_count = t.gcount;
+        h->stats.ms_pair_sort = path == 3 ? t.histogram + t.sort : 0.f;
+        h->stats.ms_group_scatter = t.gscatter;
+        h->stats.ms_fold = t.fold;
+        h->stats.ms_compact = t.compact;
         h->stats.ms_colptr = t.colptr;
         h->stats.ms_other = t.other;
     }

@@ -20,6 +20,7 @@
 // table raises an overflow flag; the caller then finishes with the general (col,row) sort.
 #include "xsb_fold.cuh"
 #include "xsb_internal.h"
+#include <cstdlib>
 
 namespace xsb {
 
@@ -377,11 +378,15 @@ __device__ __forceinline__ void emit_group(WS &ws, u32 dcount, int rowbits, u32 
     __syncwarp();
 }
 
-template <bool SIMPLE, int WARPS>
+// LIST = false: warp `tile` takes the columns that start inside span `tile` (tilek).
+// LIST = true : the warps walk `list` (compact column indices left over by colthread_kernel:
+//               columns too long or too rich for a single thread), one column at a time.
+template <bool SIMPLE, int WARPS, bool LIST>
 __global__ void __launch_bounds__(WARPS * 32, SIMPLE ? 1024 / (WARPS * 32) : 384 / (WARPS * 32))
 colfold_kernel(const Rec *__restrict__ sorted, KeyLayout L, int combine, u32 chunk, const u32 *__restrict__ nzcol,
                const u32 *__restrict__ nzstart, const u32 *__restrict__ tilek, u32 ntiles, Rec *__restrict__ tmp,
-               u32 *__restrict__ colcount, u32 *__restrict__ d_overflow)
+               u32 *__restrict__ colcount, u32 *__restrict__ d_overflow, const u32 *__restrict__ list,
+               const u32 *__restrict__ list_count)
 {
     typedef WarpSpace<SIMPLE> WS;
     constexpr u32 full = 0xffffffffu;
@@ -389,16 +394,18 @@ colfold_kernel(const Rec *__restrict__ sorted, KeyLayout L, int combine, u32 chu
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WS &ws = reinterpret_cast<WS *>(smem_raw)[warp];
-    const u32 tile = blockIdx.x * WARPS + warp;
-    if (tile >= ntiles)
-        return;
-    const u32 k_begin = tilek[tile], k_end = tilek[tile + 1];
     const u32 lt = lanemask_lt();
     const u32 le = lt | (1u << lane);
     const int rowbits = L.rowbits;
     const int low = L.low;
     const u32 rowmask = (1u << rowbits) - 1u;
     const u32 metamask = (1u << low) - 1u;
+    const u32 tend = LIST ? *list_count : ntiles;
+    const u32 tstep = LIST ? gridDim.x * WARPS : 0xffffffffu - ntiles; // one span per warp without a list
+  for (u32 tile = blockIdx.x * WARPS + warp; tile < tend; tile += tstep)
+  {
+    const u32 k_begin = LIST ? list[tile] : tilek[tile];
+    const u32 k_end = LIST ? k_begin + 1u : tilek[tile + 1];
 
     for (u32 kw = k_begin; kw < k_end; kw += 32)
     { // window of up to 32 non-empty columns: lane j holds column kw + j
@@ -597,6 +604,142 @@ colfold_kernel(const Rec *__restrict__ sorted, KeyLayout L, int combine, u32 chu
             a += nc;
         }
     }
+  }
+}
+
+// ------------------------------------------------------------------------
+// one THREAD per column (plain += streams: one partition, no assign flavour, old values seed)
+// ------------------------------------------------------------------------
+// Thread k walks the records of non-empty column k in stream order.  Its accumulators live in a
+// private open-addressing table in shared memory, laid out slot-major ([slot][lane]) so that a
+// lane only ever touches its own bank: no conflicts whatever the slots are.  Every record is one
+// probe, one add: the exact left fold of the reference's accumulate-on-insert
+// (src/matrix/sparsematrixlnk.jl:210-253) with the list walk replaced by the hash probe.  The
+// column's distinct entries are then compacted, ranked by row and parked at the column's offset.
+// Columns longer than maxlen, or with more distinct rows than the table takes, are appended to
+// `list` for the warp-per-column kernel above.
+constexpr int CT_WARPS = 4;
+constexpr int CT_U = 4; // records in flight per thread and step (x2: the next step is prefetched)
+constexpr u32 CT_EMPTY = 0x7fffffffu;
+constexpr u32 CT_EXISTS = 0x80000000u;
+constexpr int CT_MAXROWBITS = 30;
+
+template <int HBITS>
+__global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 4 : 2))
+colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxlen, const u32 *__restrict__ nzcol,
+                 const u32 *__restrict__ nzstart, const u64 *__restrict__ totals, Rec *__restrict__ tmp,
+                 u32 *__restrict__ colcount, u32 *__restrict__ list, u32 *__restrict__ list_count)
+{
+    constexpr int H = 1 << HBITS;
+    constexpr u32 MAXD = H - H / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *acc = reinterpret_cast<double *>(smem_raw) + warp * (H * 32) + lane; // slot s: acc[s * 32]
+    u32 *key = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * H * 32 * sizeof(double)) + warp * (H * 32) + lane;
+    const u64 K = totals[1];
+    const u64 k = (u64)blockIdx.x * (CT_WARPS * 32) + threadIdx.x;
+    if (k >= K)
+        return;
+    const u32 cstart = nzstart[k], cend = nzstart[k + 1];
+    if (cend - cstart > maxlen)
+    {
+        list[atomicAdd(list_count, 1u)] = (u32)k;
+        return;
+    }
+    const u32 rowmask = (1u << rowbits) - 1u;
+#pragma unroll
+    for (int s = 0; s < H; ++s)
+        key[s * 32] = CT_EMPTY;
+
+    u32 d = 0;
+    bool ovf = false;
+    Rec nxt[CT_U];
+#pragma unroll
+    for (int i = 0; i < CT_U; ++i)
+        if (cstart + i < cend)
+            nxt[i] = sorted[cstart + i];
+    for (u32 p = cstart; p < cend && !ovf; p += CT_U)
+    {
+        Rec cur[CT_U];
+#pragma unroll
+        for (int i = 0; i < CT_U; ++i)
+            cur[i] = nxt[i];
+#pragma unroll
+        for (int i = 0; i < CT_U; ++i)
+            if (p + CT_U + i < cend)
+                nxt[i] = sorted[p + CT_U + i];
+#pragma unroll
+        for (int i = 0; i < CT_U; ++i)
+        {
+            if (p + i < cend && !ovf)
+            {
+                const u32 row = (u32)(cur[i].key >> low) & rowmask;
+                const u32 fl = (u32)cur[i].key & 3u;
+                const double v = cur[i].val;
+                const u32 creates = ((fl != FL_UPDATE) | (v != 0.0)) ? CT_EXISTS : 0u;
+                u32 s = (row * 0x9E3779B1u) >> (32 - HBITS);
+                for (;;)
+                {
+                    const u32 kk = key[s * 32];
+                    if ((kk & ~CT_EXISTS) == row)
+                    {
+                        acc[s * 32] = (fl == FL_OLD) ? v : acc[s * 32] + v;
+                        if (creates & ~kk)
+                            key[s * 32] = kk | CT_EXISTS;
+                        break;
+                    }
+                    if (kk == CT_EMPTY)
+                    {
+                        if (d >= MAXD)
+                        {
+                            ovf = true;
+                            break;
+                        }
+                        key[s * 32] = row | creates;
+                        // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value
+                        // seeds it (extendable.jl:165-166)
+                        acc[s * 32] = (fl == FL_OLD) ? v : 0.0 + v;
+                        ++d;
+                        break;
+                    }
+                    s = (s + 1) & (H - 1);
+                }
+            }
+        }
+    }
+    if (ovf)
+    {
+        list[atomicAdd(list_count, 1u)] = (u32)k;
+        return;
+    }
+    // ---- compact the existing entries to the front of the table (j <= s: in place)
+    u32 dd = 0;
+#pragma unroll 8
+    for (int s = 0; s < H; ++s)
+    {
+        const u32 kk = key[s * 32];
+        if (kk != CT_EMPTY && (kk & CT_EXISTS))
+        {
+            const double a = acc[s * 32];
+            key[dd * 32] = kk & ~CT_EXISTS;
+            acc[dd * 32] = a;
+            ++dd;
+        }
+    }
+    // ---- rank by row, park at the column's offset
+    Rec *dst = tmp + cstart;
+    for (u32 e = 0; e < dd; ++e)
+    {
+        const u32 r = key[e * 32];
+        u32 rank = 0;
+        for (u32 t = 0; t < dd; ++t)
+            rank += key[t * 32] < r;
+        Rec o;
+        o.key = (u64)r;
+        o.val = acc[e * 32];
+        st_rec(dst + rank, o);
+    }
+    colcount[nzcol[k]] = dd;
 }
 
 // ------------------------------------------------------------------------
@@ -730,9 +873,47 @@ compact_entries_kernel(const Rec *__restrict__ tmp, const u32 *__restrict__ nzco
 // host side
 // ------------------------------------------------------------------------
 namespace {
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+// tuning knobs (debugging and the tile-shape sweeps of tools/): XSB_THREAD_FOLD=0 keeps every
+// column on the warp kernel, XSB_THREAD_HBITS=4|5|6 fixes the per-thread table size
+const int g_thread_fold = env_int("XSB_THREAD_FOLD", 1);
+const int g_thread_hbits = env_int("XSB_THREAD_HBITS", 0);
+
+template <int HBITS>
+void launch_colthread_t(cudaStream_t stream, unsigned blocks, const Rec *sorted, int low, int rowbits, u32 maxlen,
+                        const u32 *nzcol, const u32 *nzstart, const u64 *totals, Rec *tmp, u32 *colcount, u32 *list,
+                        u32 *list_count)
+{
+    constexpr size_t smem = (size_t)CT_WARPS * (1 << HBITS) * 32 * (sizeof(double) + sizeof(u32));
+    static bool attr = false;
+    if (!attr)
+    {
+        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
+        attr = true;
+    }
+    colthread_kernel<HBITS><<<blocks, CT_WARPS * 32, smem, stream>>>(sorted, low, rowbits, maxlen, nzcol, nzstart, totals,
+                                                                     tmp, colcount, list, list_count);
+}
+void launch_colthread(cudaStream_t stream, int hbits, unsigned blocks, const Rec *sorted, int low, int rowbits,
+                      u32 maxlen, const u32 *nzcol, const u32 *nzstart, const u64 *totals, Rec *tmp, u32 *colcount,
+                      u32 *list, u32 *list_count)
+{
+    if (hbits == 4)
+        launch_colthread_t<4>(stream, blocks, sorted, low, rowbits, maxlen, nzcol, nzstart, totals, tmp, colcount, list, list_count);
+    else if (hbits == 5)
+        launch_colthread_t<5>(stream, blocks, sorted, low, rowbits, maxlen, nzcol, nzstart, totals, tmp, colcount, list, list_count);
+    else
+        launch_colthread_t<6>(stream, blocks, sorted, low, rowbits, maxlen, nzcol, nzstart, totals, tmp, colcount, list, list_count);
+}
 struct CfLayout
 {
-    size_t off_cnt, off_nzcol, off_nzstart, off_tilek, off_trec, off_tnz, off_tsum, off_tot, bytes;
+    size_t off_cnt, off_nzcol, off_nzstart, off_tilek, off_trec, off_tnz, off_tsum, off_tot, off_list, bytes;
 };
 CfLayout cf_layout(u64 nrec, i64 ncols)
 {
@@ -758,6 +939,8 @@ CfLayout cf_layout(u64 nrec, i64 ncols)
     o = up(o + sizeof(u64) * (ctiles + 1));
     l.off_tot = o;
     o = up(o + sizeof(u64) * 4);
+    l.off_list = o; // columns left over by the thread-per-column kernel
+    o = up(o + sizeof(u32) * (kmax + 1));
     l.bytes = o;
     return l;
 }
@@ -840,18 +1023,43 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     // Groups of short columns hold many distinct entries per record (little duplication), and the
     // in-register sort of the distinct entries grows faster than linearly: keep such groups small.
     const u32 chunk = (nrec / std::max<u64>(1, std::min<u64>((u64)ncols, nrec)) >= 48) ? (u32)CF_PIECE : 128u;
-    if (simple)
+    if (simple && L.rowbits <= CT_MAXROWBITS && g_thread_fold)
+    { // one thread per column; the columns it leaves over go to the warp kernel through a list
+        u32 *list = reinterpret_cast<u32 *>(ws + l.off_list);
+        u32 *list_count = reinterpret_cast<u32 *>(totals + 2);
+        XSB_CUDA(cudaMemsetAsync(list_count, 0, sizeof(u32), stream));
+        const u64 avg = nrec / std::max<u64>(1, kmax);
+        int hbits = avg < 14 ? 4 : (avg < 40 ? 5 : 6);
+        if (g_thread_hbits >= 4 && g_thread_hbits <= 6)
+            hbits = g_thread_hbits;
+        const u32 maxlen = (u32)std::max<u64>(256, 6 * avg);
+        const unsigned blocks = (unsigned)((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32));
+        launch_colthread(stream, hbits, blocks, sorted, L.low, L.rowbits, maxlen, nzcol, nzstart, totals, tmp, cnt, list,
+                         list_count);
+        constexpr int W = 8;
+        const size_t smem = sizeof(WarpSpace<true>) * W;
+        static bool attr = false;
+        if (!attr)
+        {
+            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<true, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        colfold_kernel<true, W, true><<<kNumSM * 2, W * 32, smem, stream>>>(sorted, L, combine, chunk, nzcol, nzstart, tilek,
+                                                                          ntiles, tmp, cnt, d_overflow, list, list_count);
+        lc.add();
+    }
+    else if (simple)
     {
         constexpr int W = 8;
         const size_t smem = sizeof(WarpSpace<true>) * W;
         static bool attr = false;
         if (!attr)
         {
-            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<true, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = true;
         }
-        colfold_kernel<true, W><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(sorted, L, combine, chunk, nzcol, nzstart,
-                                                                                tilek, ntiles, tmp, cnt, d_overflow);
+        colfold_kernel<true, W, false><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(
+            sorted, L, combine, chunk, nzcol, nzstart, tilek, ntiles, tmp, cnt, d_overflow, nullptr, nullptr);
     }
     else
     {
@@ -860,16 +1068,16 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         static bool attr = false;
         if (!attr)
         {
-            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<false, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = true;
         }
-        colfold_kernel<false, W><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(sorted, L, combine, chunk, nzcol, nzstart,
-                                                                                 tilek, ntiles, tmp, cnt, d_overflow);
+        colfold_kernel<false, W, false><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(
+            sorted, L, combine, chunk, nzcol, nzstart, tilek, ntiles, tmp, cnt, d_overflow, nullptr, nullptr);
     }
     lc.add();
     XSB_CUDA(cudaGetLastError());
     if (timer)
-        timer->end(stream, &StageTimes::reduce);
+        timer->end(stream, &StageTimes::fold);
 
     if (timer)
         timer->begin(stream);
@@ -908,7 +1116,7 @@ void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, i
     lc.add();
     XSB_CUDA(cudaGetLastError());
     if (timer)
-        timer->end(stream, &StageTimes::reduce);
+        timer->end(stream, &StageTimes::compact);
 }
 
 } // namespace xsb

@@ -461,7 +461,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     XSB_CUDA(cudaMemcpyAsync(h_scal_pinned, pair_total, sizeof(u32), cudaMemcpyDeviceToHost, stream));
     XSB_CUDA(cudaMemcpyAsync(h_scal_pinned + 1, flags, sizeof(u32), cudaMemcpyDeviceToHost, stream));
     if (timer)
-        timer->end(stream, &StageTimes::histogram);
+        timer->end(stream, &StageTimes::gcount);
     XSB_CUDA(cudaStreamSynchronize(stream));
     const u32 npairs = (u32)(h_scal_pinned[0] & 0xffffffffull);
     const bool toomany = (u32)(h_scal_pinned[1] & 0xffffffffull) != 0u;
@@ -491,7 +491,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     lc.add();
     XSB_CUDA(cudaGetLastError());
     if (timer)
-        timer->end(stream, &StageTimes::sort);
+        timer->end(stream, &StageTimes::gscatter);
     return true;
 }
 

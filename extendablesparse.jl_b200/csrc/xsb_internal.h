@@ -31,6 +31,7 @@ struct LaunchCounter
 struct StageTimes
 {
     float expand = 0, histogram = 0, sort = 0, reduce = 0, colptr = 0, other = 0, total = 0;
+    float gcount = 0, gscatter = 0, fold = 0, compact = 0; // two-pass grouping and per-column fold, in detail
 };
 
 // Optional CUDA-event bracket around pipeline stages (profiling mode only).

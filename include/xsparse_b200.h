@@ -93,6 +93,13 @@ typedef struct xsb_flush_stats
     float ms_other;           /* buffer management, shrink copy        */
     float ms_host_alloc;      /* host wall time spent in device allocations during the flush */
     int64_t group_pairs;      /* (chunk, column) pairs of the two-pass grouping; 0 when it was not tried */
+    /* detail of the column paths (already included in ms_histogram / ms_sort / ms_reduce above) */
+    float ms_group_count;     /* grouping pass 1: per-chunk column histograms             */
+    float ms_pair_sort;       /* radix sort of the (column, chunk) pairs                  */
+    float ms_group_scatter;   /* pair offsets + grouping pass 2: stable scatter by column */
+    float ms_fold;            /* per-column fold of duplicates (entries parked)           */
+    float ms_compact;         /* parked entries -> rowval / nzval                         */
+    float reserved_;
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */
