@@ -220,6 +220,7 @@ struct xsb_matrix
     int grouping_misses = 0;          // consecutive flushes whose stream had no column locality
     i64 stats_pairs = 0;
     bool last_column_path = false;
+    u32 fold_hint = 0; // most distinct rows a column held in the previous thread-per-column fold
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
     {
@@ -504,10 +505,13 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             spare = (sorted == A) ? B : A;
         }
         colfold_reduce(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
-                       new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), grouped, h->lc, tp);
+                       new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), grouped,
+                       reinterpret_cast<u32 *>(h->d_scal + 7), h->fold_hint, h->lc, tp);
         path = grouped ? 3 : 2;
-        XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, sizeof(u64), cudaMemcpyDeviceToHost, s));
+        XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
         nnz_new = (i64)read_scalar(h, 0);
+        if ((u32)h->h_scal[7])
+            h->fold_hint = (u32)h->h_scal[7]; // distinct rows per column: picks the next flush's table size
         if ((u32)h->h_scal[6] == 0u)
         {
             const size_t rv_bytes = (h->isz() * (size_t)nnz_new + 15) & ~(size_t)15;

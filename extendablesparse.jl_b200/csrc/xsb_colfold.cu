@@ -610,136 +610,193 @@ colfold_kernel(const Rec *__restrict__ sorted, KeyLayout L, int combine, u32 chu
 // ------------------------------------------------------------------------
 // one THREAD per column (plain += streams: one partition, no assign flavour, old values seed)
 // ------------------------------------------------------------------------
-// Thread k walks the records of non-empty column k in stream order.  Its accumulators live in a
-// private open-addressing table in shared memory, laid out slot-major ([slot][lane]) so that a
-// lane only ever touches its own bank: no conflicts whatever the slots are.  Every record is one
-// probe, one add: the exact left fold of the reference's accumulate-on-insert
-// (src/matrix/sparsematrixlnk.jl:210-253) with the list walk replaced by the hash probe.  The
-// column's distinct entries are then compacted, ranked by row and parked at the column's offset.
-// Columns longer than maxlen, or with more distinct rows than the table takes, are appended to
-// `list` for the warp-per-column kernel above.
+// Thread k walks the records of non-empty column k in stream order.  Its accumulators live in
+// shared memory, in a private open-addressing table laid out slot-major ([slot][lane]) so that a
+// lane only ever touches its own bank: no conflicts whatever the slots are.  A table slot holds
+// (row << HBITS | accumulator index); the accumulators are numbered in order of first appearance.
+// Every record is one probe and one add: the exact left fold of the reference's
+// accumulate-on-insert (src/matrix/sparsematrixlnk.jl:210-253) with the list walk replaced by the
+// hash probe.  At the end the slots of the existing entries are insertion-sorted by row in place
+// (src/matrix/sparsematrixlnk.jl:339) and the entries parked at the column's offset.
+//
+// Three table sizes (16/12, 32/24, 64/48 slots/accumulators) trade occupancy against capacity: a
+// column with more distinct rows than the table takes is appended to `next` (the next size, or the
+// warp-per-column kernel); columns longer than maxlen go straight to `longlist` (warp kernel).
 constexpr int CT_WARPS = 4;
-constexpr int CT_U = 4; // records in flight per thread and step (x2: the next step is prefetched)
-constexpr u32 CT_EMPTY = 0x7fffffffu;
-constexpr u32 CT_EXISTS = 0x80000000u;
-constexpr int CT_MAXROWBITS = 30;
+constexpr int CT_U = 2; // 32-byte record pairs per step (the next step is prefetched)
+constexpr u32 CT_EMPTY = 0xffffffffu;
 
-template <int HBITS>
-__global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 4 : 2))
+template <int HBITS> struct CtShape
+{
+    static constexpr int H = 1 << HBITS;
+    static constexpr int D = H - H / 4;
+    static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + sizeof(double) * D);
+};
+
+template <int HBITS, bool LIST>
+__global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 5 : 2))
 colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxlen, const u32 *__restrict__ nzcol,
                  const u32 *__restrict__ nzstart, const u64 *__restrict__ totals, Rec *__restrict__ tmp,
-                 u32 *__restrict__ colcount, u32 *__restrict__ list, u32 *__restrict__ list_count)
+                 u32 *__restrict__ colcount, const u32 *__restrict__ src, const u32 *__restrict__ src_count,
+                 u32 *__restrict__ next, u32 *__restrict__ next_count, u32 *__restrict__ longlist,
+                 u32 *__restrict__ long_count, u32 *__restrict__ maxd)
 {
-    constexpr int H = 1 << HBITS;
-    constexpr u32 MAXD = H - H / 4;
+    constexpr int H = CtShape<HBITS>::H;
+    constexpr u32 D = CtShape<HBITS>::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *acc = reinterpret_cast<double *>(smem_raw) + warp * (H * 32) + lane; // slot s: acc[s * 32]
-    u32 *key = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * H * 32 * sizeof(double)) + warp * (H * 32) + lane;
-    const u64 K = totals[1];
-    const u64 k = (u64)blockIdx.x * (CT_WARPS * 32) + threadIdx.x;
-    if (k >= K)
-        return;
-    const u32 cstart = nzstart[k], cend = nzstart[k + 1];
-    if (cend - cstart > maxlen)
-    {
-        list[atomicAdd(list_count, 1u)] = (u32)k;
-        return;
-    }
+    double *acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane; // accumulator i: acc[i * 32]
+    u32 *key = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
     const u32 rowmask = (1u << rowbits) - 1u;
-#pragma unroll
-    for (int s = 0; s < H; ++s)
-        key[s * 32] = CT_EMPTY;
-
-    u32 d = 0;
-    bool ovf = false;
-    Rec nxt[CT_U];
-#pragma unroll
-    for (int i = 0; i < CT_U; ++i)
-        if (cstart + i < cend)
-            nxt[i] = sorted[cstart + i];
-    for (u32 p = cstart; p < cend && !ovf; p += CT_U)
+    const u64 K = LIST ? (u64)*src_count : totals[1];
+    const u64 step = LIST ? (u64)gridDim.x * (CT_WARPS * 32) : ~0ull >> 1;
+    for (u64 t = (u64)blockIdx.x * (CT_WARPS * 32) + threadIdx.x; t < K; t += step)
     {
-        Rec cur[CT_U];
-#pragma unroll
-        for (int i = 0; i < CT_U; ++i)
-            cur[i] = nxt[i];
-#pragma unroll
-        for (int i = 0; i < CT_U; ++i)
-            if (p + CT_U + i < cend)
-                nxt[i] = sorted[p + CT_U + i];
-#pragma unroll
-        for (int i = 0; i < CT_U; ++i)
+        const u32 k = LIST ? src[t] : (u32)t;
+        const u32 cstart = nzstart[k], cend = nzstart[k + 1];
+        if (cend - cstart > maxlen)
         {
-            if (p + i < cend && !ovf)
+            longlist[atomicAdd(long_count, 1u)] = k;
+            continue;
+        }
+#pragma unroll
+        for (int s = 0; s < H; ++s)
+            key[s * 32] = CT_EMPTY;
+
+        u32 d = 0;       // accumulators in use
+        u32 pending = 0; // of which not (yet) existing: only updateindex! of a zero touched them
+        u64 exmask = 0;  // accumulator i holds an existing entry
+        bool ovf = false;
+        auto apply = [&](const Rec &r) {
+            const u32 row = (u32)(r.key >> low) & rowmask;
+            const double v = r.val;
+            u32 s = (row * 0x9E3779B1u) >> (32 - HBITS);
+            for (;;)
             {
-                const u32 row = (u32)(cur[i].key >> low) & rowmask;
-                const u32 fl = (u32)cur[i].key & 3u;
-                const double v = cur[i].val;
-                const u32 creates = ((fl != FL_UPDATE) | (v != 0.0)) ? CT_EXISTS : 0u;
-                u32 s = (row * 0x9E3779B1u) >> (32 - HBITS);
-                for (;;)
-                {
-                    const u32 kk = key[s * 32];
-                    if ((kk & ~CT_EXISTS) == row)
+                const u32 kk = key[s * 32];
+                const u32 x = kk ^ (row << HBITS);
+                if (x < D)
+                { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
+                    acc[x * 32] = acc[x * 32] + v;
+                    if (pending)
                     {
-                        acc[s * 32] = (fl == FL_OLD) ? v : acc[s * 32] + v;
-                        if (creates & ~kk)
-                            key[s * 32] = kk | CT_EXISTS;
-                        break;
-                    }
-                    if (kk == CT_EMPTY)
-                    {
-                        if (d >= MAXD)
+                        const u32 fl = (u32)r.key & 3u;
+                        if (!((exmask >> x) & 1ull) && ((fl != FL_UPDATE) | (v != 0.0)))
                         {
-                            ovf = true;
-                            break;
+                            exmask |= 1ull << x;
+                            --pending;
                         }
-                        key[s * 32] = row | creates;
-                        // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value
-                        // seeds it (extendable.jl:165-166)
-                        acc[s * 32] = (fl == FL_OLD) ? v : 0.0 + v;
-                        ++d;
-                        break;
                     }
-                    s = (s + 1) & (H - 1);
+                    return;
                 }
+                if (kk == CT_EMPTY)
+                {
+                    if (d >= D)
+                    {
+                        ovf = true;
+                        return;
+                    }
+                    const u32 fl = (u32)r.key & 3u;
+                    key[s * 32] = (row << HBITS) | d;
+                    // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value
+                    // seeds it (extendable.jl:165-166); updateindex! of a zero creates nothing (:212,223)
+                    acc[d * 32] = (fl == FL_OLD) ? v : 0.0 + v;
+                    if ((fl != FL_UPDATE) | (v != 0.0))
+                        exmask |= 1ull << d;
+                    else
+                        ++pending;
+                    ++d;
+                    return;
+                }
+                s = (s + 1) & (H - 1);
+            }
+        };
+
+        // A lane streams its own column: every load instruction of the warp touches 32 different
+        // lines, so the L1 sees one request per lane.  256-bit loads (two records per request, 32-byte
+        // aligned: the records of an odd start and an odd end go alone) halve that.
+        u32 p = cstart;
+        if ((p & 1u) && p < cend)
+            apply(sorted[p++]);
+        const Rec *col = sorted + p;
+        const u32 npair = (cend - p) >> 1;
+        const u32 nfull = npair / CT_U;
+        RecPair nxt[CT_U];
+        if (nfull)
+        {
+#pragma unroll
+            for (int i = 0; i < CT_U; ++i)
+                nxt[i] = ld_pair_stream(col + 2 * i);
+        }
+        u32 g = 0;
+        for (; g < nfull && !ovf; ++g)
+        {
+            RecPair cur[CT_U];
+#pragma unroll
+            for (int i = 0; i < CT_U; ++i)
+                cur[i] = nxt[i];
+            if (g + 1 < nfull)
+            {
+#pragma unroll
+                for (int i = 0; i < CT_U; ++i)
+                    nxt[i] = ld_pair_stream(col + 2 * ((g + 1) * CT_U + i));
+            }
+#pragma unroll
+            for (int i = 0; i < CT_U; ++i)
+            {
+                if (!ovf)
+                    apply(cur[i].a);
+                if (!ovf)
+                    apply(cur[i].b);
             }
         }
-    }
-    if (ovf)
-    {
-        list[atomicAdd(list_count, 1u)] = (u32)k;
-        return;
-    }
-    // ---- compact the existing entries to the front of the table (j <= s: in place)
-    u32 dd = 0;
-#pragma unroll 8
-    for (int s = 0; s < H; ++s)
-    {
-        const u32 kk = key[s * 32];
-        if (kk != CT_EMPTY && (kk & CT_EXISTS))
+        for (u32 q = p + 2 * nfull * CT_U; q < cend && !ovf; ++q)
+            apply(sorted[q]);
+        if (ovf)
         {
-            const double a = acc[s * 32];
-            key[dd * 32] = kk & ~CT_EXISTS;
-            acc[dd * 32] = a;
-            ++dd;
+            next[atomicAdd(next_count, 1u)] = k;
+            continue;
         }
+        // ---- existing entries: (row, accumulator) words compacted to the front of the table (in
+        // place: j <= s), then insertion-sorted by row.  Both loops run about equally long in all lanes.
+        u32 j = 0;
+#pragma unroll 8
+        for (int s = 0; s < H; ++s)
+        {
+            const u32 kk = key[s * 32];
+            if (kk != CT_EMPTY && ((exmask >> (kk & (H - 1))) & 1ull))
+            {
+                key[j * 32] = kk;
+                ++j;
+            }
+        }
+        for (u32 e = 1; e < j; ++e)
+        {
+            const u32 kk = key[e * 32];
+            u32 q = e;
+            while (q > 0)
+            {
+                const u32 prev = key[(q - 1) * 32];
+                if (prev < kk)
+                    break;
+                key[q * 32] = prev;
+                --q;
+            }
+            key[q * 32] = kk;
+        }
+        Rec *dst = tmp + cstart;
+        for (u32 e = 0; e < j; ++e)
+        {
+            const u32 pk = key[e * 32];
+            Rec o;
+            o.key = (u64)(pk >> HBITS);
+            o.val = acc[(pk & (H - 1)) * 32];
+            st_rec(dst + e, o);
+        }
+        colcount[nzcol[k]] = j;
+        if (d > ld_relaxed_u32(maxd))
+            atomicMax(maxd, d);
     }
-    // ---- rank by row, park at the column's offset
-    Rec *dst = tmp + cstart;
-    for (u32 e = 0; e < dd; ++e)
-    {
-        const u32 r = key[e * 32];
-        u32 rank = 0;
-        for (u32 t = 0; t < dd; ++t)
-            rank += key[t * 32] < r;
-        Rec o;
-        o.key = (u64)r;
-        o.val = acc[e * 32];
-        st_rec(dst + rank, o);
-    }
-    colcount[nzcol[k]] = dd;
 }
 
 // ------------------------------------------------------------------------
@@ -883,33 +940,52 @@ int env_int(const char *name, int dflt)
 const int g_thread_fold = env_int("XSB_THREAD_FOLD", 1);
 const int g_thread_hbits = env_int("XSB_THREAD_HBITS", 0);
 
-template <int HBITS>
-void launch_colthread_t(cudaStream_t stream, unsigned blocks, const Rec *sorted, int low, int rowbits, u32 maxlen,
-                        const u32 *nzcol, const u32 *nzstart, const u64 *totals, Rec *tmp, u32 *colcount, u32 *list,
-                        u32 *list_count)
+struct CtArgs
 {
-    constexpr size_t smem = (size_t)CT_WARPS * (1 << HBITS) * 32 * (sizeof(double) + sizeof(u32));
+    const Rec *sorted;
+    int low, rowbits;
+    u32 maxlen;
+    const u32 *nzcol, *nzstart;
+    const u64 *totals;
+    Rec *tmp;
+    u32 *colcount;
+    const u32 *src, *src_count;
+    u32 *next, *next_count, *longlist, *long_count, *maxd;
+};
+template <int HBITS, bool LIST> void launch_colthread_t(cudaStream_t stream, unsigned blocks, const CtArgs &a)
+{
+    constexpr size_t smem = CT_WARPS * CtShape<HBITS>::kBytesPerWarp;
     static bool attr = false;
     if (!attr)
     {
-        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS, LIST>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       (int)cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    colthread_kernel<HBITS><<<blocks, CT_WARPS * 32, smem, stream>>>(sorted, low, rowbits, maxlen, nzcol, nzstart, totals,
-                                                                     tmp, colcount, list, list_count);
+    colthread_kernel<HBITS, LIST><<<blocks, CT_WARPS * 32, smem, stream>>>(
+        a.sorted, a.low, a.rowbits, a.maxlen, a.nzcol, a.nzstart, a.totals, a.tmp, a.colcount, a.src, a.src_count, a.next,
+        a.next_count, a.longlist, a.long_count, a.maxd);
 }
-void launch_colthread(cudaStream_t stream, int hbits, unsigned blocks, const Rec *sorted, int low, int rowbits,
-                      u32 maxlen, const u32 *nzcol, const u32 *nzstart, const u64 *totals, Rec *tmp, u32 *colcount,
-                      u32 *list, u32 *list_count)
+// level 0/1/2 = 16/32/64 table slots; list = false: every non-empty column, true: the columns of a.src
+void launch_colthread(cudaStream_t stream, int level, bool list, unsigned blocks, const CtArgs &a)
 {
-    if (hbits == 4)
-        launch_colthread_t<4>(stream, blocks, sorted, low, rowbits, maxlen, nzcol, nzstart, totals, tmp, colcount, list, list_count);
-    else if (hbits == 5)
-        launch_colthread_t<5>(stream, blocks, sorted, low, rowbits, maxlen, nzcol, nzstart, totals, tmp, colcount, list, list_count);
+    if (!list)
+    {
+        if (level == 0)
+            launch_colthread_t<4, false>(stream, blocks, a);
+        else if (level == 1)
+            launch_colthread_t<5, false>(stream, blocks, a);
+        else
+            launch_colthread_t<6, false>(stream, blocks, a);
+    }
     else
-        launch_colthread_t<6>(stream, blocks, sorted, low, rowbits, maxlen, nzcol, nzstart, totals, tmp, colcount, list, list_count);
+    {
+        if (level == 1)
+            launch_colthread_t<5, true>(stream, blocks, a);
+        else
+            launch_colthread_t<6, true>(stream, blocks, a);
+    }
 }
 struct CfLayout
 {
@@ -939,8 +1015,8 @@ CfLayout cf_layout(u64 nrec, i64 ncols)
     o = up(o + sizeof(u64) * (ctiles + 1));
     l.off_tot = o;
     o = up(o + sizeof(u64) * 4);
-    l.off_list = o; // columns left over by the thread-per-column kernel
-    o = up(o + sizeof(u32) * (kmax + 1));
+    l.off_list = o; // columns left over by the thread-per-column kernels: two hand-over lists + the long columns
+    o = up(o + 3 * sizeof(u32) * (kmax + 1));
     l.bytes = o;
     return l;
 }
@@ -983,7 +1059,7 @@ void colfold_clear_counts(cudaStream_t stream, void *workspace, u64 nrec, i64 nc
 // *d_overflow != 0 if a group of columns did not fit the in-warp table (outputs then undefined).
 void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine, bool plain_adds,
                     i64 ncols, int idx64, int base, Rec *tmp, void *colptr_out, void *workspace, u64 *d_nnz,
-                    u32 *d_overflow, bool lists_ready, LaunchCounter &lc, StageTimer *timer)
+                    u32 *d_overflow, bool lists_ready, u32 *d_maxd, u32 hint_maxd, LaunchCounter &lc, StageTimer *timer)
 {
     const CfLayout l = cf_layout(nrec, ncols);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -1002,6 +1078,7 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     if (timer)
         timer->begin(stream);
     XSB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(u32), stream));
+    XSB_CUDA(cudaMemsetAsync(d_maxd, 0, sizeof(u32), stream));
     if (!lists_ready)
     { // column list from the per-column record counts (taken by the sort's histogram kernel)
         colscan_tilesum_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, ncols, trec, tnz);
@@ -1023,19 +1100,34 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     // Groups of short columns hold many distinct entries per record (little duplication), and the
     // in-register sort of the distinct entries grows faster than linearly: keep such groups small.
     const u32 chunk = (nrec / std::max<u64>(1, std::min<u64>((u64)ncols, nrec)) >= 48) ? (u32)CF_PIECE : 128u;
-    if (simple && L.rowbits <= CT_MAXROWBITS && g_thread_fold)
-    { // one thread per column; the columns it leaves over go to the warp kernel through a list
-        u32 *list = reinterpret_cast<u32 *>(ws + l.off_list);
-        u32 *list_count = reinterpret_cast<u32 *>(totals + 2);
-        XSB_CUDA(cudaMemsetAsync(list_count, 0, sizeof(u32), stream));
+    if (simple && g_thread_fold)
+    { // one thread per column, smallest table first; what a size cannot take is handed to the next
+      // one through a list, the rest (and the long columns) to the warp kernel
+        u32 *listA = reinterpret_cast<u32 *>(ws + l.off_list);
+        u32 *listB = listA + (kmax + 1);
+        u32 *longlist = listB + (kmax + 1);
+        u32 *counters = reinterpret_cast<u32 *>(totals + 2); // [0] listA, [1] listB, [2] long columns
+        XSB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(u32), stream));
         const u64 avg = nrec / std::max<u64>(1, kmax);
-        int hbits = avg < 14 ? 4 : (avg < 40 ? 5 : 6);
+        // table size to start with: what the previous flush of this handle needed, else the mean
+        // column length (a column cannot hold more distinct rows than records)
+        int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : 1);
         if (g_thread_hbits >= 4 && g_thread_hbits <= 6)
-            hbits = g_thread_hbits;
-        const u32 maxlen = (u32)std::max<u64>(256, 6 * avg);
+            level = g_thread_hbits - 4;
+        CtArgs a{sorted, L.low, L.rowbits, (u32)std::max<u64>(256, 6 * avg), nzcol, nzstart, totals, tmp, cnt,
+                 nullptr, nullptr, nullptr, nullptr, longlist, counters + 2, d_maxd};
         const unsigned blocks = (unsigned)((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32));
-        launch_colthread(stream, hbits, blocks, sorted, L.low, L.rowbits, maxlen, nzcol, nzstart, totals, tmp, cnt, list,
-                         list_count);
+        const unsigned lblocks = (unsigned)std::min<u64>(blocks, (u64)kNumSM * 8);
+        u32 *lists[2] = {listA, listB};
+        for (int lv = level, hop = 0; lv <= 2; ++lv, ++hop)
+        {
+            a.src = hop ? lists[(hop - 1) & 1] : nullptr;
+            a.src_count = hop ? counters + ((hop - 1) & 1) : nullptr;
+            a.next = lv == 2 ? longlist : lists[hop & 1];
+            a.next_count = lv == 2 ? counters + 2 : counters + (hop & 1);
+            launch_colthread(stream, lv, hop != 0, hop ? lblocks : blocks, a);
+            lc.add();
+        }
         constexpr int W = 8;
         const size_t smem = sizeof(WarpSpace<true>) * W;
         static bool attr = false;
@@ -1045,8 +1137,7 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
             attr = true;
         }
         colfold_kernel<true, W, true><<<kNumSM * 2, W * 32, smem, stream>>>(sorted, L, combine, chunk, nzcol, nzstart, tilek,
-                                                                          ntiles, tmp, cnt, d_overflow, list, list_count);
-        lc.add();
+                                                                          ntiles, tmp, cnt, d_overflow, longlist, counters + 2);
     }
     else if (simple)
     {

@@ -127,6 +127,20 @@ __device__ __forceinline__ Rec ld_rec_stream(const Rec *p)
                  : "l"(p));
     return r;
 }
+// two consecutive records in one 256-bit request (sm_100: LDG.256); p must be 32-byte aligned
+struct RecPair
+{
+    Rec a, b;
+};
+__device__ __forceinline__ RecPair ld_pair_stream(const Rec *p)
+{
+    RecPair r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(r.a.key), "=l"(*reinterpret_cast<u64 *>(&r.a.val)), "=l"(r.b.key),
+                   "=l"(*reinterpret_cast<u64 *>(&r.b.val))
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void st_rec(Rec *p, const Rec &r)
 {
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(r.key),

@@ -107,9 +107,16 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
                 {
                     const bool valid = bb + lane < cnt_here;
                     const u32 col = (u32)(key[i] >> colshift) & colmask;
+                    const u32 vm = __ballot_sync(full, valid);
+                    u32 peers = 0;
+                    if (valid)
+                        peers = __match_any_sync(vm, col);
+                    // the FIRST lane that holds a column speaks for it: the order of the chunk's column
+                    // list does not depend on timing, and the table sees one request per distinct column
+                    const bool leader = valid && (peers & lt) == 0u;
                     u32 slot = gp_hash(col);
                     bool fresh = false;
-                    if (valid)
+                    if (leader)
                     {
                         for (;;)
                         {
@@ -124,21 +131,13 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
                             slot = (slot + 1) & (GP_H - 1);
                         }
                     }
-                    const u32 fb = __ballot_sync(full, fresh);
-                    const u32 vm = __ballot_sync(full, valid);
-                    u32 peers = 0;
-                    if (valid)
-                        peers = __match_any_sync(vm, slot);
-                    const bool leader = valid && (peers & lt) == 0u;
-                    // a new column is registered by the FIRST lane that holds it: the order of the
-                    // chunk's column list must not depend on which lane won the CAS
-                    const bool reg = leader && (fb & peers) != 0u;
-                    const u32 rb = __ballot_sync(full, reg);
-                    if (reg)
+                    const u32 rb = __ballot_sync(full, fresh);
+                    if (fresh)
                         ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
                     d += __popc(rb);
                     if (leader)
-                        atomicAdd(&ws.cnt[slot], (u32)__popc(peers));
+                        ws.cnt[slot] += (u32)__popc(peers); // leaders hold distinct slots of a warp-private table
+                    __syncwarp();
                 }
             }
         }
@@ -325,6 +324,19 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
         ws.cur[slot] = o;
     }
     __syncwarp();
+    Rec nxt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const u32 p = i * 32 + lane;
+        if (p < cnt_here)
+            nxt[i] = ld_rec_stream(in + r0 + p);
+        else
+        {
+            nxt[i].key = 0;
+            nxt[i].val = 0.0;
+        }
+    }
 #pragma unroll 1
     for (int g = 0; g < GP_NB; g += 4)
     {
@@ -332,14 +344,10 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            const u32 p = (g + i) * 32 + lane;
+            r[i] = nxt[i];
+            const u32 p = (g + 4 + i) * 32 + lane; // the next group travels while this one is ranked
             if (p < cnt_here)
-                r[i] = ld_rec_stream(in + r0 + p);
-            else
-            {
-                r[i].key = 0;
-                r[i].val = 0.0;
-            }
+                nxt[i] = ld_rec_stream(in + r0 + p);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -349,18 +357,21 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
             {
                 const bool valid = bb + lane < cnt_here;
                 const u32 col = (u32)(r[i].key >> colshift) & colmask;
-                u32 slot = gp_hash(col);
-                if (valid)
-                    while (ws.key[slot] != col)
-                        slot = (slot + 1) & (GP_H - 1);
                 const u32 vm = __ballot_sync(full, valid);
                 u32 peers = 1u << lane;
                 if (valid)
-                    peers = __match_any_sync(vm, slot);
+                    peers = __match_any_sync(vm, col);
                 const int ldr = __ffs(peers) - 1;
                 u32 b = 0;
                 if (valid && lane == ldr)
-                    b = atomicAdd(&ws.cur[slot], (u32)__popc(peers));
+                { // one lane per distinct column looks it up and advances its cursor
+                    u32 slot = gp_hash(col);
+                    while (ws.key[slot] != col)
+                        slot = (slot + 1) & (GP_H - 1);
+                    b = ws.cur[slot];
+                    ws.cur[slot] = b + (u32)__popc(peers);
+                }
+                __syncwarp();
                 b = __shfl_sync(full, b, ldr);
                 if (valid)
                     st_rec(out + (b + __popc(peers & lt)), r[i]);

@@ -124,7 +124,9 @@ void colfold_clear_counts(cudaStream_t stream, void *workspace, u64 nrec, i64 nc
 // records sorted by column only (stable) + per-column record counts -> entries parked in tmp, colptr, nnz
 void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, int combine, bool plain_adds,
                     i64 ncols, int idx64, int base, Rec *tmp, void *colptr_out, void *workspace, u64 *d_nnz,
-                    u32 *d_overflow, bool lists_ready, LaunchCounter &lc, StageTimer *timer);
+                    u32 *d_overflow, bool lists_ready, u32 *d_maxd, u32 hint_maxd, LaunchCounter &lc, StageTimer *timer);
+// d_maxd receives the largest number of distinct rows a thread-folded column held (0: path not taken);
+// hint_maxd is that number from the handle's previous flush (0: unknown) and picks the first table size
 void colfold_lists(void *workspace, u64 nrec, i64 ncols, u32 **nzcol, u32 **nzstart, u64 **totals);
 
 // ---- xsb_group.cu
