@@ -64,7 +64,7 @@ class FlushStats(C.Structure):
         ("ms_group_scatter", C.c_float),
         ("ms_fold", C.c_float),
         ("ms_compact", C.c_float),
-        ("reserved_", C.c_float),
+        ("direct_fold", C.c_int32),
     ]
 
     def as_dict(self):

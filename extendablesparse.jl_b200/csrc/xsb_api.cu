@@ -220,6 +220,8 @@ struct xsb_matrix
     int grouping_misses = 0;          // consecutive flushes whose stream had no column locality
     i64 stats_pairs = 0;
     bool last_column_path = false;
+    bool no_direct_fold = false; // the one-pass fold met columns it cannot take: park + compact instead
+    int stats_direct = 0;
     u32 fold_hint = 0; // most distinct rows a column held in the previous thread-per-column fold
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
@@ -419,6 +421,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     const i64 nnz_old = h->nnz;
     const i64 total = nnz_old + n_ins;
     h->stats_pairs = 0;
+    h->stats_direct = 0;
     REQUIRE((u64)total < (1ull << 40), XSB_EINVAL, "too many staged entries");
 
     // ---- input buffer A = [old CSC as records | staged records in tid order]
@@ -504,15 +507,46 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             passes_run += plan.npasses;
             spare = (sorted == A) ? B : A;
         }
-        colfold_reduce(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
-                       new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), grouped,
-                       reinterpret_cast<u32 *>(h->d_scal + 7), h->fold_hint, h->lc, tp);
-        path = grouped ? 3 : 2;
-        XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-        nnz_new = (i64)read_scalar(h, 0);
-        if ((u32)h->h_scal[7])
-            h->fold_hint = (u32)h->h_scal[7]; // distinct rows per column: picks the next flush's table size
-        if ((u32)h->h_scal[6] == 0u)
+        bool direct = false, lists_ready = grouped;
+        if (!h->no_direct_fold && colfold_direct_supported(h->L, combine, !h->has_assign))
+        { // one pass: fold every column and write rowval / nzval / colptr in place (the spare buffer)
+            new_rowval = spare;
+            new_nzval = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spare) + 8 * (size_t)total);
+            colfold_direct(s, sorted, (u64)total, h->L, h->n, h->idx64, h->base, new_rowval, new_nzval, new_colptr, cws,
+                           h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), grouped,
+                           reinterpret_cast<u32 *>(h->d_scal + 7), h->fold_hint, h->lc, tp);
+            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+            nnz_new = (i64)read_scalar(h, 0);
+            const u32 redo = (u32)h->h_scal[6];
+            if ((u32)h->h_scal[7])
+                h->fold_hint = (u32)h->h_scal[7];
+            lists_ready = true;
+            if (redo == 0u)
+            {
+                direct = true;
+                new_store = spare;
+                new_store_bytes = sizeof(Rec) * (size_t)total;
+                path = grouped ? 3 : 2;
+                h->stats_direct = 1;
+            }
+            else if (redo & 6u)
+                h->no_direct_fold = true; // long or very rich columns: this handle parks and compacts from now on
+        }
+        if (!direct)
+        {
+            colfold_reduce(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
+                           new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), lists_ready,
+                           reinterpret_cast<u32 *>(h->d_scal + 7), h->fold_hint, h->lc, tp);
+            path = grouped ? 3 : 2;
+            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+            nnz_new = (i64)read_scalar(h, 0);
+            if ((u32)h->h_scal[7])
+                h->fold_hint = (u32)h->h_scal[7]; // distinct rows per column: picks the next flush's table size
+        }
+        if (direct)
+        {
+        }
+        else if ((u32)h->h_scal[6] == 0u)
         {
             const size_t rv_bytes = (h->isz() * (size_t)nnz_new + 15) & ~(size_t)15;
             new_store_bytes = rv_bytes + 8 * (size_t)nnz_new;
@@ -616,6 +650,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.kernel_launches = h->lc.in_flush;
     h->stats.ms_host_alloc = h->alloc_ms;
     h->stats.group_pairs = h->stats_pairs;
+    h->stats.direct_fold = h->stats_direct;
     if (tp)
     {
         XSB_CUDA(cudaEventRecord(e1, s));

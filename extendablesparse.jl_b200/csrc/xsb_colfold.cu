@@ -629,9 +629,140 @@ constexpr u32 CT_EMPTY = 0xffffffffu;
 template <int HBITS> struct CtShape
 {
     static constexpr int H = 1 << HBITS;
-    static constexpr int D = H - H / 4;
-    static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + sizeof(double) * D);
+    static constexpr int D = HBITS == 6 ? 32 : H - H / 4; // 12, 24, 32 accumulators
+    // table words + accumulators + row of every accumulator (first-appearance order)
+    static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + sizeof(u32)) * D);
 };
+
+// Folds the records [cstart, cend) of one column.  Returns the number of existing entries j, their
+// (row << HBITS | accumulator) words sorted in key[0 .. j), or -1 if the table is too small.
+// d_out = distinct rows seen.
+template <int HBITS>
+__device__ __forceinline__ int ct_fold_column(const Rec *__restrict__ sorted, u32 cstart, u32 cend, int low,
+                                              u32 rowmask, u32 *key, double *acc, u32 *rows, u32 &d_out)
+{
+    constexpr int H = CtShape<HBITS>::H;
+    constexpr u32 D = CtShape<HBITS>::D;
+#pragma unroll
+    for (int s = 0; s < H; ++s)
+        key[s * 32] = CT_EMPTY;
+
+    u32 d = 0;       // accumulators in use
+    u32 pending = 0; // of which not (yet) existing: only updateindex! of a zero touched them
+    u64 exmask = 0;  // accumulator i holds an existing entry
+    bool ovf = false;
+    auto apply = [&](const Rec &r) {
+        const u32 row = (u32)(r.key >> low) & rowmask;
+        const double v = r.val;
+        u32 s = (row * 0x9E3779B1u) >> (32 - HBITS);
+        for (;;)
+        {
+            const u32 kk = key[s * 32];
+            const u32 x = kk ^ (row << HBITS);
+            if (x < D)
+            { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
+                acc[x * 32] = acc[x * 32] + v;
+                if (pending)
+                {
+                    const u32 fl = (u32)r.key & 3u;
+                    if (!((exmask >> x) & 1ull) && ((fl != FL_UPDATE) | (v != 0.0)))
+                    {
+                        exmask |= 1ull << x;
+                        --pending;
+                    }
+                }
+                return;
+            }
+            if (kk == CT_EMPTY)
+            {
+                if (d >= D)
+                {
+                    ovf = true;
+                    return;
+                }
+                const u32 fl = (u32)r.key & 3u;
+                key[s * 32] = (row << HBITS) | d;
+                rows[d * 32] = row;
+                // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value
+                // seeds it (extendable.jl:165-166); updateindex! of a zero creates nothing (:212,223)
+                acc[d * 32] = (fl == FL_OLD) ? v : 0.0 + v;
+                if ((fl != FL_UPDATE) | (v != 0.0))
+                    exmask |= 1ull << d;
+                else
+                    ++pending;
+                ++d;
+                return;
+            }
+            s = (s + 1) & (H - 1);
+        }
+    };
+
+    // A lane streams its own column: every load instruction of the warp touches 32 different
+    // lines, so the L1 sees one request per lane.  256-bit loads (two records per request, 32-byte
+    // aligned: the records of an odd start and an odd end go alone) halve that.
+    u32 p = cstart;
+    if ((p & 1u) && p < cend)
+        apply(sorted[p++]);
+    const Rec *col = sorted + p;
+    const u32 npair = (cend - p) >> 1;
+    const u32 nfull = npair / CT_U;
+    RecPair nxt[CT_U];
+    if (nfull)
+    {
+#pragma unroll
+        for (int i = 0; i < CT_U; ++i)
+            nxt[i] = ld_pair_stream(col + 2 * i);
+    }
+    u32 g = 0;
+    for (; g < nfull && !ovf; ++g)
+    {
+        RecPair cur[CT_U];
+#pragma unroll
+        for (int i = 0; i < CT_U; ++i)
+            cur[i] = nxt[i];
+        if (g + 1 < nfull)
+        {
+#pragma unroll
+            for (int i = 0; i < CT_U; ++i)
+                nxt[i] = ld_pair_stream(col + 2 * ((g + 1) * CT_U + i));
+        }
+#pragma unroll
+        for (int i = 0; i < CT_U; ++i)
+        {
+            if (!ovf)
+                apply(cur[i].a);
+            if (!ovf)
+                apply(cur[i].b);
+        }
+    }
+    for (u32 q = p + 2 * nfull * CT_U; q < cend && !ovf; ++q)
+        apply(sorted[q]);
+    d_out = ovf ? D + 1 : d;
+    if (ovf)
+        return -1;
+    // ---- existing entries as (row << HBITS | accumulator) words, insertion-sorted by row into the
+    // (no longer needed) table.  They are taken in order of first appearance, which an assembly
+    // stream visits nearly in row order: few shifts (src/matrix/sparsematrixlnk.jl:339 sorts here too).
+    u32 j = 0;
+    for (u32 i = 0; i < d; ++i)
+    {
+        if (!((exmask >> i) & 1ull))
+            continue;
+        const u32 kk = (rows[i * 32] << HBITS) | i;
+        u32 q = j;
+        while (q > 0)
+        {
+            const u32 prev = key[(q - 1) * 32];
+            if (prev < kk)
+                break;
+            key[q * 32] = prev;
+            --q;
+        }
+        key[q * 32] = kk;
+        ++j;
+    }
+    return (int)j;
+}
 
 template <int HBITS, bool LIST>
 __global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 5 : 2))
@@ -647,6 +778,8 @@ colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxle
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane; // accumulator i: acc[i * 32]
     u32 *key = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
+    u32 *rows = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * 32 * (D * sizeof(double) + H * sizeof(u32))) +
+                warp * (D * 32) + lane;
     const u32 rowmask = (1u << rowbits) - 1u;
     const u64 K = LIST ? (u64)*src_count : totals[1];
     const u64 step = LIST ? (u64)gridDim.x * (CT_WARPS * 32) : ~0ull >> 1;
@@ -659,133 +792,17 @@ colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxle
             longlist[atomicAdd(long_count, 1u)] = k;
             continue;
         }
-#pragma unroll
-        for (int s = 0; s < H; ++s)
-            key[s * 32] = CT_EMPTY;
-
-        u32 d = 0;       // accumulators in use
-        u32 pending = 0; // of which not (yet) existing: only updateindex! of a zero touched them
-        u64 exmask = 0;  // accumulator i holds an existing entry
-        bool ovf = false;
-        auto apply = [&](const Rec &r) {
-            const u32 row = (u32)(r.key >> low) & rowmask;
-            const double v = r.val;
-            u32 s = (row * 0x9E3779B1u) >> (32 - HBITS);
-            for (;;)
-            {
-                const u32 kk = key[s * 32];
-                const u32 x = kk ^ (row << HBITS);
-                if (x < D)
-                { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
-                    acc[x * 32] = acc[x * 32] + v;
-                    if (pending)
-                    {
-                        const u32 fl = (u32)r.key & 3u;
-                        if (!((exmask >> x) & 1ull) && ((fl != FL_UPDATE) | (v != 0.0)))
-                        {
-                            exmask |= 1ull << x;
-                            --pending;
-                        }
-                    }
-                    return;
-                }
-                if (kk == CT_EMPTY)
-                {
-                    if (d >= D)
-                    {
-                        ovf = true;
-                        return;
-                    }
-                    const u32 fl = (u32)r.key & 3u;
-                    key[s * 32] = (row << HBITS) | d;
-                    // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value
-                    // seeds it (extendable.jl:165-166); updateindex! of a zero creates nothing (:212,223)
-                    acc[d * 32] = (fl == FL_OLD) ? v : 0.0 + v;
-                    if ((fl != FL_UPDATE) | (v != 0.0))
-                        exmask |= 1ull << d;
-                    else
-                        ++pending;
-                    ++d;
-                    return;
-                }
-                s = (s + 1) & (H - 1);
-            }
-        };
-
-        // A lane streams its own column: every load instruction of the warp touches 32 different
-        // lines, so the L1 sees one request per lane.  256-bit loads (two records per request, 32-byte
-        // aligned: the records of an odd start and an odd end go alone) halve that.
-        u32 p = cstart;
-        if ((p & 1u) && p < cend)
-            apply(sorted[p++]);
-        const Rec *col = sorted + p;
-        const u32 npair = (cend - p) >> 1;
-        const u32 nfull = npair / CT_U;
-        RecPair nxt[CT_U];
-        if (nfull)
-        {
-#pragma unroll
-            for (int i = 0; i < CT_U; ++i)
-                nxt[i] = ld_pair_stream(col + 2 * i);
-        }
-        u32 g = 0;
-        for (; g < nfull && !ovf; ++g)
-        {
-            RecPair cur[CT_U];
-#pragma unroll
-            for (int i = 0; i < CT_U; ++i)
-                cur[i] = nxt[i];
-            if (g + 1 < nfull)
-            {
-#pragma unroll
-                for (int i = 0; i < CT_U; ++i)
-                    nxt[i] = ld_pair_stream(col + 2 * ((g + 1) * CT_U + i));
-            }
-#pragma unroll
-            for (int i = 0; i < CT_U; ++i)
-            {
-                if (!ovf)
-                    apply(cur[i].a);
-                if (!ovf)
-                    apply(cur[i].b);
-            }
-        }
-        for (u32 q = p + 2 * nfull * CT_U; q < cend && !ovf; ++q)
-            apply(sorted[q]);
-        if (ovf)
+        u32 d;
+        const int j = ct_fold_column<HBITS>(sorted, cstart, cend, low, rowmask, key, acc, rows, d);
+        if (j < 0)
         {
             next[atomicAdd(next_count, 1u)] = k;
+            if (d > ld_relaxed_u32(maxd))
+                atomicMax(maxd, d);
             continue;
         }
-        // ---- existing entries: (row, accumulator) words compacted to the front of the table (in
-        // place: j <= s), then insertion-sorted by row.  Both loops run about equally long in all lanes.
-        u32 j = 0;
-#pragma unroll 8
-        for (int s = 0; s < H; ++s)
-        {
-            const u32 kk = key[s * 32];
-            if (kk != CT_EMPTY && ((exmask >> (kk & (H - 1))) & 1ull))
-            {
-                key[j * 32] = kk;
-                ++j;
-            }
-        }
-        for (u32 e = 1; e < j; ++e)
-        {
-            const u32 kk = key[e * 32];
-            u32 q = e;
-            while (q > 0)
-            {
-                const u32 prev = key[(q - 1) * 32];
-                if (prev < kk)
-                    break;
-                key[q * 32] = prev;
-                --q;
-            }
-            key[q * 32] = kk;
-        }
         Rec *dst = tmp + cstart;
-        for (u32 e = 0; e < j; ++e)
+        for (int e = 0; e < j; ++e)
         {
             const u32 pk = key[e * 32];
             Rec o;
@@ -793,9 +810,173 @@ colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxle
             o.val = acc[(pk & (H - 1)) * 32];
             st_rec(dst + e, o);
         }
-        colcount[nzcol[k]] = j;
+        colcount[nzcol[k]] = (u32)j;
         if (d > ld_relaxed_u32(maxd))
             atomicMax(maxd, d);
+    }
+}
+
+// The same fold writing the final CSC in ONE pass: the entries of column k go to
+// rowval/nzval[sum of the entry counts of the columns before k ...], that sum coming from a block
+// scan plus a decoupled look-back over the block totals (blocks are dispatched in index order).
+// A column that needs another table size or the warp kernel raises *d_redo; the caller then runs
+// the parking path (colthread_kernel + compact) instead.
+constexpr u64 DS_AGG = 1ull << 62, DS_INCL = 2ull << 62, DS_VALUE = (1ull << 62) - 1ull;
+
+template <int HBITS, typename Ti>
+__global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 5 : 2))
+colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxlen,
+                        const u32 *__restrict__ nzcol, const u32 *__restrict__ nzstart,
+                        const u64 *__restrict__ totals, i64 ncols, Ti base, Ti *__restrict__ rowval,
+                        double *__restrict__ nzval, Ti *__restrict__ colptr, u64 *__restrict__ status,
+                        u64 *__restrict__ d_nnz, u32 *__restrict__ d_redo, u32 *__restrict__ maxd)
+{
+    constexpr int H = CtShape<HBITS>::H;
+    constexpr u32 D = CtShape<HBITS>::D;
+    constexpr u32 full = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_wsum[CT_WARPS];
+    __shared__ u64 s_prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane;
+    u32 *key = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
+    u32 *rows = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * 32 * (D * sizeof(double) + H * sizeof(u32))) +
+                warp * (D * 32) + lane;
+    const u32 rowmask = (1u << rowbits) - 1u;
+    const u64 K = totals[1];
+    const u64 k = (u64)blockIdx.x * (CT_WARPS * 32) + threadIdx.x;
+    int j = 0;
+    u32 cstart = 0;
+    if (k < K && ld_relaxed_u32(d_redo) == 0u)
+    {
+        cstart = nzstart[k];
+        const u32 cend = nzstart[k + 1];
+        if (cend - cstart > maxlen)
+            atomicOr(d_redo, 2u);
+        else
+        {
+            u32 d;
+            j = ct_fold_column<HBITS>(sorted, cstart, cend, low, rowmask, key, acc, rows, d);
+            if (j < 0)
+            { // bit 2: not even the largest table takes this column
+                atomicOr(d_redo, HBITS == 6 ? 5u : 1u);
+                j = 0;
+            }
+            if (d > ld_relaxed_u32(maxd))
+                atomicMax(maxd, d);
+        }
+    }
+    // ---- entries before this column: warp scan, block scan, look-back over the blocks
+    u32 incl = (u32)j;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u32 t = __shfl_up_sync(full, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_wsum[warp] = incl;
+    __syncthreads();
+    u32 wpre = 0, btotal = 0;
+#pragma unroll
+    for (int w = 0; w < CT_WARPS; ++w)
+    {
+        const u32 c = s_wsum[w];
+        if (w < warp)
+            wpre += c;
+        btotal += c;
+    }
+    if (warp == 0)
+    {
+        u64 *mine = status + blockIdx.x;
+        u64 prefix = 0;
+        if (blockIdx.x == 0)
+        {
+            if (lane == 0)
+                st_relaxed_u64(mine, DS_INCL | (u64)btotal);
+        }
+        else
+        {
+            if (lane == 0)
+                st_relaxed_u64(mine, DS_AGG | (u64)btotal);
+            i64 b = (i64)blockIdx.x - 1;
+            for (;;)
+            { // lane l looks at block b - l
+                u64 v = DS_INCL;
+                if (b - lane >= 0)
+                {
+                    do
+                        v = ld_relaxed_u64(status + (b - lane));
+                    while ((v >> 62) == 0ull);
+                }
+                const u32 inc = __ballot_sync(full, (v >> 62) == 2ull);
+                const int first = inc ? __ffs(inc) - 1 : 31; // nearest block with an inclusive prefix, if in this window
+                u64 c = (lane <= first) ? (v & DS_VALUE) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    c += __shfl_xor_sync(full, c, o);
+                prefix += c;
+                if (inc)
+                    break;
+                b -= 32;
+            }
+            if (lane == 0)
+                st_relaxed_u64(mine, DS_INCL | (prefix + (u64)btotal));
+        }
+        if (lane == 0)
+            s_prefix = prefix;
+    }
+    __syncthreads();
+    if (k >= K)
+        return;
+    const u64 o0 = s_prefix + wpre + (incl - (u32)j);
+    // 256-bit stores where the destination is 32-byte aligned (rowval and nzval separately: their
+    // bases differ): a lane writes its own run, so every store instruction costs one request per lane
+    {
+        Ti *rv = rowval + o0;
+        auto row_at = [&](int e) { return (Ti)(key[e * 32] >> HBITS) + base; };
+        constexpr int V = 32 / (int)sizeof(Ti);
+        int e = 0;
+        for (; e < j && (reinterpret_cast<uintptr_t>(rv + e) & 31u); ++e)
+            rv[e] = row_at(e);
+        for (; e + V <= j; e += V)
+        {
+            if (sizeof(Ti) == 8)
+                st_v4_u64(rv + e, (u64)row_at(e), (u64)row_at(e + 1), (u64)row_at(e + 2), (u64)row_at(e + 3));
+            else
+            {
+                const u64 w0 = (u64)(u32)row_at(e) | ((u64)(u32)row_at(e + 1) << 32);
+                const u64 w1 = (u64)(u32)row_at(e + 2) | ((u64)(u32)row_at(e + 3) << 32);
+                const u64 w2 = (u64)(u32)row_at(e + 4) | ((u64)(u32)row_at(e + 5) << 32);
+                const u64 w3 = (u64)(u32)row_at(e + 6) | ((u64)(u32)row_at(e + 7) << 32);
+                st_v4_u64(rv + e, w0, w1, w2, w3);
+            }
+        }
+        for (; e < j; ++e)
+            rv[e] = row_at(e);
+    }
+    {
+        double *nv = nzval + o0;
+        auto val_at = [&](int e) { return (u64)__double_as_longlong(acc[(key[e * 32] & (H - 1)) * 32]); };
+        int e = 0;
+        for (; e < j && (reinterpret_cast<uintptr_t>(nv + e) & 31u); ++e)
+            nv[e] = __longlong_as_double((long long)val_at(e));
+        for (; e + 4 <= j; e += 4)
+            st_v4_u64(nv + e, val_at(e), val_at(e + 1), val_at(e + 2), val_at(e + 3));
+        for (; e < j; ++e)
+            nv[e] = __longlong_as_double((long long)val_at(e));
+    }
+    // colptr of this column and of the empty columns right before it
+    const i64 c1 = (i64)nzcol[k];
+    const i64 c0 = k ? (i64)nzcol[k - 1] + 1 : 0;
+    for (i64 c = c0; c <= c1; ++c)
+        colptr[c] = (Ti)o0 + base;
+    if (k == K - 1)
+    {
+        for (i64 c = c1 + 1; c <= ncols; ++c)
+            colptr[c] = (Ti)(o0 + j) + base;
+        *d_nnz = o0 + (u64)j;
     }
 }
 
@@ -939,6 +1120,7 @@ int env_int(const char *name, int dflt)
 // column on the warp kernel, XSB_THREAD_HBITS=4|5|6 fixes the per-thread table size
 const int g_thread_fold = env_int("XSB_THREAD_FOLD", 1);
 const int g_thread_hbits = env_int("XSB_THREAD_HBITS", 0);
+const int g_direct_fold = env_int("XSB_DIRECT_FOLD", 1); // 0: always park the entries and compact them
 
 struct CtArgs
 {
@@ -989,7 +1171,7 @@ void launch_colthread(cudaStream_t stream, int level, bool list, unsigned blocks
 }
 struct CfLayout
 {
-    size_t off_cnt, off_nzcol, off_nzstart, off_tilek, off_trec, off_tnz, off_tsum, off_tot, off_list, bytes;
+    size_t off_cnt, off_nzcol, off_nzstart, off_tilek, off_trec, off_tnz, off_tsum, off_tot, off_list, off_status, bytes;
 };
 CfLayout cf_layout(u64 nrec, i64 ncols)
 {
@@ -1017,6 +1199,8 @@ CfLayout cf_layout(u64 nrec, i64 ncols)
     o = up(o + sizeof(u64) * 4);
     l.off_list = o; // columns left over by the thread-per-column kernels: two hand-over lists + the long columns
     o = up(o + 3 * sizeof(u32) * (kmax + 1));
+    l.off_status = o; // look-back words of the one-pass fold, one per block of CT_WARPS*32 columns
+    o = up(o + sizeof(u64) * ((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32) + 1));
     l.bytes = o;
     return l;
 }
@@ -1052,6 +1236,101 @@ u32 *colfold_counts(void *workspace, u64 nrec, i64 ncols)
 void colfold_clear_counts(cudaStream_t stream, void *workspace, u64 nrec, i64 ncols)
 {
     XSB_CUDA(cudaMemsetAsync(colfold_counts(workspace, nrec, ncols), 0, sizeof(u32) * ((size_t)ncols + 1), stream));
+}
+
+namespace {
+template <int HBITS, typename Ti>
+void launch_direct_t(cudaStream_t stream, unsigned blocks, const Rec *sorted, int low, int rowbits, u32 maxlen,
+                     const u32 *nzcol, const u32 *nzstart, const u64 *totals, i64 ncols, i64 base, void *rowval,
+                     double *nzval, void *colptr, u64 *status, u64 *d_nnz, u32 *d_redo, u32 *maxd)
+{
+    constexpr size_t smem = CT_WARPS * CtShape<HBITS>::kBytesPerWarp;
+    static bool attr = false;
+    if (!attr)
+    {
+        XSB_CUDA(cudaFuncSetAttribute(colthread_direct_kernel<HBITS, Ti>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        XSB_CUDA(cudaFuncSetAttribute(colthread_direct_kernel<HBITS, Ti>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
+        attr = true;
+    }
+    colthread_direct_kernel<HBITS, Ti><<<blocks, CT_WARPS * 32, smem, stream>>>(
+        sorted, low, rowbits, maxlen, nzcol, nzstart, totals, ncols, (Ti)base, (Ti *)rowval, nzval, (Ti *)colptr, status,
+        d_nnz, d_redo, maxd);
+}
+} // namespace
+
+bool colfold_direct_supported(const KeyLayout &L, int combine, bool plain_adds)
+{
+    return g_thread_fold && g_direct_fold && plain_adds && L.tidbits == 0 && combine == 0;
+}
+
+// One-pass variant of the fold for plain += streams: records grouped by column -> final rowval / nzval /
+// colptr (rowval_out / nzval_out need room for nrec entries).  *d_redo != 0 afterwards: a column did not
+// fit the chosen table (bit 0) or is too long for one thread (bit 1); nothing valid was written and the
+// caller runs colfold_reduce (lists_ready = true) + colfold_compact instead.
+void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, i64 ncols, int idx64, int base,
+                    void *rowval_out, double *nzval_out, void *colptr_out, void *workspace, u64 *d_nnz, u32 *d_redo,
+                    bool lists_ready, u32 *d_maxd, u32 hint_maxd, LaunchCounter &lc, StageTimer *timer)
+{
+    const CfLayout l = cf_layout(nrec, ncols);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    u32 *cnt = reinterpret_cast<u32 *>(ws + l.off_cnt);
+    u32 *nzcol = reinterpret_cast<u32 *>(ws + l.off_nzcol);
+    u32 *nzstart = reinterpret_cast<u32 *>(ws + l.off_nzstart);
+    u64 *trec = reinterpret_cast<u64 *>(ws + l.off_trec);
+    u32 *tnz = reinterpret_cast<u32 *>(ws + l.off_tnz);
+    u64 *totals = reinterpret_cast<u64 *>(ws + l.off_tot);
+    u64 *status = reinterpret_cast<u64 *>(ws + l.off_status);
+    const u64 kmax = std::min<u64>((u64)ncols, nrec);
+    const unsigned ctiles = (unsigned)(((u64)ncols + CS_TILE - 1) / CS_TILE);
+    const unsigned blocks = (unsigned)((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32));
+    if (timer)
+        timer->begin(stream);
+    XSB_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(u32), stream));
+    XSB_CUDA(cudaMemsetAsync(d_maxd, 0, sizeof(u32), stream));
+    XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * ((size_t)blocks + 1), stream));
+    if (!lists_ready)
+    {
+        colscan_tilesum_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, ncols, trec, tnz);
+        colscan_scan_kernel<<<1, 1024, 0, stream>>>(trec, tnz, (i64)ctiles, totals, nzstart);
+        colscan_emit_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, trec, tnz, ncols, nzcol, nzstart);
+        lc.add(3);
+    }
+    if (timer)
+        timer->end(stream, &StageTimes::colptr);
+    if (timer)
+        timer->begin(stream);
+    const u64 avg = nrec / std::max<u64>(1, kmax);
+    int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : 1);
+    if (g_thread_hbits >= 4 && g_thread_hbits <= 6)
+        level = g_thread_hbits - 4;
+    const u32 maxlen = (u32)std::max<u64>(256, 6 * avg);
+#define XSB_DIRECT(HB, TI)                                                                                              \
+    launch_direct_t<HB, TI>(stream, blocks, sorted, L.low, L.rowbits, maxlen, nzcol, nzstart, totals, ncols, base,      \
+                            rowval_out, nzval_out, colptr_out, status, d_nnz, d_redo, d_maxd)
+    if (idx64)
+    {
+        if (level == 0)
+            XSB_DIRECT(4, int64_t);
+        else if (level == 1)
+            XSB_DIRECT(5, int64_t);
+        else
+            XSB_DIRECT(6, int64_t);
+    }
+    else
+    {
+        if (level == 0)
+            XSB_DIRECT(4, int32_t);
+        else if (level == 1)
+            XSB_DIRECT(5, int32_t);
+        else
+            XSB_DIRECT(6, int32_t);
+    }
+#undef XSB_DIRECT
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+    if (timer)
+        timer->end(stream, &StageTimes::fold);
 }
 
 // Stage 1: records sorted by column (stable), per-column record counts already in the workspace

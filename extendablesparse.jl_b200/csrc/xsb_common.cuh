@@ -141,6 +141,11 @@ __device__ __forceinline__ RecPair ld_pair_stream(const Rec *p)
                  : "l"(p));
     return r;
 }
+// 256-bit store; p must be 32-byte aligned
+__device__ __forceinline__ void st_v4_u64(void *p, u64 a, u64 b, u64 c, u64 d)
+{
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 __device__ __forceinline__ void st_rec(Rec *p, const Rec &r)
 {
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(r.key),

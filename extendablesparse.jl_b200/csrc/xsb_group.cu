@@ -394,7 +394,7 @@ GpLayout gp_layout(u64 nrec)
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const u64 nchunks = (nrec + GP_W - 1) / GP_W;
     GpLayout l{};
-    l.cap = (u32)std::min<u64>(nrec / 4 + 4096, 0xfffffff0ull); // pairs we make room for
+    l.cap = (u32)std::min<u64>(nrec / 8 * 3 + 4096, 0xfffffff0ull); // pairs we make room for (7-point FD streams: ~0.27 per record)
     const u64 ptiles = ((u64)l.cap + PS_TILE - 1) / PS_TILE;
     size_t o = 0;
     l.off_ticket = o;

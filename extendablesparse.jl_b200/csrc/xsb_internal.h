@@ -127,6 +127,11 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
                     u32 *d_overflow, bool lists_ready, u32 *d_maxd, u32 hint_maxd, LaunchCounter &lc, StageTimer *timer);
 // d_maxd receives the largest number of distinct rows a thread-folded column held (0: path not taken);
 // hint_maxd is that number from the handle's previous flush (0: unknown) and picks the first table size
+bool colfold_direct_supported(const KeyLayout &L, int combine, bool plain_adds);
+// one-pass fold of plain += streams straight into rowval / nzval / colptr; *d_redo != 0: run colfold_reduce instead
+void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout L, i64 ncols, int idx64, int base,
+                    void *rowval_out, double *nzval_out, void *colptr_out, void *workspace, u64 *d_nnz, u32 *d_redo,
+                    bool lists_ready, u32 *d_maxd, u32 hint_maxd, LaunchCounter &lc, StageTimer *timer);
 void colfold_lists(void *workspace, u64 nrec, i64 ncols, u32 **nzcol, u32 **nzstart, u64 **totals);
 
 // ---- xsb_group.cu

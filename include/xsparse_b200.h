@@ -99,7 +99,7 @@ typedef struct xsb_flush_stats
     float ms_group_scatter;   /* pair offsets + grouping pass 2: stable scatter by column */
     float ms_fold;            /* per-column fold of duplicates (entries parked)           */
     float ms_compact;         /* parked entries -> rowval / nzval                         */
-    float reserved_;
+    int32_t direct_fold;      /* 1: the fold wrote rowval / nzval / colptr in one pass (no park + compact) */
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */
