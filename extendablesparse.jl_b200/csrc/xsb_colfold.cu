@@ -821,7 +821,6 @@ colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxle
 // scan plus a decoupled look-back over the block totals (blocks are dispatched in index order).
 // A column that needs another table size or the warp kernel raises *d_redo; the caller then runs
 // the parking path (colthread_kernel + compact) instead.
-constexpr u64 DS_AGG = 1ull << 62, DS_INCL = 2ull << 62, DS_VALUE = (1ull << 62) - 1ull;
 
 template <int HBITS, typename Ti>
 __global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 5 : 2))
@@ -889,41 +888,7 @@ colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u3
     }
     if (warp == 0)
     {
-        u64 *mine = status + blockIdx.x;
-        u64 prefix = 0;
-        if (blockIdx.x == 0)
-        {
-            if (lane == 0)
-                st_relaxed_u64(mine, DS_INCL | (u64)btotal);
-        }
-        else
-        {
-            if (lane == 0)
-                st_relaxed_u64(mine, DS_AGG | (u64)btotal);
-            i64 b = (i64)blockIdx.x - 1;
-            for (;;)
-            { // lane l looks at block b - l
-                u64 v = DS_INCL;
-                if (b - lane >= 0)
-                {
-                    do
-                        v = ld_relaxed_u64(status + (b - lane));
-                    while ((v >> 62) == 0ull);
-                }
-                const u32 inc = __ballot_sync(full, (v >> 62) == 2ull);
-                const int first = inc ? __ffs(inc) - 1 : 31; // nearest block with an inclusive prefix, if in this window
-                u64 c = (lane <= first) ? (v & DS_VALUE) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    c += __shfl_xor_sync(full, c, o);
-                prefix += c;
-                if (inc)
-                    break;
-                b -= 32;
-            }
-            if (lane == 0)
-                st_relaxed_u64(mine, DS_INCL | (prefix + (u64)btotal));
-        }
+        const u64 prefix = warp_lookback(status, blockIdx.x, (u64)btotal, lane);
         if (lane == 0)
             s_prefix = prefix;
     }

@@ -153,4 +153,46 @@ __device__ __forceinline__ void st_rec(Rec *p, const Rec &r)
                  : "memory");
 }
 
+// Decoupled look-back over per-tile totals (tiles are dispatched in index order): the calling WARP
+// publishes `mine` for tile `index` and returns the sum of the totals of all tiles before it.
+// status[] starts zeroed; values must stay below 2^62.
+constexpr u64 LB_AGG = 1ull << 62, LB_INCL = 2ull << 62, LB_VALUE = (1ull << 62) - 1ull;
+__device__ __forceinline__ u64 warp_lookback(u64 *__restrict__ status, u32 index, u64 mine, int lane)
+{
+    constexpr u32 full = 0xffffffffu;
+    u64 prefix = 0;
+    if (index == 0)
+    {
+        if (lane == 0)
+            st_relaxed_u64(status, LB_INCL | mine);
+        return 0;
+    }
+    if (lane == 0)
+        st_relaxed_u64(status + index, LB_AGG | mine);
+    long long b = (long long)index - 1;
+    for (;;)
+    { // lane l looks at tile b - l
+        u64 v = LB_INCL;
+        if (b - lane >= 0)
+        {
+            do
+                v = ld_relaxed_u64(status + (b - lane));
+            while ((v >> 62) == 0ull);
+        }
+        const u32 inc = __ballot_sync(full, (v >> 62) == 2ull);
+        const int first = inc ? __ffs(inc) - 1 : 31; // nearest tile with an inclusive prefix, if in this window
+        u64 c = (lane <= first) ? (v & LB_VALUE) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            c += __shfl_xor_sync(full, c, o);
+        prefix += c;
+        if (inc)
+            break;
+        b -= 32;
+    }
+    if (lane == 0)
+        st_relaxed_u64(status + index, LB_INCL | (prefix + mine));
+    return prefix;
+}
+
 } // namespace xsb

@@ -47,7 +47,7 @@ struct CountSpace
 // pass 1: distinct columns of every chunk and their record counts
 // ------------------------------------------------------------------------
 __global__ void __launch_bounds__(GP_WARPS * 32, 5)
-group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks, int chunkbits,
+group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks,
                    u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
                    uint2 *__restrict__ chunkinfo, u32 cap, u32 *__restrict__ d_flags)
 {
@@ -144,7 +144,8 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
     }
     __syncwarp();
 
-    // ---- room for this chunk's pairs
+    // ---- room for this chunk's pairs (atomic ticket: chunks land in completion order; the pair list
+    // is brought into chunk = stream order by pair_order_kernel before the sort)
     u32 base = 0;
     if (lane == 0)
         base = atomicAdd(pair_total, d);
@@ -164,10 +165,106 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
         const u32 col = ws.key[slot];
         chunkcols[base + j] = col;
         Rec pr;
-        pr.key = ((u64)col << chunkbits) | (u64)chunk;
+        pr.key = (u64)col;
         const u64 payload = ((u64)(base + j) << 16) | (u64)ws.cnt[slot];
         pr.val = __longlong_as_double((long long)payload);
         st_rec(pairs + base + j, pr);
+    }
+}
+
+// ------------------------------------------------------------------------
+// pair list into chunk order: exclusive scan of the chunks' pair counts, then a copy
+// ------------------------------------------------------------------------
+constexpr int PO_THREADS = 256; // chunks per block
+
+__global__ void __launch_bounds__(PO_THREADS)
+pair_order_tilesum_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, u32 *__restrict__ tsum)
+{
+    __shared__ u32 s_w[PO_THREADS / 32];
+    const u32 c = blockIdx.x * PO_THREADS + threadIdx.x;
+    u32 v = c < nchunks ? chunkinfo[c].y : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0)
+        s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        u32 t = 0;
+        for (int w = 0; w < PO_THREADS / 32; ++w)
+            t += s_w[w];
+        tsum[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of the tile sums in place
+__global__ void __launch_bounds__(1024) pair_order_scan_kernel(u32 *__restrict__ tsum, u32 nt)
+{
+    __shared__ u32 s_w[32];
+    __shared__ u32 s_carry;
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 b0 = 0; b0 < nt; b0 += 1024)
+    {
+        const u32 j = b0 + threadIdx.x;
+        const u32 x = j < nt ? tsum[j] : 0u;
+        u32 v = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o)
+                v += t;
+        }
+        if (lane == 31)
+            s_w[warp] = v;
+        __syncthreads();
+        u32 pre = s_carry;
+        for (int w = 0; w < warp; ++w)
+            pre += s_w[w];
+        if (j < nt)
+            tsum[j] = pre + v - x;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            s_carry = pre + v;
+        __syncthreads();
+    }
+}
+
+// block = 256 chunks: in-block scan of the pair counts, then every warp copies the pairs of its 32
+// chunks from their ticket position to their position in chunk order
+__global__ void __launch_bounds__(PO_THREADS)
+pair_order_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, const u32 *__restrict__ tsum,
+                  const Rec *__restrict__ pairs_in, Rec *__restrict__ pairs_out)
+{
+    __shared__ u32 s_w[PO_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 c = blockIdx.x * PO_THREADS + threadIdx.x;
+    const uint2 info = c < nchunks ? chunkinfo[c] : make_uint2(0u, 0u);
+    u32 incl = info.y;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_w[warp] = incl;
+    __syncthreads();
+    u32 dst = tsum[blockIdx.x] + incl - info.y;
+    for (int w = 0; w < warp; ++w)
+        dst += s_w[w];
+    for (int q = 0; q < 32; ++q)
+    { // chunk of lane q, all lanes copy
+        const u32 src = __shfl_sync(0xffffffffu, info.x, q);
+        const u32 cnt = __shfl_sync(0xffffffffu, info.y, q);
+        const u32 to = __shfl_sync(0xffffffffu, dst, q);
+        for (u32 j = lane; j < cnt; j += 32)
+            pairs_out[to + j] = pairs_in[src + j];
     }
 }
 
@@ -386,7 +483,7 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
 namespace {
 struct GpLayout
 {
-    size_t off_ticket, off_chunkinfo, off_chunkcols, off_offs, off_trec, off_tnz, bytes;
+    size_t off_ticket, off_chunkinfo, off_chunkcols, off_offs, off_trec, off_tnz, off_status, bytes;
     u32 cap;
 };
 GpLayout gp_layout(u64 nrec)
@@ -409,6 +506,8 @@ GpLayout gp_layout(u64 nrec)
     o = up(o + sizeof(u64) * (ptiles + 1));
     l.off_tnz = o;
     o = up(o + sizeof(u32) * (ptiles + 1));
+    l.off_status = o; // tile sums of the chunks' pair counts (pair_order kernels)
+    o = up(o + sizeof(u32) * (nchunks / 256 + 2));
     l.bytes = o;
     return l;
 }
@@ -460,12 +559,10 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     if (timer)
         timer->begin(stream);
     XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair_total, flags
-    int chunkbits = 1;
-    while ((1ull << chunkbits) < (u64)nchunks)
-        ++chunkbits;
+    const int chunkbits = 0; // pair keys hold the column only
     const unsigned cblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;
     group_count_kernel<<<cblocks, GP_WARPS * 32, sizeof(CountSpace) * GP_WARPS, stream>>>(
-        in, nrec, colshift, colmask, nchunks, chunkbits, pair_total, pairs_a, chunkcols, chunkinfo, l.cap, flags);
+        in, nrec, colshift, colmask, nchunks, pair_total, pairs_b, chunkcols, chunkinfo, l.cap, flags);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     // pairs made, too-many flag
@@ -480,8 +577,21 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     if (toomany || npairs > l.cap || npairs == 0)
         return false;
 
-    // ---- pairs sorted by column (stable: chunk order inside a column)
-    const SortPlan plan = make_sort_plan(0, L.colbits + chunkbits);
+    // ---- pairs into chunk order, then sorted by column (stable: chunk order inside a column)
+    if (timer)
+        timer->begin(stream);
+    {
+        u32 *otsum = reinterpret_cast<u32 *>(ws + l.off_status);
+        const unsigned oblocks = (nchunks + PO_THREADS - 1) / PO_THREADS;
+        pair_order_tilesum_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, otsum);
+        pair_order_scan_kernel<<<1, 1024, 0, stream>>>(otsum, oblocks);
+        pair_order_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, otsum, pairs_b, pairs_a);
+        lc.add(3);
+        XSB_CUDA(cudaGetLastError());
+    }
+    if (timer)
+        timer->end(stream, &StageTimes::sort);
+    const SortPlan plan = make_sort_plan(0, L.colbits);
     *pair_passes = plan.npasses;
     Rec *sp = radix_sort_records(stream, pairs_a, pairs_b, npairs, plan, sort_workspace, lc, timer);
 
