@@ -65,6 +65,9 @@ class FlushStats(C.Structure):
         ("ms_fold", C.c_float),
         ("ms_compact", C.c_float),
         ("direct_fold", C.c_int32),
+        ("preagg_records", C.c_int64),
+        ("ms_preagg", C.c_float),
+        ("reserved_", C.c_float),
     ]
 
     def as_dict(self):
@@ -122,6 +125,7 @@ SIGNATURES = {
     "xsb_set_profiling": (_i32, [_p, _i32]),
     "xsb_set_strategy": (_i32, [_p, _i32]),
     "xsb_set_grouping": (_i32, [_p, _i32]),
+    "xsb_set_preaggregation": (_i32, [_p, _i32]),
     "xsb_get_flush_stats": (_i32, [_p, C.POINTER(FlushStats)]),
     "xsb_kernel_launches": (_i32, [_p, C.POINTER(_i64)]),
 }
@@ -386,6 +390,9 @@ class Handle:
         """GROUPING_AUTO (two-pass grouping by column when the stream has column locality), GROUPING_OFF
         (always the radix sort) or GROUPING_ON (always try)."""
         self._c(lib().xsb_set_grouping(self._h, int(grouping)))
+
+    def set_preaggregation(self, on=True):
+        self._c(lib().xsb_set_preaggregation(self._h, 1 if on else 0))
 
     def set_strategy(self, strategy):
         """STRATEGY_AUTO (column sort + in-tile row ordering) or STRATEGY_FULLSORT ((col,row) sort)."""

@@ -4,6 +4,7 @@
 #include "xsb_internal.h"
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -222,6 +223,9 @@ struct xsb_matrix
     bool last_column_path = false;
     bool no_direct_fold = false; // the one-pass fold met columns it cannot take: park + compact instead
     int stats_direct = 0;
+    i64 stats_preagg = 0;
+    bool preagg = false;   // xsb_set_preaggregation
+    int preagg_misses = 0; // consecutive XSB_FAST flushes whose windows held few duplicates
     u32 fold_hint = 0; // most distinct rows a column held in the previous thread-per-column fold
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
@@ -263,6 +267,13 @@ struct xsb_matrix
 };
 
 namespace {
+
+// XSB_PREAGG=1 turns window pre-aggregation on for every handle's XSB_FAST flushes (A-B measurements);
+// the regular switch is xsb_set_preaggregation
+const bool g_preagg = []() {
+    const char *e = getenv("XSB_PREAGG");
+    return e && *e == '1';
+}();
 
 void set_err(xsb_matrix *h, const std::string &s)
 {
@@ -419,9 +430,11 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     }
 
     const i64 nnz_old = h->nnz;
-    const i64 total = nnz_old + n_ins;
+    i64 total = nnz_old + n_ins; // records the flush works on (shrinks if XSB_FAST pre-aggregates)
+    const i64 total_cap = total;
     h->stats_pairs = 0;
     h->stats_direct = 0;
+    h->stats_preagg = 0;
     REQUIRE((u64)total < (1ull << 40), XSB_EINVAL, "too many staged entries");
 
     // ---- input buffer A = [old CSC as records | staged records in tid order]
@@ -456,6 +469,38 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         tp->end(s, &StageTimes::expand);
 
     Rec *B = static_cast<Rec *>(h->dalloc(sizeof(Rec) * (size_t)total));
+    struct
+    {
+        Rec *p;
+        i64 cap;
+    } bufs[2] = {{A, a_is_stage0 ? h->stage[0].cap : total_cap}, {B, total_cap}};
+    auto cap_of = [&](const Rec *p) { return p == bufs[0].p ? bufs[0].cap : bufs[1].cap; };
+
+    // ---- XSB_FAST: accumulate-on-insert inside windows of the staged stream (xsb_preagg.cu); the
+    // partial sums replace the staged records, the old entries ride in front of them as before
+    bool preagged = false;
+    if (mode == XSB_FAST && !h->has_assign && combine == XSB_COMBINE_SEED && (h->preagg || g_preagg) && h->preagg_misses < 2 &&
+        n_ins >= 4096)
+    {
+        if (tp)
+            tp->begin(s);
+        XSB_CUDA(cudaMemsetAsync(h->d_scal + 3, 0, sizeof(u64), s));
+        if (nnz_old)
+            XSB_CUDA(cudaMemcpyAsync(B, A, sizeof(Rec) * (size_t)nnz_old, cudaMemcpyDeviceToDevice, s));
+        preaggregate_records(s, A + nnz_old, (u64)n_ins, h->L, B + nnz_old, h->d_scal + 3, h->lc);
+        if (tp)
+            tp->end(s, &StageTimes::preagg);
+        const i64 kept = (i64)read_scalar(h, 3);
+        h->stats_preagg = kept;
+        // a stream that hardly repeats itself inside a window gains nothing: stop trying on this handle
+        h->preagg_misses = (kept * 4 > n_ins * 3) ? h->preagg_misses + 1 : 0;
+        total = nnz_old + kept;
+        std::swap(A, B);
+        preagged = true;
+    }
+    KeyLayout Lf = h->L; // layout the fold sees: partial sums are not tied to a partition
+    if (preagged)
+        Lf.tidbits = 0;
     const size_t ws_bytes = std::max(std::max(sort_workspace_bytes((u64)total), reduce_workspace_bytes((u64)total, h->n)),
                                      column_workspace_bytes((u64)total, h->n));
     void *ws = h->dalloc(ws_bytes);
@@ -508,11 +553,11 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             spare = (sorted == A) ? B : A;
         }
         bool direct = false, lists_ready = grouped;
-        if (!h->no_direct_fold && colfold_direct_supported(h->L, combine, !h->has_assign))
+        if (!h->no_direct_fold && colfold_direct_supported(Lf, combine, !h->has_assign))
         { // one pass: fold every column and write rowval / nzval / colptr in place (the spare buffer)
             new_rowval = spare;
             new_nzval = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spare) + 8 * (size_t)total);
-            colfold_direct(s, sorted, (u64)total, h->L, h->n, h->idx64, h->base, new_rowval, new_nzval, new_colptr, cws,
+            colfold_direct(s, sorted, (u64)total, Lf, h->n, h->idx64, h->base, new_rowval, new_nzval, new_colptr, cws,
                            h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), grouped,
                            reinterpret_cast<u32 *>(h->d_scal + 7), h->fold_hint, h->lc, tp);
             XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -534,7 +579,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         }
         if (!direct)
         {
-            colfold_reduce(s, sorted, (u64)total, h->L, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
+            colfold_reduce(s, sorted, (u64)total, Lf, combine, !h->has_assign, h->n, h->idx64, h->base, spare,
                            new_colptr, cws, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), lists_ready,
                            reinterpret_cast<u32 *>(h->d_scal + 7), h->fold_hint, h->lc, tp);
             path = grouped ? 3 : 2;
@@ -631,7 +676,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     if (a_is_stage0)
     {
         h->stage[0].buf = sorted;
-        h->stage[0].cap = total;
+        h->stage[0].cap = cap_of(sorted);
     }
     else
         h->dfree(sorted);
@@ -651,6 +696,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.ms_host_alloc = h->alloc_ms;
     h->stats.group_pairs = h->stats_pairs;
     h->stats.direct_fold = h->stats_direct;
+    h->stats.preagg_records = h->stats_preagg;
     if (tp)
     {
         XSB_CUDA(cudaEventRecord(e1, s));
@@ -670,6 +716,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         h->stats.ms_group_scatter = t.gscatter;
         h->stats.ms_fold = t.fold;
         h->stats.ms_compact = t.compact;
+        h->stats.ms_preagg = t.preagg;
         h->stats.ms_colptr = t.colptr;
         h->stats.ms_other = t.other;
     }
@@ -1424,6 +1471,15 @@ int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping)
         return XSB_EINVAL;
     h->grouping = grouping;
     h->grouping_misses = 0;
+    return XSB_OK;
+}
+
+int32_t xsb_set_preaggregation(xsb_matrix *h, int32_t enable)
+{
+    if (!h)
+        return XSB_EINVAL;
+    h->preagg = enable != 0;
+    h->preagg_misses = 0;
     return XSB_OK;
 }
 

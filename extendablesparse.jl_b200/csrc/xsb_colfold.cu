@@ -1266,7 +1266,7 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     if (timer)
         timer->begin(stream);
     const u64 avg = nrec / std::max<u64>(1, kmax);
-    int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : 1);
+    int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : (avg < 40 ? 1 : 2));
     if (g_thread_hbits >= 4 && g_thread_hbits <= 6)
         level = g_thread_hbits - 4;
     const u32 maxlen = (u32)std::max<u64>(256, 6 * avg);
@@ -1355,7 +1355,7 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         const u64 avg = nrec / std::max<u64>(1, kmax);
         // table size to start with: what the previous flush of this handle needed, else the mean
         // column length (a column cannot hold more distinct rows than records)
-        int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : 1);
+        int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : (avg < 40 ? 1 : 2));
         if (g_thread_hbits >= 4 && g_thread_hbits <= 6)
             level = g_thread_hbits - 4;
         CtArgs a{sorted, L.low, L.rowbits, (u32)std::max<u64>(256, 6 * avg), nzcol, nzstart, totals, tmp, cnt,

@@ -31,7 +31,7 @@ struct LaunchCounter
 struct StageTimes
 {
     float expand = 0, histogram = 0, sort = 0, reduce = 0, colptr = 0, other = 0, total = 0;
-    float gcount = 0, gscatter = 0, fold = 0, compact = 0; // two-pass grouping and per-column fold, in detail
+    float gcount = 0, gscatter = 0, fold = 0, compact = 0, preagg = 0; // two-pass grouping and per-column fold, in detail
 };
 
 // Optional CUDA-event bracket around pipeline stages (profiling mode only).
@@ -145,6 +145,11 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
 void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, int idx64, int base,
                      const void *colptr, void *rowval_out, double *nzval_out, void *workspace, LaunchCounter &lc,
                      StageTimer *timer);
+
+// ---- xsb_preagg.cu
+// XSB_FAST: in[0, nrec) -> out[0, *d_count): partial sums of windows of the stream; d_count zeroed by the caller
+void preaggregate_records(cudaStream_t stream, const Rec *in, u64 nrec, const KeyLayout &L, Rec *out, u64 *d_count,
+                          LaunchCounter &lc);
 
 // ---- xsb_insert.cu
 // (I,J,V) -> records; *d_err receives the smallest offending index (or ~0)

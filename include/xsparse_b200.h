@@ -100,6 +100,9 @@ typedef struct xsb_flush_stats
     float ms_fold;            /* per-column fold of duplicates (entries parked)           */
     float ms_compact;         /* parked entries -> rowval / nzval                         */
     int32_t direct_fold;      /* 1: the fold wrote rowval / nzval / colptr in one pass (no park + compact) */
+    int64_t preagg_records;   /* XSB_FAST: staged records left after accumulate-on-insert in windows; 0: not used */
+    float ms_preagg;          /* ... and its device time (also inside ms_total)                */
+    float reserved_;
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */
@@ -272,6 +275,12 @@ int32_t xsb_set_strategy(xsb_matrix *h, int32_t strategy);
 #define XSB_GROUPING_OFF 1
 #define XSB_GROUPING_ON 2
 int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping);
+/* XSB_FAST flushes only (ignored otherwise, and when A[i,j]=v records are staged): fold the staged
+ * stream inside windows of 512 insertions first -- the reference's accumulate-on-insert
+ * (src/matrix/sparsematrixlnk.jl:210-253) -- so that fewer records are grouped.  Pattern unchanged,
+ * values <= 1e-14 relative, summation order not reproducible from run to run.  Off by default:
+ * on B200 it only pays when the windows shrink the stream more than about 3x. */
+int32_t xsb_set_preaggregation(xsb_matrix *h, int32_t enable);
 int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
 /* Total kernels launched by this handle since creation. */
 int32_t xsb_kernel_launches(const xsb_matrix *h, int64_t *count);

@@ -1,0 +1,160 @@
+"""Full-size GPU checks of BASELINE.json's single-GPU configurations through size-independent
+properties (the CPU oracle needs minutes at these sizes and /root/reference does not exist on the
+GPU box):
+  * two independent implementations of flush! -- grouping by column + thread-per-column fold
+    (STRATEGY_AUTO) and the (col,row) radix sort + flat segmented fold (STRATEGY_FULLSORT) -- must
+    agree bit for bit on colptr, rowval and nzval;
+  * closed-form nnz of the stencil, strictly increasing rows per column, structural symmetry;
+  * XSB_FAST (plain and with window pre-aggregation) keeps the pattern and stays within 1e-14;
+  * the frozen-pattern re-assembly (Newton loop of configs[2]) reproduces a full flush! bit for bit.
+All comparisons run on the device (torch); nothing here reads the oracle.
+"""
+import ctypes as C
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xsb():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import xsparse_b200
+
+    assert xsparse_b200.capi.device_count() > 0
+    return xsparse_b200
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def device_csc(torch, h):
+    nnz = h.nnz
+    cp = torch.empty(h.n + 1, dtype=torch.int64, device="cuda")
+    rv = torch.empty(nnz, dtype=torch.int64, device="cuda")
+    nz = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    h.fetch_csc(cp, rv, nz)
+    h.synchronize()
+    return cp, rv, nz
+
+
+def check_structure(torch, cp, rv, n, nnz):
+    assert int(cp[0]) == 1 and int(cp[-1]) == nnz + 1
+    cols = torch.repeat_interleave(torch.arange(1, n + 1, device="cuda"), cp[1:] - cp[:-1])
+    same_col = cols[1:] == cols[:-1]
+    assert bool(torch.all((rv[1:] > rv[:-1]) | ~same_col)), "rows not strictly increasing inside a column"
+    # structural symmetry: the multiset of (i,j) equals the multiset of (j,i)
+    a = torch.sort(rv * (n + 1) + cols).values
+    b = torch.sort(cols * (n + 1) + rv).values
+    assert torch.equal(a, b), "pattern not structurally symmetric"
+    return cols
+
+
+def assemble(xsb, n, emit, strategy=None, mode=None, preagg=False):
+    h = xsb.Handle(n, n)
+    if strategy is not None:
+        h.set_strategy(strategy)
+    if preagg:
+        h.set_preaggregation(True)
+    emit(h)
+    n_ins = h.pending
+    nnz, changed = h.flush(xsb.DETERMINISTIC if mode is None else mode)
+    assert changed
+    return h, n_ins, nnz
+
+
+CASES = {
+    # name: (unknowns, emitter, inserted, nnz)
+    "cfg2_fem128": (128 ** 3, lambda x: (lambda h: h.emit_p1fem(128, 128, 128, flavour=x.RAW)), 245805960, 31065598),
+    "cfg3_fd200": (200 ** 3, lambda x: (lambda h: h.emit_fdrand(200, 200, 200, seed=5)), 95760000, 55760000),
+    "cfg4_rd96": (4 * 96 ** 3, lambda x: (lambda h: h.emit_blockrd(96, 96, 96, 4, seed=5)), 182255616, 98205696),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_two_flush_implementations_agree_bitwise(xsb, torch, case):
+    n, mk, n_ins_ref, nnz_ref = CASES[case]
+    emit = mk(xsb)
+    h, n_ins, nnz = assemble(xsb, n, emit)
+    st = h.flush_stats()
+    assert (n_ins, nnz) == (n_ins_ref, nnz_ref)
+    assert st["column_path"] == 3  # the product path of the bench: grouping by column + thread-per-column fold
+    cp, rv, nz = device_csc(torch, h)
+    h.close()
+    check_structure(torch, cp, rv, n, nnz)
+    g, _, nnz2 = assemble(xsb, n, emit, strategy=xsb.capi.STRATEGY_FULLSORT)
+    assert g.flush_stats()["column_path"] == 0 and nnz2 == nnz
+    cp2, rv2, nz2 = device_csc(torch, g)
+    g.close()
+    assert torch.equal(cp, cp2) and torch.equal(rv, rv2)
+    assert torch.equal(nz.view(torch.int64), nz2.view(torch.int64)), "nzval differs between the two flush paths"
+
+
+@pytest.mark.parametrize("preagg", [False, True])
+def test_fast_mode_full_size_fem(xsb, torch, preagg):
+    n, mk, _, nnz_ref = CASES["cfg2_fem128"]
+    emit = mk(xsb)
+    h, _, nnz = assemble(xsb, n, emit)
+    cp, rv, nz = device_csc(torch, h)
+    h.close()
+    g, n_ins, nnz2 = assemble(xsb, n, emit, mode=xsb.FAST, preagg=preagg)
+    st = g.flush_stats()
+    assert nnz2 == nnz == nnz_ref
+    if preagg:
+        assert 0 < st["preagg_records"] < n_ins // 2
+    cp2, rv2, nz2 = device_csc(torch, g)
+    g.close()
+    assert torch.equal(cp, cp2) and torch.equal(rv, rv2)
+    tol = 1e-14 * float(nz.abs().max())
+    assert float((nz - nz2).abs().max()) <= tol
+
+
+def test_newton_loop_fd200_values_only(xsb, torch):
+    """configs[2]: fdrand 200^3 built once, then values-only re-assemblies into the frozen pattern;
+    every re-assembly must equal a fresh insert + flush! of the same stream bit for bit."""
+    nx = 200
+    n = nx ** 3
+    c = xsb.capi
+
+    def staged(seed):
+        g = xsb.Handle(n, n)
+        g.emit_fdrand(nx, nx, nx, seed=seed)
+        cnt = g.pending
+        dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
+        dJ = torch.empty(cnt, dtype=torch.int64, device="cuda")
+        dV = torch.empty(cnt, dtype=torch.float64, device="cuda")
+        got = C.c_int64(0)
+        c.check(c.lib().xsb_debug_fetch_staged(g._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt,
+                                               C.byref(got)), g._h)
+        g.synchronize()
+        return g, dI, dJ, dV
+
+    g0, dI, dJ, dV = staged(100)
+    g0.close()
+    h = xsb.Handle(n, n)
+    h.insert_batch(dI, dJ, dV, xsb.UPDATE, count=len(dV))
+    nnz, _ = h.flush()
+    assert nnz == 7 * n - 6 * nx * nx
+    h.freeze_pattern(dI, dJ, count=len(dI))
+    for seed in (101, 102, 103):
+        g, _, _, dVn = staged(seed)
+        g.flush()
+        _, _, ref = device_csc(torch, g)
+        g.close()
+        h.zero_values()
+        h.reassemble_values(dVn, xsb.DETERMINISTIC, count=len(dVn))
+        _, _, nz = device_csc(torch, h)
+        assert torch.equal(nz.view(torch.int64), ref.view(torch.int64)), f"re-assembly {seed} not bit-exact"
+        h.zero_values()
+        h.reassemble_values(dVn, xsb.FAST, count=len(dVn))
+        _, _, nzf = device_csc(torch, h)
+        assert float((nzf - ref).abs().max()) <= 1e-14 * float(ref.abs().max())
+        del dVn, ref, nz, nzf
+    h.close()

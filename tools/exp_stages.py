@@ -44,10 +44,11 @@ def run(name, reps=4, mode=None):
         if best is None or st["ms_total"] < best["ms_total"]:
             best = st
     rec = best["n_inserted"]
-    keys = ["ms_emit", "ms_total", "ms_group_count", "ms_pair_sort", "ms_group_scatter", "ms_fold", "ms_compact",
+    keys = ["ms_emit", "ms_total", "ms_preagg", "ms_group_count", "ms_pair_sort", "ms_group_scatter", "ms_fold", "ms_compact",
             "ms_colptr", "ms_histogram", "ms_sort", "ms_reduce", "ms_other"]
     print(f"{name}: n_ins={rec} nnz={best['nnz_new']} path={best['column_path']} pairs={best['group_pairs']} "
-          f"passes={best['sort_passes']} launches={best['kernel_launches']} direct={best['direct_fold']}")
+          f"passes={best['sort_passes']} launches={best['kernel_launches']} direct={best['direct_fold']} "
+          f"preagg={best['preagg_records']}")
     print("   " + "  ".join(f"{k[3:]}={best[k]:.3f}" for k in keys))
     gbs = lambda b, ms: b / ms / 1e6 if ms > 0 else 0
     print(f"   GB/s: count={gbs(16 * rec, best['ms_group_count']):.0f} scatter={gbs(32 * rec, best['ms_group_scatter']):.0f} "
