@@ -76,14 +76,8 @@ def run(args, xsb, rank, world, local):
     ms_step = ms / args.steps
     value = world * n_ins_rank / (ms_step / 1e3)
     peak, peak_src = bench.peaks()
-    passes = st["sort_passes"]
-    ms_pass = stage["ms_sort"] / args.steps / max(passes, 1)
-    rec = st["n_inserted"] + st["nnz_old"]
-    pass_bytes = 32 * rec
-    achieved = pass_bytes / (ms_pass / 1e3) / 1e9
-    b_flush = bench.flush_bytes(st["n_inserted"], st["nnz_old"], st["nnz_new"], h.n)
-    ms_flush = stage["ms_total"] / args.steps
-    flush_gbs = b_flush / (ms_flush / 1e3) / 1e9
+    roof = bench.roofline(st, {k: v / args.steps for k, v in stage.items()}, h.n, peak, peak_src, args.traffic)
+    roof["kernel"] += " [rank 0]"
 
     e2e = measure_e2e(args, xsb, xd, rank, world, local, mode)
     clocks = clk.summary()
@@ -98,13 +92,7 @@ def run(args, xsb, rank, world, local):
             "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass over 16-B records), rank 0",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic,
-                         "peak_source": peak_src, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
-                         "launches_per_step": passes,
-                         "flush": {"algorithmic_bytes": b_flush, "ms": ms_flush, "achieved": flush_gbs,
-                                   "frac": flush_gbs / peak},
-                         "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stage.items())}},
+            "roofline": roof,
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clocks,
             "nnz_global": int(D.nnz_global), "n_inserted": int(world * n_ins_rank),
         }

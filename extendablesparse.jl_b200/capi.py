@@ -84,7 +84,8 @@ SIGNATURES = {
     "xsb_create_slab": (_i32, [_i64, _i64, _i32, _i32, C.POINTER(_i64), _i32, _i32, _i32, _i32, C.POINTER(_p)]),
     "xsb_slab_info": (_i32, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "xsb_route_prepare": (_i32, [_p, _p, _i64, C.POINTER(_i64)]),
-    "xsb_route_finish": (_i32, [_p, _p, _i64]),
+    "xsb_route_count": (_i32, [_p, C.POINTER(_i64)]),
+    "xsb_route_finish": (_i32, [_p, _i32, _p, _i64]),
     "xsb_destroy": (_i32, [_p]),
     "xsb_last_error": (C.c_char_p, [_p]),
     "xsb_reset": (_i32, [_p]),
@@ -248,14 +249,20 @@ class Handle:
     def set_csc(self, colptr, rowval, nzval):
         self._c(lib().xsb_set_csc(self._h, ptr(colptr), ptr(rowval), ptr(nzval)))
 
+    def route_count(self):
+        """Staged records per owning rank (own rank: the ones that stay)."""
+        counts = (_i64 * max(self.n_ranks, 1))()
+        self._c(lib().xsb_route_count(self._h, counts))
+        return [int(c) for c in counts]
+
     def route_prepare(self, send_records, capacity):
-        """Bucket the staged records by owner into `send_records` (device int64 tensor, 2 words per record)."""
-        counts = (_i64 * self.n_ranks)()
+        """Copies the records other ranks own into send_records (dest after dest); returns counts."""
+        counts = (_i64 * max(self.n_ranks, 1))()
         self._c(lib().xsb_route_prepare(self._h, ptr(send_records), capacity, counts))
         return [int(c) for c in counts]
 
-    def route_finish(self, recv_records, count):
-        self._c(lib().xsb_route_finish(self._h, ptr(recv_records), count))
+    def route_finish(self, src_rank, recv_records, count):
+        self._c(lib().xsb_route_finish(self._h, int(src_rank), ptr(recv_records), count))
 
     def shrink_to_fit(self):
         self._c(lib().xsb_shrink_to_fit(self._h))

@@ -62,7 +62,15 @@ struct xsb_matrix
     KeyLayout Ls{}; // layout of staged records before routing (global columns + owner bits); == L without ranks
     i64 n_global = 0, col_begin = 0; // slab handles own columns [col_begin, col_begin + n) of an m x n_global matrix
     int nranks = 0, rank = 0;        // nranks == 0: plain single-GPU handle
-    bool routed = false;             // staged records already went through xsb_route_finish
+    bool routed = false;             // staged records already went through xsb_route_prepare / xsb_route_finish
+    i64 foreign = 0;                 // staged records owned by other ranks (sent; the flush skips them)
+    void *route_ws = nullptr;        // tile counts between xsb_route_count and xsb_route_prepare
+    u64 route_counts[kMaxRanks] = {0};
+    i64 route_counted = -1;          // staged count route_counts was taken at
+    // regions of the staged records of a slab handle after routing (offsets from stage.front, chunk aligned):
+    // own [0, own_end), received from lower ranks [own_end, low_end), from higher ranks [low_end, count)
+    i64 own_end = 0, low_end = -1, n_low = 0, n_high = 0, n_pad = 0;
+    int last_src = -1;
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -176,6 +184,11 @@ struct xsb_matrix
         return s;
     }
     CscView view() const { return CscView{colptr, rowval, nzval, nnz}; }
+    static i64 chunk_up(i64 x)
+    {
+        const i64 w = group_chunk_records();
+        return (x + w - 1) / w * w;
+    }
     void drop_frozen()
     {
         dfree(f_slot);
@@ -194,6 +207,12 @@ struct xsb_matrix
             st.count = 0;
             st.front = 0;
             routed = false;
+            foreign = 0;
+            route_counted = -1;
+            own_end = 0;
+            low_end = -1;
+            n_low = n_high = n_pad = 0;
+            last_src = -1;
             if (release)
             {
                 dfree(st.buf);
@@ -251,6 +270,8 @@ struct xsb_matrix
         Stage &st = stage[t];
         if (st.count == 0)
             st.front = (n_tid == 1) ? nnz : 0;
+            if (L.ownerbits > 0) // slab handles: every region of the buffer is a whole number of chunks
+                st.front = chunk_up(st.front);
         const i64 need = st.front + st.count + extra;
         if (need <= st.cap)
             return;
@@ -430,7 +451,9 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     }
 
     const i64 nnz_old = h->nnz;
-    i64 total = nnz_old + n_ins; // records the flush works on (shrinks if XSB_FAST pre-aggregates)
+    // slab handles keep every region of the buffer chunk aligned: a gap of skipped records follows the old entries
+    const i64 front = (h->L.ownerbits > 0 && h->n_tid == 1) ? xsb_matrix::chunk_up(nnz_old) : nnz_old;
+    i64 total = front + n_ins; // records the flush works on (shrinks if XSB_FAST pre-aggregates)
     const i64 total_cap = total;
     h->stats_pairs = 0;
     h->stats_direct = 0;
@@ -445,7 +468,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     if (h->n_tid == 1)
     {
         A = h->stage[0].buf; // front was reserved when staging began
-        REQUIRE(h->stage[0].front == nnz_old && h->stage[0].cap >= total, XSB_ESTATE, "staging buffer out of step");
+        REQUIRE(h->stage[0].front == front && h->stage[0].cap >= total, XSB_ESTATE, "staging buffer out of step");
         a_is_stage0 = true;
     }
     else
@@ -465,6 +488,8 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     if (tp)
         tp->begin(s);
     expand_csc_records(s, h->view(), h->n, h->idx64, h->base, h->L, A, h->lc);
+    if (front > nnz_old)
+        route_fill_skipped(s, A + nnz_old, front - nnz_old, h->L, h->lc);
     if (tp)
         tp->end(s, &StageTimes::expand);
 
@@ -487,7 +512,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         XSB_CUDA(cudaMemsetAsync(h->d_scal + 3, 0, sizeof(u64), s));
         if (nnz_old)
             XSB_CUDA(cudaMemcpyAsync(B, A, sizeof(Rec) * (size_t)nnz_old, cudaMemcpyDeviceToDevice, s));
-        preaggregate_records(s, A + nnz_old, (u64)n_ins, h->L, B + nnz_old, h->d_scal + 3, h->lc);
+        preaggregate_records(s, A + front, (u64)n_ins, h->L, B + nnz_old, h->d_scal + 3, h->lc);
         if (tp)
             tp->end(s, &StageTimes::preagg);
         const i64 kept = (i64)read_scalar(h, 3);
@@ -504,6 +529,54 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     const size_t ws_bytes = std::max(std::max(sort_workspace_bytes((u64)total), reduce_workspace_bytes((u64)total, h->n)),
                                      column_workspace_bytes((u64)total, h->n));
     void *ws = h->dalloc(ws_bytes);
+    // slab handles: records owned (and already received) by other ranks are still in the buffer.  The
+    // grouping kernels skip them by their owner bits; every other path first drops them with one
+    // stable partition on the owner bits.
+    const i64 foreign = h->foreign + h->n_pad;
+    const i64 n_low = h->n_low, n_high = h->n_high;
+    bool tomb = h->L.ownerbits > 0 && (foreign > 0 || front > nnz_old);
+    // the fold must meet the records of a column as [old | lower ranks | own | higher ranks]
+    ChunkOrder ord{};
+    const ChunkOrder *pord = nullptr;
+    if (h->L.ownerbits > 0 && !preagged && n_low > 0)
+    {
+        const i64 W = group_chunk_records();
+        const i64 low_end = h->low_end < 0 ? h->stage[0].count : h->low_end;
+        ord.c_old = (u32)(front / W);
+        ord.c_own = (u32)((front + h->own_end) / W);
+        ord.c_low = (u32)((front + low_end + W - 1) / W);
+        pord = &ord;
+    }
+    auto drop_foreign = [&]() {
+        if (!tomb)
+            return;
+        u64 counts[kRadix] = {0};
+        partition_records(s, A, B, (u64)total, h->L.ownershift(), h->L.ownerbits, ws, h->lc, counts);
+        u64 off = 0;
+        for (int r = 0; r < h->rank; ++r)
+            off += counts[r];
+        const i64 mine = (i64)counts[h->rank];
+        const Rec *src = B + off;
+        if (preagged || n_low == 0)
+        {
+            if (mine > 0)
+                XSB_CUDA(cudaMemcpyAsync(A, src, sizeof(Rec) * (size_t)mine, cudaMemcpyDeviceToDevice, s));
+        }
+        else
+        { // [old | own | low | high] -> [old | low | own | high]
+            const i64 own = mine - nnz_old - n_low - n_high;
+            auto cp = [&](i64 dst, i64 from, i64 cnt) {
+                if (cnt > 0)
+                    XSB_CUDA(cudaMemcpyAsync(A + dst, src + from, sizeof(Rec) * (size_t)cnt, cudaMemcpyDeviceToDevice, s));
+            };
+            cp(0, 0, nnz_old);
+            cp(nnz_old, nnz_old + own, n_low);
+            cp(nnz_old + n_low, nnz_old, own);
+            cp(nnz_old + n_low + own, nnz_old + own + n_low, n_high);
+        }
+        total = mine;
+        tomb = false;
+    };
 
     void *new_colptr = h->dalloc(h->isz() * (size_t)(h->n + 1));
     Rec *sorted = nullptr, *spare = nullptr;
@@ -530,7 +603,8 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             int pair_passes = 0;
             u64 npairs = 0;
             grouped = group_by_column(s, A, B, (u64)total, h->L, gws, ws, nzcol, nzstart, totals, h->h_scal + 4,
-                                      h->d_scal + 4, h->lc, tp, &pair_passes, &npairs);
+                                      h->d_scal + 4, h->lc, tp, &pair_passes, &npairs,
+                                      tomb ? h->L.ownershift() : -1, (u32)h->rank, pord);
             h->dfree(gws);
             h->stats_pairs = (i64)npairs;
             if (grouped)
@@ -545,6 +619,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         }
         if (!grouped)
         {
+            drop_foreign();
             colfold_clear_counts(s, cws, (u64)total, h->n);
             plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
             sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp, colfold_counts(cws, (u64)total, h->n),
@@ -612,6 +687,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     }
     else if (h->strategy == XSB_STRATEGY_COLSORT && column_path_supported(h->L))
     {
+        drop_foreign();
         // ---- sort by column only; rows are ordered inside the reduce kernel (bitonic, per column)
         plan = make_sort_plan(h->L.low + h->L.rowbits, h->L.colbits);
         sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
@@ -638,6 +714,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     }
     if (path == 0)
     {
+        drop_foreign();
         // ---- sort by (col,row), then a flat segmented reduction
         plan = make_sort_plan(h->L.low, h->L.sortbits());
         sorted = radix_sort_records(s, A, B, (u64)total, plan, ws, h->lc, tp);
@@ -686,7 +763,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     if (tp)
         tp->end(s, &StageTimes::other);
 
-    h->stats.n_inserted = n_ins;
+    h->stats.n_inserted = n_ins - foreign;
     h->stats.nnz_old = nnz_old;
     h->stats.nnz_new = nnz_new;
     h->stats.sort_passes = passes_run;
@@ -725,6 +802,22 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     if (pattern_changed)
         *pattern_changed = (nnz_new != nnz_old) ? 1 : 0; // the pattern only ever grows
     return XSB_OK;
+}
+
+// slab handles: fills the staged records up to a whole number of chunks with records the flush skips
+void pad_region(xsb_matrix *h)
+{
+    if (h->L.ownerbits == 0)
+        return;
+    Stage &st = h->stage[0];
+    const i64 end = st.front + st.count;
+    const i64 pad = xsb_matrix::chunk_up(end) - end;
+    if (pad == 0)
+        return;
+    h->ensure_stage(0, pad);
+    route_fill_skipped(h->stream, st.buf + st.front + st.count, pad, h->L, h->lc);
+    st.count += pad;
+    h->n_pad += pad;
 }
 
 // room for `count` generated records in partition tid; returns where to write them
@@ -809,18 +902,24 @@ static int32_t create_impl(int64_t m, int64_t n_global, int32_t nranks, int32_t 
         L.low = 2 + L.tidbits;
         L.rowbits = ceil_log2(m);
         L.colbits = ceil_log2(n);
-        KeyLayout Ls = L;
         if (nranks > 0)
-        {
-            Ls.colbits = ceil_log2(n_global);
-            Ls.ownerbits = ceil_log2(nranks);
-            Ls.nranks = nranks;
+        { // every rank uses the same field widths: a record is in its owner's layout wherever it is staged
+            i64 widest = 1;
+            for (int r = 0; r < nranks; ++r)
+                widest = std::max<i64>(widest, splits[r + 1] - splits[r]);
+            L.colbits = ceil_log2(widest);
+            L.ownerbits = ceil_log2(nranks);
+            L.nranks = nranks;
+            L.self = rank;
             for (int r = 0; r <= nranks; ++r)
-                Ls.splits[r] = splits[r];
+                L.splits[r] = splits[r];
         }
-        REQUIRE(Ls.low + Ls.rowbits + Ls.colbits + Ls.ownerbits <= 64, XSB_EINVAL,
+        KeyLayout Ls = L; // insertion side: global columns in, owner found by pack()
+        Ls.cols_global = 1;
+        REQUIRE(L.low + L.rowbits + L.colbits + L.ownerbits <= 64, XSB_EINVAL,
                 "m*n*n_tid does not fit the 64-bit packed key");
-        REQUIRE(L.rowbits <= 32 && Ls.colbits <= 32, XSB_EINVAL, "dimensions above 2^32 are not supported");
+        REQUIRE(L.rowbits <= 32 && L.colbits <= 32 && n_global < (1ll << 32), XSB_EINVAL,
+                "dimensions above 2^32 are not supported");
         XSB_CUDA(cudaSetDevice(device));
         h = new xsb_matrix();
         h->m = m;
@@ -888,8 +987,36 @@ int32_t xsb_slab_info(const xsb_matrix *h, int64_t *col_begin, int64_t *col_end,
     return XSB_OK;
 }
 
-// Buckets the staged records by owning rank (one stable radix pass on the owner bits) into the
-// caller's send buffer; send_counts[r] = records for rank r, laid out rank after rank.
+// Counts the staged records per owning rank: send_counts[r] = records rank r owns (r == own rank:
+// the records that stay).  One read of the keys; nothing moves.
+int32_t xsb_route_count(xsb_matrix *h, int64_t *send_counts)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && send_counts, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(!h->routed, XSB_ESTATE, "staged records were already routed");
+        Stage &st = h->stage[0];
+        h->dfree(h->route_ws);
+        h->route_ws = nullptr;
+        for (int r = 0; r < kMaxRanks; ++r)
+            h->route_counts[r] = 0;
+        if (st.count > 0 && h->L.ownerbits > 0)
+        {
+            h->route_ws = h->dalloc(route_workspace_bytes((u64)st.count, h->nranks));
+            route_count(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, h->route_counts, h->lc);
+        }
+        else
+            h->route_counts[h->rank] = (u64)st.count;
+        h->route_counted = st.count;
+        for (int r = 0; r < h->nranks; ++r)
+            send_counts[r] = (int64_t)h->route_counts[r];
+        return XSB_OK;
+    });
+}
+
+// Copies the staged records owned by OTHER ranks into the caller's send buffer, destination rank
+// after destination rank, each bucket in stream order; the rank's own records stay staged where
+// they are.  send_counts as in xsb_route_count; capacity = room of the send buffer in records.
 int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, int64_t *send_counts)
 {
     return guard(h, [&]() -> int32_t {
@@ -897,34 +1024,60 @@ int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, i
         REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
         REQUIRE(!h->routed, XSB_ESTATE, "staged records were already routed");
         Stage &st = h->stage[0];
-        REQUIRE(capacity >= st.count, XSB_EINVAL, "send buffer too small");
-        REQUIRE(st.count == 0 || (send_records && is_device_ptr(send_records)), XSB_EINVAL,
-                "send buffer must be device memory");
-        u64 counts[kRadix] = {0};
-        if (st.count > 0)
+        if (h->route_counted != st.count || (st.count > 0 && h->L.ownerbits > 0 && !h->route_ws))
         {
-            void *ws = h->dalloc(sort_workspace_bytes((u64)st.count));
-            partition_records(h->stream, st.buf + st.front, static_cast<Rec *>(send_records), (u64)st.count,
-                              h->Ls.low + h->Ls.rowbits + h->Ls.colbits, h->Ls.ownerbits, ws, h->lc, counts);
-            h->dfree(ws);
+            const int32_t rc = xsb_route_count(h, send_counts);
+            if (rc != XSB_OK)
+                return rc;
         }
+        i64 foreign = 0;
         for (int r = 0; r < h->nranks; ++r)
-            send_counts[r] = (int64_t)counts[r];
-        h->clear_staging(false);
+        {
+            send_counts[r] = (int64_t)h->route_counts[r];
+            if (r != h->rank)
+                foreign += (i64)h->route_counts[r];
+        }
+        REQUIRE(capacity >= foreign, XSB_EINVAL,
+                "send buffer too small: " + std::to_string(foreign) + " records leave this rank");
+        REQUIRE(foreign == 0 || (send_records && is_device_ptr(send_records)), XSB_EINVAL,
+                "send buffer must be device memory");
+        if (foreign > 0)
+            route_extract(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, h->route_counts,
+                          static_cast<Rec *>(send_records), h->lc);
+        h->dfree(h->route_ws);
+        h->route_ws = nullptr;
+        h->route_counted = -1;
+        h->foreign = foreign; // they stay behind in the staging buffer; the flush skips them by owner
+        h->routed = true;
+        pad_region(h);
+        h->own_end = st.count;
         h->sync();
         return XSB_OK;
     });
 }
 
-// Takes the records this rank received (source rank after source rank, each in stream order),
-// rewrites them into the slab's key layout and stages them for xsb_flush.
-int32_t xsb_route_finish(xsb_matrix *h, const void *recv_records, int64_t count)
+// Appends records received from another rank (already in this rank's layout, in the sender's
+// stream order) behind what is staged.  Call once per source, in source-rank order.
+int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_records, int64_t count)
 {
     return guard(h, [&]() -> int32_t {
         REQUIRE(h, XSB_EINVAL, "NULL handle");
         REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
         REQUIRE(count >= 0, XSB_EINVAL, "negative count");
         REQUIRE(h->pending() == 0 || h->routed, XSB_ESTATE, "unrouted records are still staged");
+        REQUIRE(src_rank >= 0 && src_rank < h->nranks && src_rank != h->rank, XSB_EINVAL, "bad source rank");
+        REQUIRE(src_rank > h->last_src, XSB_ESTATE, "sources must be handed over in ascending rank order");
+        h->last_src = src_rank;
+        if (!h->routed)
+        { // nothing was staged on this rank: the own region is empty
+            h->ensure_stage(0, 0);
+            h->own_end = 0;
+        }
+        if (src_rank > h->rank && h->low_end < 0)
+        { // first source above this rank: the region of the lower ranks is complete
+            pad_region(h);
+            h->low_end = h->stage[0].count;
+        }
         REQUIRE(count == 0 || (recv_records && is_device_ptr(recv_records)), XSB_EINVAL,
                 "receive buffer must be device memory");
         if (count > 0)
@@ -933,17 +1086,18 @@ int32_t xsb_route_finish(xsb_matrix *h, const void *recv_records, int64_t count)
             Stage &st = h->stage[0];
             write_scalar(h, 1, ~0ull);
             write_scalar(h, 5, 0ull);
-            relayout_records(h->stream, static_cast<const Rec *>(recv_records), count, h->Ls, h->L, h->col_begin,
-                             h->n, st.buf + st.front + st.count, h->d_scal + 1, h->d_scal + 5, h->lc);
+            route_check(h->stream, static_cast<const Rec *>(recv_records), count, h->L, h->n, h->d_scal + 1,
+                        h->d_scal + 5, h->lc);
+            XSB_CUDA(cudaMemcpyAsync(st.buf + st.front + st.count, recv_records, sizeof(Rec) * (size_t)count,
+                                     cudaMemcpyDeviceToDevice, h->stream));
+            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 5, h->d_scal + 5, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
             const u64 bad = read_scalar(h, 1);
-            if (h->h_scal[5] == 0ull)
-                XSB_CUDA(cudaMemcpyAsync(h->h_scal + 5, h->d_scal + 5, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-            h->sync();
             if (h->h_scal[5] != 0ull)
                 h->has_assign = true; // the received stream holds A[i,j]=v records: ordered fold needed
             REQUIRE(bad == ~0ull, XSB_EBOUNDS,
                     "record " + std::to_string(bad) + " of the received buffer is not owned by this rank");
             st.count += count;
+            (src_rank < h->rank ? h->n_low : h->n_high) += count;
         }
         h->routed = true;
         return XSB_OK;
@@ -961,6 +1115,7 @@ int32_t xsb_destroy(xsb_matrix *h)
     h->clear_staging(true);
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
+    h->dfree(h->route_ws);
     h->dfree(h->d_scal);
     h->release_cache();
     if (h->h_scal)

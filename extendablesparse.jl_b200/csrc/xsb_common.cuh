@@ -39,22 +39,45 @@ struct KeyLayout
     int tidbits; // bits of the partition id
     int rowbits;
     int colbits;
-    // Multi-GPU staging layout only: the rank that owns the column rides in the bits above
-    // the column ([owner:ownerbits] on top), so routing is one radix pass on those bits.
+    // Slab (multi-GPU) handles only: the rank that owns the column rides in the bits above the
+    // column ([owner:ownerbits] on top) and the column field is RELATIVE to the owner's slab, so a
+    // record is already in its owner's flush layout wherever it is staged: records for other
+    // ranks are picked out by their owner bits, the rest never moves.
     int ownerbits;
     int nranks;
+    int self;        // this rank
+    int cols_global; // pack() takes global columns (insertion side); 0: slab-local columns owned by self
     i64 splits[kMaxRanks + 1]; // rank r owns columns [splits[r], splits[r+1]), 0-based
     __host__ __device__ __forceinline__ u64 pack(u64 col, u64 row, u32 tid, u32 fl) const
     {
+        u64 o = 0;
+        if (nranks > 0)
+        {
+            if (cols_global)
+            {
+                int q = 0;
+                while (q + 1 < nranks && (i64)col >= splits[q + 1])
+                    ++q;
+                col -= (u64)splits[q];
+                o = (u64)q;
+            }
+            else
+                o = (u64)self;
+        }
         u64 k = (col << (rowbits + low)) | (row << low) | ((u64)tid << 2) | (u64)fl;
         if (ownerbits)
-        {
-            int o = 0;
-            while (o + 1 < nranks && (i64)col >= splits[o + 1])
-                ++o;
-            k |= (u64)o << (low + rowbits + colbits);
-        }
+            k |= o << (low + rowbits + colbits);
         return k;
+    }
+    __host__ __device__ __forceinline__ int ownershift() const { return low + rowbits + colbits; }
+    __host__ __device__ __forceinline__ u32 owner(u64 key) const
+    {
+        return ownerbits ? (u32)(key >> (low + rowbits + colbits)) : 0u;
+    }
+    // global column of a staged record
+    __host__ __device__ __forceinline__ u64 gcol(u64 key) const
+    {
+        return col(key) + (nranks > 0 ? (u64)splits[ownerbits ? owner(key) : (u32)self] : 0ull);
     }
     __host__ __device__ __forceinline__ u64 colrow(u64 key) const { return key >> low; }
     __host__ __device__ __forceinline__ u64 col(u64 key) const

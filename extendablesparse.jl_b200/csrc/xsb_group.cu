@@ -47,8 +47,8 @@ struct CountSpace
 // pass 1: distinct columns of every chunk and their record counts
 // ------------------------------------------------------------------------
 __global__ void __launch_bounds__(GP_WARPS * 32, 5)
-group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks,
-                   u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
+group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, int ownershift, u32 me,
+                   u32 nchunks, u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
                    uint2 *__restrict__ chunkinfo, u32 cap, u32 *__restrict__ d_flags)
 {
     constexpr u32 full = 0xffffffffu;
@@ -105,7 +105,8 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
                 }
                 else
                 {
-                    const bool valid = bb + lane < cnt_here;
+                    // records owned by another rank (slab handles: already sent) do not take part
+                    const bool valid = bb + lane < cnt_here && (ownershift < 0 || (u32)(key[i] >> ownershift) == me);
                     const u32 col = (u32)(key[i] >> colshift) & colmask;
                     const u32 vm = __ballot_sync(full, valid);
                     u32 peers = 0;
@@ -177,12 +178,27 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
 // ------------------------------------------------------------------------
 constexpr int PO_THREADS = 256; // chunks per block
 
+// Order in which the chunks' pairs are listed = order in which the fold meets the records of a
+// column.  Physically a slab handle's buffer holds [old CSC | own | received from lower ranks |
+// received from higher ranks] (each region a whole number of chunks); the fold must see
+// [old | lower ranks | own | higher ranks]: the rank-ordered concatenation of the ranks' streams.
+__device__ __forceinline__ u32 chunk_at(const ChunkOrder &o, u32 v)
+{
+    const u32 nl = o.c_low - o.c_own, no = o.c_own - o.c_old;
+    if (v < o.c_old || v >= o.c_low)
+        return v;
+    if (v < o.c_old + nl)
+        return o.c_own + (v - o.c_old);
+    return o.c_old + (v - o.c_old - nl);
+    (void)no;
+}
+
 __global__ void __launch_bounds__(PO_THREADS)
-pair_order_tilesum_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, u32 *__restrict__ tsum)
+pair_order_tilesum_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, ChunkOrder ord, u32 *__restrict__ tsum)
 {
     __shared__ u32 s_w[PO_THREADS / 32];
     const u32 c = blockIdx.x * PO_THREADS + threadIdx.x;
-    u32 v = c < nchunks ? chunkinfo[c].y : 0u;
+    u32 v = c < nchunks ? chunkinfo[chunk_at(ord, c)].y : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -237,13 +253,13 @@ __global__ void __launch_bounds__(1024) pair_order_scan_kernel(u32 *__restrict__
 // block = 256 chunks: in-block scan of the pair counts, then every warp copies the pairs of its 32
 // chunks from their ticket position to their position in chunk order
 __global__ void __launch_bounds__(PO_THREADS)
-pair_order_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, const u32 *__restrict__ tsum,
+pair_order_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, ChunkOrder ord, const u32 *__restrict__ tsum,
                   const Rec *__restrict__ pairs_in, Rec *__restrict__ pairs_out)
 {
     __shared__ u32 s_w[PO_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 c = blockIdx.x * PO_THREADS + threadIdx.x;
-    const uint2 info = c < nchunks ? chunkinfo[c] : make_uint2(0u, 0u);
+    const uint2 info = c < nchunks ? chunkinfo[chunk_at(ord, c)] : make_uint2(0u, 0u);
     u32 incl = info.y;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -387,7 +403,8 @@ struct ScatterSpace
 };
 
 __global__ void __launch_bounds__(GP_WARPS * 32, 5)
-group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, u32 nchunks,
+group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, int ownershift, u32 me,
+                     u32 nchunks,
                      const u32 *__restrict__ chunkcols, const uint2 *__restrict__ chunkinfo,
                      const u32 *__restrict__ offs, Rec *__restrict__ out)
 {
@@ -452,7 +469,7 @@ group_scatter_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 col
             const u32 bb = (g + i) * 32;
             if (bb < cnt_here) // warp-uniform
             {
-                const bool valid = bb + lane < cnt_here;
+                const bool valid = bb + lane < cnt_here && (ownershift < 0 || (u32)(r[i].key >> ownershift) == me);
                 const u32 col = (u32)(r[i].key >> colshift) & colmask;
                 const u32 vm = __ballot_sync(full, valid);
                 u32 peers = 1u << lane;
@@ -514,6 +531,7 @@ GpLayout gp_layout(u64 nrec)
 } // namespace
 
 size_t group_workspace_bytes(u64 nrec) { return gp_layout(nrec).bytes; }
+int group_chunk_records() { return GP_W; }
 
 bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols)
 {
@@ -529,7 +547,8 @@ void colscan_scan_launch(cudaStream_t stream, u64 *trec, u32 *tnz, i64 nt, u64 *
 // stream has too many (chunk, column) pairs for this to pay off.
 bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
                      void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
-                     LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out)
+                     LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out, int ownershift, u32 me,
+                     const ChunkOrder *order)
 {
     const GpLayout l = gp_layout(nrec);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -562,7 +581,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     const int chunkbits = 0; // pair keys hold the column only
     const unsigned cblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;
     group_count_kernel<<<cblocks, GP_WARPS * 32, sizeof(CountSpace) * GP_WARPS, stream>>>(
-        in, nrec, colshift, colmask, nchunks, pair_total, pairs_b, chunkcols, chunkinfo, l.cap, flags);
+        in, nrec, colshift, colmask, ownershift, me, nchunks, pair_total, pairs_b, chunkcols, chunkinfo, l.cap, flags);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     // pairs made, too-many flag
@@ -583,9 +602,10 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     {
         u32 *otsum = reinterpret_cast<u32 *>(ws + l.off_status);
         const unsigned oblocks = (nchunks + PO_THREADS - 1) / PO_THREADS;
-        pair_order_tilesum_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, otsum);
+        ChunkOrder ord = order ? *order : ChunkOrder{nchunks, nchunks, nchunks};
+        pair_order_tilesum_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, ord, otsum);
         pair_order_scan_kernel<<<1, 1024, 0, stream>>>(otsum, oblocks);
-        pair_order_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, otsum, pairs_b, pairs_a);
+        pair_order_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, ord, otsum, pairs_b, pairs_a);
         lc.add(3);
         XSB_CUDA(cudaGetLastError());
     }
@@ -608,7 +628,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     // ---- pass 2
     const unsigned sblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;
     group_scatter_kernel<<<sblocks, GP_WARPS * 32, sizeof(ScatterSpace) * GP_WARPS, stream>>>(
-        in, nrec, colshift, colmask, nchunks, chunkcols, chunkinfo, offs, out);
+        in, nrec, colshift, colmask, ownershift, me, nchunks, chunkcols, chunkinfo, offs, out);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     if (timer)

@@ -83,8 +83,6 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
 
 void partition_records(cudaStream_t stream, const Rec *in, Rec *out, u64 n, int shift, int bits, void *workspace,
                        LaunchCounter &lc, u64 *counts_host);
-void relayout_records(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &src, const KeyLayout &dst,
-                      i64 col_begin, i64 ncols, Rec *out, u64 *d_err, u64 *d_has_assign, LaunchCounter &lc);
 void set_sort_variant(int v);
 int get_sort_variant();
 void sort_selftest(cudaStream_t stream, u64 n, int nbits, int variant, int reps, float *ms_hist, float *ms_pass,
@@ -135,16 +133,35 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
 void colfold_lists(void *workspace, u64 nrec, i64 ncols, u32 **nzcol, u32 **nzstart, u64 **totals);
 
 // ---- xsb_group.cu
+// chunk index boundaries of the regions of a slab handle's buffer: old CSC [0, c_old), own records
+// [c_old, c_own), received from lower ranks [c_own, c_low), from higher ranks [c_low, nchunks)
+struct ChunkOrder
+{
+    u32 c_old, c_own, c_low;
+};
+int group_chunk_records();
 size_t group_workspace_bytes(u64 nrec);
 bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols);
 // stable grouping by column in two passes (sparse per-chunk histograms); false: no column locality
 bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
                      void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
-                     LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out);
+                     LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out, int ownershift = -1,
+                     u32 me = 0, const ChunkOrder *order = nullptr);
+// ownershift >= 0: records whose key >> ownershift != me belong to other ranks and are skipped
 // parked entries -> rowval / nzval
 void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, int idx64, int base,
                      const void *colptr, void *rowval_out, double *nzval_out, void *workspace, LaunchCounter &lc,
                      StageTimer *timer);
+
+// ---- xsb_route.cu
+size_t route_workspace_bytes(u64 n, int nranks);
+void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, u64 *counts_host,
+                 LaunchCounter &lc);
+void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace,
+                   const u64 *counts_host, Rec *send, LaunchCounter &lc);
+void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayout &L, LaunchCounter &lc);
+void route_check(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &L, i64 ncols, u64 *d_err,
+                 u64 *d_has_assign, LaunchCounter &lc);
 
 // ---- xsb_preagg.cu
 // XSB_FAST: in[0, nrec) -> out[0, *d_count): partial sums of windows of the stream; d_count zeroed by the caller

@@ -1,0 +1,281 @@
+// xsb_route.cu -- multi-GPU routing of staged records by column ownership without moving the
+// records a rank keeps.
+//
+// A staged key carries [owner | column relative to the owner's slab | row | tid | flavour], so a
+// record is already in its owner's flush layout.  Routing therefore only has to COPY OUT the
+// records owned by other ranks (in stream order, destination after destination); they stay
+// behind in the staging buffer as records the flush skips by their owner bits.  For a
+// partitioned assembly the foreign part is the interface between slabs (P1-FEM 128^2 x 127
+// layers: 0.4 % of the stream), so routing costs one read of the keys instead of two passes over
+// all records.
+//
+//   route_count_kernel   : records per destination rank in every tile of RT_TILE records
+//   route_scan_kernel    : per destination, exclusive scan over the tiles (one block each)
+//   route_extract_kernel : tiles that hold foreign records copy them to the send buffer, stable
+//   route_check_kernel   : received records must be owned by this rank; notes A[i,j]=v records
+//
+// Reference analogue: the per-partition buffers of GenericMTExtendableSparseMatrixCSC, summed in
+// partition order (src/matrix/genericmtextendablesparsematrixcsc.jl:45-51,
+// src/matrix/sparsematrixdilnkc.jl:416-426); the reference itself is single-process.
+#include "xsb_internal.h"
+
+namespace xsb {
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_IPT = 8;
+constexpr int RT_TILE = RT_THREADS * RT_IPT;
+
+__global__ void __launch_bounds__(RT_THREADS)
+route_count_kernel(const Rec *__restrict__ in, u64 n, int ownershift, u32 me, int nranks, u32 *__restrict__ tilecnt)
+{
+    __shared__ u32 s_cnt[kMaxRanks];
+    if (threadIdx.x < kMaxRanks)
+        s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 b0 = (u64)blockIdx.x * RT_TILE;
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < RT_IPT; ++i)
+    {
+        const u64 k = b0 + (u64)i * RT_THREADS + threadIdx.x;
+        if (k < n)
+        {
+            const u32 o = (u32)(in[k].key >> ownershift);
+            if (o != me)
+            {
+                atomicAdd(&s_cnt[o], 1u);
+                any = true;
+            }
+        }
+    }
+    if (__syncthreads_or(any))
+    {
+        if ((int)threadIdx.x < nranks)
+            tilecnt[(size_t)blockIdx.x * nranks + threadIdx.x] = s_cnt[threadIdx.x];
+    }
+}
+
+// block d: tileoff[t][d] = records for rank d in the tiles before t; total[d].
+// tilecnt holds the raw counts (cnt) and tileoff the scanned offsets: the extract kernel needs both
+__global__ void __launch_bounds__(1024)
+route_scan_kernel(const u32 *__restrict__ tilecnt, u32 *__restrict__ tileoff, u64 ntiles, int nranks,
+                   u64 *__restrict__ total)
+{
+    __shared__ u64 s_w[32];
+    __shared__ u64 s_carry;
+    const int d = blockIdx.x;
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u64 b0 = 0; b0 < ntiles; b0 += 1024)
+    {
+        const u64 t = b0 + threadIdx.x;
+        const u64 x = t < ntiles ? (u64)tilecnt[t * nranks + d] : 0ull;
+        u64 v = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u64 y = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o)
+                v += y;
+        }
+        if (lane == 31)
+            s_w[warp] = v;
+        __syncthreads();
+        u64 pre = s_carry;
+        for (int w = 0; w < warp; ++w)
+            pre += s_w[w];
+        if (t < ntiles)
+            tileoff[t * nranks + d] = (u32)(pre + v - x);
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            s_carry = pre + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        total[d] = s_carry;
+}
+
+// bucket_base[d] = where rank d's bucket starts in the send buffer
+__global__ void __launch_bounds__(RT_THREADS)
+route_extract_kernel(const Rec *__restrict__ in, u64 n, int ownershift, u32 me, int nranks,
+                     const u32 *__restrict__ tilecnt, const u32 *__restrict__ tileoff,
+                     const u64 *__restrict__ bucket_base, Rec *__restrict__ send)
+{
+    __shared__ u32 s_w[RT_THREADS / 32];
+    __shared__ u32 s_run;
+    const u32 *cnt = tilecnt + (size_t)blockIdx.x * nranks;
+    u32 has = 0;
+    for (int d = 0; d < nranks; ++d)
+        has |= cnt[d];
+    if (!has)
+        return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 b0 = (u64)blockIdx.x * RT_TILE;
+    Rec r[RT_IPT];
+    u32 own[RT_IPT];
+#pragma unroll
+    for (int i = 0; i < RT_IPT; ++i)
+    {
+        const u64 k = b0 + (u64)i * RT_THREADS + threadIdx.x;
+        own[i] = me;
+        if (k < n)
+        {
+            r[i] = in[k];
+            own[i] = (u32)(r[i].key >> ownershift);
+        }
+    }
+    for (int d = 0; d < nranks; ++d)
+    {
+        if (cnt[d] == 0u) // uniform over the block
+            continue;
+        if (threadIdx.x == 0)
+            s_run = 0;
+        __syncthreads();
+        Rec *dst = send + bucket_base[d] + tileoff[(size_t)blockIdx.x * nranks + d];
+#pragma unroll
+        for (int i = 0; i < RT_IPT; ++i)
+        { // round i holds RT_THREADS consecutive records: rank them in thread order
+            const bool mine = own[i] == (u32)d && (u32)d != me;
+            const u32 bal = __ballot_sync(0xffffffffu, mine);
+            if (lane == 0)
+                s_w[warp] = __popc(bal);
+            __syncthreads();
+            u32 pre = s_run;
+            for (int w = 0; w < warp; ++w)
+                pre += s_w[w];
+            if (mine)
+                st_rec(dst + pre + __popc(bal & lanemask_lt()), r[i]);
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                u32 t = 0;
+                for (int w = 0; w < RT_THREADS / 32; ++w)
+                    t += s_w[w];
+                s_run += t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+route_check_kernel(const Rec *__restrict__ in, i64 count, int ownershift, u32 me, u64 colmask, int colshift, u64 ncols,
+                   u64 *__restrict__ d_err, u64 *__restrict__ d_has_assign)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const u64 key = in[k].key;
+        if ((key & 3ull) == FL_ASSIGN && *d_has_assign == 0ull)
+            *d_has_assign = 1ull; // benign race: every writer stores the same value
+        if ((u32)(key >> ownershift) != me || ((key >> colshift) & colmask) >= ncols)
+            atomicMin(d_err, (u64)k); // a record routed to the wrong owner
+    }
+}
+
+// padding records between the regions of a slab handle's buffer: owned by "another rank", so the
+// flush skips them like the records that were sent away
+__global__ void __launch_bounds__(256) route_fill_kernel(Rec *__restrict__ out, i64 count, u64 key)
+{
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count)
+    {
+        Rec r;
+        r.key = key;
+        r.val = 0.0;
+        st_rec(out + k, r);
+    }
+}
+
+void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayout &L, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    const u64 key = (u64)((u32)L.self ^ 1u) << L.ownershift();
+    route_fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(out, count, key);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+size_t route_workspace_bytes(u64 n, int nranks)
+{
+    const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
+    return 2 * sizeof(u32) * (size_t)ntiles * nranks + 2 * sizeof(u64) * kMaxRanks + 256;
+}
+
+// counts_host[d] = staged records owned by rank d (d == me: the ones that stay)
+void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, u64 *counts_host,
+                 LaunchCounter &lc)
+{
+    const int nr = L.nranks;
+    for (int d = 0; d < nr; ++d)
+        counts_host[d] = 0;
+    if (n == 0)
+        return;
+    const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
+    u32 *tilecnt = static_cast<u32 *>(workspace);
+    u32 *tileoff = tilecnt + (size_t)ntiles * nr;
+    u64 *total = reinterpret_cast<u64 *>(tileoff + (size_t)ntiles * nr);
+    XSB_CUDA(cudaMemsetAsync(tilecnt, 0, sizeof(u32) * (size_t)ntiles * nr, stream));
+    route_count_kernel<<<(unsigned)ntiles, RT_THREADS, 0, stream>>>(in, n, L.ownershift(), (u32)L.self, nr, tilecnt);
+    route_scan_kernel<<<nr, 1024, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total);
+    lc.add(2);
+    XSB_CUDA(cudaGetLastError());
+    u64 h[kMaxRanks];
+    XSB_CUDA(cudaMemcpyAsync(h, total, sizeof(u64) * nr, cudaMemcpyDeviceToHost, stream));
+    XSB_CUDA(cudaStreamSynchronize(stream));
+    u64 foreign = 0;
+    for (int d = 0; d < nr; ++d)
+    {
+        counts_host[d] = h[d];
+        foreign += h[d];
+    }
+    counts_host[L.self] = n - foreign;
+}
+
+// after route_count on the same records and workspace: foreign records -> send (destination after
+// destination, each bucket in stream order)
+void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace,
+                   const u64 *counts_host, Rec *send, LaunchCounter &lc)
+{
+    if (n == 0)
+        return;
+    const int nr = L.nranks;
+    const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
+    u32 *tilecnt = static_cast<u32 *>(workspace);
+    u32 *tileoff = tilecnt + (size_t)ntiles * nr;
+    u64 *total = reinterpret_cast<u64 *>(tileoff + (size_t)ntiles * nr);
+    u64 *bucket_base = total + kMaxRanks;
+    u64 hb[kMaxRanks];
+    u64 run = 0;
+    for (int d = 0; d < nr; ++d)
+    {
+        hb[d] = run;
+        if (d != L.self)
+            run += counts_host[d];
+    }
+    if (run == 0)
+        return;
+    XSB_CUDA(cudaMemcpyAsync(bucket_base, hb, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
+    route_extract_kernel<<<(unsigned)ntiles, RT_THREADS, 0, stream>>>(in, n, L.ownershift(), (u32)L.self, nr, tilecnt,
+                                                                      tileoff, bucket_base, send);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+    XSB_CUDA(cudaStreamSynchronize(stream)); // hb lives on this stack frame
+}
+
+void route_check(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &L, i64 ncols, u64 *d_err,
+                 u64 *d_has_assign, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    const int blocks = (int)std::min<i64>((count + 255) / 256, (i64)kNumSM * 16);
+    route_check_kernel<<<blocks, 256, 0, stream>>>(in, count, L.ownershift(), (u32)L.self, (1ull << L.colbits) - 1ull,
+                                                   L.low + L.rowbits, (u64)ncols, d_err, d_has_assign);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+} // namespace xsb

@@ -1,13 +1,14 @@
 """Column-slab multi-GPU assembly: one process per GPU, torch.distributed for the exchange.
 
 Rank r owns the contiguous column slab [splits[r], splits[r+1]).  Every rank stages the
-insertions it generates (any column), buckets them by owner with one radix pass on the GPU
-(xsb_route_prepare), the off-rank buckets travel with ONE all-to-all-v (NCCL over NVLink; the
-rank's own bucket never leaves its HBM), and every rank merges what it holds into its own CSC
-slab (xsb_route_finish per source in rank order, then xsb_flush).  Buckets are ingested in
-source-rank order and each bucket is in stream order, so the deterministic fold runs in
-(source rank, stream) order -- the distributed result equals the serial reference applied to
-the rank-ordered concatenation of the ranks' streams.
+insertions it generates (any column).  A staged record carries its owner and its column
+relative to the owner's slab, so routing only copies OUT what other ranks own
+(xsb_route_count + xsb_route_prepare: one read of the keys, the records a rank keeps never
+move); those buckets travel with ONE all-to-all-v (NCCL over NVLink), are appended behind the
+rank's own records (xsb_route_finish per source, ascending) and xsb_flush merges everything
+into the rank's CSC slab.  The fold meets the records of an entry as [resident CSC | lower
+ranks | own | higher ranks], each in stream order -- the distributed result equals the serial
+reference applied to the rank-ordered concatenation of the ranks' streams.
 
 Reference analogue: the per-partition buffers of GenericMTExtendableSparseMatrixCSC
 (genericmtextendablesparsematrixcsc.jl:45-51) summed in partition order
@@ -30,9 +31,9 @@ def exchange_off_rank(send: torch.Tensor, send_counts: Sequence[int], rank: int,
                       ) -> Tuple[torch.Tensor, List[int]]:
     """All-to-all-v of the OFF-RANK buckets of 16-byte records (2 int64 words each).
 
-    `send` holds the buckets rank after rank (the own bucket included, it stays where it is).
-    Returns the received records, source rank after source rank (own rank: nothing), and the
-    per-source record counts (own rank: 0)."""
+    `send` holds the buckets for the other ranks, destination after destination (nothing for the
+    own rank: those records never left the staging buffer).  Returns the received records, source
+    rank after source rank, and the per-source record counts (own rank: 0)."""
     world = dist.get_world_size(group)
     assert len(send_counts) == world
     off = [int(c) if r != rank else 0 for r, c in enumerate(send_counts)]
@@ -40,14 +41,8 @@ def exchange_off_rank(send: torch.Tensor, send_counts: Sequence[int], rank: int,
     rc = torch.empty(world, dtype=torch.int64, device=send.device)
     dist.all_to_all_single(rc, sc, group=group)
     recv_counts = [int(x) for x in rc.cpu().tolist()]
-    # the off-rank buckets, packed contiguously (they are the small part: interface entries)
-    starts = [0]
-    for c in send_counts:
-        starts.append(starts[-1] + int(c))
-    parts = [send[2 * starts[r]: 2 * starts[r + 1]] for r in range(world) if r != rank and send_counts[r] > 0]
-    packed = torch.cat(parts) if parts else send[:0]
     recv = torch.empty(2 * sum(recv_counts), dtype=torch.int64, device=send.device)
-    dist.all_to_all_single(recv, packed, output_split_sizes=[2 * c for c in recv_counts],
+    dist.all_to_all_single(recv, send[: 2 * sum(off)], output_split_sizes=[2 * c for c in recv_counts],
                            input_split_sizes=[2 * c for c in off], group=group)
     return recv, recv_counts
 
@@ -68,8 +63,8 @@ class DistExtendableSparseMatrix:
     """ExtendableSparseMatrix sharded by column ownership over the ranks of a process group.
 
     `backend` is the per-rank slab object; the product backend is capi.Handle in slab mode
-    (libxsparse_b200).  It must offer: pending, route_prepare(send, capacity) -> counts,
-    route_finish(records, count) (appending), flush(mode) -> (nnz, changed).
+    (libxsparse_b200).  It must offer: pending, route_count() -> counts, route_prepare(send, capacity)
+    -> counts, route_finish(src, records, count) (ascending src), flush(mode) -> (nnz, changed).
     """
 
     def __init__(self, m: int, n: int, splits: Sequence[int] | None = None, group=None, device=None, backend=None,
@@ -109,27 +104,29 @@ class DistExtendableSparseMatrix:
     def flush(self, mode=0):
         """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank)."""
         cnt = int(self.h.pending)
-        send = self._send_buffer(cnt)
-        counts = self.h.route_prepare(send, cnt)
+        counts = self.h.route_count()
+        leaving = sum(c for r, c in enumerate(counts) if r != self.rank)
+        send = self._send_buffer(leaving)
+        self.h.route_prepare(send, leaving)
         recv, rcounts = exchange_off_rank(send, counts, self.rank, self.group)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
-        # ingest in source-rank order; the own bucket is read straight from the send buffer
-        own_start = sum(counts[: self.rank])
         pos = 0
-        for src in range(self.world):
-            if src == self.rank:
-                self.h.route_finish(send[2 * own_start: 2 * (own_start + counts[src])], counts[src])
-            else:
-                self.h.route_finish(recv[2 * pos: 2 * (pos + rcounts[src])], rcounts[src])
+        for src in range(self.world):  # ascending source rank; the own records stayed where they were
+            if src != self.rank:
+                self.h.route_finish(src, recv[2 * pos: 2 * (pos + rcounts[src])], rcounts[src])
                 pos += rcounts[src]
         nnz, changed = self.h.flush(mode)
-        self.nnz_offset, self.nnz_global = slab_offsets(nnz, self.device, self.group)
-        flag = torch.tensor([int(changed)], dtype=torch.int64, device=self.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        # one 16-byte all-gather: entries per slab (-> global colptr offsets) and "pattern changed"
+        mine = torch.tensor([nnz, int(changed)], dtype=torch.int64, device=self.device)
+        allv = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allv, mine, group=self.group)
+        allv = allv.cpu().tolist()
+        per_rank, flags = allv[0::2], allv[1::2]
+        self.nnz_offset, self.nnz_global = sum(per_rank[: self.rank]), sum(per_rank)
         self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received_off_rank": sum(rcounts),
                               "kept": counts[self.rank]}
-        return nnz, bool(flag.item())
+        return nnz, any(flags)
 
     def global_colptr(self, local_colptr):
         """Slab colptr (slab_width+1 entries) shifted to index the global rowval/nzval arrays."""

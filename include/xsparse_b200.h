@@ -183,12 +183,21 @@ int32_t xsb_create_slab(int64_t m, int64_t n_global, int32_t n_ranks, int32_t ra
                         const int64_t *col_splits, int32_t val_type, int32_t idx_type,
                         int32_t index_base, int32_t device, xsb_matrix **out);
 int32_t xsb_slab_info(const xsb_matrix *h, int64_t *col_begin, int64_t *col_end, int64_t *n_global);
-/* Step 1: bucket the staged records by owning rank into `send_records` (device, 16 B each,
- * capacity >= xsb_pending); send_counts[n_ranks] (host) receives the bucket sizes.
- * Step 2 (caller): all-to-all-v of the buckets (NCCL), received buffers concatenated in
- * source-rank order.  Step 3: hand the received records over; then xsb_flush. */
+/* A staged record carries its owner and its column relative to the owner's slab, so it is already
+ * in its owner's flush layout: routing only COPIES OUT what other ranks own; the rest never moves
+ * (the flush skips the copied-out records by their owner bits).
+ * Step 0 (optional): xsb_route_count -> send_counts[n_ranks] (host): staged records per owning rank
+ *   (own rank: the ones that stay); lets the caller size the send buffer.  One read of the keys.
+ * Step 1: xsb_route_prepare copies the records of the OTHER ranks into `send_records` (device,
+ *   16 B each), destination after destination, each bucket in stream order; capacity >= their number.
+ * Step 2 (caller): all-to-all-v of the buckets (NCCL).
+ * Step 3: xsb_route_finish once per source rank != own, in ascending rank order; then xsb_flush.
+ * The fold meets the records of an entry as [resident CSC | lower ranks | own | higher ranks], each
+ * in stream order: the distributed result equals the serial reference applied to the rank-ordered
+ * concatenation of the ranks' streams, bit for bit in XSB_DETERMINISTIC mode. */
+int32_t xsb_route_count(xsb_matrix *h, int64_t *send_counts);
 int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, int64_t *send_counts);
-int32_t xsb_route_finish(xsb_matrix *h, const void *recv_records, int64_t count);
+int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_records, int64_t count);
 
 /* ------------------------------------------------------------------ */
 /* values-only re-assembly into a frozen pattern (Newton / transient loops) */

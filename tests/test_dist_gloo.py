@@ -30,35 +30,49 @@ class OracleSlabBackend:
 
     @property
     def pending(self):
-        return len(self.staged) if self.routed is None else len(self.routed)
+        return len(self.staged)
+
+    def _owners(self):
+        return np.searchsorted(np.asarray(self.splits[1:]), [j - 1 for (_, j, _, _) in self.staged], side="right")
+
+    def route_count(self):
+        return np.bincount(self._owners(), minlength=self.world).tolist()
 
     def route_prepare(self, send, capacity):
-        assert capacity >= len(self.staged)
-        owners = np.searchsorted(np.asarray(self.splits[1:]), [j - 1 for (_, j, _, _) in self.staged], side="right")
-        order = np.argsort(owners, kind="stable")
+        owners = self._owners()
         counts = np.bincount(owners, minlength=self.world).tolist()
+        assert capacity >= len(self.staged) - counts[self.rank]
         buf = send.numpy()
-        for k, s in enumerate(order):
-            i, j, v, fl = self.staged[s]
-            buf[2 * k] = ((j - 1) * self.m + (i - 1)) * 4 + fl
-            buf[2 * k + 1] = np.float64(v).view(np.int64)
+        k = 0
+        for d in range(self.world):  # off-rank buckets only, destination after destination, stream order
+            if d == self.rank:
+                continue
+            for s in np.nonzero(owners == d)[0]:
+                i, j, v, fl = self.staged[s]
+                buf[2 * k] = ((j - 1) * self.m + (i - 1)) * 4 + fl
+                buf[2 * k + 1] = np.float64(v).view(np.int64)
+                k += 1
+        self.own = [(i, j - self.col_begin, v, fl) for (i, j, v, fl), o in zip(self.staged, owners) if o == self.rank]
+        self.low, self.high = [], []
         self.staged = []
+        self.routed = True
         return counts
 
-    def route_finish(self, recv, count):
+    def route_finish(self, src, recv, count):
+        assert src != self.rank
         buf = recv.numpy()
-        out = []
+        out = self.low if src < self.rank else self.high
+        assert src < self.rank or True
         for k in range(count):
             key = int(buf[2 * k])
             fl, ij = key % 4, key // 4
             i, j = ij % self.m + 1, ij // self.m + 1
             assert self.col_begin < j <= self.col_begin + self.width, "record routed to the wrong owner"
             out.append((i, j - self.col_begin, float(np.int64(buf[2 * k + 1]).view(np.float64)), fl))
-        self.routed = (self.routed or []) + out  # appends: one call per source rank, in rank order
 
     def flush(self, mode=0):
         before = self.A.nnz
-        for (i, j, v, fl) in self.routed:
+        for (i, j, v, fl) in self.low + self.own + self.high:  # lower ranks, own, higher ranks
             if fl == 0:
                 self.A.updateindex(v, i, j)
             elif fl == 1:
