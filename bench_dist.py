@@ -88,6 +88,8 @@ def run(args, xsb, rank, world, local):
                            f"NCCL all-to-all-v of the interface plane, CSC left sharded")
         cfg["parallelism"] = f"column-slab x{world}"
         cfg["exchange"] = dict(D.last_exchange)
+        cfg["host_phase_ms_last_step"] = dict(zip(["route_count", "copy_out", "all_to_all", "append", "flush", "offsets"],
+                                                  [round(x, 3) for x in D.last_phase_ms]))
         line = {
             "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -65,6 +65,8 @@ struct xsb_matrix
     bool routed = false;             // staged records already went through xsb_route_prepare / xsb_route_finish
     i64 foreign = 0;                 // staged records owned by other ranks (sent; the flush skips them)
     void *route_ws = nullptr;        // tile counts between xsb_route_count and xsb_route_prepare
+    unsigned char *tileflags = nullptr; // slab handles: tiles of the staged records that hold records of other ranks
+    i64 tileflags_cap = 0;
     u64 route_counts[kMaxRanks] = {0};
     i64 route_counted = -1;          // staged count route_counts was taken at
     // regions of the staged records of a slab handle after routing (offsets from stage.front, chunk aligned):
@@ -221,6 +223,8 @@ struct xsb_matrix
             }
         }
         has_assign = false;
+        if (tileflags)
+            cudaMemsetAsync(tileflags, 0, (size_t)tileflags_cap, stream);
     }
     void set_empty_csc()
     {
@@ -274,7 +278,10 @@ struct xsb_matrix
                 st.front = chunk_up(st.front);
         const i64 need = st.front + st.count + extra;
         if (need <= st.cap)
+        {
+            ensure_tileflags(st.cap);
             return;
+        }
         i64 cap = std::max<i64>(need, st.cap + st.cap / 2);
         cap = std::max<i64>(cap, 1024);
         Rec *nb = static_cast<Rec *>(dalloc(sizeof(Rec) * (size_t)cap));
@@ -284,7 +291,25 @@ struct xsb_matrix
         dfree(st.buf);
         st.buf = nb;
         st.cap = cap;
+        ensure_tileflags(cap);
     }
+    // one byte per 2048 staged records, set by the producers (StageFlags) where another rank's record lands
+    void ensure_tileflags(i64 cap_records)
+    {
+        if (L.ownerbits == 0)
+            return;
+        const i64 need = (cap_records >> kRouteTileShift) + 2;
+        if (need <= tileflags_cap)
+            return;
+        unsigned char *nf = static_cast<unsigned char *>(dalloc((size_t)need));
+        XSB_CUDA(cudaMemsetAsync(nf, 0, (size_t)need, stream));
+        if (tileflags)
+            XSB_CUDA(cudaMemcpyAsync(nf, tileflags, (size_t)tileflags_cap, cudaMemcpyDeviceToDevice, stream));
+        dfree(tileflags);
+        tileflags = nf;
+        tileflags_cap = need;
+    }
+    StageFlags stage_flags(int t) const { return StageFlags{n_tid == 1 ? tileflags : nullptr, stage[t].count}; }
 };
 
 namespace {
@@ -913,6 +938,8 @@ static int32_t create_impl(int64_t m, int64_t n_global, int32_t nranks, int32_t 
             L.self = rank;
             for (int r = 0; r <= nranks; ++r)
                 L.splits[r] = splits[r];
+            L.self_lo = splits[rank];
+            L.self_width = (u64)(splits[rank + 1] - splits[rank]);
         }
         KeyLayout Ls = L; // insertion side: global columns in, owner found by pack()
         Ls.cols_global = 1;
@@ -1003,7 +1030,8 @@ int32_t xsb_route_count(xsb_matrix *h, int64_t *send_counts)
         if (st.count > 0 && h->L.ownerbits > 0)
         {
             h->route_ws = h->dalloc(route_workspace_bytes((u64)st.count, h->nranks));
-            route_count(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, h->route_counts, h->lc);
+            route_count(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, h->route_counts, h->lc,
+                        h->tileflags);
         }
         else
             h->route_counts[h->rank] = (u64)st.count;
@@ -1116,6 +1144,7 @@ int32_t xsb_destroy(xsb_matrix *h)
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
     h->dfree(h->route_ws);
+    h->dfree(h->tileflags);
     h->dfree(h->d_scal);
     h->release_cache();
     if (h->h_scal)
@@ -1250,7 +1279,7 @@ int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *
         DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count), dV(h, V, 8 * (size_t)count);
         write_scalar(h, 1, ~0ull);
         pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
-                     h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc);
+                     h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc, h->stage_flags(tid));
         const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
@@ -1478,7 +1507,8 @@ int32_t xsb_emit_fdrand_range(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny
         REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= N, XSB_EINVAL, "bad node range");
         const i64 count = fdrand_prefix(nx, ny, nz, l_end) - fdrand_prefix(nx, ny, nz, l_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        emit_fdrand(h->stream, nx, ny, nz, seed, ones, h->Ls, (u32)tid, (u32)flavour, l_begin, l_end, dst, h->lc);
+        emit_fdrand(h->stream, nx, ny, nz, seed, ones, h->Ls, (u32)tid, (u32)flavour, l_begin, l_end, dst, h->lc,
+                    h->stage_flags(tid));
         end_emit(h, tid, flavour, count);
         return XSB_OK;
     });
@@ -1501,7 +1531,8 @@ int32_t xsb_emit_p1fem_range(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t ny
         REQUIRE(0 <= cz_begin && cz_begin <= cz_end && cz_end <= nzn - 1, XSB_EINVAL, "bad cube-layer range");
         const i64 count = 20 * 6 * (nxn - 1) * (nyn - 1) * (cz_end - cz_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        emit_p1fem(h->stream, nxn, nyn, nzn, h->Ls, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc);
+        emit_p1fem(h->stream, nxn, nyn, nzn, h->Ls, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc,
+                   h->stage_flags(tid));
         end_emit(h, tid, flavour, count);
         return XSB_OK;
     });
@@ -1522,7 +1553,7 @@ int32_t xsb_emit_blockrd(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int
         REQUIRE(h->m == N && h->n_global == N, XSB_ESIZE, "Matrix size mismatch");
         const i64 count = blockrd_count(nx, ny, nz, ns);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        emit_blockrd(h->stream, nx, ny, nz, ns, seed, h->Ls, (u32)tid, (u32)flavour, dst, h->lc);
+        emit_blockrd(h->stream, nx, ny, nz, ns, seed, h->Ls, (u32)tid, (u32)flavour, dst, h->lc, h->stage_flags(tid));
         end_emit(h, tid, flavour, count);
         return XSB_OK;
     });

@@ -47,6 +47,8 @@ struct KeyLayout
     int nranks;
     int self;        // this rank
     int cols_global; // pack() takes global columns (insertion side); 0: slab-local columns owned by self
+    i64 self_lo;     // splits[self] and the width of the own slab: pack()'s fast path
+    u64 self_width;
     i64 splits[kMaxRanks + 1]; // rank r owns columns [splits[r], splits[r+1]), 0-based
     __host__ __device__ __forceinline__ u64 pack(u64 col, u64 row, u32 tid, u32 fl) const
     {
@@ -55,11 +57,20 @@ struct KeyLayout
         {
             if (cols_global)
             {
-                int q = 0;
-                while (q + 1 < nranks && (i64)col >= splits[q + 1])
-                    ++q;
-                col -= (u64)splits[q];
-                o = (u64)q;
+                const u64 rel = col - (u64)self_lo; // a partitioned assembly mostly inserts into its own slab
+                if (rel < self_width)
+                {
+                    col = rel;
+                    o = (u64)self;
+                }
+                else
+                {
+                    int q = 0;
+                    while (q + 1 < nranks && (i64)col >= splits[q + 1])
+                        ++q;
+                    col -= (u64)splits[q];
+                    o = (u64)q;
+                }
             }
             else
                 o = (u64)self;
@@ -68,6 +79,13 @@ struct KeyLayout
         if (ownerbits)
             k |= o << (low + rowbits + colbits);
         return k;
+    }
+    // pack(col,row,tid,fl) == colpart(col) | rowpart(row,tid,fl): producers that reuse a column or a
+    // row for several records (element matrices) build the halves once
+    __host__ __device__ __forceinline__ u64 colpart(u64 col) const { return pack(col, 0, 0u, 0u); }
+    __host__ __device__ __forceinline__ u64 rowpart(u64 row, u32 tid, u32 fl) const
+    {
+        return (row << low) | ((u64)tid << 2) | (u64)fl;
     }
     __host__ __device__ __forceinline__ int ownershift() const { return low + rowbits + colbits; }
     __host__ __device__ __forceinline__ u32 owner(u64 key) const
@@ -174,6 +192,22 @@ __device__ __forceinline__ void st_rec(Rec *p, const Rec &r)
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(r.key),
                  "l"(*reinterpret_cast<const u64 *>(&r.val))
                  : "memory");
+}
+
+// Slab handles: a producer that stages a record owned by another rank marks the tile of the
+// staging buffer it lands in, so that routing only looks at marked tiles (xsb_route.cu).
+constexpr int kRouteTileShift = 11; // tiles of 2048 records
+struct StageFlags
+{
+    unsigned char *flags; // one byte per tile, relative to the first staged record; nullptr: not a slab handle
+    i64 pos0;             // staged records ahead of out0
+};
+__device__ __forceinline__ void st_staged(Rec *p, const Rec &r, const KeyLayout &L, const StageFlags &sf,
+                                          const Rec *out0)
+{
+    st_rec(p, r);
+    if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+        sf.flags[(sf.pos0 + (i64)(p - out0)) >> kRouteTileShift] = 1; // benign race: same value
 }
 
 // Decoupled look-back over per-tile totals (tiles are dispatched in index order): the calling WARP

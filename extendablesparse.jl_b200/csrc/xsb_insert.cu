@@ -18,7 +18,8 @@ namespace xsb {
 template <typename Ti>
 __global__ void __launch_bounds__(256)
 pack_kernel(const Ti *__restrict__ I, const Ti *__restrict__ J, const double *__restrict__ V, i64 count, Ti base,
-            i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out, u64 *__restrict__ d_err)
+            i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out, u64 *__restrict__ d_err,
+            StageFlags sf)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
@@ -32,13 +33,13 @@ pack_kernel(const Ti *__restrict__ I, const Ti *__restrict__ J, const double *__
         Rec r;
         r.key = L.pack((u64)j, (u64)i, tid, flavour);
         r.val = V[k];
-        st_rec(out + k, r);
+        st_staged(out + k, r, L, sf, out);
     }
 }
 
 void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                   int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
-                  LaunchCounter &lc)
+                  LaunchCounter &lc, StageFlags sf)
 {
     if (count <= 0)
         return;
@@ -46,10 +47,10 @@ void pack_records(cudaStream_t stream, const void *I, const void *J, const doubl
     const int blocks = (int)std::min<i64>((count + threads - 1) / threads, (i64)kNumSM * 16);
     if (idx64)
         pack_kernel<int64_t><<<blocks, threads, 0, stream>>>((const int64_t *)I, (const int64_t *)J, V, count,
-                                                             (int64_t)base, m, n, L, tid, flavour, out, d_err);
+                                                             (int64_t)base, m, n, L, tid, flavour, out, d_err, sf);
     else
         pack_kernel<int32_t><<<blocks, threads, 0, stream>>>((const int32_t *)I, (const int32_t *)J, V, count,
-                                                             (int32_t)base, m, n, L, tid, flavour, out, d_err);
+                                                             (int32_t)base, m, n, L, tid, flavour, out, d_err, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }
@@ -177,7 +178,7 @@ constexpr int FD_MAXREC = 15;   // records per node upper bound
 
 __global__ void __launch_bounds__(FD_THREADS)
 emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour, i64 l_begin, i64 l_end,
-                   i64 rec_begin, Rec *__restrict__ out)
+                   i64 rec_begin, Rec *__restrict__ out, StageFlags sf)
 {
     __shared__ Rec s_rec[FD_THREADS * FD_MAXREC];
     const i64 l_first = l_begin + (i64)blockIdx.x * FD_THREADS;
@@ -226,18 +227,18 @@ emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavo
     const i64 nrec = blk_rec1 - blk_rec0;
     Rec *dst = out + (blk_rec0 - rec_begin);
     for (i64 q = threadIdx.x; q < nrec; q += FD_THREADS)
-        st_rec(dst + q, s_rec[q]);
+        st_staged(dst + q, s_rec[q], L, sf, out);
 }
 
 void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid,
-                 u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc)
+                 u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc, StageFlags sf)
 {
     if (l_end <= l_begin)
         return;
     FdGeom g{nx, ny, nz};
     const i64 blocks = (l_end - l_begin + FD_THREADS - 1) / FD_THREADS;
     emit_fdrand_kernel<<<(unsigned)blocks, FD_THREADS, 0, stream>>>(g, seed, ones, L, tid, flavour, l_begin, l_end,
-                                                                    g.before_node<4>(l_begin), out);
+                                                                    g.before_node<4>(l_begin), out, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }
@@ -253,7 +254,7 @@ constexpr int FEM_REC = 20;
 
 __global__ void __launch_bounds__(FEM_THREADS)
 emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
-                  Rec *__restrict__ out)
+                  Rec *__restrict__ out, StageFlags sf)
 {
     __shared__ Rec s_rec[FEM_THREADS * FEM_REC];
     const i64 t_first = tet_begin + (i64)blockIdx.x * FEM_THREADS;
@@ -332,17 +333,24 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
             }
         Rec *dst = s_rec + threadIdx.x * FEM_REC;
         int q = 0;
+        u64 ckey[4], rkey[4]; // a node is the column of 5 and the row of 5 of the element's 20 records
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+        {
+            ckey[v] = L.colpart(node[v]);
+            rkey[v] = L.rowpart(node[v], tid, flavour);
+        }
 #pragma unroll
         for (int il = 0; il < 4; ++il)
         {
             Rec r;
-            r.key = L.pack(node[il], node[il], tid, flavour);
+            r.key = ckey[il] | rkey[il];
             r.val = 0.1 * vol / 4.0;
             dst[q++] = r;
 #pragma unroll
             for (int jl = 0; jl < 4; ++jl)
             {
-                r.key = L.pack(node[jl], node[il], tid, flavour); // A[i,j]: row = node[il], col = node[jl]
+                r.key = ckey[jl] | rkey[il]; // A[i,j]: row = node[il], col = node[jl]
                 r.val = vol * S[il][jl];
                 dst[q++] = r;
             }
@@ -352,11 +360,11 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     const i64 nrec = (t_last - t_first) * FEM_REC;
     Rec *dst = out + (t_first - tet_begin) * FEM_REC;
     for (i64 q = threadIdx.x; q < nrec; q += FEM_THREADS)
-        st_rec(dst + q, s_rec[q]);
+        st_staged(dst + q, s_rec[q], L, sf, out);
 }
 
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
-                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc)
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf)
 {
     const i64 per_layer = 6 * (nxn - 1) * (nyn - 1);
     const i64 tet_begin = cz_begin * per_layer, tet_end = cz_end * per_layer;
@@ -364,7 +372,7 @@ void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32
         return;
     const i64 blocks = (tet_end - tet_begin + FEM_THREADS - 1) / FEM_THREADS;
     emit_p1fem_kernel<<<(unsigned)blocks, FEM_THREADS, 0, stream>>>(nxn, nyn, nzn, L, tid, flavour, tet_begin,
-                                                                    tet_end, out);
+                                                                    tet_end, out, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }
@@ -399,7 +407,7 @@ i64 blockrd_count(i64 nx, i64 ny, i64 nz, i64 ns)
 }
 
 __global__ void __launch_bounds__(256)
-emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out)
+emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out, StageFlags sf)
 {
     const i64 ns2 = g.ns * g.ns;
     const i64 total = g.nx * g.ny * g.nz * ns2;
@@ -428,32 +436,32 @@ emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *
             Rec r;
             r.val = -v;
             r.key = L.pack(jb, ia, tid, flavour); // (-v, i_a, j_b)
-            st_rec(dst + 0, r);
+            st_staged(dst + 0, r, L, sf, out);
             r.key = L.pack(ib, ja, tid, flavour); // (-v, j_a, i_b)
-            st_rec(dst + 1, r);
+            st_staged(dst + 1, r, L, sf, out);
             r.val = v;
             r.key = L.pack(ib, ia, tid, flavour); // ( v, i_a, i_b)
-            st_rec(dst + 2, r);
+            st_staged(dst + 2, r, L, sf, out);
             r.key = L.pack(jb, ja, tid, flavour); // ( v, j_a, j_b)
-            st_rec(dst + 3, r);
+            st_staged(dst + 3, r, L, sf, out);
             rec += 4 * ns2;
             call += (u64)ns2;
         }
         Rec r;
         r.val = philox_uniform(seed, call + (u64)ab);
         r.key = L.pack(ib, ia, tid, flavour);
-        st_rec(out + rec + ab, r);
+        st_staged(out + rec + ab, r, L, sf, out);
     }
 }
 
 void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,
-                  u32 flavour, Rec *out, LaunchCounter &lc)
+                  u32 flavour, Rec *out, LaunchCounter &lc, StageFlags sf)
 {
     RdGeom g{nx, ny, nz, (i64)ns};
     const i64 total = nx * ny * nz * ns * ns;
     const int threads = 256;
     const int blocks = (int)std::min<i64>((total + threads - 1) / threads, (i64)kNumSM * 32);
-    emit_blockrd_kernel<<<blocks, threads, 0, stream>>>(g, seed, L, tid, flavour, out);
+    emit_blockrd_kernel<<<blocks, threads, 0, stream>>>(g, seed, L, tid, flavour, out, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }

@@ -155,8 +155,9 @@ void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, i
 
 // ---- xsb_route.cu
 size_t route_workspace_bytes(u64 n, int nranks);
+// tileflags != nullptr: only tiles whose byte is set can hold records of other ranks (StageFlags)
 void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, u64 *counts_host,
-                 LaunchCounter &lc);
+                 LaunchCounter &lc, const unsigned char *tileflags = nullptr);
 void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace,
                    const u64 *counts_host, Rec *send, LaunchCounter &lc);
 void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayout &L, LaunchCounter &lc);
@@ -172,17 +173,18 @@ void preaggregate_records(cudaStream_t stream, const Rec *in, u64 nrec, const Ke
 // (I,J,V) -> records; *d_err receives the smallest offending index (or ~0)
 void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                   int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
-                  LaunchCounter &lc);
+                  LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
 void unpack_records(cudaStream_t stream, const Rec *in, i64 count, int idx64, int base, KeyLayout L, void *I,
                     void *J, double *V, int *flavour, LaunchCounter &lc);
 i64 fdrand_prefix(i64 nx, i64 ny, i64 nz, i64 l); // records emitted by nodes [0,l)
 void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid,
-                 u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc);
+                 u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc,
+                 StageFlags sf = StageFlags{nullptr, 0});
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
-                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc);
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
 i64 blockrd_count(i64 nx, i64 ny, i64 nz, i64 ns);
 void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,
-                  u32 flavour, Rec *out, LaunchCounter &lc);
+                  u32 flavour, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
 
 // ---- xsb_values.cu
 void zero_values(cudaStream_t stream, double *nzval, i64 nnz, LaunchCounter &lc);

@@ -24,34 +24,56 @@ namespace xsb {
 constexpr int RT_THREADS = 256;
 constexpr int RT_IPT = 8;
 constexpr int RT_TILE = RT_THREADS * RT_IPT;
+static_assert(RT_TILE == (1 << kRouteTileShift), "tile size of the producers' flags");
+
+// A block looks after RT_GROUP consecutive tiles and only reads the ones the producers marked.
+constexpr int RT_GROUP = RT_THREADS;
 
 __global__ void __launch_bounds__(RT_THREADS)
-route_count_kernel(const Rec *__restrict__ in, u64 n, int ownershift, u32 me, int nranks, u32 *__restrict__ tilecnt)
+route_count_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershift, u32 me, int nranks,
+                   u32 *__restrict__ tilecnt, const unsigned char *__restrict__ tileflags)
 {
     __shared__ u32 s_cnt[kMaxRanks];
-    if (threadIdx.x < kMaxRanks)
-        s_cnt[threadIdx.x] = 0;
+    __shared__ u32 s_list[RT_GROUP];
+    __shared__ u32 s_nlist;
+    if (threadIdx.x == 0)
+        s_nlist = 0;
     __syncthreads();
-    const u64 b0 = (u64)blockIdx.x * RT_TILE;
-    bool any = false;
-#pragma unroll
-    for (int i = 0; i < RT_IPT; ++i)
+    { // tiles are dealt out round-robin: the marked ones usually sit next to each other in the stream
+        const u64 t = (u64)threadIdx.x * gridDim.x + blockIdx.x;
+        if (t < ntiles && (tileflags == nullptr || tileflags[t] != 0))
+            s_list[atomicAdd(&s_nlist, 1u)] = (u32)threadIdx.x;
+    }
+    __syncthreads();
+    const u32 nlist = s_nlist;
+    for (u32 q = 0; q < nlist; ++q)
     {
-        const u64 k = b0 + (u64)i * RT_THREADS + threadIdx.x;
-        if (k < n)
+        const u64 tile = (u64)s_list[q] * gridDim.x + blockIdx.x;
+        if (threadIdx.x < kMaxRanks)
+            s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const u64 b0 = tile * RT_TILE;
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < RT_IPT; ++i)
         {
-            const u32 o = (u32)(in[k].key >> ownershift);
-            if (o != me)
+            const u64 k = b0 + (u64)i * RT_THREADS + threadIdx.x;
+            if (k < n)
             {
-                atomicAdd(&s_cnt[o], 1u);
-                any = true;
+                const u32 o = (u32)(in[k].key >> ownershift);
+                if (o != me)
+                {
+                    atomicAdd(&s_cnt[o], 1u);
+                    any = true;
+                }
             }
         }
-    }
-    if (__syncthreads_or(any))
-    {
-        if ((int)threadIdx.x < nranks)
-            tilecnt[(size_t)blockIdx.x * nranks + threadIdx.x] = s_cnt[threadIdx.x];
+        if (__syncthreads_or(any))
+        {
+            if ((int)threadIdx.x < nranks)
+                tilecnt[tile * nranks + threadIdx.x] = s_cnt[threadIdx.x];
+        }
+        __syncthreads();
     }
 }
 
@@ -59,103 +81,117 @@ route_count_kernel(const Rec *__restrict__ in, u64 n, int ownershift, u32 me, in
 // tilecnt holds the raw counts (cnt) and tileoff the scanned offsets: the extract kernel needs both
 __global__ void __launch_bounds__(1024)
 route_scan_kernel(const u32 *__restrict__ tilecnt, u32 *__restrict__ tileoff, u64 ntiles, int nranks,
-                   u64 *__restrict__ total)
+                  u64 *__restrict__ total)
 {
     __shared__ u64 s_w[32];
-    __shared__ u64 s_carry;
     const int d = blockIdx.x;
-    if (threadIdx.x == 0)
-        s_carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u64 b0 = 0; b0 < ntiles; b0 += 1024)
-    {
-        const u64 t = b0 + threadIdx.x;
-        const u64 x = t < ntiles ? (u64)tilecnt[t * nranks + d] : 0ull;
-        u64 v = x;
+    // every thread owns a run of consecutive tiles: one block-wide scan for the whole column
+    const u64 per = (ntiles + 1023) / 1024;
+    const u64 t0 = (u64)threadIdx.x * per, t1 = min(t0 + per, ntiles);
+    u64 sum = 0;
+    for (u64 t = t0; t < t1; ++t)
+        sum += tilecnt[t * nranks + d];
+    u64 v = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const u64 y = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o)
-                v += y;
-        }
-        if (lane == 31)
-            s_w[warp] = v;
-        __syncthreads();
-        u64 pre = s_carry;
-        for (int w = 0; w < warp; ++w)
-            pre += s_w[w];
-        if (t < ntiles)
-            tileoff[t * nranks + d] = (u32)(pre + v - x);
-        __syncthreads();
-        if (threadIdx.x == 1023)
-            s_carry = pre + v;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u64 y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o)
+            v += y;
     }
-    if (threadIdx.x == 0)
-        total[d] = s_carry;
+    if (lane == 31)
+        s_w[warp] = v;
+    __syncthreads();
+    u64 run = v - sum;
+    for (int w = 0; w < warp; ++w)
+        run += s_w[w];
+    for (u64 t = t0; t < t1; ++t)
+    { // offsets of one destination stay below 2^32 (a staging buffer holds < 2^32 records)
+        tileoff[t * nranks + d] = (u32)run;
+        run += tilecnt[t * nranks + d];
+    }
+    if (threadIdx.x == 1023)
+        total[d] = run;
 }
 
 // bucket_base[d] = where rank d's bucket starts in the send buffer
 __global__ void __launch_bounds__(RT_THREADS)
-route_extract_kernel(const Rec *__restrict__ in, u64 n, int ownershift, u32 me, int nranks,
+route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershift, u32 me, int nranks,
                      const u32 *__restrict__ tilecnt, const u32 *__restrict__ tileoff,
                      const u64 *__restrict__ bucket_base, Rec *__restrict__ send)
 {
     __shared__ u32 s_w[RT_THREADS / 32];
     __shared__ u32 s_run;
-    const u32 *cnt = tilecnt + (size_t)blockIdx.x * nranks;
-    u32 has = 0;
-    for (int d = 0; d < nranks; ++d)
-        has |= cnt[d];
-    if (!has)
-        return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u64 b0 = (u64)blockIdx.x * RT_TILE;
-    Rec r[RT_IPT];
-    u32 own[RT_IPT];
-#pragma unroll
-    for (int i = 0; i < RT_IPT; ++i)
+    __shared__ u32 s_list[RT_GROUP];
+    __shared__ u32 s_nlist;
+    if (threadIdx.x == 0)
+        s_nlist = 0;
+    __syncthreads();
     {
-        const u64 k = b0 + (u64)i * RT_THREADS + threadIdx.x;
-        own[i] = me;
-        if (k < n)
+        const u64 t = (u64)threadIdx.x * gridDim.x + blockIdx.x;
+        if (t < ntiles)
         {
-            r[i] = in[k];
-            own[i] = (u32)(r[i].key >> ownershift);
+            u32 has = 0;
+            for (int d = 0; d < nranks; ++d)
+                has |= tilecnt[t * nranks + d];
+            if (has)
+                s_list[atomicAdd(&s_nlist, 1u)] = (u32)threadIdx.x;
         }
     }
-    for (int d = 0; d < nranks; ++d)
+    __syncthreads();
+    const u32 nlist = s_nlist;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 q = 0; q < nlist; ++q)
     {
-        if (cnt[d] == 0u) // uniform over the block
-            continue;
-        if (threadIdx.x == 0)
-            s_run = 0;
-        __syncthreads();
-        Rec *dst = send + bucket_base[d] + tileoff[(size_t)blockIdx.x * nranks + d];
+        const u64 tile = (u64)s_list[q] * gridDim.x + blockIdx.x;
+        const u32 *cnt = tilecnt + tile * nranks;
+        const u64 b0 = tile * RT_TILE;
+        Rec r[RT_IPT];
+        u32 own[RT_IPT];
 #pragma unroll
         for (int i = 0; i < RT_IPT; ++i)
-        { // round i holds RT_THREADS consecutive records: rank them in thread order
-            const bool mine = own[i] == (u32)d && (u32)d != me;
-            const u32 bal = __ballot_sync(0xffffffffu, mine);
-            if (lane == 0)
-                s_w[warp] = __popc(bal);
-            __syncthreads();
-            u32 pre = s_run;
-            for (int w = 0; w < warp; ++w)
-                pre += s_w[w];
-            if (mine)
-                st_rec(dst + pre + __popc(bal & lanemask_lt()), r[i]);
+        {
+            const u64 k = b0 + (u64)i * RT_THREADS + threadIdx.x;
+            own[i] = me;
+            if (k < n)
+            {
+                r[i] = in[k];
+                own[i] = (u32)(r[i].key >> ownershift);
+            }
+        }
+        for (int d = 0; d < nranks; ++d)
+        {
+            if (cnt[d] == 0u) // uniform over the block
+                continue;
             __syncthreads();
             if (threadIdx.x == 0)
-            {
-                u32 t = 0;
-                for (int w = 0; w < RT_THREADS / 32; ++w)
-                    t += s_w[w];
-                s_run += t;
-            }
+                s_run = 0;
             __syncthreads();
+            Rec *dst = send + bucket_base[d] + tileoff[tile * nranks + d];
+#pragma unroll
+            for (int i = 0; i < RT_IPT; ++i)
+            { // round i holds RT_THREADS consecutive records: rank them in thread order
+                const bool mine = own[i] == (u32)d && (u32)d != me;
+                const u32 bal = __ballot_sync(0xffffffffu, mine);
+                if (lane == 0)
+                    s_w[warp] = __popc(bal);
+                __syncthreads();
+                u32 pre = s_run;
+                for (int w = 0; w < warp; ++w)
+                    pre += s_w[w];
+                if (mine)
+                    st_rec(dst + pre + __popc(bal & lanemask_lt()), r[i]);
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    u32 t = 0;
+                    for (int w = 0; w < RT_THREADS / 32; ++w)
+                        t += s_w[w];
+                    s_run += t;
+                }
+                __syncthreads();
+            }
         }
     }
 }
@@ -207,7 +243,7 @@ size_t route_workspace_bytes(u64 n, int nranks)
 
 // counts_host[d] = staged records owned by rank d (d == me: the ones that stay)
 void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, u64 *counts_host,
-                 LaunchCounter &lc)
+                 LaunchCounter &lc, const unsigned char *tileflags)
 {
     const int nr = L.nranks;
     for (int d = 0; d < nr; ++d)
@@ -219,7 +255,8 @@ void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, 
     u32 *tileoff = tilecnt + (size_t)ntiles * nr;
     u64 *total = reinterpret_cast<u64 *>(tileoff + (size_t)ntiles * nr);
     XSB_CUDA(cudaMemsetAsync(tilecnt, 0, sizeof(u32) * (size_t)ntiles * nr, stream));
-    route_count_kernel<<<(unsigned)ntiles, RT_THREADS, 0, stream>>>(in, n, L.ownershift(), (u32)L.self, nr, tilecnt);
+    route_count_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+        in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileflags);
     route_scan_kernel<<<nr, 1024, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total);
     lc.add(2);
     XSB_CUDA(cudaGetLastError());
@@ -259,8 +296,8 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
     if (run == 0)
         return;
     XSB_CUDA(cudaMemcpyAsync(bucket_base, hb, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
-    route_extract_kernel<<<(unsigned)ntiles, RT_THREADS, 0, stream>>>(in, n, L.ownershift(), (u32)L.self, nr, tilecnt,
-                                                                      tileoff, bucket_base, send);
+    route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+        in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, send);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     XSB_CUDA(cudaStreamSynchronize(stream)); // hb lives on this stack frame

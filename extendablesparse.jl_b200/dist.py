@@ -90,6 +90,7 @@ class DistExtendableSparseMatrix:
         self.nnz_global = 0
         self.last_exchange = {"sent_off_rank": 0, "received_off_rank": 0, "kept": 0}
         self._send = None
+        self.last_phase_ms = []
 
     # insertion: global (i,j) on any rank
     def insert_batch(self, I, J, V, flavour=0):
@@ -103,29 +104,44 @@ class DistExtendableSparseMatrix:
 
     def flush(self, mode=0):
         """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank)."""
+        import time
+
+        t = [time.perf_counter()]
+
+        def lap():
+            t.append(time.perf_counter())
+
         cnt = int(self.h.pending)
         counts = self.h.route_count()
+        lap()
         leaving = sum(c for r, c in enumerate(counts) if r != self.rank)
         send = self._send_buffer(leaving)
         self.h.route_prepare(send, leaving)
+        lap()
         recv, rcounts = exchange_off_rank(send, counts, self.rank, self.group)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
+        lap()
         pos = 0
         for src in range(self.world):  # ascending source rank; the own records stayed where they were
             if src != self.rank:
                 self.h.route_finish(src, recv[2 * pos: 2 * (pos + rcounts[src])], rcounts[src])
                 pos += rcounts[src]
+        lap()
         nnz, changed = self.h.flush(mode)
+        lap()
         # one 16-byte all-gather: entries per slab (-> global colptr offsets) and "pattern changed"
         mine = torch.tensor([nnz, int(changed)], dtype=torch.int64, device=self.device)
         allv = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(allv, mine, group=self.group)
         allv = allv.cpu().tolist()
+        lap()
         per_rank, flags = allv[0::2], allv[1::2]
         self.nnz_offset, self.nnz_global = sum(per_rank[: self.rank]), sum(per_rank)
         self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received_off_rank": sum(rcounts),
                               "kept": counts[self.rank]}
+        # host wall time of the phases (ms): count, copy-out, all-to-all, append, flush, offsets
+        self.last_phase_ms = [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
         return nnz, any(flags)
 
     def global_colptr(self, local_colptr):
