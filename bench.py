@@ -332,6 +332,10 @@ def main():
     ap.add_argument("--ref-mesh", type=int, default=64, help="mesh of one --impl reference step (bounded sample)")
     ap.add_argument("--mode", default="deterministic", choices=["deterministic", "fast"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="fem", choices=["fem", "fd400"],
+                    help="N>1 only: fem = weak scaling of configs[1] (default, the bench line); fd400 = configs[4], "
+                         "fdrand 400^3 sharded by node slab over the ranks (strong scaling, no e2e leg)")
+    ap.add_argument("--fd-n", type=int, default=400, help="grid points per direction of --workload fd400")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per onesweep launch, if known")
     args = ap.parse_args()
     args.steps = max(1, args.steps)

@@ -20,10 +20,17 @@ import torch.distributed as dist
 def run(args, xsb, rank, world, local):
     import bench
 
+    # watchdog: a rank stuck in a collective dumps its Python stack and exits instead of hanging the box
+    import faulthandler
+    import sys
+
+    faulthandler.dump_traceback_later(int(os.environ.get("XSB_BENCH_WATCHDOG_S", "240")), exit=True, file=sys.stderr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from xsparse_b200 import dist as xd
 
     dev = torch.device("cuda", local)
+    if getattr(args, "workload", "fem") == "fd400":
+        return run_fd(args, xsb, xd, bench, rank, world, local, dev)
     nx = ny = args.mesh
     layers = args.mesh - 1
     nz_nodes = layers * world + 1
@@ -102,6 +109,7 @@ def run(args, xsb, rank, world, local):
     h.close()
     dist.barrier()
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
 
 
 def measure_e2e(args, xsb, xd, rank, world, local, mode):
@@ -163,3 +171,60 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
             "d2h_bytes_per_step": int(tot[2].item()), "ms_per_step": ms,
             "workload": f"P1-FEM {emesh}x{emesh}x{nz_nodes}-node mesh over {world} ranks, (I,J,V) from pinned host, "
                         f"CSC slabs read back to host"}
+
+
+def run_fd(args, xsb, xd, bench, rank, world, local, dev):
+    """BASELINE.json configs[4]: fdrand 3-D n^3 (n = 400: 64 M unknowns, 767 M updateindex! calls, 447 M
+    nnz), generation sharded by node slab, columns owned by the same slabs, STRONG scaling.  Only the
+    (l, l + nx*ny) couplings that straddle a slab face change owner."""
+    n1 = args.fd_n
+    N = n1 ** 3
+    splits = [N * r // world for r in range(world)] + [N]
+    mode = xsb.DETERMINISTIC if args.mode == "deterministic" else xsb.FAST
+    D = xd.DistExtendableSparseMatrix(N, N, splits=splits, device=local)
+    h = D.h
+    h.set_profiling(True)
+    n_ins = xsb.capi.stream_count_fdrand(n1, n1, n1)
+
+    def step():
+        h.reset()
+        h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=(splits[rank], splits[rank + 1]))
+        return D.flush(mode)
+
+    for _ in range(args.warmup):
+        step()
+    h.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    h.timer_start()
+    for _ in range(args.steps):
+        nnz, _ = step()
+    ms_local = h.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    st = h.flush_stats()
+    if rank == 0:
+        peak, _ = bench.peaks()
+        b_flush = bench.flush_bytes(n_ins, 0, int(D.nnz_global), N)
+        line = {"metric": bench.METRIC, "value": n_ins / (ms_step / 1e3), "unit": bench.UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"fdrand 3-D {n1}^3 (BASELINE.json configs[4]), node-slab generation and column-slab "
+                                       f"ownership over {world} ranks, updateindex! stream + flush!, CSC left sharded",
+                           "mode": args.mode, "exchange": dict(D.last_exchange),
+                           "host_phase_ms_last_step": [round(x, 3) for x in D.last_phase_ms]},
+                "flush_rank0": {"ms": st["ms_total"], "column_path": st["column_path"], "n_inserted": st["n_inserted"],
+                                "nnz_new": st["nnz_new"]},
+                "whole_job_flush_fraction_of_hbm_peak": b_flush / (ms_step / 1e3) / 1e9 / (peak * world),
+                "nnz_global": int(D.nnz_global), "n_inserted": int(n_ins)}
+        print(json.dumps(line))
+    h.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    import faulthandler
+
+    faulthandler.cancel_dump_traceback_later()

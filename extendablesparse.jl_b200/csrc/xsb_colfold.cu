@@ -828,7 +828,8 @@ colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u3
                         const u32 *__restrict__ nzcol, const u32 *__restrict__ nzstart,
                         const u64 *__restrict__ totals, i64 ncols, Ti base, Ti *__restrict__ rowval,
                         double *__restrict__ nzval, Ti *__restrict__ colptr, u64 *__restrict__ status,
-                        u64 *__restrict__ d_nnz, u32 *__restrict__ d_redo, u32 *__restrict__ maxd)
+                        u32 *__restrict__ ticket, u64 *__restrict__ d_nnz, u32 *__restrict__ d_redo,
+                        u32 *__restrict__ maxd)
 {
     constexpr int H = CtShape<HBITS>::H;
     constexpr u32 D = CtShape<HBITS>::D;
@@ -836,6 +837,13 @@ colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_wsum[CT_WARPS];
     __shared__ u64 s_prefix;
+    __shared__ u32 s_bid;
+    // blocks take their columns in the order they START (ticket), so a block only ever waits for
+    // blocks that are already running: the look-back cannot starve whatever the dispatch order
+    if (threadIdx.x == 0)
+        s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 bid = s_bid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane;
     u32 *key = reinterpret_cast<u32 *>(smem_raw + (size_t)CT_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
@@ -843,7 +851,7 @@ colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u3
                 warp * (D * 32) + lane;
     const u32 rowmask = (1u << rowbits) - 1u;
     const u64 K = totals[1];
-    const u64 k = (u64)blockIdx.x * (CT_WARPS * 32) + threadIdx.x;
+    const u64 k = (u64)bid * (CT_WARPS * 32) + threadIdx.x;
     int j = 0;
     u32 cstart = 0;
     if (k < K && ld_relaxed_u32(d_redo) == 0u)
@@ -888,7 +896,7 @@ colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u3
     }
     if (warp == 0)
     {
-        const u64 prefix = warp_lookback(status, blockIdx.x, (u64)btotal, lane);
+        const u64 prefix = warp_lookback(status, bid, (u64)btotal, lane);
         if (lane == 0)
             s_prefix = prefix;
     }
@@ -1165,7 +1173,7 @@ CfLayout cf_layout(u64 nrec, i64 ncols)
     l.off_list = o; // columns left over by the thread-per-column kernels: two hand-over lists + the long columns
     o = up(o + 3 * sizeof(u32) * (kmax + 1));
     l.off_status = o; // look-back words of the one-pass fold, one per block of CT_WARPS*32 columns
-    o = up(o + sizeof(u64) * ((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32) + 1));
+    o = up(o + sizeof(u64) * ((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32) + 2));
     l.bytes = o;
     return l;
 }
@@ -1207,7 +1215,7 @@ namespace {
 template <int HBITS, typename Ti>
 void launch_direct_t(cudaStream_t stream, unsigned blocks, const Rec *sorted, int low, int rowbits, u32 maxlen,
                      const u32 *nzcol, const u32 *nzstart, const u64 *totals, i64 ncols, i64 base, void *rowval,
-                     double *nzval, void *colptr, u64 *status, u64 *d_nnz, u32 *d_redo, u32 *maxd)
+                     double *nzval, void *colptr, u64 *status, u32 *ticket, u64 *d_nnz, u32 *d_redo, u32 *maxd)
 {
     constexpr size_t smem = CT_WARPS * CtShape<HBITS>::kBytesPerWarp;
     static bool attr = false;
@@ -1220,7 +1228,7 @@ void launch_direct_t(cudaStream_t stream, unsigned blocks, const Rec *sorted, in
     }
     colthread_direct_kernel<HBITS, Ti><<<blocks, CT_WARPS * 32, smem, stream>>>(
         sorted, low, rowbits, maxlen, nzcol, nzstart, totals, ncols, (Ti)base, (Ti *)rowval, nzval, (Ti *)colptr, status,
-        d_nnz, d_redo, maxd);
+        ticket, d_nnz, d_redo, maxd);
 }
 } // namespace
 
@@ -1253,7 +1261,8 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         timer->begin(stream);
     XSB_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(u32), stream));
     XSB_CUDA(cudaMemsetAsync(d_maxd, 0, sizeof(u32), stream));
-    XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * ((size_t)blocks + 1), stream));
+    XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * ((size_t)blocks + 2), stream)); // look-back words + ticket
+    u32 *ticket = reinterpret_cast<u32 *>(status + blocks + 1);
     if (!lists_ready)
     {
         colscan_tilesum_kernel<<<ctiles, CS_THREADS, 0, stream>>>(cnt, ncols, trec, tnz);
@@ -1272,7 +1281,7 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     const u32 maxlen = (u32)std::max<u64>(256, 6 * avg);
 #define XSB_DIRECT(HB, TI)                                                                                              \
     launch_direct_t<HB, TI>(stream, blocks, sorted, L.low, L.rowbits, maxlen, nzcol, nzstart, totals, ncols, base,      \
-                            rowval_out, nzval_out, colptr_out, status, d_nnz, d_redo, d_maxd)
+                            rowval_out, nzval_out, colptr_out, status, ticket, d_nnz, d_redo, d_maxd)
     if (idx64)
     {
         if (level == 0)
