@@ -125,6 +125,7 @@ SIGNATURES = {
     "xsb_timer_stop": (_i32, [_p, C.POINTER(C.c_float)]),
     "xsb_set_profiling": (_i32, [_p, _i32]),
     "xsb_set_strategy": (_i32, [_p, _i32]),
+    "xsb_mul": (_i32, [_p, _p, _p]),
     "xsb_set_grouping": (_i32, [_p, _i32]),
     "xsb_set_preaggregation": (_i32, [_p, _i32]),
     "xsb_get_flush_stats": (_i32, [_p, C.POINTER(FlushStats)]),
@@ -336,6 +337,15 @@ class Handle:
     def eliminate_dirichlet(self, marker):
         mk = np.ascontiguousarray(marker, np.uint8) if not hasattr(marker, "data_ptr") else marker
         self._c(lib().xsb_eliminate_dirichlet(self._h, ptr(mk)))
+
+    def mul(self, x, y=None):
+        """y = A*x on the resident CSC (numpy arrays or torch tensors, host or device)."""
+        if y is None:
+            y = np.empty(self.m, np.float64)
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, np.float64)
+        self._c(lib().xsb_mul(self._h, ptr(x), ptr(y)))
+        return y
 
     def pattern_hash(self) -> int:
         v = _u64(0)

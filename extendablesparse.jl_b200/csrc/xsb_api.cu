@@ -94,6 +94,7 @@ struct xsb_matrix
     u32 *f_perm = nullptr;
     i64 *f_segstart = nullptr;
 
+    u32 *csr_map = nullptr; // row-major view of the resident pattern for xsb_mul (rebuilt when the pattern changes)
     u64 *d_scal = nullptr; // 8 device scalars
     u64 *h_scal = nullptr; // pinned mirror
 
@@ -193,6 +194,8 @@ struct xsb_matrix
     }
     void drop_frozen()
     {
+        dfree(csr_map);
+        csr_map = nullptr;
         dfree(f_slot);
         dfree(f_perm);
         dfree(f_segstart);
@@ -1457,6 +1460,36 @@ int32_t xsb_eliminate_dirichlet(xsb_matrix *h, const uint8_t *marker)
         DevIn dM(h, marker, (size_t)h->n);
         eliminate_dirichlet(h->stream, h->view(), h->n, h->idx64, h->base, static_cast<const unsigned char *>(dM.ptr),
                             h->lc);
+        h->sync();
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_mul(xsb_matrix *h, const void *x, void *y)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && x && y, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->pending() == 0, XSB_ESTATE, "staged insertions are pending: flush first");
+        REQUIRE(h->nnz < (1ll << 32) && h->m < (1ll << 32) - 1 && h->n < (1ll << 32), XSB_EINVAL,
+                "matrix too large for the 32-bit row-major map");
+        cudaStream_t s = h->stream;
+        if (!h->csr_map)
+        { // once per pattern
+            h->csr_map = static_cast<u32 *>(h->dalloc(csr_map_bytes(h->m, h->nnz)));
+            const size_t cnt = (size_t)std::max<i64>(h->nnz, 1);
+            Rec *ta = static_cast<Rec *>(h->dalloc(sizeof(Rec) * cnt));
+            Rec *tb = static_cast<Rec *>(h->dalloc(sizeof(Rec) * cnt));
+            void *ws = h->dalloc(sort_workspace_bytes((u64)cnt));
+            build_csr_map(s, h->view(), h->m, h->n, h->idx64, h->base, ta, tb, ws, h->csr_map, h->lc);
+            h->dfree(ws);
+            h->dfree(tb);
+            h->dfree(ta);
+        }
+        DevIn dx(h, x, sizeof(double) * (size_t)h->n);
+        DevOut dy(h, y, sizeof(double) * (size_t)h->m);
+        csr_mul(s, h->csr_map, h->m, h->nnz, h->nzval, static_cast<const double *>(dx.ptr), static_cast<double *>(dy.ptr),
+                h->lc);
+        dy.finish();
         h->sync();
         return XSB_OK;
     });

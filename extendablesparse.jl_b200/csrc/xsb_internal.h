@@ -207,4 +207,11 @@ void eliminate_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx
                          const unsigned char *marker, LaunchCounter &lc);
 void pattern_hash(cudaStream_t stream, const CscView &csc, i64 n, int idx64, u64 *d_hash, LaunchCounter &lc);
 
+// ---- xsb_mul.cu
+size_t csr_map_bytes(i64 m, i64 nnz);
+void build_csr_map(cudaStream_t stream, const CscView &csc, i64 m, i64 n, int idx64, int base, Rec *tags_a, Rec *tags_b,
+                   void *sort_ws, u32 *map, LaunchCounter &lc);
+void csr_mul(cudaStream_t stream, const u32 *map, i64 m, i64 nnz, const double *nzval, const double *x, double *y,
+             LaunchCounter &lc);
+
 } // namespace xsb

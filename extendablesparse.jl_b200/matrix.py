@@ -135,6 +135,14 @@ class ExtendableSparseMatrix:
         cp, rv, nz = self.csc()
         return sp.csc_matrix((nz, rv - 1, cp - 1), shape=(self.m, self.n))
 
+    def mul(self, x):
+        """A*x: flush, then the column-order kernel (abstractextendablesparsematrixcsc.jl:170-181)."""
+        self.flush()
+        return self._h.mul(np.ascontiguousarray(x, np.float64))
+
+    def __matmul__(self, x):
+        return self.mul(x)
+
     @property
     def nnz(self):
         self.flush()  # abstractextendablesparsematrixcsc.jl:24

@@ -210,6 +210,14 @@ int32_t xsb_freeze_pattern(xsb_matrix *h, const void *I, const void *J, int64_t 
 int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32_t mode);
 int32_t xsb_unfreeze(xsb_matrix *h);
 
+/* y = A*x on the resident CSC (x: n values, y: m values; host or device pointers).  mul!(r,A,x):
+ * src/matrix/abstractextendablesparsematrixcsc.jl:170-181 (flush, then the stdlib kernel: columns
+ * ascending, y[rowval[k]] += nzval[k]*x[j]).  Every y[i] is that left fold in column order with
+ * separately rounded products: bit-identical to the reference.  The row-major view of the pattern
+ * it needs is built on first use and dropped when a flush changes the pattern.  On a slab handle
+ * x holds the slab's columns and y is the slab's contribution (sum over the ranks = A*x). */
+int32_t xsb_mul(xsb_matrix *h, const void *x, void *y);
+
 /* ------------------------------------------------------------------ */
 /* values-only passes over the resident CSC                            */
 /* ------------------------------------------------------------------ */

@@ -492,6 +492,82 @@ def test_get_values_and_pattern_hash(xsb, oracle):
     assert h.flush()[1] is True and h.pattern_hash() != h0  # new entry changes it (test_lu.jl:33-45)
 
 
+def reference_mul(cp, rv, nz, x, m):
+    """The stdlib kernel behind mul!(y, A, x): columns ascending, y[rowval[k]] += nzval[k] * x[j]."""
+    y = np.zeros(m)
+    for j in range(len(cp) - 1):
+        xj = x[j]
+        for k in range(cp[j] - 1, cp[j + 1] - 1):
+            y[rv[k] - 1] += nz[k] * xj
+    return y
+
+
+def test_mul_bit_exact_and_tracks_the_matrix(xsb, oracle):
+    """y = A*x: bit-identical to the reference's column-order kernel, follows
+    values-only updates without rebuilding its row-major view, rebuilds it when the pattern grows,
+    handles empty rows/columns and a rectangular matrix."""
+    rng = np.random.default_rng(12)
+    m, n, cnt = 700, 500, 30000
+    I = rng.integers(1, m + 1, cnt)
+    J = rng.integers(1, n + 1, cnt)
+    I[I % 50 == 0] = 1  # rows 50, 100, ... stay empty
+    J[J % 40 == 0] = 2  # columns 40, 80, ... stay empty
+    V = rng.standard_normal(cnt)
+    h = xsb.Handle(m, n)
+    x = rng.standard_normal(n)
+    assert np.array_equal(h.mul(x), np.zeros(m))  # empty matrix
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    with pytest.raises(xsb.XsbError):
+        h.mul(x)  # pending inserts: flush first
+    h.flush()
+    cp, rv, nz = h.fetch_csc_numpy()
+    y = h.mul(x)
+    assert np.array_equal(bits(y), bits(reference_mul(cp, rv, nz, x, m)))
+    S = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(m, n))
+    assert np.allclose(y, S @ x, rtol=1e-12, atol=1e-12)
+    # same pattern, new values
+    h.insert_batch(I[:5000], J[:5000], V[:5000], xsb.UPDATE)
+    assert h.flush()[1] is False
+    cp2, rv2, nz2 = h.fetch_csc_numpy()
+    assert np.array_equal(bits(h.mul(x)), bits(reference_mul(cp2, rv2, nz2, x, m)))
+    # pattern grows: the view is rebuilt
+    h.insert_batch(np.array([50, 100]), np.array([40, 80]), np.array([2.5, -1.0]), xsb.UPDATE)
+    assert h.flush()[1] is True
+    cp3, rv3, nz3 = h.fetch_csc_numpy()
+    y3 = h.mul(x)
+    assert np.array_equal(bits(y3), bits(reference_mul(cp3, rv3, nz3, x, m)))
+    assert y3[49] == 2.5 * x[39]
+    # Int32 / 0-based handle and the host mirror
+    g = xsb.Handle(m, n, idx_type=xsb.capi.I32, index_base=0)
+    g.insert_batch((I - 1).astype(np.int32), (J - 1).astype(np.int32), V, xsb.UPDATE)
+    g.flush()
+    assert np.array_equal(bits(g.mul(x)), bits(y))
+    A = xsb.ExtendableSparseMatrix(30, 30)
+    xsb.fdrand(A, 30, 1, 1, rand=lambda: 1.0)
+    assert np.allclose(A @ np.ones(30), A.sparse() @ np.ones(30))
+
+
+def test_mul_slab_contributions_add_up(xsb):
+    torch = pytest.importorskip("torch")
+    nx = 20
+    N = nx ** 3
+    world = 3
+    splits = [0, 3000, 5500, N]
+    full = xsb.Handle(N, N)
+    full.emit_fdrand(nx, nx, nx, seed=9)
+    full.flush()
+    x = np.random.default_rng(3).standard_normal(N)
+    y = full.mul(x)
+    from tests.test_gpu_dist import route_and_flush
+
+    handles = [xsb.Handle(N, N, slab=(world, r, splits)) for r in range(world)]
+    for r, h in enumerate(handles):
+        h.emit_fdrand(nx, nx, nx, seed=9, l_range=(splits[r], splits[r + 1]))
+    route_and_flush(xsb, torch, handles)
+    parts = [h.mul(x[splits[r]:splits[r + 1]]) for r, h in enumerate(handles)]
+    assert np.allclose(sum(parts), y, rtol=1e-13, atol=1e-13)
+
+
 def test_reset_and_reuse(xsb, oracle):
     h = xsb.Handle(50, 50)
     I, J, V = oracle.fdrand_stream(50, 1, 1, seed=4)
