@@ -251,12 +251,15 @@ __constant__ int c_kuhn[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2,
 
 constexpr int FEM_THREADS = 128;
 constexpr int FEM_REC = 20;
+constexpr int FEM_PITCH = FEM_REC + 1;
 
 __global__ void __launch_bounds__(FEM_THREADS)
 emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
                   Rec *__restrict__ out, StageFlags sf)
 {
-    __shared__ Rec s_rec[FEM_THREADS * FEM_REC];
+    // a thread's 20 records sit FEM_PITCH records apart: with a pitch of 21 (84 words) the 16-byte
+    // stores of a quarter warp fall into eight different bank groups instead of two
+    __shared__ Rec s_rec[FEM_THREADS * FEM_PITCH];
     const i64 t_first = tet_begin + (i64)blockIdx.x * FEM_THREADS;
     const i64 t_last = min(t_first + FEM_THREADS, tet_end);
     const i64 t = t_first + threadIdx.x;
@@ -331,7 +334,7 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
                 S[il][jl] = s;
                 S[jl][il] = s;
             }
-        Rec *dst = s_rec + threadIdx.x * FEM_REC;
+        Rec *dst = s_rec + threadIdx.x * FEM_PITCH;
         int q = 0;
         u64 ckey[4], rkey[4]; // a node is the column of 5 and the row of 5 of the element's 20 records
 #pragma unroll
@@ -360,7 +363,10 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     const i64 nrec = (t_last - t_first) * FEM_REC;
     Rec *dst = out + (t_first - tet_begin) * FEM_REC;
     for (i64 q = threadIdx.x; q < nrec; q += FEM_THREADS)
-        st_staged(dst + q, s_rec[q], L, sf, out);
+    {
+        const int t = (int)q / FEM_REC;
+        st_staged(dst + q, s_rec[t * FEM_PITCH + ((int)q - t * FEM_REC)], L, sf, out);
+    }
 }
 
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
