@@ -46,6 +46,58 @@ struct CountSpace
 // ------------------------------------------------------------------------
 // pass 1: distinct columns of every chunk and their record counts
 // ------------------------------------------------------------------------
+// One batch of 32 consecutive records.  FULL: every lane holds a record that takes part (whole
+// chunk, no records of other ranks to skip).
+template <bool FULL>
+__device__ __forceinline__ void count_batch(CountSpace &ws, u64 key, bool valid, int colshift, u32 colmask, u32 lt,
+                                            u32 &d)
+{
+    constexpr u32 full = 0xffffffffu;
+    const u32 col = (u32)(key >> colshift) & colmask;
+    u32 peers;
+    if (FULL)
+        peers = __match_any_sync(full, col);
+    else
+    {
+        const u32 vm = __ballot_sync(full, valid);
+        peers = 0;
+        if (valid)
+            peers = __match_any_sync(vm, col);
+    }
+    // the FIRST lane that holds a column speaks for it: the table sees one request per distinct column
+    const bool leader = (FULL || valid) && (peers & lt) == 0u;
+    u32 slot = gp_hash(col);
+    bool fresh = false;
+    if (leader)
+    {
+        for (;;)
+        { // a plain look first: after a few batches nearly every column of the chunk is in the table
+            u32 k = ws.key[slot];
+            if (k == col)
+                break;
+            if (k == GP_EMPTY)
+            {
+                k = atomicCAS(&ws.key[slot], GP_EMPTY, col);
+                if (k == GP_EMPTY)
+                {
+                    fresh = true;
+                    break;
+                }
+                if (k == col)
+                    break;
+            }
+            slot = (slot + 1) & (GP_H - 1);
+        }
+    }
+    const u32 rb = __ballot_sync(full, fresh);
+    if (fresh)
+        ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
+    d += __popc(rb);
+    if (leader)
+        ws.cnt[slot] += (u32)__popc(peers); // leaders hold distinct slots of a warp-private table
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(GP_WARPS * 32, 5)
 group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, int ownershift, u32 me,
                    u32 nchunks, u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
@@ -76,73 +128,71 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
 
     u32 d = 0;
     bool crowded = false;
-    u64 key[4], nkey[4];
+    const Rec *rec = in + r0 + lane;
+    if (cnt_here == (u32)GP_W && ownershift < 0)
+    { // whole chunk, every record takes part: no validity bookkeeping
+        u64 key[4], nkey[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-        const u32 p = i * 32 + lane;
-        nkey[i] = p < cnt_here ? in[r0 + p].key : 0ull;
-    }
+        for (int i = 0; i < 4; ++i)
+            nkey[i] = rec[i * 32].key;
 #pragma unroll 1
-    for (int g = 0; g < GP_NB && !crowded; g += 4)
-    {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int g = 0; g < GP_NB && !crowded; g += 4)
         {
-            key[i] = nkey[i];
-            const u32 p = (g + 4 + i) * 32 + lane; // the next group's keys travel while this one is ranked
-            nkey[i] = p < cnt_here ? in[r0 + p].key : 0ull;
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            const u32 bb = (g + i) * 32;
-            if (bb < cnt_here && !crowded) // warp-uniform
+            for (int i = 0; i < 4; ++i)
             {
-                if (d > (u32)GP_DMAX)
+                key[i] = nkey[i];
+                if (g + 4 < GP_NB) // the next group's keys travel while this one is counted
+                    nkey[i] = rec[(g + 4 + i) * 32].key;
+            }
+            if (d > (u32)GP_DMAX - 96u)
+                crowded = true; // the table may not take another 4 x 32 columns
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    count_batch<true>(ws, key[i], true, colshift, colmask, lt, d);
+            }
+        }
+    }
+    else
+    {
+        u64 key[4], nkey[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const u32 p = i * 32 + lane;
+            nkey[i] = p < cnt_here ? rec[i * 32].key : 0ull;
+        }
+#pragma unroll 1
+        for (int g = 0; g < GP_NB && !crowded; g += 4)
+        {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                key[i] = nkey[i];
+                const u32 p = (g + 4 + i) * 32 + lane;
+                nkey[i] = p < cnt_here ? rec[(g + 4 + i) * 32].key : 0ull;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const u32 bb = (g + i) * 32;
+                if (bb < cnt_here && !crowded) // warp-uniform
                 {
-                    crowded = true; // the table may not take another 32 columns
-                }
-                else
-                {
-                    // records owned by another rank (slab handles: already sent) do not take part
-                    const bool valid = bb + lane < cnt_here && (ownershift < 0 || (u32)(key[i] >> ownershift) == me);
-                    const u32 col = (u32)(key[i] >> colshift) & colmask;
-                    const u32 vm = __ballot_sync(full, valid);
-                    u32 peers = 0;
-                    if (valid)
-                        peers = __match_any_sync(vm, col);
-                    // the FIRST lane that holds a column speaks for it: the order of the chunk's column
-                    // list does not depend on timing, and the table sees one request per distinct column
-                    const bool leader = valid && (peers & lt) == 0u;
-                    u32 slot = gp_hash(col);
-                    bool fresh = false;
-                    if (leader)
-                    {
-                        for (;;)
-                        {
-                            const u32 prev = atomicCAS(&ws.key[slot], GP_EMPTY, col);
-                            if (prev == GP_EMPTY)
-                            {
-                                fresh = true;
-                                break;
-                            }
-                            if (prev == col)
-                                break;
-                            slot = (slot + 1) & (GP_H - 1);
-                        }
+                    if (d > (u32)GP_DMAX)
+                        crowded = true; // the table may not take another 32 columns
+                    else
+                    { // records owned by another rank (slab handles: already sent) do not take part
+                        const bool valid =
+                            bb + lane < cnt_here && (ownershift < 0 || (u32)(key[i] >> ownershift) == me);
+                        count_batch<false>(ws, key[i], valid, colshift, colmask, lt, d);
                     }
-                    const u32 rb = __ballot_sync(full, fresh);
-                    if (fresh)
-                        ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
-                    d += __popc(rb);
-                    if (leader)
-                        ws.cnt[slot] += (u32)__popc(peers); // leaders hold distinct slots of a warp-private table
-                    __syncwarp();
                 }
             }
         }
     }
+    (void)full;
     __syncwarp();
 
     // ---- room for this chunk's pairs (atomic ticket: chunks land in completion order; the pair list
