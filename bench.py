@@ -97,6 +97,12 @@ def flush_bytes(n_ins, nnz_old, nnz_new, ncols):
 
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the
+# same workload (profiles/r1d_ncu_full_fem128.csv, FEM 128^3); other workloads / kernels: null
+NCU_TRAFFIC_FEM128 = {"group_scatter_kernel": 4.063222e9 + 3.898295e9, "colthread_kernel": 4.160314e9 + 0.497858e9,
+                      "group_count_kernel": 3.932929e9 + 0.235842e9}
+
+
 def roofline(st, ms, ncols, peak, peak_src, traffic):
     """Roofline of the DOMINANT kernel of the flush (largest device time per step, CUDA events on the
     library's stream around that kernel) + the whole-flush fraction on SURVEY.md 8(d)'s bytes.
@@ -125,6 +131,8 @@ def roofline(st, ms, ncols, peak, peak_src, traffic):
     name = max(cands, key=lambda k: cands[k][0])
     t, byts, launches = cands[name]
     achieved = byts / (t / 1e3) / 1e9
+    if traffic is None and st["n_inserted"] == 245805960 and st["nnz_old"] == 0:
+        traffic = next((v for k, v in NCU_TRAFFIC_FEM128.items() if name.startswith(k)), None)
     b_flush = flush_bytes(st["n_inserted"], st["nnz_old"], nnz, ncols)
     flush_gbs = b_flush / (ms["ms_total"] / 1e3) / 1e9
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -336,7 +344,8 @@ def main():
                     help="N>1 only: fem = weak scaling of configs[1] (default, the bench line); fd400 = configs[4], "
                          "fdrand 400^3 sharded by node slab over the ranks (strong scaling, no e2e leg)")
     ap.add_argument("--fd-n", type=int, default=400, help="grid points per direction of --workload fd400")
-    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per onesweep launch, if known")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="ncu dram bytes per launch of the dominant kernel (default: the committed capture's figure)")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(0, args.warmup)
