@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         sig("ora_mt_destroy", None, _p)
         sig("ora_mt_update", C.c_int, _p, _f64, _i64, _i64, _i64, C.c_int)
         sig("ora_mt_insert_batch", _i64, _p, _p, _p, _p, _i64, _i64, C.c_int)
+        sig("ora_mt_insert_partitioned", _i64, _p, _p, _p, _p, _p, _i64, C.c_int)
         sig("ora_mt_flush", None, _p)
         sig("ora_mt_nnz", _i64, _p)
         sig("ora_mt_nnznew", _i64, _p)
@@ -274,6 +275,16 @@ class OracleMT:
     def insert_batch(self, I, J, V, tid=1, flavour=RAW):
         I, J, V = _i64a(I), _i64a(J), _f64a(V)
         r = lib().ora_mt_insert_batch(self._h, _ptr(I), _ptr(J), _ptr(V), len(V), int(tid), int(flavour))
+        if r < 0:
+            raise OracleBoundsError(f"error at entry {-r - 1}")
+
+    def insert_partitioned(self, I, J, V, part_begin, nthreads=1, flavour=RAW):
+        """testassemble_parallel! (test/femtools.jl:75-110): partition p (tid p+1) inserts the slice
+        [part_begin[p], part_begin[p+1]) of the stream; two colours (parity of p) run one after the
+        other, the partitions of a colour on `nthreads` POSIX threads."""
+        I, J, V, pb = _i64a(I), _i64a(J), _f64a(V), _i64a(part_begin)
+        assert len(pb) == self.np + 1 and pb[0] >= 0 and pb[-1] <= len(V) and np.all(np.diff(pb) >= 0)
+        r = lib().ora_mt_insert_partitioned(self._h, _ptr(I), _ptr(J), _ptr(V), _ptr(pb), int(nthreads), int(flavour))
         if r < 0:
             raise OracleBoundsError(f"error at entry {-r - 1}")
 

@@ -43,6 +43,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <pthread.h>
 
 typedef int64_t i64;
 
@@ -636,6 +637,7 @@ void ora_ext_eliminate_dirichlet(ora_ext *e, const uint8_t *marker)
 typedef struct
 {
     i64 m, n, nnz, nentries, len;
+    i64 jlo, jhi;  /* 1-based range of columns that have a list (the Dict's keys lie inside it) */
     i64 *colstart; /* Dict{Ti,Ti} of the reference, restated as a dense map (0 = absent) */
     i64 *colptr;
     i64 *rowval;
@@ -645,7 +647,9 @@ typedef struct
 /* ctor: sparsematrixdilnkc.jl:61-63 (initial capacity 10) */
 static ora_dilnkc *dilnkc_create(i64 m, i64 n)
 {
-    ora_dilnkc *l = (ora_dilnkc *)calloc(1, sizeof(ora_dilnkc));
+    /* own cache lines: partitions are filled by concurrent threads (ora_mt_insert_partitioned) */
+    ora_dilnkc *l = (ora_dilnkc *)aligned_alloc(128, (sizeof(ora_dilnkc) + 127) / 128 * 128);
+    memset(l, 0, sizeof(ora_dilnkc));
     l->m = m;
     l->n = n;
     l->len = 10;
@@ -704,7 +708,13 @@ static i64 dilnkc_addentry(ora_dilnkc *l, i64 i, i64 j, i64 k0)
         l->len = newsize;
     }
     if (k0 == 0)
+    {
         l->colstart[j - 1] = l->nentries;
+        if (l->jhi == 0 || j < l->jlo)
+            l->jlo = j;
+        if (j > l->jhi)
+            l->jhi = j;
+    }
     l->rowval[l->nentries - 1] = i;
     l->colptr[l->nentries - 1] = 0;
     if (k0 > 0)
@@ -786,6 +796,69 @@ i64 ora_mt_insert_batch(ora_mt *e, const i64 *I, const i64 *J, const double *V, 
     return 0;
 }
 
+/* Partitioned parallel insertion, the loop of test/femtools.jl:75-110 (testassemble_parallel!):
+ * `for color in pcolors(grid)` runs the colours one after the other; inside a colour the partitions
+ * are independent tasks (`@tasks for part in pcolor_partitions(grid, color)`), each inserting its own
+ * cells with its own tid = part into xmatrices[part] (genericmt...:87-114).  Here partition p
+ * (tid p+1) is the slice [part_begin[p], part_begin[p+1]) of a pre-generated stream, colours are
+ * the parities of p (neighbouring slabs never run together), and `nthreads` POSIX threads pull the
+ * partitions of the running colour from a shared counter.  A partition is inserted by exactly one
+ * thread in stream order, so the result equals the serial tid-wise insertion bit for bit. */
+typedef struct
+{
+    ora_mt *e;
+    const i64 *I, *J, *part_begin;
+    const double *V;
+    i64 colour, ncolours;
+    int flavour;
+    i64 next; /* next partition index of this colour (atomic) */
+    i64 err;
+} mt_colour_job;
+
+static void *mt_colour_worker(void *arg)
+{
+    mt_colour_job *job = (mt_colour_job *)arg;
+    for (;;)
+    {
+        i64 k = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+        i64 p = job->colour + k * job->ncolours;
+        if (p >= job->e->np)
+            break;
+        for (i64 r = job->part_begin[p]; r < job->part_begin[p + 1]; r++)
+            if (ora_mt_update(job->e, job->V[r], job->I[r], job->J[r], p + 1, job->flavour))
+            {
+                i64 zero = 0;
+                __atomic_compare_exchange_n(&job->err, &zero, -(r + 1), 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+                return NULL;
+            }
+    }
+    return NULL;
+}
+
+i64 ora_mt_insert_partitioned(ora_mt *e, const i64 *I, const i64 *J, const double *V, const i64 *part_begin,
+                              i64 nthreads, int flavour)
+{
+    if (nthreads < 1)
+        nthreads = 1;
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    mt_colour_job job = {e, I, J, part_begin, V, 0, 2, flavour, 0, 0};
+    for (i64 colour = 0; colour < 2 && job.err == 0; colour++)
+    {
+        job.colour = colour;
+        job.next = 0;
+        i64 started = 0;
+        for (i64 t = 0; t < nthreads; t++, started++)
+            if (pthread_create(&th[t], NULL, mt_colour_worker, &job))
+                break;
+        if (started == 0)
+            mt_colour_worker(&job);
+        for (i64 t = 0; t < started; t++)
+            pthread_join(th[t], NULL);
+    }
+    free(th);
+    return job.err;
+}
+
 typedef struct
 {
     i64 row;
@@ -821,7 +894,7 @@ void ora_mt_flush(ora_mt *e)
         for (i64 j = 1; j <= n; j++)
             cnt[j] += e->csc->colptr[j] - e->csc->colptr[j - 1];
         for (i64 p = 0; p < e->np; p++)
-            for (i64 j = 1; j <= n; j++)
+            for (i64 j = e->x[p]->jlo; j <= e->x[p]->jhi && j >= 1; j++)
                 for (i64 k = e->x[p]->colstart[j - 1]; k > 0; k = e->x[p]->colptr[k - 1])
                     cnt[j] += 1;
         i64 *start = (i64 *)calloc((size_t)(n + 2), sizeof(i64));
@@ -839,7 +912,7 @@ void ora_mt_flush(ora_mt *e)
                 t->seq = seq++;
             }
         for (i64 p = 0; p < e->np; p++)
-            for (i64 j = 1; j <= n; j++)
+            for (i64 j = e->x[p]->jlo; j <= e->x[p]->jhi && j >= 1; j++)
                 for (i64 k = e->x[p]->colstart[j - 1]; k > 0; k = e->x[p]->colptr[k - 1])
                 {
                     coo_ent *t = &buf[start[j] + fill[j]++];
@@ -854,7 +927,22 @@ void ora_mt_flush(ora_mt *e)
             r->colptr[j - 1] = inz;
             coo_ent *c = buf + start[j];
             i64 len = cnt[j];
-            qsort(c, (size_t)len, sizeof(coo_ent), coo_less);
+            if (len <= 64)
+            { /* stable insertion sort by row: input order (seq) survives among equal rows */
+                for (i64 a = 1; a < len; a++)
+                {
+                    coo_ent x = c[a];
+                    i64 b = a;
+                    while (b > 0 && c[b - 1].row > x.row)
+                    {
+                        c[b] = c[b - 1];
+                        b--;
+                    }
+                    c[b] = x;
+                }
+            }
+            else
+                qsort(c, (size_t)len, sizeof(coo_ent), coo_less);
             for (i64 t = 0; t < len; t++)
             {
                 if (t > 0 && c[t].row == c[t - 1].row)

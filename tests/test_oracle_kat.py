@@ -285,6 +285,36 @@ def test_mt_matches_ext(oracle):
     assert np.array_equal(A3.csc()[2], A0.csc()[2])
 
 
+def test_mt_threaded_matches_serial(oracle):
+    """testassemble_parallel! (test/femtools.jl:75-110): partitions of a colour inserted by concurrent
+    threads give the bits of the serial tid-wise insertion; second assembly = CSC hits only."""
+    nn = 12
+    I, J, V = oracle.fem_stream(nn, nn, nn)
+    n = nn ** 3
+    nparts = 6
+    ncells = len(V) // 20
+    pb = 20 * (np.arange(nparts + 1) * ncells // nparts)
+    A = oracle.OracleMT(n, n, nparts)
+    for t in range(nparts):
+        sl = slice(pb[t], pb[t + 1])
+        A.insert_batch(I[sl], J[sl], V[sl], t + 1, oracle.RAW)
+    ref = A.csc()
+    for nthreads in (1, 3, 8):
+        B = oracle.OracleMT(n, n, nparts)
+        B.insert_partitioned(I, J, V, pb, nthreads, oracle.RAW)
+        got = B.csc()
+        for x, y in zip(ref, got):
+            assert np.array_equal(x.view(np.int64), y.view(np.int64))
+        B.zero_values()
+        B.insert_partitioned(I, J, V, pb, nthreads, oracle.RAW)
+        assert B.nnznew == 0
+    A0 = oracle.OracleExt(n, n)
+    A0.insert_batch(I, J, V, oracle.RAW)
+    cp0, rv0, nz0 = A0.csc()
+    assert np.array_equal(ref[0], cp0) and np.array_equal(ref[1], rv0)
+    assert np.allclose(ref[2], nz0, rtol=1e-12, atol=1e-15)
+
+
 def test_dirichlet(oracle):
     """test/test_dirichlet.jl:7-28 (values-only passes, sparsematrixcsc.jl:97-148)."""
     I, J, V = oracle.fdrand_stream(6, 5, 1, seed=11)
