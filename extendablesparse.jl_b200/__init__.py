@@ -9,5 +9,6 @@ from .capi import (  # noqa: F401
     XsbIllegalError, XsbSizeError,
 )
 from .matrix import (  # noqa: F401
-    ExtendableSparseMatrix, MTExtendableSparseMatrix, fdrand, flush, nnz, rawupdateindex, reset, sparse, updateindex,
+    ExtendableSparseMatrix, MTExtendableSparseMatrix, fdrand, flush, nnz, pointblock, rawupdateindex, reset, sparse,
+    updateindex,
 )

@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         o = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        # XSB_NVCC_EXTRA: tuning experiments only (e.g. "-DXSB_GP_W=1024"); use with --force
+        cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("XSB_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

@@ -17,6 +17,9 @@ OK, EBOUNDS, ESIZE, EILLEGAL, EINVAL, ECUDA, ENOMEM, ESTATE = range(8)
 F64 = 0
 I32, I64 = 0, 1
 UPDATE, RAW, ASSIGN = 0, 1, 2
+# xsb_triplet of include/xsparse_b200.h: what one updateindex! call appends to the host buffer
+TRIPLET_DTYPE = np.dtype([("row", "<u4"), ("col", "<u4"), ("val", "<f8")])
+assert TRIPLET_DTYPE.itemsize == 16
 DETERMINISTIC, FAST = 0, 1
 COMBINE_SEED, COMBINE_ADD = 0, 1
 STRATEGY_AUTO, STRATEGY_FULLSORT, STRATEGY_COLSORT = 0, 1, 2
@@ -95,6 +98,7 @@ SIGNATURES = {
     "xsb_nnz": (_i32, [_p, C.POINTER(_i64)]),
     "xsb_reserve": (_i32, [_p, _i32, _i64]),
     "xsb_insert_batch": (_i32, [_p, _i32, _p, _p, _p, _i64, _i32]),
+    "xsb_insert_triplets": (_i32, [_p, _i32, _p, _i64, _i32]),
     "xsb_pending": (_i32, [_p, C.POINTER(_i64)]),
     "xsb_flush": (_i32, [_p, _i32, C.POINTER(_i64), C.POINTER(_i32)]),
     "xsb_flush_ex": (_i32, [_p, _i32, _i32, C.POINTER(_i64), C.POINTER(_i32)]),
@@ -107,6 +111,9 @@ SIGNATURES = {
     "xsb_mark_dirichlet": (_i32, [_p, _f64, _p]),
     "xsb_eliminate_dirichlet": (_i32, [_p, _p]),
     "xsb_pattern_hash": (_i32, [_p, C.POINTER(_u64)]),
+    "xsb_pointblock": (_i32, [_p, _i32, C.POINTER(_p)]),
+    "xsb_block_size": (_i32, [_p, C.POINTER(_i32)]),
+    "xsb_fetch_blocks": (_i32, [_p, _p]),
     "xsb_emit_fdrand": (_i32, [_p, _i32, _i64, _i64, _i64, _u64, _i32, _i32]),
     "xsb_emit_fdrand_range": (_i32, [_p, _i32, _i64, _i64, _i64, _u64, _i32, _i32, _i64, _i64]),
     "xsb_emit_p1fem": (_i32, [_p, _i32, _i64, _i64, _i64, _i32]),
@@ -288,6 +295,13 @@ class Handle:
             count = len(V)
         self._c(lib().xsb_insert_batch(self._h, tid, ptr(I), ptr(J), ptr(V), count, flavour))
 
+    def insert_triplets(self, T, flavour=UPDATE, tid=0, count=None):
+        """T: `count` 16-byte triplets {u32 row, u32 col, f64 val} (numpy array of TRIPLET_DTYPE, or any
+        16-byte-aligned buffer / torch tensor holding them); indices carry the handle's index base."""
+        if count is None:
+            count = len(T)
+        self._c(lib().xsb_insert_triplets(self._h, tid, ptr(T), count, flavour))
+
     def flush(self, mode=DETERMINISTIC, combine=COMBINE_SEED):
         nnz, changed = _i64(0), _i32(0)
         self._c(lib().xsb_flush_ex(self._h, mode, combine, C.byref(nnz), C.byref(changed)))
@@ -346,6 +360,29 @@ class Handle:
             x = np.ascontiguousarray(x, np.float64)
         self._c(lib().xsb_mul(self._h, ptr(x), ptr(y)))
         return y
+
+    def pointblock(self, blocksize) -> "Handle":
+        """pointblock(A, blocksize) (extendable.jl:292-318): a new handle holding the block matrix."""
+        out = _p()
+        self._c(lib().xsb_pointblock(self._h, int(blocksize), C.byref(out)))
+        nb = self.n // int(blocksize)
+        hb = Handle.__new__(Handle)
+        hb._h = out
+        hb.m = hb.n = hb.n_global = nb
+        hb.col_begin = 0
+        hb.idx_type, hb.index_base, hb.n_tid, hb.device = self.idx_type, self.index_base, 1, self.device
+        hb.idx_dtype = self.idx_dtype
+        hb.block_size = int(blocksize)
+        return hb
+
+    def fetch_blocks_numpy(self):
+        """Blocks of a pointblock result: array [nnz, bs, bs] with blocks[k, jj, ii] = block k's [ii, jj]
+        (every block column-major, as SMatrix stores it), in CSC order."""
+        bs = _i32(0)
+        self._c(lib().xsb_block_size(self._h, C.byref(bs)))
+        out = np.zeros((self.nnz, bs.value, bs.value), np.float64)
+        self._c(lib().xsb_fetch_blocks(self._h, ptr(out)))
+        return out
 
     def pattern_hash(self) -> int:
         v = _u64(0)

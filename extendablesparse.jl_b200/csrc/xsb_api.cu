@@ -94,6 +94,8 @@ struct xsb_matrix
     u32 *f_perm = nullptr;
     i64 *f_segstart = nullptr;
 
+    double *blocks = nullptr; // result handle of xsb_pointblock: nnz dense bs x bs blocks, column-major, CSC order
+    int block_size = 0;
     u32 *csr_map = nullptr; // row-major view of the resident pattern for xsb_mul (rebuilt when the pattern changes)
     u64 *d_scal = nullptr; // 8 device scalars
     u64 *h_scal = nullptr; // pinned mirror
@@ -187,6 +189,12 @@ struct xsb_matrix
         return s;
     }
     CscView view() const { return CscView{colptr, rowval, nzval, nnz}; }
+    void drop_blocks()
+    {
+        dfree(blocks);
+        blocks = nullptr;
+        block_size = 0;
+    }
     static i64 chunk_up(i64 x)
     {
         const i64 w = group_chunk_records();
@@ -1143,6 +1151,7 @@ int32_t xsb_destroy(xsb_matrix *h)
     if (h->stream)
         cudaStreamSynchronize(h->stream);
     h->drop_frozen();
+    h->drop_blocks();
     h->clear_staging(true);
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
@@ -1173,6 +1182,7 @@ int32_t xsb_reset(xsb_matrix *h)
     return guard(h, [&]() -> int32_t {
         REQUIRE(h, XSB_EINVAL, "NULL handle");
         h->drop_frozen();
+        h->drop_blocks();
         h->clear_staging(false);
         h->set_empty_csc();
         return XSB_OK;
@@ -1183,6 +1193,7 @@ int32_t xsb_set_csc(xsb_matrix *h, const void *colptr, const void *rowval, const
 {
     return guard(h, [&]() -> int32_t {
         REQUIRE(h && colptr, XSB_EINVAL, "NULL argument");
+        h->drop_blocks();
         const size_t isz = h->isz();
         // nnz = colptr[n] - base
         unsigned char last[8];
@@ -1283,6 +1294,37 @@ int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *
         write_scalar(h, 1, ~0ull);
         pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
                      h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc, h->stage_flags(tid));
+        const u64 bad = read_scalar(h, 1);
+        if (bad != ~0ull)
+            throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
+                                            " of the batch is outside the matrix; batch rejected");
+        end_emit(h, tid, flavour, count);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_insert_triplets(xsb_matrix *h, int32_t tid, const xsb_triplet *T, int64_t count, int32_t flavour)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        check_tid_flavour(h, tid, flavour);
+        REQUIRE(count >= 0, XSB_EINVAL, "negative count");
+        REQUIRE((u64)h->m < (1ull << 32) && (u64)h->n_global < (1ull << 32), XSB_EINVAL,
+                "triplets carry 32-bit indices: the matrix needs fewer than 2^32 rows and columns");
+        if (count == 0)
+            return XSB_OK;
+        REQUIRE(T, XSB_EINVAL, "NULL array");
+        REQUIRE((reinterpret_cast<uintptr_t>(T) & 15u) == 0, XSB_EINVAL, "triplet array must be 16-byte aligned");
+        Rec *dst = begin_emit(h, tid, flavour, count);
+        const void *src = T;
+        if (!is_device_ptr(T))
+        { // PCIe straight into the staging buffer; the kernel below rewrites the records in place
+            XSB_CUDA(cudaMemcpyAsync(dst, T, sizeof(Rec) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+            src = dst;
+        }
+        write_scalar(h, 1, ~0ull);
+        pack_triplets(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
+                      h->d_scal + 1, h->lc, h->stage_flags(tid));
         const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
@@ -1501,6 +1543,90 @@ int32_t xsb_pattern_hash(xsb_matrix *h, uint64_t *hash_out)
         REQUIRE(h && hash_out, XSB_EINVAL, "NULL argument");
         pattern_hash(h->stream, h->view(), h->n, h->idx64, h->d_scal + 4, h->lc);
         *hash_out = read_scalar(h, 4);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_pointblock(xsb_matrix *h, int32_t blocksize, xsb_matrix **out)
+{
+    if (out)
+        *out = nullptr;
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && out, XSB_EINVAL, "NULL argument");
+        REQUIRE(blocksize >= 1, XSB_EINVAL, "blocksize must be >= 1");
+        REQUIRE(h->nranks == 0, XSB_ESTATE, "pointblock works on a whole matrix, not on a column slab");
+        REQUIRE(h->pending() == 0, XSB_ESTATE, "flush! before pointblock");
+        const i64 bs = blocksize;
+        const i64 nb = h->n / bs; // nblock = n / blocksize, extendable.jl:299
+        REQUIRE(nb >= 1, XSB_ESIZE, "blocksize exceeds the matrix size");
+        xsb_matrix *b = nullptr;
+        const int32_t rc = create_impl(nb, nb, 0, 0, nullptr, XSB_F64, h->idx64 ? XSB_I64 : XSB_I32, h->base, 1,
+                                       h->device, &b);
+        if (rc != XSB_OK)
+            throw ApiError(rc, "pointblock: " + g_err);
+        try
+        {
+            h->sync(); // the pattern handle works on its own stream
+            if (h->nnz > 0)
+            {
+                Rec *dst = begin_emit(b, 0, XSB_RAW, h->nnz);
+                write_scalar(b, 1, ~0ull);
+                pointblock_emit(b->stream, h->view(), h->n, h->idx64, h->base, bs, nb, b->Ls, dst, b->d_scal + 1,
+                                b->lc);
+                const u64 bad = read_scalar(b, 1);
+                if (bad != ~0ull)
+                    throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
+                                                    " of the matrix falls outside the " + std::to_string(nb) + "x" +
+                                                    std::to_string(nb) + " block matrix");
+                end_emit(b, 0, XSB_RAW, h->nnz);
+                int64_t nnzb = 0;
+                int32_t changed = 0;
+                const int32_t frc = do_flush(b, XSB_DETERMINISTIC, XSB_COMBINE_SEED, &nnzb, &changed);
+                if (frc != XSB_OK)
+                    throw ApiError(frc, "pointblock: " + b->err);
+            }
+            b->block_size = (int)bs;
+            const size_t nbytes = sizeof(double) * (size_t)b->nnz * (size_t)(bs * bs);
+            b->blocks = static_cast<double *>(b->dalloc(nbytes));
+            if (b->nnz > 0)
+            {
+                XSB_CUDA(cudaMemsetAsync(b->blocks, 0, nbytes, b->stream));
+                write_scalar(b, 1, ~0ull);
+                pointblock_fill(b->stream, h->view(), h->n, h->idx64, h->base, bs, b->view(), b->blocks,
+                                b->d_scal + 1, b->lc);
+                const u64 lost = read_scalar(b, 1);
+                REQUIRE(lost == ~0ull, XSB_EINVAL, "pointblock: entry without a block (internal error)");
+            }
+            b->sync();
+        }
+        catch (...)
+        {
+            xsb_destroy(b);
+            XSB_CUDA(cudaSetDevice(h->device));
+            throw;
+        }
+        *out = b;
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_block_size(const xsb_matrix *hb, int32_t *blocksize)
+{
+    if (!hb || !blocksize)
+        return XSB_EINVAL;
+    *blocksize = hb->block_size;
+    return XSB_OK;
+}
+
+int32_t xsb_fetch_blocks(xsb_matrix *hb, void *blocks_out)
+{
+    return guard(hb, [&]() -> int32_t {
+        REQUIRE(hb && blocks_out, XSB_EINVAL, "NULL argument");
+        REQUIRE(hb->blocks != nullptr && hb->block_size > 0, XSB_ESTATE, "not a result of xsb_pointblock");
+        const size_t nbytes = sizeof(double) * (size_t)hb->nnz * (size_t)hb->block_size * (size_t)hb->block_size;
+        if (nbytes)
+            XSB_CUDA(cudaMemcpyAsync(blocks_out, hb->blocks, nbytes, cudaMemcpyDefault, hb->stream));
+        hb->sync();
         return XSB_OK;
     });
 }

@@ -623,7 +623,10 @@ colfold_kernel(const Rec *__restrict__ sorted, KeyLayout L, int combine, u32 chu
 // column with more distinct rows than the table takes is appended to `next` (the next size, or the
 // warp-per-column kernel); columns longer than maxlen go straight to `longlist` (warp kernel).
 constexpr int CT_WARPS = 4;
-constexpr int CT_U = 2; // 32-byte record pairs per step (the next step is prefetched)
+#ifndef XSB_CT_U
+#define XSB_CT_U 2
+#endif
+constexpr int CT_U = XSB_CT_U; // 32-byte record pairs per step (the next step is prefetched)
 constexpr u32 CT_EMPTY = 0xffffffffu;
 
 template <int HBITS> struct CtShape

@@ -26,7 +26,10 @@
 
 namespace xsb {
 
-constexpr int GP_W = 512;           // records per chunk (one warp)
+#ifndef XSB_GP_W
+#define XSB_GP_W 512
+#endif
+constexpr int GP_W = XSB_GP_W;      // records per chunk (one warp)
 constexpr int GP_NB = GP_W / 32;    // batches per chunk
 constexpr int GP_HBITS = 9;
 constexpr int GP_H = 1 << GP_HBITS; // hash slots per warp

@@ -55,6 +55,43 @@ void pack_records(cudaStream_t stream, const void *I, const void *J, const doubl
     XSB_CUDA(cudaGetLastError());
 }
 
+// 16-byte triplets {u32 row, u32 col, f64 val} -> staged records.  `in` may BE `out` (a host array
+// is copied straight into the staging buffer and rewritten in place: every thread reads and writes
+// its own 16 bytes), so neither pointer is __restrict__.
+__global__ void __launch_bounds__(256)
+pack_triplets_kernel(const uint4 *in, i64 count, u32 base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour,
+                     Rec *out, u64 *__restrict__ d_err, StageFlags sf)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const uint4 t = in[k];
+        const i64 i = (i64)t.x - (i64)base, j = (i64)t.y - (i64)base;
+        if (i < 0 || i >= m || j < 0 || j >= n)
+        { // BoundsError: sparsematrixcsc.jl:8-10
+            atomicMin(d_err, (u64)k);
+            continue;
+        }
+        Rec r;
+        r.key = L.pack((u64)j, (u64)i, tid, flavour);
+        r.val = __hiloint2double((int)t.w, (int)t.z);
+        st_staged(out + k, r, L, sf, out);
+    }
+}
+
+void pack_triplets(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
+                   u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, StageFlags sf)
+{
+    if (count <= 0)
+        return;
+    const int threads = 256;
+    const int blocks = (int)std::min<i64>((count + threads - 1) / threads, (i64)kNumSM * 16);
+    pack_triplets_kernel<<<blocks, threads, 0, stream>>>(static_cast<const uint4 *>(T), count, (u32)base, m, n, L,
+                                                         tid, flavour, out, d_err, sf);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
 template <typename Ti>
 __global__ void __launch_bounds__(256)
 unpack_kernel(const Rec *__restrict__ in, i64 count, Ti base, KeyLayout L, Ti *__restrict__ I, Ti *__restrict__ J,

@@ -174,6 +174,13 @@ void preaggregate_records(cudaStream_t stream, const Rec *in, u64 nrec, const Ke
 void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                   int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
                   LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
+// pointblock (xsb_values.cu): CSC entries -> records of the block pattern; values into the blocks
+void pointblock_emit(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs, i64 nb,
+                     KeyLayout Lb, Rec *out, u64 *d_err, LaunchCounter &lc);
+void pointblock_fill(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs,
+                     const CscView &pattern, double *blocks, u64 *d_err, LaunchCounter &lc);
+void pack_triplets(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
+                   u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, StageFlags sf);
 void unpack_records(cudaStream_t stream, const Rec *in, i64 count, int idx64, int base, KeyLayout L, void *I,
                     void *J, double *V, int *flavour, LaunchCounter &lc);
 i64 fdrand_prefix(i64 nx, i64 ny, i64 nz, i64 l); // records emitted by nodes [0,l)

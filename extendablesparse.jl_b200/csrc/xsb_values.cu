@@ -351,4 +351,112 @@ void pattern_hash(cudaStream_t stream, const CscView &csc, i64 n, int idx64, u64
     XSB_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------
+// pointblock(A, blocksize): src/matrix/extendable.jl:292-318.
+// The reference walks A in CSC order (column i, entries k) and, for the entry in row j, calls
+// rawupdateindex!(Ab, +, block, iblock, jblock) with iblock = (i-1)/bs+1 taken from the COLUMN,
+// jblock from the ROW and block[ii,jj] = nzval[k] (ii from the column, jj from the row).
+//   pointblock_emit_kernel : entry k -> staged record (row iblock, column jblock, +0.0) of the block
+//                            pattern matrix, at stream position k (the reference's call order)
+//   pointblock_fill_kernel : entry k -> its value into block (iblock, jblock) of the flushed pattern,
+//                            column-major position ii + jj*bs.  Every (block, position) receives
+//                            exactly one entry, so the sum of single-entry blocks is 0.0 + v.
+// ------------------------------------------------------------------------
+template <typename Ti>
+__device__ __forceinline__ i64 column_of_entry(const Ti *__restrict__ colptr, Ti base, i64 n, i64 k)
+{ // the column c with colptr[c] <= k < colptr[c+1]: the largest c whose start is <= k
+    i64 lo = 0, hi = n - 1;
+    while (lo < hi)
+    {
+        const i64 mid = (lo + hi + 1) >> 1;
+        if ((i64)colptr[mid] - base <= k)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+pointblock_emit_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval, Ti base, i64 n, i64 nnz, i64 bs,
+                       i64 nb, KeyLayout Lb, Rec *__restrict__ out, u64 *__restrict__ d_err)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride)
+    {
+        const i64 col = column_of_entry<Ti>(colptr, base, n, k);
+        const i64 row = (i64)rowval[k] - base;
+        const i64 ib = col / bs, jb = row / bs;
+        Rec r;
+        r.val = 0.0;
+        if (ib >= nb || jb >= nb)
+        { // BoundsError of rawupdateindex!(Ab, ...): sparsematrixcsc.jl:8-10
+            atomicMin(d_err, (u64)k);
+            r.key = Lb.pack(0, 0, 0u, FL_RAW);
+        }
+        else
+            r.key = Lb.pack((u64)jb, (u64)ib, 0u, FL_RAW);
+        st_rec(out + k, r);
+    }
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+pointblock_fill_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval, const double *__restrict__ nzval,
+                       Ti base, i64 n, i64 nnz, i64 bs, const Ti *__restrict__ bcolptr,
+                       const Ti *__restrict__ browval, double *__restrict__ blocks, u64 *__restrict__ d_err)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride)
+    {
+        const i64 col = column_of_entry<Ti>(colptr, base, n, k);
+        const i64 row = (i64)rowval[k] - base;
+        const i64 ib = col / bs, jb = row / bs, ii = col % bs, jj = row % bs;
+        const i64 pos = find_slot<Ti>(bcolptr, browval, base, ib, jb);
+        if (pos < 0)
+        {
+            atomicMin(d_err, (u64)k);
+            continue;
+        }
+        blocks[pos * bs * bs + ii + jj * bs] = 0.0 + nzval[k];
+    }
+}
+
+void pointblock_emit(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs, i64 nb,
+                     KeyLayout Lb, Rec *out, u64 *d_err, LaunchCounter &lc)
+{
+    if (csc.nnz <= 0)
+        return;
+    const int blocks = grid_for(csc.nnz, 256);
+    if (idx64)
+        pointblock_emit_kernel<int64_t><<<blocks, 256, 0, stream>>>((const int64_t *)csc.colptr,
+                                                                    (const int64_t *)csc.rowval, (int64_t)base, n,
+                                                                    csc.nnz, bs, nb, Lb, out, d_err);
+    else
+        pointblock_emit_kernel<int32_t><<<blocks, 256, 0, stream>>>((const int32_t *)csc.colptr,
+                                                                    (const int32_t *)csc.rowval, (int32_t)base, n,
+                                                                    csc.nnz, bs, nb, Lb, out, d_err);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+void pointblock_fill(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs,
+                     const CscView &pattern, double *blocks, u64 *d_err, LaunchCounter &lc)
+{
+    if (csc.nnz <= 0)
+        return;
+    const int grid = grid_for(csc.nnz, 256);
+    if (idx64)
+        pointblock_fill_kernel<int64_t><<<grid, 256, 0, stream>>>(
+            (const int64_t *)csc.colptr, (const int64_t *)csc.rowval, csc.nzval, (int64_t)base, n, csc.nnz, bs,
+            (const int64_t *)pattern.colptr, (const int64_t *)pattern.rowval, blocks, d_err);
+    else
+        pointblock_fill_kernel<int32_t><<<grid, 256, 0, stream>>>(
+            (const int32_t *)csc.colptr, (const int32_t *)csc.rowval, csc.nzval, (int32_t)base, n, csc.nnz, bs,
+            (const int32_t *)pattern.colptr, (const int32_t *)pattern.rowval, blocks, d_err);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
 } // namespace xsb

@@ -12,8 +12,10 @@
 # been written against the reference sources but NOT executed.  The C ABI it binds is
 # exercised by the Python tests (tests/test_gpu_parity.py) through ctypes.
 #
-# Per-entry calls are appended to a per-partition host buffer (no ccall per entry) and shipped
-# with one `xsb_insert_batch` when the buffer is full, the flavour changes, or at `flush!`.
+# Per-entry calls are appended to a per-partition host buffer of 16-byte triplets
+# (`XsbTriplet` = `xsb_triplet` of include/xsparse_b200.h: one 16-byte store per call, no ccall per
+# entry) and shipped with one `xsb_insert_triplets` when the buffer is full, the flavour changes, or
+# at `flush!`: 16 bytes per insertion cross PCIe instead of the 24 of three Int64/Int64/Float64 arrays.
 
 module ExtendableSparseB200
 
@@ -40,6 +42,13 @@ function check(h::Ptr{Cvoid}, rc::Int32)
     error("libxsparse_b200: [$rc] $msg")                        # genericmt...:67,80
 end
 
+"`xsb_triplet`: what one updateindex!/rawupdateindex!/setindex! call appends (1-based row/col)."
+struct XsbTriplet
+    row::UInt32
+    col::UInt32
+    val::Float64
+end
+
 idxcode(::Type{Int64}) = XSB_I64
 idxcode(::Type{Int32}) = XSB_I32
 
@@ -53,22 +62,20 @@ mutable struct SparseMatrixB200{Tv, Ti <: Integer} <: AbstractSparseMatrixExtens
     m::Ti
     n::Ti
     handle::Ptr{Cvoid}
-    I::Vector{Ti}
-    J::Vector{Ti}
-    V::Vector{Tv}
+    T::Vector{XsbTriplet}
     fill::Int
     flavour::Int32
     shipped::Int            # insertions already on the device
 
     function SparseMatrixB200{Tv, Ti}(m, n) where {Tv, Ti <: Integer}
         Tv === Float64 || error("libxsparse_b200 implements Float64 values")
+        (m < 2^32 && n < 2^32) || error("triplet buffers carry 32-bit indices")
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:xsb_create, libxsb), Int32,
                    (Int64, Int64, Int32, Int32, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
                    m, n, XSB_F64, idxcode(Ti), 1, 1, 0, h)
         check(Ptr{Cvoid}(C_NULL), rc)
-        x = new{Tv, Ti}(m, n, h[], Vector{Ti}(undef, CHUNK), Vector{Ti}(undef, CHUNK),
-                        Vector{Tv}(undef, CHUNK), 0, XSB_RAW, 0)
+        x = new{Tv, Ti}(m, n, h[], Vector{XsbTriplet}(undef, CHUNK), 0, XSB_RAW, 0)
         finalizer(x) do y
             y.handle == C_NULL || ccall((:xsb_destroy, libxsb), Int32, (Ptr{Cvoid},), y.handle)
             y.handle = C_NULL
@@ -86,9 +93,9 @@ function ship!(x::SparseMatrixB200)
     x.fill == 0 && return
     n = x.fill
     x.fill = 0
-    rc = ccall((:xsb_insert_batch, libxsb), Int32,
-               (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32),
-               x.handle, 0, x.I, x.J, x.V, n, x.flavour)
+    rc = ccall((:xsb_insert_triplets, libxsb), Int32,
+               (Ptr{Cvoid}, Int32, Ptr{XsbTriplet}, Int64, Int32),
+               x.handle, 0, x.T, n, x.flavour)
     check(x.handle, rc)
     x.shipped += n
 end
@@ -100,9 +107,7 @@ end
     end
     x.flavour = flavour
     k = (x.fill += 1)
-    @inbounds x.I[k] = i
-    @inbounds x.J[k] = j
-    @inbounds x.V[k] = v
+    @inbounds x.T[k] = XsbTriplet(i % UInt32, j % UInt32, v)
     x
 end
 
@@ -235,6 +240,34 @@ function reassemble!(a::B200Assembler{Tv}, V::Vector{Tv}; mode = XSB_DETERMINIST
                           a.handle, V, length(V), mode))
 end
 
+"""
+    pointblock(a::B200Assembler, blocksize) -> (colptr, rowval, blocks)
+
+Device version of `pointblock` (src/matrix/extendable.jl:292-318): the block pattern is assembled on
+the GPU from the resident CSC; `blocks[:, :, k]` is the k-th stored `blocksize x blocksize` block
+(column-major, the memory layout of `SMatrix{bs,bs}`), so
+`reinterpret(SMatrix{bs,bs,Tv,bs*bs}, vec(blocks))` is the `nzval` of the reference's result.
+"""
+function pointblock(a::B200Assembler{Tv, Ti}, blocksize::Integer) where {Tv, Ti}
+    hb = Ref{Ptr{Cvoid}}(C_NULL)
+    check(a.handle, ccall((:xsb_pointblock, libxsb), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}),
+                          a.handle, blocksize, hb))
+    try
+        nnzb = Ref{Int64}(0)
+        check(hb[], ccall((:xsb_nnz, libxsb), Int32, (Ptr{Cvoid}, Ref{Int64}), hb[], nnzb))
+        nb = a.n ÷ blocksize
+        colptr = Vector{Ti}(undef, nb + 1)
+        rowval = Vector{Ti}(undef, nnzb[])
+        blocks = Array{Tv, 3}(undef, blocksize, blocksize, nnzb[])
+        check(hb[], ccall((:xsb_fetch_csc, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                          hb[], colptr, rowval, C_NULL))
+        check(hb[], ccall((:xsb_fetch_blocks, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), hb[], blocks))
+        return colptr, rowval, blocks
+    finally
+        ccall((:xsb_destroy, libxsb), Int32, (Ptr{Cvoid},), hb[])
+    end
+end
+
 # the drop-in aliases, mirroring src/ExtendableSparse.jl:35-39
 const B200ExtendableSparseMatrixCSC{Tv, Ti} =
     ExtendableSparse.GenericMTExtendableSparseMatrixCSC{SparseMatrixB200{Tv, Ti}, Tv, Ti}
@@ -242,6 +275,6 @@ const STB200ExtendableSparseMatrixCSC{Tv, Ti} =
     ExtendableSparse.GenericExtendableSparseMatrixCSC{SparseMatrixB200{Tv, Ti}, Tv, Ti}
 
 export SparseMatrixB200, B200Assembler, B200ExtendableSparseMatrixCSC, STB200ExtendableSparseMatrixCSC,
-       set_csc!, insert!, fetch!, freeze!, reassemble!
+       set_csc!, insert!, fetch!, freeze!, reassemble!, pointblock, XsbTriplet
 
 end # module

@@ -7,12 +7,14 @@ mutators is dropped):
     updateindex(A, op, v, i, j)                       extendable.jl:159-174
     rawupdateindex(A, op, v, i, j[, tid])             extendable.jl:181-197, genericmt...:87-99
     A[i, j] = v ; A[i, j]                             extendable.jl:205-238
+    pointblock(A, blocksize)                          extendable.jl:292-318
     flush(A) ; sparse(A) ; nnz(A) ; reset(A)          extendable.jl:248-272
     MTExtendableSparseMatrix(m, n, nparts)            src/ExtendableSparse.jl:35-39, genericmt...:1-114
 
-Indices are 1-based like the reference's.  Per-entry calls are appended to a host buffer
-and shipped to the device in batches through the C ABI (xsb_insert_batch); everything
-else happens on the GPU.  There is no CPU fallback.
+Indices are 1-based like the reference's.  Per-entry calls are appended to a host buffer of
+16-byte triplets {u32 row, u32 col, f64 val} and shipped to the device in batches through the
+C ABI (xsb_insert_triplets; xsb_insert_batch for the bulk (I, J, V) variants); everything else
+happens on the GPU.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -29,9 +31,7 @@ class _HostBuffer:
     """Insert calls of one partition, in call order, waiting to be shipped."""
 
     def __init__(self):
-        self.I = np.empty(_CHUNK, np.int64)
-        self.J = np.empty(_CHUNK, np.int64)
-        self.V = np.empty(_CHUNK, np.float64)
+        self.T = np.empty(_CHUNK, capi.TRIPLET_DTYPE)
         self.n = 0
         self.flavour = capi.UPDATE
 
@@ -72,7 +72,7 @@ class ExtendableSparseMatrix:
         if b.n:
             n = b.n
             b.n = 0  # a rejected batch is dropped, like the failing call in the reference
-            self._h.insert_batch(b.I[:n], b.J[:n], b.V[:n], b.flavour, t, n)
+            self._h.insert_triplets(b.T, b.flavour, t, n)
 
     def _push(self, flavour, v, i, j, t=0):
         if not (1 <= i <= self.m and 1 <= j <= self.n):
@@ -81,7 +81,7 @@ class ExtendableSparseMatrix:
         if b.n and (b.flavour != flavour or b.n == _CHUNK):
             self._ship(t)
         b.flavour = flavour
-        b.I[b.n], b.J[b.n], b.V[b.n] = i, j, v
+        b.T[b.n] = (i, j, v)
         b.n += 1
 
     @staticmethod
@@ -176,6 +176,18 @@ class ExtendableSparseMatrix:
         self._h.eliminate_dirichlet(marker)
         return self
 
+    def pointblock(self, blocksize):
+        """pointblock(A, blocksize) (extendable.jl:292-318): (colptr, rowval, blocks) of the block matrix,
+        1-based, blocks[k] the k-th stored blocksize x blocksize block (blocks[k][ii-1, jj-1] = block[ii, jj])."""
+        self.flush()
+        hb = self._h.pointblock(blocksize)
+        try:
+            cp, rv, _ = hb.fetch_csc_numpy()
+            blocks = hb.fetch_blocks_numpy().transpose(0, 2, 1).copy()
+        finally:
+            hb.close()
+        return cp, rv, blocks
+
 
 class MTExtendableSparseMatrix(ExtendableSparseMatrix):
     """MTExtendableSparseMatrixCSC: one insert buffer per partition (genericmt...:1-114)."""
@@ -205,6 +217,10 @@ def updateindex(A, op, v, i, j, *tid):
 
 def rawupdateindex(A, op, v, i, j, *tid):
     return A.rawupdateindex(op, v, i, j, *tid)
+
+
+def pointblock(A, blocksize):
+    return A.pointblock(blocksize)
 
 
 def flush(A):

@@ -147,6 +147,21 @@ int32_t xsb_reserve(xsb_matrix *h, int32_t tid, int64_t count);
 int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *J, const void *V,
                          int64_t count, int32_t flavour);
 
+/* The same `count` calls as xsb_insert_batch, handed over as ONE array of 16-byte triplets: the
+ * layout the Julia glue appends to in updateindex!/rawupdateindex!(A,+,v,i,j[,tid]) (one 16-byte
+ * store per call instead of three 8-byte ones) and the cheapest one to ship: a host array goes
+ * over PCIe straight into the staging buffer (16 B per call instead of 24 B with Int64 indices) and
+ * is turned into staged records in place.  row/col carry the handle's index_base; the matrix must
+ * have fewer than 2^32 rows and columns (XSB_EINVAL otherwise).  Out-of-range indices reject the
+ * whole batch with XSB_EBOUNDS (findindex, sparsematrixcsc.jl:8-10). */
+typedef struct xsb_triplet
+{
+    uint32_t row;
+    uint32_t col;
+    double val;
+} xsb_triplet;
+int32_t xsb_insert_triplets(xsb_matrix *h, int32_t tid, const xsb_triplet *T, int64_t count, int32_t flavour);
+
 /* Number of staged insertions (an upper bound of nnznew(A), genericextendable...:21). */
 int32_t xsb_pending(const xsb_matrix *h, int64_t *count);
 
@@ -227,6 +242,19 @@ int32_t xsb_eliminate_dirichlet(xsb_matrix *h, const uint8_t *marker);
 /* 64-bit fingerprint of (colptr,rowval): stands in for phash (sparsematrixcsc.jl:74);
  * equal patterns give equal values, it is NOT Julia's hash(). */
 int32_t xsb_pattern_hash(xsb_matrix *h, uint64_t *hash_out);
+
+/* pointblock(A, blocksize): src/matrix/extendable.jl:292-318 (feeds PointBlockILUZeroPreconditioner,
+ * src/factorizations/iluzero.jl:61-71).  Returns a NEW handle *out holding the nblock x nblock block
+ * matrix Ab, nblock = n / blocksize: its CSC pattern is read with xsb_nnz / xsb_fetch_csc, its values
+ * -- one dense blocksize x blocksize block per pattern entry, column-major (SMatrix layout), in CSC
+ * order -- with xsb_fetch_blocks.  As in the reference the block index taken from A's COLUMN becomes
+ * the block ROW: Ab[(i-1)/bs+1, (j-1)/bs+1][(i-1)%bs+1, (j-1)%bs+1] = A[j,i] for every stored A[j,i]
+ * (the reference's loop variable i runs over columns).  An entry that falls outside nblock blocks is
+ * the reference's BoundsError (XSB_EBOUNDS).  Pending inserts: XSB_ESTATE (flush first).  The caller
+ * destroys *out with xsb_destroy; it is a result, not an assembly target. */
+int32_t xsb_pointblock(xsb_matrix *h, int32_t blocksize, xsb_matrix **out);
+int32_t xsb_block_size(const xsb_matrix *hb, int32_t *blocksize);
+int32_t xsb_fetch_blocks(xsb_matrix *hb, void *blocks_out);
 
 /* ------------------------------------------------------------------ */
 /* on-device emitters of the benchmark insertion streams               */

@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         sig("ora_ext_insert_batch", _i64, _p, _p, _p, _p, _i64, C.c_int)
         sig("ora_ext_mark_dirichlet", None, _p, _f64, _p)
         sig("ora_ext_eliminate_dirichlet", None, _p, _p)
+        sig("ora_ext_pointblock", _i64, _p, _i64, _p, _p, _p)
         sig("ora_mt_create", _p, _i64, _i64, _i64)
         sig("ora_mt_destroy", None, _p)
         sig("ora_mt_update", C.c_int, _p, _f64, _i64, _i64, _i64, C.c_int)
@@ -251,6 +252,22 @@ class OracleExt:
     def eliminate_dirichlet(self, marker):
         mk = np.ascontiguousarray(marker, dtype=np.uint8)
         lib().ora_ext_eliminate_dirichlet(self._h, _ptr(mk))
+
+
+def _ext_pointblock(self, bs):
+    """pointblock(A, bs) (extendable.jl:292-318): (colptr, rowval, blocks[nnzb, bs*bs] column-major), 1-based."""
+    bs = int(bs)
+    cap = max(1, self.nnz)
+    cp = np.empty(self.n // bs + 1, np.int64)
+    rv = np.empty(cap, np.int64)
+    bl = np.zeros(cap * bs * bs, np.float64)
+    r = lib().ora_ext_pointblock(self._h, bs, _ptr(cp), _ptr(rv), _ptr(bl))
+    if r < 0:
+        raise OracleBoundsError(f"entry {-r - 1} falls outside the block matrix")
+    return cp, rv[:r].copy(), bl[: r * bs * bs].reshape(r, bs * bs).copy()
+
+
+OracleExt.pointblock = _ext_pointblock
 
 
 class OracleMT:

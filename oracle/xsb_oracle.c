@@ -630,6 +630,64 @@ void ora_ext_eliminate_dirichlet(ora_ext *e, const uint8_t *marker)
     }
 }
 
+/* pointblock(A0, blocksize): src/matrix/extendable.jl:292-318.
+ * A = SparseMatrixCSC(A0) (flushes), nblock = n / blocksize, Ab = ExtendableSparseMatrixCSC of
+ * nblock x nblock SMatrix{bs,bs} blocks.  The loop visits column i, entries k, row j = rowval[k]:
+ *   iblock = (i-1)/bs+1 (from the COLUMN), jblock = (j-1)/bs+1 (from the ROW), ii, jj likewise;
+ *   block[ii,jj] = nzval[k]; rawupdateindex!(Ab, +, block, iblock, jblock); block[ii,jj] = 0
+ * then flush!(Ab).  Restated with the scalar machinery above: the PATTERN of Ab is what the same
+ * rawupdateindex! calls build in a scalar matrix (a block-valued LNK buffer links the same slots in
+ * the same order); the VALUES are the block sums in call order, zero(Tb) + block for the call that
+ * creates the entry (sparsematrixlnk.jl:242,251), acc + block after that (:247), all bs*bs
+ * components each time.  Blocks are column-major (SMatrix layout), in CSC order of Ab.
+ * colptr_out[nblock+1]; rowval_out / blocks_out sized for nnz(A) entries / nnz(A)*bs*bs values.
+ * Returns nnz(Ab), or -(k+1) when entry k of A falls outside the block matrix (BoundsError). */
+i64 ora_ext_pointblock(ora_ext *e, i64 bs, i64 *colptr_out, i64 *rowval_out, double *blocks_out)
+{
+    ora_ext_flush(e);
+    const ora_csc *A = e->csc;
+    const i64 n = A->n, nb = n / bs;
+    if (bs < 1 || nb < 1)
+        return -1;
+    ora_ext *P = ora_ext_create(nb, nb);
+    i64 k0 = 0;
+    for (i64 i = 1; i <= n; i++)
+        for (i64 k = A->colptr[i - 1]; k < A->colptr[i]; k++, k0++)
+        {
+            i64 j = A->rowval[k - 1];
+            i64 iblock = (i - 1) / bs + 1, jblock = (j - 1) / bs + 1;
+            if (ora_ext_rawupdateindex(P, 0.0, iblock, jblock))
+            {
+                ora_ext_destroy(P);
+                return -(k0 + 1);
+            }
+        }
+    ora_ext_flush(P);
+    const i64 nnzb = csc_nnz(P->csc);
+    memcpy(colptr_out, P->csc->colptr, sizeof(i64) * (size_t)(nb + 1));
+    memcpy(rowval_out, P->csc->rowval, sizeof(i64) * (size_t)nnzb);
+    unsigned char *created = (unsigned char *)calloc((size_t)(nnzb ? nnzb : 1), 1);
+    double *block = (double *)calloc((size_t)(bs * bs), sizeof(double));
+    for (i64 i = 1; i <= n; i++)
+        for (i64 k = A->colptr[i - 1]; k < A->colptr[i]; k++)
+        {
+            i64 j = A->rowval[k - 1];
+            i64 iblock = (i - 1) / bs + 1, jblock = (j - 1) / bs + 1;
+            i64 ii = (i - 1) % bs + 1, jj = (j - 1) % bs + 1;
+            block[(ii - 1) + (jj - 1) * bs] = A->nzval[k - 1];
+            i64 pos = csc_findindex(P->csc, iblock, jblock); /* 1-based slot of Ab[iblock,jblock] */
+            double *acc = blocks_out + (size_t)(pos - 1) * (size_t)(bs * bs);
+            for (i64 c = 0; c < bs * bs; c++)
+                acc[c] = (created[pos - 1] ? acc[c] : 0.0) + block[c];
+            created[pos - 1] = 1;
+            block[(ii - 1) + (jj - 1) * bs] = 0.0;
+        }
+    free(created);
+    free(block);
+    ora_ext_destroy(P);
+    return nnzb;
+}
+
 /* ------------------------------------------------------------------ */
 /* Multi-partition path: GenericMTExtendableSparseMatrixCSC with        */
 /* SparseMatrixDILNKC buffers (src/ExtendableSparse.jl:35-39).          */

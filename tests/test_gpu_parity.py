@@ -95,6 +95,74 @@ def test_readme_example(xsb):
     assert A.nnz == 28 and np.array_equal(S, T)
 
 
+def triplets(xsb, I, J, V):
+    T = np.empty(len(V), xsb.capi.TRIPLET_DTYPE)
+    T["row"], T["col"], T["val"] = I, J, V
+    return T
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_insert_triplets_equals_insert_batch(xsb, oracle, where):
+    """xsb_insert_triplets: the k-th 16-byte triplet is the k-th updateindex!/rawupdateindex!/setindex!
+    call (extendable.jl:159-218); host arrays land in the staging buffer and are rewritten in place."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(77)
+    m, n, cnt = 57, 43, 20000
+    I = rng.integers(1, m + 1, cnt)
+    J = rng.integers(1, n + 1, cnt)
+    V = rng.standard_normal(cnt)
+    V[rng.random(cnt) < 0.1] = 0.0
+    h = xsb.Handle(m, n)
+    A = oracle.OracleExt(m, n)
+    for k, fl in enumerate((xsb.UPDATE, xsb.RAW, xsb.ASSIGN, xsb.UPDATE)):
+        sl = slice(k * cnt // 4, (k + 1) * cnt // 4)
+        T = triplets(xsb, I[sl], J[sl], V[sl])
+        if where == "device":
+            dT = torch.from_numpy(T.view(np.uint8)).cuda()
+            h.insert_triplets(dT, fl, 0, len(T))
+        else:
+            h.insert_triplets(T, fl)
+        if k == 1:  # a (I, J, V) batch between two triplet batches keeps the call order
+            h.insert_batch(I[:50], J[:50], V[:50], xsb.UPDATE)
+            A.insert_batch(I[sl], J[sl], V[sl], fl)
+            A.insert_batch(I[:50], J[:50], V[:50], oracle.UPDATE)
+        else:
+            A.insert_batch(I[sl], J[sl], V[sl], fl)
+        if k == 2:
+            h.flush()
+            A.flush()
+    h.flush()
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+def test_insert_triplets_fem_stream_and_bounds(xsb, oracle):
+    I, J, V = oracle.fem_stream(9, 8, 7)
+    n = 9 * 8 * 7
+    h = xsb.Handle(n, n)
+    h.insert_triplets(triplets(xsb, I, J, V), xsb.RAW)
+    assert h.pending == len(V)
+    h.flush()
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.RAW)
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    bad = triplets(xsb, [1, n + 1, 1], [1, 1, 1], [1.0, 1.0, 1.0])
+    with pytest.raises(IndexError) as e:
+        h.insert_triplets(bad, xsb.UPDATE)
+    assert "entry 1" in str(e.value) and h.pending == 0
+    for i, j in [(0, 1), (1, 0), (1, n + 1), (2 ** 32 - 1, 1)]:
+        with pytest.raises(IndexError):
+            h.insert_triplets(triplets(xsb, [i], [j], [1.0]), xsb.RAW)
+    assert h.flush()[1] is False
+    # 0-based handles: index 0 is valid, n is not
+    h0 = xsb.Handle(4, 4, index_base=0)
+    h0.insert_triplets(triplets(xsb, [0, 3], [0, 3], [1.0, 2.0]), xsb.UPDATE)
+    with pytest.raises(IndexError):
+        h0.insert_triplets(triplets(xsb, [4], [0], [1.0]), xsb.UPDATE)
+    assert h0.flush() == (2, True)
+    cp, rv, nz = h0.fetch_csc_numpy()
+    assert cp.tolist() == [0, 1, 1, 1, 2] and rv.tolist() == [0, 3] and nz.tolist() == [1.0, 2.0]
+
+
 def test_bounds_error_rejects_batch(xsb):
     h = xsb.Handle(4, 5)
     I = np.array([1, 2, 5, 1], np.int64)
@@ -792,3 +860,66 @@ def test_grouping_fdrand_large(xsb, oracle):
     A = oracle.OracleExt(N, N)
     A.insert_batch(I, J, V, oracle.UPDATE)
     assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+
+
+# ---------------------------------------------------------------- pointblock
+@pytest.mark.parametrize("case", ["fd_bs4_i64", "fem_bs3_i32", "rd_bs4_big"])
+def test_pointblock_matches_oracle(xsb, oracle, case):
+    """pointblock(A, blocksize), src/matrix/extendable.jl:292-318: pattern and blocks bit for bit."""
+    if case == "fd_bs4_i64":
+        I, J, V = oracle.fdrand_stream(6, 4, 2, seed=5)
+        n, bs, idx = 48, 4, xsb.I64
+    elif case == "fem_bs3_i32":
+        I, J, V = oracle.fem_stream(6, 5, 4)
+        n, bs, idx = 120, 3, xsb.I32
+    else:  # enough entries for the grouping path of the block-pattern flush
+        I, J, V = oracle.blockrd_stream(12, 10, 8, 4, seed=3)
+        n, bs, idx = 4 * 960, 4, xsb.I64
+    V = V.copy()
+    V[::97] = -0.0
+    h = xsb.Handle(n, n, idx_type=idx)
+    dt = np.int64 if idx == xsb.I64 else np.int32
+    h.insert_batch(I.astype(dt), J.astype(dt), V, xsb.RAW)
+    h.flush()
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.RAW)
+    ocp, orv, obl = A.pointblock(bs)
+    hb = h.pointblock(bs)
+    cp, rv, _ = hb.fetch_csc_numpy()
+    bl = hb.fetch_blocks_numpy().reshape(hb.nnz, bs * bs)
+    assert hb.nnz == len(orv)
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+    assert np.array_equal(bits(bl), bits(obl)), "blocks not bit-exact"
+    hb.close()
+    # the source matrix is untouched and can be converted again
+    hb2 = h.pointblock(1)
+    assert hb2.nnz == h.nnz
+    hb2.close()
+
+
+def test_pointblock_errors_and_mirror(xsb, oracle):
+    h = xsb.Handle(5, 5)
+    h.insert_batch(np.array([1, 2], np.int64), np.array([1, 5], np.int64), np.ones(2), xsb.RAW)
+    with pytest.raises(xsb.XsbError):  # pending inserts
+        h.pointblock(2)
+    h.flush()
+    with pytest.raises(IndexError) as e:  # column 5 -> block row 3 of a 2x2 block matrix
+        h.pointblock(2)
+    assert "entry 1" in str(e.value)
+    with pytest.raises(xsb.XsbError):
+        h.pointblock(6)
+    # host mirror on the hand vector of tests/test_oracle_kat.py::test_pointblock_hand_vector
+    import operator
+
+    A = xsb.ExtendableSparseMatrix(4, 4)
+    for v, i, j in [(1.0, 1, 1), (2.0, 2, 1), (3.0, 3, 2), (4.0, 1, 4), (-0.0, 4, 4)]:
+        A.rawupdateindex(operator.add, v, i, j)
+    cp, rv, blocks = xsb.pointblock(A, 2)
+    assert cp.tolist() == [1, 3, 5] and rv.tolist() == [1, 2, 1, 2]
+    assert blocks[0].tolist() == [[1.0, 2.0], [0.0, 0.0]] and blocks[1].tolist() == [[0.0, 0.0], [4.0, 0.0]]
+    assert blocks[2].tolist() == [[0.0, 0.0], [3.0, 0.0]] and not np.signbit(blocks).any()
+    # an empty matrix gives an empty block matrix
+    E = xsb.Handle(6, 6)
+    hb = E.pointblock(3)
+    assert hb.nnz == 0 and hb.fetch_csc_numpy()[0].tolist() == [1, 1, 1]
+    hb.close()

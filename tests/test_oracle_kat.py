@@ -331,3 +331,48 @@ def test_dirichlet(oracle):
     D = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(n, n)).toarray()
     for d in (0, 10, 20):
         assert D[d, d] == 1.0 and np.count_nonzero(D[d, :]) == 1 and np.count_nonzero(D[:, d]) == 1
+
+
+def test_pointblock_hand_vector(oracle):
+    """pointblock (src/matrix/extendable.jl:292-318), stepped through by hand on a 4x4 matrix with
+    blocksize 2: the block index of A's COLUMN becomes the block row, single-entry blocks are summed."""
+    A = oracle.OracleExt(4, 4)
+    for v, i, j in [(1.0, 1, 1), (2.0, 2, 1), (3.0, 3, 2), (4.0, 1, 4), (-0.0, 4, 4)]:
+        A.rawupdateindex(v, i, j)
+    cp, rv, bl = A.pointblock(2)
+    assert cp.tolist() == [1, 3, 5] and rv.tolist() == [1, 2, 1, 2]
+    # column-major blocks: [b11, b21, b12, b22]
+    assert bl.tolist() == [[1.0, 0.0, 2.0, 0.0], [0.0, 4.0, 0.0, 0.0], [0.0, 3.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]]
+    assert not np.signbit(bl).any()  # zero(Tb) + block: -0.0 becomes +0.0
+    # blocksize 1: Ab[i,j] = A[j,i]
+    cp1, rv1, bl1 = A.pointblock(1)
+    S = sp.csc_matrix((A.csc()[2], A.csc()[1] - 1, A.csc()[0] - 1), shape=(4, 4))
+    T = sp.csc_matrix((bl1[:, 0], rv1 - 1, cp1 - 1), shape=(4, 4))
+    assert np.array_equal(T.toarray(), S.toarray().T)
+    # an entry beyond nblock*blocksize is the reference's BoundsError
+    B = oracle.OracleExt(5, 5)
+    B.rawupdateindex(1.0, 1, 1)
+    B.rawupdateindex(1.0, 2, 5)
+    with pytest.raises(IndexError):
+        B.pointblock(2)
+    B2 = oracle.OracleExt(5, 5)
+    B2.rawupdateindex(1.0, 4, 3)
+    assert B2.pointblock(2)[1].tolist() == [2]
+
+
+def test_pointblock_dense_property(oracle):
+    """Every stored A[j,i] lands at Ab[(i-1)/bs+1, (j-1)/bs+1][(i-1)%bs+1, (j-1)%bs+1]; nothing else is set."""
+    I, J, V = oracle.fdrand_stream(6, 4, 2, seed=5)
+    n, bs = 48, 4
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    cp, rv, nz = A.csc()
+    D = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(n, n)).toarray()
+    bcp, brv, bl = A.pointblock(bs)
+    nb = n // bs
+    R = np.zeros((n, n))
+    for jb in range(nb):
+        for k in range(bcp[jb] - 1, bcp[jb + 1] - 1):
+            ib = brv[k] - 1
+            R[ib * bs:(ib + 1) * bs, jb * bs:(jb + 1) * bs] = bl[k].reshape(bs, bs).T  # column-major block
+    assert np.array_equal(R, D.T)
