@@ -70,7 +70,7 @@ class FlushStats(C.Structure):
         ("direct_fold", C.c_int32),
         ("preagg_records", C.c_int64),
         ("ms_preagg", C.c_float),
-        ("reserved_", C.c_float),
+        ("precounted", C.c_float),
     ]
 
     def as_dict(self):
@@ -134,6 +134,7 @@ SIGNATURES = {
     "xsb_set_strategy": (_i32, [_p, _i32]),
     "xsb_mul": (_i32, [_p, _p, _p]),
     "xsb_set_grouping": (_i32, [_p, _i32]),
+    "xsb_set_precount": (_i32, [_p, _i32]),
     "xsb_set_preaggregation": (_i32, [_p, _i32]),
     "xsb_get_flush_stats": (_i32, [_p, C.POINTER(FlushStats)]),
     "xsb_kernel_launches": (_i32, [_p, C.POINTER(_i64)]),
@@ -444,6 +445,10 @@ class Handle:
         """GROUPING_AUTO (two-pass grouping by column when the stream has column locality), GROUPING_OFF
         (always the radix sort) or GROUPING_ON (always try)."""
         self._c(lib().xsb_set_grouping(self._h, int(grouping)))
+
+    def set_precount(self, on=True):
+        """Counting at insertion (default on): pack / emit kernels also take the grouping's per-chunk column histograms."""
+        self._c(lib().xsb_set_precount(self._h, 1 if on else 0))
 
     def set_preaggregation(self, on=True):
         self._c(lib().xsb_set_preaggregation(self._h, 1 if on else 0))

@@ -234,6 +234,9 @@ struct xsb_matrix
             }
         }
         has_assign = false;
+        pre.counted = 0;
+        pre.colled = 0;
+        pre.dead = false;
         if (tileflags)
             cudaMemsetAsync(tileflags, 0, (size_t)tileflags_cap, stream);
     }
@@ -258,9 +261,31 @@ struct xsb_matrix
     bool no_direct_fold = false; // the one-pass fold met columns it cannot take: park + compact instead
     int stats_direct = 0;
     i64 stats_preagg = 0;
+    i64 stats_precounted = 0;
     bool preagg = false;   // xsb_set_preaggregation
     int preagg_misses = 0; // consecutive XSB_FAST flushes whose windows held few duplicates
     u32 fold_hint = 0; // most distinct rows a column held in the previous thread-per-column fold
+    // "count rides along with insertion": the kernels that stage records (pack / emit) take the column
+    // histograms of whole chunks while the records are in registers / shared memory; the flush counts
+    // only what is left (xsb_group.cu).  Single-partition, non-slab handles assembling from an empty CSC.
+    struct PreCountState
+    {
+        void *ws = nullptr;   // grouping workspace laid out for cap_records
+        Rec *pairs = nullptr; // pair list
+        u32 *cols = nullptr;  // column id of every staged record (producers that do not count themselves)
+        i64 cap_records = 0;
+        i64 counted = 0;      // staged records of partition 0 already counted (a whole number of chunks)
+        i64 colled = 0;       // >= counted: staged records [counted, colled) have their column id in cols[]
+        bool dead = false;    // this assembly cannot use what was counted (stage grew, batch rejected)
+    } pre;
+    bool precount = true; // xsb_set_precount
+    void precount_release()
+    {
+        dfree(pre.ws);
+        dfree(pre.pairs);
+        dfree(pre.cols);
+        pre = PreCountState{};
+    }
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
     {
@@ -494,6 +519,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats_pairs = 0;
     h->stats_direct = 0;
     h->stats_preagg = 0;
+    h->stats_precounted = 0;
     REQUIRE((u64)total < (1ull << 40), XSB_EINVAL, "too many staged entries");
 
     // ---- input buffer A = [old CSC as records | staged records in tid order]
@@ -638,9 +664,24 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             colfold_lists(cws, (u64)total, h->n, &nzcol, &nzstart, &totals);
             int pair_passes = 0;
             u64 npairs = 0;
+            // chunks whose column histograms were taken when they were staged (pack / emit kernels)
+            PreCounted pc{};
+            const PreCounted *ppc = nullptr;
+            if (h->pre.colled > 0 && !h->pre.dead && a_is_stage0 && !preagged && !tomb && nnz_old == 0 && front == 0 &&
+                h->pre.cap_records >= total && h->pre.colled <= n_ins)
+            {
+                pc.ws = h->pre.ws;
+                pc.pairs = h->pre.pairs;
+                pc.cap_records = (u64)h->pre.cap_records;
+                pc.counted_chunks = (u32)(h->pre.counted / group_chunk_records());
+                pc.cols = h->pre.cols;
+                pc.cols_chunks = (u32)(h->pre.colled / group_chunk_records());
+                ppc = &pc;
+                h->stats_precounted = h->pre.colled;
+            }
             grouped = group_by_column(s, A, B, (u64)total, h->L, gws, ws, nzcol, nzstart, totals, h->h_scal + 4,
                                       h->d_scal + 4, h->lc, tp, &pair_passes, &npairs,
-                                      tomb ? h->L.ownershift() : -1, (u32)h->rank, pord);
+                                      tomb ? h->L.ownershift() : -1, (u32)h->rank, pord, ppc);
             h->dfree(gws);
             h->stats_pairs = (i64)npairs;
             if (grouped)
@@ -810,6 +851,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.group_pairs = h->stats_pairs;
     h->stats.direct_fold = h->stats_direct;
     h->stats.preagg_records = h->stats_preagg;
+    h->stats.precounted = n_ins > 0 ? (float)((double)h->stats_precounted / (double)n_ins) : 0.f;
     if (tp)
     {
         XSB_CUDA(cudaEventRecord(e1, s));
@@ -865,6 +907,66 @@ Rec *begin_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
     h->ensure_stage(tid, count);
     Stage &st = h->stage[tid];
     return st.buf + st.front + st.count;
+}
+
+// XSB_PRECOUNT=0 switches counting-at-insertion off for every handle (A-B measurements)
+const bool g_precount_off = []() {
+    const char *e = getenv("XSB_PRECOUNT");
+    return e && *e == '0';
+}();
+
+// Called after begin_emit: may the producer of the next `count` records of partition `tid` help the
+// flush's counting pass?  Two kinds of help:
+//   counts == true : the producer counts its whole chunks itself (pack kernels); *ct / *chunk0 say where
+//                    the pairs go and which chunk the batch starts at.  Needs everything staged so far counted.
+//   counts == false: the producer only leaves the column id of every record in *cols (emit kernels, whose
+//                    shared memory is taken by the transposition); everything staged so far must be counted
+//                    or have its column ids.
+bool precount_begin(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count, bool counts, CountTarget *ct, u32 *chunk0,
+                    u32 **cols)
+{
+    if (!h->precount || g_precount_off || h->n_tid != 1 || h->nranks != 0 || tid != 0)
+        return false;
+    if (flavour == XSB_ASSIGN || h->has_assign || h->nnz != 0 || h->strategy != XSB_STRATEGY_AUTO)
+        return false;
+    if (h->grouping == XSB_GROUPING_OFF || (h->grouping == XSB_GROUPING_AUTO && h->grouping_misses >= 2))
+        return false;
+    Stage &st = h->stage[0];
+    const i64 W = group_chunk_records();
+    if (h->pre.dead || st.front != 0 || st.count != h->pre.colled || count < W)
+        return false;
+    if (counts && h->pre.colled != h->pre.counted)
+        return false;
+    if (!group_supported(h->L, (u64)std::max<i64>(st.cap, 32768), h->n) || !colfold_supported(h->L, (u64)st.cap, h->n))
+        return false;
+    if (st.count == 0)
+    { // a new assembly: size the workspace for the stage, clear the pair ticket
+        if (h->pre.cap_records < st.cap || h->pre.cap_records > 2 * st.cap)
+        {
+            h->precount_release();
+            h->pre.ws = h->dalloc(group_workspace_bytes((u64)st.cap));
+            h->pre.pairs = static_cast<Rec *>(h->dalloc(sizeof(Rec) * group_pair_capacity((u64)st.cap)));
+            h->pre.cap_records = st.cap;
+        }
+        group_precount_reset(h->stream, h->pre.ws);
+    }
+    else if (st.cap > h->pre.cap_records)
+    { // the stage grew under chunks that were counted into a smaller workspace
+        h->pre.dead = true;
+        return false;
+    }
+    if (counts)
+    {
+        *ct = group_count_target(h->pre.ws, h->pre.pairs, (u64)h->pre.cap_records, h->L);
+        *chunk0 = (u32)(st.count / W);
+    }
+    else
+    {
+        if (!h->pre.cols)
+            h->pre.cols = static_cast<u32 *>(h->dalloc(sizeof(u32) * (size_t)h->pre.cap_records));
+        *cols = h->pre.cols + st.count;
+    }
+    return true;
 }
 
 void end_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
@@ -1153,6 +1255,7 @@ int32_t xsb_destroy(xsb_matrix *h)
     h->drop_frozen();
     h->drop_blocks();
     h->clear_staging(true);
+    h->precount_release();
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
     h->dfree(h->route_ws);
@@ -1243,7 +1346,10 @@ int32_t xsb_shrink_to_fit(xsb_matrix *h)
         REQUIRE(h, XSB_EINVAL, "NULL handle");
         h->shrink_store();
         if (h->pending() == 0)
+        {
             h->clear_staging(true);
+            h->precount_release();
+        }
         h->release_cache();
         return XSB_OK;
     });
@@ -1292,13 +1398,40 @@ int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *
         Rec *dst = begin_emit(h, tid, flavour, count);
         DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count), dV(h, V, 8 * (size_t)count);
         write_scalar(h, 1, ~0ull);
-        pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
-                     h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc, h->stage_flags(tid));
-        const u64 bad = read_scalar(h, 1);
+        CountTarget ct;
+        u32 chunk0 = 0;
+        i64 counted = 0;
+        u64 bad = ~0ull;
+        if (precount_begin(h, tid, flavour, count, true, &ct, &chunk0, nullptr))
+        {
+            write_scalar(h, 2, ~0ull);
+            counted = pack_records_counted(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count,
+                                           h->idx64, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
+                                           h->d_scal + 1, h->d_scal + 2, h->lc, ct, chunk0);
+            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+            bad = read_scalar(h, 1);
+            if (h->h_scal[2] != ~0ull)
+                bad = std::min(bad, h->h_scal[2] + (u64)counted);
+        }
+        else
+        {
+            pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
+                         h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc, h->stage_flags(tid));
+            bad = read_scalar(h, 1);
+        }
         if (bad != ~0ull)
+        {
+            if (counted)
+                h->pre.dead = true; // the rejected batch left pairs behind: this assembly is counted at flush time
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
                                             " of the batch is outside the matrix; batch rejected");
+        }
         end_emit(h, tid, flavour, count);
+        if (counted)
+        {
+            h->pre.counted += counted;
+            h->pre.colled = h->pre.counted;
+        }
         return XSB_OK;
     });
 }
@@ -1323,13 +1456,39 @@ int32_t xsb_insert_triplets(xsb_matrix *h, int32_t tid, const xsb_triplet *T, in
             src = dst;
         }
         write_scalar(h, 1, ~0ull);
-        pack_triplets(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
-                      h->d_scal + 1, h->lc, h->stage_flags(tid));
-        const u64 bad = read_scalar(h, 1);
+        CountTarget ct;
+        u32 chunk0 = 0;
+        i64 counted = 0;
+        u64 bad = ~0ull;
+        if (precount_begin(h, tid, flavour, count, true, &ct, &chunk0, nullptr))
+        {
+            write_scalar(h, 2, ~0ull);
+            counted = pack_triplets_counted(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid,
+                                            (u32)flavour, dst, h->d_scal + 1, h->d_scal + 2, h->lc, ct, chunk0);
+            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+            bad = read_scalar(h, 1);
+            if (h->h_scal[2] != ~0ull)
+                bad = std::min(bad, h->h_scal[2] + (u64)counted);
+        }
+        else
+        {
+            pack_triplets(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
+                          h->d_scal + 1, h->lc, h->stage_flags(tid));
+            bad = read_scalar(h, 1);
+        }
         if (bad != ~0ull)
+        {
+            if (counted)
+                h->pre.dead = true;
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
                                             " of the batch is outside the matrix; batch rejected");
+        }
         end_emit(h, tid, flavour, count);
+        if (counted)
+        {
+            h->pre.counted += counted;
+            h->pre.colled = h->pre.counted;
+        }
         return XSB_OK;
     });
 }
@@ -1690,9 +1849,13 @@ int32_t xsb_emit_p1fem_range(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t ny
         REQUIRE(0 <= cz_begin && cz_begin <= cz_end && cz_end <= nzn - 1, XSB_EINVAL, "bad cube-layer range");
         const i64 count = 20 * 6 * (nxn - 1) * (nyn - 1) * (cz_end - cz_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
+        u32 *cols = nullptr;
+        const bool helps = precount_begin(h, tid, flavour, count, false, nullptr, nullptr, &cols);
         emit_p1fem(h->stream, nxn, nyn, nzn, h->Ls, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc,
-                   h->stage_flags(tid));
+                   h->stage_flags(tid), helps ? cols : nullptr);
         end_emit(h, tid, flavour, count);
+        if (helps)
+            h->pre.colled += count;
         return XSB_OK;
     });
 }
@@ -1816,6 +1979,16 @@ int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping)
         return XSB_EINVAL;
     h->grouping = grouping;
     h->grouping_misses = 0;
+    return XSB_OK;
+}
+
+int32_t xsb_set_precount(xsb_matrix *h, int32_t enable)
+{
+    if (!h)
+        return XSB_EINVAL;
+    h->precount = enable != 0;
+    if (!h->precount && h->pre.colled > 0)
+        h->pre.dead = true;
     return XSB_OK;
 }
 

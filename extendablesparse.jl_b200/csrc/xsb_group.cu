@@ -23,116 +23,59 @@
 // (the linked lists ARE the columns there); stdlib sparse! counting sort reached from
 // src/matrix/sparsematrixdilnkc.jl:428-432.
 #include "xsb_internal.h"
+#include "xsb_group_count.cuh"
 
 namespace xsb {
 
-#ifndef XSB_GP_W
-#define XSB_GP_W 512
-#endif
-constexpr int GP_W = XSB_GP_W;      // records per chunk (one warp)
-constexpr int GP_NB = GP_W / 32;    // batches per chunk
-constexpr int GP_HBITS = 9;
-constexpr int GP_H = 1 << GP_HBITS; // hash slots per warp
-constexpr int GP_DMAX = GP_H - 96;  // distinct columns a chunk may hold; more means "no locality" anyway
-constexpr int GP_WARPS = 8;
-constexpr u32 GP_EMPTY = 0xffffffffu;
-
-__device__ __forceinline__ u32 gp_hash(u32 col) { return (col * 0x9E3779B1u) >> (32 - GP_HBITS); }
-
-struct CountSpace
-{
-    u32 key[GP_H];
-    u32 cnt[GP_H];
-    unsigned short cand[GP_H];
-};
-
-// ------------------------------------------------------------------------
-// pass 1: distinct columns of every chunk and their record counts
-// ------------------------------------------------------------------------
-// One batch of 32 consecutive records.  FULL: every lane holds a record that takes part (whole
-// chunk, no records of other ranks to skip).
-template <bool FULL>
-__device__ __forceinline__ void count_batch(CountSpace &ws, u64 key, bool valid, int colshift, u32 colmask, u32 lt,
-                                            u32 &d)
-{
-    constexpr u32 full = 0xffffffffu;
-    const u32 col = (u32)(key >> colshift) & colmask;
-    u32 peers;
-    if (FULL)
-        peers = __match_any_sync(full, col);
-    else
-    {
-        const u32 vm = __ballot_sync(full, valid);
-        peers = 0;
-        if (valid)
-            peers = __match_any_sync(vm, col);
-    }
-    // the FIRST lane that holds a column speaks for it: the table sees one request per distinct column
-    const bool leader = (FULL || valid) && (peers & lt) == 0u;
-    u32 slot = gp_hash(col);
-    bool fresh = false;
-    if (leader)
-    {
-        for (;;)
-        { // a plain look first: after a few batches nearly every column of the chunk is in the table
-            u32 k = ws.key[slot];
-            if (k == col)
-                break;
-            if (k == GP_EMPTY)
-            {
-                k = atomicCAS(&ws.key[slot], GP_EMPTY, col);
-                if (k == GP_EMPTY)
-                {
-                    fresh = true;
-                    break;
-                }
-                if (k == col)
-                    break;
-            }
-            slot = (slot + 1) & (GP_H - 1);
-        }
-    }
-    const u32 rb = __ballot_sync(full, fresh);
-    if (fresh)
-        ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
-    d += __popc(rb);
-    if (leader)
-        ws.cnt[slot] += (u32)__popc(peers); // leaders hold distinct slots of a warp-private table
-    __syncwarp();
-}
-
 __global__ void __launch_bounds__(GP_WARPS * 32, 5)
 group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, int ownershift, u32 me,
-                   u32 nchunks, u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
+                   u32 chunk0, u32 nchunks, const u32 *__restrict__ cols, u32 cols_chunks, u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
                    uint2 *__restrict__ chunkinfo, u32 cap, u32 *__restrict__ d_flags)
 {
     constexpr u32 full = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CountSpace &ws = reinterpret_cast<CountSpace *>(smem_raw)[warp];
-    const u32 chunk = blockIdx.x * GP_WARPS + warp;
+    const u32 chunk = chunk0 + blockIdx.x * GP_WARPS + warp; // chunks below chunk0 were counted when they were staged
     if (chunk >= nchunks)
         return;
     const u32 lt = lanemask_lt();
     const u64 r0 = (u64)chunk * GP_W;
     const u32 cnt_here = (u32)min((u64)GP_W, nrec - r0);
 
-    {
-        uint4 *kq = reinterpret_cast<uint4 *>(ws.key);
-#pragma unroll
-        for (int i = 0; i < GP_H / 128; ++i)
-            kq[i * 32 + lane] = make_uint4(GP_EMPTY, GP_EMPTY, GP_EMPTY, GP_EMPTY);
-        uint4 *cq = reinterpret_cast<uint4 *>(ws.cnt);
-#pragma unroll
-        for (int i = 0; i < GP_H / 128; ++i)
-            cq[i * 32 + lane] = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
+    count_space_init(ws, lane);
 
     u32 d = 0;
     bool crowded = false;
     const Rec *rec = in + r0 + lane;
-    if (cnt_here == (u32)GP_W && ownershift < 0)
+    if (chunk < cols_chunks)
+    { // the producer of this chunk left the records' column ids in cols[]: 4 instead of 16 bytes per record
+        const u32 *cp = cols + r0 + lane;
+        u32 c[4], nc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            nc[i] = cp[i * 32];
+#pragma unroll 1
+        for (int g = 0; g < GP_NB && !crowded; g += 4)
+        {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                c[i] = nc[i];
+                if (g + 4 < GP_NB)
+                    nc[i] = cp[(g + 4 + i) * 32];
+            }
+            if (d > (u32)GP_DMAX - 96u)
+                crowded = true;
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    count_batch<true>(ws, (u64)c[i] << colshift, true, colshift, colmask, lt, d);
+            }
+        }
+    }
+    else if (cnt_here == (u32)GP_W && ownershift < 0)
     { // whole chunk, every record takes part: no validity bookkeeping
         u64 key[4], nkey[4];
 #pragma unroll
@@ -198,32 +141,8 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
     (void)full;
     __syncwarp();
 
-    // ---- room for this chunk's pairs (atomic ticket: chunks land in completion order; the pair list
-    // is brought into chunk = stream order by pair_order_kernel before the sort)
-    u32 base = 0;
-    if (lane == 0)
-        base = atomicAdd(pair_total, d);
-    base = __shfl_sync(full, base, 0);
-    const bool room = !crowded && (u64)base + d <= (u64)cap;
-    if (lane == 0)
-    {
-        chunkinfo[chunk] = make_uint2(base, room ? d : 0u);
-        if (!room) // more pairs than the caller made room for: the stream has no column locality
-            atomicExch(d_flags, 1u);
-    }
-    if (!room)
-        return;
-    for (u32 j = lane; j < d; j += 32)
-    {
-        const u32 slot = ws.cand[j];
-        const u32 col = ws.key[slot];
-        chunkcols[base + j] = col;
-        Rec pr;
-        pr.key = (u64)col;
-        const u64 payload = ((u64)(base + j) << 16) | (u64)ws.cnt[slot];
-        pr.val = __longlong_as_double((long long)payload);
-        st_rec(pairs + base + j, pr);
-    }
+    CountTarget ct{pair_total, d_flags, pairs, chunkcols, chunkinfo, cap, colshift, colmask};
+    count_publish(ws, ct, chunk, d, crowded, lane);
 }
 
 // ------------------------------------------------------------------------
@@ -584,6 +503,28 @@ GpLayout gp_layout(u64 nrec)
 } // namespace
 
 size_t group_workspace_bytes(u64 nrec) { return gp_layout(nrec).bytes; }
+size_t group_pair_capacity(u64 nrec) { return (size_t)gp_layout(nrec).cap + 1; }
+
+CountTarget group_count_target(void *workspace, Rec *pairs, u64 cap_records, const KeyLayout &L)
+{
+    const GpLayout l = gp_layout(cap_records);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    CountTarget ct{};
+    ct.pair_total = reinterpret_cast<u32 *>(ws + l.off_ticket);
+    ct.flags = ct.pair_total + 1;
+    ct.pairs = pairs;
+    ct.chunkcols = reinterpret_cast<u32 *>(ws + l.off_chunkcols);
+    ct.chunkinfo = reinterpret_cast<uint2 *>(ws + l.off_chunkinfo);
+    ct.cap = l.cap;
+    ct.colshift = L.low + L.rowbits;
+    ct.colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
+    return ct;
+}
+
+void group_precount_reset(cudaStream_t stream, void *workspace)
+{ // pair ticket and too-many flag (gp_layout puts them first)
+    XSB_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
+}
 int group_chunk_records() { return GP_W; }
 
 bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols)
@@ -601,10 +542,11 @@ void colscan_scan_launch(cudaStream_t stream, u64 *trec, u32 *tnz, i64 nt, u64 *
 bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
                      void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
                      LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out, int ownershift, u32 me,
-                     const ChunkOrder *order)
+                     const ChunkOrder *order, const PreCounted *pre)
 {
-    const GpLayout l = gp_layout(nrec);
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    // pre: the producers of the first pre->counted_chunks chunks already appended their pairs
+    const GpLayout l = gp_layout(pre ? pre->cap_records : nrec);
+    unsigned char *ws = static_cast<unsigned char *>(pre ? pre->ws : workspace);
     u32 *pair_total = reinterpret_cast<u32 *>(ws + l.off_ticket);
     u32 *flags = pair_total + 1;
     uint2 *chunkinfo = reinterpret_cast<uint2 *>(ws + l.off_chunkinfo);
@@ -625,18 +567,24 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
         attr = true;
     }
     Rec *pairs_a = out;
-    Rec *pairs_b = out + l.cap;
+    Rec *pairs_b = pre ? pre->pairs : out + l.cap;
 
     // ---- pass 1
     if (timer)
         timer->begin(stream);
-    XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair_total, flags
+    if (!pre || pre->counted_chunks == 0)
+        XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair_total, flags
     const int chunkbits = 0; // pair keys hold the column only
-    const unsigned cblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;
-    group_count_kernel<<<cblocks, GP_WARPS * 32, sizeof(CountSpace) * GP_WARPS, stream>>>(
-        in, nrec, colshift, colmask, ownershift, me, nchunks, pair_total, pairs_b, chunkcols, chunkinfo, l.cap, flags);
-    lc.add();
-    XSB_CUDA(cudaGetLastError());
+    const u32 chunk0 = pre ? std::min(pre->counted_chunks, nchunks) : 0u;
+    if (chunk0 < nchunks)
+    {
+        const unsigned cblocks = (nchunks - chunk0 + GP_WARPS - 1) / GP_WARPS;
+        group_count_kernel<<<cblocks, GP_WARPS * 32, sizeof(CountSpace) * GP_WARPS, stream>>>(
+            in, nrec, colshift, colmask, ownershift, me, chunk0, nchunks, pre ? pre->cols : nullptr,
+            pre ? std::min(pre->cols_chunks, nchunks) : 0u, pair_total, pairs_b, chunkcols, chunkinfo, l.cap, flags);
+        lc.add();
+        XSB_CUDA(cudaGetLastError());
+    }
     // pairs made, too-many flag
     XSB_CUDA(cudaMemcpyAsync(h_scal_pinned, pair_total, sizeof(u32), cudaMemcpyDeviceToHost, stream));
     XSB_CUDA(cudaMemcpyAsync(h_scal_pinned + 1, flags, sizeof(u32), cudaMemcpyDeviceToHost, stream));

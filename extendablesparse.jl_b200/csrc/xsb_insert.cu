@@ -9,6 +9,7 @@
 //
 // Compiled with -fmad=false: the element arithmetic must round like the CPU oracle's.
 #include "xsb_internal.h"
+#include "xsb_group_count.cuh"
 
 namespace xsb {
 
@@ -90,6 +91,143 @@ void pack_triplets(cudaStream_t stream, const void *T, i64 count, int base, i64 
                                                          tid, flavour, out, d_err, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------
+// pack + count: the same conversion, a warp per chunk of GP_W records, and the chunk's column
+// histogram (pass 1 of the grouping, xsb_group.cu) taken from the keys while they are in
+// registers -- the flush then does not read these records back just to count them.
+// ------------------------------------------------------------------------
+template <typename Ti> struct SrcIJV
+{
+    const Ti *I, *J;
+    const double *V;
+    i64 base;
+    __device__ __forceinline__ void load(i64 k, i64 &i, i64 &j, double &v) const
+    {
+        i = (i64)I[k] - base;
+        j = (i64)J[k] - base;
+        v = V[k];
+    }
+};
+struct SrcTriplet
+{
+    const uint4 *T; // may alias the output: a thread reads and writes its own 16 bytes
+    i64 base;
+    __device__ __forceinline__ void load(i64 k, i64 &i, i64 &j, double &v) const
+    {
+        const uint4 t = T[k];
+        i = (i64)t.x - base;
+        j = (i64)t.y - base;
+        v = __hiloint2double((int)t.w, (int)t.z);
+    }
+};
+
+constexpr int PC_WARPS = 8;
+
+template <class Src>
+__global__ void __launch_bounds__(PC_WARPS * 32)
+pack_count_kernel(Src src, u32 nchunks, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out,
+                  u64 *__restrict__ d_err, CountTarget ct, u32 chunk0)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 c = blockIdx.x * PC_WARPS + warp;
+    if (c >= nchunks)
+        return;
+    CountSpace &ws = reinterpret_cast<CountSpace *>(smem_raw)[warp];
+    count_space_init(ws, lane);
+    const u32 lt = lanemask_lt();
+    u32 d = 0;
+    bool crowded = false;
+    const i64 k0 = (i64)c * GP_W + lane;
+#pragma unroll 1
+    for (int g = 0; g < GP_NB; g += 4)
+    {
+        i64 i[4], j[4];
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            src.load(k0 + (g + q) * 32, i[q], j[q], v[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const i64 k = k0 + (g + q) * 32;
+            if (i[q] < 0 || i[q] >= m || j[q] < 0 || j[q] >= n)
+            { // BoundsError (sparsematrixcsc.jl:8-10): the batch is rejected, whatever is written here is dropped
+                atomicMin(d_err, (u64)k);
+                i[q] = 0;
+                j[q] = 0;
+            }
+            Rec r;
+            r.key = L.pack((u64)j[q], (u64)i[q], tid, flavour);
+            r.val = v[q];
+            if (d > (u32)GP_H - 64u)
+                crowded = true; // the table may not take another 32 columns: no column locality here
+            if (!crowded)
+                count_batch<true>(ws, r.key, true, ct.colshift, ct.colmask, lt, d);
+            st_rec(out + k, r);
+        }
+    }
+    count_publish(ws, ct, chunk0 + c, d, crowded, lane);
+}
+
+template <class Src>
+static void launch_pack_count(cudaStream_t stream, Src src, i64 nchunks, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour,
+                              Rec *out, u64 *d_err, const CountTarget &ct, u32 chunk0, LaunchCounter &lc)
+{
+    static bool attr = false;
+    const int smem = (int)(sizeof(CountSpace) * PC_WARPS);
+    if (!attr)
+    {
+        XSB_CUDA(cudaFuncSetAttribute(pack_count_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    const unsigned blocks = (unsigned)((nchunks + PC_WARPS - 1) / PC_WARPS);
+    pack_count_kernel<Src><<<blocks, PC_WARPS * 32, smem, stream>>>(src, (u32)nchunks, m, n, L, tid, flavour, out,
+                                                                    d_err, ct, chunk0);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// whole chunks of the batch through the fused kernel, the tail through the plain one (its first
+// offending position, relative to the tail, goes to d_err_tail); returns the records that were counted
+i64 pack_records_counted(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
+                         int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
+                         u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct, u32 chunk0)
+{
+    const i64 nchunks = count / GP_W, whole = nchunks * GP_W;
+    if (nchunks > 0)
+    {
+        if (idx64)
+            launch_pack_count(stream, SrcIJV<int64_t>{(const int64_t *)I, (const int64_t *)J, V, (i64)base}, nchunks, m, n,
+                              L, tid, flavour, out, d_err, ct, chunk0, lc);
+        else
+            launch_pack_count(stream, SrcIJV<int32_t>{(const int32_t *)I, (const int32_t *)J, V, (i64)base}, nchunks, m, n,
+                              L, tid, flavour, out, d_err, ct, chunk0, lc);
+    }
+    if (count > whole)
+    {
+        const size_t isz = idx64 ? 8 : 4;
+        pack_records(stream, static_cast<const unsigned char *>(I) + isz * (size_t)whole,
+                     static_cast<const unsigned char *>(J) + isz * (size_t)whole, V + whole, count - whole, idx64, base, m,
+                     n, L, tid, flavour, out + whole, d_err_tail, lc);
+    }
+    return whole;
+}
+
+i64 pack_triplets_counted(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
+                          u32 flavour, Rec *out, u64 *d_err, u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct,
+                          u32 chunk0)
+{
+    const i64 nchunks = count / GP_W, whole = nchunks * GP_W;
+    if (nchunks > 0)
+        launch_pack_count(stream, SrcTriplet{static_cast<const uint4 *>(T), (i64)base}, nchunks, m, n, L, tid, flavour,
+                          out, d_err, ct, chunk0, lc);
+    if (count > whole)
+        pack_triplets(stream, static_cast<const uint4 *>(T) + whole, count - whole, base, m, n, L, tid, flavour,
+                      out + whole, d_err_tail, lc, StageFlags{nullptr, 0});
+    return whole;
 }
 
 template <typename Ti>
@@ -290,9 +428,12 @@ constexpr int FEM_THREADS = 128;
 constexpr int FEM_REC = 20;
 constexpr int FEM_PITCH = FEM_REC + 1;
 
+// cols != nullptr: the block also writes the column id of every record it emits to cols[position]
+// (4 bytes per record, coalesced): the grouping's counting pass then reads those instead of the
+// 16-byte records (xsb_group.cu, PreCounted::cols).
 __global__ void __launch_bounds__(FEM_THREADS)
 emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
-                  Rec *__restrict__ out, StageFlags sf)
+                  Rec *__restrict__ out, StageFlags sf, u32 *__restrict__ cols, int colshift, u32 colmask)
 {
     // a thread's 20 records sit FEM_PITCH records apart: with a pitch of 21 (84 words) the 16-byte
     // stores of a quarter warp fall into eight different bank groups instead of two
@@ -398,24 +539,31 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     }
     __syncthreads();
     const i64 nrec = (t_last - t_first) * FEM_REC;
-    Rec *dst = out + (t_first - tet_begin) * FEM_REC;
+    const i64 pos0 = (t_first - tet_begin) * FEM_REC;
+    Rec *dst = out + pos0;
     for (i64 q = threadIdx.x; q < nrec; q += FEM_THREADS)
     {
         const int t = (int)q / FEM_REC;
-        st_staged(dst + q, s_rec[t * FEM_PITCH + ((int)q - t * FEM_REC)], L, sf, out);
+        const Rec r = s_rec[t * FEM_PITCH + ((int)q - t * FEM_REC)];
+        st_staged(dst + q, r, L, sf, out);
+        if (cols)
+            cols[pos0 + q] = (u32)(r.key >> colshift) & colmask;
     }
 }
 
+// cols != nullptr: column ids of the emitted records go to cols[0 .. count) as well
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
-                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf)
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf, u32 *cols)
 {
     const i64 per_layer = 6 * (nxn - 1) * (nyn - 1);
     const i64 tet_begin = cz_begin * per_layer, tet_end = cz_end * per_layer;
     if (tet_end <= tet_begin)
         return;
     const i64 blocks = (tet_end - tet_begin + FEM_THREADS - 1) / FEM_THREADS;
+    const int colshift = L.low + L.rowbits;
+    const u32 colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
     emit_p1fem_kernel<<<(unsigned)blocks, FEM_THREADS, 0, stream>>>(nxn, nyn, nzn, L, tid, flavour, tet_begin,
-                                                                    tet_end, out, sf);
+                                                                    tet_end, out, sf, cols, colshift, colmask);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }

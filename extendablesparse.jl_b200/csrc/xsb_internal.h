@@ -139,6 +139,36 @@ struct ChunkOrder
 {
     u32 c_old, c_own, c_low;
 };
+// where a chunk's (column, count) pairs go: fields of the grouping workspace (xsb_group.cu)
+struct CountTarget
+{
+    u32 *pair_total;  // ticket: pairs appended so far
+    u32 *flags;       // != 0: a chunk had too many distinct columns / the pair list is full
+    Rec *pairs;       // (column, ticket position << 16 | count)
+    u32 *chunkcols;   // column of pair p
+    uint2 *chunkinfo; // per chunk: (first pair, pairs)
+    u32 cap;          // room of the pair list
+    int colshift;
+    u32 colmask;
+};
+
+// Counting done ahead of the flush by the kernels that staged the records ("count rides along
+// with insertion"): the first counted_chunks chunks of the flush's input already have their pairs in
+// `pairs` and their chunkinfo / chunkcols in `ws` (laid out for cap_records records).
+struct PreCounted
+{
+    void *ws;
+    Rec *pairs;
+    u64 cap_records;
+    u32 counted_chunks;
+    // chunks [counted_chunks, cols_chunks) are not counted yet, but their producers left the column id
+    // of every record in cols[record position]: the counting pass reads 4 instead of 16 bytes per record
+    const u32 *cols;
+    u32 cols_chunks;
+};
+size_t group_pair_capacity(u64 nrec);
+CountTarget group_count_target(void *ws, Rec *pairs, u64 cap_records, const KeyLayout &L);
+void group_precount_reset(cudaStream_t stream, void *ws);
 int group_chunk_records();
 size_t group_workspace_bytes(u64 nrec);
 bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols);
@@ -146,7 +176,7 @@ bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols);
 bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
                      void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
                      LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out, int ownershift = -1,
-                     u32 me = 0, const ChunkOrder *order = nullptr);
+                     u32 me = 0, const ChunkOrder *order = nullptr, const PreCounted *pre = nullptr);
 // ownershift >= 0: records whose key >> ownershift != me belong to other ranks and are skipped
 // parked entries -> rowval / nzval
 void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, int idx64, int base,
@@ -174,6 +204,13 @@ void preaggregate_records(cudaStream_t stream, const Rec *in, u64 nrec, const Ke
 void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                   int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
                   LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
+// pack + count (xsb_insert.cu): whole chunks are counted for the grouping while they are packed
+i64 pack_records_counted(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
+                         int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
+                         u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct, u32 chunk0);
+i64 pack_triplets_counted(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
+                          u32 flavour, Rec *out, u64 *d_err, u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct,
+                          u32 chunk0);
 // pointblock (xsb_values.cu): CSC entries -> records of the block pattern; values into the blocks
 void pointblock_emit(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs, i64 nb,
                      KeyLayout Lb, Rec *out, u64 *d_err, LaunchCounter &lc);
@@ -188,7 +225,8 @@ void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones
                  u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc,
                  StageFlags sf = StageFlags{nullptr, 0});
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
-                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0},
+                u32 *cols = nullptr);
 i64 blockrd_count(i64 nx, i64 ny, i64 nz, i64 ns);
 void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,
                   u32 flavour, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});

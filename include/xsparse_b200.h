@@ -102,7 +102,8 @@ typedef struct xsb_flush_stats
     int32_t direct_fold;      /* 1: the fold wrote rowval / nzval / colptr in one pass (no park + compact) */
     int64_t preagg_records;   /* XSB_FAST: staged records left after accumulate-on-insert in windows; 0: not used */
     float ms_preagg;          /* ... and its device time (also inside ms_total)                */
-    float reserved_;
+    float precounted;         /* share of the staged records whose column histograms (grouping pass 1) were
+                                 taken by the kernels that staged them; ms_group_count covers the rest */
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */
@@ -326,6 +327,11 @@ int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping);
  * values <= 1e-14 relative, summation order not reproducible from run to run.  Off by default:
  * on B200 it only pays when the windows shrink the stream more than about 3x. */
 int32_t xsb_set_preaggregation(xsb_matrix *h, int32_t enable);
+/* Counting at insertion (default on): the kernels behind xsb_insert_batch / xsb_insert_triplets /
+ * xsb_emit_p1fem also take the per-chunk column histograms the flush's grouping needs, while the
+ * records are in registers, so the flush does not read them once more just to count.  Applies to
+ * single-partition handles assembling from an empty CSC; results are identical either way. */
+int32_t xsb_set_precount(xsb_matrix *h, int32_t enable);
 int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
 /* Total kernels launched by this handle since creation. */
 int32_t xsb_kernel_launches(const xsb_matrix *h, int64_t *count);

@@ -923,3 +923,129 @@ def test_pointblock_errors_and_mirror(xsb, oracle):
     hb = E.pointblock(3)
     assert hb.nnz == 0 and hb.fetch_csc_numpy()[0].tolist() == [1, 1, 1]
     hb.close()
+
+
+# ---------------------------------------------------------------- counting at insertion (pre-count)
+def _fem_case(oracle, n1=30):
+    I, J, V = oracle.fem_stream(n1, n1, n1)
+    n = n1 ** 3
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.RAW)
+    return I, J, V, n, A.csc()
+
+
+@pytest.mark.parametrize("producer", ["emit", "batch", "triplets"])
+def test_precount_equals_flush_time_count(xsb, oracle, producer):
+    """The column histograms taken by the staging kernels (xsb_set_precount, default on) give the bits
+    of the flush-time counting pass and of the oracle; the flush then counts (almost) nothing."""
+    n1 = 30
+    I, J, V, n, ref = _fem_case(oracle, n1)
+    out = {}
+    for on in (True, False):
+        h = xsb.Handle(n, n)
+        h.set_precount(on)
+        if producer == "emit":
+            h.emit_p1fem(n1, n1, n1, flavour=xsb.RAW)
+        elif producer == "batch":
+            h.insert_batch(I, J, V, xsb.RAW)
+        else:
+            h.insert_triplets(triplets(xsb, I, J, V), xsb.RAW)
+        h.flush()
+        st = h.flush_stats()
+        assert st["column_path"] == 3
+        if on:
+            assert st["precounted"] > 0.99
+        else:
+            assert st["precounted"] == 0.0
+        out[on] = h.fetch_csc_numpy()
+        assert_csc_equal(out[on], ref)
+        h.close()
+
+
+def test_precount_ragged_batches_and_rejections(xsb, oracle):
+    """Batches that end off a chunk boundary stop the counting at insertion (the flush counts the rest);
+    a rejected batch or a stage that grows under counted chunks makes the flush count everything."""
+    n1 = 30
+    I, J, V, n, ref = _fem_case(oracle, n1)
+    cnt = len(V)
+    W = 512
+    cuts = {
+        "aligned_then_ragged": [0, 200 * W, 200 * W + 777, 300 * W + 777, cnt],
+        "all_aligned": [0, 64 * W, 640 * W, cnt],
+        "ragged_first": [0, 100, 100 + 300 * W, cnt],
+    }
+    for name, cut in cuts.items():
+        h = xsb.Handle(n, n)
+        h.reserve(0, cnt)
+        for a, b in zip(cut[:-1], cut[1:]):
+            h.insert_batch(I[a:b], J[a:b], V[a:b], xsb.RAW)
+        h.flush()
+        st = h.flush_stats()
+        assert st["column_path"] == 3, name
+        if name == "ragged_first":
+            assert st["precounted"] == 0.0
+        else:
+            assert 0.0 < st["precounted"] <= 1.0, name
+        assert_csc_equal(h.fetch_csc_numpy(), ref)
+        h.close()
+    # rejected batch after counted chunks
+    h = xsb.Handle(n, n)
+    h.reserve(0, cnt)
+    h.insert_batch(I[:400 * W], J[:400 * W], V[:400 * W], xsb.RAW)
+    badI = I[400 * W:500 * W].copy()
+    badI[12345] = n + 7
+    with pytest.raises(IndexError) as e:
+        h.insert_batch(badI, J[400 * W:500 * W], V[400 * W:500 * W], xsb.RAW)
+    assert "entry 12345" in str(e.value)
+    badI[12345] = I[400 * W + 12345]
+    badI[-3] = 0  # in the tail handled by the plain kernel? no: whole chunks -> fused kernel reports it too
+    with pytest.raises(IndexError) as e:
+        h.insert_batch(badI, J[400 * W:500 * W], V[400 * W:500 * W], xsb.RAW)
+    assert f"entry {100 * W - 3}" in str(e.value)
+    h.insert_batch(I[400 * W:], J[400 * W:], V[400 * W:], xsb.RAW)
+    h.flush()
+    assert h.flush_stats()["precounted"] == 0.0
+    assert_csc_equal(h.fetch_csc_numpy(), ref)
+    h.close()
+    # the stage grows under counted chunks (no reserve)
+    h = xsb.Handle(n, n)
+    for a, b in [(0, 128 * W), (128 * W, 1024 * W), (1024 * W, cnt)]:
+        h.insert_batch(I[a:b], J[a:b], V[a:b], xsb.RAW)
+    h.flush()
+    assert_csc_equal(h.fetch_csc_numpy(), ref)
+    # second assembly into the now non-empty matrix: old entries shift the chunk grid, nothing is pre-counted
+    h.insert_batch(I, J, V, xsb.RAW)
+    h.flush()
+    assert h.flush_stats()["precounted"] == 0.0
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.RAW)
+    A.flush()
+    A.insert_batch(I, J, V, oracle.RAW)
+    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    # reset! starts over: counting at insertion again
+    h.reset()
+    h.insert_batch(I, J, V, xsb.RAW)
+    h.flush()
+    assert h.flush_stats()["precounted"] > 0.99
+    assert_csc_equal(h.fetch_csc_numpy(), ref)
+    h.close()
+
+
+def test_precount_tail_bounds_error(xsb):
+    """An out-of-range entry in the ragged tail of a batch (plain kernel) is reported at its batch position."""
+    h = xsb.Handle(1000, 1000)
+    cnt = 3 * 512 + 100
+    I = np.ones(cnt, np.int64)
+    J = np.ones(cnt, np.int64)
+    I[3 * 512 + 40] = 1001
+    with pytest.raises(IndexError) as e:
+        h.insert_batch(I, J, np.ones(cnt), xsb.UPDATE)
+    assert f"entry {3 * 512 + 40}" in str(e.value) and h.pending == 0
+    T = triplets(xsb, I, J, np.ones(cnt))
+    with pytest.raises(IndexError) as e:
+        h.insert_triplets(T, xsb.UPDATE)
+    assert f"entry {3 * 512 + 40}" in str(e.value) and h.pending == 0
+    I[3 * 512 + 40] = 1
+    h.insert_batch(I, J, np.ones(cnt), xsb.UPDATE)
+    assert h.flush() == (1, True)
+    assert h.fetch_csc_numpy()[2].tolist() == [float(cnt)]
