@@ -49,7 +49,8 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
     bool crowded = false;
     const Rec *rec = in + r0 + lane;
     if (chunk < cols_chunks)
-    { // the producer of this chunk left the records' column ids in cols[]: 4 instead of 16 bytes per record
+    { // the producer of this chunk left the records' column ids in cols[]: 4 instead of 16 bytes per
+      // record (kNotMine: a record another rank owns, already sent)
         const u32 *cp = cols + r0 + lane;
         u32 c[4], nc[4];
 #pragma unroll
@@ -67,11 +68,17 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
             }
             if (d > (u32)GP_DMAX - 96u)
                 crowded = true;
-            else
+            else if (ownershift < 0)
             {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     count_batch<true>(ws, (u64)c[i] << colshift, true, colshift, colmask, lt, d);
+            }
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    count_batch<false>(ws, (u64)c[i] << colshift, c[i] != kNotMine, colshift, colmask, lt, d);
             }
         }
     }

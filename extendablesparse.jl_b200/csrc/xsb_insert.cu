@@ -428,12 +428,9 @@ constexpr int FEM_THREADS = 128;
 constexpr int FEM_REC = 20;
 constexpr int FEM_PITCH = FEM_REC + 1;
 
-// cols != nullptr: the block also writes the column id of every record it emits to cols[position]
-// (4 bytes per record, coalesced): the grouping's counting pass then reads those instead of the
-// 16-byte records (xsb_group.cu, PreCounted::cols).
 __global__ void __launch_bounds__(FEM_THREADS)
 emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
-                  Rec *__restrict__ out, StageFlags sf, u32 *__restrict__ cols, int colshift, u32 colmask)
+                  Rec *__restrict__ out, StageFlags sf)
 {
     // a thread's 20 records sit FEM_PITCH records apart: with a pitch of 21 (84 words) the 16-byte
     // stores of a quarter warp fall into eight different bank groups instead of two
@@ -541,29 +538,31 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     const i64 nrec = (t_last - t_first) * FEM_REC;
     const i64 pos0 = (t_first - tet_begin) * FEM_REC;
     Rec *dst = out + pos0;
+    // column side array (StageFlags::cols): written here, in the coalesced store loop, not per record in st_staged
+    u32 *const cols = sf.cols ? sf.cols + pos0 : nullptr;
+    sf.cols = nullptr;
+    const int colshift = L.low + L.rowbits;
+    const u32 colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
     for (i64 q = threadIdx.x; q < nrec; q += FEM_THREADS)
     {
         const int t = (int)q / FEM_REC;
         const Rec r = s_rec[t * FEM_PITCH + ((int)q - t * FEM_REC)];
         st_staged(dst + q, r, L, sf, out);
         if (cols)
-            cols[pos0 + q] = (u32)(r.key >> colshift) & colmask;
+            cols[q] = (sf.flags != nullptr && L.owner(r.key) != (u32)L.self) ? kNotMine : ((u32)(r.key >> colshift) & colmask);
     }
 }
 
-// cols != nullptr: column ids of the emitted records go to cols[0 .. count) as well
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
-                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf, u32 *cols)
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf)
 {
     const i64 per_layer = 6 * (nxn - 1) * (nyn - 1);
     const i64 tet_begin = cz_begin * per_layer, tet_end = cz_end * per_layer;
     if (tet_end <= tet_begin)
         return;
     const i64 blocks = (tet_end - tet_begin + FEM_THREADS - 1) / FEM_THREADS;
-    const int colshift = L.low + L.rowbits;
-    const u32 colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
     emit_p1fem_kernel<<<(unsigned)blocks, FEM_THREADS, 0, stream>>>(nxn, nyn, nzn, L, tid, flavour, tet_begin,
-                                                                    tet_end, out, sf, cols, colshift, colmask);
+                                                                    tet_end, out, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }

@@ -225,8 +225,7 @@ void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones
                  u32 flavour, i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc,
                  StageFlags sf = StageFlags{nullptr, 0});
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
-                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0},
-                u32 *cols = nullptr);
+                i64 cz_begin, i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
 i64 blockrd_count(i64 nx, i64 ny, i64 nz, i64 ns);
 void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,
                   u32 flavour, Rec *out, LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
