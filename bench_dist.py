@@ -46,7 +46,7 @@ def run(args, xsb, rank, world, local):
     def step():
         h.reset()
         h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
-        return D.flush(mode)
+        return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
     for _ in range(args.warmup):
         step()
@@ -113,8 +113,8 @@ def run(args, xsb, rank, world, local):
 
 
 def measure_e2e(args, xsb, xd, rank, world, local, mode):
-    """End to end at N ranks with HOST buffers: every step each rank copies its (I,J,V) stream from
-    pinned host memory, inserts, routes, flushes and reads its CSC slab back to pinned host memory."""
+    """End to end at N ranks with HOST buffers: every step each rank copies its insertion stream (16-byte
+    triplets) from pinned host memory, inserts, routes, flushes and reads its CSC slab back to pinned host memory."""
     import ctypes as C
 
     emesh = args.e2e_mesh
@@ -133,13 +133,15 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
     c = xsb.capi
     c.check(c.lib().xsb_debug_fetch_staged(g._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt,
                                            C.byref(got)), g._h)
-    hI = torch.empty(cnt, dtype=torch.int64, pin_memory=True).copy_(dI)
-    hJ = torch.empty(cnt, dtype=torch.int64, pin_memory=True).copy_(dJ)
-    hV = torch.empty(cnt, dtype=torch.float64, pin_memory=True).copy_(dV)
+    # the stream as 16-byte triplets {u32 row, u32 col, f64 val} (xsb_insert_triplets), as at N=1
+    dT = torch.empty((cnt, 2), dtype=torch.int64, device="cuda")
+    dT[:, 0] = dI | (dJ << 32)
+    dT[:, 1] = dV.view(torch.int64)
+    hT = torch.empty((cnt, 2), dtype=torch.int64, pin_memory=True).copy_(dT)
     torch.cuda.synchronize()
-    del dI, dJ, dV
+    del dI, dJ, dV, dT
     g.reset()
-    g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
+    g.insert_triplets(hT, xsb.RAW, 0, cnt)
     nnz, _ = D.flush(mode)
     ocp = torch.empty(g.n + 1, dtype=torch.int64, pin_memory=True)
     orv = torch.empty(nnz, dtype=torch.int64, pin_memory=True)
@@ -147,8 +149,8 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
 
     def step():
         g.reset()
-        g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
-        D.flush(mode)
+        g.insert_triplets(hT, xsb.RAW, 0, cnt)
+        D.flush(mode, wait=False)
         g.fetch_csc(ocp, orv, onz)
 
     step()
@@ -163,14 +165,14 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
     dist.barrier()
     t = torch.tensor([ms_e2e / steps], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot = torch.tensor([cnt, 24 * cnt, 8 * (g.n + 1) + 16 * int(nnz)], dtype=torch.int64, device="cuda")
+    tot = torch.tensor([cnt, 16 * cnt, 8 * (g.n + 1) + 16 * int(nnz)], dtype=torch.int64, device="cuda")
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms = float(t.item())
     g.close()
     return {"value": int(tot[0].item()) / (ms / 1e3), "unit": "entries/s", "h2d_bytes_per_step": int(tot[1].item()),
             "d2h_bytes_per_step": int(tot[2].item()), "ms_per_step": ms,
-            "workload": f"P1-FEM {emesh}x{emesh}x{nz_nodes}-node mesh over {world} ranks, (I,J,V) from pinned host, "
-                        f"CSC slabs read back to host"}
+            "workload": f"P1-FEM {emesh}x{emesh}x{nz_nodes}-node mesh over {world} ranks, 16-byte triplets from pinned host "
+                        f"(xsb_insert_triplets), CSC slabs read back to host"}
 
 
 def run_fd(args, xsb, xd, bench, rank, world, local, dev):
@@ -189,7 +191,7 @@ def run_fd(args, xsb, xd, bench, rank, world, local, dev):
     def step():
         h.reset()
         h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=(splits[rank], splits[rank + 1]))
-        return D.flush(mode)
+        return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
     for _ in range(args.warmup):
         step()

@@ -658,7 +658,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
         if (h->grouping != XSB_GROUPING_OFF && (h->grouping == XSB_GROUPING_ON || h->grouping_misses < 2) &&
             group_supported(h->L, (u64)total, h->n))
         { // two-pass grouping through sparse per-chunk column histograms (streams with column locality)
-            void *gws = h->dalloc(group_workspace_bytes((u64)total));
+            void *gws = h->dalloc(group_workspace_bytes((u64)total, h->n));
             u32 *nzcol, *nzstart;
             u64 *totals;
             colfold_lists(cws, (u64)total, h->n, &nzcol, &nzstart, &totals);
@@ -680,7 +680,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
                 ppc = &pc;
                 h->stats_precounted = h->pre.colled;
             }
-            grouped = group_by_column(s, A, B, (u64)total, h->L, gws, ws, nzcol, nzstart, totals, h->h_scal + 4,
+            grouped = group_by_column(s, A, B, (u64)total, h->n, h->L, gws, ws, nzcol, nzstart, totals, h->h_scal + 4,
                                       h->d_scal + 4, h->lc, tp, &pair_passes, &npairs,
                                       tomb ? h->L.ownershift() : -1, (u32)h->rank, pord, ppc);
             h->dfree(gws);
@@ -947,11 +947,11 @@ bool precount_begin(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count, bool
         if (h->pre.cap_records < want || h->pre.cap_records > 2 * want)
         {
             h->precount_release();
-            h->pre.ws = h->dalloc(group_workspace_bytes((u64)want));
+            h->pre.ws = h->dalloc(group_workspace_bytes((u64)want, h->n));
             h->pre.pairs = static_cast<Rec *>(h->dalloc(sizeof(Rec) * group_pair_capacity((u64)want)));
             h->pre.cap_records = want;
         }
-        group_precount_reset(h->stream, h->pre.ws);
+        group_precount_reset(h->stream, h->pre.ws, (u64)h->pre.cap_records, h->n);
     }
     else if (st.count + count > h->pre.cap_records)
     { // the stage grew beyond the workspace the earlier chunks were counted into
@@ -960,7 +960,7 @@ bool precount_begin(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count, bool
     }
     if (counts)
     {
-        *ct = group_count_target(h->pre.ws, h->pre.pairs, (u64)h->pre.cap_records, h->L);
+        *ct = group_count_target(h->pre.ws, h->pre.pairs, (u64)h->pre.cap_records, h->n, h->L);
         *chunk0 = (u32)(st.count / W);
     }
     else

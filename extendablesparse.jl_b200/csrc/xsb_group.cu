@@ -28,10 +28,11 @@
 namespace xsb {
 
 __global__ void __launch_bounds__(GP_WARPS * 32, 5)
-group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colmask, int ownershift, u32 me,
-                   u32 chunk0, u32 nchunks, const u32 *__restrict__ cols, u32 cols_chunks, u32 *__restrict__ pair_total, Rec *__restrict__ pairs, u32 *__restrict__ chunkcols,
-                   uint2 *__restrict__ chunkinfo, u32 cap, u32 *__restrict__ d_flags)
+group_count_kernel(const Rec *__restrict__ in, u64 nrec, int ownershift, u32 me, u32 chunk0, u32 nchunks,
+                   const u32 *__restrict__ cols, u32 cols_chunks, CountTarget ct)
 {
+    const int colshift = ct.colshift;
+    const u32 colmask = ct.colmask;
     constexpr u32 full = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -148,7 +149,6 @@ group_count_kernel(const Rec *__restrict__ in, u64 nrec, int colshift, u32 colma
     (void)full;
     __syncwarp();
 
-    CountTarget ct{pair_total, d_flags, pairs, chunkcols, chunkinfo, cap, colshift, colmask};
     count_publish(ws, ct, chunk, d, crowded, lane);
 }
 
@@ -373,6 +373,282 @@ pair_emit_kernel(const Rec *__restrict__ sp, u32 npairs, int chunkbits, const u6
 }
 
 // ------------------------------------------------------------------------
+// Bucketed pair path: the pairs are NOT sorted.  The counting pass left, per column, its records and
+// its pairs (colrec / colpairs, CountTarget).  A scan over the columns gives every column its bucket
+// in a pair-sized array and its place in the output; the pairs are dropped into their column's
+// bucket (atomic cursor), each bucket -- about a handful of pairs -- is put into chunk order by the
+// thread that owns the column, and a running sum over it gives the output offset of every
+// (chunk, column).  Against the radix sort of the pairs (3 passes of 32 B per pair + pair_order):
+// two reads and one write of 8-byte bucket entries.
+// ------------------------------------------------------------------------
+constexpr int PB_TILE = 2048; // columns per tile of the per-column scan
+constexpr int PB_THREADS = 256;
+constexpr int PB_IPT = PB_TILE / PB_THREADS;
+
+// per column: its records and its pairs (L2-resident arrays, one atomic each per pair)
+__global__ void __launch_bounds__(256)
+pair_totals_kernel(const u32 *__restrict__ pair_total, u32 cap, const u32 *__restrict__ chunkcols,
+                   const unsigned short *__restrict__ chunkcnt, u32 *__restrict__ colrec, u32 *__restrict__ colpairs,
+                   u32 *__restrict__ flags, u32 ncols)
+{
+    if (*flags & 1u) // a chunk gave up (no column locality): the pair list has holes and is not used
+        return;
+    const u32 np = min(*pair_total, cap);
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride)
+    {
+        const u32 col = chunkcols[p];
+        if (col >= ncols)
+            continue;
+        atomicAdd(colrec + col, (u32)chunkcnt[p]);
+        if (atomicAdd(colpairs + col, 1u) >= kMaxColPairs)
+            atomicOr(flags, 2u); // its pairs are ordered by the radix sort, not inside one thread
+    }
+}
+
+// tile sums: a = records, b = pairs << 32 | non-empty columns
+__global__ void __launch_bounds__(PB_THREADS)
+colpair_tilesum_kernel(const u32 *__restrict__ colrec, const u32 *__restrict__ colpairs, i64 n, u64 *__restrict__ ta,
+                       u64 *__restrict__ tb)
+{
+    __shared__ u64 s_a[PB_THREADS / 32], s_b[PB_THREADS / 32];
+    const i64 b0 = (i64)blockIdx.x * PB_TILE;
+    u64 a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < PB_IPT; ++i)
+    {
+        const i64 j = b0 + i * PB_THREADS + threadIdx.x;
+        if (j < n)
+        {
+            const u32 np = colpairs[j];
+            a += colrec[j];
+            b += ((u64)np << 32) | (u64)(np != 0u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        s_a[threadIdx.x >> 5] = a;
+        s_b[threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < PB_THREADS / 32; ++w)
+        {
+            a += s_a[w];
+            b += s_b[w];
+        }
+        ta[blockIdx.x] = a;
+        tb[blockIdx.x] = b;
+    }
+}
+
+// single block: exclusive scan of both tile sums in place; totals[0] = records, totals[1] = K (non-empty columns)
+__global__ void __launch_bounds__(1024)
+colpair_scan_kernel(u64 *__restrict__ ta, u64 *__restrict__ tb, i64 nt, u64 *__restrict__ totals, u32 *__restrict__ nzstart)
+{
+    __shared__ u64 s_wa[32], s_wb[32];
+    __shared__ u64 s_ca, s_cb;
+    if (threadIdx.x == 0)
+    {
+        s_ca = 0;
+        s_cb = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (i64 b0 = 0; b0 < nt; b0 += 1024)
+    {
+        const i64 j = b0 + threadIdx.x;
+        const u64 xa = j < nt ? ta[j] : 0ull, xb = j < nt ? tb[j] : 0ull;
+        u64 va = xa, vb = xb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u64 pa = __shfl_up_sync(0xffffffffu, va, o);
+            const u64 pb = __shfl_up_sync(0xffffffffu, vb, o);
+            if (lane >= o)
+            {
+                va += pa;
+                vb += pb;
+            }
+        }
+        if (lane == 31)
+        {
+            s_wa[warp] = va;
+            s_wb[warp] = vb;
+        }
+        __syncthreads();
+        u64 pa = s_ca, pb = s_cb;
+        for (int w = 0; w < warp; ++w)
+        {
+            pa += s_wa[w];
+            pb += s_wb[w];
+        }
+        if (j < nt)
+        {
+            ta[j] = pa + va - xa;
+            tb[j] = pb + vb - xb;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023)
+        {
+            s_ca = pa + va;
+            s_cb = pb + vb;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        totals[0] = s_ca;
+        totals[1] = s_cb & 0xffffffffull;
+        nzstart[s_cb & 0xffffffffull] = (u32)s_ca; // sentinel: one past the last record
+    }
+}
+
+// per column: pstart[col] = first slot of its bucket; per non-empty column k: nzcol[k], nzstart[k]
+__global__ void __launch_bounds__(PB_THREADS)
+colpair_emit_kernel(const u32 *__restrict__ colrec, const u32 *__restrict__ colpairs, const u64 *__restrict__ ta,
+                    const u64 *__restrict__ tb, i64 n, u32 *__restrict__ pstart, u32 *__restrict__ nzcol,
+                    u32 *__restrict__ nzstart)
+{
+    __shared__ u64 s_a[PB_THREADS / 32], s_b[PB_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 b0 = (i64)blockIdx.x * PB_TILE + (i64)threadIdx.x * PB_IPT; // blocked: a thread owns PB_IPT columns
+    u32 rc[PB_IPT], np[PB_IPT];
+    u64 sa = 0, sb = 0;
+#pragma unroll
+    for (int i = 0; i < PB_IPT; ++i)
+    {
+        const i64 j = b0 + i;
+        rc[i] = j < n ? colrec[j] : 0u;
+        np[i] = j < n ? colpairs[j] : 0u;
+        sa += rc[i];
+        sb += ((u64)np[i] << 32) | (u64)(np[i] != 0u);
+    }
+    u64 ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u64 pa = __shfl_up_sync(0xffffffffu, ia, o);
+        const u64 pb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o)
+        {
+            ia += pa;
+            ib += pb;
+        }
+    }
+    if (lane == 31)
+    {
+        s_a[warp] = ia;
+        s_b[warp] = ib;
+    }
+    __syncthreads();
+    u64 ra = ia - sa, rb = ib - sb;
+    for (int w = 0; w < warp; ++w)
+    {
+        ra += s_a[w];
+        rb += s_b[w];
+    }
+    u64 rec = ta[blockIdx.x] + ra;
+    const u64 bb = tb[blockIdx.x] + rb;
+    u32 slot = (u32)(bb >> 32), k = (u32)(bb & 0xffffffffull);
+#pragma unroll
+    for (int i = 0; i < PB_IPT; ++i)
+    {
+        if (b0 + i < n)
+            pstart[b0 + i] = slot;
+        if (np[i])
+        {
+            nzcol[k] = (u32)(b0 + i);
+            nzstart[k] = (u32)rec;
+            ++k;
+        }
+        slot += np[i];
+        rec += rc[i];
+    }
+}
+
+// position of a chunk in the order the fold meets the chunks (inverse of chunk_at)
+__device__ __forceinline__ u32 chunk_pos(const ChunkOrder &o, u32 c)
+{
+    if (c < o.c_old || c >= o.c_low)
+        return c;
+    if (c >= o.c_own)                     // region of the lower ranks: met right after the old entries
+        return o.c_old + (c - o.c_own);
+    return c + (o.c_low - o.c_own);       // own region: met after the lower ranks'
+}
+
+// bucket entry: [chunk position : 23][pair (ticket) index : 31][records - 1 : 9]
+__device__ __forceinline__ u64 pb_entry(u32 pos, u32 pair, u32 cnt) { return ((u64)pos << 40) | ((u64)pair << 9) | (u64)(cnt - 1u); }
+
+// a warp per chunk: its pairs go into their columns' buckets
+__global__ void __launch_bounds__(256)
+pair_bucket_kernel(const uint2 *__restrict__ chunkinfo, u32 nchunks, ChunkOrder ord, const u32 *__restrict__ chunkcols,
+                   const unsigned short *__restrict__ chunkcnt, const u32 *__restrict__ pstart,
+                   u32 *__restrict__ pcursor, u64 *__restrict__ bucket)
+{
+    const int lane = threadIdx.x & 31;
+    const u32 c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= nchunks)
+        return;
+    const uint2 info = chunkinfo[c];
+    const u32 pos = chunk_pos(ord, c);
+    for (u32 j = lane; j < info.y; j += 32)
+    {
+        const u32 p = info.x + j;
+        const u32 col = chunkcols[p];
+        const u32 slot = pstart[col] + atomicAdd(pcursor + col, 1u);
+        bucket[slot] = pb_entry(pos, p, (u32)chunkcnt[p]);
+    }
+}
+
+// a thread per non-empty column: bucket into chunk order (insertion sort in place: the entries arrive
+// nearly in order), then offs[pair] = where the records of that (chunk, column) start in the output
+__global__ void __launch_bounds__(256)
+pair_offsets_kernel(const u32 *__restrict__ nzcol, const u32 *__restrict__ nzstart, const u64 *__restrict__ totals,
+                    const u32 *__restrict__ pstart, const u32 *__restrict__ colpairs, u64 *__restrict__ bucket,
+                    u32 *__restrict__ offs)
+{
+    const u64 K = totals[1];
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K)
+        return;
+    const u32 col = nzcol[k];
+    u64 *b = bucket + pstart[col];
+    const u32 np = colpairs[col];
+    u32 run = nzstart[k];
+    u64 prev = b[0];
+    for (u32 i = 1; i < np; ++i)
+    {
+        const u64 e = b[i];
+        if (e < prev)
+        { // out of order: insert (prev stays the largest entry so far, now at b[i])
+            u32 q = i;
+            while (q > 0 && b[q - 1] > e)
+            {
+                b[q] = b[q - 1];
+                --q;
+            }
+            b[q] = e;
+        }
+        else
+            prev = e;
+    }
+    for (u32 i = 0; i < np; ++i)
+    {
+        const u64 e = b[i];
+        offs[(u32)(e >> 9) & 0x7fffffffu] = run;
+        run += (u32)(e & 0x1ffull) + 1u;
+    }
+}
+
+// ------------------------------------------------------------------------
 // pass 2: stable scatter
 // ------------------------------------------------------------------------
 struct ScatterSpace
@@ -480,28 +756,45 @@ namespace {
 struct GpLayout
 {
     size_t off_ticket, off_chunkinfo, off_chunkcols, off_offs, off_trec, off_tnz, off_status, bytes;
+    size_t off_colrec, off_colpairs, off_pstart, off_pcursor, off_chunkcnt, off_ta, off_tb;
     u32 cap;
 };
-GpLayout gp_layout(u64 nrec)
+GpLayout gp_layout(u64 nrec, i64 ncols)
 {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const u64 nchunks = (nrec + GP_W - 1) / GP_W;
     GpLayout l{};
     l.cap = (u32)std::min<u64>(nrec / 8 * 3 + 4096, 0xfffffff0ull); // pairs we make room for (7-point FD streams: ~0.27 per record)
     const u64 ptiles = ((u64)l.cap + PS_TILE - 1) / PS_TILE;
+    const u64 ctiles = ((u64)ncols + PB_TILE - 1) / PB_TILE;
     size_t o = 0;
     l.off_ticket = o;
     o = up(o + 256);
+    // per-column totals right behind the ticket: one memset clears ticket, flags, colrec, colpairs and pcursor
+    l.off_colrec = o;
+    o = up(o + sizeof(u32) * ((size_t)ncols + 1));
+    l.off_colpairs = o;
+    o = up(o + sizeof(u32) * ((size_t)ncols + 1));
+    l.off_pcursor = o;
+    o = up(o + sizeof(u32) * ((size_t)ncols + 1));
+    l.off_pstart = o;
+    o = up(o + sizeof(u32) * ((size_t)ncols + 1));
     l.off_chunkinfo = o;
     o = up(o + sizeof(uint2) * (nchunks + 1));
     l.off_chunkcols = o;
     o = up(o + sizeof(u32) * ((size_t)l.cap + 1));
+    l.off_chunkcnt = o;
+    o = up(o + sizeof(unsigned short) * ((size_t)l.cap + 1));
     l.off_offs = o;
     o = up(o + sizeof(u32) * ((size_t)l.cap + 1));
     l.off_trec = o;
     o = up(o + sizeof(u64) * (ptiles + 1));
     l.off_tnz = o;
     o = up(o + sizeof(u32) * (ptiles + 1));
+    l.off_ta = o;
+    o = up(o + sizeof(u64) * (ctiles + 1));
+    l.off_tb = o;
+    o = up(o + sizeof(u64) * (ctiles + 1));
     l.off_status = o; // tile sums of the chunks' pair counts (pair_order kernels)
     o = up(o + sizeof(u32) * (nchunks / 256 + 2));
     l.bytes = o;
@@ -509,12 +802,12 @@ GpLayout gp_layout(u64 nrec)
 }
 } // namespace
 
-size_t group_workspace_bytes(u64 nrec) { return gp_layout(nrec).bytes; }
-size_t group_pair_capacity(u64 nrec) { return (size_t)gp_layout(nrec).cap + 1; }
+size_t group_workspace_bytes(u64 nrec, i64 ncols) { return gp_layout(nrec, ncols).bytes; }
+size_t group_pair_capacity(u64 nrec) { return (size_t)gp_layout(nrec, 1).cap + 1; }
 
-CountTarget group_count_target(void *workspace, Rec *pairs, u64 cap_records, const KeyLayout &L)
+CountTarget group_count_target(void *workspace, Rec *pairs, u64 cap_records, i64 ncols, const KeyLayout &L)
 {
-    const GpLayout l = gp_layout(cap_records);
+    const GpLayout l = gp_layout(cap_records, ncols);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     CountTarget ct{};
     ct.pair_total = reinterpret_cast<u32 *>(ws + l.off_ticket);
@@ -525,11 +818,14 @@ CountTarget group_count_target(void *workspace, Rec *pairs, u64 cap_records, con
     ct.cap = l.cap;
     ct.colshift = L.low + L.rowbits;
     ct.colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
+    ct.chunkcnt = reinterpret_cast<unsigned short *>(ws + l.off_chunkcnt);
     return ct;
 }
 
-void group_precount_reset(cudaStream_t stream, void *workspace)
-{ // pair ticket and too-many flag (gp_layout puts them first)
+void group_precount_reset(cudaStream_t stream, void *workspace, u64 cap_records, i64 ncols)
+{ // pair ticket and flags (gp_layout puts them first)
+    (void)cap_records;
+    (void)ncols;
     XSB_CUDA(cudaMemsetAsync(workspace, 0, 256, stream));
 }
 int group_chunk_records() { return GP_W; }
@@ -546,13 +842,19 @@ void colscan_scan_launch(cudaStream_t stream, u64 *trec, u32 *tnz, i64 nt, u64 *
 // sort before the scatter.  On success nzcol / nzstart / totals (workspace of xsb_colfold.cu) hold
 // the compact column list.  Returns false -- with `in` untouched and `out` undefined -- when the
 // stream has too many (chunk, column) pairs for this to pay off.
-bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
+// XSB_PAIRS=sort: always order the (chunk, column) pairs with the radix sort (A-B measurements)
+static const bool g_pairs_sort = []() {
+    const char *e = getenv("XSB_PAIRS");
+    return e && e[0] == 's';
+}();
+
+bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, i64 ncols, const KeyLayout &L, void *workspace,
                      void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
                      LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out, int ownershift, u32 me,
                      const ChunkOrder *order, const PreCounted *pre)
 {
     // pre: the producers of the first pre->counted_chunks chunks already appended their pairs
-    const GpLayout l = gp_layout(pre ? pre->cap_records : nrec);
+    const GpLayout l = gp_layout(pre ? pre->cap_records : nrec, ncols);
     unsigned char *ws = static_cast<unsigned char *>(pre ? pre->ws : workspace);
     u32 *pair_total = reinterpret_cast<u32 *>(ws + l.off_ticket);
     u32 *flags = pair_total + 1;
@@ -564,6 +866,13 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     const u32 nchunks = (u32)((nrec + GP_W - 1) / GP_W);
     const int colshift = L.low + L.rowbits;
     const u32 colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
+    u32 *colrec = reinterpret_cast<u32 *>(ws + l.off_colrec);
+    u32 *colpairs = reinterpret_cast<u32 *>(ws + l.off_colpairs);
+    u32 *pcursor = reinterpret_cast<u32 *>(ws + l.off_pcursor);
+    u32 *pstart = reinterpret_cast<u32 *>(ws + l.off_pstart);
+    unsigned short *chunkcnt = reinterpret_cast<unsigned short *>(ws + l.off_chunkcnt);
+    u64 *ta = reinterpret_cast<u64 *>(ws + l.off_ta);
+    u64 *tb = reinterpret_cast<u64 *>(ws + l.off_tb);
     static bool attr = false;
     if (!attr)
     {
@@ -580,15 +889,25 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
     if (timer)
         timer->begin(stream);
     if (!pre || pre->counted_chunks == 0)
-        XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair_total, flags
+        XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair ticket, flags
+    if (!g_pairs_sort) // per-column totals and bucket cursors of the bucketed pair path
+        XSB_CUDA(cudaMemsetAsync(ws + l.off_colrec, 0, l.off_pstart - l.off_colrec, stream));
     const int chunkbits = 0; // pair keys hold the column only
     const u32 chunk0 = pre ? std::min(pre->counted_chunks, nchunks) : 0u;
     if (chunk0 < nchunks)
     {
+        CountTarget ct{pair_total, flags, pairs_b, chunkcols, chunkinfo, l.cap, colshift, colmask, chunkcnt};
         const unsigned cblocks = (nchunks - chunk0 + GP_WARPS - 1) / GP_WARPS;
         group_count_kernel<<<cblocks, GP_WARPS * 32, sizeof(CountSpace) * GP_WARPS, stream>>>(
-            in, nrec, colshift, colmask, ownershift, me, chunk0, nchunks, pre ? pre->cols : nullptr,
-            pre ? std::min(pre->cols_chunks, nchunks) : 0u, pair_total, pairs_b, chunkcols, chunkinfo, l.cap, flags);
+            in, nrec, ownershift, me, chunk0, nchunks, pre ? pre->cols : nullptr,
+            pre ? std::min(pre->cols_chunks, nchunks) : 0u, ct);
+        lc.add();
+        XSB_CUDA(cudaGetLastError());
+    }
+    if (!g_pairs_sort)
+    { // records and pairs per column (sizes of the buckets), "a column is met by very many chunks" flag
+        pair_totals_kernel<<<kNumSM * 8, 256, 0, stream>>>(pair_total, l.cap, chunkcols, chunkcnt, colrec, colpairs, flags,
+                                                           (u32)ncols);
         lc.add();
         XSB_CUDA(cudaGetLastError());
     }
@@ -599,39 +918,66 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, con
         timer->end(stream, &StageTimes::gcount);
     XSB_CUDA(cudaStreamSynchronize(stream));
     const u32 npairs = (u32)(h_scal_pinned[0] & 0xffffffffull);
-    const bool toomany = (u32)(h_scal_pinned[1] & 0xffffffffull) != 0u;
+    const u32 fl = (u32)(h_scal_pinned[1] & 0xffffffffull);
+    const bool toomany = (fl & 1u) != 0u;
+    const bool longcol = (fl & 2u) != 0u; // some column is met by more than kMaxColPairs chunks
     *npairs_out = npairs;
     if (toomany || npairs > l.cap || npairs == 0)
         return false;
+    ChunkOrder ord = order ? *order : ChunkOrder{nchunks, nchunks, nchunks};
 
-    // ---- pairs into chunk order, then sorted by column (stable: chunk order inside a column)
-    if (timer)
-        timer->begin(stream);
+    if (!longcol && !g_pairs_sort)
+    { // ---- bucketed pair path: no sort (see above)
+        if (timer)
+            timer->begin(stream);
+        const unsigned ctiles = (unsigned)(((u64)ncols + PB_TILE - 1) / PB_TILE);
+        u64 *bucket = reinterpret_cast<u64 *>(out);
+        colpair_tilesum_kernel<<<ctiles, PB_THREADS, 0, stream>>>(colrec, colpairs, ncols, ta, tb);
+        colpair_scan_kernel<<<1, 1024, 0, stream>>>(ta, tb, (i64)ctiles, totals, nzstart);
+        colpair_emit_kernel<<<ctiles, PB_THREADS, 0, stream>>>(colrec, colpairs, ta, tb, ncols, pstart, nzcol, nzstart);
+        pair_bucket_kernel<<<(nchunks + 7) / 8, 256, 0, stream>>>(chunkinfo, nchunks, ord, chunkcols, chunkcnt, pstart,
+                                                                  pcursor, bucket);
+        const u64 kmax = std::min<u64>((u64)ncols, (u64)npairs);
+        pair_offsets_kernel<<<(unsigned)((kmax + 255) / 256), 256, 0, stream>>>(nzcol, nzstart, totals, pstart, colpairs,
+                                                                                 bucket, offs);
+        lc.add(5);
+        XSB_CUDA(cudaGetLastError());
+        *pair_passes = 0;
+        if (timer)
+            timer->end(stream, &StageTimes::sort);
+        if (timer)
+            timer->begin(stream);
+    }
+    else
     {
-        u32 *otsum = reinterpret_cast<u32 *>(ws + l.off_status);
-        const unsigned oblocks = (nchunks + PO_THREADS - 1) / PO_THREADS;
-        ChunkOrder ord = order ? *order : ChunkOrder{nchunks, nchunks, nchunks};
-        pair_order_tilesum_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, ord, otsum);
-        pair_order_scan_kernel<<<1, 1024, 0, stream>>>(otsum, oblocks);
-        pair_order_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, ord, otsum, pairs_b, pairs_a);
+        // ---- pairs into chunk order, then sorted by column (stable: chunk order inside a column)
+        if (timer)
+            timer->begin(stream);
+        {
+            u32 *otsum = reinterpret_cast<u32 *>(ws + l.off_status);
+            const unsigned oblocks = (nchunks + PO_THREADS - 1) / PO_THREADS;
+            pair_order_tilesum_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, ord, otsum);
+            pair_order_scan_kernel<<<1, 1024, 0, stream>>>(otsum, oblocks);
+            pair_order_kernel<<<oblocks, PO_THREADS, 0, stream>>>(chunkinfo, nchunks, ord, otsum, pairs_b, pairs_a);
+            lc.add(3);
+            XSB_CUDA(cudaGetLastError());
+        }
+        if (timer)
+            timer->end(stream, &StageTimes::sort);
+        const SortPlan plan = make_sort_plan(0, L.colbits);
+        *pair_passes = plan.npasses;
+        Rec *sp = radix_sort_records(stream, pairs_a, pairs_b, npairs, plan, sort_workspace, lc, timer);
+
+        // ---- offsets + column list
+        if (timer)
+            timer->begin(stream);
+        const unsigned ptiles = (npairs + PS_TILE - 1) / PS_TILE;
+        pair_tilesum_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, chunkbits, trec, tnz);
+        colscan_scan_launch(stream, trec, tnz, (i64)ptiles, totals, nzstart);
+        pair_emit_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, chunkbits, trec, tnz, offs, nzcol, nzstart);
         lc.add(3);
         XSB_CUDA(cudaGetLastError());
     }
-    if (timer)
-        timer->end(stream, &StageTimes::sort);
-    const SortPlan plan = make_sort_plan(0, L.colbits);
-    *pair_passes = plan.npasses;
-    Rec *sp = radix_sort_records(stream, pairs_a, pairs_b, npairs, plan, sort_workspace, lc, timer);
-
-    // ---- offsets + column list
-    if (timer)
-        timer->begin(stream);
-    const unsigned ptiles = (npairs + PS_TILE - 1) / PS_TILE;
-    pair_tilesum_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, chunkbits, trec, tnz);
-    colscan_scan_launch(stream, trec, tnz, (i64)ptiles, totals, nzstart);
-    pair_emit_kernel<<<ptiles, PS_THREADS, 0, stream>>>(sp, npairs, chunkbits, trec, tnz, offs, nzcol, nzstart);
-    lc.add(3);
-    XSB_CUDA(cudaGetLastError());
     (void)d_scal;
     // ---- pass 2
     const unsigned sblocks = (nchunks + GP_WARPS - 1) / GP_WARPS;

@@ -112,7 +112,7 @@ __device__ __forceinline__ void count_publish(CountSpace &ws, const CountTarget 
     {
         ct.chunkinfo[chunk] = make_uint2(base, room ? d : 0u);
         if (!room) // more pairs than the caller made room for: the stream has no column locality
-            atomicExch(ct.flags, 1u);
+            atomicOr(ct.flags, 1u);
     }
     if (!room)
         return;
@@ -120,10 +120,12 @@ __device__ __forceinline__ void count_publish(CountSpace &ws, const CountTarget 
     {
         const u32 slot = ws.cand[j];
         const u32 col = ws.key[slot];
+        const u32 cnt = ws.cnt[slot];
         ct.chunkcols[base + j] = col;
+        ct.chunkcnt[base + j] = (unsigned short)cnt;
         Rec pr;
         pr.key = (u64)col;
-        const u64 payload = ((u64)(base + j) << 16) | (u64)ws.cnt[slot];
+        const u64 payload = ((u64)(base + j) << 16) | (u64)cnt;
         pr.val = __longlong_as_double((long long)payload);
         st_rec(ct.pairs + base + j, pr);
     }

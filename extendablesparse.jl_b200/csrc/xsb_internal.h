@@ -150,7 +150,9 @@ struct CountTarget
     u32 cap;          // room of the pair list
     int colshift;
     u32 colmask;
+    unsigned short *chunkcnt; // records of pair p (1..chunk size)
 };
+constexpr u32 kMaxColPairs = 128; // a column met by more chunks than this sends the flush to the pair SORT
 
 // Counting done ahead of the flush by the kernels that staged the records ("count rides along
 // with insertion"): the first counted_chunks chunks of the flush's input already have their pairs in
@@ -167,13 +169,13 @@ struct PreCounted
     u32 cols_chunks;
 };
 size_t group_pair_capacity(u64 nrec);
-CountTarget group_count_target(void *ws, Rec *pairs, u64 cap_records, const KeyLayout &L);
-void group_precount_reset(cudaStream_t stream, void *ws);
+CountTarget group_count_target(void *ws, Rec *pairs, u64 cap_records, i64 ncols, const KeyLayout &L);
+void group_precount_reset(cudaStream_t stream, void *ws, u64 cap_records, i64 ncols);
 int group_chunk_records();
-size_t group_workspace_bytes(u64 nrec);
+size_t group_workspace_bytes(u64 nrec, i64 ncols);
 bool group_supported(const KeyLayout &L, u64 nrec, i64 ncols);
 // stable grouping by column in two passes (sparse per-chunk histograms); false: no column locality
-bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, const KeyLayout &L, void *workspace,
+bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, i64 ncols, const KeyLayout &L, void *workspace,
                      void *sort_workspace, u32 *nzcol, u32 *nzstart, u64 *totals, u64 *h_scal_pinned, u64 *d_scal,
                      LaunchCounter &lc, StageTimer *timer, int *pair_passes, u64 *npairs_out, int ownershift = -1,
                      u32 me = 0, const ChunkOrder *order = nullptr, const PreCounted *pre = nullptr);

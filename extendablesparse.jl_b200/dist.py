@@ -86,8 +86,10 @@ class DistExtendableSparseMatrix:
             self.device = torch.device("cpu") if device is None else device
         self.h = backend
         self.col_begin, self.col_end = self.splits[self.rank], self.splits[self.rank + 1]
-        self.nnz_offset = 0
-        self.nnz_global = 0
+        self._nnz_offset = 0
+        self._nnz_global = 0
+        self._changed_any = False
+        self._offsets_pending = None
         self.last_exchange = {"sent_off_rank": 0, "received_off_rank": 0, "kept": 0}
         self._send = None
         self.last_phase_ms = []
@@ -102,8 +104,9 @@ class DistExtendableSparseMatrix:
             self._send = torch.empty(words, dtype=torch.int64, device=self.device)
         return self._send
 
-    def flush(self, mode=0):
-        """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank)."""
+    def flush(self, mode=0, wait=True):
+        """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank); with wait=False the
+        second value is the LOCAL flag and the global one is `changed_any` (read on demand)."""
         import time
 
         t = [time.perf_counter()]
@@ -130,19 +133,49 @@ class DistExtendableSparseMatrix:
         lap()
         nnz, changed = self.h.flush(mode)
         lap()
-        # one 16-byte all-gather: entries per slab (-> global colptr offsets) and "pattern changed"
+        # one 16-byte all-gather: entries per slab (-> global colptr offsets) and "pattern changed".  With
+        # wait=False it is only LAUNCHED here (stream-ordered behind the flush); nnz_offset / nnz_global /
+        # changed_any read it when they are first asked for, so an assembly loop that does not look at
+        # the global offsets every step does not stop for them.
         mine = torch.tensor([nnz, int(changed)], dtype=torch.int64, device=self.device)
         allv = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(allv, mine, group=self.group)
-        allv = allv.cpu().tolist()
-        lap()
-        per_rank, flags = allv[0::2], allv[1::2]
-        self.nnz_offset, self.nnz_global = sum(per_rank[: self.rank]), sum(per_rank)
+        work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=True)
+        self._offsets_pending = (work, allv, mine)
         self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received_off_rank": sum(rcounts),
                               "kept": counts[self.rank]}
+        if wait:
+            self._resolve_offsets()
+        lap()
         # host wall time of the phases (ms): count, copy-out, all-to-all, append, flush, offsets
         self.last_phase_ms = [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
-        return nnz, any(flags)
+        return nnz, (self._changed_any if wait else bool(changed))
+
+    def _resolve_offsets(self):
+        if self._offsets_pending is not None:
+            work, allv, _ = self._offsets_pending
+            work.wait()
+            vals = allv.cpu().tolist()
+            per_rank, flags = vals[0::2], vals[1::2]
+            self._nnz_offset, self._nnz_global = sum(per_rank[: self.rank]), sum(per_rank)
+            self._changed_any = any(flags)
+            self._offsets_pending = None
+
+    @property
+    def nnz_offset(self) -> int:
+        """Entries owned by lower ranks: the shift from the slab's colptr to the global one."""
+        self._resolve_offsets()
+        return self._nnz_offset
+
+    @property
+    def nnz_global(self) -> int:
+        self._resolve_offsets()
+        return self._nnz_global
+
+    @property
+    def changed_any(self) -> bool:
+        """The last flush changed the pattern on some rank."""
+        self._resolve_offsets()
+        return self._changed_any
 
     def global_colptr(self, local_colptr):
         """Slab colptr (slab_width+1 entries) shifted to index the global rowval/nzval arrays."""

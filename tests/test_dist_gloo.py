@@ -125,7 +125,11 @@ def _worker(rank, world, port, m, n, splits, out_q):
             fl = splice  # update flavour, then raw
             D.insert_batch(I, J, V, fl)
             streams.append((I, J, V, fl))
-            nnz, changed = D.flush()
+            if splice % 2 == 0:
+                nnz, changed = D.flush()
+            else:  # offsets all-gather launched only; the global values are read on demand
+                nnz, _local = D.flush(wait=False)
+                changed = D.changed_any
             cp, rv, nz = backend.A.csc()
             results.append((nnz, changed, D.nnz_offset, D.nnz_global, cp, rv, nz, dict(D.last_exchange)))
         out_q.put((rank, streams, results))

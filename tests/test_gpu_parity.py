@@ -1049,3 +1049,33 @@ def test_precount_tail_bounds_error(xsb):
     h.insert_batch(I, J, np.ones(cnt), xsb.UPDATE)
     assert h.flush() == (1, True)
     assert h.fetch_csc_numpy()[2].tolist() == [float(cnt)]
+
+
+def test_column_met_by_many_chunks_uses_pair_sort(xsb, oracle):
+    """The bucketed pair path orders a column's (chunk, column) pairs inside one thread; a column that more
+    than 128 chunks write to sends the flush to the radix sort of the pairs instead.  Same bits either way."""
+    n1 = 30
+    I, J, V, n, _ = _fem_case(oracle, n1)
+    I, J = I.copy(), J.copy()
+    hot = np.arange(0, len(V), 300)
+    I[hot] = (hot % n) + 1
+    J[hot] = 7
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.RAW)
+    ref = A.csc()
+    for pre in (True, False):
+        h = xsb.Handle(n, n)
+        h.set_precount(pre)
+        h.insert_batch(I, J, V, xsb.RAW)
+        h.flush()
+        st = h.flush_stats()
+        assert st["column_path"] == 3 and st["sort_passes"] > 0  # pairs went through the sort
+        assert_csc_equal(h.fetch_csc_numpy(), ref)
+        h.close()
+    # the plain FEM stream takes the bucketed path: no sort passes at all
+    h = xsb.Handle(n, n)
+    h.emit_p1fem(n1, n1, n1, flavour=xsb.RAW)
+    h.flush()
+    st = h.flush_stats()
+    assert st["column_path"] == 3 and st["sort_passes"] == 0
+    h.close()
