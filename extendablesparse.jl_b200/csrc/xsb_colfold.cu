@@ -632,7 +632,10 @@ constexpr u32 CT_EMPTY = 0xffffffffu;
 template <int HBITS> struct CtShape
 {
     static constexpr int H = 1 << HBITS;
-    static constexpr int D = HBITS == 6 ? 32 : H - H / 4; // 12, 24, 32 accumulators
+#ifndef XSB_CT_D5
+#define XSB_CT_D5 24
+#endif
+    static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? XSB_CT_D5 : H - H / 4); // 12, 24, 32 accumulators
     // table words + accumulators + row of every accumulator (first-appearance order)
     static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + sizeof(u32)) * D);
 };

@@ -455,14 +455,24 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
                 idx[v][d] = idx[v - 1][d] + (c_kuhn[perm][v - 1] == d ? 1 : 0);
         }
         const double dx = (double)(nxn - 1), dy = (double)(nyn - 1), dz = (double)(nzn - 1);
+        // a vertex coordinate is index / cells; along an axis the four vertices only take the cube's lower
+        // or upper index, so two divisions per axis (not four) give the same bits
+        const double dd[3] = {dx, dy, dz};
+        double lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            lo[d] = (double)idx[0][d] / dd[d];
+            hi[d] = (double)(idx[0][d] + 1) / dd[d];
+        }
         double p[4][3];
         u64 node[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v)
         {
-            p[v][0] = (double)idx[v][0] / dx;
-            p[v][1] = (double)idx[v][1] / dy;
-            p[v][2] = (double)idx[v][2] / dz;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                p[v][d] = idx[v][d] == idx[0][d] ? lo[d] : hi[d];
             node[v] = (u64)(idx[v][0] + nxn * idx[v][1] + nxn * nyn * idx[v][2]);
         }
         // P1 gradients from the inverse edge matrix; operation order mirrors the CPU oracle
