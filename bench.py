@@ -98,9 +98,9 @@ def flush_bytes(n_ins, nnz_old, nnz_new, ncols):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the
-# same workload (profiles/r1d_ncu_full_fem128.csv, FEM 128^3); other workloads / kernels: null
-NCU_TRAFFIC_FEM128 = {"group_scatter_kernel": 4.063222e9 + 3.898295e9, "colthread_kernel": 4.160314e9 + 0.497858e9,
-                      "group_count_kernel": 3.932929e9 + 0.235842e9}
+# same workload (profiles/r1e_ncu_full_fem128.csv, FEM 128^3); other workloads / kernels: null
+NCU_TRAFFIC_FEM128 = {"group_scatter_kernel": 4.0631e9 + 3.8998e9, "colthread_direct_kernel": 4.1566e9 + 0.4968e9,
+                      "group_count_kernel": 0.9834e9 + 0.2440e9}
 
 
 def roofline(st, ms, ncols, peak, peak_src, traffic):
@@ -113,17 +113,25 @@ def roofline(st, ms, ncols, peak, peak_src, traffic):
     path = st["column_path"]
     cands = {}
     if path == 3:
-        cands["group_count_kernel (read every record, write the (column, chunk) pairs)"] = (
-            ms["ms_group_count"], 16 * rec + 16 * pairs, 1)
-        cands["group_scatter_kernel (+ pair offsets: stable scatter of every record to its column)"] = (
-            ms["ms_group_scatter"], 32 * rec + 24 * pairs, 1)
-        cands["onesweep_kernel on the (column, chunk) pairs"] = (ms["ms_pair_sort"], 32 * pairs * st["sort_passes"],
-                                                                 st["sort_passes"])
+        # counting at insertion: a share `pre` of the records is counted from the 4-byte column ids their producer
+        # left (or was counted by the producer itself); a pair costs 16 (pair record) + 4 (column) + 2 (count) bytes
+        pre = float(st.get("precounted", 0.0))
+        cands["group_count_kernel (+ pair_totals: column ids / records in, (column, chunk) pairs out)"] = (
+            ms["ms_group_count"], (16 - 12 * pre) * rec + 22 * pairs, 1)
+        cands["group_scatter_kernel (stable scatter of every record to its column)"] = (
+            ms["ms_group_scatter"], 32 * rec + 8 * pairs, 1)
+        if st["sort_passes"]:
+            cands["onesweep_kernel on the (column, chunk) pairs (+ pair offsets)"] = (
+                ms["ms_pair_sort"], 32 * pairs * st["sort_passes"] + 24 * pairs, st["sort_passes"])
+        else:
+            cands["pair buckets (colpair scans + pair_bucket_kernel + pair_offsets_kernel)"] = (
+                ms["ms_pair_sort"], 12 * ncols + 26 * pairs, 1)
     else:
         cands["onesweep_kernel (one radix pass over 16-B records)"] = (ms["ms_sort"], 32 * rec * st["sort_passes"],
                                                                       st["sort_passes"])
     if path >= 2:
-        cands["colthread_kernel (+ leftover colfold_kernel: per-column fold, read records, park entries)"] = (
+        cands["colthread_direct_kernel (thread-per-column fold writing rowval / nzval / colptr)" if st.get("direct_fold")
+              else "colthread_kernel (+ leftover colfold_kernel: per-column fold, read records, park entries)"] = (
             ms["ms_fold"], 16 * rec + 16 * nnz, 1)
         cands["compact_entries_kernel (parked entries -> rowval / nzval)"] = (ms["ms_compact"], 32 * nnz, 1)
     else:

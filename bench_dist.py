@@ -70,13 +70,17 @@ def run(args, xsb, rank, world, local):
         torch.cuda.synchronize()
         dist.barrier()
         launches_timed = h.kernel_launches - launches0
-        t_end = time.time() + max(0.0, 0.5 - ms_local / 1e3)
-        while time.time() < t_end:
+        # max over ranks, on the device clock
+        tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        # keep the clock sampler busy for about half a second: the SAME number of extra steps on every rank
+        # (a step holds collectives; a per-rank time limit would let the ranks disagree and hang)
+        n_fill = int(max(0.0, 500.0 - ms) / max(ms / args.steps, 1e-3)) + 1
+        for _ in range(min(n_fill, 200)):
             step()
-    # max over ranks, on the device clock
-    tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
+        torch.cuda.synchronize()
+        dist.barrier()
     launches = torch.tensor([launches_timed], dtype=torch.int64, device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     st = h.flush_stats()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for profiles/ (development tool): launch list of the bench command + one full capture of a step
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 30 --csv --log-file gpurun_out/r1e_launches_fem128.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 33 -c 22 --csv --log-file gpurun_out/r1e_launches_fem128.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r1e_launches_bench.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on \
     -k regex:"group_count|group_scatter|colthread|emit_p1fem|onesweep|pair_" -s 26 -c 13 -f -o gpurun_out/r1e_full \
