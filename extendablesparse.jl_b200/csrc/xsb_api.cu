@@ -309,9 +309,11 @@ struct xsb_matrix
     {
         Stage &st = stage[t];
         if (st.count == 0)
+        {
             st.front = (n_tid == 1) ? nnz : 0;
             if (L.ownerbits > 0) // slab handles: every region of the buffer is a whole number of chunks
                 st.front = chunk_up(st.front);
+        }
         const i64 need = st.front + st.count + extra;
         if (need <= st.cap)
         {

@@ -629,13 +629,16 @@ constexpr int CT_WARPS = 4;
 constexpr int CT_U = XSB_CT_U; // 32-byte record pairs per step (the next step is prefetched)
 constexpr u32 CT_EMPTY = 0xffffffffu;
 
+// Table shapes, smallest first.  The template argument is the number of hash bits, except 15 = the
+// 5-bit table with 16 instead of 24 accumulators: a P1 tetrahedral mesh has at most 15 rows per column,
+// and the smaller accumulator array lets 5 instead of 4 blocks share an SM.
+//   shape  4: 16 slots / 12 accumulators     shape 15: 32 / 16     shape 5: 32 / 24     shape 6: 64 / 32
 template <int HBITS> struct CtShape
 {
-    static constexpr int H = 1 << HBITS;
-#ifndef XSB_CT_D5
-#define XSB_CT_D5 24
-#endif
-    static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? XSB_CT_D5 : H - H / 4); // 12, 24, 32 accumulators
+    static constexpr int HB = HBITS == 15 ? 5 : HBITS;
+    static constexpr int H = 1 << HB;
+    static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? 24 : (HBITS == 15 ? 16 : 12));
+    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 2 : 5); // launch bound (registers)
     // table words + accumulators + row of every accumulator (first-appearance order)
     static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + sizeof(u32)) * D);
 };
@@ -648,6 +651,7 @@ __device__ __forceinline__ int ct_fold_column(const Rec *__restrict__ sorted, u3
                                               u32 rowmask, u32 *key, double *acc, u32 *rows, u32 &d_out)
 {
     constexpr int H = CtShape<HBITS>::H;
+    constexpr int HB = CtShape<HBITS>::HB;
     constexpr u32 D = CtShape<HBITS>::D;
 #pragma unroll
     for (int s = 0; s < H; ++s)
@@ -660,11 +664,11 @@ __device__ __forceinline__ int ct_fold_column(const Rec *__restrict__ sorted, u3
     auto apply = [&](const Rec &r) {
         const u32 row = (u32)(r.key >> low) & rowmask;
         const double v = r.val;
-        u32 s = (row * 0x9E3779B1u) >> (32 - HBITS);
+        u32 s = (row * 0x9E3779B1u) >> (32 - HB);
         for (;;)
         {
             const u32 kk = key[s * 32];
-            const u32 x = kk ^ (row << HBITS);
+            const u32 x = kk ^ (row << HB);
             if (x < D)
             { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
                 acc[x * 32] = acc[x * 32] + v;
@@ -687,7 +691,7 @@ __device__ __forceinline__ int ct_fold_column(const Rec *__restrict__ sorted, u3
                     return;
                 }
                 const u32 fl = (u32)r.key & 3u;
-                key[s * 32] = (row << HBITS) | d;
+                key[s * 32] = (row << HB) | d;
                 rows[d * 32] = row;
                 // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value
                 // seeds it (extendable.jl:165-166); updateindex! of a zero creates nothing (:212,223)
@@ -754,7 +758,7 @@ __device__ __forceinline__ int ct_fold_column(const Rec *__restrict__ sorted, u3
     {
         if (!((exmask >> i) & 1ull))
             continue;
-        const u32 kk = (rows[i * 32] << HBITS) | i;
+        const u32 kk = (rows[i * 32] << HB) | i;
         u32 q = j;
         while (q > 0)
         {
@@ -771,7 +775,7 @@ __device__ __forceinline__ int ct_fold_column(const Rec *__restrict__ sorted, u3
 }
 
 template <int HBITS, bool LIST>
-__global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 5 : 2))
+__global__ void __launch_bounds__(CT_WARPS * 32, CtShape<HBITS>::kBlocks)
 colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxlen, const u32 *__restrict__ nzcol,
                  const u32 *__restrict__ nzstart, const u64 *__restrict__ totals, Rec *__restrict__ tmp,
                  u32 *__restrict__ colcount, const u32 *__restrict__ src, const u32 *__restrict__ src_count,
@@ -812,7 +816,7 @@ colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxle
         {
             const u32 pk = key[e * 32];
             Rec o;
-            o.key = (u64)(pk >> HBITS);
+            o.key = (u64)(pk >> CtShape<HBITS>::HB);
             o.val = acc[(pk & (H - 1)) * 32];
             st_rec(dst + e, o);
         }
@@ -829,7 +833,7 @@ colthread_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxle
 // the parking path (colthread_kernel + compact) instead.
 
 template <int HBITS, typename Ti>
-__global__ void __launch_bounds__(CT_WARPS * 32, HBITS == 4 ? 8 : (HBITS == 5 ? 5 : 2))
+__global__ void __launch_bounds__(CT_WARPS * 32, CtShape<HBITS>::kBlocks)
 colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u32 maxlen,
                         const u32 *__restrict__ nzcol, const u32 *__restrict__ nzstart,
                         const u64 *__restrict__ totals, i64 ncols, Ti base, Ti *__restrict__ rowval,
@@ -914,7 +918,7 @@ colthread_direct_kernel(const Rec *__restrict__ sorted, int low, int rowbits, u3
     // bases differ): a lane writes its own run, so every store instruction costs one request per lane
     {
         Ti *rv = rowval + o0;
-        auto row_at = [&](int e) { return (Ti)(key[e * 32] >> HBITS) + base; };
+        auto row_at = [&](int e) { return (Ti)(key[e * 32] >> CtShape<HBITS>::HB) + base; };
         constexpr int V = 32 / (int)sizeof(Ti);
         int e = 0;
         for (; e < j && (reinterpret_cast<uintptr_t>(rv + e) & 31u); ++e)
@@ -1282,6 +1286,8 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         timer->begin(stream);
     const u64 avg = nrec / std::max<u64>(1, kmax);
     int level = hint_maxd ? (hint_maxd <= 12 ? 0 : (hint_maxd <= 24 ? 1 : 2)) : (avg < 14 ? 0 : (avg < 40 ? 1 : 2));
+    // 13..16 distinct rows in the previous flush (P1 FEM: 15): the 32-slot table with 16 accumulators
+    const bool slim = level == 1 && hint_maxd != 0 && hint_maxd <= 16 && g_thread_hbits == 0;
     if (g_thread_hbits >= 4 && g_thread_hbits <= 6)
         level = g_thread_hbits - 4;
     const u32 maxlen = (u32)std::max<u64>(256, 6 * avg);
@@ -1292,6 +1298,8 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     {
         if (level == 0)
             XSB_DIRECT(4, int64_t);
+        else if (slim)
+            XSB_DIRECT(15, int64_t);
         else if (level == 1)
             XSB_DIRECT(5, int64_t);
         else
@@ -1301,6 +1309,8 @@ void colfold_direct(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     {
         if (level == 0)
             XSB_DIRECT(4, int32_t);
+        else if (slim)
+            XSB_DIRECT(15, int32_t);
         else if (level == 1)
             XSB_DIRECT(5, int32_t);
         else

@@ -1079,3 +1079,33 @@ def test_column_met_by_many_chunks_uses_pair_sort(xsb, oracle):
     st = h.flush_stats()
     assert st["column_path"] == 3 and st["sort_passes"] == 0
     h.close()
+
+
+def test_fold_table_shape_follows_previous_flush(xsb, oracle):
+    """The thread fold picks its table from the distinct rows per column the previous flush saw (15 for a P1
+    mesh: the 32-slot / 16-accumulator shape).  A following assembly with richer columns overflows that table once,
+    is folded by the fallback path, and the result is the oracle's both times."""
+    n1 = 30
+    I, J, V, n, ref = _fem_case(oracle, n1)
+    h = xsb.Handle(n, n)
+    for _ in range(3):  # first flush: no hint; later ones: the slim table
+        h.reset()
+        h.insert_batch(I, J, V, xsb.RAW)
+        h.flush()
+        assert h.flush_stats()["column_path"] == 3
+        assert_csc_equal(h.fetch_csc_numpy(), ref)
+    # 22 distinct rows in every column
+    rng = np.random.default_rng(5)
+    cols = np.repeat(np.arange(1, n + 1), 44)
+    rows = ((cols[:, None].reshape(-1, 44) * 7 + np.arange(44)[None, :] % 22 * 131) % n + 1).reshape(-1)
+    vals = rng.standard_normal(len(cols))
+    perm = np.argsort(rng.integers(0, 64, len(cols)) + (cols // 40) * 64, kind="stable")  # keep column locality
+    I2, J2, V2 = rows[perm], cols[perm], vals[perm]
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I2, J2, V2, oracle.RAW)
+    for _ in range(2):
+        h.reset()
+        h.insert_batch(I2, J2, V2, xsb.RAW)
+        h.flush()
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    h.close()
