@@ -65,3 +65,23 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for needle in ("import oracle", "from oracle", "xsb_oracle", "libxsb_oracle", "ora_"):
                     assert needle not in src, f"{f} references the oracle ({needle})"
+
+
+def test_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: the oracle port of BOTH reference paths (serial and partitioned) timed on the
+    host cores, one JSON line with the contract's keys; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-mesh", "12",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "entries/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["serial_value"] > 0 and cb["cores"] >= 1
+    assert cb["value"] == max(cb["serial_value"], cb["mt_value"] or 0.0)
