@@ -438,6 +438,7 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     const i64 t_first = tet_begin + (i64)blockIdx.x * FEM_THREADS;
     const i64 t_last = min(t_first + FEM_THREADS, tet_end);
     const i64 t = t_first + threadIdx.x;
+    int has_foreign = 0;
     if (t < t_last)
     {
         const i64 cube = t / 6;
@@ -527,6 +528,8 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
         {
             ckey[v] = L.colpart(node[v]);
             rkey[v] = L.rowpart(node[v], tid, flavour);
+            if (sf.flags != nullptr && L.owner(ckey[v]) != (u32)L.self)
+                has_foreign = 1; // slab handles: a column of this element belongs to another rank
         }
 #pragma unroll
         for (int il = 0; il < 4; ++il)
@@ -544,7 +547,10 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
             }
         }
     }
-    __syncthreads();
+    // slab handles: only blocks at a slab face hold records of other ranks; every other block stores without
+    // looking at owner bits (the emitter is issue-bound: the per-record checks cost 0.16 ms of 1.07 ms)
+    if (!__syncthreads_or(has_foreign))
+        sf.flags = nullptr;
     const i64 nrec = (t_last - t_first) * FEM_REC;
     const i64 pos0 = (t_first - tet_begin) * FEM_REC;
     Rec *dst = out + pos0;
