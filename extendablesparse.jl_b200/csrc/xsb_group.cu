@@ -585,6 +585,7 @@ __device__ __forceinline__ u32 chunk_pos(const ChunkOrder &o, u32 c)
 }
 
 // bucket entry: [chunk position : 23][pair (ticket) index : 31][records - 1 : 9]
+static_assert(GP_W <= 512, "a bucket entry keeps 9 bits for the records of a (chunk, column) pair");
 __device__ __forceinline__ u64 pb_entry(u32 pos, u32 pair, u32 cnt) { return ((u64)pos << 40) | ((u64)pair << 9) | (u64)(cnt - 1u); }
 
 // a warp per chunk: its pairs go into their columns' buckets
