@@ -50,5 +50,56 @@ def main():
     case_stream("blockrd_3x3x2x2", 36, 36, [(I, J, V, ora.UPDATE, True)])
 
 
+def digest(*arrays):
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+# Streams large enough for the product path of the flush (grouping by column + thread fold; >= 32768 records):
+# too big to commit as arrays, so only SHA-256 digests of the oracle's result are recorded.  The CPU test
+# regenerates them with the oracle (drift guard), the GPU test must reach the same bytes through the
+# library's own on-device emitters.
+HASHED = {
+    "p1fem_20": dict(kind="fem", dims=(20, 20, 20), flavour="raw"),
+    "fdrand_40": dict(kind="fd", dims=(40, 40, 40), seed=20240717, flavour="update"),
+    "blockrd_12x10x8x4": dict(kind="rd", dims=(12, 10, 8, 4), seed=3, flavour="update"),
+}
+
+
+def hashed_case(spec):
+    k, dims = spec["kind"], spec["dims"]
+    if k == "fem":
+        I, J, V = ora.fem_stream(*dims)
+        n = dims[0] * dims[1] * dims[2]
+    elif k == "fd":
+        I, J, V = ora.fdrand_stream(*dims, seed=spec["seed"])
+        n = dims[0] * dims[1] * dims[2]
+    else:
+        I, J, V = ora.blockrd_stream(*dims, seed=spec["seed"])
+        n = dims[0] * dims[1] * dims[2] * dims[3]
+    A = ora.OracleExt(n, n)
+    A.insert_batch(I, J, V, ora.RAW if spec["flavour"] == "raw" else ora.UPDATE)
+    cp, rv, nz = A.csc()
+    out = {"n": n, "records": int(len(V)), "nnz": int(len(nz)), "csc": digest(cp, rv, nz)}
+    bcp, brv, bl = A.pointblock(4)
+    out["pointblock4"] = digest(bcp, brv, bl)
+    out["nnz_blocks"] = int(len(brv))
+    return out
+
+
+def main_hashes():
+    import json
+
+    ora.build()
+    res = {name: dict(spec, **hashed_case(spec)) for name, spec in HASHED.items()}
+    with open(os.path.join(HERE, "hashes.json"), "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     main()
+    main_hashes()
