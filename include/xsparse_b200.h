@@ -27,8 +27,8 @@
  *  - Index arrays have the element type `idx_type` and the base `index_base`
  *    chosen at creation (Julia: XSB_I64, base 1).  Values are Float64.
  *  - Calls on one handle must not overlap, except xsb_insert_batch /
- *    xsb_emit_* with DISTINCT `tid` (the reference's threading contract,
- *    test/femtools.jl:88-105).
+ *    xsb_insert_triplets / xsb_emit_* with DISTINCT `tid` (the reference's
+ *    threading contract, test/femtools.jl:88-105).
  *  - There is no CPU fallback: without a CUDA device xsb_create fails with
  *    XSB_ECUDA.
  */
