@@ -891,7 +891,10 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, i64
         timer->begin(stream);
     if (!pre || pre->counted_chunks == 0)
         XSB_CUDA(cudaMemsetAsync(ws + l.off_ticket, 0, 256, stream)); // pair ticket, flags
-    if (!g_pairs_sort) // per-column totals and bucket cursors of the bucketed pair path
+    // The bucketed pair path works on per-column arrays (12 bytes cleared + 12 bytes scanned per column and
+    // flush); for a hypersparse flush (far more columns than records) the radix sort of the pairs is cheaper.
+    const bool try_buckets = !g_pairs_sort && (u64)ncols <= 8ull * nrec;
+    if (try_buckets) // per-column totals and bucket cursors
         XSB_CUDA(cudaMemsetAsync(ws + l.off_colrec, 0, l.off_pstart - l.off_colrec, stream));
     const int chunkbits = 0; // pair keys hold the column only
     const u32 chunk0 = pre ? std::min(pre->counted_chunks, nchunks) : 0u;
@@ -905,7 +908,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, i64
         lc.add();
         XSB_CUDA(cudaGetLastError());
     }
-    if (!g_pairs_sort)
+    if (try_buckets)
     { // records and pairs per column (sizes of the buckets), "a column is met by very many chunks" flag
         pair_totals_kernel<<<kNumSM * 8, 256, 0, stream>>>(pair_total, l.cap, chunkcols, chunkcnt, colrec, colpairs, flags,
                                                            (u32)ncols);
@@ -927,7 +930,7 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, i64
         return false;
     ChunkOrder ord = order ? *order : ChunkOrder{nchunks, nchunks, nchunks};
 
-    if (!longcol && !g_pairs_sort)
+    if (!longcol && try_buckets)
     { // ---- bucketed pair path: no sort (see above)
         if (timer)
             timer->begin(stream);
