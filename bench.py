@@ -344,6 +344,7 @@ def measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch):
     emesh = args.e2e_mesh
     en = emesh ** 3
     g = xsb.Handle(en, en, device=h.device)
+    g.set_precount(False)  # the host arrays hold the stream in call order, as user code would produce it
     g.emit_p1fem(emesh, emesh, emesh, flavour=xsb.RAW)
     cnt = g.pending
     dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
@@ -370,6 +371,7 @@ def measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch):
     torch.cuda.synchronize()
     del dI, dJ, dV, dT
     g.reset()
+    g.set_precount(True)
     # result buffers (pinned), sized after one dry run
     g.insert_triplets(hT, xsb.RAW, 0, cnt)
     nnz, _ = g.flush(mode)

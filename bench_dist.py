@@ -128,6 +128,7 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
     splits = [emesh * emesh * layers * r for r in range(world)] + [N]
     D = xd.DistExtendableSparseMatrix(N, N, splits=splits, device=local)
     g = D.h
+    g.set_precount(False)  # the host array holds the stream in call order
     g.emit_p1fem(emesh, emesh, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
     cnt = g.pending
     dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
@@ -145,6 +146,7 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
     torch.cuda.synchronize()
     del dI, dJ, dV, dT
     g.reset()
+    g.set_precount(True)
     g.insert_triplets(hT, xsb.RAW, 0, cnt)
     nnz, _ = D.flush(mode)
     ocp = torch.empty(g.n + 1, dtype=torch.int64, pin_memory=True)

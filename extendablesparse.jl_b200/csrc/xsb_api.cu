@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <unordered_map>
@@ -75,6 +76,9 @@ struct xsb_matrix
     int last_src = -1;
     cudaStream_t stream = nullptr;
     std::string err;
+    // Calls on one handle are serialised here: insertions with distinct `tid` may be ISSUED concurrently
+    // (the reference's threading contract, test/femtools.jl:88-105), their host side runs one at a time.
+    std::recursive_mutex mu;
 
     // resident CSC, in the caller's index type and base
     void *colptr = nullptr;
@@ -234,9 +238,11 @@ struct xsb_matrix
             }
         }
         has_assign = false;
-        pre.counted = 0;
-        pre.colled = 0;
-        pre.dead = false;
+        if (runs.ws && (runs.nchunks > 0 || runs.dead))
+            cudaMemsetAsync(runs.ws, 0, 256, stream); // pair ticket and flags of the run index
+        runs.nchunks = 0;
+        runs.sorted_end = 0;
+        runs.dead = false;
         if (tileflags)
             cudaMemsetAsync(tileflags, 0, (size_t)tileflags_cap, stream);
     }
@@ -256,6 +262,7 @@ struct xsb_matrix
     int strategy = XSB_STRATEGY_AUTO;
     int grouping = XSB_GROUPING_AUTO; // two-pass grouping by column before the hash fold
     int grouping_misses = 0;          // consecutive flushes whose stream had no column locality
+    int runs_misses = 0;              // consecutive flushes whose columns were too long / rich for the thread-per-column merge
     i64 stats_pairs = 0;
     bool last_column_path = false;
     bool no_direct_fold = false; // the one-pass fold met columns it cannot take: park + compact instead
@@ -265,26 +272,51 @@ struct xsb_matrix
     bool preagg = false;   // xsb_set_preaggregation
     int preagg_misses = 0; // consecutive XSB_FAST flushes whose windows held few duplicates
     u32 fold_hint = 0; // most distinct rows a column held in the previous thread-per-column fold
-    // "count rides along with insertion": the kernels that stage records (pack / emit) take the column
-    // histograms of whole chunks while the records are in registers / shared memory; the flush counts
-    // only what is left (xsb_group.cu).  Single-partition, non-slab handles assembling from an empty CSC.
-    struct PreCountState
+    // Grouping at insertion (xsb_chunk.cuh): the kernels that stage records (pack / emit) bring every chunk
+    // into column order while its records are in registers / shared memory and publish its runs in the run
+    // index; the flush (xsb_runs.cu) reads the runs in place.  Partition 0 of single-partition handles.
+    struct RunIndexState
     {
-        void *ws = nullptr;   // grouping workspace laid out for cap_records
-        Rec *pairs = nullptr; // pair list
-        u32 *cols = nullptr;  // column id of every staged record (producers that do not count themselves)
+        void *ws = nullptr;  // run index laid out for cap_records staged records
         i64 cap_records = 0;
-        i64 counted = 0;      // staged records of partition 0 already counted (a whole number of chunks)
-        i64 colled = 0;       // >= counted: staged records [counted, colled) have their column id in cols[]
-        bool dead = false;    // this assembly cannot use what was counted (stage grew, batch rejected)
-    } pre;
-    bool precount = true; // xsb_set_precount
-    void precount_release()
+        u32 cap_chunks = 0;
+        u32 nchunks = 0;     // chunks published so far
+        i64 sorted_end = 0;  // staged records [0, sorted_end) are grouped chunks whose runs are published
+        bool dead = false;   // a rejected batch left runs behind: the index is rebuilt at flush time
+    } runs;
+    bool precount = true; // xsb_set_precount: producers group their chunks (else the flush does)
+    void runs_release()
     {
-        dfree(pre.ws);
-        dfree(pre.pairs);
-        dfree(pre.cols);
-        pre = PreCountState{};
+        dfree(runs.ws);
+        runs = RunIndexState{};
+    }
+    // room in the run index for `records` staged records (contents are kept)
+    void runs_reserve(i64 records)
+    {
+        if (runs.ws && runs.cap_records >= records)
+            return;
+        const i64 want = std::max<i64>(records + records / 4, 65536);
+        const RunIndexLayout nl = run_index_layout((u64)want);
+        void *nw = dalloc(nl.bytes);
+        XSB_CUDA(cudaMemsetAsync(nw, 0, 256, stream));
+        if (runs.ws && runs.nchunks > 0 && !runs.dead)
+        { // an assembly in progress outgrew the index: move what was published
+            const RunIndexLayout ol = run_index_layout((u64)runs.cap_records);
+            unsigned char *o = static_cast<unsigned char *>(runs.ws), *n2 = static_cast<unsigned char *>(nw);
+            XSB_CUDA(cudaMemcpyAsync(n2 + nl.off_counters, o + ol.off_counters, 256, cudaMemcpyDeviceToDevice, stream));
+            XSB_CUDA(cudaMemcpyAsync(n2 + nl.off_chunkinfo, o + ol.off_chunkinfo, sizeof(uint2) * (size_t)runs.nchunks,
+                                     cudaMemcpyDeviceToDevice, stream));
+            XSB_CUDA(cudaMemcpyAsync(n2 + nl.off_chunkstart, o + ol.off_chunkstart, sizeof(u32) * (size_t)runs.nchunks,
+                                     cudaMemcpyDeviceToDevice, stream));
+            XSB_CUDA(cudaMemcpyAsync(n2 + nl.off_pcol, o + ol.off_pcol, sizeof(u32) * (size_t)ol.cap_pairs,
+                                     cudaMemcpyDeviceToDevice, stream));
+            XSB_CUDA(cudaMemcpyAsync(n2 + nl.off_pinfo, o + ol.off_pinfo, sizeof(u32) * (size_t)ol.cap_pairs,
+                                     cudaMemcpyDeviceToDevice, stream));
+        }
+        dfree(runs.ws);
+        runs.ws = nw;
+        runs.cap_records = want;
+        runs.cap_chunks = nl.cap_chunks;
     }
     // move rowval/nzval into an allocation of exactly nnz entries
     void shrink_store()
@@ -369,6 +401,9 @@ void set_err(xsb_matrix *h, const std::string &s)
 
 template <class F> int32_t guard(xsb_matrix *h, F &&f)
 {
+    std::unique_lock<std::recursive_mutex> lock;
+    if (h)
+        lock = std::unique_lock<std::recursive_mutex>(h->mu);
     try
     {
         if (h)
@@ -482,6 +517,168 @@ void check_tid_flavour(xsb_matrix *h, int32_t tid, int32_t flavour)
     REQUIRE(flavour >= XSB_UPDATE && flavour <= XSB_ASSIGN, XSB_EINVAL, "unknown insertion flavour");
 }
 
+// The multi-partition wrapper refuses A[i,j] = v for an entry that is not in the CSC yet
+// (genericmtextendablesparsematrixcsc.jl:63-68: error("use rawupdateindex! for new entries ...")).
+// Called on the freshly packed records of an assign batch of a handle with several partition buffers.
+void check_mt_assign(xsb_matrix *h, const Rec *recs, i64 count)
+{
+    write_scalar(h, 2, 0);
+    count_missing_records(h->stream, recs, count, h->Ls, h->view(), h->idx64, h->base, h->d_scal + 2, h->lc);
+    const u64 missing = read_scalar(h, 2);
+    REQUIRE(missing == 0, XSB_EILLEGAL,
+            "use rawupdateindex! for new entries into a matrix with several partition buffers (" +
+                std::to_string(missing) + " assigned positions are not in the CSC); batch rejected");
+}
+
+bool runs_eligible(const xsb_matrix *h);
+
+// flush! on grouped chunks (xsb_runs.cu): the product path.  Returns false -- with the staged records and the
+// resident CSC untouched (apart from the in-place grouping of chunks, which keeps every entry's insertions in
+// stream order) -- when this flush has to take another path: a stream without column locality, a column too long
+// or too rich for one thread.
+bool runs_flush(xsb_matrix *h, int32_t mode, i64 n_ins, StageTimer *tp, int64_t *nnz_out)
+{
+    (void)mode; // the fold is an exact left fold in insertion order in both modes
+    cudaStream_t s = h->stream;
+    Stage &st = h->stage[0];
+    const i64 count = st.count;
+    if (!runs_eligible(h) || !runs_supported(h->L, (u64)count, h->n) || !colfold_supported(h->L, (u64)count, h->n))
+        return false;
+    Rec *buf = st.buf + st.front;
+    // ---- the run index: what the producers published, plus the regions they left in stream order
+    if (tp)
+        tp->begin(s);
+    if (h->runs.dead || !h->runs.ws)
+    {
+        if (h->runs.ws)
+            XSB_CUDA(cudaMemsetAsync(h->runs.ws, 0, 256, s));
+        h->runs.nchunks = 0;
+        h->runs.sorted_end = 0;
+        h->runs.dead = false;
+    }
+    h->runs_reserve(count);
+    RunRegions reg{0xffffffffu, 0xffffffffu};
+    i64 bounds[4] = {h->runs.sorted_end, count, count, count};
+    if (h->L.ownerbits > 0 || h->nranks > 0)
+    { // [own | from lower ranks | from higher ranks]: a chunk never straddles two regions
+        const i64 low_end = h->low_end < 0 ? count : h->low_end;
+        const i64 own_end = h->routed ? h->own_end : count;
+        bounds[1] = std::max(own_end, h->runs.sorted_end);
+        bounds[2] = std::max(low_end, bounds[1]);
+        reg.own_end = (u32)bounds[1];
+        reg.low_end = (u32)bounds[2];
+    }
+    {
+        u64 extra = 0;
+        for (int r = 0; r < 3; ++r)
+            extra += chunk_sort_chunks((u64)(bounds[r + 1] - bounds[r]));
+        if ((u64)h->runs.nchunks + extra > (u64)h->runs.cap_chunks)
+        { // many small batches filled the chunk table: rebuild the index from scratch, in whole chunks
+            XSB_CUDA(cudaMemsetAsync(h->runs.ws, 0, 256, s));
+            h->runs.nchunks = 0;
+            h->runs.sorted_end = 0;
+            bounds[0] = 0;
+        }
+    }
+    const RunTarget rt = run_target(h->runs.ws, (u64)h->runs.cap_records, h->L);
+    h->stats_precounted = h->runs.sorted_end;
+    for (int r = 0; r < 3; ++r)
+    {
+        if (bounds[r + 1] > bounds[r])
+        {
+            chunk_sort(s, buf, (u64)bounds[r], (u64)bounds[r + 1], rt, h->runs.nchunks, h->lc);
+            h->runs.nchunks += chunk_sort_chunks((u64)(bounds[r + 1] - bounds[r]));
+        }
+    }
+    h->runs.sorted_end = count;
+    XSB_CUDA(cudaMemcpyAsync(h->h_scal + 4, rt.counters, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    if (tp)
+        tp->end(s, &StageTimes::gcount);
+    h->sync();
+    const u32 npairs = (u32)(h->h_scal[4] & 0xffffffffull);
+    const u32 flags = (u32)(h->h_scal[4] >> 32);
+    h->stats_pairs = (i64)npairs;
+    if (flags != 0u || npairs > rt.cap)
+    { // a chunk with too many distinct columns: this stream has no column locality
+        if (h->grouping == XSB_GROUPING_AUTO)
+            h->grouping_misses++;
+        h->runs.dead = true;
+        return false;
+    }
+    // ---- every column's runs into its bucket
+    if (tp)
+        tp->begin(s);
+    void *ws = h->dalloc(runs_workspace_bytes((u64)npairs, h->n));
+    runs_bucket(s, rt, h->runs.nchunks, npairs, h->n, h->L, reg, ws, h->lc);
+    if (tp)
+        tp->end(s, &StageTimes::sort);
+    // ---- merge: resident column + runs -> new column
+    const i64 nnz_old = h->nnz;
+    const size_t ub = (size_t)(nnz_old + count); // entries the new matrix can hold at most
+    const size_t rv_bytes = (h->isz() * ub + 255) & ~(size_t)255;
+    void *new_colptr = h->dalloc(h->isz() * (size_t)(h->n + 1));
+    unsigned char *store = static_cast<unsigned char *>(h->dalloc(rv_bytes + 8 * ub + 32));
+    void *new_rowval = store;
+    double *new_nzval = reinterpret_cast<double *>(store + rv_bytes);
+    const u64 avg = (u64)count / (u64)std::max<i64>(1, h->n);
+    const u32 maxlen = (u32)std::max<u64>(1024, 8 * avg);
+    int level = h->fold_hint ? runs_level_for(h->fold_hint) : (nnz_old > 0 ? runs_level_for((u32)std::min<i64>(64, 2 * nnz_old / std::max<i64>(1, h->n) + 4))
+                                                                           : (avg < 14 ? 0 : (avg < 40 ? 2 : 3)));
+    i64 nnz_new = -1;
+    bool ok = false;
+    if (tp)
+        tp->begin(s);
+    for (bool first = true;; first = false)
+    {
+        runs_fold(s, buf, h->L, h->n, h->idx64, h->base, h->view(), ws, npairs, level, maxlen, new_rowval, new_nzval,
+                  new_colptr, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), reinterpret_cast<u32 *>(h->d_scal + 7),
+                  first, h->lc);
+        XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        nnz_new = (i64)read_scalar(h, 0);
+        const u32 redo = (u32)h->h_scal[6];
+        const u32 maxd = (u32)h->h_scal[7];
+        if (redo == 0u)
+        {
+            if (maxd)
+                h->fold_hint = maxd;
+            ok = true;
+            break;
+        }
+        if ((redo & 6u) || level >= 3)
+            break; // a very long column, or one too rich for the largest table
+        level = std::max(level + 1, maxd > 0 ? runs_level_for(maxd) : 0); // the next table shape
+    }
+    if (tp)
+        tp->end(s, &StageTimes::fold);
+    h->dfree(ws);
+    if (!ok)
+    {
+        h->dfree(new_colptr);
+        h->dfree(store);
+        h->runs_misses++; // two in a row: this handle's producers stop grouping, its flushes take the other paths
+        return false;
+    }
+    h->runs_misses = 0;
+    // ---- the new matrix replaces the resident one; the staging buffer stays where it is
+    h->dfree(h->colptr);
+    h->dfree(h->csc_store);
+    h->colptr = new_colptr;
+    h->csc_store = store;
+    h->csc_store_bytes = rv_bytes + 8 * ub + 32;
+    h->rowval = new_rowval;
+    h->nzval = new_nzval;
+    h->nnz = nnz_new;
+    const size_t exact = (h->isz() + 8) * (size_t)nnz_new;
+    if (h->csc_store_bytes > exact + h->shrink_surplus_bytes)
+        h->shrink_store();
+    h->clear_staging(false);
+    if (nnz_new != nnz_old)
+        h->drop_frozen();
+    (void)n_ins;
+    *nnz_out = nnz_new;
+    return true;
+}
+
 int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out, int32_t *pattern_changed)
 {
     REQUIRE(mode == XSB_DETERMINISTIC || mode == XSB_FAST, XSB_EINVAL, "unknown summation mode");
@@ -494,6 +691,8 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     h->stats.nnz_new = h->nnz;
     if (n_ins == 0)
     { // flush! is a no-op without new entries: extendable.jl:249
+        if (h->nranks > 0)
+            h->clear_staging(false); // a rank that staged and received nothing: forget the routing state of this step
         if (nnz_out)
             *nnz_out = h->nnz;
         if (pattern_changed)
@@ -514,6 +713,54 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     }
 
     const i64 nnz_old = h->nnz;
+    h->stats_pairs = 0;
+    h->stats_direct = 0;
+    h->stats_preagg = 0;
+    h->stats_precounted = 0;
+    if (combine == XSB_COMBINE_SEED && !(mode == XSB_FAST && (h->preagg || g_preagg)))
+    { // ---- the product path: grouped chunks, records never move, resident CSC merged column by column
+        int64_t nnz_runs = 0;
+        const i64 foreign_runs = h->foreign + h->n_pad;
+        if (runs_flush(h, mode, n_ins, tp, &nnz_runs))
+        {
+            h->last_column_path = true;
+            h->stats.n_inserted = n_ins - foreign_runs;
+            h->stats.nnz_old = nnz_old;
+            h->stats.nnz_new = nnz_runs;
+            h->stats.column_path = 4;
+            h->stats.kernel_launches = h->lc.in_flush;
+            h->stats.ms_host_alloc = h->alloc_ms;
+            h->stats.group_pairs = h->stats_pairs;
+            h->stats.direct_fold = 1;
+            h->stats.precounted = n_ins > 0 ? (float)((double)h->stats_precounted / (double)n_ins) : 0.f;
+            if (tp)
+            {
+                XSB_CUDA(cudaEventRecord(e1, s));
+                h->sync();
+                StageTimes t;
+                timer.collect(t);
+                cudaEventElapsedTime(&t.total, e0, e1);
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                h->stats.ms_total = t.total;
+                h->stats.ms_histogram = t.gcount;
+                h->stats.ms_group_count = t.gcount;
+                h->stats.ms_pair_sort = t.sort;
+                h->stats.ms_sort = t.sort;
+                h->stats.ms_fold = t.fold;
+                h->stats.ms_reduce = t.fold;
+            }
+            if (nnz_out)
+                *nnz_out = nnz_runs;
+            if (pattern_changed)
+                *pattern_changed = (nnz_runs != nnz_old) ? 1 : 0; // the pattern only ever grows
+            return XSB_OK;
+        }
+        if (tp)
+        { // spans of the abandoned attempt stay in the totals of this flush
+            h->sync();
+        }
+    }
     // slab handles keep every region of the buffer chunk aligned: a gap of skipped records follows the old entries
     const i64 front = (h->L.ownerbits > 0 && h->n_tid == 1) ? xsb_matrix::chunk_up(nnz_old) : nnz_old;
     i64 total = front + n_ins; // records the flush works on (shrinks if XSB_FAST pre-aggregates)
@@ -666,25 +913,9 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
             colfold_lists(cws, (u64)total, h->n, &nzcol, &nzstart, &totals);
             int pair_passes = 0;
             u64 npairs = 0;
-            // chunks whose column histograms were taken when they were staged (pack / emit kernels)
-            PreCounted pc{};
-            const PreCounted *ppc = nullptr;
-            if (h->pre.colled > 0 && !h->pre.dead && a_is_stage0 && !preagged && (!tomb || h->pre.counted == 0) &&
-                nnz_old == 0 && front == 0 &&
-                h->pre.cap_records >= total && h->pre.colled <= n_ins)
-            {
-                pc.ws = h->pre.ws;
-                pc.pairs = h->pre.pairs;
-                pc.cap_records = (u64)h->pre.cap_records;
-                pc.counted_chunks = (u32)(h->pre.counted / group_chunk_records());
-                pc.cols = h->pre.cols;
-                pc.cols_chunks = (u32)(h->pre.colled / group_chunk_records());
-                ppc = &pc;
-                h->stats_precounted = h->pre.colled;
-            }
             grouped = group_by_column(s, A, B, (u64)total, h->n, h->L, gws, ws, nzcol, nzstart, totals, h->h_scal + 4,
                                       h->d_scal + 4, h->lc, tp, &pair_passes, &npairs,
-                                      tomb ? h->L.ownershift() : -1, (u32)h->rank, pord, ppc);
+                                      tomb ? h->L.ownershift() : -1, (u32)h->rank, pord, nullptr);
             h->dfree(gws);
             h->stats_pairs = (i64)npairs;
             if (grouped)
@@ -912,77 +1143,49 @@ Rec *begin_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
     return st.buf + st.front + st.count;
 }
 
-// XSB_PRECOUNT=0 switches counting-at-insertion off for every handle (A-B measurements)
+// XSB_PRECOUNT=0 switches grouping at insertion off for every handle (A-B measurements): the flush then
+// groups the chunks itself; XSB_RUNS=0 switches the whole grouped-chunk flush off (previous product path)
 const bool g_precount_off = []() {
     const char *e = getenv("XSB_PRECOUNT");
     return e && *e == '0';
 }();
+const bool g_runs_off = []() {
+    const char *e = getenv("XSB_RUNS");
+    return e && *e == '0';
+}();
 
-// Called after begin_emit: may the producer of the next `count` records of partition `tid` help the
-// flush's counting pass?  Two kinds of help:
-//   counts == true : the producer counts its whole chunks itself (pack kernels); *ct / *chunk0 say where
-//                    the pairs go and which chunk the batch starts at.  Needs everything staged so far counted.
-//   counts == false: the producer only leaves the column id of every record in *cols (emit kernels, whose
-//                    shared memory is taken by the transposition); everything staged so far must be counted
-//                    or have its column ids.
-bool precount_begin(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count, bool counts, CountTarget *ct, u32 *chunk0,
-                    u32 **cols)
+// may this handle's flush work on grouped chunks (xsb_runs.cu)?
+bool runs_eligible(const xsb_matrix *h)
 {
-    if (!h->precount || g_precount_off || h->n_tid != 1 || tid != 0 || (counts && h->nranks != 0))
-        return false;
-    if (flavour == XSB_ASSIGN || h->has_assign || h->nnz != 0 || h->strategy != XSB_STRATEGY_AUTO)
-        return false;
-    if (h->grouping == XSB_GROUPING_OFF || (h->grouping == XSB_GROUPING_AUTO && h->grouping_misses >= 2))
+    return !g_runs_off && h->n_tid == 1 && h->strategy == XSB_STRATEGY_AUTO && h->grouping != XSB_GROUPING_OFF &&
+           (h->grouping == XSB_GROUPING_ON || (h->grouping_misses < 2 && h->runs_misses < 2));
+}
+
+// Called after begin_emit: may the producer of the next `count` records of partition `tid` group its chunks
+// (xsb_chunk.cuh) and publish their runs?  `chunks` = chunks it will append.  On success *rt / *chunk0 / *pos0
+// say where the runs go, the id of the first chunk and the position of the first record.
+bool runs_begin(xsb_matrix *h, int32_t tid, i64 count, u32 chunks, RunTarget *rt, u32 *chunk0, u32 *pos0)
+{
+    if (!h->precount || g_precount_off || tid != 0 || !runs_eligible(h) || count <= 0)
         return false;
     Stage &st = h->stage[0];
-    const i64 W = group_chunk_records();
-    if (h->pre.dead || st.front != 0 || st.count != h->pre.colled || count < W)
+    if (h->runs.dead || st.count != h->runs.sorted_end)
+        return false; // something staged before was not grouped: the flush groups the rest
+    if (!runs_supported(h->L, (u64)(st.count + count), h->n))
         return false;
-    if (counts && h->pre.colled != h->pre.counted)
+    h->runs_reserve(std::max<i64>(st.cap - st.front, st.count + count));
+    if ((u64)h->runs.nchunks + chunks > (u64)h->runs.cap_chunks)
         return false;
-    if (!group_supported(h->L, (u64)std::max<i64>(st.cap, 32768), h->n) || !colfold_supported(h->L, (u64)st.cap, h->n))
-        return false;
-    if (st.count == 0)
-    { // a new assembly: size the workspace for the stage, clear the pair ticket
-        // slab handles append what other ranks send behind the own records: leave room for that
-        const i64 want = h->nranks > 0 ? st.cap + st.cap / 4 + 65536 : st.cap;
-        if (h->pre.cap_records < want || h->pre.cap_records > 2 * want)
-        {
-            h->precount_release();
-            h->pre.ws = h->dalloc(group_workspace_bytes((u64)want, h->n));
-            h->pre.pairs = static_cast<Rec *>(h->dalloc(sizeof(Rec) * group_pair_capacity((u64)want)));
-            h->pre.cap_records = want;
-        }
-        group_precount_reset(h->stream, h->pre.ws, (u64)h->pre.cap_records, h->n);
-    }
-    else if (st.count + count > h->pre.cap_records)
-    { // the stage grew beyond the workspace the earlier chunks were counted into
-        h->pre.dead = true;
-        return false;
-    }
-    if (counts)
-    {
-        *ct = group_count_target(h->pre.ws, h->pre.pairs, (u64)h->pre.cap_records, h->n, h->L);
-        *chunk0 = (u32)(st.count / W);
-    }
-    else
-    {
-        if (!h->pre.cols)
-            h->pre.cols = static_cast<u32 *>(h->dalloc(sizeof(u32) * (size_t)h->pre.cap_records));
-        *cols = h->pre.cols + st.count;
-    }
+    *rt = run_target(h->runs.ws, (u64)h->runs.cap_records, h->L);
+    *chunk0 = h->runs.nchunks;
+    *pos0 = (u32)st.count;
     return true;
 }
 
-// StageFlags of a producer that does not count itself: with the column side array when that helps
-StageFlags producer_flags(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count, bool *helps)
+void runs_end(xsb_matrix *h, i64 count, u32 chunks)
 {
-    StageFlags sf = h->stage_flags(tid);
-    u32 *cols = nullptr;
-    *helps = precount_begin(h, tid, flavour, count, false, nullptr, nullptr, &cols);
-    if (*helps)
-        sf.cols = cols;
-    return sf;
+    h->runs.nchunks += chunks;
+    h->runs.sorted_end += count;
 }
 
 void end_emit(xsb_matrix *h, int32_t tid, int32_t flavour, i64 count)
@@ -1271,7 +1474,7 @@ int32_t xsb_destroy(xsb_matrix *h)
     h->drop_frozen();
     h->drop_blocks();
     h->clear_staging(true);
-    h->precount_release();
+    h->runs_release();
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
     h->dfree(h->route_ws);
@@ -1364,7 +1567,7 @@ int32_t xsb_shrink_to_fit(xsb_matrix *h)
         if (h->pending() == 0)
         {
             h->clear_staging(true);
-            h->precount_release();
+            h->runs_release();
         }
         h->release_cache();
         return XSB_OK;
@@ -1414,44 +1617,29 @@ int32_t xsb_insert_batch(xsb_matrix *h, int32_t tid, const void *I, const void *
         Rec *dst = begin_emit(h, tid, flavour, count);
         DevIn dI(h, I, h->isz() * (size_t)count), dJ(h, J, h->isz() * (size_t)count), dV(h, V, 8 * (size_t)count);
         write_scalar(h, 1, ~0ull);
-        CountTarget ct;
-        u32 chunk0 = 0;
-        i64 counted = 0;
-        bool helps = false;
-        u64 bad = ~0ull;
-        if (precount_begin(h, tid, flavour, count, true, &ct, &chunk0, nullptr))
-        {
-            write_scalar(h, 2, ~0ull);
-            counted = pack_records_counted(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count,
-                                           h->idx64, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
-                                           h->d_scal + 1, h->d_scal + 2, h->lc, ct, chunk0);
-            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-            bad = read_scalar(h, 1);
-            if (h->h_scal[2] != ~0ull)
-                bad = std::min(bad, h->h_scal[2] + (u64)counted);
-        }
+        RunTarget rt;
+        u32 chunk0 = 0, pos0 = 0, chunks = 0;
+        const bool grouped = runs_begin(h, tid, count, pack_chunks(count), &rt, &chunk0, &pos0);
+        if (grouped)
+            chunks = pack_records_grouped(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64,
+                                          h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1,
+                                          h->lc, rt, chunk0, pos0, h->stage_flags(tid));
         else
-        {
             pack_records(h->stream, dI.ptr, dJ.ptr, static_cast<const double *>(dV.ptr), count, h->idx64, h->base, h->m,
-                         h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc,
-                         producer_flags(h, tid, flavour, count, &helps));
-            bad = read_scalar(h, 1);
-        }
+                         h->n_global, h->Ls, (u32)tid, (u32)flavour, dst, h->d_scal + 1, h->lc, h->stage_flags(tid));
+        const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)
         {
-            if (counted)
-                h->pre.dead = true; // the rejected batch left pairs behind: this assembly is counted at flush time
+            if (grouped)
+                h->runs.dead = true; // the rejected batch left runs behind: the index is rebuilt at flush time
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
                                             " of the batch is outside the matrix; batch rejected");
         }
+        if (h->n_tid > 1 && flavour == XSB_ASSIGN)
+            check_mt_assign(h, dst, count);
         end_emit(h, tid, flavour, count);
-        if (counted)
-        {
-            h->pre.counted += counted;
-            h->pre.colled = h->pre.counted;
-        }
-        else if (helps)
-            h->pre.colled += count;
+        if (grouped)
+            runs_end(h, count, chunks);
         return XSB_OK;
     });
 }
@@ -1476,42 +1664,28 @@ int32_t xsb_insert_triplets(xsb_matrix *h, int32_t tid, const xsb_triplet *T, in
             src = dst;
         }
         write_scalar(h, 1, ~0ull);
-        CountTarget ct;
-        u32 chunk0 = 0;
-        i64 counted = 0;
-        bool helps = false;
-        u64 bad = ~0ull;
-        if (precount_begin(h, tid, flavour, count, true, &ct, &chunk0, nullptr))
-        {
-            write_scalar(h, 2, ~0ull);
-            counted = pack_triplets_counted(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid,
-                                            (u32)flavour, dst, h->d_scal + 1, h->d_scal + 2, h->lc, ct, chunk0);
-            XSB_CUDA(cudaMemcpyAsync(h->h_scal + 2, h->d_scal + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-            bad = read_scalar(h, 1);
-            if (h->h_scal[2] != ~0ull)
-                bad = std::min(bad, h->h_scal[2] + (u64)counted);
-        }
+        RunTarget rt;
+        u32 chunk0 = 0, pos0 = 0, chunks = 0;
+        const bool grouped = runs_begin(h, tid, count, pack_chunks(count), &rt, &chunk0, &pos0);
+        if (grouped)
+            chunks = pack_triplets_grouped(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid,
+                                           (u32)flavour, dst, h->d_scal + 1, h->lc, rt, chunk0, pos0, h->stage_flags(tid));
         else
-        {
             pack_triplets(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
-                          h->d_scal + 1, h->lc, producer_flags(h, tid, flavour, count, &helps));
-            bad = read_scalar(h, 1);
-        }
+                          h->d_scal + 1, h->lc, h->stage_flags(tid));
+        const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)
         {
-            if (counted)
-                h->pre.dead = true;
+            if (grouped)
+                h->runs.dead = true;
             throw ApiError(XSB_EBOUNDS, "BoundsError: entry " + std::to_string(bad) +
                                             " of the batch is outside the matrix; batch rejected");
         }
+        if (h->n_tid > 1 && flavour == XSB_ASSIGN)
+            check_mt_assign(h, dst, count);
         end_emit(h, tid, flavour, count);
-        if (counted)
-        {
-            h->pre.counted += counted;
-            h->pre.colled = h->pre.counted;
-        }
-        else if (helps)
-            h->pre.colled += count;
+        if (grouped)
+            runs_end(h, count, chunks);
         return XSB_OK;
     });
 }
@@ -1848,8 +2022,16 @@ int32_t xsb_emit_fdrand_range(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny
         REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= N, XSB_EINVAL, "bad node range");
         const i64 count = fdrand_prefix(nx, ny, nz, l_end) - fdrand_prefix(nx, ny, nz, l_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        // no column side array here: with ~130 distinct columns per chunk the counting pass of this stream is
-        // bound by its table work, not by the 16-byte reads (measured: +0.05 ms emission, -0.05 ms counting)
+        RunTarget rt;
+        u32 chunk0 = 0, pos0 = 0;
+        if (runs_begin(h, tid, count, emit_fdrand_chunks(l_begin, l_end), &rt, &chunk0, &pos0))
+        {
+            const u32 chunks = emit_fdrand_grouped(h->stream, nx, ny, nz, seed, ones, h->Ls, (u32)tid, (u32)flavour, l_begin,
+                                                   l_end, dst, h->lc, h->stage_flags(tid), rt, chunk0, pos0);
+            end_emit(h, tid, flavour, count);
+            runs_end(h, count, chunks);
+            return XSB_OK;
+        }
         emit_fdrand(h->stream, nx, ny, nz, seed, ones, h->Ls, (u32)tid, (u32)flavour, l_begin, l_end, dst, h->lc,
                     h->stage_flags(tid));
         end_emit(h, tid, flavour, count);
@@ -1874,12 +2056,19 @@ int32_t xsb_emit_p1fem_range(xsb_matrix *h, int32_t tid, int64_t nxn, int64_t ny
         REQUIRE(0 <= cz_begin && cz_begin <= cz_end && cz_end <= nzn - 1, XSB_EINVAL, "bad cube-layer range");
         const i64 count = 20 * 6 * (nxn - 1) * (nyn - 1) * (cz_end - cz_begin);
         Rec *dst = begin_emit(h, tid, flavour, count);
-        bool helps = false;
+        RunTarget rt;
+        u32 chunk0 = 0, pos0 = 0;
+        if (runs_begin(h, tid, count, emit_p1fem_chunks(nxn, nyn, cz_begin, cz_end), &rt, &chunk0, &pos0))
+        {
+            const u32 chunks = emit_p1fem_grouped(h->stream, nxn, nyn, nzn, h->Ls, (u32)tid, (u32)flavour, cz_begin, cz_end,
+                                                  dst, h->lc, h->stage_flags(tid), rt, chunk0, pos0);
+            end_emit(h, tid, flavour, count);
+            runs_end(h, count, chunks);
+            return XSB_OK;
+        }
         emit_p1fem(h->stream, nxn, nyn, nzn, h->Ls, (u32)tid, (u32)flavour, cz_begin, cz_end, dst, h->lc,
-                   producer_flags(h, tid, flavour, count, &helps));
+                   h->stage_flags(tid));
         end_emit(h, tid, flavour, count);
-        if (helps)
-            h->pre.colled += count;
         return XSB_OK;
     });
 }
@@ -2003,6 +2192,7 @@ int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping)
         return XSB_EINVAL;
     h->grouping = grouping;
     h->grouping_misses = 0;
+    h->runs_misses = 0;
     return XSB_OK;
 }
 
@@ -2011,8 +2201,6 @@ int32_t xsb_set_precount(xsb_matrix *h, int32_t enable)
     if (!h)
         return XSB_EINVAL;
     h->precount = enable != 0;
-    if (!h->precount && h->pre.colled > 0)
-        h->pre.dead = true;
     return XSB_OK;
 }
 

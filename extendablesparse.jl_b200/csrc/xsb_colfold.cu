@@ -1120,14 +1120,8 @@ struct CtArgs
 template <int HBITS, bool LIST> void launch_colthread_t(cudaStream_t stream, unsigned blocks, const CtArgs &a)
 {
     constexpr size_t smem = CT_WARPS * CtShape<HBITS>::kBytesPerWarp;
-    static bool attr = false;
-    if (!attr)
-    {
-        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        XSB_CUDA(cudaFuncSetAttribute(colthread_kernel<HBITS, LIST>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      (int)cudaSharedmemCarveoutMaxShared));
-        attr = true;
-    }
+    static FuncAttrOnce once;
+    once.set(colthread_kernel<HBITS, LIST>, (int)smem, true);
     colthread_kernel<HBITS, LIST><<<blocks, CT_WARPS * 32, smem, stream>>>(
         a.sorted, a.low, a.rowbits, a.maxlen, a.nzcol, a.nzstart, a.totals, a.tmp, a.colcount, a.src, a.src_count, a.next,
         a.next_count, a.longlist, a.long_count, a.maxd);
@@ -1228,14 +1222,8 @@ void launch_direct_t(cudaStream_t stream, unsigned blocks, const Rec *sorted, in
                      double *nzval, void *colptr, u64 *status, u32 *ticket, u64 *d_nnz, u32 *d_redo, u32 *maxd)
 {
     constexpr size_t smem = CT_WARPS * CtShape<HBITS>::kBytesPerWarp;
-    static bool attr = false;
-    if (!attr)
-    {
-        XSB_CUDA(cudaFuncSetAttribute(colthread_direct_kernel<HBITS, Ti>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        XSB_CUDA(cudaFuncSetAttribute(colthread_direct_kernel<HBITS, Ti>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      (int)cudaSharedmemCarveoutMaxShared));
-        attr = true;
-    }
+    static FuncAttrOnce once;
+    once.set(colthread_direct_kernel<HBITS, Ti>, (int)smem, true);
     colthread_direct_kernel<HBITS, Ti><<<blocks, CT_WARPS * 32, smem, stream>>>(
         sorted, low, rowbits, maxlen, nzcol, nzstart, totals, ncols, (Ti)base, (Ti *)rowval, nzval, (Ti *)colptr, status,
         ticket, d_nnz, d_redo, maxd);
@@ -1399,12 +1387,8 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         }
         constexpr int W = 8;
         const size_t smem = sizeof(WarpSpace<true>) * W;
-        static bool attr = false;
-        if (!attr)
-        {
-            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<true, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        static FuncAttrOnce once;
+        once.set(colfold_kernel<true, W, true>, (int)smem);
         colfold_kernel<true, W, true><<<kNumSM * 2, W * 32, smem, stream>>>(sorted, L, combine, chunk, nzcol, nzstart, tilek,
                                                                           ntiles, tmp, cnt, d_overflow, longlist, counters + 2);
     }
@@ -1412,12 +1396,8 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     {
         constexpr int W = 8;
         const size_t smem = sizeof(WarpSpace<true>) * W;
-        static bool attr = false;
-        if (!attr)
-        {
-            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<true, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        static FuncAttrOnce once;
+        once.set(colfold_kernel<true, W, false>, (int)smem);
         colfold_kernel<true, W, false><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(
             sorted, L, combine, chunk, nzcol, nzstart, tilek, ntiles, tmp, cnt, d_overflow, nullptr, nullptr);
     }
@@ -1425,12 +1405,8 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
     {
         constexpr int W = 4;
         const size_t smem = sizeof(WarpSpace<false>) * W;
-        static bool attr = false;
-        if (!attr)
-        {
-            XSB_CUDA(cudaFuncSetAttribute(colfold_kernel<false, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        static FuncAttrOnce once;
+        once.set(colfold_kernel<false, W, false>, (int)smem);
         colfold_kernel<false, W, false><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(
             sorted, L, combine, chunk, nzcol, nzstart, tilek, ntiles, tmp, cnt, d_overflow, nullptr, nullptr);
     }

@@ -274,15 +274,11 @@ void column_reduce_emit_csc(cudaStream_t stream, const Rec *sorted, u64 nrec, Ke
     XSB_CUDA(cudaMemsetAsync(d_nnz, 0, sizeof(u64), stream));
     XSB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(u32), stream));
     const bool simple = plain_adds && L.tidbits == 0 && combine == 0;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        XSB_CUDA(cudaFuncSetAttribute(column_reduce_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static FuncAttrOnce once[4];
+    once[0].set(column_reduce_kernel<int64_t, true>, (int)smem);
+    once[1].set(column_reduce_kernel<int64_t, false>, (int)smem);
+    once[2].set(column_reduce_kernel<int32_t, true>, (int)smem);
+    once[3].set(column_reduce_kernel<int32_t, false>, (int)smem);
 #define XSB_LAUNCH_COL(TI, SIMPLE)                                                                                 \
     column_reduce_kernel<TI, SIMPLE><<<(unsigned)ntiles, CK_THREADS, smem, stream>>>(                              \
         sorted, nrec, L, posbits, combine, (TI)base, (TI *)rowval_out, nzval_out, colcount, status, counter, d_nnz, \

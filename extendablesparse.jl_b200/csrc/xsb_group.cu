@@ -874,15 +874,9 @@ bool group_by_column(cudaStream_t stream, const Rec *in, Rec *out, u64 nrec, i64
     unsigned short *chunkcnt = reinterpret_cast<unsigned short *>(ws + l.off_chunkcnt);
     u64 *ta = reinterpret_cast<u64 *>(ws + l.off_ta);
     u64 *tb = reinterpret_cast<u64 *>(ws + l.off_tb);
-    static bool attr = false;
-    if (!attr)
-    {
-        XSB_CUDA(cudaFuncSetAttribute(group_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(CountSpace) * GP_WARPS)));
-        XSB_CUDA(cudaFuncSetAttribute(group_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(ScatterSpace) * GP_WARPS)));
-        attr = true;
-    }
+    static FuncAttrOnce once[2];
+    once[0].set(group_count_kernel, (int)(sizeof(CountSpace) * GP_WARPS));
+    once[1].set(group_scatter_kernel, (int)(sizeof(ScatterSpace) * GP_WARPS));
     Rec *pairs_a = out;
     Rec *pairs_b = pre ? pre->pairs : out + l.cap;
 

@@ -9,7 +9,7 @@
 //
 // Compiled with -fmad=false: the element arithmetic must round like the CPU oracle's.
 #include "xsb_internal.h"
-#include "xsb_group_count.cuh"
+#include "xsb_chunk.cuh"
 
 namespace xsb {
 
@@ -94,9 +94,9 @@ void pack_triplets(cudaStream_t stream, const void *T, i64 count, int base, i64 
 }
 
 // ------------------------------------------------------------------------
-// pack + count: the same conversion, a warp per chunk of GP_W records, and the chunk's column
-// histogram (pass 1 of the grouping, xsb_group.cu) taken from the keys while they are in
-// registers -- the flush then does not read these records back just to count them.
+// pack + group: the same conversion, a warp per chunk of CH_RECORDS insertions, and the chunk is brought
+// into column order (xsb_chunk.cuh) while its records are in registers -- the flush then reads the
+// records of a column where they were staged and never moves them.
 // ------------------------------------------------------------------------
 template <typename Ti> struct SrcIJV
 {
@@ -112,7 +112,7 @@ template <typename Ti> struct SrcIJV
 };
 struct SrcTriplet
 {
-    const uint4 *T; // may alias the output: a thread reads and writes its own 16 bytes
+    const uint4 *T; // may alias the output: a warp reads its whole chunk before it writes any of it
     i64 base;
     __device__ __forceinline__ void load(i64 k, i64 &i, i64 &j, double &v) const
     {
@@ -123,111 +123,121 @@ struct SrcTriplet
     }
 };
 
-constexpr int PC_WARPS = 8;
+constexpr int PG_WARPS = 8;
+constexpr int PG_HB = 9;
+constexpr int PG_NB = CH_RECORDS / 32;
 
 template <class Src>
-__global__ void __launch_bounds__(PC_WARPS * 32)
-pack_count_kernel(Src src, u32 nchunks, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out,
-                  u64 *__restrict__ d_err, CountTarget ct, u32 chunk0)
+__global__ void __launch_bounds__(PG_WARPS * 32)
+pack_grouped_kernel(Src src, i64 count, u32 nchunks, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out,
+                    u64 *__restrict__ d_err, RunTarget rt, u32 chunk0, u32 pos0, StageFlags sf)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef ChunkSpaceT<PG_HB> Space;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 c = blockIdx.x * PC_WARPS + warp;
+    const u32 c = blockIdx.x * PG_WARPS + warp;
     if (c >= nchunks)
         return;
-    CountSpace &ws = reinterpret_cast<CountSpace *>(smem_raw)[warp];
-    count_space_init(ws, lane);
+    Space &ws = reinterpret_cast<Space *>(smem_raw)[warp];
+    chunk_space_init(ws, lane);
     const u32 lt = lanemask_lt();
-    u32 d = 0;
-    bool crowded = false;
-    const i64 k0 = (i64)c * GP_W + lane;
-#pragma unroll 1
-    for (int g = 0; g < GP_NB; g += 4)
+    const i64 c0 = (i64)c * CH_RECORDS;
+    const u32 len = (u32)min((i64)CH_RECORDS, count - c0);
+    Rec r[PG_NB];
+#pragma unroll
+    for (int b = 0; b < PG_NB; ++b)
     {
-        i64 i[4], j[4];
-        double v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            src.load(k0 + (g + q) * 32, i[q], j[q], v[q]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
+        const u32 p = b * 32 + lane;
+        r[b].key = 0;
+        r[b].val = 0.0;
+        if (p < len)
         {
-            const i64 k = k0 + (g + q) * 32;
-            if (i[q] < 0 || i[q] >= m || j[q] < 0 || j[q] >= n)
+            i64 i, j;
+            double v;
+            src.load(c0 + p, i, j, v);
+            if (i < 0 || i >= m || j < 0 || j >= n)
             { // BoundsError (sparsematrixcsc.jl:8-10): the batch is rejected, whatever is written here is dropped
-                atomicMin(d_err, (u64)k);
-                i[q] = 0;
-                j[q] = 0;
+                atomicMin(d_err, (u64)(c0 + p));
+                i = 0;
+                j = 0;
             }
-            Rec r;
-            r.key = L.pack((u64)j[q], (u64)i[q], tid, flavour);
-            r.val = v[q];
-            if (d > (u32)GP_H - 64u)
-                crowded = true; // the table may not take another 32 columns: no column locality here
-            if (!crowded)
-                count_batch<true>(ws, r.key, true, ct.colshift, ct.colmask, lt, d);
-            st_rec(out + k, r);
+            r[b].key = L.pack((u64)j, (u64)i, tid, flavour);
+            r[b].val = v;
         }
     }
-    count_publish(ws, ct, chunk0 + c, d, crowded, lane);
+    u32 rs[PG_NB];
+    u32 d = 0;
+    bool grouped = true;
+#pragma unroll
+    for (int b = 0; b < PG_NB; ++b)
+    {
+        rs[b] = 0;
+        if ((u32)(b * 32) < len && grouped) // warp-uniform
+        {
+            if (d > Space::DMAX - 32u)
+                grouped = false; // the table may not take another 32 columns: no column locality here
+            else
+                rs[b] = chunk_count_batch(ws, (u32)(r[b].key >> rt.colshift) & rt.gmask, b * 32 + lane < len, lt, d);
+        }
+    }
+    if (grouped)
+        chunk_scan(ws, d, lane);
+#pragma unroll
+    for (int b = 0; b < PG_NB; ++b)
+    {
+        const u32 p = b * 32 + lane;
+        if (p < len)
+        {
+            const u32 dst = grouped ? chunk_dest(ws.start, rs[b]) : p;
+            st_rec(out + c0 + dst, r[b]);
+            if (sf.flags != nullptr && L.owner(r[b].key) != (u32)L.self)
+                sf.flags[(sf.pos0 + c0 + (i64)dst) >> kRouteTileShift] = 1; // benign race: same value
+        }
+    }
+    chunk_publish(ws, rt, chunk0 + c, pos0 + (u32)c0, d, grouped, lane);
 }
 
 template <class Src>
-static void launch_pack_count(cudaStream_t stream, Src src, i64 nchunks, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour,
-                              Rec *out, u64 *d_err, const CountTarget &ct, u32 chunk0, LaunchCounter &lc)
+static u32 launch_pack_grouped(cudaStream_t stream, Src src, i64 count, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour,
+                               Rec *out, u64 *d_err, const RunTarget &rt, u32 chunk0, u32 pos0, StageFlags sf,
+                               LaunchCounter &lc)
 {
-    static bool attr = false;
-    const int smem = (int)(sizeof(CountSpace) * PC_WARPS);
-    if (!attr)
-    {
-        XSB_CUDA(cudaFuncSetAttribute(pack_count_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
-    const unsigned blocks = (unsigned)((nchunks + PC_WARPS - 1) / PC_WARPS);
-    pack_count_kernel<Src><<<blocks, PC_WARPS * 32, smem, stream>>>(src, (u32)nchunks, m, n, L, tid, flavour, out,
-                                                                    d_err, ct, chunk0);
+    static FuncAttrOnce once;
+    const int smem = (int)(sizeof(ChunkSpaceT<PG_HB>) * PG_WARPS);
+    once.set(pack_grouped_kernel<Src>, smem);
+    const u32 nchunks = (u32)((count + CH_RECORDS - 1) / CH_RECORDS);
+    const unsigned blocks = (nchunks + PG_WARPS - 1) / PG_WARPS;
+    pack_grouped_kernel<Src><<<blocks, PG_WARPS * 32, smem, stream>>>(src, count, nchunks, m, n, L, tid, flavour, out,
+                                                                      d_err, rt, chunk0, pos0, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
+    return nchunks;
 }
 
-// whole chunks of the batch through the fused kernel, the tail through the plain one (its first
-// offending position, relative to the tail, goes to d_err_tail); returns the records that were counted
-i64 pack_records_counted(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
+u32 pack_chunks(i64 count) { return (u32)((count + CH_RECORDS - 1) / CH_RECORDS); }
+
+// returns the chunks appended to the run index (pack_chunks(count))
+u32 pack_records_grouped(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                          int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
-                         u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct, u32 chunk0)
+                         LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0, StageFlags sf)
 {
-    const i64 nchunks = count / GP_W, whole = nchunks * GP_W;
-    if (nchunks > 0)
-    {
-        if (idx64)
-            launch_pack_count(stream, SrcIJV<int64_t>{(const int64_t *)I, (const int64_t *)J, V, (i64)base}, nchunks, m, n,
-                              L, tid, flavour, out, d_err, ct, chunk0, lc);
-        else
-            launch_pack_count(stream, SrcIJV<int32_t>{(const int32_t *)I, (const int32_t *)J, V, (i64)base}, nchunks, m, n,
-                              L, tid, flavour, out, d_err, ct, chunk0, lc);
-    }
-    if (count > whole)
-    {
-        const size_t isz = idx64 ? 8 : 4;
-        pack_records(stream, static_cast<const unsigned char *>(I) + isz * (size_t)whole,
-                     static_cast<const unsigned char *>(J) + isz * (size_t)whole, V + whole, count - whole, idx64, base, m,
-                     n, L, tid, flavour, out + whole, d_err_tail, lc);
-    }
-    return whole;
+    if (count <= 0)
+        return 0;
+    if (idx64)
+        return launch_pack_grouped(stream, SrcIJV<int64_t>{(const int64_t *)I, (const int64_t *)J, V, (i64)base}, count, m,
+                                   n, L, tid, flavour, out, d_err, rt, chunk0, pos0, sf, lc);
+    return launch_pack_grouped(stream, SrcIJV<int32_t>{(const int32_t *)I, (const int32_t *)J, V, (i64)base}, count, m, n,
+                               L, tid, flavour, out, d_err, rt, chunk0, pos0, sf, lc);
 }
 
-i64 pack_triplets_counted(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
-                          u32 flavour, Rec *out, u64 *d_err, u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct,
-                          u32 chunk0)
+u32 pack_triplets_grouped(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
+                          u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0,
+                          StageFlags sf)
 {
-    const i64 nchunks = count / GP_W, whole = nchunks * GP_W;
-    if (nchunks > 0)
-        launch_pack_count(stream, SrcTriplet{static_cast<const uint4 *>(T), (i64)base}, nchunks, m, n, L, tid, flavour,
-                          out, d_err, ct, chunk0, lc);
-    if (count > whole)
-        pack_triplets(stream, static_cast<const uint4 *>(T) + whole, count - whole, base, m, n, L, tid, flavour,
-                      out + whole, d_err_tail, lc, StageFlags{nullptr, 0});
-    return whole;
+    if (count <= 0)
+        return 0;
+    return launch_pack_grouped(stream, SrcTriplet{static_cast<const uint4 *>(T), (i64)base}, count, m, n, L, tid, flavour,
+                               out, d_err, rt, chunk0, pos0, sf, lc);
 }
 
 template <typename Ti>
@@ -351,6 +361,47 @@ i64 fdrand_prefix(i64 nx, i64 ny, i64 nz, i64 l)
 constexpr int FD_THREADS = 128; // nodes per block
 constexpr int FD_MAXREC = 15;   // records per node upper bound
 
+// records of node l0 (0-based), in call order, to dst[0 ..); returns their number
+__device__ __forceinline__ int fd_node_records(const FdGeom &g, i64 l0, u64 seed, int ones, const KeyLayout &L, u32 tid,
+                                               u32 flavour, Rec *dst)
+{
+    const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+    int pos = 0;
+    u64 call = (u64)g.before<1>(i, j, k);
+    const double hx = 1.0 / (double)g.nx, hy = 1.0 / (double)g.ny, hz = 1.0 / (double)g.nz;
+    const u64 l = (u64)l0; // 0-based unknown
+    auto rnd = [&]() -> double {
+        const double u = ones ? 1.0 : philox_uniform(seed, call);
+        ++call;
+        return u;
+    };
+    auto put = [&](double v, u64 row, u64 col) {
+        Rec r;
+        r.key = L.pack(col, row, tid, flavour);
+        r.val = v;
+        dst[pos++] = r;
+    };
+    auto pair = [&](double v, u64 a, u64 b) { // update_pair, sprand.jl:87-92
+        put(-v, a, b);
+        put(-v, b, a);
+        put(v, a, a);
+        put(v, b, b);
+    };
+    if (i < g.nx)
+        pair(rnd() * hy * hz / hx, l, l + 1);
+    if (i == 1 || i == g.nx)
+        put(rnd() * hy * hz, l, l);
+    if (j < g.ny)
+        pair(rnd() * hx * hz / hy, l, l + (u64)g.nx);
+    if (g.ny > 2 && (j == 1 || j == g.ny))
+        put(rnd() * hx * hz, l, l);
+    if (k < g.nz)
+        pair(rnd() * hx * hy / hz, l, l + (u64)(g.nx * g.ny));
+    if (g.nz > 2 && (k == 1 || k == g.nz))
+        put(rnd() * hx * hy, l, l);
+    return pos;
+}
+
 __global__ void __launch_bounds__(FD_THREADS)
 emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour, i64 l_begin, i64 l_end,
                    i64 rec_begin, Rec *__restrict__ out, StageFlags sf)
@@ -362,47 +413,78 @@ emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavo
     const i64 blk_rec1 = g.before_node<4>(l_last);
     const i64 l0 = l_first + threadIdx.x;
     if (l0 < l_last)
-    {
-        const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
-        i64 pos = g.before<4>(i, j, k) - blk_rec0;
-        u64 call = (u64)g.before<1>(i, j, k);
-        const double hx = 1.0 / (double)g.nx, hy = 1.0 / (double)g.ny, hz = 1.0 / (double)g.nz;
-        const u64 l = (u64)l0; // 0-based unknown
-        auto rnd = [&]() -> double {
-            const double u = ones ? 1.0 : philox_uniform(seed, call);
-            ++call;
-            return u;
-        };
-        auto put = [&](double v, u64 row, u64 col) {
-            Rec r;
-            r.key = L.pack(col, row, tid, flavour);
-            r.val = v;
-            s_rec[pos++] = r;
-        };
-        auto pair = [&](double v, u64 a, u64 b) { // update_pair, sprand.jl:87-92
-            put(-v, a, b);
-            put(-v, b, a);
-            put(v, a, a);
-            put(v, b, b);
-        };
-        if (i < g.nx)
-            pair(rnd() * hy * hz / hx, l, l + 1);
-        if (i == 1 || i == g.nx)
-            put(rnd() * hy * hz, l, l);
-        if (j < g.ny)
-            pair(rnd() * hx * hz / hy, l, l + (u64)g.nx);
-        if (g.ny > 2 && (j == 1 || j == g.ny))
-            put(rnd() * hx * hz, l, l);
-        if (k < g.nz)
-            pair(rnd() * hx * hy / hz, l, l + (u64)(g.nx * g.ny));
-        if (g.nz > 2 && (k == 1 || k == g.nz))
-            put(rnd() * hx * hy, l, l);
-    }
+        fd_node_records(g, l0, seed, ones, L, tid, flavour, s_rec + (g.before_node<4>(l0) - blk_rec0));
     __syncthreads();
     const i64 nrec = blk_rec1 - blk_rec0;
     Rec *dst = out + (blk_rec0 - rec_begin);
     for (i64 q = threadIdx.x; q < nrec; q += FD_THREADS)
         st_staged(dst + q, s_rec[q], L, sf, out);
+}
+
+// Grouped chunks (xsb_chunk.cuh): the records of a warp's 32 nodes (at most 480) = one chunk.
+constexpr int FDG_HB = 8;
+constexpr int FDG_NB = FD_MAXREC; // 32 nodes x at most 15 records
+struct FdWarpSpace
+{
+    Rec rec[32 * FD_MAXREC];
+    ChunkSpaceT<FDG_HB> tab;
+};
+
+__global__ void __launch_bounds__(FD_THREADS)
+emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour, i64 l_begin, i64 l_end,
+                           i64 rec_begin, Rec *__restrict__ out, StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FdWarpSpace &sp = reinterpret_cast<FdWarpSpace *>(smem_raw)[warp];
+    const u32 wchunk = blockIdx.x * (FD_THREADS / 32) + warp;
+    const i64 l_first = l_begin + (i64)wchunk * 32;
+    if (l_first >= l_end)
+        return;
+    const i64 l_last = min(l_first + 32, l_end);
+    const i64 w_rec0 = g.before_node<4>(l_first);
+    const u32 len = (u32)(g.before_node<4>(l_last) - w_rec0);
+    chunk_space_init(sp.tab, lane);
+    const i64 l0 = l_first + lane;
+    if (l0 < l_last)
+        fd_node_records(g, l0, seed, ones, L, tid, flavour, sp.rec + (g.before_node<4>(l0) - w_rec0));
+    __syncwarp();
+    const i64 c0 = w_rec0 - rec_begin; // position of the chunk in this launch's output
+    const u32 lt = lanemask_lt();
+    u32 rs[FDG_NB];
+    u32 d = 0;
+    bool grouped = true;
+#pragma unroll
+    for (int b = 0; b < FDG_NB; ++b)
+    {
+        rs[b] = 0;
+        if ((u32)(b * 32) < len && grouped) // warp-uniform
+        {
+            const u32 q = b * 32 + lane;
+            const u64 key = q < len ? sp.rec[q].key : 0ull;
+            if (d > ChunkSpaceT<FDG_HB>::DMAX - 32u)
+                grouped = false;
+            else
+                rs[b] = chunk_count_batch(sp.tab, (u32)(key >> rt.colshift) & rt.gmask, q < len, lt, d);
+        }
+    }
+    if (grouped)
+        chunk_scan(sp.tab, d, lane);
+    Rec *dst = out + c0;
+#pragma unroll
+    for (int b = 0; b < FDG_NB; ++b)
+    {
+        const u32 q = b * 32 + lane;
+        if (q < len)
+        {
+            const Rec r = sp.rec[q];
+            const u32 to = grouped ? chunk_dest(sp.tab.start, rs[b]) : q;
+            st_rec(dst + to, r);
+            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                sf.flags[(sf.pos0 + c0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
+        }
+    }
+    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, grouped, lane);
 }
 
 void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid,
@@ -418,6 +500,26 @@ void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones
     XSB_CUDA(cudaGetLastError());
 }
 
+u32 emit_fdrand_chunks(i64 l_begin, i64 l_end) { return (u32)((l_end - l_begin + 31) / 32); }
+
+u32 emit_fdrand_grouped(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour,
+                        i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0,
+                        u32 pos0)
+{
+    if (l_end <= l_begin)
+        return 0;
+    FdGeom g{nx, ny, nz};
+    static FuncAttrOnce once;
+    const int smem = (int)(sizeof(FdWarpSpace) * (FD_THREADS / 32));
+    once.set(emit_fdrand_grouped_kernel, smem, true);
+    const i64 blocks = (l_end - l_begin + FD_THREADS - 1) / FD_THREADS;
+    emit_fdrand_grouped_kernel<<<(unsigned)blocks, FD_THREADS, smem, stream>>>(
+        g, seed, ones, L, tid, flavour, l_begin, l_end, g.before_node<4>(l_begin), out, sf, rt, chunk0, pos0);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+    return emit_fdrand_chunks(l_begin, l_end);
+}
+
 // ------------------------------------------------------------------------
 // P1 FEM stream on the Kuhn tensor mesh: 20 rawupdateindex! calls per tetrahedron
 // (test/femtools.jl:62-69).  One thread per tetrahedron, 128 tetrahedra per block.
@@ -428,6 +530,120 @@ constexpr int FEM_THREADS = 128;
 constexpr int FEM_REC = 20;
 constexpr int FEM_PITCH = FEM_REC + 1;
 
+// The 20 records of tetrahedron t, in call order, to dst[0..20).  Returns 1 if one of its columns belongs to
+// another rank (slab handles).
+__device__ __forceinline__ int fem_tet_records(i64 t, i64 nxn, i64 nyn, i64 nzn, const KeyLayout &L, u32 tid, u32 flavour,
+                                               bool slab, Rec *dst)
+{
+    int has_foreign = 0;
+    const i64 cube = t / 6;
+    const int perm = (int)(t % 6);
+    const i64 cxn = nxn - 1, cyn = nyn - 1;
+    i64 idx[4][3];
+    idx[0][0] = cube % cxn;
+    idx[0][1] = (cube / cxn) % cyn;
+    idx[0][2] = cube / (cxn * cyn);
+#pragma unroll
+    for (int v = 1; v < 4; ++v)
+    {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            idx[v][d] = idx[v - 1][d] + (c_kuhn[perm][v - 1] == d ? 1 : 0);
+    }
+    const double dx = (double)(nxn - 1), dy = (double)(nyn - 1), dz = (double)(nzn - 1);
+    // a vertex coordinate is index / cells; along an axis the four vertices only take the cube's lower
+    // or upper index, so two divisions per axis (not four) give the same bits
+    const double dd[3] = {dx, dy, dz};
+    double lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+        lo[d] = (double)idx[0][d] / dd[d];
+        hi[d] = (double)(idx[0][d] + 1) / dd[d];
+    }
+    double p[4][3];
+    u64 node[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+    {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            p[v][d] = idx[v][d] == idx[0][d] ? lo[d] : hi[d];
+        node[v] = (u64)(idx[v][0] + nxn * idx[v][1] + nxn * nyn * idx[v][2]);
+    }
+    // P1 gradients from the inverse edge matrix; operation order mirrors the CPU oracle
+    double a[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            a[r][c] = p[c + 1][r] - p[0][r];
+    const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+    const double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+    const double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+    const double c10 = a[0][2] * a[2][1] - a[0][1] * a[2][2];
+    const double c11 = a[0][0] * a[2][2] - a[0][2] * a[2][0];
+    const double c12 = a[0][1] * a[2][0] - a[0][0] * a[2][1];
+    const double c20 = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+    const double c21 = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+    const double c22 = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+    const double det = (a[0][0] * c00 + a[0][1] * c01) + a[0][2] * c02;
+    double gr[4][3];
+    gr[1][0] = c00 / det;
+    gr[1][1] = c10 / det;
+    gr[1][2] = c20 / det;
+    gr[2][0] = c01 / det;
+    gr[2][1] = c11 / det;
+    gr[2][2] = c21 / det;
+    gr[3][0] = c02 / det;
+    gr[3][1] = c12 / det;
+    gr[3][2] = c22 / det;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        gr[0][d] = -((gr[1][d] + gr[2][d]) + gr[3][d]);
+    const double vol = fabs(det) / 6.0;
+    double S[4][4];
+#pragma unroll
+    for (int il = 0; il < 4; ++il)
+#pragma unroll
+        for (int jl = il; jl < 4; ++jl)
+        {
+            double sum = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                sum += gr[jl][d] * gr[il][d];
+            S[il][jl] = sum;
+            S[jl][il] = sum;
+        }
+    int q = 0;
+    u64 ckey[4], rkey[4]; // a node is the column of 5 and the row of 5 of the element's 20 records
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+    {
+        ckey[v] = L.colpart(node[v]);
+        rkey[v] = L.rowpart(node[v], tid, flavour);
+        if (slab && L.owner(ckey[v]) != (u32)L.self)
+            has_foreign = 1; // slab handles: a column of this element belongs to another rank
+    }
+#pragma unroll
+    for (int il = 0; il < 4; ++il)
+    {
+        Rec r;
+        r.key = ckey[il] | rkey[il];
+        r.val = 0.1 * vol / 4.0;
+        dst[q++] = r;
+#pragma unroll
+        for (int jl = 0; jl < 4; ++jl)
+        {
+            r.key = ckey[jl] | rkey[il]; // A[i,j]: row = node[il], col = node[jl]
+            r.val = vol * S[il][jl];
+            dst[q++] = r;
+        }
+    }
+    return has_foreign;
+}
+
+// Stream order: a block's records through shared memory, coalesced 16-byte stores.
 __global__ void __launch_bounds__(FEM_THREADS)
 emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
                   Rec *__restrict__ out, StageFlags sf)
@@ -440,113 +656,7 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     const i64 t = t_first + threadIdx.x;
     int has_foreign = 0;
     if (t < t_last)
-    {
-        const i64 cube = t / 6;
-        const int perm = (int)(t % 6);
-        const i64 cxn = nxn - 1, cyn = nyn - 1;
-        i64 idx[4][3];
-        idx[0][0] = cube % cxn;
-        idx[0][1] = (cube / cxn) % cyn;
-        idx[0][2] = cube / (cxn * cyn);
-#pragma unroll
-        for (int v = 1; v < 4; ++v)
-        {
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                idx[v][d] = idx[v - 1][d] + (c_kuhn[perm][v - 1] == d ? 1 : 0);
-        }
-        const double dx = (double)(nxn - 1), dy = (double)(nyn - 1), dz = (double)(nzn - 1);
-        // a vertex coordinate is index / cells; along an axis the four vertices only take the cube's lower
-        // or upper index, so two divisions per axis (not four) give the same bits
-        const double dd[3] = {dx, dy, dz};
-        double lo[3], hi[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-        {
-            lo[d] = (double)idx[0][d] / dd[d];
-            hi[d] = (double)(idx[0][d] + 1) / dd[d];
-        }
-        double p[4][3];
-        u64 node[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-        {
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                p[v][d] = idx[v][d] == idx[0][d] ? lo[d] : hi[d];
-            node[v] = (u64)(idx[v][0] + nxn * idx[v][1] + nxn * nyn * idx[v][2]);
-        }
-        // P1 gradients from the inverse edge matrix; operation order mirrors the CPU oracle
-        double a[3][3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                a[r][c] = p[c + 1][r] - p[0][r];
-        const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
-        const double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
-        const double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
-        const double c10 = a[0][2] * a[2][1] - a[0][1] * a[2][2];
-        const double c11 = a[0][0] * a[2][2] - a[0][2] * a[2][0];
-        const double c12 = a[0][1] * a[2][0] - a[0][0] * a[2][1];
-        const double c20 = a[0][1] * a[1][2] - a[0][2] * a[1][1];
-        const double c21 = a[0][2] * a[1][0] - a[0][0] * a[1][2];
-        const double c22 = a[0][0] * a[1][1] - a[0][1] * a[1][0];
-        const double det = (a[0][0] * c00 + a[0][1] * c01) + a[0][2] * c02;
-        double gr[4][3];
-        gr[1][0] = c00 / det;
-        gr[1][1] = c10 / det;
-        gr[1][2] = c20 / det;
-        gr[2][0] = c01 / det;
-        gr[2][1] = c11 / det;
-        gr[2][2] = c21 / det;
-        gr[3][0] = c02 / det;
-        gr[3][1] = c12 / det;
-        gr[3][2] = c22 / det;
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-            gr[0][d] = -((gr[1][d] + gr[2][d]) + gr[3][d]);
-        const double vol = fabs(det) / 6.0;
-        double S[4][4];
-#pragma unroll
-        for (int il = 0; il < 4; ++il)
-#pragma unroll
-            for (int jl = il; jl < 4; ++jl)
-            {
-                double s = 0.0;
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                    s += gr[jl][d] * gr[il][d];
-                S[il][jl] = s;
-                S[jl][il] = s;
-            }
-        Rec *dst = s_rec + threadIdx.x * FEM_PITCH;
-        int q = 0;
-        u64 ckey[4], rkey[4]; // a node is the column of 5 and the row of 5 of the element's 20 records
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-        {
-            ckey[v] = L.colpart(node[v]);
-            rkey[v] = L.rowpart(node[v], tid, flavour);
-            if (sf.flags != nullptr && L.owner(ckey[v]) != (u32)L.self)
-                has_foreign = 1; // slab handles: a column of this element belongs to another rank
-        }
-#pragma unroll
-        for (int il = 0; il < 4; ++il)
-        {
-            Rec r;
-            r.key = ckey[il] | rkey[il];
-            r.val = 0.1 * vol / 4.0;
-            dst[q++] = r;
-#pragma unroll
-            for (int jl = 0; jl < 4; ++jl)
-            {
-                r.key = ckey[jl] | rkey[il]; // A[i,j]: row = node[il], col = node[jl]
-                r.val = vol * S[il][jl];
-                dst[q++] = r;
-            }
-        }
-    }
+        has_foreign = fem_tet_records(t, nxn, nyn, nzn, L, tid, flavour, sf.flags != nullptr, s_rec + threadIdx.x * FEM_PITCH);
     // slab handles: only blocks at a slab face hold records of other ranks; every other block stores without
     // looking at owner bits (the emitter is issue-bound: the per-record checks cost 0.16 ms of 1.07 ms)
     if (!__syncthreads_or(has_foreign))
@@ -554,19 +664,84 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
     const i64 nrec = (t_last - t_first) * FEM_REC;
     const i64 pos0 = (t_first - tet_begin) * FEM_REC;
     Rec *dst = out + pos0;
-    // column side array (StageFlags::cols): written here, in the coalesced store loop, not per record in st_staged
-    u32 *const cols = sf.cols ? sf.cols + pos0 : nullptr;
-    sf.cols = nullptr;
-    const int colshift = L.low + L.rowbits;
-    const u32 colmask = L.colbits >= 32 ? 0xffffffffu : ((1u << L.colbits) - 1u);
     for (i64 q = threadIdx.x; q < nrec; q += FEM_THREADS)
     {
-        const int t = (int)q / FEM_REC;
-        const Rec r = s_rec[t * FEM_PITCH + ((int)q - t * FEM_REC)];
+        const int tt = (int)q / FEM_REC;
+        const Rec r = s_rec[tt * FEM_PITCH + ((int)q - tt * FEM_REC)];
         st_staged(dst + q, r, L, sf, out);
-        if (cols)
-            cols[q] = (sf.flags != nullptr && L.owner(r.key) != (u32)L.self) ? kNotMine : ((u32)(r.key >> colshift) & colmask);
     }
+}
+
+// Grouped chunks (xsb_chunk.cuh): a warp's 32 tetrahedra = one chunk of 640 records, brought into column
+// order in the warp's own shared memory (no block-wide barrier) and stored where the flush will read them.
+constexpr int FEMG_HB = 8;
+constexpr int FEMG_NB = FEM_REC; // 32 tetrahedra x 20 records = 20 batches of 32
+struct FemWarpSpace
+{
+    Rec rec[32 * FEM_PITCH];
+    ChunkSpaceT<FEMG_HB> tab;
+};
+
+__global__ void __launch_bounds__(FEM_THREADS)
+emit_p1fem_grouped_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
+                          Rec *__restrict__ out, StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr u32 full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FemWarpSpace &sp = reinterpret_cast<FemWarpSpace *>(smem_raw)[warp];
+    const u32 wchunk = blockIdx.x * (FEM_THREADS / 32) + warp; // chunk of this warp
+    const i64 t_first = tet_begin + (i64)wchunk * 32;
+    if (t_first >= tet_end)
+        return;
+    const i64 t_last = min(t_first + 32, tet_end);
+    const i64 t = t_first + lane;
+    chunk_space_init(sp.tab, lane);
+    int has_foreign = 0;
+    if (t < t_last)
+        has_foreign = fem_tet_records(t, nxn, nyn, nzn, L, tid, flavour, sf.flags != nullptr, sp.rec + lane * FEM_PITCH);
+    if (!__any_sync(full, has_foreign))
+        sf.flags = nullptr;
+    __syncwarp();
+    const u32 len = (u32)(t_last - t_first) * FEM_REC;
+    const i64 c0 = (t_first - tet_begin) * FEM_REC; // position of the chunk in this launch's output
+    const u32 lt = lanemask_lt();
+    u32 rs[FEMG_NB];
+    u32 d = 0;
+    bool grouped = true;
+#pragma unroll
+    for (int b = 0; b < FEMG_NB; ++b)
+    {
+        rs[b] = 0;
+        if ((u32)(b * 32) < len && grouped) // warp-uniform
+        {
+            const u32 q = b * 32 + lane;
+            const u32 tt = q / FEM_REC;
+            const u64 key = q < len ? sp.rec[tt * FEM_PITCH + (q - tt * FEM_REC)].key : 0ull;
+            if (d > ChunkSpaceT<FEMG_HB>::DMAX - 32u)
+                grouped = false;
+            else
+                rs[b] = chunk_count_batch(sp.tab, (u32)(key >> rt.colshift) & rt.gmask, q < len, lt, d);
+        }
+    }
+    if (grouped)
+        chunk_scan(sp.tab, d, lane);
+    Rec *dst = out + c0;
+#pragma unroll
+    for (int b = 0; b < FEMG_NB; ++b)
+    {
+        const u32 q = b * 32 + lane;
+        if (q < len)
+        {
+            const u32 tt = q / FEM_REC;
+            const Rec r = sp.rec[tt * FEM_PITCH + (q - tt * FEM_REC)];
+            const u32 to = grouped ? chunk_dest(sp.tab.start, rs[b]) : q;
+            st_rec(dst + to, r);
+            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                sf.flags[(sf.pos0 + c0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
+        }
+    }
+    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, grouped, lane);
 }
 
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
@@ -581,6 +756,31 @@ void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32
                                                                     tet_end, out, sf);
     lc.add();
     XSB_CUDA(cudaGetLastError());
+}
+
+u32 emit_p1fem_chunks(i64 nxn, i64 nyn, i64 cz_begin, i64 cz_end)
+{
+    const i64 tets = 6 * (nxn - 1) * (nyn - 1) * (cz_end - cz_begin);
+    return (u32)((tets + 31) / 32);
+}
+
+// grouped variant: returns the chunks appended to the run index
+u32 emit_p1fem_grouped(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 cz_begin,
+                       i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0, u32 pos0)
+{
+    const i64 per_layer = 6 * (nxn - 1) * (nyn - 1);
+    const i64 tet_begin = cz_begin * per_layer, tet_end = cz_end * per_layer;
+    if (tet_end <= tet_begin)
+        return 0;
+    static FuncAttrOnce once;
+    const int smem = (int)(sizeof(FemWarpSpace) * (FEM_THREADS / 32));
+    once.set(emit_p1fem_grouped_kernel, smem, true);
+    const i64 blocks = (tet_end - tet_begin + FEM_THREADS - 1) / FEM_THREADS;
+    emit_p1fem_grouped_kernel<<<(unsigned)blocks, FEM_THREADS, smem, stream>>>(nxn, nyn, nzn, L, tid, flavour, tet_begin,
+                                                                               tet_end, out, sf, rt, chunk0, pos0);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+    return emit_p1fem_chunks(nxn, nyn, cz_begin, cz_end);
 }
 
 // ------------------------------------------------------------------------

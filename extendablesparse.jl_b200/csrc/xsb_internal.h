@@ -2,6 +2,7 @@
 #pragma once
 #include "xsb_common.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <vector>
 
@@ -69,6 +70,26 @@ struct StageTimer
             cudaEventDestroy(sp.b);
         }
         spans.clear();
+    }
+};
+
+// cudaFuncSetAttribute applies to the device that is current when it is called, and a process may hold
+// handles on several GPUs: remember per device what was set (devices >= 32: set on every launch).
+struct FuncAttrOnce
+{
+    std::atomic<unsigned> done{0};
+    template <class K> void set(K kernel, int smem_bytes, bool max_carveout = false)
+    {
+        int dev = 0;
+        XSB_CUDA(cudaGetDevice(&dev));
+        if (dev < 32 && ((done.load(std::memory_order_acquire) >> dev) & 1u))
+            return;
+        XSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        if (max_carveout)
+            XSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+        if (dev < 32)
+            done.fetch_or(1u << dev, std::memory_order_release);
     }
 };
 
@@ -185,6 +206,45 @@ void colfold_compact(cudaStream_t stream, const Rec *tmp, u64 nrec, i64 ncols, i
                      const void *colptr, void *rowval_out, double *nzval_out, void *workspace, LaunchCounter &lc,
                      StageTimer *timer);
 
+// ---- xsb_runs.cu / xsb_chunk.cuh: flush on grouped chunks (the product path)
+// Where the kernels that stage records publish the runs of their chunks (the run index of a handle).
+struct RunTarget
+{
+    u32 *counters;    // [0] pairs appended so far (ticket), [1] != 0: a chunk gave up / the pair list is full
+    uint2 *chunkinfo; // per chunk: (first pair, pairs)
+    u32 *chunkstart;  // per chunk: position of its first record in the staging buffer
+    u32 *pcol;        // per pair: grouping key = column (owner bits on top on slab handles)
+    u32 *pinfo;       // per pair: (offset of the run inside its chunk << 16) | records
+    u32 cap;          // room of the pair list
+    int colshift;
+    u32 gmask;        // mask of the grouping key
+};
+struct RunIndexLayout
+{
+    size_t off_counters, off_chunkinfo, off_chunkstart, off_pcol, off_pinfo, bytes;
+    u32 cap_pairs, cap_chunks;
+};
+// regions of a slab handle's staged records by position: own [0, own_end), received from lower ranks
+// [own_end, low_end), from higher ranks [low_end, ...).  The fold meets a column's runs as
+// [lower ranks | own | higher ranks], each in stream order.  Plain handles: own_end = low_end = 2^32-1.
+struct RunRegions
+{
+    u32 own_end, low_end;
+};
+RunIndexLayout run_index_layout(u64 cap_records);
+RunTarget run_target(void *workspace, u64 cap_records, const KeyLayout &L);
+bool runs_supported(const KeyLayout &L, u64 nrec, i64 ncols);
+u32 chunk_sort_chunks(u64 count);
+// groups buf[r0, r1) in place, chunk by chunk; chunk ids from chunk0
+void chunk_sort(cudaStream_t stream, Rec *buf, u64 r0, u64 r1, const RunTarget &rt, u32 chunk0, LaunchCounter &lc);
+size_t runs_workspace_bytes(u64 npairs, i64 ncols);
+void runs_bucket(cudaStream_t stream, const RunTarget &rt, u32 nchunks, u32 npairs, i64 ncols, const KeyLayout &L,
+                 RunRegions reg, void *workspace, LaunchCounter &lc);
+int runs_level_for(u32 maxd);
+void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncols, int idx64, int base, const CscView &old,
+               void *workspace, u32 npairs, int level, u32 maxlen, void *rowval_out, double *nzval_out, void *colptr_out,
+               u64 *d_nnz, u32 *d_redo, u32 *d_maxd, bool first_try, LaunchCounter &lc);
+
 // ---- xsb_route.cu
 size_t route_workspace_bytes(u64 n, int nranks);
 // tileflags != nullptr: only tiles whose byte is set can hold records of other ranks (StageFlags)
@@ -206,13 +266,23 @@ void preaggregate_records(cudaStream_t stream, const Rec *in, u64 nrec, const Ke
 void pack_records(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                   int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
                   LaunchCounter &lc, StageFlags sf = StageFlags{nullptr, 0});
-// pack + count (xsb_insert.cu): whole chunks are counted for the grouping while they are packed
-i64 pack_records_counted(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
+// pack + group (xsb_insert.cu, xsb_chunk.cuh): a warp per chunk brings its records into column order while it
+// packs them and publishes the chunk's runs; pos0 = position of out[0] among the staged records.  Return the
+// chunks appended to the run index.
+u32 pack_chunks(i64 count);
+u32 pack_records_grouped(cudaStream_t stream, const void *I, const void *J, const double *V, i64 count, int idx64,
                          int base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *out, u64 *d_err,
-                         u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct, u32 chunk0);
-i64 pack_triplets_counted(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
-                          u32 flavour, Rec *out, u64 *d_err, u64 *d_err_tail, LaunchCounter &lc, const CountTarget &ct,
-                          u32 chunk0);
+                         LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0, StageFlags sf);
+u32 pack_triplets_grouped(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
+                          u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0,
+                          StageFlags sf);
+u32 emit_fdrand_chunks(i64 l_begin, i64 l_end);
+u32 emit_fdrand_grouped(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour,
+                        i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0,
+                        u32 pos0);
+u32 emit_p1fem_chunks(i64 nxn, i64 nyn, i64 cz_begin, i64 cz_end);
+u32 emit_p1fem_grouped(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 cz_begin,
+                       i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0, u32 pos0);
 // pointblock (xsb_values.cu): CSC entries -> records of the block pattern; values into the blocks
 void pointblock_emit(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs, i64 nb,
                      KeyLayout Lb, Rec *out, u64 *d_err, LaunchCounter &lc);
@@ -240,6 +310,8 @@ void lookup_slots(cudaStream_t stream, const CscView &csc, i64 m, i64 n, int idx
                   const void *J, i64 count, i64 *slot, u64 *d_missing, u64 *d_oob, LaunchCounter &lc);
 void gather_values(cudaStream_t stream, const double *nzval, const i64 *slot, i64 count, double *out,
                    LaunchCounter &lc);
+void count_missing_records(cudaStream_t stream, const Rec *recs, i64 count, const KeyLayout &L, const CscView &csc,
+                           int idx64, int base, u64 *d_missing, LaunchCounter &lc);
 void slots_to_records(cudaStream_t stream, const i64 *slot, i64 count, Rec *out, LaunchCounter &lc);
 void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, i64 *segstart,
                       LaunchCounter &lc);

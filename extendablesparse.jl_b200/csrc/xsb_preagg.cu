@@ -151,13 +151,8 @@ void preaggregate_records(cudaStream_t stream, const Rec *in, u64 nrec, const Ke
 {
     if (nrec == 0)
         return;
-    static bool attr = false;
-    if (!attr)
-    {
-        XSB_CUDA(cudaFuncSetAttribute(preagg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(PreaggSpace) * PA_WARPS)));
-        attr = true;
-    }
+    static FuncAttrOnce once;
+    once.set(preagg_kernel, (int)(sizeof(PreaggSpace) * PA_WARPS));
     const u32 nchunks = (u32)((nrec + PA_W - 1) / PA_W);
     preagg_kernel<<<(nchunks + PA_WARPS - 1) / PA_WARPS, PA_WARPS * 32, sizeof(PreaggSpace) * PA_WARPS, stream>>>(
         in, nrec, L.low, nchunks, out, reinterpret_cast<unsigned long long *>(d_count));

@@ -1,0 +1,750 @@
+// xsb_runs.cu -- flush! on GROUPED CHUNKS (xsb_chunk.cuh): the staged records are never moved.
+//
+//   chunk_sort_kernel : brings what the producers left in stream order (records received from other
+//                       ranks, batches staged while grouping at insertion was off) into grouped chunks,
+//                       in place, and appends their (chunk, column) pairs to the run index.
+//   run_totals_kernel : pairs per column (one L2 atomic per pair).
+//   runpair_scan_kernel: exclusive scan over the columns (single pass, decoupled look-back): every
+//                       column's bucket in a pair-sized array.
+//   run_bucket_kernel : a warp per chunk drops its pairs into their columns' buckets as 8-byte run
+//                       descriptors [region rank | position in the staging buffer | records].
+//   runfold_kernel    : ONE THREAD per column of the matrix.  It puts its handful of run descriptors
+//                       into stream order, seeds a thread-private hash table (shared memory, laid out
+//                       [slot][lane]) with the column of the RESIDENT CSC, walks its runs where they lie
+//                       -- one probe and one add per record: the reference's accumulate-on-insert
+//                       (src/matrix/sparsematrixlnk.jl:210-253, CSC hits: src/matrix/extendable.jl:164-166)
+//                       as an exact left fold in insertion order -- sorts the entries by row
+//                       (sparsematrixlnk.jl:339) and writes rowval / nzval / colptr of the new matrix in
+//                       the same pass (block scan + look-back).  A column without new records is copied.
+//                       This is the 3-way merge of Base.:+(lnk, csc) (sparsematrixlnk.jl:328-378): old
+//                       entries are read once and written once, never turned back into records.
+//
+// HBM traffic of a flush: 16 B per staged record (read once) + the old CSC read once + the new CSC
+// written once + 20 B per (chunk, column) pair -- SURVEY.md 8(d)'s algorithmic bytes plus the pairs.
+#include "xsb_chunk.cuh"
+#include "xsb_internal.h"
+#include <cstdlib>
+
+namespace xsb {
+
+// ------------------------------------------------------------------------
+// flush-time grouping of a region, in place
+// ------------------------------------------------------------------------
+constexpr int CS_WARPS = 8;
+constexpr int CS_HB = 9;
+constexpr int CS_NB = CH_RECORDS / 32;
+
+__global__ void __launch_bounds__(CS_WARPS * 32)
+chunk_sort_kernel(Rec *buf, u64 r0, u64 r1, u32 chunk0, u32 nchunks, RunTarget rt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef ChunkSpaceT<CS_HB> Space;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 c = blockIdx.x * CS_WARPS + warp;
+    if (c >= nchunks)
+        return;
+    Space &ws = reinterpret_cast<Space *>(smem_raw)[warp];
+    chunk_space_init(ws, lane);
+    const u32 lt = lanemask_lt();
+    const u64 c0 = r0 + (u64)c * CH_RECORDS;
+    const u32 len = (u32)min((u64)CH_RECORDS, r1 - c0);
+    Rec *rec = buf + c0;
+    Rec r[CS_NB];
+#pragma unroll
+    for (int b = 0; b < CS_NB; ++b)
+    {
+        const u32 p = b * 32 + lane;
+        if (p < len)
+            r[b] = ld_rec_stream(rec + p);
+        else
+        {
+            r[b].key = 0;
+            r[b].val = 0.0;
+        }
+    }
+    u32 rs[CS_NB];
+    u32 d = 0;
+    bool grouped = true;
+#pragma unroll
+    for (int b = 0; b < CS_NB; ++b)
+    {
+        rs[b] = 0;
+        if ((u32)(b * 32) < len && grouped) // warp-uniform
+        {
+            if (d > Space::DMAX - 32u)
+                grouped = false; // the table may not take another 32 columns: no column locality here
+            else
+                rs[b] = chunk_count_batch(ws, (u32)(r[b].key >> rt.colshift) & rt.gmask, b * 32 + lane < len, lt, d);
+        }
+    }
+    if (grouped)
+    {
+        chunk_scan(ws, d, lane);
+#pragma unroll
+        for (int b = 0; b < CS_NB; ++b)
+            if ((u32)(b * 32 + lane) < len)
+                st_rec(rec + chunk_dest(ws.start, rs[b]), r[b]);
+    }
+    chunk_publish(ws, rt, chunk0 + c, (u32)c0, d, grouped, lane);
+}
+
+// ------------------------------------------------------------------------
+// pairs per column; scan; buckets
+// ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+run_totals_kernel(const u32 *__restrict__ counters, u32 cap, const u32 *__restrict__ pcol, int colbits, u32 me,
+                  u32 *__restrict__ colpairs)
+{
+    const u32 np = min(counters[0], cap);
+    const u32 cmask = (1u << colbits) - 1u;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride)
+    {
+        const u32 g = pcol[p];
+        if ((g >> colbits) == me) // records of other ranks (sent already) and padding are skipped
+            atomicAdd(colpairs + (g & cmask), 1u);
+    }
+}
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_IPT = 8;
+constexpr int SC_TILE = SC_THREADS * SC_IPT;
+
+// pstart[c] = pairs of the columns before c, c = 0..n (pstart[n] = all pairs of this rank)
+__global__ void __launch_bounds__(SC_THREADS)
+runpair_scan_kernel(const u32 *__restrict__ colpairs, i64 n, u32 *__restrict__ pstart, u64 *__restrict__ status,
+                    u32 *__restrict__ ticket)
+{
+    __shared__ u32 s_w[SC_THREADS / 32];
+    __shared__ u64 s_prefix;
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0)
+        s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 b0 = (i64)tile * SC_TILE + (i64)threadIdx.x * SC_IPT; // a thread owns SC_IPT consecutive columns
+    u32 v[SC_IPT];
+    u32 sum = 0;
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i)
+    {
+        v[i] = b0 + i < n ? colpairs[b0 + i] : 0u;
+        sum += v[i];
+    }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_w[warp] = incl;
+    __syncthreads();
+    u32 wpre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; ++w)
+    {
+        const u32 c = s_w[w];
+        if (w < warp)
+            wpre += c;
+        total += c;
+    }
+    if (warp == 0)
+    {
+        const u64 prefix = warp_lookback(status, tile, (u64)total, lane);
+        if (lane == 0)
+            s_prefix = prefix;
+    }
+    __syncthreads();
+    u32 run = (u32)s_prefix + wpre + incl - sum;
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i)
+    {
+        if (b0 + i <= n)
+            pstart[b0 + i] = run;
+        run += v[i];
+    }
+}
+
+// run descriptor: [region rank : 2][position of the run's first record : 32][records : 11]
+__device__ __forceinline__ u64 run_entry(u32 rank, u32 pos, u32 cnt) { return ((u64)rank << 43) | ((u64)pos << 11) | (u64)cnt; }
+
+// a warp per chunk: its pairs go into their columns' buckets.  colpairs counts DOWN: afterwards it is zero again.
+__global__ void __launch_bounds__(256)
+run_bucket_kernel(const uint2 *__restrict__ chunkinfo, const u32 *__restrict__ chunkstart, u32 nchunks,
+                  const u32 *__restrict__ pcol, const u32 *__restrict__ pinfo, int colbits, u32 me, RunRegions reg,
+                  const u32 *__restrict__ pstart, u32 *__restrict__ colpairs, u64 *__restrict__ bucket)
+{
+    const int lane = threadIdx.x & 31;
+    const u32 c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= nchunks)
+        return;
+    const uint2 info = chunkinfo[c];
+    const u32 start = chunkstart[c];
+    const u32 rank = start < reg.own_end ? 1u : (start < reg.low_end ? 0u : 2u);
+    const u32 cmask = (1u << colbits) - 1u;
+    for (u32 j = lane; j < info.y; j += 32)
+    {
+        const u32 p = info.x + j;
+        const u32 g = pcol[p];
+        if ((g >> colbits) != me)
+            continue;
+        const u32 col = g & cmask;
+        const u32 pi = pinfo[p];
+        const u32 slot = pstart[col] + atomicSub(colpairs + col, 1u) - 1u;
+        bucket[slot] = run_entry(rank, start + (pi >> 16), pi & 0xffffu);
+    }
+}
+
+// ------------------------------------------------------------------------
+// one THREAD per column: merge the column of the resident CSC with the column's runs
+// ------------------------------------------------------------------------
+constexpr int RF_WARPS = 4;
+constexpr u32 RF_EMPTY = 0xffffffffu;
+
+// Table shapes, smallest first.  The template argument is the number of hash bits, except 15 = the
+// 5-bit table with 16 instead of 24 accumulators (a P1 tetrahedral mesh has at most 15 rows per column).
+//   shape  4: 16 slots / 12 accumulators     shape 15: 32 / 16     shape 5: 32 / 24     shape 6: 64 / 32
+template <int HBITS> struct RfShape
+{
+    static constexpr int HB = HBITS == 15 ? 5 : HBITS;
+    static constexpr int H = 1 << HB;
+    static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? 24 : (HBITS == 15 ? 16 : 12));
+    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 2 : (HBITS == 15 ? 5 : 4));
+    static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + sizeof(u32)) * D);
+};
+
+// The fold state of one column.  A table slot holds (row << HB | accumulator index); accumulators are
+// numbered in order of first appearance.  Flavour semantics (single partition): src/matrix/sparsematrixlnk.jl
+// :178-253 behind the CSC-hit router src/matrix/extendable.jl:159-218.
+template <int HBITS> struct ThreadFold
+{
+    static constexpr int H = RfShape<HBITS>::H;
+    static constexpr int HB = RfShape<HBITS>::HB;
+    static constexpr u32 D = RfShape<HBITS>::D;
+    u32 *key;    // [slot * 32]
+    double *acc; // [i * 32]
+    u32 *rows;   // [i * 32]
+    u32 d = 0;       // accumulators in use
+    u32 pending = 0; // of which not (yet) existing: only updateindex! / setindex! of a zero touched them
+    u64 exmask = 0;  // accumulator i holds an existing entry
+    bool ovf = false;
+
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int s = 0; s < H; ++s)
+            key[s * 32] = RF_EMPTY;
+    }
+    __device__ __forceinline__ void apply(u32 row, double v, u32 fl)
+    {
+        u32 s = (row * 0x9E3779B1u) >> (32 - HB);
+        for (;;)
+        {
+            const u32 kk = key[s * 32];
+            const u32 x = kk ^ (row << HB);
+            if (x < D)
+            { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
+                if (fl == FL_ASSIGN)
+                { // A[i,j] = v: overwrites; creates only if v != 0 (sparsematrixlnk.jl:184-199)
+                    const bool ex = (exmask >> x) & 1ull;
+                    if (ex | (v != 0.0))
+                    {
+                        acc[x * 32] = v;
+                        if (!ex)
+                        {
+                            exmask |= 1ull << x;
+                            --pending;
+                        }
+                    }
+                    return;
+                }
+                acc[x * 32] = acc[x * 32] + v;
+                if (pending)
+                {
+                    if (!((exmask >> x) & 1ull) && ((fl != FL_UPDATE) | (v != 0.0)))
+                    {
+                        exmask |= 1ull << x;
+                        --pending;
+                    }
+                }
+                return;
+            }
+            if (kk == RF_EMPTY)
+            {
+                if (d >= D)
+                {
+                    ovf = true;
+                    return;
+                }
+                key[s * 32] = (row << HB) | d;
+                rows[d * 32] = row;
+                // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value seeds it
+                // (extendable.jl:165-166) or it is assigned; updateindex! / setindex! of a zero create
+                // nothing (:212,223,184)
+                const bool creates = (fl == FL_RAW) | (fl == FL_OLD) | (v != 0.0);
+                acc[d * 32] = (fl == FL_OLD || (fl == FL_ASSIGN && creates)) ? v : 0.0 + v;
+                if (creates)
+                    exmask |= 1ull << d;
+                else
+                    ++pending;
+                ++d;
+                return;
+            }
+            s = (s + 1) & (H - 1);
+        }
+    }
+    // existing entries as (row << HB | accumulator) words, insertion-sorted by row into key[0 .. j): taken in
+    // order of first appearance, which an assembly stream visits nearly in row order (few shifts)
+    __device__ __forceinline__ int finish()
+    {
+        u32 j = 0;
+        for (u32 i = 0; i < d; ++i)
+        {
+            if (!((exmask >> i) & 1ull))
+                continue;
+            const u32 kk = (rows[i * 32] << HB) | i;
+            u32 q = j;
+            while (q > 0)
+            {
+                const u32 prev = key[(q - 1) * 32];
+                if (prev < kk)
+                    break;
+                key[q * 32] = prev;
+                --q;
+            }
+            key[q * 32] = kk;
+            ++j;
+        }
+        return (int)j;
+    }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int HBITS, typename Ti>
+__global__ void __launch_bounds__(RF_WARPS * 32, RfShape<HBITS>::kBlocks)
+runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, const u32 *__restrict__ pstart,
+               u64 *__restrict__ bucket, const Ti *__restrict__ old_colptr, const Ti *__restrict__ old_rowval,
+               const double *__restrict__ old_nzval, i64 ncols, Ti base, Ti *__restrict__ rowval,
+               double *__restrict__ nzval, Ti *__restrict__ colptr, u64 *__restrict__ status, u32 *__restrict__ ticket,
+               u64 *__restrict__ d_nnz, u32 *__restrict__ d_redo, u32 *__restrict__ maxd)
+{
+    typedef RfShape<HBITS> Shape;
+    constexpr int H = Shape::H;
+    constexpr int HB = Shape::HB;
+    constexpr u32 D = Shape::D;
+    constexpr u32 full = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_wsum[RF_WARPS];
+    __shared__ u64 s_prefix;
+    __shared__ u32 s_bid;
+    // blocks take their columns in the order they START (ticket), so a block only ever waits for
+    // blocks that are already running: the look-back cannot starve whatever the dispatch order
+    if (threadIdx.x == 0)
+        s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 bid = s_bid;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ThreadFold<HBITS> f;
+    f.acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane;
+    f.key = reinterpret_cast<u32 *>(smem_raw + (size_t)RF_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
+    f.rows = reinterpret_cast<u32 *>(smem_raw + (size_t)RF_WARPS * 32 * (D * sizeof(double) + H * sizeof(u32))) +
+             warp * (D * 32) + lane;
+    const u32 rowmask = (1u << rowbits) - 1u;
+    const i64 k = (i64)bid * (RF_WARPS * 32) + threadIdx.x;
+    int j = 0;           // entries of this column in the new matrix
+    i64 os = 0, oe = 0;  // its entries in the resident matrix
+    bool copy = false;   // no new records: the old column is copied
+    if (k < ncols && ld_relaxed_u32(d_redo) == 0u)
+    {
+        if (old_colptr != nullptr)
+        {
+            os = (i64)old_colptr[k] - (i64)base;
+            oe = (i64)old_colptr[k + 1] - (i64)base;
+        }
+        const u32 ps = pstart[k], np = pstart[k + 1] - ps;
+        if (np == 0)
+        {
+            copy = true;
+            j = (int)(oe - os);
+        }
+        else if (np > kMaxColPairs || (u64)(oe - os) > (u64)D)
+            atomicOr(d_redo, np > kMaxColPairs ? 2u : (HBITS == 6 ? 5u : 1u));
+        else
+        {
+            // ---- the column's runs into stream order (insertion sort in place: they arrive nearly in order)
+            u64 *b = bucket + ps;
+            u64 prev = b[0];
+            u32 nrec = (u32)(prev & 0x7ffull);
+            for (u32 i = 1; i < np; ++i)
+            {
+                const u64 e = b[i];
+                nrec += (u32)(e & 0x7ffull);
+                if (e < prev)
+                {
+                    u32 q = i;
+                    while (q > 0 && b[q - 1] > e)
+                    {
+                        b[q] = b[q - 1];
+                        --q;
+                    }
+                    b[q] = e;
+                }
+                else
+                    prev = e;
+            }
+            if (nrec > maxlen)
+                atomicOr(d_redo, 2u); // a very long column would stall its warp: the caller takes another path
+            else
+            {
+                f.init();
+                // ---- the resident column seeds the table (CSC hits: extendable.jl:164-166)
+                for (i64 e = os; e < oe; ++e)
+                    f.apply((u32)((i64)old_rowval[e] - (i64)base), old_nzval[e], FL_OLD);
+                // ---- the runs, where the producers left them
+                u64 e = b[0];
+                for (u32 i = 0; i < np && !f.ovf; ++i)
+                {
+                    const u64 en = i + 1 < np ? b[i + 1] : 0ull;
+                    u32 cnt = (u32)(e & 0x7ffull);
+                    const u32 pos = (u32)(e >> 11);
+                    const Rec *p = buf + pos;
+                    if (i + 1 < np)
+                        prefetch_l2(buf + (u32)(en >> 11));
+                    if (pos & 1u)
+                    { // 256-bit loads need 32-byte alignment: an odd first record goes alone
+                        const Rec r = ld_rec_stream(p);
+                        f.apply((u32)(r.key >> low) & rowmask, r.val, (u32)r.key & 3u);
+                        ++p;
+                        --cnt;
+                    }
+                    const u32 npair = cnt >> 1;
+                    if (npair)
+                    {
+                        RecPair nx = ld_pair_stream(p);
+                        for (u32 q = 0; q < npair; ++q)
+                        {
+                            const RecPair cur = nx;
+                            if (q + 1 < npair)
+                                nx = ld_pair_stream(p + 2 * (q + 1));
+                            f.apply((u32)(cur.a.key >> low) & rowmask, cur.a.val, (u32)cur.a.key & 3u);
+                            if (!f.ovf)
+                                f.apply((u32)(cur.b.key >> low) & rowmask, cur.b.val, (u32)cur.b.key & 3u);
+                            if (f.ovf)
+                                break;
+                        }
+                        p += 2 * npair;
+                    }
+                    if ((cnt & 1u) && !f.ovf)
+                    {
+                        const Rec r = ld_rec_stream(p);
+                        f.apply((u32)(r.key >> low) & rowmask, r.val, (u32)r.key & 3u);
+                    }
+                    e = en;
+                }
+                if (f.ovf)
+                { // bit 2: not even the largest table takes this column
+                    atomicOr(d_redo, HBITS == 6 ? 5u : 1u);
+                    if (D + 1 > ld_relaxed_u32(maxd))
+                        atomicMax(maxd, D + 1);
+                }
+                else
+                {
+                    j = f.finish();
+                    if (f.d > ld_relaxed_u32(maxd))
+                        atomicMax(maxd, f.d);
+                }
+            }
+        }
+    }
+    // ---- entries before this column: warp scan, block scan, look-back over the blocks
+    u32 incl = (u32)j;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u32 t = __shfl_up_sync(full, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_wsum[warp] = incl;
+    __syncthreads();
+    u32 wpre = 0, btotal = 0;
+#pragma unroll
+    for (int w = 0; w < RF_WARPS; ++w)
+    {
+        const u32 c = s_wsum[w];
+        if (w < warp)
+            wpre += c;
+        btotal += c;
+    }
+    if (warp == 0)
+    {
+        const u64 prefix = warp_lookback(status, bid, (u64)btotal, lane);
+        if (lane == 0)
+            s_prefix = prefix;
+    }
+    __syncthreads();
+    if (k >= ncols)
+        return;
+    const u64 o0 = s_prefix + wpre + (incl - (u32)j);
+    colptr[k] = (Ti)o0 + base;
+    if (k == ncols - 1)
+    {
+        colptr[ncols] = (Ti)(o0 + (u64)j) + base;
+        *d_nnz = o0 + (u64)j;
+    }
+    if (copy)
+    { // untouched column: old entries move to their new place (read once, written once)
+        const Ti *srv = old_rowval + os;
+        const double *snv = old_nzval + os;
+        Ti *rv = rowval + o0;
+        double *nv = nzval + o0;
+        for (int e = 0; e < j; ++e)
+        {
+            rv[e] = srv[e];
+            nv[e] = snv[e];
+        }
+        return;
+    }
+    // 256-bit stores where the destination is 32-byte aligned (rowval and nzval separately: their
+    // bases differ): a lane writes its own run, so every store instruction costs one request per lane
+    {
+        Ti *rv = rowval + o0;
+        auto row_at = [&](int e) { return (Ti)(f.key[e * 32] >> HB) + base; };
+        constexpr int V = 32 / (int)sizeof(Ti);
+        int e = 0;
+        for (; e < j && (reinterpret_cast<uintptr_t>(rv + e) & 31u); ++e)
+            rv[e] = row_at(e);
+        for (; e + V <= j; e += V)
+        {
+            if (sizeof(Ti) == 8)
+                st_v4_u64(rv + e, (u64)row_at(e), (u64)row_at(e + 1), (u64)row_at(e + 2), (u64)row_at(e + 3));
+            else
+            {
+                const u64 w0 = (u64)(u32)row_at(e) | ((u64)(u32)row_at(e + 1) << 32);
+                const u64 w1 = (u64)(u32)row_at(e + 2) | ((u64)(u32)row_at(e + 3) << 32);
+                const u64 w2 = (u64)(u32)row_at(e + 4) | ((u64)(u32)row_at(e + 5) << 32);
+                const u64 w3 = (u64)(u32)row_at(e + 6) | ((u64)(u32)row_at(e + 7) << 32);
+                st_v4_u64(rv + e, w0, w1, w2, w3);
+            }
+        }
+        for (; e < j; ++e)
+            rv[e] = row_at(e);
+    }
+    {
+        double *nv = nzval + o0;
+        auto val_at = [&](int e) { return (u64)__double_as_longlong(f.acc[(f.key[e * 32] & (H - 1)) * 32]); };
+        int e = 0;
+        for (; e < j && (reinterpret_cast<uintptr_t>(nv + e) & 31u); ++e)
+            nv[e] = __longlong_as_double((long long)val_at(e));
+        for (; e + 4 <= j; e += 4)
+            st_v4_u64(nv + e, val_at(e), val_at(e + 1), val_at(e + 2), val_at(e + 3));
+        for (; e < j; ++e)
+            nv[e] = __longlong_as_double((long long)val_at(e));
+    }
+}
+
+// ------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------
+namespace {
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+const int g_runs_hbits = env_int("XSB_RUNS_HBITS", 0); // 4|5|6|15: fixes the fold's table shape (tuning)
+
+struct RwLayout
+{
+    size_t off_colpairs, off_status, off_fstatus, off_pstart, off_bucket, clear_bytes, bytes;
+};
+RwLayout rw_layout(u64 npairs, i64 ncols)
+{
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const u64 stiles = ((u64)ncols + 1 + SC_TILE - 1) / SC_TILE;
+    const u64 fblocks = ((u64)ncols + RF_WARPS * 32 - 1) / (RF_WARPS * 32);
+    RwLayout l{};
+    size_t o = 0;
+    // cleared by one memset: pairs per column, look-back words + tickets of the scan and of the fold
+    l.off_colpairs = o;
+    o = up(o + sizeof(u32) * ((size_t)ncols + 1));
+    l.off_status = o;
+    o = up(o + sizeof(u64) * (stiles + 2));
+    l.off_fstatus = o;
+    o = up(o + sizeof(u64) * (fblocks + 2));
+    l.clear_bytes = o;
+    l.off_pstart = o;
+    o = up(o + sizeof(u32) * ((size_t)ncols + 2));
+    l.off_bucket = o;
+    o = up(o + sizeof(u64) * ((size_t)npairs + 1));
+    l.bytes = o;
+    return l;
+}
+} // namespace
+
+RunIndexLayout run_index_layout(u64 cap_records)
+{
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    RunIndexLayout l{};
+    l.cap_pairs = (u32)std::min<u64>(cap_records / 8 * 3 + 4096, 0xfffffff0ull); // 7-point FD streams: ~0.27 per record
+    l.cap_chunks = (u32)std::min<u64>(cap_records / 128 + 4096, 0xfffffff0ull);
+    size_t o = 0;
+    l.off_counters = o;
+    o = up(o + 256);
+    l.off_chunkinfo = o;
+    o = up(o + sizeof(uint2) * ((size_t)l.cap_chunks + 1));
+    l.off_chunkstart = o;
+    o = up(o + sizeof(u32) * ((size_t)l.cap_chunks + 1));
+    l.off_pcol = o;
+    o = up(o + sizeof(u32) * ((size_t)l.cap_pairs + 1));
+    l.off_pinfo = o;
+    o = up(o + sizeof(u32) * ((size_t)l.cap_pairs + 1));
+    l.bytes = o;
+    return l;
+}
+
+RunTarget run_target(void *workspace, u64 cap_records, const KeyLayout &L)
+{
+    const RunIndexLayout l = run_index_layout(cap_records);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    RunTarget rt{};
+    rt.counters = reinterpret_cast<u32 *>(ws + l.off_counters);
+    rt.chunkinfo = reinterpret_cast<uint2 *>(ws + l.off_chunkinfo);
+    rt.chunkstart = reinterpret_cast<u32 *>(ws + l.off_chunkstart);
+    rt.pcol = reinterpret_cast<u32 *>(ws + l.off_pcol);
+    rt.pinfo = reinterpret_cast<u32 *>(ws + l.off_pinfo);
+    rt.cap = l.cap_pairs;
+    rt.colshift = L.low + L.rowbits;
+    rt.gmask = (1u << (L.colbits + L.ownerbits)) - 1u;
+    return rt;
+}
+
+// records below 2^32 (positions are 32-bit), thread-table keys hold (row << 6 | index), the grouping key
+// (column + owner bits) must stay below CH_EMPTY
+bool runs_supported(const KeyLayout &L, u64 nrec, i64 ncols)
+{
+    return L.rowbits <= 26 && L.low <= 32 && L.tidbits == 0 && L.colbits + L.ownerbits <= 31 &&
+           nrec < (1ull << 32) - 2048ull && (u64)ncols < (1ull << 31);
+}
+
+u32 chunk_sort_chunks(u64 count) { return (u32)((count + CH_RECORDS - 1) / CH_RECORDS); }
+
+void chunk_sort(cudaStream_t stream, Rec *buf, u64 r0, u64 r1, const RunTarget &rt, u32 chunk0, LaunchCounter &lc)
+{
+    if (r1 <= r0)
+        return;
+    static FuncAttrOnce once;
+    const int smem = (int)(sizeof(ChunkSpaceT<CS_HB>) * CS_WARPS);
+    once.set(chunk_sort_kernel, smem);
+    const u32 nchunks = chunk_sort_chunks(r1 - r0);
+    chunk_sort_kernel<<<(nchunks + CS_WARPS - 1) / CS_WARPS, CS_WARPS * 32, smem, stream>>>(buf, r0, r1, chunk0, nchunks, rt);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+size_t runs_workspace_bytes(u64 npairs, i64 ncols) { return rw_layout(npairs, ncols).bytes; }
+
+void runs_bucket(cudaStream_t stream, const RunTarget &rt, u32 nchunks, u32 npairs, i64 ncols, const KeyLayout &L,
+                 RunRegions reg, void *workspace, LaunchCounter &lc)
+{
+    const RwLayout l = rw_layout(npairs, ncols);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    u32 *colpairs = reinterpret_cast<u32 *>(ws + l.off_colpairs);
+    u64 *status = reinterpret_cast<u64 *>(ws + l.off_status);
+    u32 *pstart = reinterpret_cast<u32 *>(ws + l.off_pstart);
+    u64 *bucket = reinterpret_cast<u64 *>(ws + l.off_bucket);
+    const u32 me = L.ownerbits ? (u32)L.self : 0u;
+    XSB_CUDA(cudaMemsetAsync(ws, 0, l.clear_bytes, stream));
+    run_totals_kernel<<<kNumSM * 8, 256, 0, stream>>>(rt.counters, rt.cap, rt.pcol, L.colbits, me, colpairs);
+    const unsigned stiles = (unsigned)(((u64)ncols + 1 + SC_TILE - 1) / SC_TILE);
+    runpair_scan_kernel<<<stiles, SC_THREADS, 0, stream>>>(colpairs, ncols, pstart, status,
+                                                           reinterpret_cast<u32 *>(status + stiles + 1));
+    run_bucket_kernel<<<(nchunks + 7) / 8, 256, 0, stream>>>(rt.chunkinfo, rt.chunkstart, nchunks, rt.pcol, rt.pinfo,
+                                                             L.colbits, me, reg, pstart, colpairs, bucket);
+    lc.add(3);
+    XSB_CUDA(cudaGetLastError());
+}
+
+namespace {
+template <int HBITS, typename Ti>
+void launch_runfold_t(cudaStream_t stream, unsigned blocks, const Rec *buf, int low, int rowbits, u32 maxlen,
+                      const u32 *pstart, u64 *bucket, const CscView &old, i64 ncols, i64 base, void *rowval, double *nzval,
+                      void *colptr, u64 *status, u32 *ticket, u64 *d_nnz, u32 *d_redo, u32 *maxd)
+{
+    constexpr size_t smem = RF_WARPS * RfShape<HBITS>::kBytesPerWarp;
+    static FuncAttrOnce once;
+    once.set(runfold_kernel<HBITS, Ti>, (int)smem, true);
+    const bool has_old = old.nnz > 0;
+    runfold_kernel<HBITS, Ti><<<blocks, RF_WARPS * 32, smem, stream>>>(
+        buf, low, rowbits, maxlen, pstart, bucket, has_old ? (const Ti *)old.colptr : nullptr, (const Ti *)old.rowval,
+        old.nzval, ncols, (Ti)base, (Ti *)rowval, nzval, (Ti *)colptr, status, ticket, d_nnz, d_redo, maxd);
+}
+} // namespace
+
+int runs_fold_levels() { return 4; }
+
+// level 0..3 = table shapes 4, 15, 5, 6.  *d_redo afterwards: bit 0: a column did not fit the table (bit 2 as well:
+// not even the largest one); bit 1: a column is too long / met by too many chunks for one thread.
+void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncols, int idx64, int base, const CscView &old,
+               void *workspace, u32 npairs, int level, u32 maxlen, void *rowval_out, double *nzval_out, void *colptr_out,
+               u64 *d_nnz, u32 *d_redo, u32 *d_maxd, bool first_try, LaunchCounter &lc)
+{
+    const RwLayout l = rw_layout(npairs, ncols);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    u32 *pstart = reinterpret_cast<u32 *>(ws + l.off_pstart);
+    u64 *bucket = reinterpret_cast<u64 *>(ws + l.off_bucket);
+    u64 *status = reinterpret_cast<u64 *>(ws + l.off_fstatus);
+    const unsigned blocks = (unsigned)(((u64)ncols + RF_WARPS * 32 - 1) / (RF_WARPS * 32));
+    u32 *ticket = reinterpret_cast<u32 *>(status + blocks + 1);
+    if (!first_try) // look-back words + ticket were cleared with the bucket workspace the first time
+        XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * ((size_t)blocks + 2), stream));
+    XSB_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(u32), stream));
+    XSB_CUDA(cudaMemsetAsync(d_maxd, 0, sizeof(u32), stream));
+    if (g_runs_hbits == 4)
+        level = 0;
+    else if (g_runs_hbits == 15)
+        level = 1;
+    else if (g_runs_hbits == 5)
+        level = 2;
+    else if (g_runs_hbits == 6)
+        level = 3;
+#define XSB_RUNFOLD(HB, TI)                                                                                             \
+    launch_runfold_t<HB, TI>(stream, blocks, buf, L.low, L.rowbits, maxlen, pstart, bucket, old, ncols, base, rowval_out, \
+                             nzval_out, colptr_out, status, ticket, d_nnz, d_redo, d_maxd)
+    if (idx64)
+    {
+        if (level == 0)
+            XSB_RUNFOLD(4, int64_t);
+        else if (level == 1)
+            XSB_RUNFOLD(15, int64_t);
+        else if (level == 2)
+            XSB_RUNFOLD(5, int64_t);
+        else
+            XSB_RUNFOLD(6, int64_t);
+    }
+    else
+    {
+        if (level == 0)
+            XSB_RUNFOLD(4, int32_t);
+        else if (level == 1)
+            XSB_RUNFOLD(15, int32_t);
+        else if (level == 2)
+            XSB_RUNFOLD(5, int32_t);
+        else
+            XSB_RUNFOLD(6, int32_t);
+    }
+#undef XSB_RUNFOLD
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// table shape for columns with at most `maxd` distinct rows
+int runs_level_for(u32 maxd) { return maxd <= 12 ? 0 : (maxd <= 16 ? 1 : (maxd <= 24 ? 2 : 3)); }
+
+} // namespace xsb

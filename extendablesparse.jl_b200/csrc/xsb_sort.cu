@@ -360,13 +360,8 @@ Rec *radix_sort_records(cudaStream_t stream, Rec *a, Rec *b, u64 n, const SortPl
     if (nosort && (colcnt == nullptr || n == 0))
         return a;
     const OnesweepVariant &var = kVariants[g_variant];
-    static bool attr_set[kNumVariants] = {};
-    if (!attr_set[g_variant])
-    {
-        XSB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(var.fn),
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var.tile * sizeof(Rec))));
-        attr_set[g_variant] = true;
-    }
+    static FuncAttrOnce once[kNumVariants];
+    once[g_variant].set(reinterpret_cast<const void *>(var.fn), (int)(var.tile * sizeof(Rec)));
     const u64 portion = sort_portion(var.tile);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     u64 *ghist = reinterpret_cast<u64 *>(ws);
@@ -459,13 +454,8 @@ void partition_records(cudaStream_t stream, const Rec *in, Rec *out, u64 n, int 
     histogram_scan_kernel<<<1, kRadix, 0, stream>>>(ghist, 1);
     lc.add();
     const OnesweepVariant &var = kVariants[g_variant];
-    static bool attr_set[kNumVariants] = {};
-    if (!attr_set[g_variant])
-    {
-        XSB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(var.fn),
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var.tile * sizeof(Rec))));
-        attr_set[g_variant] = true;
-    }
+    static FuncAttrOnce once[kNumVariants];
+    once[g_variant].set(reinterpret_cast<const void *>(var.fn), (int)(var.tile * sizeof(Rec)));
     const u64 portion = sort_portion(var.tile);
     u64 *gnext0 = ghist + kMaxPasses * kRadix;
     u64 *gnext1 = gnext0 + kRadix;

@@ -153,6 +153,47 @@ void slots_to_records(cudaStream_t stream, const i64 *slot, i64 count, Rec *out,
     XSB_CUDA(cudaGetLastError());
 }
 
+// staged records whose (row, column) is not an entry of the CSC (MT wrapper: setindex! of a new entry is an error)
+template <typename Ti>
+__global__ void __launch_bounds__(256)
+count_missing_kernel(const Rec *__restrict__ recs, i64 count, KeyLayout L, const Ti *__restrict__ colptr,
+                     const Ti *__restrict__ rowval, Ti base, u64 *__restrict__ d_missing)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const u64 key = recs[k].key;
+        const i64 j = (i64)L.col(key), i = (i64)L.row(key);
+        i64 lo = (i64)colptr[j] - base, hi = (i64)colptr[j + 1] - base;
+        while (lo < hi)
+        {
+            const i64 mid = (lo + hi) >> 1;
+            if ((i64)rowval[mid] - base < i)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        const i64 end = (i64)colptr[j + 1] - base;
+        if (!(lo < end && (i64)rowval[lo] - base == i))
+            atomicAdd(reinterpret_cast<unsigned long long *>(d_missing), 1ull);
+    }
+}
+
+void count_missing_records(cudaStream_t stream, const Rec *recs, i64 count, const KeyLayout &L, const CscView &csc,
+                           int idx64, int base, u64 *d_missing, LaunchCounter &lc)
+{
+    if (count <= 0)
+        return;
+    if (idx64)
+        count_missing_kernel<int64_t><<<grid_for(count, 256), 256, 0, stream>>>(
+            recs, count, L, (const int64_t *)csc.colptr, (const int64_t *)csc.rowval, (int64_t)base, d_missing);
+    else
+        count_missing_kernel<int32_t><<<grid_for(count, 256), 256, 0, stream>>>(
+            recs, count, L, (const int32_t *)csc.colptr, (const int32_t *)csc.rowval, (int32_t)base, d_missing);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
 // sorted (slot,index) records -> perm[] and segstart[0..nnz]
 __global__ void __launch_bounds__(256)
 frozen_map_kernel(const Rec *__restrict__ sorted, i64 count, i64 nnz, u32 *__restrict__ perm,

@@ -100,7 +100,7 @@ def test_cuda_matches_hashed_golden(name):
         h.emit_blockrd(*rec["dims"], seed=rec["seed"], flavour=fl)
     assert h.pending == rec["records"]
     nnz, _ = h.flush(xsb.DETERMINISTIC)
-    assert nnz == rec["nnz"] and h.flush_stats()["column_path"] == 3
+    assert nnz == rec["nnz"] and h.flush_stats()["column_path"] == 4
     assert _digest(*h.fetch_csc_numpy()) == rec["csc"]
     hb = h.pointblock(4)
     assert hb.nnz == rec["nnz_blocks"]

@@ -85,7 +85,7 @@ def test_two_flush_implementations_agree_bitwise(xsb, torch, case):
     h, n_ins, nnz = assemble(xsb, n, emit)
     st = h.flush_stats()
     assert (n_ins, nnz) == (n_ins_ref, nnz_ref)
-    assert st["column_path"] == 3  # the product path of the bench: grouping by column + thread-per-column fold
+    assert st["column_path"] == 4  # the product path of the bench: grouped chunks + thread-per-column merge
     cp, rv, nz = device_csc(torch, h)
     h.close()
     check_structure(torch, cp, rv, n, nnz)
@@ -125,6 +125,7 @@ def test_newton_loop_fd200_values_only(xsb, torch):
 
     def staged(seed):
         g = xsb.Handle(n, n)
+        g.set_precount(False)  # staged in stream order: this IS the user's (I, J, V) stream
         g.emit_fdrand(nx, nx, nx, seed=seed)
         cnt = g.pending
         dI = torch.empty(cnt, dtype=torch.int64, device="cuda")

@@ -316,6 +316,18 @@ def test_csc_roundtrip(xsb, seed):
     assert np.array_equal(cp3, cp) and np.array_equal(rv3, rv) and np.array_equal(nz3, nz)
 
 
+def assert_same_entry_streams(got, ref):
+    """Grouping at insertion reorders a chunk by column but must keep, for every (i, j), its insertions in
+    stream order: stable-sort both streams by (j, i) and compare."""
+    gI, gJ, gV = got
+    I, J, V = ref
+    assert len(gV) == len(V)
+    kg = np.lexsort((gI, gJ))  # stable
+    kr = np.lexsort((I, J))
+    assert np.array_equal(gI[kg], I[kr]) and np.array_equal(gJ[kg], J[kr])
+    assert np.array_equal(bits(gV[kg]), bits(V[kr]))
+
+
 # ---------------------------------------------------------------- generated streams
 @pytest.mark.parametrize("dims", [(100, 100, 1), (100, 1, 1), (10, 10, 1), (5, 5, 5), (2, 2, 2), (3, 1, 1), (1, 1, 1),
                                   (2, 1, 1), (1, 4, 1), (1, 1, 3), (17, 33, 9), (40, 40, 40)])
@@ -324,16 +336,21 @@ def test_emit_fdrand_stream_and_matrix(xsb, oracle, dims, ones):
     """cfg 1 (fdrand 2D 100x100 via updateindex! + flush!, test_fdrand.jl) and friends."""
     nx, ny, nz_ = dims
     N = nx * ny * nz_
-    h = xsb.Handle(N, N)
-    h.emit_fdrand(nx, ny, nz_, seed=20240717, ones=ones, flavour=xsb.UPDATE)
     I, J, V = oracle.fdrand_stream(nx, ny, nz_, seed=20240717, ones=ones)
-    gI, gJ, gV, gF = h.debug_fetch_staged()
-    assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
-    assert np.all(gF == xsb.UPDATE)
     A = oracle.OracleExt(N, N)
     A.insert_batch(I, J, V, oracle.UPDATE)
-    h.flush()
-    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    for grouped in (False, True):  # stream order as staged / chunks grouped by column while they are staged
+        h = xsb.Handle(N, N)
+        h.set_precount(grouped)
+        h.emit_fdrand(nx, ny, nz_, seed=20240717, ones=ones, flavour=xsb.UPDATE)
+        gI, gJ, gV, gF = h.debug_fetch_staged()
+        if not grouped:
+            assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
+        assert_same_entry_streams((gI, gJ, gV), (I, J, V))
+        assert np.all(gF == xsb.UPDATE)
+        h.flush()
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        h.close()
 
 
 def test_fdrand_ones_analytic(xsb):
@@ -357,15 +374,20 @@ def test_fdrand_ones_analytic(xsb):
 def test_emit_p1fem(xsb, oracle, dims):
     """cfg 2 at oracle-sized meshes: testassemble! stream (femtools.jl:45-72), rawupdateindex!."""
     N = dims[0] * dims[1] * dims[2]
-    h = xsb.Handle(N, N)
-    h.emit_p1fem(*dims, flavour=xsb.RAW)
     I, J, V = oracle.fem_stream(*dims)
-    gI, gJ, gV, gF = h.debug_fetch_staged()
-    assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
     A = oracle.OracleExt(N, N)
     A.insert_batch(I, J, V, oracle.RAW)
-    h.flush()
-    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    for grouped in (False, True):
+        h = xsb.Handle(N, N)
+        h.set_precount(grouped)
+        h.emit_p1fem(*dims, flavour=xsb.RAW)
+        gI, gJ, gV, gF = h.debug_fetch_staged()
+        if not grouped:
+            assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
+        assert_same_entry_streams((gI, gJ, gV), (I, J, V))
+        h.flush()
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        h.close()
 
 
 @pytest.mark.parametrize("dims", [(2, 2, 2, 4), (5, 4, 3, 4), (6, 6, 6, 2), (3, 1, 1, 3)])
@@ -374,6 +396,7 @@ def test_emit_blockrd_with_dirichlet(xsb, oracle, dims):
     nx, ny, nz_, ns = dims
     N = nx * ny * nz_ * ns
     h = xsb.Handle(N, N)
+    h.set_precount(False)  # keep the staged records in stream order for the comparison below
     h.emit_blockrd(nx, ny, nz_, ns, seed=7, flavour=xsb.UPDATE)
     I, J, V = oracle.blockrd_stream(nx, ny, nz_, ns, seed=7)
     gI, gJ, gV, _ = h.debug_fetch_staged()
@@ -784,7 +807,7 @@ def test_hash_fold_groups_of_columns(xsb, oracle):
                     h.insert_batch(I[idx], J[idx], V[idx] * (rnd + 1), fl)
             A.flush()
             h.flush()
-            assert h.flush_stats()["column_path"] in ((2,) if grouping == xsb.capi.GROUPING_OFF else (2, 3))
+            assert h.flush_stats()["column_path"] in ((2,) if grouping == xsb.capi.GROUPING_OFF else (2, 3, 4))
             assert_csc_equal(h.fetch_csc_numpy(), A.csc())
 
 
@@ -806,7 +829,7 @@ def test_grouping_by_column_fem_and_fallback(xsb, oracle):
         h.insert_batch(I, J, V, xsb.RAW)
         h.flush()
         st = h.flush_stats()
-        assert st["column_path"] == (3 if grouping == xsb.capi.GROUPING_AUTO else 2)
+        assert st["column_path"] == (4 if grouping == xsb.capi.GROUPING_AUTO else 2)
         if grouping == xsb.capi.GROUPING_AUTO:
             assert 0 < st["group_pairs"] < len(V) // 4
         got[grouping] = h.fetch_csc_numpy()
@@ -855,7 +878,7 @@ def test_grouping_fdrand_large(xsb, oracle):
     h = xsb.Handle(N, N)
     h.emit_fdrand(nx, nx, nx, seed=3)
     h.flush()
-    assert h.flush_stats()["column_path"] == 3
+    assert h.flush_stats()["column_path"] == 4
     I, J, V = oracle.fdrand_stream(nx, nx, nx, seed=3)
     A = oracle.OracleExt(N, N)
     A.insert_batch(I, J, V, oracle.UPDATE)
@@ -952,7 +975,7 @@ def test_precount_equals_flush_time_count(xsb, oracle, producer):
             h.insert_triplets(triplets(xsb, I, J, V), xsb.RAW)
         h.flush()
         st = h.flush_stats()
-        assert st["column_path"] == 3
+        assert st["column_path"] == 4
         if on:
             assert st["precounted"] > 0.99
         else:
@@ -981,11 +1004,8 @@ def test_precount_ragged_batches_and_rejections(xsb, oracle):
             h.insert_batch(I[a:b], J[a:b], V[a:b], xsb.RAW)
         h.flush()
         st = h.flush_stats()
-        assert st["column_path"] == 3, name
-        if name == "ragged_first":
-            assert st["precounted"] == 0.0
-        else:
-            assert 0.0 < st["precounted"] <= 1.0, name
+        assert st["column_path"] == 4, name
+        assert st["precounted"] > 0.99, name  # a batch of any length is grouped while it is packed
         assert_csc_equal(h.fetch_csc_numpy(), ref)
         h.close()
     # rejected batch after counted chunks
@@ -1013,10 +1033,10 @@ def test_precount_ragged_batches_and_rejections(xsb, oracle):
         h.insert_batch(I[a:b], J[a:b], V[a:b], xsb.RAW)
     h.flush()
     assert_csc_equal(h.fetch_csc_numpy(), ref)
-    # second assembly into the now non-empty matrix: old entries shift the chunk grid, nothing is pre-counted
+    # second assembly into the now non-empty matrix: grouped at insertion as well, merged with the resident columns
     h.insert_batch(I, J, V, xsb.RAW)
     h.flush()
-    assert h.flush_stats()["precounted"] == 0.0
+    assert h.flush_stats()["precounted"] > 0.99 and h.flush_stats()["column_path"] == 4
     A = oracle.OracleExt(n, n)
     A.insert_batch(I, J, V, oracle.RAW)
     A.flush()
@@ -1077,7 +1097,7 @@ def test_column_met_by_many_chunks_uses_pair_sort(xsb, oracle):
     h.emit_p1fem(n1, n1, n1, flavour=xsb.RAW)
     h.flush()
     st = h.flush_stats()
-    assert st["column_path"] == 3 and st["sort_passes"] == 0
+    assert st["column_path"] == 4 and st["sort_passes"] == 0
     h.close()
 
 
@@ -1092,7 +1112,7 @@ def test_fold_table_shape_follows_previous_flush(xsb, oracle):
         h.reset()
         h.insert_batch(I, J, V, xsb.RAW)
         h.flush()
-        assert h.flush_stats()["column_path"] == 3
+        assert h.flush_stats()["column_path"] == 4
         assert_csc_equal(h.fetch_csc_numpy(), ref)
     # 22 distinct rows in every column
     rng = np.random.default_rng(5)
