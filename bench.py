@@ -96,61 +96,86 @@ def flush_bytes(n_ins, nnz_old, nnz_new, ncols):
     return 16 * n_ins + 16 * nnz_old + 8 * (ncols + 1) + 16 * nnz_new + 8 * (ncols + 1)
 
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the
-# same workload (profiles/r1e_ncu_full_fem128.csv, FEM 128^3); other workloads / kernels: null
-NCU_TRAFFIC_FEM128 = {"group_scatter_kernel": 4.0631e9 + 3.8998e9, "colthread_direct_kernel": 4.1566e9 + 0.4968e9,
-                      "group_count_kernel": 0.9834e9 + 0.2440e9}
+def values_only_bytes(n_ins, nnz):
+    """B_vo = 8 N_ins (values) + 4 N_ins (int32 entry -> nzval map) + 8 nnz (nzval written)."""
+    return 12 * n_ins + 8 * nnz
 
 
-def roofline(st, ms, ncols, peak, peak_src, traffic):
-    """Roofline of the DOMINANT kernel of the flush (largest device time per step, CUDA events on the
-    library's stream around that kernel) + the whole-flush fraction on SURVEY.md 8(d)'s bytes.
-    Algorithmic bytes per launch: records are 16 B, CSC entries 16 B."""
-    rec = st["n_inserted"] + st["nnz_old"]
-    nnz = st["nnz_new"]
+FLUSH_KERNELS = ("runfold_kernel", "run_bucket_kernel", "run_totals_kernel", "runpair_scan_kernel", "chunk_sort_kernel")
+
+
+def ncu_traffic(workload_tag, kernels=FLUSH_KERNELS):
+    """dram__bytes_read.sum + dram__bytes_write.sum per flush, summed over the flush's kernels, from the committed
+    `ncu --set full` capture of one step of this workload (profiles/r2_ncu_full_<tag>.csv, written by
+    tools/ncu_extract.py).  None if no capture of this workload is committed."""
+    import csv
+
+    p = os.path.join(ROOT, "profiles", f"r2_ncu_full_{workload_tag}.csv")
+    if not os.path.exists(p):
+        return None, None
+    rows = list(csv.reader(open(p)))
+    hdr = rows[0]
+    try:
+        kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None, None
+    units = rows[1] if len(rows) > 1 else []
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_kernel = {}
+    for r in rows[2:]:
+        k = next((x for x in kernels if x in r[kn]), None)
+        if k is None or k in per_kernel:  # one launch of every kernel = one flush
+            continue
+        try:
+            per_kernel[k] = float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
+        except (ValueError, IndexError):
+            pass
+    if not per_kernel:
+        return None, None
+    return sum(per_kernel.values()), per_kernel
+
+
+def roofline(st, ms, ms_emit, ncols, peak, peak_src, tag):
+    """roofline.frac is SURVEY.md 8(d)'s fraction: the flush's ALGORITHMIC bytes (triplets + old CSC read + new
+    CSC written) over the device time of the whole flush! (CUDA events on the library's stream around xsb_flush),
+    against the measured HBM copy peak.  Per-kernel detail beside it, with each kernel's own algorithmic bytes."""
+    n_ins, nnz_old, nnz = st["n_inserted"], st["nnz_old"], st["nnz_new"]
     pairs = st["group_pairs"]
     path = st["column_path"]
-    cands = {}
-    if path == 3:
-        # counting at insertion: a share `pre` of the records is counted from the 4-byte column ids their producer
-        # left (or was counted by the producer itself); a pair costs 16 (pair record) + 4 (column) + 2 (count) bytes
-        pre = float(st.get("precounted", 0.0))
-        cands["group_count_kernel (+ pair_totals: column ids / records in, (column, chunk) pairs out)"] = (
-            ms["ms_group_count"], (16 - 12 * pre) * rec + 22 * pairs, 1)
-        cands["group_scatter_kernel (stable scatter of every record to its column)"] = (
-            ms["ms_group_scatter"], 32 * rec + 8 * pairs, 1)
-        if st["sort_passes"]:
-            cands["onesweep_kernel on the (column, chunk) pairs (+ pair offsets)"] = (
-                ms["ms_pair_sort"], 32 * pairs * st["sort_passes"] + 24 * pairs, st["sort_passes"])
-        else:
-            cands["pair buckets (colpair scans + pair_bucket_kernel + pair_offsets_kernel)"] = (
-                ms["ms_pair_sort"], 12 * ncols + 26 * pairs, 1)
+    b_flush = flush_bytes(n_ins, nnz_old, nnz, ncols)
+    t_flush = ms["ms_total"]
+    achieved = b_flush / (t_flush / 1e3) / 1e9
+    det = {}
+    if path == 4:
+        det["runfold_kernel (thread-per-column merge: staged runs + resident column -> new column)"] = (
+            ms["ms_fold"], 16 * n_ins + 16 * nnz_old + 16 * nnz + 16 * ncols + 8 * pairs)
+        det["run buckets (run_totals + runpair_scan + run_bucket kernels)"] = (ms["ms_pair_sort"], 8 * ncols + 24 * pairs)
+        if ms.get("ms_group_count", 0.0) > 0.005:
+            det["chunk_sort_kernel (records the producers left in stream order, grouped in place)"] = (
+                ms["ms_group_count"], 32 * n_ins * (1.0 - float(st.get("precounted", 0.0))))
     else:
-        cands["onesweep_kernel (one radix pass over 16-B records)"] = (ms["ms_sort"], 32 * rec * st["sort_passes"],
-                                                                      st["sort_passes"])
-    if path >= 2:
-        cands["colthread_direct_kernel (thread-per-column fold writing rowval / nzval / colptr)" if st.get("direct_fold")
-              else "colthread_kernel (+ leftover colfold_kernel: per-column fold, read records, park entries)"] = (
-            ms["ms_fold"], 16 * rec + 16 * nnz, 1)
-        cands["compact_entries_kernel (parked entries -> rowval / nzval)"] = (ms["ms_compact"], 32 * nnz, 1)
-    else:
-        cands["reduce_emit_kernel"] = (ms["ms_reduce"], 16 * rec + 16 * nnz, 1)
-    name = max(cands, key=lambda k: cands[k][0])
-    t, byts, launches = cands[name]
-    achieved = byts / (t / 1e3) / 1e9
-    if traffic is None and st["n_inserted"] == 245805960 and st["nnz_old"] == 0:
-        traffic = next((v for k, v in NCU_TRAFFIC_FEM128.items() if name.startswith(k)), None)
-    b_flush = flush_bytes(st["n_inserted"], st["nnz_old"], nnz, ncols)
-    flush_gbs = b_flush / (ms["ms_total"] / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-            "bytes_per_launch": byts / launches, "ms_per_launch": t / launches, "launches_per_step": launches,
-            "kernels": {k: {"ms": v[0], "GB/s": v[1] / (v[0] / 1e3) / 1e9 if v[0] > 0 else None,
-                            "frac": v[1] / (v[0] / 1e3) / 1e9 / peak if v[0] > 0 else None} for k, v in cands.items()},
-            "flush": {"algorithmic_bytes": b_flush, "ms": ms["ms_total"], "achieved": flush_gbs,
-                      "frac": flush_gbs / peak, "column_path": path},
-            "stage_ms_per_step": dict(sorted(ms.items()))}
+        rec = n_ins + nnz_old
+        det["count / histogram"] = (ms["ms_group_count"] + ms.get("ms_histogram", 0.0), 16 * rec)
+        det["scatter / sort passes"] = (ms["ms_sort"], 32 * rec * max(1, st["sort_passes"]))
+        det["fold"] = (ms["ms_reduce"], 16 * rec + 16 * nnz)
+    traffic, per_kernel = ncu_traffic(tag) if (path == 4 and tag) else (None, None)
+    name = max(det, key=lambda k: det[k][0])
+    out = {"bound": "hbm", "kernel": "xsb_flush (all kernels of one flush!; dominant: " + name.split(" ")[0] + ")",
+           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+           "peak_source": peak_src, "bytes_per_launch": b_flush, "ms_per_launch": t_flush, "launches_per_step": 1,
+           "definition": "SURVEY.md 8(d): (16 N_ins + 16 nnz_old + 16 nnz_new + 16 (n+1)) / device time of flush! / peak",
+           "traffic_source": f"profiles/r2_ncu_full_{tag}.csv (dram read + write of the flush's kernels)" if traffic else None,
+           "traffic_per_kernel": per_kernel,
+           "kernels": {k: {"ms": v[0], "GB/s": v[1] / (v[0] / 1e3) / 1e9 if v[0] > 0 else None,
+                           "frac": v[1] / (v[0] / 1e3) / 1e9 / peak if v[0] > 0 else None} for k, v in det.items()},
+           "column_path": path, "stage_ms_per_step": dict(sorted(ms.items()))}
+    if ms_emit is not None:
+        span = ms_emit + t_flush
+        out["span_emission_to_csc"] = {"ms": span, "achieved": b_flush / (span / 1e3) / 1e9,
+                                       "frac": b_flush / (span / 1e3) / 1e9 / peak, "ms_emit": ms_emit,
+                                       "note": "8(d)'s time span with the insertion kernels inside: grouping by column "
+                                               "happens in the kernels that stage the records"}
+    return out
 
 
 # ---------------------------------------------------------------------------------- CPU legs
@@ -163,6 +188,7 @@ def cpu_reference_leg(mesh, steps, warmup):
     I, J, V = ora.fem_stream(mesh, mesh, mesh)
     n = mesh ** 3
     times = []
+    digest = None
     for it in range(warmup + steps):
         A = ora.OracleExt(n, n)
         t0 = time.perf_counter()
@@ -171,8 +197,26 @@ def cpu_reference_leg(mesh, steps, warmup):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        if it == warmup + steps - 1:
+            digest = csc_digest(*A.csc())
         del A
+    ORACLE_DIGEST[mesh] = digest
     return len(V), times
+
+
+ORACLE_DIGEST = {}  # mesh -> SHA-256 of the oracle's (colptr, rowval, nzval) of the FEM assembly
+
+
+def csc_digest(colptr, rowval, nzval):
+    """SHA-256 over the raw bytes of colptr | rowval | nzval (Int64 / Int64 / Float64, 1-based)."""
+    import hashlib
+
+    import numpy as np
+
+    hsh = hashlib.sha256()
+    for a, dt in ((colptr, np.int64), (rowval, np.int64), (nzval, np.float64)):
+        hsh.update(np.ascontiguousarray(a, dt).tobytes())
+    return hsh.hexdigest()
 
 
 def host_threads():
@@ -255,6 +299,34 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------- GPU arm
+def timed_steps(h, step, steps):
+    h.synchronize()
+    h.timer_start()
+    for _ in range(steps):
+        step()
+    return h.timer_stop() / steps
+
+
+def profiled_steps(h, emit, mode, steps):
+    """Stage times of `steps` assemblies with CUDA events around every stage of the flush (xsb_set_profiling) and
+    around the emission.  Not the headline timing: profiling adds a stream synchronisation per flush."""
+    h.set_profiling(True)
+    stage, ms_emit = {}, 0.0
+    st = None
+    for _ in range(steps):
+        h.reset()
+        h.timer_start()
+        emit()
+        ms_emit += h.timer_stop()
+        h.flush(mode)
+        st = h.flush_stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage[k] = stage.get(k, 0.0) + v
+    h.set_profiling(False)
+    return st, {k: v / steps for k, v in stage.items()}, ms_emit / steps
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -280,12 +352,14 @@ def run_ours(args):
     n = mesh ** 3
     mode = xsb.DETERMINISTIC if args.mode == "deterministic" else xsb.FAST
     h = xsb.Handle(n, n, device=local)
-    h.set_profiling(True)
     n_ins = xsb.capi.stream_count_p1fem(mesh, mesh, mesh)
+
+    def emit():
+        h.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
 
     def step():
         h.reset()
-        h.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
+        emit()
         return h.flush(mode)
 
     for _ in range(args.warmup):
@@ -293,35 +367,41 @@ def run_ours(args):
     h.synchronize()
     torch.cuda.synchronize()
     launches0 = h.kernel_launches
-    stage = {}
     with ClockSampler(local) as clk:
-        h.timer_start()
-        for _ in range(args.steps):
-            nnz, _ = step()
-            st = h.flush_stats()
-            for k, v in st.items():
-                if k.startswith("ms_"):
-                    stage[k] = stage.get(k, 0.0) + v
-        ms = h.timer_stop()
+        ms_step = timed_steps(h, step, args.steps)
         launches_timed = h.kernel_launches - launches0
         # keep the sampler alive for at least a few samples on very short runs
-        t_end = time.time() + max(0.0, 0.5 - ms / 1e3)
+        t_end = time.time() + max(0.0, 0.5 - ms_step * args.steps / 1e3)
         while time.time() < t_end:
             step()
-    st = h.flush_stats()
-    ms_step = ms / args.steps
+    nnz = h.nnz
     value = n_ins / (ms_step / 1e3)
     peak, peak_src = peaks()
+    st, stage_ms, ms_emit = profiled_steps(h, emit, mode, min(args.steps, 3))
+    roof = roofline(st, stage_ms, ms_emit, n, peak, peak_src, f"fem{mesh}")
+    gpu_digest = csc_digest(*h.fetch_csc_numpy())
 
-    roof = roofline(st, {k: v / args.steps for k, v in stage.items()}, n, peak, peak_src, args.traffic)
+    extra = {}
+    if not args.no_legs:
+        extra["splice"] = measure_splice(args, xsb, h, mesh, n, n_ins, mode, peak)
+        extra["fast"] = measure_fast(args, xsb, h, mesh, n_ins, st, peak)
+    h.close()
+    if not args.no_legs:
+        extra["values_only"] = measure_values_only(args, xsb, torch, peak, local)
+        extra["cfg5"] = measure_fd(args, xsb, peak, local, args.fd_n)
 
     # ---- end-to-end through the C ABI with HOST buffers
-    e2e = measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch)
+    e2e = measure_e2e(args, xsb, local, mesh, n, mode, np, torch)
 
-    # ---- CPU baseline (rank 0, N=1): the oracle port on the same workload
+    # ---- CPU baseline (rank 0, N=1): the oracle port on the same workload; its CSC pins the GPU's
     cpu = None
+    parity = None
     if not args.no_cpu:
         _, _, cpu = cpu_baseline_both(args.cpu_mesh, 1, 0)
+        if args.cpu_mesh == mesh and ORACLE_DIGEST.get(mesh):
+            parity = ORACLE_DIGEST[mesh] == gpu_digest
+            if not parity:
+                raise SystemExit(f"PARITY FAILURE: SHA-256 of the GPU CSC {gpu_digest} != oracle's {ORACLE_DIGEST[mesh]}")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -330,29 +410,169 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed),
         "clocks": clk.summary(), "nnz": int(nnz), "n_inserted": int(n_ins),
+        "parity_checked": parity, "csc_sha256": gpu_digest,
+        "parity_note": "SHA-256 of colptr|rowval|nzval of the GPU product path == the CPU oracle's on the same 128^3 "
+                       "stream (bit-exact CSC)" if parity else None,
     }
+    line.update(extra)
     print(json.dumps(line))
+
+
+def measure_splice(args, xsb, h, mesh, n, n_ins, mode, peak):
+    """flush! on top of a RESIDENT matrix (the 3-way merge of sparsematrixlnk.jl:328-378): (i) the same assembly
+    once more (every call a CSC hit, extendable.jl:164-166; pattern unchanged), (ii) ~1 % new entries spliced in
+    (one off-stencil coupling per column for 1 % of the columns... here: a sparse random stream)."""
+    import numpy as np
+
+    out = {}
+    # (i) identical second assembly onto the resident CSC
+    h.reset()
+    h.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
+    h.flush(mode)
+    nnz0 = h.nnz
+
+    def again():
+        h.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
+        return h.flush(mode)
+
+    again()
+    reps = max(1, min(args.steps, 3))
+    ms = timed_steps(h, again, reps)
+    nnz1, changed = h.nnz, None
+    h.set_profiling(True)
+    _, changed = again()
+    st = h.flush_stats()
+    h.set_profiling(False)
+    b = flush_bytes(n_ins, nnz0, nnz1, n)
+    out["all_hits"] = {"ms_per_step": ms, "ms_flush": st["ms_total"], "pattern_changed": bool(changed),
+                       "nnz": int(nnz1), "entries_per_s": n_ins / (ms / 1e3),
+                       "flush_frac_of_hbm_peak": b / (st["ms_total"] / 1e3) / 1e9 / peak,
+                       "workload": "the same FEM assembly onto the resident CSC: emit + flush!, nothing new"}
+    # (ii) 1 % new entries: random positions, 1 % of nnz of them
+    rng = np.random.default_rng(5)
+    k = nnz0 // 100
+    I = rng.integers(1, n + 1, k)
+    J = rng.integers(1, n + 1, k)
+    V = rng.standard_normal(k)
+    h.insert_batch(I, J, V, xsb.UPDATE)
+    h.set_profiling(True)
+    h.timer_start()
+    nnz2, ch2 = h.flush(mode)
+    ms2 = h.timer_stop()
+    st2 = h.flush_stats()
+    h.set_profiling(False)
+    out["one_percent_new"] = {"ms_flush": st2["ms_total"], "ms_wall": ms2, "inserted": int(k), "nnz_old": int(nnz1),
+                              "nnz_new": int(nnz2), "pattern_changed": bool(ch2), "column_path": st2["column_path"],
+                              "old_entry_traffic_bytes_per_entry": 32,
+                              "flush_frac_of_hbm_peak": flush_bytes(k, nnz1, nnz2, n) / (st2["ms_total"] / 1e3) / 1e9 / peak,
+                              "workload": "1 % new random entries spliced into the resident 128^3 FEM matrix"}
+    return out
+
+
+def measure_fast(args, xsb, h, mesh, n_ins, st_det, peak):
+    """XSB_FAST (<= 1e-14 relative, pattern bit-exact): same workload, same span."""
+    def step():
+        h.reset()
+        h.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
+        return h.flush(xsb.FAST)
+
+    step()
+    ms = timed_steps(h, step, max(1, min(args.steps, 3)))
+    return {"ms_per_step": ms, "entries_per_s": n_ins / (ms / 1e3), "mode": "XSB_FAST",
+            "workload": "P1-FEM 128^3: emit + flush! in fast mode"}
+
+
+def measure_values_only(args, xsb, torch, peak, local):
+    """BASELINE.json configs[2]: fdrand 200^3 built once, then 10 values-only re-assemblies into the frozen pattern
+    (Newton loop; values device-resident).  Roofline: B_vo = 12 N_ins + 8 nnz."""
+    import ctypes as C
+
+    nx = args.vo_n
+    n = nx ** 3
+    g = xsb.Handle(n, n, device=local)
+    g.set_precount(False)  # staged in stream order: the user's (I, J, V) stream
+    g.emit_fdrand(nx, nx, nx, seed=100)
+    cnt = g.pending
+    dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dJ = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dV = torch.empty(cnt, dtype=torch.float64, device="cuda")
+    got = C.c_int64(0)
+    c = xsb.capi
+    c.check(c.lib().xsb_debug_fetch_staged(g._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt, C.byref(got)), g._h)
+    g.set_precount(True)
+    g.synchronize()
+    nnz, _ = g.flush()
+    g.timer_start()
+    g.freeze_pattern(dI, dJ, count=cnt)
+    ms_freeze = g.timer_stop()
+    out = {"n_inserted": int(cnt), "nnz": int(nnz), "ms_freeze_once": ms_freeze,
+           "workload": f"fdrand {nx}^3 (BASELINE.json configs[2]): 10 values-only re-assemblies into the frozen pattern, "
+                       f"nonzeros .= 0 + xsb_reassemble_values, values resident in HBM"}
+    b_vo = values_only_bytes(cnt, nnz)
+    for name, m in (("deterministic", xsb.DETERMINISTIC), ("fast", xsb.FAST)):
+        def re():
+            g.zero_values()
+            g.reassemble_values(dV, m, count=cnt)
+
+        re()
+        ms = timed_steps(g, re, 10)
+        out[name] = {"ms_per_reassembly": ms, "entries_per_s": cnt / (ms / 1e3),
+                     "roofline": {"bound": "hbm", "algorithmic_bytes": b_vo, "achieved": b_vo / (ms / 1e3) / 1e9,
+                                  "peak": peak, "unit": "GB/s", "frac": b_vo / (ms / 1e3) / 1e9 / peak}}
+    g.close()
+    return out
+
+
+def measure_fd(args, xsb, peak, local, n1):
+    """BASELINE.json configs[4] on ONE GPU (the base of the strong-scaling curve): fdrand n1^3 via updateindex!."""
+    N = n1 ** 3
+    h = xsb.Handle(N, N, device=local)
+    n_ins = xsb.capi.stream_count_fdrand(n1, n1, n1)
+
+    def emit():
+        h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE)
+
+    def step():
+        h.reset()
+        emit()
+        return h.flush()
+
+    step()
+    step()
+    ms = timed_steps(h, step, max(1, min(args.steps, 3)))
+    st, stage_ms, ms_emit = profiled_steps(h, emit, xsb.DETERMINISTIC, 1)
+    b = flush_bytes(n_ins, 0, st["nnz_new"], N)
+    out = {"ms_per_step": ms, "entries_per_s": n_ins / (ms / 1e3), "n_gpus": 1, "n_inserted": int(n_ins),
+           "nnz": int(st["nnz_new"]), "ms_emit": ms_emit, "ms_flush": stage_ms["ms_total"],
+           "flush_frac_of_hbm_peak": b / (stage_ms["ms_total"] / 1e3) / 1e9 / peak, "column_path": st["column_path"],
+           "workload": f"fdrand 3-D {n1}^3 (BASELINE.json configs[4]) on one GPU: the base of the strong-scaling curve "
+                       f"(bench.py --gpus N prints the same key for N ranks)"}
     h.close()
+    return out
 
 
-def measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch):
-    """Same metric through the public C ABI with HOST buffers.  Every step copies the insertion stream
-    host->device from pinned memory, runs insert + flush!, and reads the CSC (colptr, rowval, nzval)
-    back to pinned host memory.  Headline: the stream as 16-byte triplets (xsb_insert_triplets, the
-    buffer the glue's updateindex! appends to: 16 B per insertion over PCIe); beside it the same
-    stream as three Int64/Int64/Float64 arrays (xsb_insert_batch: 24 B per insertion)."""
+def measure_e2e(args, xsb, local, mesh, n, mode, np, torch):
+    """Same metric through the drop-in boundary with HOST buffers, the call sequence of the Julia glue's
+    Base.sum(exts, csc) (julia/ExtendableSparseB200.jl; mirrored by extendablesparse.jl_b200/dropin.py):
+        xsb_set_csc (old CSC host -> device) -> xsb_insert_triplets (the partition's 16-byte triplets, pinned host
+        memory -> device) -> xsb_flush -> xsb_fetch_csc (new CSC device -> pinned host)
+    on ONE cached handle.  Headline: the build from an empty matrix.  Beside it: a SPLICE step (resident CSC of
+    the first assembly uploaded through xsb_set_csc, 1 % new entries) and the stream as three Int64/Int64/Float64
+    arrays (xsb_insert_batch: 24 B per insertion)."""
+    import ctypes as C
+
+    from xsparse_b200 import dropin
+
     emesh = args.e2e_mesh
     en = emesh ** 3
-    g = xsb.Handle(en, en, device=h.device)
+    c = xsb.capi
+    g = xsb.Handle(en, en, device=local)
     g.set_precount(False)  # the host arrays hold the stream in call order, as user code would produce it
     g.emit_p1fem(emesh, emesh, emesh, flavour=xsb.RAW)
     cnt = g.pending
     dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
     dJ = torch.empty(cnt, dtype=torch.int64, device="cuda")
     dV = torch.empty(cnt, dtype=torch.float64, device="cuda")
-    c = xsb.capi
-    import ctypes as C
-
     got = C.c_int64(0)
     c.check(c.lib().xsb_debug_fetch_staged(g._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt,
                                            C.byref(got)), g._h)
@@ -372,46 +592,76 @@ def measure_e2e(args, xsb, h, mesh, n, n_ins, mode, np, torch):
     del dI, dJ, dV, dT
     g.reset()
     g.set_precount(True)
-    # result buffers (pinned), sized after one dry run
-    g.insert_triplets(hT, xsb.RAW, 0, cnt)
-    nnz, _ = g.flush(mode)
-    ocp = torch.empty(en + 1, dtype=torch.int64, pin_memory=True)
-    orv = torch.empty(nnz, dtype=torch.int64, pin_memory=True)
-    onz = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
 
-    def step_triplets():
-        g.reset()
-        g.insert_triplets(hT, xsb.RAW, 0, cnt)
-        g.flush(mode)
-        g.fetch_csc(ocp, orv, onz)
+    # the extension object of the glue, its triplet buffer living in pinned host memory
+    ext = dropin.SparseMatrixB200(en, en, buffer=hT.numpy().view(c.TRIPLET_DTYPE).reshape(-1))
+    ext.fill = cnt
+    ext.runs = [(0, xsb.RAW)]
+    empty = (np.ones(en + 1, np.int64), np.empty(0, np.int64), np.empty(0, np.float64))
+    (cp0, rv0, nz0), _ = dropin.sum_extensions([ext], en, en, empty, mode, handle=g)
+    nnz = len(rv0)
+    ocp = torch.empty(en + 1, dtype=torch.int64, pin_memory=True)
+    orv = torch.empty(nnz + nnz // 50 + 16, dtype=torch.int64, pin_memory=True)
+    onz = torch.empty(nnz + nnz // 50 + 16, dtype=torch.float64, pin_memory=True)
+    outb = (ocp.numpy(), orv.numpy(), onz.numpy())
+
+    def step_build():
+        return dropin.sum_extensions([ext], en, en, empty, mode, out=outb, handle=g)
+
+    def timed(step, reps):
+        step()
+        g.synchronize()
+        g.timer_start()
+        for _ in range(reps):
+            step()
+        return g.timer_stop() / reps
+
+    reps = max(1, min(args.steps, 3))
+    ms = timed(step_build, reps)
+    check_a = (int(orv[:1000].sum()), float(onz[:1000].sum()))
 
     def step_ijv():
-        g.reset()
+        g.set_csc(*[torch.from_numpy(a) for a in empty[:1]] + [None, None])
         g.insert_batch(hI, hJ, hV, xsb.RAW, count=cnt)
         g.flush(mode)
         g.fetch_csc(ocp, orv, onz)
 
-    def timed(step):
-        for _ in range(max(1, min(args.warmup, 2))):
-            step()
-        g.synchronize()
-        steps = max(1, min(args.steps, 3))
-        g.timer_start()
-        for _ in range(steps):
-            step()
-        return g.timer_stop() / steps
-
-    ms_ijv = timed(step_ijv)
-    check_a = (int(orv[:1000].sum()), float(onz[:1000].sum()))
-    ms = timed(step_triplets)
+    ms_ijv = timed(step_ijv, reps)
     assert check_a == (int(orv[:1000].sum()), float(onz[:1000].sum())), "triplet and (I,J,V) assemblies differ"
+
+    # splice: the matrix of the first assembly is the wrapper's host CSC; 1 % new entries arrive
+    pcp = torch.empty(en + 1, dtype=torch.int64, pin_memory=True).copy_(torch.from_numpy(cp0))
+    prv = torch.empty(nnz, dtype=torch.int64, pin_memory=True).copy_(torch.from_numpy(rv0))
+    pnz = torch.empty(nnz, dtype=torch.float64, pin_memory=True).copy_(torch.from_numpy(nz0))
+    rng = np.random.default_rng(11)
+    k = max(1, nnz // 100)
+    hS = torch.empty((k, 2), dtype=torch.int64, pin_memory=True)
+    sv = hS.numpy().view(c.TRIPLET_DTYPE).reshape(-1)
+    sv["row"], sv["col"], sv["val"] = rng.integers(1, en + 1, k), rng.integers(1, en + 1, k), rng.standard_normal(k)
+    sext = dropin.SparseMatrixB200(en, en, buffer=sv)
+    sext.fill = k
+    sext.runs = [(0, xsb.UPDATE)]
+    resident = (pcp.numpy(), prv.numpy(), pnz.numpy())
+
+    def step_splice():
+        return dropin.sum_extensions([sext], en, en, resident, mode, out=outb, handle=g)
+
+    (_, srv, _), _ = step_splice()
+    ms_splice = timed(step_splice, reps)
+    nnz_s = len(srv)
     g.close()
     d2h = 8 * (en + 1) + 16 * int(nnz)
-    return {"value": cnt / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 16 * cnt,
+    return {"value": cnt / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 16 * cnt + 8 * (en + 1),
             "d2h_bytes_per_step": d2h, "ms_per_step": ms,
-            "workload": f"P1-FEM {emesh}^3-node mesh, {cnt} insertions from a pinned host array of 16-byte triplets "
-                        f"(xsb_insert_triplets), CSC read back to host",
-            "ijv": {"value": cnt / (ms_ijv / 1e3), "unit": UNIT, "h2d_bytes_per_step": 24 * cnt,
+            "workload": f"P1-FEM {emesh}^3-node mesh through the drop-in sequence of Base.sum(exts, csc): xsb_set_csc (empty "
+                        f"CSC) + {cnt} insertions from a pinned host buffer of 16-byte triplets (xsb_insert_triplets) + "
+                        f"xsb_flush + xsb_fetch_csc into pinned host arrays",
+            "splice": {"ms_per_step": ms_splice, "inserted": int(k), "nnz_old": int(nnz), "nnz_new": int(nnz_s),
+                       "h2d_bytes_per_step": 16 * k + 16 * int(nnz) + 8 * (en + 1),
+                       "d2h_bytes_per_step": 8 * (en + 1) + 16 * int(nnz_s),
+                       "workload": "flush! with a resident matrix: old CSC uploaded through xsb_set_csc, 1 % new entries "
+                                   "(xsb_insert_triplets), merged CSC read back"},
+            "ijv": {"value": cnt / (ms_ijv / 1e3), "unit": UNIT, "h2d_bytes_per_step": 24 * cnt + 8 * (en + 1),
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_ijv,
                     "workload": "same stream as three pinned host arrays Int64 I, Int64 J, Float64 V "
                                 "(xsb_insert_batch)"}}
@@ -429,12 +679,12 @@ def main():
     ap.add_argument("--ref-mesh", type=int, default=128, help="mesh of one --impl reference step (128 = the GPU arm's workload)")
     ap.add_argument("--mode", default="deterministic", choices=["deterministic", "fast"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the splice / fast / values_only / cfg5 legs")
+    ap.add_argument("--vo-n", type=int, default=200, help="grid of the values_only leg (200 = configs[2])")
     ap.add_argument("--workload", default="fem", choices=["fem", "fd400"],
                     help="N>1 only: fem = weak scaling of configs[1] (default, the bench line); fd400 = configs[4], "
                          "fdrand 400^3 sharded by node slab over the ranks (strong scaling, no e2e leg)")
     ap.add_argument("--fd-n", type=int, default=400, help="grid points per direction of --workload fd400")
-    ap.add_argument("--traffic", type=float, default=None,
-                    help="ncu dram bytes per launch of the dominant kernel (default: the committed capture's figure)")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(0, args.warmup)

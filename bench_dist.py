@@ -87,7 +87,7 @@ def run(args, xsb, rank, world, local):
     ms_step = ms / args.steps
     value = world * n_ins_rank / (ms_step / 1e3)
     peak, peak_src = bench.peaks()
-    roof = bench.roofline(st, {k: v / args.steps for k, v in stage.items()}, h.n, peak, peak_src, args.traffic)
+    roof = bench.roofline(st, {k: v / args.steps for k, v in stage.items()}, None, h.n, peak, peak_src, None)
     roof["kernel"] += " [rank 0]"
 
     e2e = measure_e2e(args, xsb, xd, rank, world, local, mode)

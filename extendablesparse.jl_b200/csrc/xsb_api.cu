@@ -353,7 +353,7 @@ struct xsb_matrix
             return;
         }
         i64 cap = std::max<i64>(need, st.cap + st.cap / 2);
-        cap = std::max<i64>(cap, 1024);
+        cap = (std::max<i64>(cap, 1024) + 1) & ~(i64)1; // even: the merge reads whole 32-byte sectors (two records)
         Rec *nb = static_cast<Rec *>(dalloc(sizeof(Rec) * (size_t)cap));
         if (st.buf && st.count > 0)
             XSB_CUDA(cudaMemcpyAsync(nb + st.front, st.buf + st.front, sizeof(Rec) * (size_t)st.count,
@@ -632,7 +632,7 @@ bool runs_flush(xsb_matrix *h, int32_t mode, i64 n_ins, StageTimer *tp, int64_t 
     {
         runs_fold(s, buf, h->L, h->n, h->idx64, h->base, h->view(), ws, npairs, level, maxlen, new_rowval, new_nzval,
                   new_colptr, h->d_scal + 0, reinterpret_cast<u32 *>(h->d_scal + 6), reinterpret_cast<u32 *>(h->d_scal + 7),
-                  first, h->lc);
+                  first, h->has_assign, h->lc);
         XSB_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->d_scal + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
         nnz_new = (i64)read_scalar(h, 0);
         const u32 redo = (u32)h->h_scal[6];
@@ -2088,6 +2088,17 @@ int32_t xsb_emit_blockrd(xsb_matrix *h, int32_t tid, int64_t nx, int64_t ny, int
         REQUIRE(h->m == N && h->n_global == N, XSB_ESIZE, "Matrix size mismatch");
         const i64 count = blockrd_count(nx, ny, nz, ns);
         Rec *dst = begin_emit(h, tid, flavour, count);
+        RunTarget rt;
+        u32 chunk0 = 0, pos0 = 0;
+        const u32 want = emit_blockrd_chunks(nx, ny, nz, ns);
+        if (want > 0 && runs_begin(h, tid, count, want, &rt, &chunk0, &pos0))
+        {
+            const u32 chunks = emit_blockrd_grouped(h->stream, nx, ny, nz, ns, seed, h->Ls, (u32)tid, (u32)flavour, dst,
+                                                    h->lc, h->stage_flags(tid), rt, chunk0, pos0);
+            end_emit(h, tid, flavour, count);
+            runs_end(h, count, chunks);
+            return XSB_OK;
+        }
         emit_blockrd(h->stream, nx, ny, nz, ns, seed, h->Ls, (u32)tid, (u32)flavour, dst, h->lc, h->stage_flags(tid));
         end_emit(h, tid, flavour, count);
         return XSB_OK;

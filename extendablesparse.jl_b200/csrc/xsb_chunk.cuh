@@ -53,19 +53,25 @@ template <int HB> __device__ __forceinline__ void chunk_space_init(ChunkSpaceT<H
 }
 
 // One batch of 32 consecutive records: g = grouping key (column, owner bits on top) of this lane's
-// record, valid = the lane holds a record.  Returns (slot << 16 | rank of the record among the chunk's
-// records of its column so far).  d = distinct columns of the chunk so far.
-template <int HB>
+// record, valid = the lane holds a record (FULL: every lane does).  Returns (slot << 16 | rank of the record
+// among the chunk's records of its column so far).  d = distinct columns of the chunk so far.
+template <int HB, bool FULL = false>
 __device__ __forceinline__ u32 chunk_count_batch(ChunkSpaceT<HB> &ws, u32 g, bool valid, u32 lt, u32 &d)
 {
     constexpr u32 full = 0xffffffffu;
     constexpr int H = ChunkSpaceT<HB>::H;
-    const u32 vm = __ballot_sync(full, valid);
-    u32 peers = 0;
-    if (valid)
-        peers = __match_any_sync(vm, g);
+    u32 peers;
+    if (FULL)
+        peers = __match_any_sync(full, g);
+    else
+    {
+        const u32 vm = __ballot_sync(full, valid);
+        peers = 0;
+        if (valid)
+            peers = __match_any_sync(vm, g);
+    }
     // the FIRST lane that holds a column speaks for it: the table sees one request per distinct column
-    const bool leader = valid && (peers & lt) == 0u;
+    const bool leader = (FULL || valid) && (peers & lt) == 0u;
     u32 slot = ch_hash(g, HB), old = 0;
     bool fresh = false;
     if (leader)
@@ -92,10 +98,13 @@ __device__ __forceinline__ u32 chunk_count_batch(ChunkSpaceT<HB> &ws, u32 g, boo
         ws.cnt[slot] = (unsigned short)(old + (u32)__popc(peers));
     }
     const u32 rb = __ballot_sync(full, fresh);
-    if (fresh)
-        ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
-    d += __popc(rb);
-    const int ldr = peers ? __ffs(peers) - 1 : 0;
+    if (rb)
+    { // warp-uniform: most batches bring no new column
+        if (fresh)
+            ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
+        d += __popc(rb);
+    }
+    const int ldr = (FULL || peers) ? __ffs(peers) - 1 : 0;
     const u32 packed = __shfl_sync(full, (slot << 16) | old, ldr);
     __syncwarp();
     return packed + (u32)__popc(peers & lt);

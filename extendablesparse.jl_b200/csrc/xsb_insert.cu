@@ -530,19 +530,43 @@ constexpr int FEM_THREADS = 128;
 constexpr int FEM_REC = 20;
 constexpr int FEM_PITCH = FEM_REC + 1;
 
-// The 20 records of tetrahedron t, in call order, to dst[0..20).  Returns 1 if one of its columns belongs to
-// another rank (slab handles).
-__device__ __forceinline__ int fem_tet_records(i64 t, i64 nxn, i64 nyn, i64 nzn, const KeyLayout &L, u32 tid, u32 flavour,
-                                               bool slab, Rec *dst)
+// Element matrix of tetrahedron t: what its 20 rawupdateindex! calls (test/femtools.jl:62-69) insert.
+struct FemTet
 {
-    int has_foreign = 0;
-    const i64 cube = t / 6;
-    const int perm = (int)(t % 6);
+    u64 ckey[4], rkey[4]; // a node is the column of 5 and the row of 5 of the element's 20 records
+    double vol;
+    double S[4][4];
+    int has_foreign; // slab handles: a column of this element belongs to another rank
+    // record q = 5 il + w of the element: w == 0: mass term on (i,i); else stiffness (i, j = node[w-1])
+    __device__ __forceinline__ u64 key(int il, int w) const { return (w == 0 ? ckey[il] : ckey[w - 1]) | rkey[il]; }
+    __device__ __forceinline__ double val(int il, int w) const { return w == 0 ? 0.1 * vol / 4.0 : vol * S[il][w - 1]; }
+};
+
+__device__ __forceinline__ void fem_tet_compute(i64 t, i64 nxn, i64 nyn, i64 nzn, const KeyLayout &L, u32 tid, u32 flavour,
+                                                bool slab, FemTet &e)
+{
+    e.has_foreign = 0;
     const i64 cxn = nxn - 1, cyn = nyn - 1;
     i64 idx[4][3];
-    idx[0][0] = cube % cxn;
-    idx[0][1] = (cube / cxn) % cyn;
-    idx[0][2] = cube / (cxn * cyn);
+    int perm;
+    if (t < 0x7fffffffll)
+    { // 32-bit index arithmetic (64-bit divisions by run-time values cost hundreds of instructions)
+        const u32 t32 = (u32)t, cube = t32 / 6u, cx = (u32)cxn, cy = (u32)cyn;
+        perm = (int)(t32 - cube * 6u);
+        const u32 row = cube / cx;
+        idx[0][0] = (i64)(cube - row * cx);
+        const u32 lay = row / cy;
+        idx[0][1] = (i64)(row - lay * cy);
+        idx[0][2] = (i64)lay;
+    }
+    else
+    {
+        const i64 cube = t / 6;
+        perm = (int)(t % 6);
+        idx[0][0] = cube % cxn;
+        idx[0][1] = (cube / cxn) % cyn;
+        idx[0][2] = cube / (cxn * cyn);
+    }
 #pragma unroll
     for (int v = 1; v < 4; ++v)
     {
@@ -601,8 +625,7 @@ __device__ __forceinline__ int fem_tet_records(i64 t, i64 nxn, i64 nyn, i64 nzn,
 #pragma unroll
     for (int d = 0; d < 3; ++d)
         gr[0][d] = -((gr[1][d] + gr[2][d]) + gr[3][d]);
-    const double vol = fabs(det) / 6.0;
-    double S[4][4];
+    e.vol = fabs(det) / 6.0;
 #pragma unroll
     for (int il = 0; il < 4; ++il)
 #pragma unroll
@@ -612,35 +635,38 @@ __device__ __forceinline__ int fem_tet_records(i64 t, i64 nxn, i64 nyn, i64 nzn,
 #pragma unroll
             for (int d = 0; d < 3; ++d)
                 sum += gr[jl][d] * gr[il][d];
-            S[il][jl] = sum;
-            S[jl][il] = sum;
+            e.S[il][jl] = sum;
+            e.S[jl][il] = sum;
         }
-    int q = 0;
-    u64 ckey[4], rkey[4]; // a node is the column of 5 and the row of 5 of the element's 20 records
 #pragma unroll
     for (int v = 0; v < 4; ++v)
     {
-        ckey[v] = L.colpart(node[v]);
-        rkey[v] = L.rowpart(node[v], tid, flavour);
-        if (slab && L.owner(ckey[v]) != (u32)L.self)
-            has_foreign = 1; // slab handles: a column of this element belongs to another rank
+        e.ckey[v] = L.colpart(node[v]);
+        e.rkey[v] = L.rowpart(node[v], tid, flavour);
+        if (slab && L.owner(e.ckey[v]) != (u32)L.self)
+            e.has_foreign = 1;
     }
+}
+
+// The 20 records of tetrahedron t, in call order, to dst[0..20).  Returns 1 if one of its columns belongs to
+// another rank (slab handles).
+__device__ __forceinline__ int fem_tet_records(i64 t, i64 nxn, i64 nyn, i64 nzn, const KeyLayout &L, u32 tid, u32 flavour,
+                                               bool slab, Rec *dst)
+{
+    FemTet e;
+    fem_tet_compute(t, nxn, nyn, nzn, L, tid, flavour, slab, e);
+    int q = 0;
 #pragma unroll
     for (int il = 0; il < 4; ++il)
-    {
-        Rec r;
-        r.key = ckey[il] | rkey[il];
-        r.val = 0.1 * vol / 4.0;
-        dst[q++] = r;
 #pragma unroll
-        for (int jl = 0; jl < 4; ++jl)
+        for (int w = 0; w < 5; ++w)
         {
-            r.key = ckey[jl] | rkey[il]; // A[i,j]: row = node[il], col = node[jl]
-            r.val = vol * S[il][jl];
+            Rec r;
+            r.key = e.key(il, w);
+            r.val = e.val(il, w);
             dst[q++] = r;
         }
-    }
-    return has_foreign;
+    return e.has_foreign;
 }
 
 // Stream order: a block's records through shared memory, coalesced 16-byte stores.
@@ -673,16 +699,18 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
 }
 
 // Grouped chunks (xsb_chunk.cuh): a warp's 32 tetrahedra = one chunk of 640 records, brought into column
-// order in the warp's own shared memory (no block-wide barrier) and stored where the flush will read them.
-constexpr int FEMG_HB = 8;
-constexpr int FEMG_NB = FEM_REC; // 32 tetrahedra x 20 records = 20 batches of 32
+// order without a block-wide barrier.  Only the KEYS go through the warp's shared memory (values and element
+// matrices stay in the registers of the lane that computed them): the warp walks the keys in call order,
+// notes every record's (column slot, rank in its column) in the key's own place, and after the scan over
+// the columns every lane stores its tetrahedron's 20 records where the flush will read them.
+constexpr int FEMG_HB = 7; // 128 table slots: 32 neighbouring tetrahedra touch a few dozen nodes
 struct FemWarpSpace
 {
-    Rec rec[32 * FEM_PITCH];
+    u64 key[32 * FEM_PITCH];
     ChunkSpaceT<FEMG_HB> tab;
 };
 
-__global__ void __launch_bounds__(FEM_THREADS)
+__global__ void __launch_bounds__(FEM_THREADS, 7)
 emit_p1fem_grouped_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 tet_begin, i64 tet_end,
                           Rec *__restrict__ out, StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
 {
@@ -697,49 +725,68 @@ emit_p1fem_grouped_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 f
     const i64 t_last = min(t_first + 32, tet_end);
     const i64 t = t_first + lane;
     chunk_space_init(sp.tab, lane);
-    int has_foreign = 0;
+    FemTet e;
+    e.has_foreign = 0;
     if (t < t_last)
-        has_foreign = fem_tet_records(t, nxn, nyn, nzn, L, tid, flavour, sf.flags != nullptr, sp.rec + lane * FEM_PITCH);
-    if (!__any_sync(full, has_foreign))
+    {
+        fem_tet_compute(t, nxn, nyn, nzn, L, tid, flavour, sf.flags != nullptr, e);
+        u64 *kd = sp.key + lane * FEM_PITCH;
+#pragma unroll
+        for (int il = 0; il < 4; ++il)
+#pragma unroll
+            for (int w = 0; w < 5; ++w)
+                kd[il * 5 + w] = e.key(il, w);
+    }
+    if (!__any_sync(full, e.has_foreign))
         sf.flags = nullptr;
     __syncwarp();
     const u32 len = (u32)(t_last - t_first) * FEM_REC;
     const i64 c0 = (t_first - tet_begin) * FEM_REC; // position of the chunk in this launch's output
     const u32 lt = lanemask_lt();
-    u32 rs[FEMG_NB];
     u32 d = 0;
     bool grouped = true;
-#pragma unroll
-    for (int b = 0; b < FEMG_NB; ++b)
+#pragma unroll 4
+    for (int b = 0; b < FEM_REC; ++b)
     {
-        rs[b] = 0;
         if ((u32)(b * 32) < len && grouped) // warp-uniform
         {
             const u32 q = b * 32 + lane;
             const u32 tt = q / FEM_REC;
-            const u64 key = q < len ? sp.rec[tt * FEM_PITCH + (q - tt * FEM_REC)].key : 0ull;
+            u64 *slot = sp.key + tt * FEM_PITCH + (q - tt * FEM_REC);
+            const u64 key = q < len ? *slot : 0ull;
             if (d > ChunkSpaceT<FEMG_HB>::DMAX - 32u)
                 grouped = false;
             else
-                rs[b] = chunk_count_batch(sp.tab, (u32)(key >> rt.colshift) & rt.gmask, q < len, lt, d);
+            {
+                const u32 g = (u32)(key >> rt.colshift) & rt.gmask;
+                const u32 rs = (u32)(b * 32 + 32) <= len ? chunk_count_batch<FEMG_HB, true>(sp.tab, g, true, lt, d)
+                                                         : chunk_count_batch<FEMG_HB, false>(sp.tab, g, q < len, lt, d);
+                if (q < len)
+                    *reinterpret_cast<u32 *>(slot) = rs; // this lane read the key: its place now holds (slot, rank)
+            }
         }
     }
     if (grouped)
         chunk_scan(sp.tab, d, lane);
-    Rec *dst = out + c0;
-#pragma unroll
-    for (int b = 0; b < FEMG_NB; ++b)
+    __syncwarp();
+    if (t < t_last)
     {
-        const u32 q = b * 32 + lane;
-        if (q < len)
-        {
-            const u32 tt = q / FEM_REC;
-            const Rec r = sp.rec[tt * FEM_PITCH + (q - tt * FEM_REC)];
-            const u32 to = grouped ? chunk_dest(sp.tab.start, rs[b]) : q;
-            st_rec(dst + to, r);
-            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
-                sf.flags[(sf.pos0 + c0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
-        }
+        Rec *dst = out + c0;
+        const u64 *kd = sp.key + lane * FEM_PITCH;
+#pragma unroll
+        for (int il = 0; il < 4; ++il)
+#pragma unroll
+            for (int w = 0; w < 5; ++w)
+            {
+                const int q = il * 5 + w;
+                const u32 to = grouped ? chunk_dest(sp.tab.start, (u32)kd[q]) : (u32)(lane * FEM_REC + q);
+                Rec r;
+                r.key = e.key(il, w);
+                r.val = e.val(il, w);
+                st_rec(dst + to, r);
+                if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                    sf.flags[(sf.pos0 + c0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
+            }
     }
     chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, grouped, lane);
 }
@@ -858,6 +905,151 @@ emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *
         r.key = L.pack(ib, ia, tid, flavour);
         st_staged(out + rec + ab, r, L, sf, out);
     }
+}
+
+// Grouped chunks (xsb_chunk.cuh): a warp emits the records of `npw` consecutive nodes (at most 512 records:
+// ns <= 6) into its own shared memory in call order, brings them into column order and stores them where the
+// flush will read them.
+constexpr int RDG_WARPS = 4;
+constexpr int RDG_HB = 8;
+constexpr int RDG_NB = CH_RECORDS / 32;
+struct RdWarpSpace
+{
+    Rec rec[CH_RECORDS];
+    ChunkSpaceT<RDG_HB> tab;
+};
+__host__ __device__ inline i64 rd_node_rec(const RdGeom &g, i64 l0)
+{ // records emitted by the nodes before l0 (l0 == number of nodes: all records)
+    const i64 ns2 = g.ns * g.ns;
+    const i64 N = g.nx * g.ny * g.nz;
+    const i64 eb = l0 >= N ? g.edges_before(1, 1, g.nz + 1)
+                           : g.edges_before(l0 % g.nx + 1, (l0 / g.nx) % g.ny + 1, l0 / (g.nx * g.ny) + 1);
+    return eb * 4 * ns2 + (l0 >= N ? N : l0) * ns2;
+}
+static int rd_nodes_per_warp(i64 ns)
+{
+    const i64 ns2 = ns * ns;
+    return (int)std::max<i64>(1, std::min<i64>(32 / ns2, CH_RECORDS / (13 * ns2)));
+}
+
+__global__ void __launch_bounds__(RDG_WARPS * 32)
+emit_blockrd_grouped_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, int npw, Rec *__restrict__ out,
+                            StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RdWarpSpace &sp = reinterpret_cast<RdWarpSpace *>(smem_raw)[warp];
+    const i64 N = g.nx * g.ny * g.nz;
+    const u32 wchunk = blockIdx.x * RDG_WARPS + warp;
+    const i64 l_first = (i64)wchunk * npw;
+    if (l_first >= N)
+        return;
+    const i64 l_last = min(l_first + npw, N);
+    const i64 ns2 = g.ns * g.ns;
+    const i64 w_rec0 = rd_node_rec(g, l_first);
+    const u32 len = (u32)(rd_node_rec(g, l_last) - w_rec0);
+    chunk_space_init(sp.tab, lane);
+    const i64 nitems = (l_last - l_first) * ns2;
+    for (i64 it = lane; it < nitems; it += 32)
+    {
+        const i64 l0 = l_first + it / ns2;
+        const i64 ab = it % ns2;
+        const u64 a = (u64)(ab / g.ns), b = (u64)(ab % g.ns);
+        const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+        const i64 eb = g.edges_before(i, j, k);
+        i64 rec = eb * 4 * ns2 + l0 * ns2 - w_rec0; // records of this chunk before this node
+        u64 call = (u64)(eb * ns2 + l0 * ns2);      // rand() calls before this node
+        const i64 step[3] = {1, g.nx, g.nx * g.ny};
+        const bool has[3] = {i < g.nx, j < g.ny, k < g.nz};
+        const u64 ia = (u64)(g.ns * l0) + a, ib = (u64)(g.ns * l0) + b;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            if (!has[d])
+                continue;
+            const double v = philox_uniform(seed, call + (u64)ab);
+            const u64 l2 = (u64)(l0 + step[d]);
+            const u64 ja = (u64)g.ns * l2 + a, jb = (u64)g.ns * l2 + b;
+            Rec *dst = sp.rec + rec + ab * 4;
+            Rec r;
+            r.val = -v;
+            r.key = L.pack(jb, ia, tid, flavour); // (-v, i_a, j_b)
+            dst[0] = r;
+            r.key = L.pack(ib, ja, tid, flavour); // (-v, j_a, i_b)
+            dst[1] = r;
+            r.val = v;
+            r.key = L.pack(ib, ia, tid, flavour); // ( v, i_a, i_b)
+            dst[2] = r;
+            r.key = L.pack(jb, ja, tid, flavour); // ( v, j_a, j_b)
+            dst[3] = r;
+            rec += 4 * ns2;
+            call += (u64)ns2;
+        }
+        Rec r;
+        r.val = philox_uniform(seed, call + (u64)ab);
+        r.key = L.pack(ib, ia, tid, flavour);
+        sp.rec[rec + ab] = r;
+    }
+    __syncwarp();
+    const u32 lt = lanemask_lt();
+    u32 rs[RDG_NB];
+    u32 d = 0;
+    bool grouped = true;
+#pragma unroll
+    for (int bb = 0; bb < RDG_NB; ++bb)
+    {
+        rs[bb] = 0;
+        if ((u32)(bb * 32) < len && grouped) // warp-uniform
+        {
+            const u32 q = bb * 32 + lane;
+            const u64 key = q < len ? sp.rec[q].key : 0ull;
+            if (d > ChunkSpaceT<RDG_HB>::DMAX - 32u)
+                grouped = false;
+            else
+                rs[bb] = chunk_count_batch(sp.tab, (u32)(key >> rt.colshift) & rt.gmask, q < len, lt, d);
+        }
+    }
+    if (grouped)
+        chunk_scan(sp.tab, d, lane);
+    Rec *dst = out + w_rec0;
+#pragma unroll
+    for (int bb = 0; bb < RDG_NB; ++bb)
+    {
+        const u32 q = bb * 32 + lane;
+        if (q < len)
+        {
+            const Rec r = sp.rec[q];
+            const u32 to = grouped ? chunk_dest(sp.tab.start, rs[bb]) : q;
+            st_rec(dst + to, r);
+            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                sf.flags[(sf.pos0 + w_rec0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
+        }
+    }
+    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)w_rec0, d, grouped, lane);
+}
+
+// 0: this species count is emitted in stream order only (a node's records exceed a chunk)
+u32 emit_blockrd_chunks(i64 nx, i64 ny, i64 nz, int ns)
+{
+    if (13 * (i64)ns * ns > CH_RECORDS)
+        return 0;
+    const i64 npw = rd_nodes_per_warp(ns);
+    return (u32)((nx * ny * nz + npw - 1) / npw);
+}
+
+u32 emit_blockrd_grouped(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid, u32 flavour,
+                         Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0, u32 pos0)
+{
+    RdGeom g{nx, ny, nz, (i64)ns};
+    const u32 chunks = emit_blockrd_chunks(nx, ny, nz, ns);
+    static FuncAttrOnce once;
+    const int smem = (int)(sizeof(RdWarpSpace) * RDG_WARPS);
+    once.set(emit_blockrd_grouped_kernel, smem, true);
+    emit_blockrd_grouped_kernel<<<(chunks + RDG_WARPS - 1) / RDG_WARPS, RDG_WARPS * 32, smem, stream>>>(
+        g, seed, L, tid, flavour, rd_nodes_per_warp(ns), out, sf, rt, chunk0, pos0);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+    return chunks;
 }
 
 void emit_blockrd(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid,

@@ -243,7 +243,7 @@ void runs_bucket(cudaStream_t stream, const RunTarget &rt, u32 nchunks, u32 npai
 int runs_level_for(u32 maxd);
 void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncols, int idx64, int base, const CscView &old,
                void *workspace, u32 npairs, int level, u32 maxlen, void *rowval_out, double *nzval_out, void *colptr_out,
-               u64 *d_nnz, u32 *d_redo, u32 *d_maxd, bool first_try, LaunchCounter &lc);
+               u64 *d_nnz, u32 *d_redo, u32 *d_maxd, bool first_try, bool has_assign, LaunchCounter &lc);
 
 // ---- xsb_route.cu
 size_t route_workspace_bytes(u64 n, int nranks);
@@ -280,6 +280,9 @@ u32 emit_fdrand_chunks(i64 l_begin, i64 l_end);
 u32 emit_fdrand_grouped(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour,
                         i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0,
                         u32 pos0);
+u32 emit_blockrd_chunks(i64 nx, i64 ny, i64 nz, int ns); // 0: not available for this species count
+u32 emit_blockrd_grouped(cudaStream_t stream, i64 nx, i64 ny, i64 nz, int ns, u64 seed, KeyLayout L, u32 tid, u32 flavour,
+                         Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0, u32 pos0);
 u32 emit_p1fem_chunks(i64 nxn, i64 nyn, i64 cz_begin, i64 cz_end);
 u32 emit_p1fem_grouped(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, i64 cz_begin,
                        i64 cz_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0, u32 pos0);

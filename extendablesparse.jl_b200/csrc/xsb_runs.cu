@@ -220,7 +220,7 @@ template <int HBITS> struct RfShape
 // The fold state of one column.  A table slot holds (row << HB | accumulator index); accumulators are
 // numbered in order of first appearance.  Flavour semantics (single partition): src/matrix/sparsematrixlnk.jl
 // :178-253 behind the CSC-hit router src/matrix/extendable.jl:159-218.
-template <int HBITS> struct ThreadFold
+template <int HBITS, bool ASSIGN> struct ThreadFold
 {
     static constexpr int H = RfShape<HBITS>::H;
     static constexpr int HB = RfShape<HBITS>::HB;
@@ -230,7 +230,7 @@ template <int HBITS> struct ThreadFold
     u32 *rows;   // [i * 32]
     u32 d = 0;       // accumulators in use
     u32 pending = 0; // of which not (yet) existing: only updateindex! / setindex! of a zero touched them
-    u64 exmask = 0;  // accumulator i holds an existing entry
+    u32 exmask = 0;  // accumulator i holds an existing entry (D <= 32)
     bool ovf = false;
 
     __device__ __forceinline__ void init()
@@ -248,15 +248,15 @@ template <int HBITS> struct ThreadFold
             const u32 x = kk ^ (row << HB);
             if (x < D)
             { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
-                if (fl == FL_ASSIGN)
+                if (ASSIGN && fl == FL_ASSIGN)
                 { // A[i,j] = v: overwrites; creates only if v != 0 (sparsematrixlnk.jl:184-199)
-                    const bool ex = (exmask >> x) & 1ull;
+                    const bool ex = (exmask >> x) & 1u;
                     if (ex | (v != 0.0))
                     {
                         acc[x * 32] = v;
                         if (!ex)
                         {
-                            exmask |= 1ull << x;
+                            exmask |= 1u << x;
                             --pending;
                         }
                     }
@@ -265,9 +265,9 @@ template <int HBITS> struct ThreadFold
                 acc[x * 32] = acc[x * 32] + v;
                 if (pending)
                 {
-                    if (!((exmask >> x) & 1ull) && ((fl != FL_UPDATE) | (v != 0.0)))
+                    if (!((exmask >> x) & 1u) && ((fl != FL_UPDATE) | (v != 0.0)))
                     {
-                        exmask |= 1ull << x;
+                        exmask |= 1u << x;
                         --pending;
                     }
                 }
@@ -286,9 +286,9 @@ template <int HBITS> struct ThreadFold
                 // (extendable.jl:165-166) or it is assigned; updateindex! / setindex! of a zero create
                 // nothing (:212,223,184)
                 const bool creates = (fl == FL_RAW) | (fl == FL_OLD) | (v != 0.0);
-                acc[d * 32] = (fl == FL_OLD || (fl == FL_ASSIGN && creates)) ? v : 0.0 + v;
+                acc[d * 32] = (fl == FL_OLD || (ASSIGN && fl == FL_ASSIGN && creates)) ? v : 0.0 + v;
                 if (creates)
-                    exmask |= 1ull << d;
+                    exmask |= 1u << d;
                 else
                     ++pending;
                 ++d;
@@ -304,7 +304,7 @@ template <int HBITS> struct ThreadFold
         u32 j = 0;
         for (u32 i = 0; i < d; ++i)
         {
-            if (!((exmask >> i) & 1ull))
+            if (!((exmask >> i) & 1u))
                 continue;
             const u32 kk = (rows[i * 32] << HB) | i;
             u32 q = j;
@@ -323,9 +323,7 @@ template <int HBITS> struct ThreadFold
     }
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int HBITS, typename Ti>
+template <int HBITS, typename Ti, bool ASSIGN>
 __global__ void __launch_bounds__(RF_WARPS * 32, RfShape<HBITS>::kBlocks)
 runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, const u32 *__restrict__ pstart,
                u64 *__restrict__ bucket, const Ti *__restrict__ old_colptr, const Ti *__restrict__ old_rowval,
@@ -349,7 +347,7 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
     __syncthreads();
     const u32 bid = s_bid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ThreadFold<HBITS> f;
+    ThreadFold<HBITS, ASSIGN> f;
     f.acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane;
     f.key = reinterpret_cast<u32 *>(smem_raw + (size_t)RF_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
     f.rows = reinterpret_cast<u32 *>(smem_raw + (size_t)RF_WARPS * 32 * (D * sizeof(double) + H * sizeof(u32))) +
@@ -405,46 +403,53 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
                 // ---- the resident column seeds the table (CSC hits: extendable.jl:164-166)
                 for (i64 e = os; e < oe; ++e)
                     f.apply((u32)((i64)old_rowval[e] - (i64)base), old_nzval[e], FL_OLD);
-                // ---- the runs, where the producers left them
-                u64 e = b[0];
-                for (u32 i = 0; i < np && !f.ovf; ++i)
+                // ---- the runs, where the producers left them.  Every step a lane takes the aligned 32-byte
+                // sector (two records, one LDG.256) its cursor stands in and folds the one or two records of it
+                // that belong to its run: the same instruction stream for every lane whatever the run lengths;
+                // two sectors travel ahead of the one being folded.
+                // Positions are counted in records from the 32-byte boundary at or below buf: their parity is the
+                // record's place inside its sector.
+                const uintptr_t bufa = reinterpret_cast<uintptr_t>(buf);
+                const u32 bias = (u32)(bufa >> 4) & 1u;
+                const unsigned char *base32 = reinterpret_cast<const unsigned char *>(bufa & ~(uintptr_t)31);
+                u32 ri = 0, rem = 0, left = nrec, pos = 0;
+                RecPair q0, q1, q2;
+                u32 m0, m1, m2;
+                auto gen = [&](RecPair &q, u32 &m) {
+                    if (left == 0u)
+                    {
+                        m = 0u;
+                        return;
+                    }
+                    if (rem == 0u)
+                    {
+                        const u64 e = b[ri++];
+                        pos = (u32)(e >> 11) + bias;
+                        rem = (u32)(e & 0x7ffull);
+                    }
+                    m = (pos & 1u) ? 2u : (rem > 1u ? 3u : 1u); // which records of the sector belong to the run
+                    const u32 take = (m + 1u) >> 1;
+                    q = ld_pair_stream(reinterpret_cast<const Rec *>(base32 + (size_t)(pos >> 1) * 32u));
+                    pos += take;
+                    rem -= take;
+                    left -= take;
+                };
+                gen(q0, m0);
+                gen(q1, m1);
+                gen(q2, m2);
+                while (m0 != 0u && !f.ovf)
                 {
-                    const u64 en = i + 1 < np ? b[i + 1] : 0ull;
-                    u32 cnt = (u32)(e & 0x7ffull);
-                    const u32 pos = (u32)(e >> 11);
-                    const Rec *p = buf + pos;
-                    if (i + 1 < np)
-                        prefetch_l2(buf + (u32)(en >> 11));
-                    if (pos & 1u)
-                    { // 256-bit loads need 32-byte alignment: an odd first record goes alone
-                        const Rec r = ld_rec_stream(p);
-                        f.apply((u32)(r.key >> low) & rowmask, r.val, (u32)r.key & 3u);
-                        ++p;
-                        --cnt;
-                    }
-                    const u32 npair = cnt >> 1;
-                    if (npair)
-                    {
-                        RecPair nx = ld_pair_stream(p);
-                        for (u32 q = 0; q < npair; ++q)
-                        {
-                            const RecPair cur = nx;
-                            if (q + 1 < npair)
-                                nx = ld_pair_stream(p + 2 * (q + 1));
-                            f.apply((u32)(cur.a.key >> low) & rowmask, cur.a.val, (u32)cur.a.key & 3u);
-                            if (!f.ovf)
-                                f.apply((u32)(cur.b.key >> low) & rowmask, cur.b.val, (u32)cur.b.key & 3u);
-                            if (f.ovf)
-                                break;
-                        }
-                        p += 2 * npair;
-                    }
-                    if ((cnt & 1u) && !f.ovf)
-                    {
-                        const Rec r = ld_rec_stream(p);
-                        f.apply((u32)(r.key >> low) & rowmask, r.val, (u32)r.key & 3u);
-                    }
-                    e = en;
+                    const RecPair c = q0;
+                    const u32 m = m0;
+                    q0 = q1;
+                    m0 = m1;
+                    q1 = q2;
+                    m1 = m2;
+                    gen(q2, m2);
+                    if (m & 1u)
+                        f.apply((u32)(c.a.key >> low) & rowmask, c.a.val, (u32)c.a.key & 3u);
+                    if ((m & 2u) && !f.ovf)
+                        f.apply((u32)(c.b.key >> low) & rowmask, c.b.val, (u32)c.b.key & 3u);
                 }
                 if (f.ovf)
                 { // bit 2: not even the largest table takes this column
@@ -672,16 +677,16 @@ void runs_bucket(cudaStream_t stream, const RunTarget &rt, u32 nchunks, u32 npai
 }
 
 namespace {
-template <int HBITS, typename Ti>
+template <int HBITS, typename Ti, bool ASSIGN>
 void launch_runfold_t(cudaStream_t stream, unsigned blocks, const Rec *buf, int low, int rowbits, u32 maxlen,
                       const u32 *pstart, u64 *bucket, const CscView &old, i64 ncols, i64 base, void *rowval, double *nzval,
                       void *colptr, u64 *status, u32 *ticket, u64 *d_nnz, u32 *d_redo, u32 *maxd)
 {
     constexpr size_t smem = RF_WARPS * RfShape<HBITS>::kBytesPerWarp;
     static FuncAttrOnce once;
-    once.set(runfold_kernel<HBITS, Ti>, (int)smem, true);
+    once.set(runfold_kernel<HBITS, Ti, ASSIGN>, (int)smem, true);
     const bool has_old = old.nnz > 0;
-    runfold_kernel<HBITS, Ti><<<blocks, RF_WARPS * 32, smem, stream>>>(
+    runfold_kernel<HBITS, Ti, ASSIGN><<<blocks, RF_WARPS * 32, smem, stream>>>(
         buf, low, rowbits, maxlen, pstart, bucket, has_old ? (const Ti *)old.colptr : nullptr, (const Ti *)old.rowval,
         old.nzval, ncols, (Ti)base, (Ti *)rowval, nzval, (Ti *)colptr, status, ticket, d_nnz, d_redo, maxd);
 }
@@ -693,7 +698,7 @@ int runs_fold_levels() { return 4; }
 // not even the largest one); bit 1: a column is too long / met by too many chunks for one thread.
 void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncols, int idx64, int base, const CscView &old,
                void *workspace, u32 npairs, int level, u32 maxlen, void *rowval_out, double *nzval_out, void *colptr_out,
-               u64 *d_nnz, u32 *d_redo, u32 *d_maxd, bool first_try, LaunchCounter &lc)
+               u64 *d_nnz, u32 *d_redo, u32 *d_maxd, bool first_try, bool has_assign, LaunchCounter &lc)
 {
     const RwLayout l = rw_layout(npairs, ncols);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -715,8 +720,17 @@ void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncol
     else if (g_runs_hbits == 6)
         level = 3;
 #define XSB_RUNFOLD(HB, TI)                                                                                             \
-    launch_runfold_t<HB, TI>(stream, blocks, buf, L.low, L.rowbits, maxlen, pstart, bucket, old, ncols, base, rowval_out, \
-                             nzval_out, colptr_out, status, ticket, d_nnz, d_redo, d_maxd)
+    do                                                                                                                  \
+    {                                                                                                                   \
+        if (has_assign)                                                                                                 \
+            launch_runfold_t<HB, TI, true>(stream, blocks, buf, L.low, L.rowbits, maxlen, pstart, bucket, old, ncols,   \
+                                           base, rowval_out, nzval_out, colptr_out, status, ticket, d_nnz, d_redo,     \
+                                           d_maxd);                                                                     \
+        else                                                                                                            \
+            launch_runfold_t<HB, TI, false>(stream, blocks, buf, L.low, L.rowbits, maxlen, pstart, bucket, old, ncols,  \
+                                            base, rowval_out, nzval_out, colptr_out, status, ticket, d_nnz, d_redo,    \
+                                            d_maxd);                                                                    \
+    } while (0)
     if (idx64)
     {
         if (level == 0)

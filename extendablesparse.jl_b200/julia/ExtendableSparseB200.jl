@@ -9,13 +9,16 @@
 #         GenericMTExtendableSparseMatrixCSC{SparseMatrixB200{Tv,Ti},Tv,Ti}
 #
 # NOTE: no Julia runtime exists in the build container of this repository, so this file has
-# been written against the reference sources but NOT executed.  The C ABI it binds is
-# exercised by the Python tests (tests/test_gpu_parity.py) through ctypes.
+# been written against the reference sources but NOT executed.  The call sequence it makes
+# (xsb_set_csc -> xsb_insert_triplets per partition and flavour run -> xsb_flush -> xsb_fetch_csc, ONE
+# device handle) is mirrored line by line by extendablesparse.jl_b200/dropin.py, which the GPU tests
+# (tests/test_gpu_dropin.py) and the end-to-end leg of bench.py execute through ctypes.
 #
-# Per-entry calls are appended to a per-partition host buffer of 16-byte triplets
-# (`XsbTriplet` = `xsb_triplet` of include/xsparse_b200.h: one 16-byte store per call, no ccall per
-# entry) and shipped with one `xsb_insert_triplets` when the buffer is full, the flavour changes, or
-# at `flush!`: 16 bytes per insertion cross PCIe instead of the 24 of three Int64/Int64/Float64 arrays.
+# Per-entry calls are appended to a per-partition HOST buffer of 16-byte triplets (`XsbTriplet` =
+# `xsb_triplet` of include/xsparse_b200.h: one 16-byte store per call, no ccall per entry) and stay
+# there until `flush!`: like the reference's own buffers (SparseMatrixLNK / SparseMatrixDILNKC live in
+# host memory until `flush!` merges them, extendable.jl:248-255) nothing touches the device before the
+# flush.  16 bytes per insertion cross PCIe, once.
 
 module ExtendableSparseB200
 
@@ -55,58 +58,35 @@ idxcode(::Type{Int32}) = XSB_I32
 """
     SparseMatrixB200{Tv,Ti}(m, n)
 
-Insert buffer living in B200 HBM.  Constructor signature `T_ext(m,n)` as required by
-abstractsparsematrixextension.jl:10.
+Insert buffer of one partition: the calls since the last `flush!`, in call order, as 16-byte triplets in
+host memory, plus the runs of equal flavour (update / rawupdate / assign).  Constructor signature
+`T_ext(m,n)` as required by abstractsparsematrixextension.jl:10.  No device resource is held here; tasks
+that insert with distinct `tid` touch distinct objects (test/femtools.jl:88-105), so no lock is needed.
 """
 mutable struct SparseMatrixB200{Tv, Ti <: Integer} <: AbstractSparseMatrixExtension{Tv, Ti}
     m::Ti
     n::Ti
-    handle::Ptr{Cvoid}
     T::Vector{XsbTriplet}
     fill::Int
-    flavour::Int32
-    shipped::Int            # insertions already on the device
+    runs::Vector{Tuple{Int, Int32}}   # (index of the first triplet, flavour) of every run
 
     function SparseMatrixB200{Tv, Ti}(m, n) where {Tv, Ti <: Integer}
         Tv === Float64 || error("libxsparse_b200 implements Float64 values")
         (m < 2^32 && n < 2^32) || error("triplet buffers carry 32-bit indices")
-        h = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:xsb_create, libxsb), Int32,
-                   (Int64, Int64, Int32, Int32, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
-                   m, n, XSB_F64, idxcode(Ti), 1, 1, 0, h)
-        check(Ptr{Cvoid}(C_NULL), rc)
-        x = new{Tv, Ti}(m, n, h[], Vector{XsbTriplet}(undef, CHUNK), 0, XSB_RAW, 0)
-        finalizer(x) do y
-            y.handle == C_NULL || ccall((:xsb_destroy, libxsb), Int32, (Ptr{Cvoid},), y.handle)
-            y.handle = C_NULL
-        end
-        x
+        new{Tv, Ti}(m, n, Vector{XsbTriplet}(undef, CHUNK), 0, Tuple{Int, Int32}[])
     end
 end
 
 Base.size(x::SparseMatrixB200) = (x.m, x.n)
 # upper bound of the distinct new entries, enough for `nnz(ext)>0` in flush!
 # (genericextendablesparsematrixcsc.jl:31-37)
-SparseArrays.nnz(x::SparseMatrixB200) = x.shipped + x.fill
-
-function ship!(x::SparseMatrixB200)
-    x.fill == 0 && return
-    n = x.fill
-    x.fill = 0
-    rc = ccall((:xsb_insert_triplets, libxsb), Int32,
-               (Ptr{Cvoid}, Int32, Ptr{XsbTriplet}, Int64, Int32),
-               x.handle, 0, x.T, n, x.flavour)
-    check(x.handle, rc)
-    x.shipped += n
-end
+SparseArrays.nnz(x::SparseMatrixB200) = x.fill
 
 @inline function push_entry!(x::SparseMatrixB200{Tv, Ti}, flavour::Int32, v, i, j) where {Tv, Ti}
     (1 <= i <= x.m && 1 <= j <= x.n) || throw(BoundsError(x, (i, j)))
-    if x.fill == CHUNK || (x.fill > 0 && x.flavour != flavour)
-        ship!(x)
-    end
-    x.flavour = flavour
+    x.fill == length(x.T) && resize!(x.T, 2 * length(x.T))
     k = (x.fill += 1)
+    (isempty(x.runs) || x.runs[end][2] != flavour) && push!(x.runs, (k, flavour))
     @inbounds x.T[k] = XsbTriplet(i % UInt32, j % UInt32, v)
     x
 end
@@ -125,36 +105,67 @@ function Base.getindex(x::SparseMatrixB200{Tv}, i::Integer, j::Integer) where {T
     nnz(x) == 0 ? zero(Tv) : error("flush! before reading unflushed entries of a B200 matrix")
 end
 
+# One device handle per (index type, size, partitions): created at the first flush!, reused by the following
+# ones (its staging buffers and kernels stay warm), destroyed at exit.  flush! is called from one task
+# (test/femtools.jl:109); the lock only guards the table.
+const HANDLES = Dict{Tuple{DataType, Int, Int, Int}, Ptr{Cvoid}}()
+const HANDLES_LOCK = ReentrantLock()
+function device_handle(::Type{Ti}, m, n, nparts; device = 0) where {Ti}
+    lock(HANDLES_LOCK) do
+        get!(HANDLES, (Ti, Int(m), Int(n), nparts)) do
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            rc = ccall((:xsb_create, libxsb), Int32,
+                       (Int64, Int64, Int32, Int32, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+                       m, n, XSB_F64, idxcode(Ti), 1, nparts, device, h)
+            check(Ptr{Cvoid}(C_NULL), rc)
+            h[]
+        end
+    end
+end
+function __init__()
+    atexit() do
+        lock(HANDLES_LOCK) do
+            foreach(h -> ccall((:xsb_destroy, libxsb), Int32, (Ptr{Cvoid},), h), values(HANDLES))
+            empty!(HANDLES)
+        end
+    end
+end
+
 """
     Base.sum(exts::Vector{SparseMatrixB200}, csc) -> SparseMatrixCSC
 
-The flush of the plug-in contract (abstractsparsematrixextension.jl:13): partitions are summed
-in vector order like sparsematrixdilnkc.jl:416-426.  The old CSC seeds the device matrix, all
-buffers are replayed onto it, and the merged CSC is fetched into Julia-owned arrays.
+The flush of the plug-in contract (abstractsparsematrixextension.jl:13): partitions are summed in vector
+order like sparsematrixdilnkc.jl:416-426.  ONE device handle with one staging buffer per partition:
+
+    xsb_set_csc(h, csc)                                   old CSC -> HBM  (16 B per old entry, once)
+    xsb_insert_triplets(h, t-1, run, count, flavour)      every partition's calls, run by run, in call order
+    xsb_flush(h, mode, &nnz, &changed)                    merge on the GPU
+    xsb_fetch_csc(h, colptr, rowval, nzval)               new CSC -> Julia-owned arrays
 """
 function Base.sum(exts::Vector{SparseMatrixB200{Tv, Ti}}, csc::SparseMatrixCSC{Tv, Ti};
                   mode = XSB_DETERMINISTIC) where {Tv, Ti}
     sum(nnz, exts) == 0 && return csc
-    acc = exts[1]
-    foreach(ship!, exts)
-    check(acc.handle, ccall((:xsb_synchronize, libxsb), Int32, (Ptr{Cvoid},), acc.handle))
-    if length(exts) > 1
-        # one device matrix with one staging buffer per partition keeps the partition order
-        big = B200Assembler{Tv, Ti}(csc.m, csc.n, length(exts))
-        set_csc!(big, csc)
-        for (t, e) in enumerate(exts)
-            replay!(big, e, t - 1)
+    h = device_handle(Ti, csc.m, csc.n, length(exts))
+    check(h, ccall((:xsb_set_csc, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                   h, csc.colptr, csc.rowval, csc.nzval))
+    for (t, e) in enumerate(exts)
+        for (r, (first, flavour)) in enumerate(e.runs)
+            last = r < length(e.runs) ? e.runs[r + 1][1] - 1 : e.fill
+            GC.@preserve e begin
+                check(h, ccall((:xsb_insert_triplets, libxsb), Int32,
+                               (Ptr{Cvoid}, Int32, Ptr{XsbTriplet}, Int64, Int32),
+                               h, t - 1, pointer(e.T, first), last - first + 1, flavour))
+            end
         end
-        return fetch!(big, mode)
     end
-    h = acc.handle
-    # pending records were staged against an empty device CSC; merging with `csc` needs the old
-    # entries on the device first.  xsb_set_csc would drop the staged records, so the old matrix
-    # is inserted as the first partition of a fresh assembler instead.
-    big = B200Assembler{Tv, Ti}(csc.m, csc.n, 1)
-    set_csc!(big, csc)
-    replay!(big, acc, 0)
-    fetch!(big, mode)
+    nnz_new = Ref{Int64}(0); changed = Ref{Int32}(0)
+    check(h, ccall((:xsb_flush, libxsb), Int32, (Ptr{Cvoid}, Int32, Ref{Int64}, Ref{Int32}), h, mode, nnz_new, changed))
+    colptr = Vector{Ti}(undef, csc.n + 1)
+    rowval = Vector{Ti}(undef, nnz_new[])
+    nzval = Vector{Tv}(undef, nnz_new[])
+    check(h, ccall((:xsb_fetch_csc, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                   h, colptr, rowval, nzval))
+    SparseMatrixCSC{Tv, Ti}(csc.m, csc.n, colptr, rowval, nzval)
 end
 
 Base.:+(x::SparseMatrixB200, csc::SparseMatrixCSC) = sum([x], csc)
@@ -192,28 +203,6 @@ function insert!(a::B200Assembler{Tv, Ti}, I::Vector{Ti}, J::Vector{Ti}, V::Vect
     check(a.handle, ccall((:xsb_insert_batch, libxsb), Int32,
                           (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32),
                           a.handle, tid, I, J, V, length(V), flavour))
-end
-
-function replay!(a::B200Assembler{Tv, Ti}, e::SparseMatrixB200{Tv, Ti}, tid) where {Tv, Ti}
-    cnt = Ref{Int64}(0)
-    check(e.handle, ccall((:xsb_debug_fetch_staged, libxsb), Int32,
-                          (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Int64}),
-                          e.handle, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0, cnt))
-    n = cnt[]
-    I = Vector{Ti}(undef, n); J = Vector{Ti}(undef, n); V = Vector{Tv}(undef, n); F = Vector{Int32}(undef, n)
-    check(e.handle, ccall((:xsb_debug_fetch_staged, libxsb), Int32,
-                          (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Int64}),
-                          e.handle, 0, I, J, V, F, n, cnt))
-    # runs of equal flavour keep the call order
-    s = 1
-    while s <= n
-        t = s
-        while t < n && F[t + 1] == F[s]
-            t += 1
-        end
-        insert!(a, I[s:t], J[s:t], V[s:t]; flavour = F[s], tid = tid)
-        s = t + 1
-    end
 end
 
 "flush! + sparse(A): two-phase -- query nnz, allocate Julia arrays, fetch (ownership stays with Julia)"

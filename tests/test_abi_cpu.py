@@ -88,24 +88,23 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_roofline_accounting_covers_every_flush_path():
-    """bench.roofline(): the dominant stage, its algorithmic bytes and the whole-flush fraction for the product
-    path (bucketed or sorted pairs, with and without counting at insertion) and the fallback paths."""
+    """bench.roofline(): roofline.frac is SURVEY.md 8(d)'s fraction -- the flush's algorithmic bytes over the device
+    time of the whole flush! -- for the product path and the fallback paths; per-kernel detail beside it."""
     import bench
 
-    ms = {"ms_group_count": 0.66, "ms_group_scatter": 1.48, "ms_pair_sort": 0.27, "ms_fold": 1.18, "ms_compact": 0.0,
-          "ms_sort": 1.75, "ms_reduce": 1.18, "ms_total": 3.66}
-    st = {"n_inserted": 245805960, "nnz_old": 0, "nnz_new": 31065598, "group_pairs": 11735358, "column_path": 3,
+    ms = {"ms_group_count": 0.0, "ms_pair_sort": 0.17, "ms_fold": 1.79, "ms_sort": 0.17, "ms_reduce": 1.79, "ms_total": 1.99}
+    st = {"n_inserted": 245805960, "nnz_old": 0, "nnz_new": 31065598, "group_pairs": 10679412, "column_path": 4,
           "sort_passes": 0, "precounted": 1.0, "direct_fold": 1}
-    r = bench.roofline(st, ms, 2097152, 6543.4, "measured", None)
-    assert r["kernel"].startswith("group_scatter_kernel") and r["bound"] == "hbm" and r["unit"] == "GB/s"
-    assert abs(r["achieved"] - (32 * 245805960 + 8 * 11735358) / 1.48e-3 / 1e9) < 1e-6
-    assert abs(r["frac"] - r["achieved"] / 6543.4) < 1e-12 and r["traffic"] == 4.0631e9 + 3.8998e9
-    assert abs(r["flush"]["algorithmic_bytes"] - bench.flush_bytes(245805960, 0, 31065598, 2097152)) < 1
-    assert any(k.startswith("pair buckets") for k in r["kernels"])
-    st2 = dict(st, sort_passes=3, precounted=0.0)
-    r2 = bench.roofline(st2, dict(ms, ms_pair_sort=2.0), 2097152, 6543.4, "measured", None)
-    assert r2["kernel"].startswith("onesweep_kernel on the (column, chunk) pairs") and r2["launches_per_step"] == 3
-    for path in (0, 2):
+    b = bench.flush_bytes(245805960, 0, 31065598, 2097152)
+    assert b == 16 * 245805960 + 16 * 31065598 + 16 * (2097152 + 1)
+    r = bench.roofline(st, ms, 1.9, 2097152, 6543.4, "measured", None)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["bytes_per_launch"] == b and r["ms_per_launch"] == 1.99
+    assert abs(r["achieved"] - b / 1.99e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6543.4) < 1e-12
+    assert r["traffic"] is None and "runfold_kernel" in r["kernel"]
+    assert abs(r["span_emission_to_csc"]["ms"] - 3.89) < 1e-9
+    assert any(k.startswith("run buckets") for k in r["kernels"])
+    for path in (0, 2, 3):
         st3 = dict(st, column_path=path, sort_passes=6, group_pairs=0)
-        r3 = bench.roofline(st3, dict(ms, ms_sort=14.0), 2097152, 6543.4, "measured", None)
-        assert r3["kernel"].startswith("onesweep_kernel (one radix pass") and r3["traffic"] is None
+        r3 = bench.roofline(st3, dict(ms, ms_sort=14.0, ms_total=18.0), None, 2097152, 6543.4, "measured", "fem128")
+        assert abs(r3["achieved"] - b / 18.0e-3 / 1e9) < 1e-6 and r3["traffic"] is None
+    assert bench.values_only_bytes(95760000, 55760000) == 12 * 95760000 + 8 * 55760000

@@ -1,16 +1,20 @@
-"""Full-size GPU checks of BASELINE.json's single-GPU configurations through size-independent
-properties (the CPU oracle needs minutes at these sizes and /root/reference does not exist on the
-GPU box):
-  * two independent implementations of flush! -- grouping by column + thread-per-column fold
-    (STRATEGY_AUTO) and the (col,row) radix sort + flat segmented fold (STRATEGY_FULLSORT) -- must
-    agree bit for bit on colptr, rowval and nzval;
+"""Full-size GPU checks of BASELINE.json's single-GPU configurations.
+
+Against the CPU oracle (the C restatement of the reference's algorithm, oracle/; it assembles these sizes in
+1.5-4 s each, the streams come from its own generators, nothing here reads /root/reference):
+  * cfg 2 (P1-FEM 128^3), cfg 3 (fdrand 200^3 build + a values-only re-assembly into the frozen pattern) and
+    cfg 4 (block reaction-diffusion 96^3 x 4 + Dirichlet penalty rows + elimination): colptr / rowval / nzval of
+    the GPU product path equal the oracle's bit for bit (test/test_assembly.jl:20-32 asks for exact ==).
+Size-independent properties on top:
+  * two independent implementations of flush! -- grouped chunks + thread-per-column merge (the product path)
+    and the (col,row) radix sort + flat segmented fold (STRATEGY_FULLSORT) -- agree bit for bit;
   * closed-form nnz of the stencil, strictly increasing rows per column, structural symmetry;
   * XSB_FAST (plain and with window pre-aggregation) keeps the pattern and stays within 1e-14;
   * the frozen-pattern re-assembly (Newton loop of configs[2]) reproduces a full flush! bit for bit.
-All comparisons run on the device (torch); nothing here reads the oracle.
 """
 import ctypes as C
 
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -158,4 +162,89 @@ def test_newton_loop_fd200_values_only(xsb, torch):
         _, _, nzf = device_csc(torch, h)
         assert float((nzf - ref).abs().max()) <= 1e-14 * float(ref.abs().max())
         del dVn, ref, nz, nzf
+    h.close()
+
+
+# ---------------------------------------------------------------- full size against the oracle
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def _assert_equals_oracle(h, ref, what):
+    cp, rv, nz = h.fetch_csc_numpy()
+    ocp, orv, onz = ref
+    assert np.array_equal(cp, ocp), f"{what}: colptr differs from the oracle"
+    assert np.array_equal(rv, orv), f"{what}: rowval differs from the oracle"
+    bad = np.nonzero(_bits(nz) != _bits(onz))[0]
+    assert bad.size == 0, f"{what}: {bad.size} nzval entries not bit-exact with the oracle, first at {bad[:5]}"
+
+
+def test_cfg2_fem128_equals_oracle(xsb, oracle):
+    """configs[1]: the bench workload.  GPU product path (on-device emitter, grouped chunks) vs the oracle's
+    ExtendableSparseMatrix + rawupdateindex! + flush! on the oracle's own copy of the stream."""
+    n1 = 128
+    n = n1 ** 3
+    I, J, V = oracle.fem_stream(n1, n1, n1)
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.RAW)
+    del I, J, V
+    ref = A.csc()
+    del A
+    h = xsb.Handle(n, n)
+    h.emit_p1fem(n1, n1, n1, flavour=xsb.RAW)
+    nnz, changed = h.flush()
+    assert changed and nnz == len(ref[1]) == 31065598 and h.flush_stats()["column_path"] == 4
+    _assert_equals_oracle(h, ref, "cfg2")
+    h.close()
+
+
+def test_cfg3_fd200_build_and_reassembly_equal_oracle(xsb, oracle):
+    """configs[2]: fdrand 200^3 via updateindex! + flush!, then one values-only re-assembly (nonzeros .= 0, second
+    stream into the frozen pattern: every call a CSC hit, extendable.jl:164-166) -- both against the oracle."""
+    nx = 200
+    n = nx ** 3
+    I, J, V = oracle.fdrand_stream(nx, nx, nx, seed=100)
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    h = xsb.Handle(n, n)
+    h.emit_fdrand(nx, nx, nx, seed=100)
+    nnz, _ = h.flush()
+    assert nnz == 55760000 and h.flush_stats()["column_path"] == 4
+    _assert_equals_oracle(h, A.csc(), "cfg3 build")
+    _, _, V2 = oracle.fdrand_stream(nx, nx, nx, seed=101)
+    A.zero_values()
+    A.insert_batch(I, J, V2, oracle.UPDATE)
+    h.freeze_pattern(I, J)
+    h.zero_values()
+    h.reassemble_values(V2, xsb.DETERMINISTIC)
+    _assert_equals_oracle(h, A.csc(), "cfg3 re-assembly")
+    h.close()
+
+
+def test_cfg4_rd96_with_dirichlet_equals_oracle(xsb, oracle):
+    """configs[3]: 96^3 x 4-species block system, Dirichlet penalty rows on the two x-faces (A[d,d] = 1e30, the
+    assign flavour, test/test_dirichlet.jl:9-11) and eliminate_dirichlet! (sparsematrixcsc.jl:124-148)."""
+    nx, ns = 96, 4
+    n = ns * nx ** 3
+    I, J, V = oracle.blockrd_stream(nx, nx, nx, ns, seed=7)
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    del I, J, V
+    node = np.arange(nx ** 3)
+    face = (node % nx == 0) | (node % nx == nx - 1)
+    d = (ns * node[face][:, None] + np.arange(ns)[None, :]).reshape(-1) + 1
+    pen = np.full(len(d), 1.0e30)
+    A.insert_batch(d, d, pen, oracle.ASSIGN)
+    A.flush()
+    h = xsb.Handle(n, n)
+    h.emit_blockrd(nx, nx, nx, ns, seed=7, flavour=xsb.UPDATE)
+    h.insert_batch(d, d, pen, xsb.ASSIGN)
+    nnz, _ = h.flush()
+    assert nnz == 98205696
+    _assert_equals_oracle(h, A.csc(), "cfg4 assembly")
+    mk = h.mark_dirichlet(1.0e20)
+    assert np.array_equal(mk, A.mark_dirichlet(1.0e20)) and int(mk.sum()) == len(d)
+    h.eliminate_dirichlet(mk)
+    A.eliminate_dirichlet(mk)
+    _assert_equals_oracle(h, A.csc(), "cfg4 eliminated")
     h.close()

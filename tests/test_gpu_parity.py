@@ -390,34 +390,38 @@ def test_emit_p1fem(xsb, oracle, dims):
         h.close()
 
 
-@pytest.mark.parametrize("dims", [(2, 2, 2, 4), (5, 4, 3, 4), (6, 6, 6, 2), (3, 1, 1, 3)])
+@pytest.mark.parametrize("dims", [(2, 2, 2, 4), (5, 4, 3, 4), (6, 6, 6, 2), (3, 1, 1, 3), (4, 3, 2, 1), (3, 3, 2, 6), (2, 2, 2, 7)])
 def test_emit_blockrd_with_dirichlet(xsb, oracle, dims):
     """cfg 4 at oracle size: block system, then Dirichlet penalty rows (A[d,d]=1e30) and elimination."""
     nx, ny, nz_, ns = dims
     N = nx * ny * nz_ * ns
-    h = xsb.Handle(N, N)
-    h.set_precount(False)  # keep the staged records in stream order for the comparison below
-    h.emit_blockrd(nx, ny, nz_, ns, seed=7, flavour=xsb.UPDATE)
     I, J, V = oracle.blockrd_stream(nx, ny, nz_, ns, seed=7)
-    gI, gJ, gV, _ = h.debug_fetch_staged()
-    assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
-    A = oracle.OracleExt(N, N)
-    A.insert_batch(I, J, V, oracle.UPDATE)
     # Dirichlet on the two x-faces: test/test_dirichlet.jl:9-11
     node = np.arange(nx * ny * nz_)
     face = (node % nx == 0) | (node % nx == nx - 1)
     d = (ns * node[face][:, None] + np.arange(1, ns + 1)[None, :]).ravel().astype(np.int64)
     pen = np.full(len(d), 1.0e30)
-    h.insert_batch(d, d, pen, xsb.ASSIGN)
-    A.insert_batch(d, d, pen, oracle.ASSIGN)
-    h.flush()
-    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
-    mk = h.mark_dirichlet()
-    omk = A.mark_dirichlet()
-    assert np.array_equal(mk, omk) and mk.sum() == len(d)
-    h.eliminate_dirichlet(mk)
-    A.eliminate_dirichlet(omk)
-    assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+    for grouped in (False, True):  # stream order as staged / chunks grouped by column while they are staged
+        h = xsb.Handle(N, N)
+        h.set_precount(grouped)
+        h.emit_blockrd(nx, ny, nz_, ns, seed=7, flavour=xsb.UPDATE)
+        gI, gJ, gV, _ = h.debug_fetch_staged()
+        if not grouped:
+            assert np.array_equal(gI, I) and np.array_equal(gJ, J) and np.array_equal(bits(gV), bits(V))
+        assert_same_entry_streams((gI, gJ, gV), (I, J, V))
+        A = oracle.OracleExt(N, N)
+        A.insert_batch(I, J, V, oracle.UPDATE)
+        h.insert_batch(d, d, pen, xsb.ASSIGN)
+        A.insert_batch(d, d, pen, oracle.ASSIGN)
+        h.flush()
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        mk = h.mark_dirichlet()
+        omk = A.mark_dirichlet()
+        assert np.array_equal(mk, omk) and mk.sum() == len(d)
+        h.eliminate_dirichlet(mk)
+        A.eliminate_dirichlet(omk)
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        h.close()
 
 
 # ---------------------------------------------------------------- multi-partition
