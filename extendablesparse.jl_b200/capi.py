@@ -107,10 +107,12 @@ SIGNATURES = {
     "xsb_zero_values": (_i32, [_p]),
     "xsb_freeze_pattern": (_i32, [_p, _p, _p, _i64]),
     "xsb_reassemble_values": (_i32, [_p, _p, _i64, _i32]),
+    "xsb_reassemble_values_zeroed": (_i32, [_p, _p, _i64, _i32]),
     "xsb_unfreeze": (_i32, [_p]),
     "xsb_mark_dirichlet": (_i32, [_p, _f64, _p]),
     "xsb_eliminate_dirichlet": (_i32, [_p, _p]),
     "xsb_pattern_hash": (_i32, [_p, C.POINTER(_u64)]),
+    "xsb_pattern_equal": (_i32, [_p, _p, C.POINTER(_i32)]),
     "xsb_pointblock": (_i32, [_p, _i32, C.POINTER(_p)]),
     "xsb_block_size": (_i32, [_p, C.POINTER(_i32)]),
     "xsb_fetch_blocks": (_i32, [_p, _p]),
@@ -336,10 +338,12 @@ class Handle:
             count = len(I)
         self._c(lib().xsb_freeze_pattern(self._h, ptr(I), ptr(J), count))
 
-    def reassemble_values(self, V, mode=DETERMINISTIC, count=None):
+    def reassemble_values(self, V, mode=DETERMINISTIC, count=None, zero_first=False):
+        """zero_first: nonzeros(A) .= 0 and the re-assembly in one pass (xsb_reassemble_values_zeroed)."""
         if count is None:
             count = len(V)
-        self._c(lib().xsb_reassemble_values(self._h, ptr(V), count, mode))
+        f = lib().xsb_reassemble_values_zeroed if zero_first else lib().xsb_reassemble_values
+        self._c(f(self._h, ptr(V), count, mode))
 
     def unfreeze(self):
         self._c(lib().xsb_unfreeze(self._h))
@@ -389,6 +393,12 @@ class Handle:
         v = _u64(0)
         self._c(lib().xsb_pattern_hash(self._h, C.byref(v)))
         return v.value
+
+    def pattern_equal(self, other: "Handle") -> bool:
+        """pattern_equal(a, b) (sparsematrixcsc.jl:77-85): same colptr and rowval, compared on the device."""
+        v = _i32(0)
+        self._c(lib().xsb_pattern_equal(self._h, other._h, C.byref(v)))
+        return bool(v.value)
 
     def emit_fdrand(self, nx, ny=1, nz=1, seed=20240717, ones=False, flavour=UPDATE, tid=0, l_range=None):
         if l_range is None:

@@ -94,9 +94,9 @@ struct xsb_matrix
     // frozen pattern
     bool frozen = false;
     i64 f_count = 0;
-    i64 *f_slot = nullptr;
-    u32 *f_perm = nullptr;
-    i64 *f_segstart = nullptr;
+    u32 *f_slot = nullptr;     // 4-byte entry -> nzval map of the frozen stream (fast mode)
+    u32 *f_perm = nullptr;     // stream positions in nzval order (deterministic mode)
+    u32 *f_segstart = nullptr; // first of them per nzval entry
 
     double *blocks = nullptr; // result handle of xsb_pointblock: nnz dense bs x bs blocks, column-major, CSC order
     int block_size = 0;
@@ -659,6 +659,7 @@ bool runs_flush(xsb_matrix *h, int32_t mode, i64 n_ins, StageTimer *tp, int64_t 
         return false;
     }
     h->runs_misses = 0;
+    h->grouping_misses = 0;
     // ---- the new matrix replaces the resident one; the staging buffer stays where it is
     h->dfree(h->colptr);
     h->dfree(h->csc_store);
@@ -1791,13 +1792,14 @@ int32_t xsb_freeze_pattern(xsb_matrix *h, const void *I, const void *J, int64_t 
         slots_to_records(s, slot, count, A, h->lc);
         const SortPlan plan = make_sort_plan(0, ceil_log2(std::max<i64>(h->nnz, 2)));
         Rec *sorted = radix_sort_records(s, A, B, (u64)count, plan, ws, h->lc, nullptr);
-        h->f_perm = static_cast<u32 *>(h->dalloc(4 * (size_t)count));
-        h->f_segstart = static_cast<i64 *>(h->dalloc(8 * (size_t)(h->nnz + 1)));
-        build_frozen_map(s, sorted, count, h->nnz, h->f_perm, h->f_segstart, h->lc);
+        h->f_perm = static_cast<u32 *>(h->dalloc(4 * (size_t)std::max<i64>(count, 1)));
+        h->f_segstart = static_cast<u32 *>(h->dalloc(4 * (size_t)(h->nnz + 1)));
+        h->f_slot = static_cast<u32 *>(h->dalloc(4 * (size_t)std::max<i64>(count, 1)));
+        build_frozen_map(s, sorted, count, h->nnz, h->f_perm, h->f_segstart, h->f_slot, h->lc);
         h->dfree(A);
         h->dfree(B);
         h->dfree(ws);
-        h->f_slot = slot;
+        h->dfree(slot);
         h->f_count = count;
         h->frozen = true;
         h->sync();
@@ -1805,7 +1807,7 @@ int32_t xsb_freeze_pattern(xsb_matrix *h, const void *I, const void *J, int64_t 
     });
 }
 
-int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32_t mode)
+static int32_t reassemble_impl(xsb_matrix *h, const void *V, int64_t count, int32_t mode, bool zero_first)
 {
     return guard(h, [&]() -> int32_t {
         REQUIRE(h, XSB_EINVAL, "NULL handle");
@@ -1813,16 +1815,34 @@ int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32
         REQUIRE(count == h->f_count, XSB_ESIZE, "value count differs from the frozen stream");
         REQUIRE(mode == XSB_DETERMINISTIC || mode == XSB_FAST, XSB_EINVAL, "unknown summation mode");
         if (count == 0)
+        {
+            if (zero_first)
+                zero_values(h->stream, h->nzval, h->nnz, h->lc);
             return XSB_OK;
+        }
         REQUIRE(V, XSB_EINVAL, "NULL array");
         DevIn dV(h, V, 8 * (size_t)count);
         if (mode == XSB_DETERMINISTIC)
             reassemble_deterministic(h->stream, static_cast<const double *>(dV.ptr), h->f_perm, h->f_segstart, h->nnz,
-                                     h->nzval, h->lc);
+                                     h->nzval, zero_first, h->lc);
         else
+        {
+            if (zero_first)
+                zero_values(h->stream, h->nzval, h->nnz, h->lc);
             reassemble_fast(h->stream, static_cast<const double *>(dV.ptr), h->f_slot, count, h->nzval, h->lc);
+        }
         return XSB_OK;
     });
+}
+
+int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32_t mode)
+{
+    return reassemble_impl(h, V, count, mode, false);
+}
+
+int32_t xsb_reassemble_values_zeroed(xsb_matrix *h, const void *V, int64_t count, int32_t mode)
+{
+    return reassemble_impl(h, V, count, mode, true);
 }
 
 int32_t xsb_unfreeze(xsb_matrix *h)
@@ -1899,6 +1919,48 @@ int32_t xsb_pattern_hash(xsb_matrix *h, uint64_t *hash_out)
         REQUIRE(h && hash_out, XSB_EINVAL, "NULL argument");
         pattern_hash(h->stream, h->view(), h->n, h->idx64, h->d_scal + 4, h->lc);
         *hash_out = read_scalar(h, 4);
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_pattern_equal(xsb_matrix *a, xsb_matrix *b, int32_t *equal_out)
+{
+    if (!a || !b || !equal_out)
+        return XSB_EINVAL;
+    if (a == b)
+    {
+        *equal_out = 1;
+        return XSB_OK;
+    }
+    // lock both handles in address order (two threads comparing the same pair the other way round must not deadlock)
+    xsb_matrix *first = a < b ? a : b, *second = a < b ? b : a;
+    std::lock_guard<std::recursive_mutex> l1(first->mu), l2(second->mu);
+    return guard(a, [&]() -> int32_t {
+        REQUIRE(a->pending() == 0 && b->pending() == 0, XSB_ESTATE, "flush! both matrices first");
+        if (a->m != b->m || a->n != b->n || a->nnz != b->nnz)
+        {
+            *equal_out = 0;
+            return XSB_OK;
+        }
+        if (a->device != b->device)
+        { // no common address space to compare in: equal fingerprints (64-bit, both patterns 0-based would be needed)
+            REQUIRE(a->base == b->base && a->idx64 == b->idx64, XSB_EINVAL,
+                    "handles on different devices must share index type and base");
+            write_scalar(a, 4, 0);
+            pattern_hash(a->stream, a->view(), a->n, a->idx64, a->d_scal + 4, a->lc);
+            const u64 ha = read_scalar(a, 4);
+            XSB_CUDA(cudaSetDevice(b->device));
+            write_scalar(b, 4, 0);
+            pattern_hash(b->stream, b->view(), b->n, b->idx64, b->d_scal + 4, b->lc);
+            const u64 hb = read_scalar(b, 4);
+            XSB_CUDA(cudaSetDevice(a->device));
+            *equal_out = ha == hb;
+            return XSB_OK;
+        }
+        b->sync(); // b's arrays are read on a's stream
+        write_scalar(a, 4, 0);
+        pattern_diff(a->stream, a->view(), a->idx64, a->base, b->view(), b->idx64, b->base, a->n, a->d_scal + 4, a->lc);
+        *equal_out = read_scalar(a, 4) == 0ull;
         return XSB_OK;
     });
 }

@@ -173,4 +173,39 @@ __device__ __forceinline__ void chunk_publish(ChunkSpaceT<HB> &ws, const RunTarg
     }
 }
 
+// A chunk without column locality (more distinct columns than the table takes) stays in stream order and
+// publishes every record as a run of its own: a small unordered batch on top of a large matrix still takes the
+// grouped-chunk flush; a large one fills the pair list, and the flag sends the flush to the radix-sort path.
+// g[b] / valid: grouping key of this lane's record of batch b.
+template <int NB>
+__device__ __forceinline__ void chunk_publish_singletons(const RunTarget &rt, u32 chunk, u32 abs_start, u32 len,
+                                                         const u32 (&g)[NB], int lane)
+{
+    constexpr u32 full = 0xffffffffu;
+    u32 base = 0;
+    if (lane == 0)
+        base = atomicAdd(rt.counters, len);
+    base = __shfl_sync(full, base, 0);
+    const bool room = (u64)base + len <= (u64)rt.cap;
+    if (lane == 0)
+    {
+        rt.chunkinfo[chunk] = make_uint2(base, room ? len : 0u);
+        rt.chunkstart[chunk] = abs_start;
+        if (!room)
+            atomicOr(rt.counters + 1, 1u);
+    }
+    if (!room)
+        return;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+    {
+        const u32 p = b * 32 + lane;
+        if (p < len)
+        {
+            rt.pcol[base + p] = g[b];
+            rt.pinfo[base + p] = (p << 16) | 1u;
+        }
+    }
+}
+
 } // namespace xsb

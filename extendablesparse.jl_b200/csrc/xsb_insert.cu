@@ -194,7 +194,15 @@ pack_grouped_kernel(Src src, i64 count, u32 nchunks, i64 m, i64 n, KeyLayout L, 
                 sf.flags[(sf.pos0 + c0 + (i64)dst) >> kRouteTileShift] = 1; // benign race: same value
         }
     }
-    chunk_publish(ws, rt, chunk0 + c, pos0 + (u32)c0, d, grouped, lane);
+    if (grouped)
+        chunk_publish(ws, rt, chunk0 + c, pos0 + (u32)c0, d, true, lane);
+    else
+    { // no column locality in this chunk: stored in call order, every record a run of its own
+#pragma unroll
+        for (int b = 0; b < PG_NB; ++b)
+            rs[b] = (u32)(r[b].key >> rt.colshift) & rt.gmask;
+        chunk_publish_singletons<PG_NB>(rt, chunk0 + c, pos0 + (u32)c0, len, rs, lane);
+    }
 }
 
 template <class Src>

@@ -253,6 +253,11 @@ void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, 
 void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace,
                    const u64 *counts_host, Rec *send, LaunchCounter &lc);
 void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayout &L, LaunchCounter &lc);
+// fixed-capacity exchange (no count visits the host): see xsb_route.cu
+void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, const i64 *caps,
+                u64 *pinned_bases, u64 *pinned_caps, Rec *send, LaunchCounter &lc, const unsigned char *tileflags);
+void route_unpack(cudaStream_t stream, const Rec *block, i64 cap, Rec *out, const KeyLayout &L, i64 ncols, u64 *d_flags,
+                  u64 *d_counts, int which, LaunchCounter &lc);
 void route_check(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &L, i64 ncols, u64 *d_err,
                  u64 *d_has_assign, LaunchCounter &lc);
 
@@ -316,17 +321,19 @@ void gather_values(cudaStream_t stream, const double *nzval, const i64 *slot, i6
 void count_missing_records(cudaStream_t stream, const Rec *recs, i64 count, const KeyLayout &L, const CscView &csc,
                            int idx64, int base, u64 *d_missing, LaunchCounter &lc);
 void slots_to_records(cudaStream_t stream, const i64 *slot, i64 count, Rec *out, LaunchCounter &lc);
-void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, i64 *segstart,
+void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, u32 *segstart, u32 *slot32,
                       LaunchCounter &lc);
-void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *perm, const i64 *segstart,
-                              i64 nnz, double *nzval, LaunchCounter &lc);
-void reassemble_fast(cudaStream_t stream, const double *V, const i64 *slot, i64 count, double *nzval,
+void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *perm, const u32 *segstart, i64 nnz,
+                              double *nzval, bool zero_first, LaunchCounter &lc);
+void reassemble_fast(cudaStream_t stream, const double *V, const u32 *slot, i64 count, double *nzval,
                      LaunchCounter &lc);
 void mark_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, double penalty,
                     unsigned char *marker, LaunchCounter &lc);
 void eliminate_dirichlet(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base,
                          const unsigned char *marker, LaunchCounter &lc);
 void pattern_hash(cudaStream_t stream, const CscView &csc, i64 n, int idx64, u64 *d_hash, LaunchCounter &lc);
+void pattern_diff(cudaStream_t stream, const CscView &a, int idx64a, int basea, const CscView &b, int idx64b, int baseb,
+                  i64 n, u64 *d_diff, LaunchCounter &lc);
 
 // ---- xsb_mul.cu
 size_t csr_map_bytes(i64 m, i64 nnz);

@@ -119,7 +119,7 @@ route_scan_kernel(const u32 *__restrict__ tilecnt, u32 *__restrict__ tileoff, u6
 __global__ void __launch_bounds__(RT_THREADS)
 route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershift, u32 me, int nranks,
                      const u32 *__restrict__ tilecnt, const u32 *__restrict__ tileoff,
-                     const u64 *__restrict__ bucket_base, Rec *__restrict__ send)
+                     const u64 *__restrict__ bucket_base, const u64 *__restrict__ bucket_cap, Rec *__restrict__ send)
 {
     __shared__ u32 s_w[RT_THREADS / 32];
     __shared__ u32 s_run;
@@ -168,7 +168,10 @@ route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershi
             if (threadIdx.x == 0)
                 s_run = 0;
             __syncthreads();
-            Rec *dst = send + bucket_base[d] + tileoff[tile * nranks + d];
+            const u32 toff = tileoff[tile * nranks + d];
+            Rec *dst = send + bucket_base[d] + toff;
+            // fixed-capacity exchange: a bucket that is fuller than its block is cut off (its header says so)
+            const u64 room = bucket_cap != nullptr ? bucket_cap[d] : ~0ull;
 #pragma unroll
             for (int i = 0; i < RT_IPT; ++i)
             { // round i holds RT_THREADS consecutive records: rank them in thread order
@@ -180,7 +183,7 @@ route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershi
                 u32 pre = s_run;
                 for (int w = 0; w < warp; ++w)
                     pre += s_w[w];
-                if (mine)
+                if (mine && (u64)toff + pre + __popc(bal & lanemask_lt()) < room)
                     st_rec(dst + pre + __popc(bal & lanemask_lt()), r[i]);
                 __syncthreads();
                 if (threadIdx.x == 0)
@@ -238,7 +241,7 @@ void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayou
 size_t route_workspace_bytes(u64 n, int nranks)
 {
     const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
-    return 2 * sizeof(u32) * (size_t)ntiles * nranks + 2 * sizeof(u64) * kMaxRanks + 256;
+    return 2 * sizeof(u32) * (size_t)ntiles * nranks + 3 * sizeof(u64) * kMaxRanks + 256;
 }
 
 // counts_host[d] = staged records owned by rank d (d == me: the ones that stay)
@@ -297,10 +300,120 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
         return;
     XSB_CUDA(cudaMemcpyAsync(bucket_base, hb, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
     route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
-        in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, send);
+        in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, nullptr, send);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     XSB_CUDA(cudaStreamSynchronize(stream)); // hb lives on this stack frame
+}
+
+// ------------------------------------------------------------------------
+// Fixed-capacity exchange: no count ever visits the host.  The send buffer holds one BLOCK per destination
+// (own rank: none): a header record {records of the bucket, magic} followed by cap[d] record slots.  Sender and
+// receiver agree on the capacities beforehand (e.g. from the previous step of an assembly loop), so the
+// all-to-all runs with host-known split sizes and the whole step is stream-ordered.
+// ------------------------------------------------------------------------
+constexpr u64 kRouteMagic = 0x5853425f524f5554ull; // "XSB_ROUT"
+
+__global__ void route_header_kernel(const u64 *__restrict__ total, const u64 *__restrict__ bucket_base, int nranks, u32 me,
+                                    Rec *__restrict__ send)
+{
+    const int d = threadIdx.x;
+    if (d < nranks && (u32)d != me)
+    {
+        Rec r;
+        r.key = total[d];
+        r.val = __longlong_as_double((long long)kRouteMagic);
+        st_rec(send + bucket_base[d] - 1, r);
+    }
+}
+
+// pinned_bases / pinned_caps: host staging (pinned, kMaxRanks entries each) that outlives the call
+void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, const i64 *caps,
+                u64 *pinned_bases, u64 *pinned_caps, Rec *send, LaunchCounter &lc, const unsigned char *tileflags)
+{
+    const int nr = L.nranks;
+    const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
+    u32 *tilecnt = static_cast<u32 *>(workspace);
+    u32 *tileoff = tilecnt + (size_t)ntiles * nr;
+    u64 *total = reinterpret_cast<u64 *>(tileoff + (size_t)ntiles * nr);
+    u64 *bucket_base = total + kMaxRanks;
+    u64 *bucket_cap = bucket_base + kMaxRanks;
+    u64 run = 0;
+    for (int d = 0; d < nr; ++d)
+    {
+        pinned_caps[d] = d == L.self ? 0ull : (u64)caps[d];
+        pinned_bases[d] = run + 1; // first slot behind the header
+        if (d != L.self)
+            run += (u64)caps[d] + 1;
+    }
+    XSB_CUDA(cudaMemcpyAsync(bucket_base, pinned_bases, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
+    XSB_CUDA(cudaMemcpyAsync(bucket_cap, pinned_caps, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
+    XSB_CUDA(cudaMemsetAsync(total, 0, sizeof(u64) * kMaxRanks, stream));
+    if (n > 0)
+    {
+        XSB_CUDA(cudaMemsetAsync(tilecnt, 0, sizeof(u32) * (size_t)ntiles * nr, stream));
+        route_count_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+            in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileflags);
+        route_scan_kernel<<<nr, 1024, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total);
+        route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+            in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, bucket_cap, send);
+        lc.add(3);
+    }
+    route_header_kernel<<<1, kMaxRanks, 0, stream>>>(total, bucket_base, nr, (u32)L.self, send);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// One received block -> `cap` records behind the staged ones: the bucket's records (checked: owned by this rank),
+// then padding records the flush skips.  flags: bit 0 a record of another owner, bit 1 the bucket did not fit its
+// block (records were cut off), bit 2 not a block (bad magic).  counts[which] += records taken.
+__global__ void __launch_bounds__(256)
+route_unpack_kernel(const Rec *__restrict__ block, u64 cap, Rec *__restrict__ out, int ownershift, u32 me, u64 colmask,
+                    int colshift, u64 ncols, u64 padkey, u64 *__restrict__ flags, u64 *__restrict__ counts, int which)
+{
+    const Rec hdr = block[0];
+    const u64 count = hdr.key;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        u64 f = 0;
+        if ((u64)__double_as_longlong(hdr.val) != kRouteMagic)
+            f |= 4ull;
+        else if (count > cap)
+            f |= 2ull;
+        if (f)
+            atomicOr(reinterpret_cast<unsigned long long *>(flags), (unsigned long long)f);
+        atomicAdd(reinterpret_cast<unsigned long long *>(counts + which), (unsigned long long)min(count, cap));
+    }
+    const u64 take = (u64)__double_as_longlong(hdr.val) == kRouteMagic ? min(count, cap) : 0ull;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += stride)
+    {
+        Rec r;
+        if (k < take)
+        {
+            r = block[1 + k];
+            if ((u32)(r.key >> ownershift) != me || ((r.key >> colshift) & colmask) >= ncols)
+                atomicOr(reinterpret_cast<unsigned long long *>(flags), 1ull);
+        }
+        else
+        {
+            r.key = padkey;
+            r.val = 0.0;
+        }
+        st_rec(out + k, r);
+    }
+}
+
+void route_unpack(cudaStream_t stream, const Rec *block, i64 cap, Rec *out, const KeyLayout &L, i64 ncols, u64 *d_flags,
+                  u64 *d_counts, int which, LaunchCounter &lc)
+{
+    const u64 padkey = (u64)((u32)L.self ^ 1u) << L.ownershift();
+    const int blocks = (int)std::max<i64>(1, std::min<i64>((cap + 255) / 256, (i64)kNumSM * 8));
+    route_unpack_kernel<<<blocks, 256, 0, stream>>>(block, (u64)cap, out, L.ownershift(), (u32)L.self,
+                                                    (1ull << L.colbits) - 1ull, L.low + L.rowbits, (u64)ncols, padkey, d_flags,
+                                                    d_counts, which);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
 }
 
 void route_check(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &L, i64 ncols, u64 *d_err,

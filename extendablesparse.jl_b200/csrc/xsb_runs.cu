@@ -84,8 +84,15 @@ chunk_sort_kernel(Rec *buf, u64 r0, u64 r1, u32 chunk0, u32 nchunks, RunTarget r
         for (int b = 0; b < CS_NB; ++b)
             if ((u32)(b * 32 + lane) < len)
                 st_rec(rec + chunk_dest(ws.start, rs[b]), r[b]);
+        chunk_publish(ws, rt, chunk0 + c, (u32)c0, d, true, lane);
     }
-    chunk_publish(ws, rt, chunk0 + c, (u32)c0, d, grouped, lane);
+    else
+    { // no column locality in this chunk: it stays as it is, every record a run of its own
+#pragma unroll
+        for (int b = 0; b < CS_NB; ++b)
+            rs[b] = (u32)(r[b].key >> rt.colshift) & rt.gmask;
+        chunk_publish_singletons<CS_NB>(rt, chunk0 + c, (u32)c0, len, rs, lane);
+    }
 }
 
 // ------------------------------------------------------------------------
@@ -239,62 +246,77 @@ template <int HBITS, bool ASSIGN> struct ThreadFold
         for (int s = 0; s < H; ++s)
             key[s * 32] = RF_EMPTY;
     }
-    __device__ __forceinline__ void apply(u32 row, double v, u32 fl)
+    // slot of `row`: x = its accumulator, or x >= D with s the empty slot where the probe ended (an empty slot reads
+    // as index H-1 >= D).  One loop with one exit: the lanes of a warp leave it together before they touch an accumulator.
+    __device__ __forceinline__ u32 find(u32 row, u32 &s) const
     {
-        u32 s = (row * 0x9E3779B1u) >> (32 - HB);
+        const u32 tag = row << HB;
+        s = (row * 0x9E3779B1u) >> (32 - HB);
         for (;;)
         {
             const u32 kk = key[s * 32];
-            const u32 x = kk ^ (row << HB);
-            if (x < D)
-            { // same row (an empty slot reads as index H-1 >= D): x is the accumulator
-                if (ASSIGN && fl == FL_ASSIGN)
-                { // A[i,j] = v: overwrites; creates only if v != 0 (sparsematrixlnk.jl:184-199)
-                    const bool ex = (exmask >> x) & 1u;
-                    if (ex | (v != 0.0))
-                    {
-                        acc[x * 32] = v;
-                        if (!ex)
-                        {
-                            exmask |= 1u << x;
-                            --pending;
-                        }
-                    }
-                    return;
-                }
-                acc[x * 32] = acc[x * 32] + v;
-                if (pending)
-                {
-                    if (!((exmask >> x) & 1u) && ((fl != FL_UPDATE) | (v != 0.0)))
-                    {
-                        exmask |= 1u << x;
-                        --pending;
-                    }
-                }
-                return;
-            }
-            if (kk == RF_EMPTY)
-            {
-                if (d >= D)
-                {
-                    ovf = true;
-                    return;
-                }
-                key[s * 32] = (row << HB) | d;
-                rows[d * 32] = row;
-                // a run starts from +0.0 (sparsematrixlnk.jl:225) unless the resident CSC value seeds it
-                // (extendable.jl:165-166) or it is assigned; updateindex! / setindex! of a zero create
-                // nothing (:212,223,184)
-                const bool creates = (fl == FL_RAW) | (fl == FL_OLD) | (v != 0.0);
-                acc[d * 32] = (fl == FL_OLD || (ASSIGN && fl == FL_ASSIGN && creates)) ? v : 0.0 + v;
-                if (creates)
-                    exmask |= 1u << d;
-                else
-                    ++pending;
-                ++d;
-                return;
-            }
+            const u32 x = kk ^ tag;
+            if (x < D || kk == RF_EMPTY)
+                return x;
             s = (s + 1) & (H - 1);
+        }
+    }
+    // an entry of the resident CSC seeds its accumulator (extendable.jl:164-166); old rows are distinct
+    __device__ __forceinline__ void seed(u32 row, double v)
+    {
+        u32 s;
+        find(row, s);
+        if (d >= D)
+        {
+            ovf = true;
+            return;
+        }
+        key[s * 32] = (row << HB) | d;
+        rows[d * 32] = row;
+        acc[d * 32] = v;
+        exmask |= 1u << d;
+        ++d;
+    }
+    // one staged insertion (update / rawupdate / assign flavour)
+    __device__ __forceinline__ void apply(u32 row, double v, u32 fl)
+    {
+        u32 s;
+        u32 x = find(row, s);
+        if (x >= D)
+        { // first insertion of this row: a new accumulator at +0.0 (sparsematrixlnk.jl:225), not an entry yet
+            if (d >= D)
+            {
+                ovf = true;
+                return;
+            }
+            x = d++;
+            key[s * 32] = (row << HB) | x;
+            rows[x * 32] = row;
+            acc[x * 32] = 0.0;
+            ++pending;
+        }
+        if (ASSIGN && fl == FL_ASSIGN)
+        { // A[i,j] = v: overwrites; creates only if v != 0 (sparsematrixlnk.jl:184-199)
+            const bool ex = (exmask >> x) & 1u;
+            if (ex | (v != 0.0))
+            {
+                acc[x * 32] = v;
+                if (!ex)
+                {
+                    exmask |= 1u << x;
+                    --pending;
+                }
+            }
+            return;
+        }
+        acc[x * 32] = acc[x * 32] + v;
+        if (pending)
+        { // rawupdateindex! always creates the entry, updateindex! only with v != 0 (sparsematrixlnk.jl:212,223,239)
+            if (!((exmask >> x) & 1u) && ((fl != FL_UPDATE) | (v != 0.0)))
+            {
+                exmask |= 1u << x;
+                --pending;
+            }
         }
     }
     // existing entries as (row << HB | accumulator) words, insertion-sorted by row into key[0 .. j): taken in
@@ -374,26 +396,74 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
             atomicOr(d_redo, np > kMaxColPairs ? 2u : (HBITS == 6 ? 5u : 1u));
         else
         {
-            // ---- the column's runs into stream order (insertion sort in place: they arrive nearly in order)
+            // ---- the column's run descriptors, in stream order.  Up to W of them (the usual case) are loaded at
+            // once and ordered in registers by a sorting network; a column met by more chunks orders its bucket in
+            // place first (insertion sort: the descriptors arrive nearly in order) and reads it W at a time.
+            // W descriptors in registers (8; the small table shape serves short columns met by few chunks: 4)
+            constexpr int W = HBITS == 4 ? 4 : 8;
+            constexpr int DEPTH = HBITS == 4 ? 2 : 3; // sectors in flight ahead of the one being folded
             u64 *b = bucket + ps;
-            u64 prev = b[0];
-            u32 nrec = (u32)(prev & 0x7ffull);
-            for (u32 i = 1; i < np; ++i)
+            if (np > (u32)W)
             {
-                const u64 e = b[i];
-                nrec += (u32)(e & 0x7ffull);
-                if (e < prev)
+                u64 prev = b[0];
+                for (u32 i = 1; i < np; ++i)
                 {
-                    u32 q = i;
-                    while (q > 0 && b[q - 1] > e)
+                    const u64 e = b[i];
+                    if (e < prev)
                     {
-                        b[q] = b[q - 1];
-                        --q;
+                        u32 q = i;
+                        while (q > 0 && b[q - 1] > e)
+                        {
+                            b[q] = b[q - 1];
+                            --q;
+                        }
+                        b[q] = e;
                     }
-                    b[q] = e;
+                    else
+                        prev = e;
+                }
+            }
+            u64 e[W];
+            u32 loaded = 0; // descriptors fetched so far
+            auto fetch = [&]() {
+#pragma unroll
+                for (int i = 0; i < W; ++i)
+                    e[i] = loaded + (u32)i < np ? b[loaded + (u32)i] : ~0ull;
+                loaded += (u32)W;
+            };
+            fetch();
+            u32 nrec = 0;
+            if (np <= (u32)W)
+            {
+                auto cx = [&](int x, int y) {
+                    const u64 lo_ = e[x] < e[y] ? e[x] : e[y], hi_ = e[x] < e[y] ? e[y] : e[x];
+                    e[x] = lo_;
+                    e[y] = hi_;
+                };
+                if (W == 8)
+                { // 19-comparator network for 8 keys
+                    cx(0, 1), cx(2, 3), cx(4, 5), cx(6, 7);
+                    cx(0, 2), cx(1, 3), cx(4, 6), cx(5, 7);
+                    cx(1, 2), cx(5, 6), cx(0, 4), cx(3, 7);
+                    cx(1, 5), cx(2, 6);
+                    cx(1, 4), cx(3, 6);
+                    cx(2, 4), cx(3, 5);
+                    cx(3, 4);
                 }
                 else
-                    prev = e;
+                {
+                    cx(0, 1), cx(2, 3);
+                    cx(0, 2), cx(1, 3);
+                    cx(1, 2);
+                }
+#pragma unroll
+                for (int i = 0; i < W; ++i)
+                    nrec += e[i] != ~0ull ? (u32)(e[i] & 0x7ffull) : 0u;
+            }
+            else
+            { // ordered in place above: read in order
+                for (u32 i = 0; i < np; ++i)
+                    nrec += (u32)(b[i] & 0x7ffull);
             }
             if (nrec > maxlen)
                 atomicOr(d_redo, 2u); // a very long column would stall its warp: the caller takes another path
@@ -401,55 +471,69 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
             {
                 f.init();
                 // ---- the resident column seeds the table (CSC hits: extendable.jl:164-166)
-                for (i64 e = os; e < oe; ++e)
-                    f.apply((u32)((i64)old_rowval[e] - (i64)base), old_nzval[e], FL_OLD);
+                for (i64 eo = os; eo < oe; ++eo)
+                    f.seed((u32)((i64)old_rowval[eo] - (i64)base), old_nzval[eo]);
                 // ---- the runs, where the producers left them.  Every step a lane takes the aligned 32-byte
                 // sector (two records, one LDG.256) its cursor stands in and folds the one or two records of it
                 // that belong to its run: the same instruction stream for every lane whatever the run lengths;
-                // two sectors travel ahead of the one being folded.
+                // DEPTH sectors travel ahead of the one being folded.
                 // Positions are counted in records from the 32-byte boundary at or below buf: their parity is the
                 // record's place inside its sector.
                 const uintptr_t bufa = reinterpret_cast<uintptr_t>(buf);
                 const u32 bias = (u32)(bufa >> 4) & 1u;
                 const unsigned char *base32 = reinterpret_cast<const unsigned char *>(bufa & ~(uintptr_t)31);
-                u32 ri = 0, rem = 0, left = nrec, pos = 0;
-                RecPair q0, q1, q2;
-                u32 m0, m1, m2;
-                auto gen = [&](RecPair &q, u32 &m) {
+                u32 used = 0, rem = 0, left = nrec, pos = 0; // used: descriptors of the register window consumed
+                RecPair q[DEPTH];
+                u32 m[DEPTH];
+                auto gen = [&](RecPair &qq, u32 &mm) {
                     if (left == 0u)
                     {
-                        m = 0u;
+                        mm = 0u;
                         return;
                     }
                     if (rem == 0u)
-                    {
-                        const u64 e = b[ri++];
-                        pos = (u32)(e >> 11) + bias;
-                        rem = (u32)(e & 0x7ffull);
+                    { // next run: the head of the register window
+                        if (used == (u32)W)
+                        {
+                            fetch();
+                            used = 0u;
+                        }
+                        pos = (u32)(e[0] >> 11) + bias;
+                        rem = (u32)(e[0] & 0x7ffull);
+#pragma unroll
+                        for (int i = 0; i + 1 < W; ++i)
+                            e[i] = e[i + 1];
+                        ++used;
                     }
-                    m = (pos & 1u) ? 2u : (rem > 1u ? 3u : 1u); // which records of the sector belong to the run
-                    const u32 take = (m + 1u) >> 1;
-                    q = ld_pair_stream(reinterpret_cast<const Rec *>(base32 + (size_t)(pos >> 1) * 32u));
+                    mm = (pos & 1u) ? 2u : (rem > 1u ? 3u : 1u); // which records of the sector belong to the run
+                    const u32 take = (mm + 1u) >> 1;
+                    qq = ld_pair_stream(reinterpret_cast<const Rec *>(base32 + (size_t)(pos >> 1) * 32u));
                     pos += take;
                     rem -= take;
                     left -= take;
                 };
-                gen(q0, m0);
-                gen(q1, m1);
-                gen(q2, m2);
-                while (m0 != 0u && !f.ovf)
+#pragma unroll
+                for (int k = 0; k < DEPTH; ++k)
+                    gen(q[k], m[k]);
+                // one step: fold the records of sector k, then send its buffer for the sector DEPTH ahead
+                for (bool done = false; !done;)
                 {
-                    const RecPair c = q0;
-                    const u32 m = m0;
-                    q0 = q1;
-                    m0 = m1;
-                    q1 = q2;
-                    m1 = m2;
-                    gen(q2, m2);
-                    if (m & 1u)
-                        f.apply((u32)(c.a.key >> low) & rowmask, c.a.val, (u32)c.a.key & 3u);
-                    if ((m & 2u) && !f.ovf)
-                        f.apply((u32)(c.b.key >> low) & rowmask, c.b.val, (u32)c.b.key & 3u);
+#pragma unroll
+                    for (int k = 0; k < DEPTH; ++k)
+                    {
+                        if (m[k] == 0u || f.ovf)
+                        {
+                            done = true;
+                            break;
+                        }
+                        const RecPair c = q[k];
+                        const u32 mm = m[k];
+                        gen(q[k], m[k]);
+                        if (mm & 1u)
+                            f.apply((u32)(c.a.key >> low) & rowmask, c.a.val, (u32)c.a.key & 3u);
+                        if ((mm & 2u) && !f.ovf)
+                            f.apply((u32)(c.b.key >> low) & rowmask, c.b.val, (u32)c.b.key & 3u);
+                    }
                 }
                 if (f.ovf)
                 { // bit 2: not even the largest table takes this column

@@ -197,68 +197,100 @@ void count_missing_records(cudaStream_t stream, const Rec *recs, i64 count, cons
 // sorted (slot,index) records -> perm[] and segstart[0..nnz]
 __global__ void __launch_bounds__(256)
 frozen_map_kernel(const Rec *__restrict__ sorted, i64 count, i64 nnz, u32 *__restrict__ perm,
-                  i64 *__restrict__ segstart)
+                  u32 *__restrict__ segstart, u32 *__restrict__ slot32)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride)
     {
         const Rec r = sorted[s];
-        perm[s] = (u32) * reinterpret_cast<const u64 *>(&r.val);
+        const u32 k = (u32) * reinterpret_cast<const u64 *>(&r.val); // position in the stream
+        perm[s] = k;
         const i64 z = (i64)r.key;
+        slot32[k] = (u32)z; // the 4-byte entry -> nzval map of the stream (fast mode)
         const i64 zprev = s > 0 ? (i64)sorted[s - 1].key : -1;
         // slots zprev+1 .. z start at s (slots without entries get an empty range)
         for (i64 q = zprev + 1; q <= z; ++q)
-            segstart[q] = s;
+            segstart[q] = (u32)s;
         if (s == count - 1)
             for (i64 q = z + 1; q <= nnz; ++q)
-                segstart[q] = count;
+                segstart[q] = (u32)count;
     }
 }
 
-void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, i64 *segstart,
+void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz, u32 *perm, u32 *segstart, u32 *slot32,
                       LaunchCounter &lc)
 {
     if (count <= 0)
     {
-        XSB_CUDA(cudaMemsetAsync(segstart, 0, sizeof(i64) * (size_t)(nnz + 1), stream));
+        XSB_CUDA(cudaMemsetAsync(segstart, 0, sizeof(u32) * (size_t)(nnz + 1), stream));
         return;
     }
-    frozen_map_kernel<<<grid_for(count, 256), 256, 0, stream>>>(sorted, count, nnz, perm, segstart);
+    frozen_map_kernel<<<grid_for(count, 256), 256, 0, stream>>>(sorted, count, nnz, perm, segstart, slot32);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }
 
-// nzval[z] = ((nzval[z] + V[p0]) + V[p1]) + ...  in stream order: bit-exact with the
-// reference's in-place CSC-hit updates (extendable.jl:164-166)
-__global__ void __launch_bounds__(256)
-reassemble_det_kernel(const double *__restrict__ V, const u32 *__restrict__ perm,
-                      const i64 *__restrict__ segstart, i64 nnz, double *__restrict__ nzval)
+// nzval[z] = ((nzval[z] + V[p0]) + V[p1]) + ...  in stream order: bit-exact with the reference's in-place CSC-hit
+// updates (extendable.jl:164-166).  A warp owns 32 consecutive entries.  Their values -- one contiguous piece of
+// the permutation built at freeze time -- are gathered by the whole warp into shared memory (coalesced reads of the
+// permutation, all the 8-byte gathers of V in flight at once), then every lane folds its own entry in order from
+// there: the dependent chain of additions never waits for HBM.  ZERO: the entries start from +0.0 instead of the
+// resident value (nonzeros(A) .= 0 fused in: nzval is written, never read).
+constexpr int RA_WARPS = 8;
+constexpr int RA_CAP = 512; // values a warp stages per round
+
+template <bool ZERO>
+__global__ void __launch_bounds__(RA_WARPS * 32)
+reassemble_warp_kernel(const double *__restrict__ V, const u32 *__restrict__ perm, const u32 *__restrict__ segstart,
+                       i64 nnz, double *__restrict__ nzval)
 {
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 z = (i64)blockIdx.x * blockDim.x + threadIdx.x; z < nnz; z += stride)
+    __shared__ double s_val[RA_WARPS][RA_CAP];
+    constexpr u32 full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *vals = s_val[warp];
+    const i64 nwarps = (nnz + 31) / 32;
+    for (i64 w = (i64)blockIdx.x * RA_WARPS + warp; w < nwarps; w += (i64)gridDim.x * RA_WARPS)
     {
-        const i64 s0 = segstart[z], s1 = segstart[z + 1];
-        if (s1 == s0)
-            continue;
-        double acc = nzval[z];
-        for (i64 s = s0; s < s1; ++s)
-            acc = acc + __ldg(V + perm[s]);
-        nzval[z] = acc;
+        const i64 z = w * 32 + lane;
+        const u32 a = z < nnz ? segstart[z] : 0u, b = z < nnz ? segstart[z + 1] : 0u;
+        const u32 w0 = __shfl_sync(full, a, 0);
+        const u32 w1 = __reduce_max_sync(full, b); // segstart is non-decreasing: the end of the warp's last entry
+        double acc = (ZERO || z >= nnz || a == b) ? 0.0 : nzval[z];
+        u32 cur = a; // next value of this lane's entry
+        for (u32 c0 = w0; c0 < w1; c0 += RA_CAP)
+        {
+            const u32 c1 = min(c0 + (u32)RA_CAP, w1);
+            for (u32 k = c0 + lane; k < c1; k += 32)
+                vals[k - c0] = __ldg(V + perm[k]);
+            __syncwarp();
+            const u32 e = min(b, c1);
+            for (; cur < e; ++cur)
+                acc = acc + vals[cur - c0];
+            __syncwarp();
+        }
+        if (z < nnz && (ZERO || a != b))
+            nzval[z] = acc;
     }
 }
 
-void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *perm, const i64 *segstart,
-                              i64 nnz, double *nzval, LaunchCounter &lc)
+void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *perm, const u32 *segstart, i64 nnz,
+                              double *nzval, bool zero_first, LaunchCounter &lc)
 {
     if (nnz <= 0)
         return;
-    reassemble_det_kernel<<<grid_for(nnz, 256, 32), 256, 0, stream>>>(V, perm, segstart, nnz, nzval);
+    const i64 nwarps = (nnz + 31) / 32;
+    const int blocks = (int)std::min<i64>((nwarps + RA_WARPS - 1) / RA_WARPS, (i64)kNumSM * 32);
+    if (zero_first)
+        reassemble_warp_kernel<true><<<blocks, RA_WARPS * 32, 0, stream>>>(V, perm, segstart, nnz, nzval);
+    else
+        reassemble_warp_kernel<false><<<blocks, RA_WARPS * 32, 0, stream>>>(V, perm, segstart, nnz, nzval);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }
 
+// fast mode: one atomic add per insertion through the 4-byte entry -> nzval map, in whatever order the hardware takes
 __global__ void __launch_bounds__(256)
-reassemble_fast_kernel(const double *__restrict__ V, const i64 *__restrict__ slot, i64 count,
+reassemble_fast_kernel(const double *__restrict__ V, const u32 *__restrict__ slot, i64 count,
                        double *__restrict__ nzval)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
@@ -266,7 +298,7 @@ reassemble_fast_kernel(const double *__restrict__ V, const i64 *__restrict__ slo
         atomicAdd(nzval + slot[k], V[k]);
 }
 
-void reassemble_fast(cudaStream_t stream, const double *V, const i64 *slot, i64 count, double *nzval,
+void reassemble_fast(cudaStream_t stream, const double *V, const u32 *slot, i64 count, double *nzval,
                      LaunchCounter &lc)
 {
     if (count <= 0)
@@ -376,6 +408,46 @@ pattern_hash_kernel(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval
         acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc)
         atomicAdd(d_hash, acc);
+}
+
+// pattern_equal(a, b): a.colptr == b.colptr && a.rowval == b.rowval (sparsematrixcsc.jl:83-85); counts the differing
+// positions (index bases may differ: both patterns are compared 0-based)
+template <typename Ta, typename Tb>
+__global__ void __launch_bounds__(256)
+pattern_diff_kernel(const Ta *__restrict__ cpa, const Ta *__restrict__ rva, Ta basea, const Tb *__restrict__ cpb,
+                    const Tb *__restrict__ rvb, Tb baseb, i64 n, i64 nnz, u64 *__restrict__ d_diff)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    u32 bad = 0;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n + 1 + nnz; k += stride)
+    {
+        const i64 a = k <= n ? (i64)cpa[k] - (i64)basea : (i64)rva[k - n - 1] - (i64)basea;
+        const i64 b = k <= n ? (i64)cpb[k] - (i64)baseb : (i64)rvb[k - n - 1] - (i64)baseb;
+        bad += a != b;
+    }
+    if (bad)
+        atomicAdd(reinterpret_cast<unsigned long long *>(d_diff), (unsigned long long)bad);
+}
+
+void pattern_diff(cudaStream_t stream, const CscView &a, int idx64a, int basea, const CscView &b, int idx64b, int baseb,
+                  i64 n, u64 *d_diff, LaunchCounter &lc)
+{
+    const int blocks = grid_for(n + 1 + a.nnz, 256);
+#define XSB_PD(TA, TB)                                                                                               \
+    pattern_diff_kernel<TA, TB><<<blocks, 256, 0, stream>>>((const TA *)a.colptr, (const TA *)a.rowval, (TA)basea,      \
+                                                            (const TB *)b.colptr, (const TB *)b.rowval, (TB)baseb, n,   \
+                                                            a.nnz, d_diff)
+    if (idx64a && idx64b)
+        XSB_PD(int64_t, int64_t);
+    else if (idx64a)
+        XSB_PD(int64_t, int32_t);
+    else if (idx64b)
+        XSB_PD(int32_t, int64_t);
+    else
+        XSB_PD(int32_t, int32_t);
+#undef XSB_PD
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
 }
 
 void pattern_hash(cudaStream_t stream, const CscView &csc, i64 n, int idx64, u64 *d_hash, LaunchCounter &lc)

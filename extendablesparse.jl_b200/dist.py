@@ -177,6 +177,30 @@ class DistExtendableSparseMatrix:
         self._resolve_offsets()
         return self._changed_any
 
+    def mul(self, x_local, out=None):
+        """y = A * x for the matrix sharded by column slabs: rank r holds x[col_begin:col_end] and computes its slab's
+        contribution A[:, slab] * x[slab] with the column-order kernel (xsb_mul: every y_i a left fold over the slab's
+        columns, separately rounded products); the contributions are then summed over the ranks in RANK ORDER,
+        y = ((y_0 + y_1) + y_2) + ..., on every rank, from one all-gather -- so all ranks hold the same bits and the
+        result does not depend on the collective's internal reduction tree.  Reference: the partition loop of
+        mul!(r, ext::GenericMTExtendableSparseMatrixCSC, x) (genericmtextendablesparsematrixcsc.jl:124-143), whose
+        row partitions write disjoint parts of r; with column slabs the parts overlap and are added in slab order.
+        Against the single-process column-order sum this re-associates the additions at the slab boundaries only
+        (|error| <= (ranks-1) ulps of the partial sums); patterns whose rows never span two slabs give identical bits."""
+        y = torch.empty(self.m, dtype=torch.float64, device=self.device) if self.device.type == "cuda" else None
+        if y is None:
+            import numpy as np
+
+            y = torch.from_numpy(self.h.mul(np.ascontiguousarray(x_local)))
+        else:
+            self.h.mul(x_local, y)
+        parts = torch.empty((self.world, self.m), dtype=torch.float64, device=y.device)
+        dist.all_gather_into_tensor(parts.view(-1), y, group=self.group)
+        acc = parts[0].clone() if out is None else out.copy_(parts[0])
+        for r in range(1, self.world):
+            acc += parts[r]
+        return acc
+
     def global_colptr(self, local_colptr):
         """Slab colptr (slab_width+1 entries) shifted to index the global rowval/nzval arrays."""
         return local_colptr + self.nnz_offset

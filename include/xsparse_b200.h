@@ -26,9 +26,18 @@
  *    xsb_fetch_csc).
  *  - Index arrays have the element type `idx_type` and the base `index_base`
  *    chosen at creation (Julia: XSB_I64, base 1).  Values are Float64.
- *  - Calls on one handle must not overlap, except xsb_insert_batch /
- *    xsb_insert_triplets / xsb_emit_* with DISTINCT `tid` (the reference's
- *    threading contract, test/femtools.jl:88-105).
+ *  - Threading: every call locks its handle, so calls on one handle from several
+ *    threads are safe and run one after the other.  What the reference's contract
+ *    needs (test/femtools.jl:88-105) -- xsb_insert_batch / xsb_insert_triplets /
+ *    xsb_emit_* issued concurrently with DISTINCT `tid` -- therefore works; the
+ *    order in which such calls reach a partition's buffer is the order in which its
+ *    own thread issued them.  flush!/reset! are expected from one thread while no
+ *    insertion is in flight (test/femtools.jl:109), as in the reference.
+ *  - Streams: all work of a handle runs on the handle's own non-blocking CUDA stream
+ *    (xsb_get_stream).  DEVICE-pointer arguments (I/J/V, triplets, x, received records,
+ *    markers) are read on that stream: the caller must have finished writing them
+ *    (synchronise the producing stream, or make it wait on an event) before the call.
+ *    HOST-pointer arguments are copied before the call returns.
  *  - There is no CPU fallback: without a CUDA device xsb_create fails with
  *    XSB_ECUDA.
  */
@@ -65,7 +74,10 @@ extern "C" {
 
 /* summation modes */
 #define XSB_DETERMINISTIC 0 /* left fold in insertion order: bit-exact with the reference   */
-#define XSB_FAST 1          /* warp-shuffle tree per duplicate run: <= 1e-14 relative (f64) */
+#define XSB_FAST 1          /* summation order free: <= 1e-14 relative (f64), pattern bit-exact.  xsb_flush: duplicates
+                               may be accumulated per chunk of the stream before the per-column merge (off unless
+                               xsb_set_preaggregation; otherwise the exact merge runs); xsb_reassemble_values: one
+                               atomic add per insertion instead of the ordered per-entry fold */
 
 /* how resident CSC values combine with new duplicates */
 #define XSB_COMBINE_SEED 0 /* ((old + v1) + v2)...  the wrapper's CSC-hit branch, extendable.jl:164-166 */
@@ -83,7 +95,9 @@ typedef struct xsb_flush_stats
     int32_t sort_bits;        /* key bits sorted                       */
     int32_t kernel_launches;  /* kernels launched by the flush         */
     int32_t column_path;      /* 0: (col,row) sort + flat reduction; 1: column sort + in-tile row ordering;
-                                 2: column sort + hash fold; 3: two-pass grouping by column + hash fold */
+                                 2: column sort + hash fold; 3: two-pass grouping by column + hash fold;
+                                 4: grouped chunks (records grouped by column while they were staged) +
+                                    thread-per-column merge with the resident CSC -- the product path */
     float ms_total;           /* device time of the whole flush (CUDA events; 0 unless profiling on) */
     float ms_expand;          /* old CSC -> records                    */
     float ms_histogram;       /* digit histogram + scan                */
@@ -102,8 +116,8 @@ typedef struct xsb_flush_stats
     int32_t direct_fold;      /* 1: the fold wrote rowval / nzval / colptr in one pass (no park + compact) */
     int64_t preagg_records;   /* XSB_FAST: staged records left after accumulate-on-insert in windows; 0: not used */
     float ms_preagg;          /* ... and its device time (also inside ms_total)                */
-    float precounted;         /* share of the staged records whose column histograms (grouping pass 1) were
-                                 taken by the kernels that staged them; ms_group_count covers the rest */
+    float precounted;         /* share of the staged records whose chunks were grouped by column by the kernels that
+                                 staged them; ms_group_count covers the rest (grouped in place by the flush) */
 } xsb_flush_stats;
 
 /* ------------------------------------------------------------------ */
@@ -222,8 +236,13 @@ int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_recor
  * (the CSC-hit branch extendable.jl:164-166 resolved once instead of per insert).
  * Every (i,j) must already be in the pattern, else XSB_EILLEGAL. */
 int32_t xsb_freeze_pattern(xsb_matrix *h, const void *I, const void *J, int64_t count);
-/* nzval[slot(k)] += V[k] for the frozen stream; deterministic mode folds in stream order. */
+/* nzval[slot(k)] += V[k] for the frozen stream; deterministic mode folds every entry's values in stream order,
+ * starting from the resident value (bit-exact with the in-place CSC-hit updates); fast mode is one atomic add
+ * per insertion through the 4-byte entry -> nzval map. */
 int32_t xsb_reassemble_values(xsb_matrix *h, const void *V, int64_t count, int32_t mode);
+/* nonzeros(A) .= 0 (sprand.jl:80-85, test_parallel.jl:55) followed by xsb_reassemble_values, as ONE pass: the
+ * entries start from +0.0 and nzval is written, never read (a Newton / time step re-assembles from zero). */
+int32_t xsb_reassemble_values_zeroed(xsb_matrix *h, const void *V, int64_t count, int32_t mode);
 int32_t xsb_unfreeze(xsb_matrix *h);
 
 /* y = A*x on the resident CSC (x: n values, y: m values; host or device pointers).  mul!(r,A,x):
@@ -243,6 +262,12 @@ int32_t xsb_eliminate_dirichlet(xsb_matrix *h, const uint8_t *marker);
 /* 64-bit fingerprint of (colptr,rowval): stands in for phash (sparsematrixcsc.jl:74);
  * equal patterns give equal values, it is NOT Julia's hash(). */
 int32_t xsb_pattern_hash(xsb_matrix *h, uint64_t *hash_out);
+
+/* pattern_equal(a, b): src/matrix/sparsematrixcsc.jl:77-85 -- a.colptr == b.colptr && a.rowval == b.rowval, compared
+ * element by element on the device (exact, unlike comparing two xsb_pattern_hash values); matrices of different size
+ * or nnz are unequal.  Both matrices flushed (XSB_ESTATE otherwise).  Handles on different devices fall back to
+ * comparing fingerprints. */
+int32_t xsb_pattern_equal(xsb_matrix *a, xsb_matrix *b, int32_t *equal_out);
 
 /* pointblock(A, blocksize): src/matrix/extendable.jl:292-318 (feeds PointBlockILUZeroPreconditioner,
  * src/factorizations/iluzero.jl:61-71).  Returns a NEW handle *out holding the nblock x nblock block
@@ -327,10 +352,12 @@ int32_t xsb_set_grouping(xsb_matrix *h, int32_t grouping);
  * values <= 1e-14 relative, summation order not reproducible from run to run.  Off by default:
  * on B200 it only pays when the windows shrink the stream more than about 3x. */
 int32_t xsb_set_preaggregation(xsb_matrix *h, int32_t enable);
-/* Counting at insertion (default on): the kernels behind xsb_insert_batch / xsb_insert_triplets /
- * xsb_emit_p1fem also take the per-chunk column histograms the flush's grouping needs, while the
- * records are in registers, so the flush does not read them once more just to count.  Applies to
- * single-partition handles assembling from an empty CSC; results are identical either way. */
+/* Grouping at insertion (default on): the kernels behind xsb_insert_batch / xsb_insert_triplets / xsb_emit_* bring
+ * every chunk of ~512 consecutive insertions into column order while its records are in registers or shared memory
+ * and publish where each column's records lie; xsb_flush then reads them in place and never moves a record.  Off:
+ * records are staged in call order and the flush groups the chunks itself (one more read + write of the records).
+ * Applies to partition 0 of single-partition handles (slab handles included); results are identical either way.
+ * xsb_debug_fetch_staged returns grouped chunks in their grouped order. */
 int32_t xsb_set_precount(xsb_matrix *h, int32_t enable);
 int32_t xsb_get_flush_stats(const xsb_matrix *h, xsb_flush_stats *out);
 /* Total kernels launched by this handle since creation. */

@@ -157,6 +157,9 @@ def test_newton_loop_fd200_values_only(xsb, torch):
         h.reassemble_values(dVn, xsb.DETERMINISTIC, count=len(dVn))
         _, _, nz = device_csc(torch, h)
         assert torch.equal(nz.view(torch.int64), ref.view(torch.int64)), f"re-assembly {seed} not bit-exact"
+        h.reassemble_values(dVn, xsb.DETERMINISTIC, count=len(dVn), zero_first=True)  # nonzeros .= 0 fused in
+        _, _, nz = device_csc(torch, h)
+        assert torch.equal(nz.view(torch.int64), ref.view(torch.int64)), f"zeroed re-assembly {seed} not bit-exact"
         h.zero_values()
         h.reassemble_values(dVn, xsb.FAST, count=len(dVn))
         _, _, nzf = device_csc(torch, h)
@@ -218,6 +221,11 @@ def test_cfg3_fd200_build_and_reassembly_equal_oracle(xsb, oracle):
     h.zero_values()
     h.reassemble_values(V2, xsb.DETERMINISTIC)
     _assert_equals_oracle(h, A.csc(), "cfg3 re-assembly")
+    h.reassemble_values(V2, xsb.DETERMINISTIC, zero_first=True)
+    _assert_equals_oracle(h, A.csc(), "cfg3 re-assembly (zeroed)")
+    h.reassemble_values(V, xsb.DETERMINISTIC)  # on top of the resident values: ((old + v1) + v2) ...
+    A.insert_batch(I, J, V, oracle.UPDATE)
+    _assert_equals_oracle(h, A.csc(), "cfg3 accumulate onto resident values")
     h.close()
 
 

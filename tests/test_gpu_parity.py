@@ -486,6 +486,11 @@ def test_frozen_reassembly(xsb, oracle, dims):
         A.zero_values()
         A.insert_batch(I, J, Vn, oracle.UPDATE)
         assert_csc_equal(h.fetch_csc_numpy(), A.csc(), exact=False, rtol=1e-14)
+        # nonzeros(A) .= 0 fused into the re-assembly (xsb_reassemble_values_zeroed): same bits as the two calls
+        h.reassemble_values(Vn, xsb.DETERMINISTIC, zero_first=True)
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc())
+        h.reassemble_values(Vn, xsb.FAST, zero_first=True)
+        assert_csc_equal(h.fetch_csc_numpy(), A.csc(), exact=False, rtol=1e-14)
     assert h.pattern_hash() == hash0
     # the same re-assembly through the general path (keys re-searched) gives the same bits
     h.zero_values()
@@ -1102,6 +1107,37 @@ def test_column_met_by_many_chunks_uses_pair_sort(xsb, oracle):
     h.flush()
     st = h.flush_stats()
     assert st["column_path"] == 4 and st["sort_passes"] == 0
+    h.close()
+
+
+@pytest.mark.parametrize("stream,batch", [("fd", 700), ("fd", 96), ("fem", 300), ("fem", 64)])
+def test_columns_met_by_many_small_chunks(xsb, oracle, stream, batch):
+    """Small insertion batches make small chunks: a column then collects more run descriptors than the merge kernel
+    keeps in registers (4 with the small table shape, 8 otherwise) and orders its bucket in place instead."""
+    if stream == "fd":
+        nx = 24
+        n = nx ** 3
+        I, J, V = oracle.fdrand_stream(nx, nx, nx, seed=11)
+        fl, ofl = xsb.UPDATE, oracle.UPDATE
+    else:
+        n1 = 16
+        n = n1 ** 3
+        I, J, V = oracle.fem_stream(n1, n1, n1)
+        fl, ofl = xsb.RAW, oracle.RAW
+    A = oracle.OracleExt(n, n)
+    A.insert_batch(I, J, V, ofl)
+    ref = A.csc()
+    h = xsb.Handle(n, n)
+    for rnd in range(2):  # second round: the table shape follows the first flush's hint
+        h.reset()
+        h.reserve(0, len(V))
+        for a in range(0, len(V), batch * 37):
+            b = min(a + batch * 37, len(V))
+            for c in range(a, b, batch):
+                h.insert_batch(I[c:min(c + batch, b)], J[c:min(c + batch, b)], V[c:min(c + batch, b)], fl)
+        h.flush()
+        assert h.flush_stats()["column_path"] == 4
+        assert_csc_equal(h.fetch_csc_numpy(), ref)
     h.close()
 
 
