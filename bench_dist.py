@@ -1,11 +1,14 @@
-"""N>1 arm of bench.py: weak scaling of the partitioned FEM assembly over column-owning ranks.
+"""N>1 arm of bench.py: weak scaling of the partitioned FEM assembly over column-owning ranks, plus
+BASELINE.json configs[4] (fdrand 400^3, strong scaling) as the `cfg5` key of the same line.
 
 Global mesh: 128 x 128 x (127*N + 1) nodes (Kuhn 6-tet).  Rank r emits the tetrahedra of its
 127 cube layers (245 805 960 rawupdateindex! calls, the same per-GPU work as the N=1 workload)
 and owns the columns of the z-planes [127 r, 127 (r+1)) (the last rank also owns the top plane).
 Records whose column lies on the interface plane travel to the rank above in one NCCL
-all-to-all-v; every rank then merges into its own CSC slab.  The assembled matrix is left
-sharded (slab-local colptr + global offset); that is what is timed.
+all-to-all; every rank then merges into its own CSC slab.  The assembled matrix is left
+sharded (slab-local colptr + global offset); that is what is timed.  The first (warm-up) step
+counts what every rank sends; the following steps use the fixed-capacity exchange
+(xsb_route_pack / xsb_route_unpack): no count visits the host, one collective per step.
 """
 from __future__ import annotations
 
@@ -17,6 +20,44 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(local):
+    """Pins this rank (and therefore the pinned host buffers it allocates afterwards: first touch) to the CPUs next
+    to its GPU.  Returns a short description for the bench line."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = open(f"{base}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = ids & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"gpu": bdf, "numa_node": node, "cpus": cpus, "bound": bool(allowed)}
+    except Exception as e:  # noqa: BLE001  (containers without sysfs: run unbound)
+        return {"bound": False, "why": str(e)[:80]}
+
+
+def timed_steps(h, step, steps, dev):
+    """K steps on the device clock (CUDA events on the library's stream), barrier + synchronise on both sides, max over ranks."""
+    h.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    h.timer_start()
+    for _ in range(steps):
+        step()
+    ms_local = h.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    return float(tmax.item()) / steps
+
+
 def run(args, xsb, rank, world, local):
     import bench
 
@@ -24,13 +65,20 @@ def run(args, xsb, rank, world, local):
     import faulthandler
     import sys
 
-    faulthandler.dump_traceback_later(int(os.environ.get("XSB_BENCH_WATCHDOG_S", "240")), exit=True, file=sys.stderr)
+    faulthandler.dump_traceback_later(int(os.environ.get("XSB_BENCH_WATCHDOG_S", "400")), exit=True, file=sys.stderr)
+    numa = bind_to_gpu_numa(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from xsparse_b200 import dist as xd
 
     dev = torch.device("cuda", local)
     if getattr(args, "workload", "fem") == "fd400":
-        return run_fd(args, xsb, xd, bench, rank, world, local, dev)
+        line = run_fd(args, xsb, xd, bench, rank, world, local, dev)
+        if rank == 0:
+            print(json.dumps(line))
+        dist.barrier()
+        dist.destroy_process_group()
+        faulthandler.cancel_dump_traceback_later()
+        return
     nx = ny = args.mesh
     layers = args.mesh - 1
     nz_nodes = layers * world + 1
@@ -40,77 +88,78 @@ def run(args, xsb, rank, world, local):
     mode = xsb.DETERMINISTIC if args.mode == "deterministic" else xsb.FAST
     D = xd.DistExtendableSparseMatrix(N, N, splits=splits, device=local)
     h = D.h
-    h.set_profiling(True)
     n_ins_rank = xsb.capi.stream_count_p1fem(nx, ny, layers + 1)
+
+    def emit():
+        h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
 
     def step():
         h.reset()
-        h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
+        emit()
         return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
     for _ in range(args.warmup):
         step()
-    h.synchronize()
-    torch.cuda.synchronize()
-    dist.barrier()
     launches0 = h.kernel_launches
-    stage = {}
     with bench.ClockSampler(local) as clk:
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        h.timer_start()  # CUDA events on the stream the library launches on
-        for _ in range(args.steps):
-            nnz, _ = step()
-            st = h.flush_stats()
-            for k, v in st.items():
-                if k.startswith("ms_"):
-                    stage[k] = stage.get(k, 0.0) + v
-        ms_local = h.timer_stop()
-        torch.cuda.synchronize()
-        dist.barrier()
+        ms_step = timed_steps(h, step, args.steps, dev)
         launches_timed = h.kernel_launches - launches0
-        # max over ranks, on the device clock
-        tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
         # keep the clock sampler busy for about half a second: the SAME number of extra steps on every rank
         # (a step holds collectives; a per-rank time limit would let the ranks disagree and hang)
-        n_fill = int(max(0.0, 500.0 - ms) / max(ms / args.steps, 1e-3)) + 1
+        n_fill = int(max(0.0, 500.0 - ms_step * args.steps) / max(ms_step, 1e-3)) + 1
         for _ in range(min(n_fill, 200)):
             step()
         torch.cuda.synchronize()
         dist.barrier()
     launches = torch.tensor([launches_timed], dtype=torch.int64, device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    st = h.flush_stats()
-    ms_step = ms / args.steps
     value = world * n_ins_rank / (ms_step / 1e3)
     peak, peak_src = bench.peaks()
-    roof = bench.roofline(st, {k: v / args.steps for k, v in stage.items()}, None, h.n, peak, peak_src, None)
+    # stage times of rank 0 (profiled steps: CUDA events around every stage of the flush; not the headline timing)
+    h.set_profiling(True)
+    stage, ms_emit = {}, 0.0
+    prof_steps = min(args.steps, 3)
+    st = None
+    for _ in range(prof_steps):
+        h.reset()
+        h.timer_start()
+        emit()
+        ms_emit += h.timer_stop()
+        D.flush(mode, wait=False)
+        st = h.flush_stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage[k] = stage.get(k, 0.0) + v
+    h.set_profiling(False)
+    roof = bench.roofline(st, {k: v / prof_steps for k, v in stage.items()}, ms_emit / prof_steps, h.n, peak, peak_src, None)
     roof["kernel"] += " [rank 0]"
+    exchange = dict(D.last_exchange)
+    nnz_global = int(D.nnz_global)
+    h.close()
+    del D
 
+    cfg5 = None
+    if not args.no_legs:
+        cfg5 = run_fd(args, xsb, xd, bench, rank, world, local, dev)
     e2e = measure_e2e(args, xsb, xd, rank, world, local, mode)
     clocks = clk.summary()
     if rank == 0:
         cfg = bench.workload(args)
         cfg["workload"] = (f"P1-FEM Laplacian+mass, {nx}x{ny}x{nz_nodes}-node Kuhn mesh sharded over {world} ranks "
                            f"({layers} cube layers = {n_ins_rank} rawupdateindex! calls per rank), column-slab ownership, "
-                           f"NCCL all-to-all-v of the interface plane, CSC left sharded")
+                           f"ONE NCCL all-to-all of fixed-capacity blocks per step (interface plane), CSC left sharded")
         cfg["parallelism"] = f"column-slab x{world}"
-        cfg["exchange"] = dict(D.last_exchange)
-        cfg["host_phase_ms_last_step"] = dict(zip(["route_count", "copy_out", "all_to_all", "append", "flush", "offsets"],
-                                                  [round(x, 3) for x in D.last_phase_ms]))
+        cfg["exchange"] = exchange
+        cfg["numa"] = numa
         line = {
             "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "roofline": roof,
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clocks,
-            "nnz_global": int(D.nnz_global), "n_inserted": int(world * n_ins_rank),
+            "nnz_global": nnz_global, "n_inserted": int(world * n_ins_rank), "cfg5": cfg5,
         }
         print(json.dumps(line))
-    h.close()
     dist.barrier()
     dist.destroy_process_group()
     faulthandler.cancel_dump_traceback_later()
@@ -118,7 +167,8 @@ def run(args, xsb, rank, world, local):
 
 def measure_e2e(args, xsb, xd, rank, world, local, mode):
     """End to end at N ranks with HOST buffers: every step each rank copies its insertion stream (16-byte
-    triplets) from pinned host memory, inserts, routes, flushes and reads its CSC slab back to pinned host memory."""
+    triplets) from pinned host memory (allocated after the rank was bound to its GPU's NUMA node), inserts,
+    routes, flushes and reads its CSC slab back to pinned host memory."""
     import ctypes as C
 
     emesh = args.e2e_mesh
@@ -161,19 +211,9 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
 
     step()
     steps = max(1, min(args.steps, 3))
-    torch.cuda.synchronize()
-    dist.barrier()
-    g.timer_start()
-    for _ in range(steps):
-        step()
-    ms_e2e = g.timer_stop()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t = torch.tensor([ms_e2e / steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = timed_steps(g, step, steps, torch.device("cuda", local))
     tot = torch.tensor([cnt, 16 * cnt, 8 * (g.n + 1) + 16 * int(nnz)], dtype=torch.int64, device="cuda")
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms = float(t.item())
     g.close()
     return {"value": int(tot[0].item()) / (ms / 1e3), "unit": "entries/s", "h2d_bytes_per_step": int(tot[1].item()),
             "d2h_bytes_per_step": int(tot[2].item()), "ms_per_step": ms,
@@ -191,7 +231,6 @@ def run_fd(args, xsb, xd, bench, rank, world, local, dev):
     mode = xsb.DETERMINISTIC if args.mode == "deterministic" else xsb.FAST
     D = xd.DistExtendableSparseMatrix(N, N, splits=splits, device=local)
     h = D.h
-    h.set_profiling(True)
     n_ins = xsb.capi.stream_count_fdrand(n1, n1, n1)
 
     def step():
@@ -199,40 +238,27 @@ def run_fd(args, xsb, xd, bench, rank, world, local, dev):
         h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=(splits[rank], splits[rank + 1]))
         return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
-    for _ in range(args.warmup):
+    for _ in range(max(2, min(args.warmup, 3))):
         step()
-    h.synchronize()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    h.timer_start()
-    for _ in range(args.steps):
-        nnz, _ = step()
-    ms_local = h.timer_stop()
-    torch.cuda.synchronize()
-    dist.barrier()
-    tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / args.steps
+    steps = max(1, min(args.steps, 5))
+    ms_step = timed_steps(h, step, steps, dev)
+    h.set_profiling(True)
+    step()
     st = h.flush_stats()
-    if rank == 0:
-        peak, _ = bench.peaks()
-        b_flush = bench.flush_bytes(n_ins, 0, int(D.nnz_global), N)
-        line = {"metric": bench.METRIC, "value": n_ins / (ms_step / 1e3), "unit": bench.UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"fdrand 3-D {n1}^3 (BASELINE.json configs[4]), node-slab generation and column-slab "
-                                       f"ownership over {world} ranks, updateindex! stream + flush!, CSC left sharded",
-                           "mode": args.mode, "exchange": dict(D.last_exchange),
-                           "host_phase_ms_last_step": [round(x, 3) for x in D.last_phase_ms]},
-                "flush_rank0": {"ms": st["ms_total"], "column_path": st["column_path"], "n_inserted": st["n_inserted"],
-                                "nnz_new": st["nnz_new"]},
-                "whole_job_flush_fraction_of_hbm_peak": b_flush / (ms_step / 1e3) / 1e9 / (peak * world),
-                "nnz_global": int(D.nnz_global), "n_inserted": int(n_ins)}
-        print(json.dumps(line))
+    h.set_profiling(False)
+    nnz_global = int(D.nnz_global)
+    peak, _ = bench.peaks()
+    b_flush = bench.flush_bytes(n_ins, 0, nnz_global, N)
+    line = {"metric": bench.METRIC, "value": n_ins / (ms_step / 1e3), "entries_per_s": n_ins / (ms_step / 1e3),
+            "unit": bench.UNIT, "n_gpus": world,
+            "steps": steps, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"fdrand 3-D {n1}^3 (BASELINE.json configs[4]), node-slab generation and column-slab "
+                                   f"ownership over {world} ranks, updateindex! stream + flush!, CSC left sharded",
+                       "mode": args.mode, "exchange": dict(D.last_exchange), "fixed_capacity_steps": D.fixed_steps},
+            "flush_rank0": {"ms": st["ms_total"], "column_path": st["column_path"], "n_inserted": st["n_inserted"],
+                            "nnz_new": st["nnz_new"]},
+            "whole_job_flush_fraction_of_hbm_peak": b_flush / (ms_step / 1e3) / 1e9 / (peak * world),
+            "nnz_global": nnz_global, "n_inserted": int(n_ins)}
     h.close()
-    dist.barrier()
-    dist.destroy_process_group()
-    import faulthandler
-
-    faulthandler.cancel_dump_traceback_later()
+    return line

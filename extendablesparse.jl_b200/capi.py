@@ -89,6 +89,8 @@ SIGNATURES = {
     "xsb_route_prepare": (_i32, [_p, _p, _i64, C.POINTER(_i64)]),
     "xsb_route_count": (_i32, [_p, C.POINTER(_i64)]),
     "xsb_route_finish": (_i32, [_p, _i32, _p, _i64]),
+    "xsb_route_pack": (_i32, [_p, _p, C.POINTER(_i64), _i64]),
+    "xsb_route_unpack": (_i32, [_p, _p, C.POINTER(_i64)]),
     "xsb_destroy": (_i32, [_p]),
     "xsb_last_error": (C.c_char_p, [_p]),
     "xsb_reset": (_i32, [_p]),
@@ -274,6 +276,22 @@ class Handle:
 
     def route_finish(self, src_rank, recv_records, count):
         self._c(lib().xsb_route_finish(self._h, int(src_rank), ptr(recv_records), count))
+
+    def route_pack(self, send_records, caps, capacity):
+        """Fixed-capacity exchange: blocks (header + caps[d] slots) for every destination d != own rank."""
+        arr = (_i64 * max(self.n_ranks, 1))(*[int(c) for c in caps])
+        self._c(lib().xsb_route_pack(self._h, ptr(send_records), arr, int(capacity)))
+
+    def route_unpack(self, recv_records, caps):
+        """Fixed-capacity exchange: the received blocks (sources ascending, own rank left out) become staged regions."""
+        arr = (_i64 * max(self.n_ranks, 1))(*[int(c) for c in caps])
+        self._c(lib().xsb_route_unpack(self._h, ptr(recv_records), arr))
+
+    def get_stream(self) -> int:
+        """cudaStream_t of the handle (an integer address; wrap with torch.cuda.ExternalStream)."""
+        v = _p()
+        self._c(lib().xsb_get_stream(self._h, C.byref(v)))
+        return int(v.value or 0)
 
     def shrink_to_fit(self):
         self._c(lib().xsb_shrink_to_fit(self._h))

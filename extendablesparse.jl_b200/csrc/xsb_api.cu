@@ -103,6 +103,10 @@ struct xsb_matrix
     u32 *csr_map = nullptr; // row-major view of the resident pattern for xsb_mul (rebuilt when the pattern changes)
     u64 *d_scal = nullptr; // 8 device scalars
     u64 *h_scal = nullptr; // pinned mirror
+    // fixed-capacity exchange (xsb_route_pack / xsb_route_unpack): nothing of it visits the host until the flush
+    u64 *d_route = nullptr;    // [0] error flags of the received blocks, [1] records taken from lower ranks, [2] from higher
+    u64 *h_route = nullptr;    // pinned: block bases / capacities handed to the kernels (2 * kMaxRanks), results (4)
+    bool fixed_exchange = false; // the staged regions of other ranks are capacity-sized blocks (n_low / n_high: upper bounds)
 
     LaunchCounter lc;
     bool profiling = false;
@@ -230,6 +234,9 @@ struct xsb_matrix
             low_end = -1;
             n_low = n_high = n_pad = 0;
             last_src = -1;
+            if (fixed_exchange && d_route)
+                cudaMemsetAsync(d_route, 0, sizeof(u64) * 4, stream);
+            fixed_exchange = false;
             if (release)
             {
                 dfree(st.buf);
@@ -532,6 +539,20 @@ void check_mt_assign(xsb_matrix *h, const Rec *recs, i64 count)
 
 bool runs_eligible(const xsb_matrix *h);
 
+// fixed-capacity exchange: what the unpack kernels found (h_route[2 kMaxRanks ..] was copied and the stream synchronised)
+void check_exchange(xsb_matrix *h)
+{
+    const u64 flags = h->h_route[2 * kMaxRanks];
+    REQUIRE((flags & 4ull) == 0, XSB_EINVAL, "a received block carries no header: capacities of sender and receiver differ");
+    REQUIRE((flags & 2ull) == 0, XSB_ESTATE,
+            "a bucket of the exchange did not fit its block: records were cut off; reset! and repeat the step with larger "
+            "capacities (or use xsb_route_count / xsb_route_prepare / xsb_route_finish)");
+    REQUIRE((flags & 1ull) == 0, XSB_EBOUNDS, "a received record is not owned by this rank");
+    // the old paths need the true sizes of the regions
+    h->n_low = (i64)h->h_route[2 * kMaxRanks + 1];
+    h->n_high = (i64)h->h_route[2 * kMaxRanks + 2];
+}
+
 // flush! on grouped chunks (xsb_runs.cu): the product path.  Returns false -- with the staged records and the
 // resident CSC untouched (apart from the in-place grouping of chunks, which keeps every entry's insertions in
 // stream order) -- when this flush has to take another path: a stream without column locality, a column too long
@@ -592,9 +613,13 @@ bool runs_flush(xsb_matrix *h, int32_t mode, i64 n_ins, StageTimer *tp, int64_t 
     }
     h->runs.sorted_end = count;
     XSB_CUDA(cudaMemcpyAsync(h->h_scal + 4, rt.counters, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    if (h->fixed_exchange)
+        XSB_CUDA(cudaMemcpyAsync(h->h_route + 2 * kMaxRanks, h->d_route, sizeof(u64) * 3, cudaMemcpyDeviceToHost, s));
     if (tp)
         tp->end(s, &StageTimes::gcount);
     h->sync();
+    if (h->fixed_exchange)
+        check_exchange(h);
     const u32 npairs = (u32)(h->h_scal[4] & 0xffffffffull);
     const u32 flags = (u32)(h->h_scal[4] >> 32);
     h->stats_pairs = (i64)npairs;
@@ -845,8 +870,14 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     // grouping kernels skip them by their owner bits; every other path first drops them with one
     // stable partition on the owner bits.
     const i64 foreign = h->foreign + h->n_pad;
+    if (h->fixed_exchange)
+    { // capacity-sized regions: the true sizes (and what the unpack kernels found) are on the device
+        XSB_CUDA(cudaMemcpyAsync(h->h_route + 2 * kMaxRanks, h->d_route, sizeof(u64) * 3, cudaMemcpyDeviceToHost, s));
+        h->sync();
+        check_exchange(h);
+    }
     const i64 n_low = h->n_low, n_high = h->n_high;
-    bool tomb = h->L.ownerbits > 0 && (foreign > 0 || front > nnz_old);
+    bool tomb = h->L.ownerbits > 0 && (foreign > 0 || front > nnz_old || h->fixed_exchange);
     // the fold must meet the records of a column as [old | lower ranks | own | higher ranks]
     ChunkOrder ord{};
     const ChunkOrder *pord = nullptr;
@@ -1302,6 +1333,12 @@ static int32_t create_impl(int64_t m, int64_t n_global, int32_t nranks, int32_t 
         XSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         h->d_scal = static_cast<u64 *>(h->dalloc(sizeof(u64) * 8));
         XSB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_scal), sizeof(u64) * 8));
+        if (nranks > 0)
+        {
+            h->d_route = static_cast<u64 *>(h->dalloc(sizeof(u64) * 4));
+            XSB_CUDA(cudaMemsetAsync(h->d_route, 0, sizeof(u64) * 4, h->stream));
+            XSB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_route), sizeof(u64) * (2 * kMaxRanks + 4)));
+        }
         XSB_CUDA(cudaEventCreate(&h->ev0));
         XSB_CUDA(cudaEventCreate(&h->ev1));
         h->set_empty_csc();
@@ -1465,6 +1502,97 @@ int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_recor
     });
 }
 
+// Fixed-capacity exchange, step 1: copies the records other ranks own into one BLOCK per destination rank d != own
+// -- a 16-byte header {records of the bucket, magic} followed by caps[d] record slots -- block after block in
+// `send_records` (device; room for sum(caps[d] + 1) records).  Nothing is read back: the whole call is stream-ordered.
+// A bucket fuller than its block is cut off; the receiving rank's flush reports it (XSB_ESTATE).
+int32_t xsb_route_pack(xsb_matrix *h, void *send_records, const int64_t *caps, int64_t send_capacity)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && caps, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(!h->routed, XSB_ESTATE, "staged records were already routed");
+        i64 need = 0;
+        for (int d = 0; d < h->nranks; ++d)
+            if (d != h->rank)
+            {
+                REQUIRE(caps[d] >= 0, XSB_EINVAL, "negative block capacity");
+                need += caps[d] + 1;
+            }
+        REQUIRE(send_capacity >= need, XSB_EINVAL, "send buffer too small for the blocks");
+        REQUIRE(need == 0 || (send_records && is_device_ptr(send_records)), XSB_EINVAL, "send buffer must be device memory");
+        Stage &st = h->stage[0];
+        if (!st.buf)
+            h->ensure_stage(0, 0);
+        h->dfree(h->route_ws);
+        h->route_ws = h->dalloc(route_workspace_bytes((u64)std::max<i64>(st.count, 1), h->nranks));
+        if (need > 0)
+            route_pack(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, reinterpret_cast<const i64 *>(caps), h->h_route, h->h_route + kMaxRanks,
+                       static_cast<Rec *>(send_records), h->lc, h->tileflags);
+        h->route_counted = -1;
+        h->foreign = 0; // unknown on the host: the flush skips them by their owner bits
+        h->routed = true;
+        h->fixed_exchange = true;
+        pad_region(h);
+        h->own_end = st.count;
+        return XSB_OK;
+    });
+}
+
+// Fixed-capacity exchange, step 2 (after the all-to-all): `recv_records` holds the blocks of the source ranks
+// src != own in ascending order, block src = header + caps[src] slots.  Every block becomes a region of caps[src]
+// staged records (the bucket's records, then records the flush skips).  Stream-ordered; errors (a record of another
+// owner, a bucket that was cut off) surface at xsb_flush.
+int32_t xsb_route_unpack(xsb_matrix *h, const void *recv_records, const int64_t *caps)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && caps, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(h->pending() == 0 || h->routed, XSB_ESTATE, "unrouted records are still staged");
+        REQUIRE(h->last_src < 0, XSB_ESTATE, "records of other ranks were already appended");
+        i64 total = 0;
+        for (int s2 = 0; s2 < h->nranks; ++s2)
+            if (s2 != h->rank)
+            {
+                REQUIRE(caps[s2] >= 0, XSB_EINVAL, "negative block capacity");
+                total += caps[s2];
+            }
+        REQUIRE(total == 0 || (recv_records && is_device_ptr(recv_records)), XSB_EINVAL, "receive buffer must be device memory");
+        if (!h->routed)
+        { // nothing was staged on this rank: the own region is empty
+            h->ensure_stage(0, 0);
+            h->own_end = 0;
+        }
+        h->routed = true;
+        h->fixed_exchange = true;
+        h->has_assign = true; // flavours of the received records are not inspected on the host: ordered fold
+        const Rec *blk = static_cast<const Rec *>(recv_records);
+        for (int src = 0; src < h->nranks; ++src)
+        {
+            if (src == h->rank)
+            { // the region of the lower ranks is complete
+                pad_region(h);
+                h->low_end = h->stage[0].count;
+                continue;
+            }
+            const i64 cap = caps[src];
+            { // also for cap == 0: the header must say "no records"
+                h->ensure_stage(0, cap);
+                Stage &st = h->stage[0];
+                route_unpack(h->stream, blk, cap, st.buf + st.front + st.count, h->L, h->n, h->d_route, h->d_route + 1,
+                             src < h->rank ? 0 : 1, h->lc);
+                st.count += cap;
+                (src < h->rank ? h->n_low : h->n_high) += cap;
+            }
+            blk += cap + 1;
+            h->last_src = src;
+        }
+        if (h->low_end < 0)
+            h->low_end = h->stage[0].count;
+        return XSB_OK;
+    });
+}
+
 int32_t xsb_destroy(xsb_matrix *h)
 {
     if (!h)
@@ -1481,9 +1609,12 @@ int32_t xsb_destroy(xsb_matrix *h)
     h->dfree(h->route_ws);
     h->dfree(h->tileflags);
     h->dfree(h->d_scal);
+    h->dfree(h->d_route);
     h->release_cache();
     if (h->h_scal)
         cudaFreeHost(h->h_scal);
+    if (h->h_route)
+        cudaFreeHost(h->h_route);
     if (h->ev0)
         cudaEventDestroy(h->ev0);
     if (h->ev1)

@@ -231,45 +231,37 @@ void build_frozen_map(cudaStream_t stream, const Rec *sorted, i64 count, i64 nnz
 }
 
 // nzval[z] = ((nzval[z] + V[p0]) + V[p1]) + ...  in stream order: bit-exact with the reference's in-place CSC-hit
-// updates (extendable.jl:164-166).  A warp owns 32 consecutive entries.  Their values -- one contiguous piece of
-// the permutation built at freeze time -- are gathered by the whole warp into shared memory (coalesced reads of the
-// permutation, all the 8-byte gathers of V in flight at once), then every lane folds its own entry in order from
-// there: the dependent chain of additions never waits for HBM.  ZERO: the entries start from +0.0 instead of the
-// resident value (nonzeros(A) .= 0 fused in: nzval is written, never read).
-constexpr int RA_WARPS = 8;
-constexpr int RA_CAP = 512; // values a warp stages per round
-
+// updates (extendable.jl:164-166).  One thread per entry walks its piece of the permutation built at freeze time.
+// The gathers of V go through L1: the threads of a block hold consecutive entries (a few dozen neighbouring columns),
+// whose values come from a few short windows of the stream, so the 32-byte sectors of V are shared inside the block
+// and HBM sees every value about once.  ZERO: the entries start from +0.0 instead of the resident value
+// (nonzeros(A) .= 0 fused in: nzval is written, never read).
 template <bool ZERO>
-__global__ void __launch_bounds__(RA_WARPS * 32)
-reassemble_warp_kernel(const double *__restrict__ V, const u32 *__restrict__ perm, const u32 *__restrict__ segstart,
-                       i64 nnz, double *__restrict__ nzval)
+__global__ void __launch_bounds__(256)
+reassemble_det_kernel(const double *__restrict__ V, const u32 *__restrict__ perm, const u32 *__restrict__ segstart,
+                      i64 nnz, double *__restrict__ nzval)
 {
-    __shared__ double s_val[RA_WARPS][RA_CAP];
-    constexpr u32 full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *vals = s_val[warp];
-    const i64 nwarps = (nnz + 31) / 32;
-    for (i64 w = (i64)blockIdx.x * RA_WARPS + warp; w < nwarps; w += (i64)gridDim.x * RA_WARPS)
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 z = (i64)blockIdx.x * blockDim.x + threadIdx.x; z < nnz; z += stride)
     {
-        const i64 z = w * 32 + lane;
-        const u32 a = z < nnz ? segstart[z] : 0u, b = z < nnz ? segstart[z + 1] : 0u;
-        const u32 w0 = __shfl_sync(full, a, 0);
-        const u32 w1 = __reduce_max_sync(full, b); // segstart is non-decreasing: the end of the warp's last entry
-        double acc = (ZERO || z >= nnz || a == b) ? 0.0 : nzval[z];
-        u32 cur = a; // next value of this lane's entry
-        for (u32 c0 = w0; c0 < w1; c0 += RA_CAP)
+        const u32 s0 = segstart[z], s1 = segstart[z + 1];
+        if (s1 == s0)
         {
-            const u32 c1 = min(c0 + (u32)RA_CAP, w1);
-            for (u32 k = c0 + lane; k < c1; k += 32)
-                vals[k - c0] = __ldg(V + perm[k]);
-            __syncwarp();
-            const u32 e = min(b, c1);
-            for (; cur < e; ++cur)
-                acc = acc + vals[cur - c0];
-            __syncwarp();
+            if (ZERO)
+                nzval[z] = 0.0;
+            continue;
         }
-        if (z < nnz && (ZERO || a != b))
-            nzval[z] = acc;
+        double acc = ZERO ? 0.0 : nzval[z];
+        u32 s = s0;
+        for (; s + 2 <= s1; s += 2)
+        { // two gathers in flight, folded in order
+            const double v0 = __ldg(V + perm[s]), v1 = __ldg(V + perm[s + 1]);
+            acc = acc + v0;
+            acc = acc + v1;
+        }
+        if (s < s1)
+            acc = acc + __ldg(V + perm[s]);
+        nzval[z] = acc;
     }
 }
 
@@ -278,12 +270,11 @@ void reassemble_deterministic(cudaStream_t stream, const double *V, const u32 *p
 {
     if (nnz <= 0)
         return;
-    const i64 nwarps = (nnz + 31) / 32;
-    const int blocks = (int)std::min<i64>((nwarps + RA_WARPS - 1) / RA_WARPS, (i64)kNumSM * 32);
+    const int blocks = (int)std::min<i64>((nnz + 255) / 256, (i64)kNumSM * 64);
     if (zero_first)
-        reassemble_warp_kernel<true><<<blocks, RA_WARPS * 32, 0, stream>>>(V, perm, segstart, nnz, nzval);
+        reassemble_det_kernel<true><<<blocks, 256, 0, stream>>>(V, perm, segstart, nnz, nzval);
     else
-        reassemble_warp_kernel<false><<<blocks, RA_WARPS * 32, 0, stream>>>(V, perm, segstart, nnz, nzval);
+        reassemble_det_kernel<false><<<blocks, 256, 0, stream>>>(V, perm, segstart, nnz, nzval);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }

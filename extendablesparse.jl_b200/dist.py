@@ -93,6 +93,13 @@ class DistExtendableSparseMatrix:
         self.last_exchange = {"sent_off_rank": 0, "received_off_rank": 0, "kept": 0}
         self._send = None
         self.last_phase_ms = []
+        # fixed-capacity exchange (xsb_route_pack / xsb_route_unpack): capacities both sides derive from the last
+        # exactly counted step -- what this rank sent to d is what d received from this rank
+        self._caps_out = None  # per destination rank
+        self._caps_in = None   # per source rank
+        self._recv = None
+        self._lib_stream = None
+        self.fixed_steps = 0
 
     # insertion: global (i,j) on any rank
     def insert_batch(self, I, J, V, flavour=0):
@@ -104,10 +111,63 @@ class DistExtendableSparseMatrix:
             self._send = torch.empty(words, dtype=torch.int64, device=self.device)
         return self._send
 
-    def flush(self, mode=0, wait=True):
-        """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank); with wait=False the
-        second value is the LOCAL flag and the global one is `changed_any` (read on demand)."""
+    @staticmethod
+    def _capacity(count: int) -> int:
+        """Block capacity for a bucket that held `count` records in the last counted step."""
+        return max(256, 2 * int(count))
+
+    def _flush_fixed(self, mode, wait):
+        """The step of an assembly LOOP: same routing, but with the block capacities agreed after the last counted
+        step no count visits the host -- pack, ONE all-to-all with host-known split sizes, unpack and the flush are
+        stream-ordered on the library's stream (NCCL is chained to it through the current-stream events)."""
         import time
+
+        t0 = time.perf_counter()
+        h, world, rank = self.h, self.world, self.rank
+        co = [0 if d == rank else self._caps_out[d] for d in range(world)]
+        ci = [0 if s == rank else self._caps_in[s] for s in range(world)]
+        in_split = [0 if d == rank else 2 * (co[d] + 1) for d in range(world)]
+        out_split = [0 if s == rank else 2 * (ci[s] + 1) for s in range(world)]
+        if self._send is None or self._send.numel() < max(sum(in_split), 2):
+            self._send = torch.empty(max(sum(in_split), 2), dtype=torch.int64, device=self.device)
+        if self._recv is None or self._recv.numel() < max(sum(out_split), 2):
+            self._recv = torch.empty(max(sum(out_split), 2), dtype=torch.int64, device=self.device)
+        if self._lib_stream is None:
+            self._lib_stream = torch.cuda.ExternalStream(h.stream, device=self.device)
+        cnt = int(h.pending)
+        h.route_pack(self._send, co, sum(in_split) // 2)
+        with torch.cuda.stream(self._lib_stream):
+            dist.all_to_all_single(self._recv[: sum(out_split)], self._send[: sum(in_split)], output_split_sizes=out_split,
+                                   input_split_sizes=in_split, group=self.group)
+        h.route_unpack(self._recv, ci)
+        nnz, changed = h.flush(mode)
+        mine = torch.tensor([nnz, int(changed)], dtype=torch.int64, device=self.device)
+        allv = torch.empty(2 * world, dtype=torch.int64, device=self.device)
+        work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=True)
+        self._offsets_pending = (work, allv, mine)
+        self.last_exchange = {"sent_off_rank": None, "received_off_rank": None, "kept": None, "staged": cnt,
+                              "fixed_capacity_blocks": {"out": co, "in": ci}}
+        if wait:
+            self._resolve_offsets()
+        self.fixed_steps += 1
+        self.last_phase_ms = [0.0, 0.0, 0.0, 0.0, 1e3 * (time.perf_counter() - t0), 0.0]
+        return nnz, (self._changed_any if wait else bool(changed))
+
+    def flush(self, mode=0, wait=True, fixed=None):
+        """Route, exchange, merge.  Returns (local nnz, pattern changed on any rank); with wait=False the
+        second value is the LOCAL flag and the global one is `changed_any` (read on demand).
+
+        fixed: None = the fixed-capacity exchange once a counted step has set the capacities (product backend
+        only; every rank takes the same decision: the counted step is collective); False = always count."""
+        import time
+
+        can_fix = hasattr(self.h, "route_pack") and self.device.type == "cuda"
+        if fixed is None:
+            fixed = can_fix and self._caps_out is not None
+        if fixed:
+            if not can_fix or self._caps_out is None:
+                raise RuntimeError("fixed-capacity exchange needs a counted step first")
+            return self._flush_fixed(mode, wait)
 
         t = [time.perf_counter()]
 
@@ -143,6 +203,8 @@ class DistExtendableSparseMatrix:
         self._offsets_pending = (work, allv, mine)
         self.last_exchange = {"sent_off_rank": cnt - counts[self.rank], "received_off_rank": sum(rcounts),
                               "kept": counts[self.rank]}
+        self._caps_out = [self._capacity(c) for c in counts]
+        self._caps_in = [self._capacity(c) for c in rcounts]
         if wait:
             self._resolve_offsets()
         lap()

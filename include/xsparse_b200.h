@@ -226,6 +226,20 @@ int32_t xsb_slab_info(const xsb_matrix *h, int64_t *col_begin, int64_t *col_end,
  * in stream order: the distributed result equals the serial reference applied to the rank-ordered
  * concatenation of the ranks' streams, bit for bit in XSB_DETERMINISTIC mode. */
 int32_t xsb_route_count(xsb_matrix *h, int64_t *send_counts);
+/* The same exchange with FIXED capacities, for assembly loops that repeat a step (Newton, time stepping): no
+ * count ever visits the host, so the whole step -- insertion, routing, all-to-all, flush -- is stream-ordered
+ * apart from the flush's own two synchronisations.  Sender and receiver agree on caps[][] beforehand (e.g. twice
+ * what the previous step sent).
+ *   xsb_route_pack(h, send, caps, capacity): one BLOCK per destination d != own rank, block after block in `send`
+ *     (device): a 16-byte header {records of the bucket, magic} + caps[d] record slots; capacity >= sum(caps[d] + 1).
+ *   all-to-all of the blocks (split sizes caps[d] + 1 records, known on the host).
+ *   xsb_route_unpack(h, recv, caps): `recv` = the blocks of the sources src != own rank in ascending order, block
+ *     src = header + caps[src] slots; every block becomes caps[src] staged records (the bucket, then skipped ones).
+ *   xsb_flush.  A bucket that did not fit its block, a record of another owner or a missing header make the FLUSH
+ *     fail (XSB_ESTATE / XSB_EBOUNDS / XSB_EINVAL) with the resident matrix untouched: xsb_reset and repeat the step
+ *     through xsb_route_count / xsb_route_prepare / xsb_route_finish, or with larger capacities. */
+int32_t xsb_route_pack(xsb_matrix *h, void *send_records, const int64_t *caps, int64_t send_capacity);
+int32_t xsb_route_unpack(xsb_matrix *h, const void *recv_records, const int64_t *caps);
 int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, int64_t *send_counts);
 int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_records, int64_t count);
 
