@@ -279,12 +279,34 @@ def cpu_baseline_both(mesh, steps, warmup):
     return n_ins, times, cpu
 
 
+def julia_reference(mesh, steps):
+    """when a Julia runtime with ExtendableSparse.jl is present on the box (PATH or baseline/_ref),
+    the REAL reference is timed (tools/julia_ref.py / .jl).  Returns (seconds per assembly, description) or None."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("julia_ref", os.path.join(ROOT, "tools", "julia_ref.py"))
+    jr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(jr)
+    found = jr.probe()
+    if found is None:
+        return None
+    r = jr.run(["time", mesh, max(1, steps)])
+    try:
+        return float(r.stdout.strip().splitlines()[-1]), f"{found[0]} (ExtendableSparse {found[1]}), julia -t 1"
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     mesh = args.ref_mesh
+    jl = julia_reference(mesh, args.steps)
     n_ins, times, cpu = cpu_baseline_both(mesh, args.steps, args.warmup)
+    if jl is not None:  # the package itself, serial; the oracle port's numbers stay in the line beside it
+        cpu = dict(cpu, kind="reference", oracle_port_value=cpu["value"], value=max(cpu["value"], n_ins / jl[0]),
+                   julia_value=n_ins / jl[0], sample=f"ExtendableSparse.jl itself: {jl[1]}; " + cpu["sample"])
     total = sum(times)
     value = cpu["value"]
     line = {
@@ -397,7 +419,7 @@ def run_ours(args):
     cpu = None
     parity = None
     if not args.no_cpu:
-        _, _, cpu = cpu_baseline_both(args.cpu_mesh, 1, 0)
+        _, _, cpu = cpu_baseline_both(args.cpu_mesh, 3, 1)  # one warm-up + 3 repetitions of both CPU paths
         if args.cpu_mesh == mesh and ORACLE_DIGEST.get(mesh):
             parity = ORACLE_DIGEST[mesh] == gpu_digest
             if not parity:

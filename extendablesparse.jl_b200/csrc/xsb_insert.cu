@@ -550,6 +550,15 @@ struct FemTet
     __device__ __forceinline__ double val(int il, int w) const { return w == 0 ? 0.1 * vol / 4.0 : vol * S[il][w - 1]; }
 };
 
+// x / y for finite y != 0, bit for bit: a zero numerator (most cofactors of an axis-aligned tetrahedron, the
+// coordinate of the first mesh plane) gives the signed zero directly instead of taking the division's slow path
+__device__ __forceinline__ double div_finite(double x, double y)
+{
+    if (x == 0.0)
+        return ((__double2hiint(x) ^ __double2hiint(y)) < 0) ? -0.0 : 0.0;
+    return x / y;
+}
+
 __device__ __forceinline__ void fem_tet_compute(i64 t, i64 nxn, i64 nyn, i64 nzn, const KeyLayout &L, u32 tid, u32 flavour,
                                                 bool slab, FemTet &e)
 {
@@ -590,7 +599,7 @@ __device__ __forceinline__ void fem_tet_compute(i64 t, i64 nxn, i64 nyn, i64 nzn
 #pragma unroll
     for (int d = 0; d < 3; ++d)
     {
-        lo[d] = (double)idx[0][d] / dd[d];
+        lo[d] = div_finite((double)idx[0][d], dd[d]);
         hi[d] = (double)(idx[0][d] + 1) / dd[d];
     }
     double p[4][3];
@@ -621,15 +630,15 @@ __device__ __forceinline__ void fem_tet_compute(i64 t, i64 nxn, i64 nyn, i64 nzn
     const double c22 = a[0][0] * a[1][1] - a[0][1] * a[1][0];
     const double det = (a[0][0] * c00 + a[0][1] * c01) + a[0][2] * c02;
     double gr[4][3];
-    gr[1][0] = c00 / det;
-    gr[1][1] = c10 / det;
-    gr[1][2] = c20 / det;
-    gr[2][0] = c01 / det;
-    gr[2][1] = c11 / det;
-    gr[2][2] = c21 / det;
-    gr[3][0] = c02 / det;
-    gr[3][1] = c12 / det;
-    gr[3][2] = c22 / det;
+    gr[1][0] = div_finite(c00, det);
+    gr[1][1] = div_finite(c10, det);
+    gr[1][2] = div_finite(c20, det);
+    gr[2][0] = div_finite(c01, det);
+    gr[2][1] = div_finite(c11, det);
+    gr[2][2] = div_finite(c21, det);
+    gr[3][0] = div_finite(c02, det);
+    gr[3][1] = div_finite(c12, det);
+    gr[3][2] = div_finite(c22, det);
 #pragma unroll
     for (int d = 0; d < 3; ++d)
         gr[0][d] = -((gr[1][d] + gr[2][d]) + gr[3][d]);

@@ -224,8 +224,9 @@ function freeze!(a::B200Assembler{Tv, Ti}, I::Vector{Ti}, J::Vector{Ti}) where {
                           a.handle, I, J, length(I)))
 end
 function reassemble!(a::B200Assembler{Tv}, V::Vector{Tv}; mode = XSB_DETERMINISTIC, zero = true) where {Tv}
-    zero && check(a.handle, ccall((:xsb_zero_values, libxsb), Int32, (Ptr{Cvoid},), a.handle))
-    check(a.handle, ccall((:xsb_reassemble_values, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32),
+    # zero = true: nonzeros(A) .= 0 and the re-assembly as ONE pass over nzval (xsb_reassemble_values_zeroed)
+    f = zero ? :xsb_reassemble_values_zeroed : :xsb_reassemble_values
+    check(a.handle, ccall((f, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32),
                           a.handle, V, length(V), mode))
 end
 
@@ -263,7 +264,14 @@ const B200ExtendableSparseMatrixCSC{Tv, Ti} =
 const STB200ExtendableSparseMatrixCSC{Tv, Ti} =
     ExtendableSparse.GenericExtendableSparseMatrixCSC{SparseMatrixB200{Tv, Ti}, Tv, Ti}
 
-export SparseMatrixB200, B200Assembler, B200ExtendableSparseMatrixCSC, STB200ExtendableSparseMatrixCSC,
+"pattern_equal(a, b) on the device (sparsematrixcsc.jl:77-85)"
+function pattern_equal(a::B200Assembler, b::B200Assembler)
+    eq = Ref{Int32}(0)
+    check(a.handle, ccall((:xsb_pattern_equal, libxsb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int32}), a.handle, b.handle, eq))
+    eq[] != 0
+end
+
+export SparseMatrixB200, B200Assembler, pattern_equal, B200ExtendableSparseMatrixCSC, STB200ExtendableSparseMatrixCSC,
        set_csc!, insert!, fetch!, freeze!, reassemble!, pointblock, XsbTriplet
 
 end # module
