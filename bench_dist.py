@@ -134,6 +134,8 @@ def run(args, xsb, rank, world, local):
     roof = bench.roofline(st, {k: v / prof_steps for k, v in stage.items()}, ms_emit / prof_steps, h.n, peak, peak_src, None)
     roof["kernel"] += " [rank 0]"
     exchange = dict(D.last_exchange)
+    if D.last_device_phase_ms:
+        exchange["device_phase_ms_last_step"] = {k: round(v, 4) for k, v in D.last_device_phase_ms.items()}
     nnz_global = int(D.nnz_global)
     h.close()
     del D

@@ -317,6 +317,26 @@ __host__ __device__ __forceinline__ double philox_uniform(u64 seed, u64 counter)
 // Record and rand() counts before a node have a closed form, so every node
 // can be emitted independently at its exact stream position.
 // ------------------------------------------------------------------------
+// node l0 (0-based, x fastest) -> 1-based (i,j,k); 32-bit arithmetic when the grid allows it (a 64-bit division by
+// a run-time value costs about a hundred instructions)
+__host__ __device__ __forceinline__ void node_ijk(i64 l0, i64 nx, i64 ny, i64 nz, i64 &i, i64 &j, i64 &k)
+{
+    if (nx * ny * nz < 0x7fffffffll)
+    {
+        const u32 l = (u32)l0, ux = (u32)nx, uy = (u32)ny;
+        const u32 row = l / ux, lay = row / uy;
+        i = (i64)(l - row * ux) + 1;
+        j = (i64)(row - lay * uy) + 1;
+        k = (i64)lay + 1;
+    }
+    else
+    {
+        i = l0 % nx + 1;
+        j = (l0 / nx) % ny + 1;
+        k = l0 / (nx * ny) + 1;
+    }
+}
+
 struct FdGeom
 {
     i64 nx, ny, nz;
@@ -355,7 +375,8 @@ struct FdGeom
     { // l0 = 0-based node index; l0 == nx*ny*nz gives the stream total
         if (l0 >= nx * ny * nz)
             return before<W>(1, 1, nz + 1);
-        const i64 i = l0 % nx + 1, j = (l0 / nx) % ny + 1, k = l0 / (nx * ny) + 1;
+        i64 i, j, k;
+        node_ijk(l0, nx, ny, nz, i, j, k);
         return before<W>(i, j, k);
     }
 };
@@ -370,10 +391,13 @@ constexpr int FD_THREADS = 128; // nodes per block
 constexpr int FD_MAXREC = 15;   // records per node upper bound
 
 // records of node l0 (0-based), in call order, to dst[0 ..); returns their number
+// base: the tile's records start at stream position rec0; the node's go to base[before(node) - rec0 ...]
 __device__ __forceinline__ int fd_node_records(const FdGeom &g, i64 l0, u64 seed, int ones, const KeyLayout &L, u32 tid,
-                                               u32 flavour, Rec *dst)
+                                               u32 flavour, Rec *base, i64 rec0)
 {
-    const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+    i64 i, j, k;
+    node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
+    Rec *dst = base + (g.before<4>(i, j, k) - rec0);
     int pos = 0;
     u64 call = (u64)g.before<1>(i, j, k);
     const double hx = 1.0 / (double)g.nx, hy = 1.0 / (double)g.ny, hz = 1.0 / (double)g.nz;
@@ -421,7 +445,7 @@ emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavo
     const i64 blk_rec1 = g.before_node<4>(l_last);
     const i64 l0 = l_first + threadIdx.x;
     if (l0 < l_last)
-        fd_node_records(g, l0, seed, ones, L, tid, flavour, s_rec + (g.before_node<4>(l0) - blk_rec0));
+        fd_node_records(g, l0, seed, ones, L, tid, flavour, s_rec, blk_rec0);
     __syncthreads();
     const i64 nrec = blk_rec1 - blk_rec0;
     Rec *dst = out + (blk_rec0 - rec_begin);
@@ -455,7 +479,7 @@ emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u
     chunk_space_init(sp.tab, lane);
     const i64 l0 = l_first + lane;
     if (l0 < l_last)
-        fd_node_records(g, l0, seed, ones, L, tid, flavour, sp.rec + (g.before_node<4>(l0) - w_rec0));
+        fd_node_records(g, l0, seed, ones, L, tid, flavour, sp.rec, w_rec0);
     __syncwarp();
     const i64 c0 = w_rec0 - rec_begin; // position of the chunk in this launch's output
     const u32 lt = lanemask_lt();
@@ -887,7 +911,8 @@ emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *
         const i64 l0 = w / ns2;
         const i64 ab = w % ns2;
         const u64 a = (u64)(ab / g.ns), b = (u64)(ab % g.ns);
-        const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+        i64 i, j, k;
+        node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
         const i64 eb = g.edges_before(i, j, k);
         i64 rec = eb * 4 * ns2 + l0 * ns2;      // records before this node
         u64 call = (u64)(eb * ns2 + l0 * ns2);  // rand() calls before this node
@@ -940,7 +965,11 @@ __host__ __device__ inline i64 rd_node_rec(const RdGeom &g, i64 l0)
     const i64 ns2 = g.ns * g.ns;
     const i64 N = g.nx * g.ny * g.nz;
     const i64 eb = l0 >= N ? g.edges_before(1, 1, g.nz + 1)
-                           : g.edges_before(l0 % g.nx + 1, (l0 / g.nx) % g.ny + 1, l0 / (g.nx * g.ny) + 1);
+                           : [&]() {
+                                 i64 i, j, k;
+                                 node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
+                                 return g.edges_before(i, j, k);
+                             }();
     return eb * 4 * ns2 + (l0 >= N ? N : l0) * ns2;
 }
 static int rd_nodes_per_warp(i64 ns)
@@ -969,10 +998,12 @@ emit_blockrd_grouped_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavou
     const i64 nitems = (l_last - l_first) * ns2;
     for (i64 it = lane; it < nitems; it += 32)
     {
-        const i64 l0 = l_first + it / ns2;
-        const i64 ab = it % ns2;
-        const u64 a = (u64)(ab / g.ns), b = (u64)(ab % g.ns);
-        const i64 i = l0 % g.nx + 1, j = (l0 / g.nx) % g.ny + 1, k = l0 / (g.nx * g.ny) + 1;
+        const u32 nl = (u32)it / (u32)ns2; // items of a warp fit 32 bits: at most 32 nodes x ns^2
+        const i64 l0 = l_first + (i64)nl;
+        const i64 ab = (i64)((u32)it - nl * (u32)ns2);
+        const u64 a = (u64)((u32)ab / (u32)g.ns), b = (u64)((u32)ab % (u32)g.ns);
+        i64 i, j, k;
+        node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
         const i64 eb = g.edges_before(i, j, k);
         i64 rec = eb * 4 * ns2 + l0 * ns2 - w_rec0; // records of this chunk before this node
         u64 call = (u64)(eb * ns2 + l0 * ns2);      // rand() calls before this node

@@ -115,6 +115,76 @@ route_scan_kernel(const u32 *__restrict__ tilecnt, u32 *__restrict__ tileoff, u6
         total[d] = run;
 }
 
+// The same scan for long staging buffers, single pass with decoupled look-back: blockIdx.y = destination, a block
+// (in ticket order per destination) scans RS_TILE consecutive tiles.  status / ticket: zeroed, (nblocks + 2) u64 and
+// one u32 per destination.
+constexpr int RS_THREADS = 256;
+constexpr int RS_IPT = 8;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;
+
+__global__ void __launch_bounds__(RS_THREADS)
+route_scan_lookback_kernel(const u32 *__restrict__ tilecnt, u32 *__restrict__ tileoff, u64 ntiles, int nranks,
+                           u64 *__restrict__ total, u64 *__restrict__ status, u32 *__restrict__ ticket, u32 nblocks)
+{
+    __shared__ u32 s_w[RS_THREADS / 32];
+    __shared__ u64 s_prefix;
+    __shared__ u32 s_blk;
+    const int d = blockIdx.y;
+    if (threadIdx.x == 0)
+        s_blk = atomicAdd(ticket + d, 1u);
+    __syncthreads();
+    const u32 blk = s_blk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 t0 = (u64)blk * RS_TILE + (u64)threadIdx.x * RS_IPT;
+    u32 v[RS_IPT];
+    u32 sum = 0;
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i)
+    {
+        v[i] = t0 + i < ntiles ? tilecnt[(t0 + i) * nranks + d] : 0u;
+        sum += v[i];
+    }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += y;
+    }
+    if (lane == 31)
+        s_w[warp] = incl;
+    __syncthreads();
+    u32 wpre = 0, btotal = 0;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w)
+    {
+        const u32 c = s_w[w];
+        if (w < warp)
+            wpre += c;
+        btotal += c;
+    }
+    if (warp == 0)
+    {
+        const u64 prefix = warp_lookback(status + (size_t)d * (nblocks + 2), blk, (u64)btotal, lane);
+        if (lane == 0)
+        {
+            s_prefix = prefix;
+            if (blk == nblocks - 1)
+                total[d] = prefix + btotal;
+        }
+    }
+    __syncthreads();
+    u32 run = (u32)s_prefix + wpre + incl - sum;
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i)
+    {
+        if (t0 + i < ntiles)
+            tileoff[(t0 + i) * nranks + d] = run;
+        run += v[i];
+    }
+}
+
 // bucket_base[d] = where rank d's bucket starts in the send buffer
 __global__ void __launch_bounds__(RT_THREADS)
 route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershift, u32 me, int nranks,
@@ -241,7 +311,9 @@ void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayou
 size_t route_workspace_bytes(u64 n, int nranks)
 {
     const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
-    return 2 * sizeof(u32) * (size_t)ntiles * nranks + 3 * sizeof(u64) * kMaxRanks + 256;
+    const u64 sblocks = (ntiles + RS_TILE - 1) / RS_TILE;
+    return 2 * sizeof(u32) * (size_t)ntiles * nranks + 3 * sizeof(u64) * kMaxRanks + 256 +
+           sizeof(u64) * (size_t)(sblocks + 2) * kMaxRanks + sizeof(u32) * kMaxRanks + 64;
 }
 
 // counts_host[d] = staged records owned by rank d (d == me: the ones that stay)
@@ -354,7 +426,14 @@ void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, v
         XSB_CUDA(cudaMemsetAsync(tilecnt, 0, sizeof(u32) * (size_t)ntiles * nr, stream));
         route_count_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
             in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileflags);
-        route_scan_kernel<<<nr, 1024, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total);
+        { // offsets of every tile's records in their bucket: single-pass scan per destination
+            const u32 sblocks = (u32)((ntiles + RS_TILE - 1) / RS_TILE);
+            u64 *status = bucket_cap + kMaxRanks + 4;
+            u32 *ticket = reinterpret_cast<u32 *>(status + (size_t)(sblocks + 2) * kMaxRanks);
+            XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * (size_t)(sblocks + 2) * kMaxRanks + sizeof(u32) * kMaxRanks, stream));
+            route_scan_lookback_kernel<<<dim3(sblocks, (unsigned)nr), RS_THREADS, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total,
+                                                                                             status, ticket, sblocks);
+        }
         route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
             in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, bucket_cap, send);
         lc.add(3);

@@ -209,7 +209,6 @@ run_bucket_kernel(const uint2 *__restrict__ chunkinfo, const u32 *__restrict__ c
 // ------------------------------------------------------------------------
 // one THREAD per column: merge the column of the resident CSC with the column's runs
 // ------------------------------------------------------------------------
-constexpr int RF_WARPS = 4;
 constexpr u32 RF_EMPTY = 0xffffffffu;
 
 // Table shapes, smallest first.  The template argument is the number of hash bits, except 15 = the
@@ -220,7 +219,11 @@ template <int HBITS> struct RfShape
     static constexpr int HB = HBITS == 15 ? 5 : HBITS;
     static constexpr int H = 1 << HB;
     static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? 24 : (HBITS == 15 ? 16 : 12));
-    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 2 : (HBITS == 15 ? 5 : 4));
+    // warps per block; blocks per SM that shared memory and the register file allow.  The largest shape takes
+    // 640 B of shared memory per thread: one-warp blocks fit 11 warps per SM where four-warp blocks fit 8
+    // (measured on the block reaction-diffusion system: 2.65 -> 2.34 ms; the small shapes lose with tiny blocks)
+    static constexpr int kWarps = HBITS == 6 ? 1 : 4;
+    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 11 : (HBITS == 15 ? 5 : 4));
     static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + sizeof(u32)) * D);
 };
 
@@ -346,7 +349,7 @@ template <int HBITS, bool ASSIGN> struct ThreadFold
 };
 
 template <int HBITS, typename Ti, bool ASSIGN>
-__global__ void __launch_bounds__(RF_WARPS * 32, RfShape<HBITS>::kBlocks)
+__global__ void __launch_bounds__(RfShape<HBITS>::kWarps * 32, RfShape<HBITS>::kBlocks)
 runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, const u32 *__restrict__ pstart,
                u64 *__restrict__ bucket, const Ti *__restrict__ old_colptr, const Ti *__restrict__ old_rowval,
                const double *__restrict__ old_nzval, i64 ncols, Ti base, Ti *__restrict__ rowval,
@@ -354,6 +357,7 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
                u64 *__restrict__ d_nnz, u32 *__restrict__ d_redo, u32 *__restrict__ maxd)
 {
     typedef RfShape<HBITS> Shape;
+    constexpr int RF_WARPS = Shape::kWarps;
     constexpr int H = Shape::H;
     constexpr int HB = Shape::HB;
     constexpr u32 D = Shape::D;
@@ -657,7 +661,7 @@ RwLayout rw_layout(u64 npairs, i64 ncols)
 {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const u64 stiles = ((u64)ncols + 1 + SC_TILE - 1) / SC_TILE;
-    const u64 fblocks = ((u64)ncols + RF_WARPS * 32 - 1) / (RF_WARPS * 32);
+    const u64 fblocks = ((u64)ncols + 31) / 32; // look-back words of the merge kernel: room for one-warp blocks
     RwLayout l{};
     size_t o = 0;
     // cleared by one memset: pairs per column, look-back words + tickets of the scan and of the fold
@@ -766,6 +770,7 @@ void launch_runfold_t(cudaStream_t stream, unsigned blocks, const Rec *buf, int 
                       const u32 *pstart, u64 *bucket, const CscView &old, i64 ncols, i64 base, void *rowval, double *nzval,
                       void *colptr, u64 *status, u32 *ticket, u64 *d_nnz, u32 *d_redo, u32 *maxd)
 {
+    constexpr int RF_WARPS = RfShape<HBITS>::kWarps;
     constexpr size_t smem = RF_WARPS * RfShape<HBITS>::kBytesPerWarp;
     static FuncAttrOnce once;
     once.set(runfold_kernel<HBITS, Ti, ASSIGN>, (int)smem, true);
@@ -789,12 +794,6 @@ void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncol
     u32 *pstart = reinterpret_cast<u32 *>(ws + l.off_pstart);
     u64 *bucket = reinterpret_cast<u64 *>(ws + l.off_bucket);
     u64 *status = reinterpret_cast<u64 *>(ws + l.off_fstatus);
-    const unsigned blocks = (unsigned)(((u64)ncols + RF_WARPS * 32 - 1) / (RF_WARPS * 32));
-    u32 *ticket = reinterpret_cast<u32 *>(status + blocks + 1);
-    if (!first_try) // look-back words + ticket were cleared with the bucket workspace the first time
-        XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * ((size_t)blocks + 2), stream));
-    XSB_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(u32), stream));
-    XSB_CUDA(cudaMemsetAsync(d_maxd, 0, sizeof(u32), stream));
     if (g_runs_hbits == 4)
         level = 0;
     else if (g_runs_hbits == 15)
@@ -803,6 +802,14 @@ void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncol
         level = 2;
     else if (g_runs_hbits == 6)
         level = 3;
+    const unsigned tpb = 32u * (unsigned)(level == 3 ? RfShape<6>::kWarps : RfShape<4>::kWarps); // threads per block
+    static_assert(RfShape<4>::kWarps == RfShape<15>::kWarps && RfShape<4>::kWarps == RfShape<5>::kWarps, "block shape");
+    const unsigned blocks = (unsigned)(((u64)ncols + tpb - 1) / tpb);
+    u32 *ticket = reinterpret_cast<u32 *>(status + blocks + 1);
+    if (!first_try) // look-back words + ticket were cleared with the bucket workspace the first time
+        XSB_CUDA(cudaMemsetAsync(status, 0, sizeof(u64) * ((size_t)((u64)ncols + 31) / 32 + 2), stream));
+    XSB_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(u32), stream));
+    XSB_CUDA(cudaMemsetAsync(d_maxd, 0, sizeof(u32), stream));
 #define XSB_RUNFOLD(HB, TI)                                                                                             \
     do                                                                                                                  \
     {                                                                                                                   \

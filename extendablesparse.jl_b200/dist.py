@@ -22,6 +22,9 @@ import torch
 import torch.distributed as dist
 
 
+_ROUTE_MAGIC = 0x5853425F524F5554  # header word of a fixed-capacity block ("XSB_ROUT", xsb_route.cu)
+
+
 def uniform_splits(n: int, world: int) -> List[int]:
     """Contiguous column slabs of (almost) equal width."""
     return [(n * r) // world for r in range(world)] + [n]
@@ -100,6 +103,10 @@ class DistExtendableSparseMatrix:
         self._recv = None
         self._lib_stream = None
         self.fixed_steps = 0
+        import os
+
+        self._phase_events = os.environ.get("XSB_DIST_TIMING", "") == "1"
+        self.last_device_phase_ms = None
 
     # insertion: global (i,j) on any rank
     def insert_batch(self, I, J, V, flavour=0):
@@ -113,8 +120,15 @@ class DistExtendableSparseMatrix:
 
     @staticmethod
     def _capacity(count: int) -> int:
-        """Block capacity for a bucket that held `count` records in the last counted step."""
-        return max(256, 2 * int(count))
+        """Block capacity for a bucket that held `count` records in the last counted step.  A pair of ranks that
+        exchanged nothing then is left out of the fixed-capacity steps altogether (capacity 0: a record for such a
+        rank later on makes the flush fail; `recount()` makes the next step a counted one again)."""
+        return 0 if int(count) == 0 else max(1024, 2 * int(count))
+
+    def recount(self):
+        """The next flush counts again (exact exchange) and re-derives the block capacities.  Collective."""
+        self._caps_out = self._caps_in = None
+        self._recv = None
 
     def _flush_fixed(self, mode, wait):
         """The step of an assembly LOOP: same routing, but with the block capacities agreed after the last counted
@@ -131,16 +145,51 @@ class DistExtendableSparseMatrix:
         if self._send is None or self._send.numel() < max(sum(in_split), 2):
             self._send = torch.empty(max(sum(in_split), 2), dtype=torch.int64, device=self.device)
         if self._recv is None or self._recv.numel() < max(sum(out_split), 2):
-            self._recv = torch.empty(max(sum(out_split), 2), dtype=torch.int64, device=self.device)
+            # every block starts with a header {records, magic}; the blocks of ranks that send nothing are never
+            # received into and keep the "no records" header written here
+            self._recv = torch.zeros(max(sum(out_split), 2), dtype=torch.int64, device=self.device)
+            pos = 0
+            for s in range(world):
+                if s != rank:
+                    self._recv[pos + 1] = _ROUTE_MAGIC
+                    pos += out_split[s]
         if self._lib_stream is None:
             self._lib_stream = torch.cuda.ExternalStream(h.stream, device=self.device)
         cnt = int(h.pending)
+        ev = None
+        if self._phase_events:  # device-side phase times (XSB_DIST_TIMING=1): events on the library's stream
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record(self._lib_stream)
         h.route_pack(self._send, co, sum(in_split) // 2)
-        with torch.cuda.stream(self._lib_stream):
-            dist.all_to_all_single(self._recv[: sum(out_split)], self._send[: sum(in_split)], output_split_sizes=out_split,
-                                   input_split_sizes=in_split, group=self.group)
+        if ev:
+            ev[1].record(self._lib_stream)
+        # point-to-point with the ranks this rank actually exchanges records with (an interface plane: the
+        # neighbours), grouped into one NCCL launch; no collective couples ranks that share nothing
+        ops, spos, rpos = [], 0, 0
+        for p in range(world):
+            if p == rank:
+                continue
+            if co[p] > 0:
+                ops.append(dist.P2POp(dist.isend, self._send[spos: spos + in_split[p]], p, group=self.group))
+            if ci[p] > 0:
+                ops.append(dist.P2POp(dist.irecv, self._recv[rpos: rpos + out_split[p]], p, group=self.group))
+            spos += in_split[p]
+            rpos += out_split[p]
+        if ops:
+            with torch.cuda.stream(self._lib_stream):
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()  # stream-level: the library's stream waits for the transfers, the host does not
+        if ev:
+            ev[2].record(self._lib_stream)
         h.route_unpack(self._recv, ci)
+        if ev:
+            ev[3].record(self._lib_stream)
         nnz, changed = h.flush(mode)
+        if ev:
+            ev[4].record(self._lib_stream)
+            ev[4].synchronize()
+            self.last_device_phase_ms = {"pack": ev[0].elapsed_time(ev[1]), "p2p": ev[1].elapsed_time(ev[2]),
+                                         "unpack": ev[2].elapsed_time(ev[3]), "flush": ev[3].elapsed_time(ev[4])}
         mine = torch.tensor([nnz, int(changed)], dtype=torch.int64, device=self.device)
         allv = torch.empty(2 * world, dtype=torch.int64, device=self.device)
         work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=True)
