@@ -176,3 +176,36 @@ def test_mt_setindex_of_new_entry_is_illegal(xsb):
     assert g.flush() == (1, True)
     h.close()
     g.close()
+
+
+def test_esmp_assembly_through_partition_buffers(xsb):
+    """the experimental ExtendableSparseMatrixParallel (addtoentry! into per-thread buffers with
+    local column numbering, flush! = plus_remap) restated in oracle/esmp.py, against the library's multi-partition
+    handle fed the same calls (GLOBAL columns, tid = thread): the pattern must be identical, the values `≈`
+    (test/ExperimentalParallel.jl:287; the reference's own summation order across threads is not defined)."""
+    from oracle.esmp import ESMP
+    from xsparse_b200 import dropin
+
+    rng = np.random.default_rng(21)
+    n, nt = 80, 4
+    owners = []
+    for j in range(n):
+        t = j * nt // n + 1
+        owners.append([t] if j % 5 else sorted({t, t % nt + 1}))
+    A = ESMP(n, nt, owners)
+    G = dropin.GenericMTExtendableSparseMatrixCSC(n, n, nt)
+    for splice in range(3):
+        for _ in range(2500):
+            j = int(rng.integers(1, n + 1))
+            tid = int(rng.choice(owners[j - 1]))
+            i = int(rng.integers(1, n + 1))
+            v = float(rng.standard_normal()) if rng.random() > 0.05 else 0.0
+            A.addtoentry(i, j, tid, v)
+            G.updateindex("+", v, i, j, tid)  # A[i,j] += v creates an entry only for a non-zero value: updateindex!
+        A.flush()
+        G.flush()
+        cp, rv, nz = G.sparse()
+        ocp, orv, onz = A.csc()
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+        assert np.allclose(nz, onz, rtol=1e-13, atol=1e-14)
+    dropin.release_handles()

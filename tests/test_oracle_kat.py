@@ -376,3 +376,50 @@ def test_pointblock_dense_property(oracle):
             ib = brv[k] - 1
             R[ib * bs:(ib + 1) * bs, jb * bs:(jb + 1) * bs] = bl[k].reshape(bs, bs).T  # column-major block
     assert np.array_equal(R, D.T)
+
+
+def _esmp_case(seed, n=60, nt=4, cnt=3000):
+    """Random assembly through the ESMP restatement: columns owned by slab threads, separator columns by two."""
+    rng = np.random.default_rng(seed)
+    owners = []
+    for j in range(n):
+        t = j * nt // n + 1
+        owners.append([t] if j % 7 else sorted({t, t % nt + 1}))
+    calls = []
+    for _ in range(cnt):
+        j = int(rng.integers(1, n + 1))
+        tid = int(rng.choice(owners[j - 1]))
+        v = float(rng.standard_normal()) if rng.random() > 0.05 else 0.0
+        calls.append((int(rng.integers(1, n + 1)), j, tid, v))
+    return owners, calls
+
+
+def test_esmp_restatement_matches_dense_accumulation():
+    """oracle/esmp.py (ExtendableSparseMatrixParallel: addtoentry! + sparse flush!, local column remap) against a
+    dense accumulator over two splices: test/ExperimentalParallel.jl:273-343 asks for `≈` and the CSC invariants."""
+    from oracle.esmp import ESMP
+
+    n, nt = 60, 4
+    owners, calls = _esmp_case(5, n, nt)
+    A = ESMP(n, nt, owners)
+    D = np.zeros((n, n))
+    touched = np.zeros((n, n), bool)
+    for part in (calls[:1500], calls[1500:]):
+        for i, j, tid, v in part:
+            A.addtoentry(i, j, tid, v)
+            D[i - 1, j - 1] += v
+            touched[i - 1, j - 1] |= (v != 0.0)
+        A.flush()
+        cp, rv, nz = A.csc()
+        assert cp[0] == 1 and cp[-1] == len(rv) + 1
+        got = np.zeros((n, n))
+        for j in range(n):
+            rows = rv[cp[j] - 1:cp[j + 1] - 1]
+            assert np.all(np.diff(rows) > 0)
+            got[rows - 1, j] = nz[cp[j] - 1:cp[j + 1] - 1]
+        assert np.allclose(got, D, rtol=1e-13, atol=1e-13)
+        # the pattern holds every entry that received a non-zero value (zero-sum entries stay: keep_zeros)
+        pat = np.zeros((n, n), bool)
+        for j in range(n):
+            pat[rv[cp[j] - 1:cp[j + 1] - 1] - 1, j] = True
+        assert np.all(pat[touched])
