@@ -240,9 +240,13 @@ __device__ __forceinline__ u64 warp_lookback(u64 *__restrict__ status, u32 index
         u64 v = LB_INCL;
         if (b - lane >= 0)
         {
-            do
+            for (;;)
+            {
                 v = ld_relaxed_u64(status + (b - lane));
-            while ((v >> 62) == 0ull);
+                if ((v >> 62) != 0ull)
+                    break;
+                __nanosleep(40); // the predecessor is still working: do not spend its issue slots on polling
+            }
         }
         const u32 inc = __ballot_sync(full, (v >> 62) == 2ull);
         const int first = inc ? __ffs(inc) - 1 : 31; // nearest tile with an inclusive prefix, if in this window

@@ -511,7 +511,10 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
                     }
                     mm = (pos & 1u) ? 2u : (rem > 1u ? 3u : 1u); // which records of the sector belong to the run
                     const u32 take = (mm + 1u) >> 1;
-                    qq = ld_pair_stream(reinterpret_cast<const Rec *>(base32 + (size_t)(pos >> 1) * 32u));
+                    const unsigned char *sec = base32 + (size_t)(pos >> 1) * 32u;
+                    qq = ld_pair_stream(reinterpret_cast<const Rec *>(sec));
+                    if (rem >= 12u) // long run: pull the sector four steps ahead from HBM into L2 meanwhile
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(sec + 160));
                     pos += take;
                     rem -= take;
                     left -= take;
