@@ -405,10 +405,11 @@ def run_ours(args):
 
     extra = {}
     if not args.no_legs:
-        extra["splice"] = measure_splice(args, xsb, h, mesh, n, n_ins, mode, peak)
         extra["fast"] = measure_fast(args, xsb, h, mesh, n_ins, st, peak)
+        extra["splice"] = measure_splice(args, xsb, h, mesh, n, n_ins, mode, peak)
     h.close()
     if not args.no_legs:
+        extra["cfg1_small"] = measure_small(args, xsb, local)
         extra["values_only"] = measure_values_only(args, xsb, torch, peak, local)
         extra["cfg5"] = measure_fd(args, xsb, peak, local, args.fd_n)
 
@@ -471,13 +472,18 @@ def measure_splice(args, xsb, h, mesh, n, n_ins, mode, peak):
                        "nnz": int(nnz1), "entries_per_s": n_ins / (ms / 1e3),
                        "flush_frac_of_hbm_peak": b / (st["ms_total"] / 1e3) / 1e9 / peak,
                        "workload": "the same FEM assembly onto the resident CSC: emit + flush!, nothing new"}
-    # (ii) 1 % new entries: random positions, 1 % of nnz of them
+    # (ii) 1 % new entries: random positions, 1 % of nnz of them (a first such splice lets the buffer rotation
+    # settle on the smaller store; the second one is timed)
     rng = np.random.default_rng(5)
     k = nnz0 // 100
-    I = rng.integers(1, n + 1, k)
-    J = rng.integers(1, n + 1, k)
-    V = rng.standard_normal(k)
-    h.insert_batch(I, J, V, xsb.UPDATE)
+    for _ in range(2):
+        nnz1 = h.nnz
+        I = rng.integers(1, n + 1, k)
+        J = rng.integers(1, n + 1, k)
+        V = rng.standard_normal(k)
+        h.insert_batch(I, J, V, xsb.UPDATE)
+        if _ == 0:
+            h.flush(mode)
     h.set_profiling(True)
     h.timer_start()
     nnz2, ch2 = h.flush(mode)
@@ -503,6 +509,35 @@ def measure_fast(args, xsb, h, mesh, n_ins, st_det, peak):
     ms = timed_steps(h, step, max(1, min(args.steps, 3)))
     return {"ms_per_step": ms, "entries_per_s": n_ins / (ms / 1e3), "mode": "XSB_FAST",
             "workload": "P1-FEM 128^3: emit + flush! in fast mode"}
+
+
+def measure_small(args, xsb, local):
+    """BASELINE.json configs[0]: fdrand 2-D 100x100 (10^4 unknowns, 79 600 updateindex! calls) -- latency-bound:
+    device time of reset! + insertion + flush! per assembly, and the number of kernel launches and host
+    synchronisations it takes."""
+    nx = 100
+    h = xsb.Handle(nx * nx, nx * nx, device=local)
+
+    def step():
+        h.reset()
+        h.emit_fdrand(nx, nx, 1, seed=1, flavour=xsb.UPDATE)
+        return h.flush()
+
+    for _ in range(5):
+        step()
+    l0 = h.kernel_launches
+    ms = timed_steps(h, step, 50)
+    launches = (h.kernel_launches - l0) / 50
+    t0 = time.perf_counter()
+    for _ in range(50):
+        step()
+    h.synchronize()
+    wall = (time.perf_counter() - t0) / 50 * 1e3
+    nnz = h.nnz
+    h.close()
+    return {"ms_per_assembly_device": ms, "ms_per_assembly_wall": wall, "kernel_launches_per_assembly": launches,
+            "host_syncs_in_flush": 2, "n_inserted": 79600, "nnz": int(nnz),
+            "workload": "fdrand 100x100 via updateindex! + flush! (BASELINE.json configs[0]); latency-bound"}
 
 
 def measure_values_only(args, xsb, torch, peak, local):
