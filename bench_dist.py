@@ -4,11 +4,11 @@ BASELINE.json configs[4] (fdrand 400^3, strong scaling) as the `cfg5` key of the
 Global mesh: 128 x 128 x (127*N + 1) nodes (Kuhn 6-tet).  Rank r emits the tetrahedra of its
 127 cube layers (245 805 960 rawupdateindex! calls, the same per-GPU work as the N=1 workload)
 and owns the columns of the z-planes [127 r, 127 (r+1)) (the last rank also owns the top plane).
-Records whose column lies on the interface plane travel to the rank above in one NCCL
-all-to-all; every rank then merges into its own CSC slab.  The assembled matrix is left
+Records whose column lies on the interface plane travel to the rank above in one grouped
+NCCL send/receive between neighbours; every rank then merges into its own CSC slab.  The assembled matrix is left
 sharded (slab-local colptr + global offset); that is what is timed.  The first (warm-up) step
 counts what every rank sends; the following steps use the fixed-capacity exchange
-(xsb_route_pack / xsb_route_unpack): no count visits the host, one collective per step.
+(xsb_route_pack / xsb_route_unpack): no count visits the host, one grouped point-to-point launch per step.
 """
 from __future__ import annotations
 
@@ -149,7 +149,7 @@ def run(args, xsb, rank, world, local):
         cfg = bench.workload(args)
         cfg["workload"] = (f"P1-FEM Laplacian+mass, {nx}x{ny}x{nz_nodes}-node Kuhn mesh sharded over {world} ranks "
                            f"({layers} cube layers = {n_ins_rank} rawupdateindex! calls per rank), column-slab ownership, "
-                           f"ONE NCCL all-to-all of fixed-capacity blocks per step (interface plane), CSC left sharded")
+                           f"one grouped NCCL send/receive of fixed-capacity blocks between neighbouring slabs per step (interface plane), CSC left sharded")
         cfg["parallelism"] = f"column-slab x{world}"
         cfg["exchange"] = exchange
         cfg["numa"] = numa
