@@ -124,6 +124,13 @@ struct xsb_matrix
         if (bytes == 0)
             bytes = 16;
         if (bytes >= kBigBytes)
+        { // size classes of four significant bits (at most 1/8 more than asked for): a CSC store that grows by a
+          // per cent per flush keeps fitting the block the flush before last gave back
+            const int sh = 60 - __builtin_clzll((unsigned long long)bytes);
+            const size_t m = ((size_t)1 << sh) - 1;
+            bytes = (bytes + m) & ~m;
+        }
+        if (bytes >= kBigBytes)
         { // large buffers (staging, sort scratch, CSC store) rotate through a per-handle cache:
           // in a steady assembly loop a flush allocates nothing (measured: the CUDA pool re-maps
           // gigabytes per flush once small allocations have split its free blocks)
