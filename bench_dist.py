@@ -134,10 +134,14 @@ def run(args, xsb, rank, world, local):
     roof = bench.roofline(st, {k: v / prof_steps for k, v in stage.items()}, ms_emit / prof_steps, h.n, peak, peak_src, None)
     roof["kernel"] += " [rank 0]"
     exchange = dict(D.last_exchange)
-    if D.last_device_phase_ms:
-        exchange["device_phase_ms_last_step"] = {k: round(v, 4) for k, v in D.last_device_phase_ms.items()}
+    if D.last_device_phase_ms:  # XSB_DIST_TIMING=1 (diagnostic: the events synchronise every step)
+        mine = {k: round(v, 4) for k, v in D.last_device_phase_ms.items()}
+        mine["emit"] = round(ms_emit / prof_steps, 4)
+        allp = [None] * world
+        dist.all_gather_object(allp, mine)
+        exchange["device_phase_ms_last_step_per_rank"] = allp
     nnz_global = int(D.nnz_global)
-    h.close()
+    D.close()
     del D
 
     cfg5 = None
@@ -216,7 +220,7 @@ def measure_e2e(args, xsb, xd, rank, world, local, mode):
     ms = timed_steps(g, step, steps, torch.device("cuda", local))
     tot = torch.tensor([cnt, 16 * cnt, 8 * (g.n + 1) + 16 * int(nnz)], dtype=torch.int64, device="cuda")
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    g.close()
+    D.close()
     return {"value": int(tot[0].item()) / (ms / 1e3), "unit": "entries/s", "h2d_bytes_per_step": int(tot[1].item()),
             "d2h_bytes_per_step": int(tot[2].item()), "ms_per_step": ms,
             "workload": f"P1-FEM {emesh}x{emesh}x{nz_nodes}-node mesh over {world} ranks, 16-byte triplets from pinned host "
@@ -262,5 +266,5 @@ def run_fd(args, xsb, xd, bench, rank, world, local, dev):
                             "nnz_new": st["nnz_new"]},
             "whole_job_flush_fraction_of_hbm_peak": b_flush / (ms_step / 1e3) / 1e9 / (peak * world),
             "nnz_global": nnz_global, "n_inserted": int(n_ins)}
-    h.close()
+    D.close()
     return line

@@ -91,6 +91,13 @@ SIGNATURES = {
     "xsb_route_finish": (_i32, [_p, _i32, _p, _i64]),
     "xsb_route_pack": (_i32, [_p, _p, C.POINTER(_i64), _i64]),
     "xsb_route_unpack": (_i32, [_p, _p, C.POINTER(_i64)]),
+    "xsb_peer_exchange_create": (_i32, [_p, C.POINTER(_i64), _p]),
+    "xsb_peer_exchange_connect": (_i32, [_p, _p]),
+    "xsb_peer_exchange_connect_local": (_i32, [_p, C.POINTER(_p)]),
+    "xsb_peer_exchange_disconnect": (_i32, [_p]),
+    "xsb_peer_exchange_destroy": (_i32, [_p]),
+    "xsb_route_pack_peer": (_i32, [_p]),
+    "xsb_route_unpack_peer": (_i32, [_p]),
     "xsb_destroy": (_i32, [_p]),
     "xsb_last_error": (C.c_char_p, [_p]),
     "xsb_reset": (_i32, [_p]),
@@ -286,6 +293,37 @@ class Handle:
         """Fixed-capacity exchange: the received blocks (sources ascending, own rank left out) become staged regions."""
         arr = (_i64 * max(self.n_ranks, 1))(*[int(c) for c in caps])
         self._c(lib().xsb_route_unpack(self._h, ptr(recv_records), arr))
+
+    # peer exchange (NVLink peer memory; see include/xsparse_b200.h)
+    def peer_exchange_create(self, caps) -> bytes:
+        """caps[dst][src] (or flat, dst-major) = slots of the block src -> dst; returns this rank's 64-byte IPC handle."""
+        flat = [int(c) for row in caps for c in (row if hasattr(row, "__len__") else [row])]
+        assert len(flat) == self.n_ranks ** 2, "caps must be n_ranks x n_ranks"
+        arr = (_i64 * len(flat))(*flat)
+        out = C.create_string_buffer(64)
+        self._c(lib().xsb_peer_exchange_create(self._h, arr, C.cast(out, _p)))
+        return out.raw
+
+    def peer_exchange_connect(self, handles: bytes):
+        assert len(handles) == 64 * self.n_ranks
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        self._c(lib().xsb_peer_exchange_connect(self._h, C.cast(buf, _p)))
+
+    def peer_exchange_connect_local(self, peers):
+        arr = (_p * self.n_ranks)(*[(p._h if p is not None else None) for p in peers])
+        self._c(lib().xsb_peer_exchange_connect_local(self._h, arr))
+
+    def peer_exchange_disconnect(self):
+        self._c(lib().xsb_peer_exchange_disconnect(self._h))
+
+    def peer_exchange_destroy(self):
+        self._c(lib().xsb_peer_exchange_destroy(self._h))
+
+    def route_pack_peer(self):
+        self._c(lib().xsb_route_pack_peer(self._h))
+
+    def route_unpack_peer(self):
+        self._c(lib().xsb_route_unpack_peer(self._h))
 
     def get_stream(self) -> int:
         """cudaStream_t of the handle (an integer address; wrap with torch.cuda.ExternalStream)."""

@@ -108,6 +108,25 @@ struct xsb_matrix
     u64 *h_route = nullptr;    // pinned: block bases / capacities handed to the kernels (2 * kMaxRanks), results (4)
     bool fixed_exchange = false; // the staged regions of other ranks are capacity-sized blocks (n_low / n_high: upper bounds)
 
+    // Peer exchange (xsb_peer_exchange_*): the blocks of the fixed-capacity exchange are written straight into the
+    // MAILBOX of the receiving rank (its GPU's memory, mapped here through CUDA IPC or, inside one process, used
+    // directly) by the copy-out kernel; flags in the mailboxes order the steps.  Mailbox of rank r:
+    //   u64 ready[kMaxRanks]  ready[s] = last step whose block from s is complete   (written by s)
+    //   u64 done[kMaxRanks]   done[d]  = last step whose block TO d was taken by d  (written by d)
+    //   at 512 B: for every source s with caps[r][s] > 0, ascending: two blocks (step parity) of
+    //             round16(1 + caps[r][s]) records each
+    struct PeerExchange
+    {
+        bool created = false, connected = false, packed = false;
+        unsigned char *box = nullptr;
+        size_t box_bytes = 0;
+        unsigned char *peer[kMaxRanks] = {};
+        bool peer_ipc[kMaxRanks] = {};
+        i64 caps[kMaxRanks * kMaxRanks] = {}; // [dst * nranks + src]
+        u64 seq = 0;                          // steps packed so far
+        u64 timeout_ns = 30000000000ull;
+    } px;
+
     LaunchCounter lc;
     bool profiling = false;
     xsb_flush_stats stats{};
@@ -550,6 +569,8 @@ bool runs_eligible(const xsb_matrix *h);
 void check_exchange(xsb_matrix *h)
 {
     const u64 flags = h->h_route[2 * kMaxRanks];
+    REQUIRE((flags & 8ull) == 0, XSB_ESTATE,
+            "peer exchange: a rank did not deliver (or take) its block in time (XSB_PEER_TIMEOUT_MS); the ranks are out of step");
     REQUIRE((flags & 4ull) == 0, XSB_EINVAL, "a received block carries no header: capacities of sender and receiver differ");
     REQUIRE((flags & 2ull) == 0, XSB_ESTATE,
             "a bucket of the exchange did not fit its block: records were cut off; reset! and repeat the step with larger "
@@ -1513,6 +1534,80 @@ int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_recor
 // -- a 16-byte header {records of the bucket, magic} followed by caps[d] record slots -- block after block in
 // `send_records` (device; room for sum(caps[d] + 1) records).  Nothing is read back: the whole call is stream-ordered.
 // A bucket fuller than its block is cut off; the receiving rank's flush reports it (XSB_ESTATE).
+namespace
+{
+// common part of xsb_route_pack / xsb_route_pack_peer: h->h_route[d] holds the address of block d's first slot
+void pack_blocks(xsb_matrix *h, const i64 *caps, const PeerFlags &sig)
+{
+    Stage &st = h->stage[0];
+    if (!st.buf)
+        h->ensure_stage(0, 0);
+    h->dfree(h->route_ws);
+    h->route_ws = h->dalloc(route_workspace_bytes((u64)std::max<i64>(st.count, 1), h->nranks));
+    route_pack(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, caps, h->h_route, h->h_route + kMaxRanks, sig,
+               h->d_route, h->lc, h->tileflags);
+    h->route_counted = -1;
+    h->foreign = 0; // unknown on the host: the flush skips them by their owner bits
+    h->routed = true;
+    h->fixed_exchange = true;
+    pad_region(h);
+    h->own_end = st.count;
+}
+
+// common part of xsb_route_unpack / xsb_route_unpack_peer: blocks[src] = header of the block from rank src
+void unpack_blocks(xsb_matrix *h, const Rec *const *blocks, const i64 *caps)
+{
+    if (!h->routed)
+    { // nothing was staged on this rank: the own region is empty
+        h->ensure_stage(0, 0);
+        h->own_end = 0;
+    }
+    h->routed = true;
+    h->fixed_exchange = true;
+    h->has_assign = true; // flavours of the received records are not inspected on the host: ordered fold
+    for (int src = 0; src < h->nranks; ++src)
+    {
+        if (src == h->rank)
+        { // the region of the lower ranks is complete
+            pad_region(h);
+            h->low_end = h->stage[0].count;
+            continue;
+        }
+        const i64 cap = caps[src];
+        if (blocks[src])
+        { // also for cap == 0: the header must say "no records"
+            h->ensure_stage(0, cap);
+            Stage &st = h->stage[0];
+            route_unpack(h->stream, blocks[src], cap, st.buf + st.front + st.count, h->L, h->n, h->d_route, h->d_route + 1,
+                         src < h->rank ? 0 : 1, h->lc);
+            st.count += cap;
+            (src < h->rank ? h->n_low : h->n_high) += cap;
+        }
+        h->last_src = src;
+    }
+    if (h->low_end < 0)
+        h->low_end = h->stage[0].count;
+}
+
+size_t px_block_records(i64 cap) { return ((size_t)cap + 1 + 15) & ~(size_t)15; }
+// byte offset of the block src -> dst (step parity p) in dst's mailbox; total size for src == nranks
+size_t px_offset(const i64 *caps, int nranks, int dst, int src, int parity)
+{
+    size_t off = 512;
+    for (int s2 = 0; s2 < nranks; ++s2)
+    {
+        const i64 cap = caps[dst * nranks + s2];
+        if (s2 == dst || cap <= 0)
+            continue;
+        const size_t bytes = 16 * px_block_records(cap);
+        if (s2 == src)
+            return off + (size_t)parity * bytes;
+        off += 2 * bytes;
+    }
+    return off;
+}
+} // namespace
+
 int32_t xsb_route_pack(xsb_matrix *h, void *send_records, const int64_t *caps, int64_t send_capacity)
 {
     return guard(h, [&]() -> int32_t {
@@ -1528,20 +1623,15 @@ int32_t xsb_route_pack(xsb_matrix *h, void *send_records, const int64_t *caps, i
             }
         REQUIRE(send_capacity >= need, XSB_EINVAL, "send buffer too small for the blocks");
         REQUIRE(need == 0 || (send_records && is_device_ptr(send_records)), XSB_EINVAL, "send buffer must be device memory");
-        Stage &st = h->stage[0];
-        if (!st.buf)
-            h->ensure_stage(0, 0);
-        h->dfree(h->route_ws);
-        h->route_ws = h->dalloc(route_workspace_bytes((u64)std::max<i64>(st.count, 1), h->nranks));
-        if (need > 0)
-            route_pack(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, reinterpret_cast<const i64 *>(caps), h->h_route, h->h_route + kMaxRanks,
-                       static_cast<Rec *>(send_records), h->lc, h->tileflags);
-        h->route_counted = -1;
-        h->foreign = 0; // unknown on the host: the flush skips them by their owner bits
-        h->routed = true;
-        h->fixed_exchange = true;
-        pad_region(h);
-        h->own_end = st.count;
+        Rec *blk = static_cast<Rec *>(send_records);
+        for (int d = 0; d < h->nranks; ++d)
+        {
+            h->h_route[d] = d == h->rank ? 0ull : reinterpret_cast<u64>(blk + 1); // first slot behind the header
+            if (d != h->rank)
+                blk += caps[d] + 1;
+        }
+        PeerFlags none{};
+        pack_blocks(h, reinterpret_cast<const i64 *>(caps), none);
         return XSB_OK;
     });
 }
@@ -1565,37 +1655,267 @@ int32_t xsb_route_unpack(xsb_matrix *h, const void *recv_records, const int64_t 
                 total += caps[s2];
             }
         REQUIRE(total == 0 || (recv_records && is_device_ptr(recv_records)), XSB_EINVAL, "receive buffer must be device memory");
-        if (!h->routed)
-        { // nothing was staged on this rank: the own region is empty
-            h->ensure_stage(0, 0);
-            h->own_end = 0;
-        }
-        h->routed = true;
-        h->fixed_exchange = true;
-        h->has_assign = true; // flavours of the received records are not inspected on the host: ordered fold
+        const Rec *blocks[kMaxRanks] = {};
         const Rec *blk = static_cast<const Rec *>(recv_records);
-        for (int src = 0; src < h->nranks; ++src)
+        for (int src = 0; src < h->nranks && blk; ++src)
+            if (src != h->rank)
+            {
+                blocks[src] = blk;
+                blk += caps[src] + 1;
+            }
+        unpack_blocks(h, blocks, reinterpret_cast<const i64 *>(caps));
+        return XSB_OK;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Peer exchange: the fixed-capacity exchange over NVLink peer memory, without a communication library on the
+// records' path.  Setup (collective over the ranks of one node, host side):
+//   every rank: xsb_peer_exchange_create(h, caps, handle)   caps[dst * n_ranks + src] = slots of the block src -> dst,
+//               the same matrix on every rank; allocates this rank's mailbox and exports it (64-byte CUDA IPC handle)
+//   all-gather the handles (any transport: they are plain bytes)
+//   every rank: xsb_peer_exchange_connect(h, handles)       maps the mailboxes of the ranks it exchanges blocks with
+// Step: xsb_route_pack_peer(h) (the copy-out kernel stores every block into its receiver's mailbox and raises the
+// receiver's flag) -> xsb_route_unpack_peer(h) (waits for the flags of this step, takes the blocks, tells the
+// senders that their blocks were taken) -> xsb_flush.  Everything is stream-ordered on the handle's stream; two
+// blocks per pair (step parity) let a sender run one step ahead of its receiver.  Every rank makes both calls in
+// every step.  Teardown: xsb_peer_exchange_disconnect on every rank, a barrier, xsb_peer_exchange_destroy.
+// ------------------------------------------------------------------------------------------------------------
+int32_t xsb_peer_exchange_create(xsb_matrix *h, const int64_t *caps, void *ipc_handle_out)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && caps, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(!h->px.created, XSB_ESTATE, "this handle has a peer exchange already: destroy it first");
+        const int nr = h->nranks;
+        for (int k = 0; k < nr * nr; ++k)
+            REQUIRE(caps[k] >= 0, XSB_EINVAL, "negative block capacity");
+        auto &px = h->px;
+        std::memcpy(px.caps, caps, sizeof(i64) * (size_t)nr * nr);
+        px.box_bytes = px_offset(px.caps, nr, h->rank, nr, 0);
+        // cudaMalloc, not the stream-ordered pool: only such memory can be exported to another process
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&px.box), px.box_bytes);
+        if (e != cudaSuccess)
         {
-            if (src == h->rank)
-            { // the region of the lower ranks is complete
-                pad_region(h);
-                h->low_end = h->stage[0].count;
-                continue;
-            }
-            const i64 cap = caps[src];
-            { // also for cap == 0: the header must say "no records"
-                h->ensure_stage(0, cap);
-                Stage &st = h->stage[0];
-                route_unpack(h->stream, blk, cap, st.buf + st.front + st.count, h->L, h->n, h->d_route, h->d_route + 1,
-                             src < h->rank ? 0 : 1, h->lc);
-                st.count += cap;
-                (src < h->rank ? h->n_low : h->n_high) += cap;
-            }
-            blk += cap + 1;
-            h->last_src = src;
+            cudaGetLastError();
+            px.box = nullptr;
+            throw ApiError(XSB_ENOMEM, std::string("mailbox allocation failed: ") + cudaGetErrorString(e));
         }
-        if (h->low_end < 0)
-            h->low_end = h->stage[0].count;
+        XSB_CUDA(cudaMemsetAsync(px.box, 0, px.box_bytes, h->stream));
+        XSB_CUDA(cudaStreamSynchronize(h->stream));
+        if (ipc_handle_out)
+        {
+            cudaIpcMemHandle_t ih;
+            e = cudaIpcGetMemHandle(&ih, px.box);
+            if (e != cudaSuccess)
+            {
+                cudaGetLastError();
+                cudaFree(px.box);
+                px.box = nullptr;
+                throw ApiError(XSB_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+            }
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+            std::memcpy(ipc_handle_out, &ih, 64);
+        }
+        px.seq = 0;
+        px.created = true;
+        px.connected = false;
+        px.packed = false;
+        if (const char *t = std::getenv("XSB_PEER_TIMEOUT_MS"))
+            px.timeout_ns = (u64)std::max(1ll, std::atoll(t)) * 1000000ull;
+        return XSB_OK;
+    });
+}
+
+namespace
+{
+bool px_talks_to(const xsb_matrix *h, int r)
+{
+    const int nr = h->nranks;
+    return r != h->rank && (h->px.caps[r * nr + h->rank] > 0 || h->px.caps[h->rank * nr + r] > 0);
+}
+} // namespace
+
+int32_t xsb_peer_exchange_connect(xsb_matrix *h, const void *ipc_handles)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && ipc_handles, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->px.created && !h->px.connected, XSB_ESTATE, "xsb_peer_exchange_create comes first (once)");
+        auto &px = h->px;
+        for (int r = 0; r < h->nranks; ++r)
+        {
+            if (!px_talks_to(h, r))
+                continue;
+            cudaIpcMemHandle_t ih;
+            std::memcpy(&ih, static_cast<const unsigned char *>(ipc_handles) + 64 * (size_t)r, 64);
+            void *p = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+            {
+                cudaGetLastError();
+                for (int q = 0; q < r; ++q)
+                    if (px.peer[q] && px.peer_ipc[q])
+                    {
+                        cudaIpcCloseMemHandle(px.peer[q]);
+                        px.peer[q] = nullptr;
+                    }
+                throw ApiError(XSB_ECUDA, "cannot map the mailbox of rank " + std::to_string(r) + " (" + cudaGetErrorString(e) +
+                                              "): the ranks must be processes on one node whose GPUs have peer access");
+            }
+            px.peer[r] = static_cast<unsigned char *>(p);
+            px.peer_ipc[r] = true;
+        }
+        px.connected = true;
+        return XSB_OK;
+    });
+}
+
+// ranks that live in ONE process (several handles, one or several GPUs with peer access): no IPC, the mailboxes of
+// the other handles are used directly.  peers[r] = handle of rank r (peers[own rank] is ignored).
+int32_t xsb_peer_exchange_connect_local(xsb_matrix *h, xsb_matrix *const *peers)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h && peers, XSB_EINVAL, "NULL argument");
+        REQUIRE(h->px.created && !h->px.connected, XSB_ESTATE, "xsb_peer_exchange_create comes first (once)");
+        auto &px = h->px;
+        for (int r = 0; r < h->nranks; ++r)
+        {
+            if (!px_talks_to(h, r))
+                continue;
+            REQUIRE(peers[r] && peers[r]->px.created && peers[r]->nranks == h->nranks && peers[r]->rank == r, XSB_EINVAL,
+                    "peers[r] must be the handle of rank r with a mailbox");
+            REQUIRE(std::memcmp(peers[r]->px.caps, px.caps, sizeof(i64) * (size_t)h->nranks * h->nranks) == 0, XSB_EINVAL,
+                    "the ranks disagree on the block capacities");
+            if (peers[r]->device != h->device)
+            {
+                int can = 0;
+                XSB_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peers[r]->device));
+                REQUIRE(can, XSB_ESTATE, "no peer access between the GPUs of two ranks");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    XSB_CUDA(e);
+                cudaGetLastError();
+            }
+            px.peer[r] = peers[r]->px.box;
+            px.peer_ipc[r] = false;
+        }
+        px.connected = true;
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_peer_exchange_disconnect(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        auto &px = h->px;
+        if (!px.created)
+            return XSB_OK;
+        XSB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < kMaxRanks; ++r)
+        {
+            if (px.peer[r] && px.peer_ipc[r])
+                cudaIpcCloseMemHandle(px.peer[r]);
+            px.peer[r] = nullptr;
+            px.peer_ipc[r] = false;
+        }
+        cudaGetLastError();
+        px.connected = false;
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_peer_exchange_destroy(xsb_matrix *h)
+{
+    const int32_t rc = xsb_peer_exchange_disconnect(h);
+    if (rc != XSB_OK)
+        return rc;
+    return guard(h, [&]() -> int32_t {
+        auto &px = h->px;
+        if (px.box)
+            cudaFree(px.box);
+        cudaGetLastError();
+        px.box = nullptr;
+        px.box_bytes = 0;
+        px.created = false;
+        px.packed = false;
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_route_pack_peer(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(h->px.connected, XSB_ESTATE, "no peer exchange: xsb_peer_exchange_create / _connect come first");
+        REQUIRE(!h->routed, XSB_ESTATE, "staged records were already routed");
+        REQUIRE(!h->px.packed, XSB_ESTATE, "xsb_route_unpack_peer of the previous step is missing");
+        auto &px = h->px;
+        const int nr = h->nranks, me = h->rank;
+        const u64 seq = ++px.seq;
+        const int parity = (int)(seq & 1ull);
+        i64 caps_out[kMaxRanks] = {};
+        PeerFlags waitf{}, sig{};
+        bool any_wait = false;
+        for (int d = 0; d < nr; ++d)
+        {
+            h->h_route[d] = 0ull;
+            caps_out[d] = d == me ? 0 : px.caps[d * nr + me];
+            if (d == me || caps_out[d] <= 0)
+                continue;
+            unsigned char *blk = px.peer[d] + px_offset(px.caps, nr, d, me, parity);
+            h->h_route[d] = reinterpret_cast<u64>(blk + 16);
+            sig.addr[d] = reinterpret_cast<u64>(px.peer[d] + 8 * (size_t)me); // ready[me] of rank d
+            sig.value[d] = seq;
+            if (seq > 2)
+            { // the block of this parity was last used in step seq - 2: d must have taken it
+                waitf.addr[d] = reinterpret_cast<u64>(px.box + 8 * (size_t)(kMaxRanks + d)); // done[d], own mailbox
+                waitf.value[d] = seq - 2;
+                any_wait = true;
+            }
+        }
+        if (any_wait)
+            peer_wait(h->stream, waitf, px.timeout_ns, h->d_route, h->lc);
+        pack_blocks(h, caps_out, sig);
+        px.packed = true;
+        return XSB_OK;
+    });
+}
+
+int32_t xsb_route_unpack_peer(xsb_matrix *h)
+{
+    return guard(h, [&]() -> int32_t {
+        REQUIRE(h, XSB_EINVAL, "NULL handle");
+        REQUIRE(h->nranks > 0, XSB_ESTATE, "not a slab handle");
+        REQUIRE(h->px.connected && h->px.packed, XSB_ESTATE, "xsb_route_pack_peer of this step comes first");
+        REQUIRE(h->last_src < 0, XSB_ESTATE, "records of other ranks were already appended");
+        auto &px = h->px;
+        const int nr = h->nranks, me = h->rank;
+        const u64 seq = px.seq;
+        const int parity = (int)(seq & 1ull);
+        i64 caps_in[kMaxRanks] = {};
+        const Rec *blocks[kMaxRanks] = {};
+        PeerFlags waitf{}, sig{};
+        bool any = false;
+        for (int s2 = 0; s2 < nr; ++s2)
+        {
+            caps_in[s2] = s2 == me ? 0 : px.caps[me * nr + s2];
+            if (s2 == me || caps_in[s2] <= 0)
+                continue;
+            blocks[s2] = reinterpret_cast<const Rec *>(px.box + px_offset(px.caps, nr, me, s2, parity));
+            waitf.addr[s2] = reinterpret_cast<u64>(px.box + 8 * (size_t)s2); // ready[s2], own mailbox
+            waitf.value[s2] = seq;
+            sig.addr[s2] = reinterpret_cast<u64>(px.peer[s2] + 8 * (size_t)(kMaxRanks + me)); // done[me] of rank s2
+            sig.value[s2] = seq;
+            any = true;
+        }
+        if (any)
+            peer_wait(h->stream, waitf, px.timeout_ns, h->d_route, h->lc);
+        unpack_blocks(h, blocks, caps_in);
+        if (any)
+            peer_signal(h->stream, sig, h->lc);
+        px.packed = false;
         return XSB_OK;
     });
 }
@@ -1607,6 +1927,11 @@ int32_t xsb_destroy(xsb_matrix *h)
     cudaSetDevice(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (h->px.peer[r] && h->px.peer_ipc[r])
+            cudaIpcCloseMemHandle(h->px.peer[r]);
+    if (h->px.box)
+        cudaFree(h->px.box);
     h->drop_frozen();
     h->drop_blocks();
     h->clear_staging(true);

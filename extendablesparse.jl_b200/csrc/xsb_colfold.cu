@@ -1373,7 +1373,8 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
             level = g_thread_hbits - 4;
         CtArgs a{sorted, L.low, L.rowbits, (u32)std::max<u64>(256, 6 * avg), nzcol, nzstart, totals, tmp, cnt,
                  nullptr, nullptr, nullptr, nullptr, longlist, counters + 2, d_maxd};
-        const unsigned blocks = (unsigned)((kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32));
+        // (nothing but skipped records: one block that finds no column)
+        const unsigned blocks = (unsigned)std::max<u64>(1, (kmax + CT_WARPS * 32 - 1) / (CT_WARPS * 32));
         const unsigned lblocks = (unsigned)std::min<u64>(blocks, (u64)kNumSM * 8);
         u32 *lists[2] = {listA, listB};
         for (int lv = level, hop = 0; lv <= 2; ++lv, ++hop)
@@ -1398,7 +1399,7 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         const size_t smem = sizeof(WarpSpace<true>) * W;
         static FuncAttrOnce once;
         once.set(colfold_kernel<true, W, false>, (int)smem);
-        colfold_kernel<true, W, false><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(
+        colfold_kernel<true, W, false><<<std::max(1u, (ntiles + W - 1) / W), W * 32, smem, stream>>>(
             sorted, L, combine, chunk, nzcol, nzstart, tilek, ntiles, tmp, cnt, d_overflow, nullptr, nullptr);
     }
     else
@@ -1407,7 +1408,7 @@ void colfold_reduce(cudaStream_t stream, const Rec *sorted, u64 nrec, KeyLayout 
         const size_t smem = sizeof(WarpSpace<false>) * W;
         static FuncAttrOnce once;
         once.set(colfold_kernel<false, W, false>, (int)smem);
-        colfold_kernel<false, W, false><<<(ntiles + W - 1) / W, W * 32, smem, stream>>>(
+        colfold_kernel<false, W, false><<<std::max(1u, (ntiles + W - 1) / W), W * 32, smem, stream>>>(
             sorted, L, combine, chunk, nzcol, nzstart, tilek, ntiles, tmp, cnt, d_overflow, nullptr, nullptr);
     }
     lc.add();

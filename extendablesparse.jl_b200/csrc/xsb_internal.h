@@ -254,8 +254,17 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
                    const u64 *counts_host, Rec *send, LaunchCounter &lc);
 void route_fill_skipped(cudaStream_t stream, Rec *out, i64 count, const KeyLayout &L, LaunchCounter &lc);
 // fixed-capacity exchange (no count visits the host): see xsb_route.cu
+// flags in device memory (own or a peer's) with the values to wait for / to store; addr 0 = unused entry
+struct PeerFlags
+{
+    u64 addr[kMaxRanks];
+    u64 value[kMaxRanks];
+};
 void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, const i64 *caps,
-                u64 *pinned_bases, u64 *pinned_caps, Rec *send, LaunchCounter &lc, const unsigned char *tileflags);
+                u64 *pinned_addr, u64 *pinned_caps, const PeerFlags &sig, u64 *d_flags, LaunchCounter &lc,
+                const unsigned char *tileflags);
+void peer_wait(cudaStream_t stream, const PeerFlags &w, u64 timeout_ns, u64 *d_flags, LaunchCounter &lc);
+void peer_signal(cudaStream_t stream, const PeerFlags &sgn, LaunchCounter &lc);
 void route_unpack(cudaStream_t stream, const Rec *block, i64 cap, Rec *out, const KeyLayout &L, i64 ncols, u64 *d_flags,
                   u64 *d_counts, int which, LaunchCounter &lc);
 void route_check(cudaStream_t stream, const Rec *in, i64 count, const KeyLayout &L, i64 ncols, u64 *d_err,

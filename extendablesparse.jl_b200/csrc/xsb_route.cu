@@ -185,11 +185,12 @@ route_scan_lookback_kernel(const u32 *__restrict__ tilecnt, u32 *__restrict__ ti
     }
 }
 
-// bucket_base[d] = where rank d's bucket starts in the send buffer
+// bucket_addr[d] = address of the first record slot of rank d's bucket: in the send buffer, or in the mailbox of
+// rank d itself (peer memory over NVLink: the copy-out IS the transfer)
 __global__ void __launch_bounds__(RT_THREADS)
 route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershift, u32 me, int nranks,
                      const u32 *__restrict__ tilecnt, const u32 *__restrict__ tileoff,
-                     const u64 *__restrict__ bucket_base, const u64 *__restrict__ bucket_cap, Rec *__restrict__ send)
+                     const u64 *__restrict__ bucket_addr, const u64 *__restrict__ bucket_cap)
 {
     __shared__ u32 s_w[RT_THREADS / 32];
     __shared__ u32 s_run;
@@ -239,7 +240,7 @@ route_extract_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershi
                 s_run = 0;
             __syncthreads();
             const u32 toff = tileoff[tile * nranks + d];
-            Rec *dst = send + bucket_base[d] + toff;
+            Rec *dst = reinterpret_cast<Rec *>(bucket_addr[d]) + toff;
             // fixed-capacity exchange: a bucket that is fuller than its block is cut off (its header says so)
             const u64 room = bucket_cap != nullptr ? bucket_cap[d] : ~0ull;
 #pragma unroll
@@ -364,7 +365,7 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
     u64 run = 0;
     for (int d = 0; d < nr; ++d)
     {
-        hb[d] = run;
+        hb[d] = reinterpret_cast<u64>(send + run);
         if (d != L.self)
             run += counts_host[d];
     }
@@ -372,7 +373,7 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
         return;
     XSB_CUDA(cudaMemcpyAsync(bucket_base, hb, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
     route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
-        in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, nullptr, send);
+        in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, nullptr);
     lc.add();
     XSB_CUDA(cudaGetLastError());
     XSB_CUDA(cudaStreamSynchronize(stream)); // hb lives on this stack frame
@@ -386,39 +387,115 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
 // ------------------------------------------------------------------------
 constexpr u64 kRouteMagic = 0x5853425f524f5554ull; // "XSB_ROUT"
 
-__global__ void route_header_kernel(const u64 *__restrict__ total, const u64 *__restrict__ bucket_base, int nranks, u32 me,
-                                    Rec *__restrict__ send)
+// flags of a mailbox are read and written by two GPUs
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 global_ns()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Headers of the blocks (bucket_addr[d] != 0: this rank sends to d), written behind the extraction in stream
+// order.  Peer exchange: the block lives in rank d's mailbox; once the header is out, `seq` is stored with
+// release semantics at system scope into d's ready flag: everything this stream wrote to d's memory before
+// -- the records of the extraction kernel, the header -- is visible to a reader on d that saw the flag.
+__global__ void route_header_kernel(const u64 *__restrict__ total, const u64 *__restrict__ bucket_addr,
+                                    const u64 *__restrict__ bucket_cap, int nranks, u32 me, PeerFlags sig,
+                                    u64 *__restrict__ d_flags)
 {
     const int d = threadIdx.x;
-    if (d < nranks && (u32)d != me)
+    if (d < nranks && (u32)d != me && total[d] > bucket_cap[d]) // also for ranks without a block (capacity 0)
+        atomicOr(reinterpret_cast<unsigned long long *>(d_flags), 2ull);
+    if (d < nranks && (u32)d != me && bucket_addr[d] != 0ull)
     {
         Rec r;
         r.key = total[d];
         r.val = __longlong_as_double((long long)kRouteMagic);
-        st_rec(send + bucket_base[d] - 1, r);
+        st_rec(reinterpret_cast<Rec *>(bucket_addr[d]) - 1, r);
+        if (sig.addr[d] != 0ull)
+        {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<u64 *>(sig.addr[d]), sig.value[d]);
+        }
     }
 }
 
-// pinned_bases / pinned_caps: host staging (pinned, kMaxRanks entries each) that outlives the call
+// One thread per flag: waits until the flag (in THIS GPU's memory, written by a peer) reaches value[k].  Polite
+// polling; gives up after timeout_ns and raises bit 3 of *d_flags (the flush then fails instead of hanging).
+__global__ void peer_wait_kernel(PeerFlags w, u64 timeout_ns, u64 *__restrict__ d_flags)
+{
+    const int k = threadIdx.x;
+    if (k >= kMaxRanks || w.addr[k] == 0ull)
+        return;
+    const u64 *p = reinterpret_cast<const u64 *>(w.addr[k]);
+    const u64 t0 = global_ns();
+    unsigned ns = 32;
+    while (ld_acquire_sys(p) < w.value[k])
+    {
+        __nanosleep(ns);
+        ns = min(ns * 2u, 2048u);
+        if (global_ns() - t0 > timeout_ns)
+        {
+            atomicOr(reinterpret_cast<unsigned long long *>(d_flags), 8ull);
+            break;
+        }
+    }
+}
+
+// value[k] -> flag k (in a peer's memory), after everything this stream did before
+__global__ void peer_signal_kernel(PeerFlags sgn)
+{
+    const int k = threadIdx.x;
+    if (k < kMaxRanks && sgn.addr[k] != 0ull)
+    {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<u64 *>(sgn.addr[k]), sgn.value[k]);
+    }
+}
+
+void peer_wait(cudaStream_t stream, const PeerFlags &w, u64 timeout_ns, u64 *d_flags, LaunchCounter &lc)
+{
+    peer_wait_kernel<<<1, kMaxRanks, 0, stream>>>(w, timeout_ns, d_flags);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+void peer_signal(cudaStream_t stream, const PeerFlags &sgn, LaunchCounter &lc)
+{
+    peer_signal_kernel<<<1, kMaxRanks, 0, stream>>>(sgn);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
+// pinned_addr / pinned_caps: host staging (pinned, kMaxRanks entries each) that outlives the call.
+// pinned_addr[d] (filled by the caller) = address of the first record slot of the block for rank d (its header sits
+// one record below), 0 = nothing is sent to d; caps[d] = slots of that block.  sig: flags to raise once a block is
+// complete (peer exchange), all-zero otherwise.  A bucket that outgrew its block raises bit 1 of *d_flags on the
+// SENDER too (the receiver sees it in the header).
 void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, void *workspace, const i64 *caps,
-                u64 *pinned_bases, u64 *pinned_caps, Rec *send, LaunchCounter &lc, const unsigned char *tileflags)
+                u64 *pinned_addr, u64 *pinned_caps, const PeerFlags &sig, u64 *d_flags, LaunchCounter &lc,
+                const unsigned char *tileflags)
 {
     const int nr = L.nranks;
     const u64 ntiles = (n + RT_TILE - 1) / RT_TILE;
     u32 *tilecnt = static_cast<u32 *>(workspace);
     u32 *tileoff = tilecnt + (size_t)ntiles * nr;
     u64 *total = reinterpret_cast<u64 *>(tileoff + (size_t)ntiles * nr);
-    u64 *bucket_base = total + kMaxRanks;
-    u64 *bucket_cap = bucket_base + kMaxRanks;
-    u64 run = 0;
+    u64 *bucket_addr = total + kMaxRanks;
+    u64 *bucket_cap = bucket_addr + kMaxRanks;
     for (int d = 0; d < nr; ++d)
-    {
-        pinned_caps[d] = d == L.self ? 0ull : (u64)caps[d];
-        pinned_bases[d] = run + 1; // first slot behind the header
-        if (d != L.self)
-            run += (u64)caps[d] + 1;
-    }
-    XSB_CUDA(cudaMemcpyAsync(bucket_base, pinned_bases, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
+        pinned_caps[d] = (d == L.self || pinned_addr[d] == 0ull) ? 0ull : (u64)caps[d];
+    XSB_CUDA(cudaMemcpyAsync(bucket_addr, pinned_addr, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
     XSB_CUDA(cudaMemcpyAsync(bucket_cap, pinned_caps, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
     XSB_CUDA(cudaMemsetAsync(total, 0, sizeof(u64) * kMaxRanks, stream));
     if (n > 0)
@@ -435,10 +512,10 @@ void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, v
                                                                                              status, ticket, sblocks);
         }
         route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
-            in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, bucket_cap, send);
+            in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_addr, bucket_cap);
         lc.add(3);
     }
-    route_header_kernel<<<1, kMaxRanks, 0, stream>>>(total, bucket_base, nr, (u32)L.self, send);
+    route_header_kernel<<<1, kMaxRanks, 0, stream>>>(total, bucket_addr, bucket_cap, nr, (u32)L.self, sig, d_flags);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }

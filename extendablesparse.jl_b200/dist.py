@@ -107,6 +107,11 @@ class DistExtendableSparseMatrix:
 
         self._phase_events = os.environ.get("XSB_DIST_TIMING", "") == "1"
         self.last_device_phase_ms = None
+        # transport of the fixed-capacity blocks: "peer" = straight into the receiver's mailbox over NVLink peer
+        # memory (xsb_route_pack_peer / xsb_route_unpack_peer; ranks of one node), "nccl" = grouped send / receive
+        self._transport_wanted = os.environ.get("XSB_EXCHANGE", "peer").lower()
+        self._peer = None  # None: not decided yet; True / False after the first fixed-capacity step
+        self.transport_note = ""
 
     # insertion: global (i,j) on any rank
     def insert_batch(self, I, J, V, flavour=0):
@@ -129,6 +134,58 @@ class DistExtendableSparseMatrix:
         """The next flush counts again (exact exchange) and re-derives the block capacities.  Collective."""
         self._caps_out = self._caps_in = None
         self._recv = None
+        self._teardown_peer()
+
+    def _setup_peer(self):
+        """Collective: every rank allocates its mailbox, the 64-byte IPC handles are all-gathered, every rank maps
+        the mailboxes of the ranks it exchanges blocks with.  Any rank failing (GPUs without peer access, ranks on
+        different nodes) makes ALL ranks fall back to the NCCL transport."""
+        import socket
+
+        self._peer = False
+        if self._transport_wanted != "peer" or not hasattr(self.h, "route_pack_peer") or self.device.type != "cuda":
+            self.transport_note = "nccl (requested)" if self._transport_wanted != "peer" else "nccl"
+            return
+        world = self.world
+        mine = {"host": socket.gethostname(), "caps_in": [int(c) for c in self._caps_in], "handle": None, "err": None}
+        try:
+            rows = [None] * world
+            dist.all_gather_object(rows, mine["caps_in"], group=self.group)
+            caps = [[0 if s == d else int(rows[d][s]) for s in range(world)] for d in range(world)]
+            mine["handle"] = self.h.peer_exchange_create(caps)
+        except Exception as e:  # noqa: BLE001  (reported to all ranks below)
+            mine["err"] = str(e)[:200]
+        infos = [None] * world
+        dist.all_gather_object(infos, mine, group=self.group)
+        ok = all(i["err"] is None and i["handle"] is not None for i in infos) and len({i["host"] for i in infos}) == 1
+        err = None
+        if ok:
+            try:
+                self.h.peer_exchange_connect(b"".join(i["handle"] for i in infos))
+            except Exception as e:  # noqa: BLE001
+                err = str(e)[:200]
+        errs = [None] * world
+        dist.all_gather_object(errs, err, group=self.group)
+        if ok and all(e is None for e in errs):
+            self._peer = True
+            self.transport_note = "peer memory (mailboxes over NVLink, CUDA IPC)"
+            return
+        why = next((i["err"] for i in infos if i["err"]), None) or next((e for e in errs if e), None) or "ranks on several nodes"
+        self.transport_note = f"nccl (peer exchange unavailable: {why})"
+        self._teardown_peer(force=True)
+
+    def _teardown_peer(self, force=False):
+        if (self._peer or force) and hasattr(self.h, "peer_exchange_disconnect"):
+            self.h.peer_exchange_disconnect()
+            dist.barrier(group=self.group)  # nobody frees a mailbox that a peer still has mapped
+            self.h.peer_exchange_destroy()
+        self._peer = None if not force else False
+
+    def close(self):
+        """Collective: releases the peer mailboxes (if any) and the slab handle."""
+        self._resolve_offsets()
+        self._teardown_peer()
+        self.h.close()
 
     def _flush_fixed(self, mode, wait):
         """The step of an assembly LOOP: same routing, but with the block capacities agreed after the last counted
@@ -138,6 +195,10 @@ class DistExtendableSparseMatrix:
 
         t0 = time.perf_counter()
         h, world, rank = self.h, self.world, self.rank
+        if self._peer is None:
+            self._setup_peer()
+        if self._peer:
+            return self._flush_peer(mode, wait, t0)
         co = [0 if d == rank else self._caps_out[d] for d in range(world)]
         ci = [0 if s == rank else self._caps_in[s] for s in range(world)]
         in_split = [0 if d == rank else 2 * (co[d] + 1) for d in range(world)]
@@ -195,7 +256,48 @@ class DistExtendableSparseMatrix:
         work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=True)
         self._offsets_pending = (work, allv, mine)
         self.last_exchange = {"sent_off_rank": None, "received_off_rank": None, "kept": None, "staged": cnt,
-                              "fixed_capacity_blocks": {"out": co, "in": ci}}
+                              "transport": self.transport_note, "fixed_capacity_blocks": {"out": co, "in": ci}}
+        if wait:
+            self._resolve_offsets()
+        self.fixed_steps += 1
+        self.last_phase_ms = [0.0, 0.0, 0.0, 0.0, 1e3 * (time.perf_counter() - t0), 0.0]
+        return nnz, (self._changed_any if wait else bool(changed))
+
+    def _flush_peer(self, mode, wait, t0):
+        """The fixed-capacity step over peer memory: the copy-out kernel of xsb_route_pack_peer stores every block
+        into its receiver's mailbox and raises the receiver's flag; xsb_route_unpack_peer waits for this step's
+        flags on the library's stream, takes the blocks and frees them for the senders.  No NCCL call, no host
+        synchronisation before the flush."""
+        import time
+
+        h, world = self.h, self.world
+        cnt = int(h.pending)
+        ev = None
+        if self._phase_events:
+            if self._lib_stream is None:
+                self._lib_stream = torch.cuda.ExternalStream(h.stream, device=self.device)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(self._lib_stream)
+        h.route_pack_peer()
+        if ev:
+            ev[1].record(self._lib_stream)
+        h.route_unpack_peer()
+        if ev:
+            ev[2].record(self._lib_stream)
+        nnz, changed = h.flush(mode)
+        if ev:
+            ev[3].record(self._lib_stream)
+            ev[3].synchronize()
+            self.last_device_phase_ms = {"pack": ev[0].elapsed_time(ev[1]), "p2p": 0.0,
+                                         "unpack": ev[1].elapsed_time(ev[2]), "flush": ev[2].elapsed_time(ev[3])}
+        mine = torch.tensor([nnz, int(changed)], dtype=torch.int64, device=self.device)
+        allv = torch.empty(2 * world, dtype=torch.int64, device=self.device)
+        work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=True)
+        self._offsets_pending = (work, allv, mine)
+        self.last_exchange = {"sent_off_rank": None, "received_off_rank": None, "kept": None, "staged": cnt,
+                              "transport": self.transport_note,
+                              "fixed_capacity_blocks": {"out": [0 if d == self.rank else self._caps_out[d] for d in range(world)],
+                                                        "in": [0 if s == self.rank else self._caps_in[s] for s in range(world)]}}
         if wait:
             self._resolve_offsets()
         self.fixed_steps += 1

@@ -242,6 +242,33 @@ int32_t xsb_route_pack(xsb_matrix *h, void *send_records, const int64_t *caps, i
 int32_t xsb_route_unpack(xsb_matrix *h, const void *recv_records, const int64_t *caps);
 int32_t xsb_route_prepare(xsb_matrix *h, void *send_records, int64_t capacity, int64_t *send_counts);
 int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_records, int64_t count);
+/* PEER EXCHANGE: the fixed-capacity exchange over NVLink peer memory, for ranks that are processes (or handles of one
+ * process) on ONE node whose GPUs have peer access.  No communication library on the records' path: the kernel that
+ * copies a bucket out of the staging buffer stores it straight into the MAILBOX of the receiving rank (that GPU's
+ * memory, mapped through CUDA IPC) -- the copy-out is the transfer -- and raises a flag there; the receiver's
+ * stream waits for the flags of the step, takes the blocks and tells the senders that the blocks are free again.  Two
+ * blocks per (sender, receiver) pair let a sender run one step ahead.  Everything is stream-ordered on the handles'
+ * streams; nothing visits the host.  (The reference has no counterpart: its partitions share one address space,
+ * src/matrix/genericmtextendablesparsematrixcsc.jl:87-114; this is that shared address space across GPUs.)
+ *   setup    xsb_peer_exchange_create(h, caps, ipc_handle)  caps[dst * n_ranks + src] = slots of the block src -> dst
+ *              (0: the pair exchanges nothing), the SAME matrix on every rank; writes the 64-byte CUDA IPC handle
+ *              of this rank's mailbox to ipc_handle (may be NULL for xsb_peer_exchange_connect_local)
+ *            all-gather the handles by any means (plain bytes)
+ *            xsb_peer_exchange_connect(h, ipc_handles)       n_ranks * 64 bytes, handle of rank r at 64 r
+ *            (ranks inside one process: xsb_peer_exchange_connect_local(h, handles_of_all_ranks))
+ *   step     insertions -> xsb_route_pack_peer(h) -> xsb_route_unpack_peer(h) -> xsb_flush(h, ...); EVERY rank makes
+ *              both calls in every step (ranks that send or receive nothing launch nothing).  Errors surface at the
+ *              flush as for xsb_route_pack / _unpack; additionally XSB_ESTATE when a peer did not deliver or take a
+ *              block within XSB_PEER_TIMEOUT_MS (environment, default 30000): the ranks are out of step.
+ *   teardown xsb_peer_exchange_disconnect on every rank, a barrier, xsb_peer_exchange_destroy (frees the mailbox;
+ *              xsb_destroy does both for a handle that still has one). */
+int32_t xsb_peer_exchange_create(xsb_matrix *h, const int64_t *caps, void *ipc_handle_out);
+int32_t xsb_peer_exchange_connect(xsb_matrix *h, const void *ipc_handles);
+int32_t xsb_peer_exchange_connect_local(xsb_matrix *h, xsb_matrix *const *peers);
+int32_t xsb_peer_exchange_disconnect(xsb_matrix *h);
+int32_t xsb_peer_exchange_destroy(xsb_matrix *h);
+int32_t xsb_route_pack_peer(xsb_matrix *h);
+int32_t xsb_route_unpack_peer(xsb_matrix *h);
 
 /* ------------------------------------------------------------------ */
 /* values-only re-assembly into a frozen pattern (Newton / transient loops) */
