@@ -741,6 +741,8 @@ def main():
     ap.add_argument("--ref-mesh", type=int, default=128, help="mesh of one --impl reference step (128 = the GPU arm's workload)")
     ap.add_argument("--mode", default="deterministic", choices=["deterministic", "fast"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1: compare every rank's slab (SHA-256) with the same global assembly done on one GPU")
     ap.add_argument("--no-legs", action="store_true", help="skip the splice / fast / values_only / cfg5 legs")
     ap.add_argument("--vo-n", type=int, default=200, help="grid of the values_only leg (200 = configs[2])")
     ap.add_argument("--workload", default="fem", choices=["fem", "fd400"],

@@ -141,6 +141,28 @@ def run(args, xsb, rank, world, local):
         dist.all_gather_object(allp, mine)
         exchange["device_phase_ms_last_step_per_rank"] = allp
     nnz_global = int(D.nnz_global)
+    parity = None
+    if getattr(args, "verify", False):
+        # the sharded result of the last step against the SAME global assembly on one GPU (rank 0 builds it with
+        # a single handle): SHA-256 of every slab's colptr | rowval | nzval must be identical
+        mine = bench.csc_digest(*h.fetch_csc_numpy())
+        digests = [None] * world
+        dist.all_gather_object(digests, mine)
+        if rank == 0:
+            import numpy as np
+
+            g = xsb.Handle(N, N)
+            g.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW)
+            g.flush(mode)
+            cp, rv, nz = g.fetch_csc_numpy()
+            g.close()
+            want = []
+            for r in range(world):
+                lo, hi = splits[r], splits[r + 1]
+                a, b = int(cp[lo]) - 1, int(cp[hi]) - 1
+                want.append(bench.csc_digest(cp[lo:hi + 1] - cp[lo] + 1, rv[a:b], nz[a:b]))
+            parity = {"slabs_identical_to_single_gpu_assembly": digests == want, "slab_sha256": digests}
+            del cp, rv, nz
     D.close()
     del D
 
@@ -165,6 +187,8 @@ def run(args, xsb, rank, world, local):
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clocks,
             "nnz_global": nnz_global, "n_inserted": int(world * n_ins_rank), "cfg5": cfg5,
         }
+        if parity is not None:
+            line["parity_checked"] = parity
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

@@ -576,6 +576,8 @@ void check_exchange(xsb_matrix *h)
             "a bucket of the exchange did not fit its block: records were cut off; reset! and repeat the step with larger "
             "capacities (or use xsb_route_count / xsb_route_prepare / xsb_route_finish)");
     REQUIRE((flags & 1ull) == 0, XSB_EBOUNDS, "a received record is not owned by this rank");
+    if (flags & 16ull)
+        h->has_assign = true; // a received record is an A[i,j] = v: ordered fold
     // the old paths need the true sizes of the regions
     h->n_low = (i64)h->h_route[2 * kMaxRanks + 1];
     h->n_high = (i64)h->h_route[2 * kMaxRanks + 2];
@@ -869,7 +871,7 @@ int32_t do_flush(xsb_matrix *h, int32_t mode, int32_t combine, int64_t *nnz_out,
     // ---- XSB_FAST: accumulate-on-insert inside windows of the staged stream (xsb_preagg.cu); the
     // partial sums replace the staged records, the old entries ride in front of them as before
     bool preagged = false;
-    if (mode == XSB_FAST && !h->has_assign && combine == XSB_COMBINE_SEED && (h->preagg || g_preagg) && h->preagg_misses < 2 &&
+    if (mode == XSB_FAST && !h->has_assign && !h->fixed_exchange && combine == XSB_COMBINE_SEED && (h->preagg || g_preagg) && h->preagg_misses < 2 &&
         n_ins >= 4096)
     {
         if (tp)
@@ -1564,7 +1566,8 @@ void unpack_blocks(xsb_matrix *h, const Rec *const *blocks, const i64 *caps)
     }
     h->routed = true;
     h->fixed_exchange = true;
-    h->has_assign = true; // flavours of the received records are not inspected on the host: ordered fold
+    // flavours of the received records: the unpack kernels raise bit 4 of the flags for A[i,j] = v records;
+    // check_exchange (at the flush) turns that into has_assign
     for (int src = 0; src < h->nranks; ++src)
     {
         if (src == h->rank)

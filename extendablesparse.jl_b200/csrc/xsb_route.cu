@@ -522,7 +522,7 @@ void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, v
 
 // One received block -> `cap` records behind the staged ones: the bucket's records (checked: owned by this rank),
 // then padding records the flush skips.  flags: bit 0 a record of another owner, bit 1 the bucket did not fit its
-// block (records were cut off), bit 2 not a block (bad magic).  counts[which] += records taken.
+// block (records were cut off), bit 2 not a block (bad magic), bit 4 an A[i,j] = v record was received.  counts[which] += records taken.
 __global__ void __launch_bounds__(256)
 route_unpack_kernel(const Rec *__restrict__ block, u64 cap, Rec *__restrict__ out, int ownershift, u32 me, u64 colmask,
                     int colshift, u64 ncols, u64 padkey, u64 *__restrict__ flags, u64 *__restrict__ counts, int which)
@@ -550,6 +550,8 @@ route_unpack_kernel(const Rec *__restrict__ block, u64 cap, Rec *__restrict__ ou
             r = block[1 + k];
             if ((u32)(r.key >> ownershift) != me || ((r.key >> colshift) & colmask) >= ncols)
                 atomicOr(reinterpret_cast<unsigned long long *>(flags), 1ull);
+            if ((r.key & 3ull) == FL_ASSIGN && (*reinterpret_cast<volatile u64 *>(flags) & 16ull) == 0ull)
+                atomicOr(reinterpret_cast<unsigned long long *>(flags), 16ull);
         }
         else
         {
