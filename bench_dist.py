@@ -90,12 +90,23 @@ def run(args, xsb, rank, world, local):
     h = D.h
     n_ins_rank = xsb.capi.stream_count_p1fem(nx, ny, layers + 1)
 
-    def emit():
-        h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, layers * (rank + 1)))
+    # Every rank visits its INTERFACE layer first (the cube layer under the plane the rank above owns: the only
+    # elements with entries in foreign columns), hands those records to the exchange and assembles the interior
+    # while they travel.  Same entries as the natural order; the stream order -- and with it the reference result
+    # this is compared with (--verify) -- is [interface layer, interior layers] per rank.
+    top = layers * (rank + 1) - 1
+
+    def emit_interface():
+        h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(top, top + 1))
+
+    def emit_interior():
+        h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, top))
 
     def step():
         h.reset()
-        emit()
+        emit_interface()
+        D.exchange_begin()
+        emit_interior()
         return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
     for _ in range(args.warmup):
@@ -123,7 +134,9 @@ def run(args, xsb, rank, world, local):
     for _ in range(prof_steps):
         h.reset()
         h.timer_start()
-        emit()
+        emit_interface()
+        D.exchange_begin()
+        emit_interior()
         ms_emit += h.timer_stop()
         D.flush(mode, wait=False)
         st = h.flush_stats()
@@ -141,6 +154,7 @@ def run(args, xsb, rank, world, local):
         dist.all_gather_object(allp, mine)
         exchange["device_phase_ms_last_step_per_rank"] = allp
     nnz_global = int(D.nnz_global)
+    D_transport = D.transport_note or "nccl"
     parity = None
     if getattr(args, "verify", False):
         # the sharded result of the last step against the SAME global assembly on one GPU (rank 0 builds it with
@@ -152,7 +166,10 @@ def run(args, xsb, rank, world, local):
             import numpy as np
 
             g = xsb.Handle(N, N)
-            g.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW)
+            for r in range(world):  # the rank-ordered concatenation of the ranks' streams
+                t = layers * (r + 1) - 1
+                g.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(t, t + 1))
+                g.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * r, t))
             g.flush(mode)
             cp, rv, nz = g.fetch_csc_numpy()
             g.close()
@@ -175,7 +192,8 @@ def run(args, xsb, rank, world, local):
         cfg = bench.workload(args)
         cfg["workload"] = (f"P1-FEM Laplacian+mass, {nx}x{ny}x{nz_nodes}-node Kuhn mesh sharded over {world} ranks "
                            f"({layers} cube layers = {n_ins_rank} rawupdateindex! calls per rank), column-slab ownership, "
-                           f"one grouped NCCL send/receive of fixed-capacity blocks between neighbouring slabs per step (interface plane), CSC left sharded")
+                           f"every rank assembles its interface layer first and its fixed-capacity block travels to the neighbouring "
+                           f"slab ({D_transport}) while the interior is assembled, CSC left sharded")
         cfg["parallelism"] = f"column-slab x{world}"
         cfg["exchange"] = exchange
         cfg["numa"] = numa
@@ -263,9 +281,21 @@ def run_fd(args, xsb, xd, bench, rank, world, local, dev):
     h = D.h
     n_ins = xsb.capi.stream_count_fdrand(n1, n1, n1)
 
+    # interface nodes first: the first and the last z-plane of the rank's node slab hold the only nodes with
+    # neighbours (= columns) in other slabs
+    plane = n1 * n1
+    lo, hi = splits[rank], splits[rank + 1]
+    parts = [(lo, min(lo + plane, hi)), (max(hi - plane, min(lo + plane, hi)), hi)]
+    interior = (parts[0][1], parts[1][0])
+
     def step():
         h.reset()
-        h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=(splits[rank], splits[rank + 1]))
+        for a, b in parts:
+            if b > a:
+                h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=(a, b))
+        D.exchange_begin()
+        if interior[1] > interior[0]:
+            h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=interior)
         return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
     for _ in range(max(2, min(args.warmup, 3))):

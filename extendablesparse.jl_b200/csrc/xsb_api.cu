@@ -124,6 +124,7 @@ struct xsb_matrix
         bool peer_ipc[kMaxRanks] = {};
         i64 caps[kMaxRanks * kMaxRanks] = {}; // [dst * nranks + src]
         u64 seq = 0;                          // steps packed so far
+        i64 packed_upto = 0;                  // staged records when xsb_route_pack_peer ran
         u64 timeout_ns = 30000000000ull;
     } px;
 
@@ -571,6 +572,8 @@ void check_exchange(xsb_matrix *h)
     const u64 flags = h->h_route[2 * kMaxRanks];
     REQUIRE((flags & 8ull) == 0, XSB_ESTATE,
             "peer exchange: a rank did not deliver (or take) its block in time (XSB_PEER_TIMEOUT_MS); the ranks are out of step");
+    REQUIRE((flags & 32ull) == 0, XSB_ESTATE,
+            "a record owned by another rank was staged after xsb_route_pack_peer: it would never reach its owner");
     REQUIRE((flags & 4ull) == 0, XSB_EINVAL, "a received block carries no header: capacities of sender and receiver differ");
     REQUIRE((flags & 2ull) == 0, XSB_ESTATE,
             "a bucket of the exchange did not fit its block: records were cut off; reset! and repeat the step with larger "
@@ -1548,6 +1551,13 @@ void pack_blocks(xsb_matrix *h, const i64 *caps, const PeerFlags &sig)
     h->route_ws = h->dalloc(route_workspace_bytes((u64)std::max<i64>(st.count, 1), h->nranks));
     route_pack(h->stream, st.buf + st.front, (u64)st.count, h->L, h->route_ws, caps, h->h_route, h->h_route + kMaxRanks, sig,
                h->d_route, h->lc, h->tileflags);
+    h->fixed_exchange = true; // the flags of this step are read (and cleared) with the staged records
+}
+
+// the own region of the step is complete
+void close_own_region(xsb_matrix *h)
+{
+    Stage &st = h->stage[0];
     h->route_counted = -1;
     h->foreign = 0; // unknown on the host: the flush skips them by their owner bits
     h->routed = true;
@@ -1635,6 +1645,7 @@ int32_t xsb_route_pack(xsb_matrix *h, void *send_records, const int64_t *caps, i
         }
         PeerFlags none{};
         pack_blocks(h, reinterpret_cast<const i64 *>(caps), none);
+        close_own_region(h);
         return XSB_OK;
     });
 }
@@ -1882,6 +1893,7 @@ int32_t xsb_route_pack_peer(xsb_matrix *h)
             peer_wait(h->stream, waitf, px.timeout_ns, h->d_route, h->lc);
         pack_blocks(h, caps_out, sig);
         px.packed = true;
+        px.packed_upto = h->stage[0].count; // insertions may go on: what follows must be this rank's own
         return XSB_OK;
     });
 }
@@ -1912,6 +1924,13 @@ int32_t xsb_route_unpack_peer(xsb_matrix *h)
             sig.addr[s2] = reinterpret_cast<u64>(px.peer[s2] + 8 * (size_t)(kMaxRanks + me)); // done[me] of rank s2
             sig.value[s2] = seq;
             any = true;
+        }
+        {
+            Stage &st = h->stage[0];
+            if (st.count > px.packed_upto)
+                route_tailcheck(h->stream, st.buf + st.front, (u64)px.packed_upto, (u64)st.count, h->L, h->tileflags, h->d_route,
+                                h->lc);
+            close_own_region(h);
         }
         if (any)
             peer_wait(h->stream, waitf, px.timeout_ns, h->d_route, h->lc);

@@ -463,6 +463,36 @@ __global__ void peer_signal_kernel(PeerFlags sgn)
     }
 }
 
+// Records [from, n) of the staged stream, staged after an early xsb_route_pack_peer: every one must be owned by this
+// rank.  A warp per tile the producers flagged (normally only the tile `from` lies in); bit 5 of *d_flags otherwise.
+__global__ void __launch_bounds__(256)
+route_tailcheck_kernel(const Rec *__restrict__ in, u64 from, u64 n, int ownershift, u32 me,
+                       const unsigned char *__restrict__ tileflags, u64 *__restrict__ d_flags)
+{
+    const u64 tile = (from >> kRouteTileShift) + (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const u64 b0 = tile << kRouteTileShift;
+    if (b0 >= n || (tileflags != nullptr && tileflags[tile] == 0))
+        return;
+    const u64 e = min(n, b0 + RT_TILE);
+    bool bad = false;
+    for (u64 k = max(b0, from) + (threadIdx.x & 31); k < e; k += 32)
+        bad |= (u32)(in[k].key >> ownershift) != me;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+        atomicOr(reinterpret_cast<unsigned long long *>(d_flags), 32ull);
+}
+
+void route_tailcheck(cudaStream_t stream, const Rec *in, u64 from, u64 n, const KeyLayout &L, const unsigned char *tileflags,
+                     u64 *d_flags, LaunchCounter &lc)
+{
+    if (from >= n)
+        return;
+    const u64 tiles = ((n + RT_TILE - 1) >> kRouteTileShift) - (from >> kRouteTileShift);
+    route_tailcheck_kernel<<<(unsigned)((tiles + 7) / 8), 256, 0, stream>>>(in, from, n, L.ownershift(), (u32)L.self, tileflags,
+                                                                          d_flags);
+    lc.add();
+    XSB_CUDA(cudaGetLastError());
+}
+
 void peer_wait(cudaStream_t stream, const PeerFlags &w, u64 timeout_ns, u64 *d_flags, LaunchCounter &lc)
 {
     peer_wait_kernel<<<1, kMaxRanks, 0, stream>>>(w, timeout_ns, d_flags);

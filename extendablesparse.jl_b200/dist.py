@@ -111,6 +111,7 @@ class DistExtendableSparseMatrix:
         # memory (xsb_route_pack_peer / xsb_route_unpack_peer; ranks of one node), "nccl" = grouped send / receive
         self._transport_wanted = os.environ.get("XSB_EXCHANGE", "peer").lower()
         self._peer = None  # None: not decided yet; True / False after the first fixed-capacity step
+        self._early = False  # exchange_begin() already packed this step
         self.transport_note = ""
 
     # insertion: global (i,j) on any rank
@@ -263,6 +264,18 @@ class DistExtendableSparseMatrix:
         self.last_phase_ms = [0.0, 0.0, 0.0, 0.0, 1e3 * (time.perf_counter() - t0), 0.0]
         return nnz, (self._changed_any if wait else bool(changed))
 
+    def exchange_begin(self):
+        """Optional, between insertions: everything staged SO FAR that other ranks own leaves now (peer transport:
+        xsb_route_pack_peer stores it into the receivers' mailboxes while this rank goes on inserting); what is
+        inserted afterwards in this step must be owned by this rank -- `flush` fails otherwise.  An assembly loop
+        that visits its interface elements first hides the whole exchange behind the interior.  Without the peer
+        transport (counted steps, NCCL) the call does nothing and `flush` exchanges everything."""
+        if self._peer is None and self._caps_out is not None and hasattr(self.h, "route_pack"):
+            self._setup_peer()
+        if self._peer and not self._early:
+            self.h.route_pack_peer()
+            self._early = True
+
     def _flush_peer(self, mode, wait, t0):
         """The fixed-capacity step over peer memory: the copy-out kernel of xsb_route_pack_peer stores every block
         into its receiver's mailbox and raises the receiver's flag; xsb_route_unpack_peer waits for this step's
@@ -278,7 +291,9 @@ class DistExtendableSparseMatrix:
                 self._lib_stream = torch.cuda.ExternalStream(h.stream, device=self.device)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record(self._lib_stream)
-        h.route_pack_peer()
+        if not self._early:
+            h.route_pack_peer()
+        self._early = False
         if ev:
             ev[1].record(self._lib_stream)
         h.route_unpack_peer()

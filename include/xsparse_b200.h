@@ -257,7 +257,10 @@ int32_t xsb_route_finish(xsb_matrix *h, int32_t src_rank, const void *recv_recor
  *            xsb_peer_exchange_connect(h, ipc_handles)       n_ranks * 64 bytes, handle of rank r at 64 r
  *            (ranks inside one process: xsb_peer_exchange_connect_local(h, handles_of_all_ranks))
  *   step     insertions -> xsb_route_pack_peer(h) -> xsb_route_unpack_peer(h) -> xsb_flush(h, ...); EVERY rank makes
- *              both calls in every step (ranks that send or receive nothing launch nothing).  Errors surface at the
+ *              both calls in every step (ranks that send or receive nothing launch nothing).  xsb_route_pack_peer
+ *              may come BEFORE the step's last insertion -- an assembly loop that visits its interface elements
+ *              first hides the transfer behind the interior --: records staged after it must be owned by this
+ *              rank (one of another rank makes the flush fail, XSB_ESTATE).  Errors surface at the
  *              flush as for xsb_route_pack / _unpack; additionally XSB_ESTATE when a peer did not deliver or take a
  *              block within XSB_PEER_TIMEOUT_MS (environment, default 30000): the ranks are out of step.
  *   teardown xsb_peer_exchange_disconnect on every rank, a barrier, xsb_peer_exchange_destroy (frees the mailbox;
