@@ -91,9 +91,9 @@ def run(args, xsb, rank, world, local):
     n_ins_rank = xsb.capi.stream_count_p1fem(nx, ny, layers + 1)
 
     # Every rank visits its INTERFACE layer first (the cube layer under the plane the rank above owns: the only
-    # elements with entries in foreign columns), hands those records to the exchange and assembles the interior
-    # while they travel.  Same entries as the natural order; the stream order -- and with it the reference result
-    # this is compared with (--verify) -- is [interface layer, interior layers] per rank.
+    # elements with entries in foreign columns), so that those records can be handed to the exchange before the
+    # interior is assembled (XSB_EXCHANGE_EARLY=1).  Same entries as the natural order; the stream order -- and
+    # with it the reference result this is compared with (--verify) -- is [interface layer, interior layers] per rank.
     top = layers * (rank + 1) - 1
 
     def emit_interface():
@@ -102,10 +102,16 @@ def run(args, xsb, rank, world, local):
     def emit_interior():
         h.emit_p1fem(nx, ny, nz_nodes, flavour=xsb.RAW, cz_range=(layers * rank, top))
 
+    # 1: the interface blocks leave before the interior is assembled (DistExtendableSparseMatrix.exchange_begin).
+    # Measured at N = 8 (B200, NVLink): 4.12 ms per step against 3.92 without -- the transfer is 31 MB per rank and
+    # the ranks wait for each other ~0.05 ms either way, while the split costs launches: off by default.
+    early = os.environ.get("XSB_EXCHANGE_EARLY", "0") == "1"
+
     def step():
         h.reset()
         emit_interface()
-        D.exchange_begin()
+        if early:
+            D.exchange_begin()
         emit_interior()
         return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for
 
@@ -135,7 +141,8 @@ def run(args, xsb, rank, world, local):
         h.reset()
         h.timer_start()
         emit_interface()
-        D.exchange_begin()
+        if early:
+            D.exchange_begin()
         emit_interior()
         ms_emit += h.timer_stop()
         D.flush(mode, wait=False)
@@ -192,8 +199,9 @@ def run(args, xsb, rank, world, local):
         cfg = bench.workload(args)
         cfg["workload"] = (f"P1-FEM Laplacian+mass, {nx}x{ny}x{nz_nodes}-node Kuhn mesh sharded over {world} ranks "
                            f"({layers} cube layers = {n_ins_rank} rawupdateindex! calls per rank), column-slab ownership, "
-                           f"every rank assembles its interface layer first and its fixed-capacity block travels to the neighbouring "
-                           f"slab ({D_transport}) while the interior is assembled, CSC left sharded")
+                           f"interface layer assembled first; its records travel to the neighbouring slab as one fixed-capacity "
+                           f"block per step ({D_transport}"
+                           f"{', sent before the interior is assembled' if early else ''}), CSC left sharded")
         cfg["parallelism"] = f"column-slab x{world}"
         cfg["exchange"] = exchange
         cfg["numa"] = numa
@@ -293,7 +301,8 @@ def run_fd(args, xsb, xd, bench, rank, world, local, dev):
         for a, b in parts:
             if b > a:
                 h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=(a, b))
-        D.exchange_begin()
+        if os.environ.get("XSB_EXCHANGE_EARLY", "0") == "1":
+            D.exchange_begin()
         if interior[1] > interior[0]:
             h.emit_fdrand(n1, n1, n1, seed=20240717, flavour=xsb.UPDATE, l_range=interior)
         return D.flush(mode, wait=False)  # the 16-byte offsets all-gather is launched, not waited for

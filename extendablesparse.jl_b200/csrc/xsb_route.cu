@@ -29,6 +29,14 @@ static_assert(RT_TILE == (1 << kRouteTileShift), "tile size of the producers' fl
 // A block looks after RT_GROUP consecutive tiles and only reads the ones the producers marked.
 constexpr int RT_GROUP = RT_THREADS;
 
+// Blocks of the tile kernels: thread x of block b looks at tile x * gridDim + b, so a block needs at most RT_GROUP
+// tiles -- and a SHORT stream (an interface layer routed ahead of the interior: every tile marked) is spread over
+// enough blocks to fill the GPU instead of RT_GROUP marked tiles per block.
+static unsigned rt_blocks(u64 ntiles)
+{
+    return (unsigned)std::max<u64>((ntiles + RT_GROUP - 1) / RT_GROUP, std::min<u64>(ntiles, (u64)kNumSM * 8));
+}
+
 __global__ void __launch_bounds__(RT_THREADS)
 route_count_kernel(const Rec *__restrict__ in, u64 n, u64 ntiles, int ownershift, u32 me, int nranks,
                    u32 *__restrict__ tilecnt, const unsigned char *__restrict__ tileflags)
@@ -331,7 +339,7 @@ void route_count(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, 
     u32 *tileoff = tilecnt + (size_t)ntiles * nr;
     u64 *total = reinterpret_cast<u64 *>(tileoff + (size_t)ntiles * nr);
     XSB_CUDA(cudaMemsetAsync(tilecnt, 0, sizeof(u32) * (size_t)ntiles * nr, stream));
-    route_count_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+    route_count_kernel<<<rt_blocks(ntiles), RT_THREADS, 0, stream>>>(
         in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileflags);
     route_scan_kernel<<<nr, 1024, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total);
     lc.add(2);
@@ -372,7 +380,7 @@ void route_extract(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L
     if (run == 0)
         return;
     XSB_CUDA(cudaMemcpyAsync(bucket_base, hb, sizeof(u64) * nr, cudaMemcpyHostToDevice, stream));
-    route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+    route_extract_kernel<<<rt_blocks(ntiles), RT_THREADS, 0, stream>>>(
         in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_base, nullptr);
     lc.add();
     XSB_CUDA(cudaGetLastError());
@@ -531,7 +539,7 @@ void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, v
     if (n > 0)
     {
         XSB_CUDA(cudaMemsetAsync(tilecnt, 0, sizeof(u32) * (size_t)ntiles * nr, stream));
-        route_count_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+        route_count_kernel<<<rt_blocks(ntiles), RT_THREADS, 0, stream>>>(
             in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileflags);
         { // offsets of every tile's records in their bucket: single-pass scan per destination
             const u32 sblocks = (u32)((ntiles + RS_TILE - 1) / RS_TILE);
@@ -541,7 +549,7 @@ void route_pack(cudaStream_t stream, const Rec *in, u64 n, const KeyLayout &L, v
             route_scan_lookback_kernel<<<dim3(sblocks, (unsigned)nr), RS_THREADS, 0, stream>>>(tilecnt, tileoff, ntiles, nr, total,
                                                                                              status, ticket, sblocks);
         }
-        route_extract_kernel<<<(unsigned)((ntiles + RT_GROUP - 1) / RT_GROUP), RT_THREADS, 0, stream>>>(
+        route_extract_kernel<<<rt_blocks(ntiles), RT_THREADS, 0, stream>>>(
             in, n, ntiles, L.ownershift(), (u32)L.self, nr, tilecnt, tileoff, bucket_addr, bucket_cap);
         lc.add(3);
     }
