@@ -110,15 +110,17 @@ __device__ __forceinline__ u32 chunk_count_batch(ChunkSpaceT<HB> &ws, u32 g, boo
     return packed + (u32)__popc(peers & lt);
 }
 
-// offsets of the runs: exclusive sum of the columns' record counts in order of first appearance
-template <int HB> __device__ __forceinline__ void chunk_scan(ChunkSpaceT<HB> &ws, u32 d, int lane)
+// offsets of the runs: exclusive sum of the columns' record counts in order of first appearance.
+// MUL: every counted request stands for MUL records (a producer that knows that its records come in groups of
+// MUL per column counts the groups: emit_p1fem_grouped_kernel)
+template <int HB, u32 MUL = 1> __device__ __forceinline__ void chunk_scan(ChunkSpaceT<HB> &ws, u32 d, int lane)
 {
     constexpr u32 full = 0xffffffffu;
     const u32 per = (d + 31u) >> 5;
     const u32 j0 = min((u32)lane * per, d), j1 = min(j0 + per, d);
     u32 sum = 0;
     for (u32 j = j0; j < j1; ++j)
-        sum += ws.cnt[ws.cand[j]];
+        sum += MUL * ws.cnt[ws.cand[j]];
     u32 incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -132,7 +134,7 @@ template <int HB> __device__ __forceinline__ void chunk_scan(ChunkSpaceT<HB> &ws
     {
         const u32 s = ws.cand[j];
         ws.start[s] = (unsigned short)run;
-        run += ws.cnt[s];
+        run += MUL * ws.cnt[s];
     }
     __syncwarp();
 }
@@ -146,7 +148,7 @@ __device__ __forceinline__ u32 chunk_dest(const unsigned short *start, u32 packe
 // completion order, the flush orders the runs of a column by their position in the staging buffer.
 // grouped == false: the chunk gave up (too many distinct columns: no column locality) and was stored
 // in stream order; the flag sends the flush to the radix-sort path.
-template <int HB>
+template <int HB, u32 MUL = 1>
 __device__ __forceinline__ void chunk_publish(ChunkSpaceT<HB> &ws, const RunTarget &rt, u32 chunk, u32 abs_start, u32 d,
                                               bool grouped, int lane)
 {
@@ -169,7 +171,7 @@ __device__ __forceinline__ void chunk_publish(ChunkSpaceT<HB> &ws, const RunTarg
     {
         const u32 s = ws.cand[j];
         rt.pcol[base + j] = ws.key[s];
-        rt.pinfo[base + j] = ((u32)ws.start[s] << 16) | (u32)ws.cnt[s];
+        rt.pinfo[base + j] = ((u32)ws.start[s] << 16) | (MUL * (u32)ws.cnt[s]);
     }
 }
 

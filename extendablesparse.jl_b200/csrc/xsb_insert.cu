@@ -740,14 +740,16 @@ emit_p1fem_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour, 
 }
 
 // Grouped chunks (xsb_chunk.cuh): a warp's 32 tetrahedra = one chunk of 640 records, brought into column
-// order without a block-wide barrier.  Only the KEYS go through the warp's shared memory (values and element
-// matrices stay in the registers of the lane that computed them): the warp walks the keys in call order,
-// notes every record's (column slot, rank in its column) in the key's own place, and after the scan over
-// the columns every lane stores its tetrahedron's 20 records where the flush will read them.
+// order without a block-wide barrier -- and without looking at the records one by one: an element's 20 records
+// fall on 4 columns (its nodes), 5 each, in a fixed order (record q = 5 il + w, FemTet), so the warp only runs
+// the chunk's 128 (element, node) VISITS through its table, in call order (4 batches instead of 20), and every
+// visit stands for 5 records: run offset = 5 x (visits of the column by earlier elements) + the record's fixed
+// rank among its element's 5.  Keys, values and element matrices stay in the registers of the lane that
+// computed them; only the 128 grouping keys pass through shared memory.
 constexpr int FEMG_HB = 7; // 128 table slots: 32 neighbouring tetrahedra touch a few dozen nodes
 struct FemWarpSpace
 {
-    u64 key[32 * FEM_PITCH];
+    u32 g[128]; // visit v = 4 element + node: grouping key, then (slot, visits before)
     ChunkSpaceT<FEMG_HB> tab;
 };
 
@@ -771,65 +773,82 @@ emit_p1fem_grouped_kernel(i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 f
     if (t < t_last)
     {
         fem_tet_compute(t, nxn, nyn, nzn, L, tid, flavour, sf.flags != nullptr, e);
-        u64 *kd = sp.key + lane * FEM_PITCH;
-#pragma unroll
-        for (int il = 0; il < 4; ++il)
-#pragma unroll
-            for (int w = 0; w < 5; ++w)
-                kd[il * 5 + w] = e.key(il, w);
+        uint4 gq;
+        gq.x = (u32)(e.ckey[0] >> rt.colshift) & rt.gmask;
+        gq.y = (u32)(e.ckey[1] >> rt.colshift) & rt.gmask;
+        gq.z = (u32)(e.ckey[2] >> rt.colshift) & rt.gmask;
+        gq.w = (u32)(e.ckey[3] >> rt.colshift) & rt.gmask;
+        reinterpret_cast<uint4 *>(sp.g)[lane] = gq;
     }
     if (!__any_sync(full, e.has_foreign))
         sf.flags = nullptr;
     __syncwarp();
-    const u32 len = (u32)(t_last - t_first) * FEM_REC;
+    const u32 visits = (u32)(t_last - t_first) * 4u;
     const i64 c0 = (t_first - tet_begin) * FEM_REC; // position of the chunk in this launch's output
     const u32 lt = lanemask_lt();
     u32 d = 0;
-    bool grouped = true;
-#pragma unroll 4
-    for (int b = 0; b < FEM_REC; ++b)
-    {
-        if ((u32)(b * 32) < len && grouped) // warp-uniform
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    { // at most 128 distinct columns: never more than the table takes
+        if ((u32)(b * 32) < visits) // warp-uniform
         {
-            const u32 q = b * 32 + lane;
-            const u32 tt = q / FEM_REC;
-            u64 *slot = sp.key + tt * FEM_PITCH + (q - tt * FEM_REC);
-            const u64 key = q < len ? *slot : 0ull;
-            if (d > ChunkSpaceT<FEMG_HB>::DMAX - 32u)
-                grouped = false;
-            else
-            {
-                const u32 g = (u32)(key >> rt.colshift) & rt.gmask;
-                const u32 rs = (u32)(b * 32 + 32) <= len ? chunk_count_batch<FEMG_HB, true>(sp.tab, g, true, lt, d)
-                                                         : chunk_count_batch<FEMG_HB, false>(sp.tab, g, q < len, lt, d);
-                if (q < len)
-                    *reinterpret_cast<u32 *>(slot) = rs; // this lane read the key: its place now holds (slot, rank)
-            }
+            const u32 v = b * 32 + lane;
+            const u32 g = v < visits ? sp.g[v] : 0u;
+            const u32 rs = (u32)(b * 32 + 32) <= visits ? chunk_count_batch<FEMG_HB, true>(sp.tab, g, true, lt, d)
+                                                        : chunk_count_batch<FEMG_HB, false>(sp.tab, g, v < visits, lt, d);
+            if (v < visits)
+                sp.g[v] = rs; // (slot, visits of this column before this one)
         }
     }
-    if (grouped)
-        chunk_scan(sp.tab, d, lane);
+    static_assert(ChunkSpaceT<FEMG_HB>::H >= 128, "a chunk's 128 visits must fit the table");
+    chunk_scan<FEMG_HB, 5>(sp.tab, d, lane);
     __syncwarp();
     if (t < t_last)
     {
         Rec *dst = out + c0;
-        const u64 *kd = sp.key + lane * FEM_PITCH;
+        const uint4 gq = reinterpret_cast<const uint4 *>(sp.g)[lane];
+        const u32 rs[4] = {gq.x, gq.y, gq.z, gq.w};
+        u32 base[4];
 #pragma unroll
-        for (int il = 0; il < 4; ++il)
+        for (int c = 0; c < 4; ++c)
+            base[c] = (u32)sp.tab.start[rs[c] >> 16] + 5u * (rs[c] & 0xffffu);
 #pragma unroll
-            for (int w = 0; w < 5; ++w)
+        for (int c = 0; c < 4; ++c)
+        { // the element's 5 records of column c sit next to each other, in call order: rows 0 .. c-1, the mass term
+          // of row c, rows c .. 3 -- written as full 32-byte sectors (STG.256) where two of them share one
+            Rec rr[5];
+#pragma unroll
+            for (int lr = 0; lr < 5; ++lr)
             {
-                const int q = il * 5 + w;
-                const u32 to = grouped ? chunk_dest(sp.tab.start, (u32)kd[q]) : (u32)(lane * FEM_REC + q);
-                Rec r;
-                r.key = e.key(il, w);
-                r.val = e.val(il, w);
-                st_rec(dst + to, r);
-                if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
-                    sf.flags[(sf.pos0 + c0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
+                const int il = lr <= c ? lr : lr - 1;
+                const int w = lr == c ? 0 : c + 1;
+                rr[lr].key = e.key(il, w);
+                rr[lr].val = e.val(il, w);
             }
+            Rec *p = dst + base[c];
+            auto pair = [&](Rec *q, const Rec &a, const Rec &b) {
+                st_v4_u64(q, a.key, (u64)__double_as_longlong(a.val), b.key, (u64)__double_as_longlong(b.val));
+            };
+            if ((reinterpret_cast<uintptr_t>(p) & 16u) != 0)
+            {
+                st_rec(p, rr[0]);
+                pair(p + 1, rr[1], rr[2]);
+                pair(p + 3, rr[3], rr[4]);
+            }
+            else
+            {
+                pair(p, rr[0], rr[1]);
+                pair(p + 2, rr[2], rr[3]);
+                st_rec(p + 4, rr[4]);
+            }
+            if (sf.flags != nullptr && L.owner(e.ckey[c]) != (u32)L.self)
+            { // (5 records: at most two tiles)
+                sf.flags[(sf.pos0 + c0 + (i64)base[c]) >> kRouteTileShift] = 1; // benign race: same value
+                sf.flags[(sf.pos0 + c0 + (i64)base[c] + 4) >> kRouteTileShift] = 1;
+            }
+        }
     }
-    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, grouped, lane);
+    chunk_publish<FEMG_HB, 5>(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, true, lane);
 }
 
 void emit_p1fem(cudaStream_t stream, i64 nxn, i64 nyn, i64 nzn, KeyLayout L, u32 tid, u32 flavour,
