@@ -220,11 +220,11 @@ template <int HBITS> struct RfShape
     static constexpr int H = 1 << HB;
     static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? 24 : (HBITS == 15 ? 16 : 12));
     // warps per block; blocks per SM that shared memory and the register file allow.  The largest shape takes
-    // 640 B of shared memory per thread: one-warp blocks fit 11 warps per SM where four-warp blocks fit 8
+    // 544 B of shared memory per thread: one-warp blocks fit 12 warps per SM where four-warp blocks fit 8
     // (measured on the block reaction-diffusion system: 2.65 -> 2.34 ms; the small shapes lose with tiny blocks)
     static constexpr int kWarps = HBITS == 6 ? 1 : 4;
-    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 11 : (HBITS == 15 ? 5 : 4));
-    static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + sizeof(u32)) * D);
+    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 12 : (HBITS == 15 ? 6 : 5));
+    static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + 1) * D);
 };
 
 // The fold state of one column.  A table slot holds (row << HB | accumulator index); accumulators are
@@ -237,7 +237,7 @@ template <int HBITS, bool ASSIGN> struct ThreadFold
     static constexpr u32 D = RfShape<HBITS>::D;
     u32 *key;    // [slot * 32]
     double *acc; // [i * 32]
-    u32 *rows;   // [i * 32]
+    unsigned char *ord; // [i * 32]: table slot of accumulator i (its row = key >> HB)
     u32 d = 0;       // accumulators in use
     u32 pending = 0; // of which not (yet) existing: only updateindex! / setindex! of a zero touched them
     u32 exmask = 0;  // accumulator i holds an existing entry (D <= 32)
@@ -275,7 +275,7 @@ template <int HBITS, bool ASSIGN> struct ThreadFold
             return;
         }
         key[s * 32] = (row << HB) | d;
-        rows[d * 32] = row;
+        ord[d * 32] = (unsigned char)s;
         acc[d * 32] = v;
         exmask |= 1u << d;
         ++d;
@@ -294,7 +294,7 @@ template <int HBITS, bool ASSIGN> struct ThreadFold
             }
             x = d++;
             key[s * 32] = (row << HB) | x;
-            rows[x * 32] = row;
+            ord[x * 32] = (unsigned char)s;
             acc[x * 32] = 0.0;
             ++pending;
         }
@@ -322,29 +322,41 @@ template <int HBITS, bool ASSIGN> struct ThreadFold
             }
         }
     }
-    // existing entries as (row << HB | accumulator) words, insertion-sorted by row into key[0 .. j): taken in
-    // order of first appearance, which an assembly stream visits nearly in row order (few shifts)
+    // existing entries as (row << HB | accumulator) words, sorted by row into key[0 .. j).  All words are read into
+    // registers first (the table is overwritten), ordered there by a bitonic network -- no branch, no
+    // memory traffic, the same instruction stream for every lane whatever its column looks like -- and written back.
     __device__ __forceinline__ int finish()
     {
-        u32 j = 0;
-        for (u32 i = 0; i < d; ++i)
+        constexpr int N = D <= 16 ? 16 : 32;
+        u32 a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
         {
-            if (!((exmask >> i) & 1u))
-                continue;
-            const u32 kk = (rows[i * 32] << HB) | i;
-            u32 q = j;
-            while (q > 0)
-            {
-                const u32 prev = key[(q - 1) * 32];
-                if (prev < kk)
-                    break;
-                key[q * 32] = prev;
-                --q;
-            }
-            key[q * 32] = kk;
-            ++j;
+            a[i] = 0xffffffffu;
+            if ((u32)i < D && (u32)i < d && ((exmask >> i) & 1u))
+                a[i] = key[(u32)ord[i * 32] * 32]; // (row << HB) | i
         }
-        return (int)j;
+#pragma unroll
+        for (int k = 2; k <= N; k <<= 1) // bitonic network: every index below is a compile-time constant
+#pragma unroll
+            for (int jj = k >> 1; jj > 0; jj >>= 1)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                {
+                    const int l = i ^ jj;
+                    if (l > i)
+                    {
+                        const u32 lo_ = min(a[i], a[l]), hi_ = max(a[i], a[l]);
+                        a[i] = (i & k) == 0 ? lo_ : hi_;
+                        a[l] = (i & k) == 0 ? hi_ : lo_;
+                    }
+                }
+        const int j = __popc(exmask);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (i < H && i < j)
+                key[i * 32] = a[i];
+        return j;
     }
 };
 
@@ -376,8 +388,7 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
     ThreadFold<HBITS, ASSIGN> f;
     f.acc = reinterpret_cast<double *>(smem_raw) + warp * (D * 32) + lane;
     f.key = reinterpret_cast<u32 *>(smem_raw + (size_t)RF_WARPS * D * 32 * sizeof(double)) + warp * (H * 32) + lane;
-    f.rows = reinterpret_cast<u32 *>(smem_raw + (size_t)RF_WARPS * 32 * (D * sizeof(double) + H * sizeof(u32))) +
-             warp * (D * 32) + lane;
+    f.ord = smem_raw + (size_t)RF_WARPS * 32 * (D * sizeof(double) + H * sizeof(u32)) + warp * (D * 32) + lane;
     const u32 rowmask = (1u << rowbits) - 1u;
     const i64 k = (i64)bid * (RF_WARPS * 32) + threadIdx.x;
     int j = 0;           // entries of this column in the new matrix
@@ -405,7 +416,7 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
             // place first (insertion sort: the descriptors arrive nearly in order) and reads it W at a time.
             // W descriptors in registers (8; the small table shape serves short columns met by few chunks: 4)
             constexpr int W = HBITS == 4 ? 4 : 8;
-            constexpr int DEPTH = HBITS == 4 ? 2 : 3; // sectors in flight ahead of the one being folded
+            constexpr int DEPTH = (HBITS == 4 || HBITS == 15) ? 2 : 3; // sectors in flight ahead of the one being folded
             u64 *b = bucket + ps;
             if (np > (u32)W)
             {
