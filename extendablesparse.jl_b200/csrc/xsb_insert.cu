@@ -453,20 +453,68 @@ emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavo
         st_staged(dst + q, s_rec[q], L, sf, out);
 }
 
-// Grouped chunks (xsb_chunk.cuh): the records of a warp's 32 nodes (at most 480) = one chunk.
-constexpr int FDG_HB = 8;
-constexpr int FDG_NB = FD_MAXREC; // 32 nodes x at most 15 records
+// Grouped chunks (xsb_chunk.cuh): the records of a warp's 32 nodes (at most 480) = one chunk -- grouped without
+// looking at the records one by one.  Node l only touches four columns: its own (2 records per edge pair it emits
+// plus its boundary terms), l+1, l+nx and l+nx*ny (2 records each, the far ends of its x / y / z pair).  The warp runs
+// these (node, column) VISITS through its table, weighted by their record counts, kind after kind: z-ends of all
+// nodes, y-ends, x-ends, own columns.  Inside one kind every lane holds a different column (no match.any, no
+// leader election), and a column meets its visitors in node = call order: l - nx*ny (z-end), l - nx (y-end),
+// l - 1 (x-end), l (own).  Then every lane computes its records straight into their place of the grouped chunk in
+// shared memory, and the chunk leaves as whole 32-byte sectors, consecutive lanes to consecutive sectors.
+constexpr int FDG_HB = 8; // 256 slots for at most 128 distinct columns
 struct FdWarpSpace
 {
     Rec rec[32 * FD_MAXREC];
     ChunkSpaceT<FDG_HB> tab;
 };
 
+// one kind of visit: every valid lane holds a DIFFERENT grouping key.  Returns (slot << 16 | records of the column
+// before this visit); the column's count grows by `weight`.
+template <int HB>
+__device__ __forceinline__ u32 chunk_visit_batch(ChunkSpaceT<HB> &ws, u32 g, bool valid, u32 weight, u32 lt, u32 &d)
+{
+    constexpr u32 full = 0xffffffffu;
+    constexpr int H = ChunkSpaceT<HB>::H;
+    u32 slot = ch_hash(g, HB), old = 0;
+    bool fresh = false;
+    if (valid)
+    {
+        for (;;)
+        {
+            u32 k = ws.key[slot];
+            if (k == g)
+                break;
+            if (k == CH_EMPTY)
+            {
+                k = atomicCAS(&ws.key[slot], CH_EMPTY, g);
+                if (k == CH_EMPTY)
+                {
+                    fresh = true;
+                    break;
+                }
+            }
+            slot = (slot + 1) & (H - 1);
+        }
+        old = ws.cnt[slot]; // distinct keys: distinct slots
+        ws.cnt[slot] = (unsigned short)(old + weight);
+    }
+    const u32 rb = __ballot_sync(full, fresh);
+    if (rb)
+    {
+        if (fresh)
+            ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
+        d += __popc(rb);
+    }
+    __syncwarp();
+    return (slot << 16) | old;
+}
+
 __global__ void __launch_bounds__(FD_THREADS)
 emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour, i64 l_begin, i64 l_end,
                            i64 rec_begin, Rec *__restrict__ out, StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr u32 full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FdWarpSpace &sp = reinterpret_cast<FdWarpSpace *>(smem_raw)[warp];
     const u32 wchunk = blockIdx.x * (FD_THREADS / 32) + warp;
@@ -474,49 +522,102 @@ emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u
     if (l_first >= l_end)
         return;
     const i64 l_last = min(l_first + 32, l_end);
-    const i64 w_rec0 = g.before_node<4>(l_first);
-    const u32 len = (u32)(g.before_node<4>(l_last) - w_rec0);
     chunk_space_init(sp.tab, lane);
     const i64 l0 = l_first + lane;
-    if (l0 < l_last)
-        fd_node_records(g, l0, seed, ones, L, tid, flavour, sp.rec, w_rec0);
+    const bool have = l0 < l_last;
+    i64 i = 1, j = 1, k = 1;
+    if (have)
+        node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
+    const bool ex = have && i < g.nx, ey = have && j < g.ny, ez = have && k < g.nz; // the node's edge pairs
+    const bool bx = have && g.bx(i), by = have && g.by(j), bz = have && g.bz(k);    // its boundary terms
+    const u64 l = (u64)l0;
+    const u64 sx = 1, sy = (u64)g.nx, sz = (u64)(g.nx * g.ny);
+    auto gkey = [&](u64 col) { return (u32)(L.pack(col, 0, tid, flavour) >> rt.colshift) & rt.gmask; };
+    const u32 w_own = 2u * ((u32)ex + (u32)ey + (u32)ez) + (u32)bx + (u32)by + (u32)bz;
+    const u32 lt = lanemask_lt();
+    u32 d = 0;
+    const u32 vz = chunk_visit_batch(sp.tab, ez ? gkey(l + sz) : 0u, ez, 2u, lt, d);
+    const u32 vy = chunk_visit_batch(sp.tab, ey ? gkey(l + sy) : 0u, ey, 2u, lt, d);
+    const u32 vx = chunk_visit_batch(sp.tab, ex ? gkey(l + sx) : 0u, ex, 2u, lt, d);
+    const u32 vo = chunk_visit_batch(sp.tab, have ? gkey(l) : 0u, have, w_own, lt, d);
+    chunk_scan(sp.tab, d, lane);
+    // position of the chunk in the stream: the records of the nodes before the warp's first one (lane 0 holds it)
+    i64 w_rec0 = lane == 0 ? g.before<4>(i, j, k) : 0;
+    w_rec0 = __shfl_sync(full, w_rec0, 0);
+    u32 len = w_own + 2u * ((u32)ex + (u32)ey + (u32)ez);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        len += __shfl_xor_sync(full, len, o);
+    if (have)
+    {
+        Rec *own = sp.rec + chunk_dest(sp.tab.start, vo);
+        u64 call = (u64)g.before<1>(i, j, k);
+        const double hx = 1.0 / (double)g.nx, hy = 1.0 / (double)g.ny, hz = 1.0 / (double)g.nz;
+        auto rnd = [&]() -> double {
+            const double u = ones ? 1.0 : philox_uniform(seed, call);
+            ++call;
+            return u;
+        };
+        auto put = [&](Rec *p, double v, u64 row, u64 col) {
+            Rec r;
+            r.key = L.pack(col, row, tid, flavour);
+            r.val = v;
+            *p = r;
+        };
+        // update_pair(v, a = l, b): (-v, a, b) (-v, b, a) (v, a, a) (v, b, b) in call order (sprand.jl:87-92):
+        // the first and the last go to column b, the two in the middle to the node's own column
+        auto pair = [&](double v, u64 b, u32 visit) {
+            Rec *far = sp.rec + chunk_dest(sp.tab.start, visit);
+            put(far, -v, l, b);
+            put(own++, -v, b, l);
+            put(own++, v, l, l);
+            put(far + 1, v, b, b);
+        };
+        if (ex)
+            pair(rnd() * hy * hz / hx, l + sx, vx);
+        if (bx)
+            put(own++, rnd() * hy * hz, l, l);
+        if (ey)
+            pair(rnd() * hx * hz / hy, l + sy, vy);
+        if (by)
+            put(own++, rnd() * hx * hz, l, l);
+        if (ez)
+            pair(rnd() * hx * hy / hz, l + sz, vz);
+        if (bz)
+            put(own++, rnd() * hx * hy, l, l);
+    }
     __syncwarp();
     const i64 c0 = w_rec0 - rec_begin; // position of the chunk in this launch's output
-    const u32 lt = lanemask_lt();
-    u32 rs[FDG_NB];
-    u32 d = 0;
-    bool grouped = true;
-#pragma unroll
-    for (int b = 0; b < FDG_NB; ++b)
-    {
-        rs[b] = 0;
-        if ((u32)(b * 32) < len && grouped) // warp-uniform
-        {
-            const u32 q = b * 32 + lane;
-            const u64 key = q < len ? sp.rec[q].key : 0ull;
-            if (d > ChunkSpaceT<FDG_HB>::DMAX - 32u)
-                grouped = false;
-            else
-                rs[b] = chunk_count_batch(sp.tab, (u32)(key >> rt.colshift) & rt.gmask, q < len, lt, d);
-        }
-    }
-    if (grouped)
-        chunk_scan(sp.tab, d, lane);
-    Rec *dst = out + c0;
-#pragma unroll
-    for (int b = 0; b < FDG_NB; ++b)
-    {
-        const u32 q = b * 32 + lane;
-        if (q < len)
-        {
-            const Rec r = sp.rec[q];
-            const u32 to = grouped ? chunk_dest(sp.tab.start, rs[b]) : q;
-            st_rec(dst + to, r);
+    { // the grouped chunk leaves shared memory as whole sectors
+        Rec *dst = out + c0;
+        const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) >> 4) & 1u; // dst[0] is the upper half of its sector
+        auto mark = [&](const Rec &r, u32 t) {
             if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
-                sf.flags[(sf.pos0 + c0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
+                sf.flags[(sf.pos0 + c0 + (i64)t) >> kRouteTileShift] = 1; // benign race: same value
+        };
+        if (a && lane == 0 && len > 0)
+        {
+            const Rec r = sp.rec[0];
+            st_rec(dst, r);
+            mark(r, 0);
+        }
+        const u32 pairs = (len - min(a, len)) >> 1;
+        for (u32 q = lane; q < pairs; q += 32)
+        {
+            const u32 t = a + 2 * q;
+            const Rec r0 = sp.rec[t], r1 = sp.rec[t + 1];
+            st_v4_u64(dst + t, r0.key, (u64)__double_as_longlong(r0.val), r1.key, (u64)__double_as_longlong(r1.val));
+            mark(r0, t);
+            mark(r1, t + 1);
+        }
+        if (len > a && ((len - a) & 1u) && lane == 31)
+        {
+            const Rec r = sp.rec[len - 1];
+            st_rec(dst + len - 1, r);
+            mark(r, len - 1);
         }
     }
-    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, grouped, lane);
+    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, true, lane);
 }
 
 void emit_fdrand(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid,
