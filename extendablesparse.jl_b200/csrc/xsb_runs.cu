@@ -816,8 +816,9 @@ void runs_fold(cudaStream_t stream, const Rec *buf, const KeyLayout &L, i64 ncol
         level = 2;
     else if (g_runs_hbits == 6)
         level = 3;
-    const unsigned tpb = 32u * (unsigned)(level == 3 ? RfShape<6>::kWarps : RfShape<4>::kWarps); // threads per block
-    static_assert(RfShape<4>::kWarps == RfShape<15>::kWarps && RfShape<4>::kWarps == RfShape<5>::kWarps, "block shape");
+    const unsigned tpb = 32u * (unsigned)(level == 3 ? RfShape<6>::kWarps
+                                                      : (level == 2 ? RfShape<5>::kWarps
+                                                                    : (level == 1 ? RfShape<15>::kWarps : RfShape<4>::kWarps)));
     const unsigned blocks = (unsigned)(((u64)ncols + tpb - 1) / tpb);
     u32 *ticket = reinterpret_cast<u32 *>(status + blocks + 1);
     if (!first_try) // look-back words + ticket were cleared with the bucket workspace the first time
