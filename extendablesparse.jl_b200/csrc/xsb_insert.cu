@@ -109,6 +109,11 @@ template <typename Ti> struct SrcIJV
         j = (i64)J[k] - base;
         v = V[k];
     }
+    __device__ __forceinline__ void load_ij(i64 k, i64 &i, i64 &j) const
+    {
+        i = (i64)I[k] - base;
+        j = (i64)J[k] - base;
+    }
 };
 struct SrcTriplet
 {
@@ -120,6 +125,12 @@ struct SrcTriplet
         i = (i64)t.x - base;
         j = (i64)t.y - base;
         v = __hiloint2double((int)t.w, (int)t.z);
+    }
+    __device__ __forceinline__ void load_ij(i64 k, i64 &i, i64 &j) const
+    {
+        const uint2 t = *reinterpret_cast<const uint2 *>(T + k);
+        i = (i64)t.x - base;
+        j = (i64)t.y - base;
     }
 };
 
@@ -205,18 +216,212 @@ pack_grouped_kernel(Src src, i64 count, u32 nchunks, i64 m, i64 n, KeyLayout L, 
     }
 }
 
+// The same grouping for a source that does NOT alias the output (device arrays of the caller, the temporary copies
+// of host (I,J,V) arrays).  pack_grouped_kernel holds a chunk's 512 records in registers (128 of them: 16 warps per
+// SM) and stores each record on its own -- a half-filled 32-byte sector per store.  Here only the 4-byte grouping
+// keys pass through shared memory: pass 1 reads the chunk (coalesced) and notes every record's key; the 16 batches
+// run over the keys and leave (slot, rank) in their place; an inverse map (2 bytes per record) turns that into
+// "which record goes to position t"; pass 3 walks the grouped chunk in DESTINATION order, reads the two records of a
+// sector again (the chunk's 8 KB are in L2), and stores whole sectors, consecutive lanes to consecutive sectors.
+// 8 KB of shared memory and ~50 registers per warp: 24 warps per SM.  Measured (FEM 128^3 as device triplets,
+// 245.8 M): 3.9 -> see profiles/r2_summary.md.
+constexpr int PG2_WARPS = 8;
+struct Pg2WarpSpace
+{
+    u32 g[CH_RECORDS];              // grouping key of record p, then (slot << 16 | rank)
+    unsigned short inv[CH_RECORDS]; // record that goes to position t of the grouped chunk
+    ChunkSpaceT<PG_HB> tab;
+};
+
+template <class Src>
+__global__ void __launch_bounds__(PG2_WARPS * 32, 3)
+pack_grouped2_kernel(Src src, i64 count, u32 nchunks, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour, Rec *__restrict__ out,
+                     u64 *__restrict__ d_err, RunTarget rt, u32 chunk0, u32 pos0, StageFlags sf)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef ChunkSpaceT<PG_HB> Space;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 c = blockIdx.x * PG2_WARPS + warp;
+    if (c >= nchunks)
+        return;
+    Pg2WarpSpace &sp = reinterpret_cast<Pg2WarpSpace *>(smem_raw)[warp];
+    chunk_space_init(sp.tab, lane);
+    const u32 lt = lanemask_lt();
+    const i64 c0 = (i64)c * CH_RECORDS;
+    const u32 len = (u32)min((i64)CH_RECORDS, count - c0);
+    // an index outside the matrix is a BoundsError (sparsematrixcsc.jl:8-10): the batch is rejected, whatever is
+    // written for it is dropped
+    auto key_of = [&](i64 i, i64 j) {
+        const bool bad = i < 0 || i >= m || j < 0 || j >= n;
+        return L.pack(bad ? 0ull : (u64)j, bad ? 0ull : (u64)i, tid, flavour);
+    };
+    // pass 1: the chunk's indices, eight coalesced loads in flight per lane before the first one is used
+#pragma unroll
+    for (int b0 = 0; b0 < PG_NB; b0 += 8)
+    {
+        if ((u32)(b0 * 32) >= len) // warp-uniform
+            break;
+        i64 ii[8], jj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+            const u32 p = (b0 + u) * 32 + lane;
+            ii[u] = jj[u] = 0;
+            if (p < len)
+                src.load_ij(c0 + p, ii[u], jj[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+            const u32 p = (b0 + u) * 32 + lane;
+            if (p < len)
+            {
+                if (ii[u] < 0 || ii[u] >= m || jj[u] < 0 || jj[u] >= n)
+                    atomicMin(d_err, (u64)(c0 + p));
+                sp.g[p] = (u32)(key_of(ii[u], jj[u]) >> rt.colshift) & rt.gmask;
+            }
+        }
+    }
+    __syncwarp();
+    u32 d = 0;
+    bool grouped = true;
+    for (int b = 0; b < PG_NB && grouped; ++b)
+    {
+        if ((u32)(b * 32) >= len) // warp-uniform
+            break;
+        if (d > Space::DMAX - 32u)
+            grouped = false; // the table may not take another 32 columns: no column locality here
+        else
+        {
+            const u32 p = b * 32 + lane;
+            const u32 rs = chunk_count_batch(sp.tab, p < len ? sp.g[p] : 0u, p < len, lt, d);
+            if (p < len)
+                sp.g[p] = rs;
+        }
+    }
+    if (grouped)
+    {
+        chunk_scan(sp.tab, d, lane);
+        for (u32 p = lane; p < len; p += 32)
+            sp.inv[chunk_dest(sp.tab.start, sp.g[p])] = (unsigned short)p;
+    }
+    else
+        for (u32 p = lane; p < len; p += 32)
+            sp.inv[p] = (unsigned short)p; // stored in call order
+    __syncwarp();
+    {
+        Rec *dst = out + c0;
+        const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) >> 4) & 1u; // dst[0] is the upper half of its sector
+        auto mark = [&](const Rec &r, u32 t) {
+            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                sf.flags[(sf.pos0 + c0 + (i64)t) >> kRouteTileShift] = 1; // benign race: same value
+        };
+        auto make = [&](u32 p) {
+            i64 i, j;
+            Rec r;
+            src.load(c0 + p, i, j, r.val);
+            r.key = key_of(i, j);
+            return r;
+        };
+        if (a && lane == 0 && len > 0)
+        {
+            const Rec r = make(sp.inv[0]);
+            st_rec(dst, r);
+            mark(r, 0);
+        }
+        const u32 pairs = (len - min(a, len)) >> 1;
+        // pass 3: four sectors per lane and round: their eight records are requested before the first one is used
+        for (u32 q0 = 0; q0 < pairs; q0 += 128)
+        {
+            i64 ii[8], jj[8];
+            double vv[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const u32 q = q0 + u * 32 + lane;
+                ii[2 * u] = jj[2 * u] = ii[2 * u + 1] = jj[2 * u + 1] = 0;
+                vv[2 * u] = vv[2 * u + 1] = 0.0;
+                if (q < pairs)
+                {
+                    const u32 t = a + 2 * q;
+                    const u32 pp = *reinterpret_cast<const u32 *>(reinterpret_cast<const unsigned char *>(sp.inv) + 2 * (t & ~1u));
+                    // inv[t], inv[t + 1] (t odd: the pair straddles two words)
+                    const u32 p0 = (t & 1u) ? (pp >> 16) : (pp & 0xffffu);
+                    const u32 p1 = (t & 1u) ? (u32)sp.inv[t + 1] : (pp >> 16);
+                    src.load(c0 + p0, ii[2 * u], jj[2 * u], vv[2 * u]);
+                    src.load(c0 + p1, ii[2 * u + 1], jj[2 * u + 1], vv[2 * u + 1]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const u32 q = q0 + u * 32 + lane;
+                if (q < pairs)
+                {
+                    const u32 t = a + 2 * q;
+                    Rec r0, r1;
+                    r0.key = key_of(ii[2 * u], jj[2 * u]);
+                    r0.val = vv[2 * u];
+                    r1.key = key_of(ii[2 * u + 1], jj[2 * u + 1]);
+                    r1.val = vv[2 * u + 1];
+                    st_v4_u64(dst + t, r0.key, (u64)__double_as_longlong(r0.val), r1.key, (u64)__double_as_longlong(r1.val));
+                    mark(r0, t);
+                    mark(r1, t + 1);
+                }
+            }
+        }
+        if (len > a && ((len - a) & 1u) && lane == 31)
+        {
+            const Rec r = make(sp.inv[len - 1]);
+            st_rec(dst + len - 1, r);
+            mark(r, len - 1);
+        }
+    }
+    if (grouped)
+        chunk_publish(sp.tab, rt, chunk0 + c, pos0 + (u32)c0, d, true, lane);
+    else
+    { // no column locality in this chunk: every record a run of its own
+        u32 gk[PG_NB];
+#pragma unroll
+        for (int b = 0; b < PG_NB; ++b)
+        {
+            const u32 p = b * 32 + lane;
+            gk[b] = 0u;
+            if (p < len)
+            {
+                i64 i, j;
+                src.load_ij(c0 + p, i, j);
+                gk[b] = (u32)(key_of(i, j) >> rt.colshift) & rt.gmask;
+            }
+        }
+        chunk_publish_singletons<PG_NB>(rt, chunk0 + c, pos0 + (u32)c0, len, gk, lane);
+    }
+}
+
 template <class Src>
 static u32 launch_pack_grouped(cudaStream_t stream, Src src, i64 count, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour,
                                Rec *out, u64 *d_err, const RunTarget &rt, u32 chunk0, u32 pos0, StageFlags sf,
-                               LaunchCounter &lc)
+                               LaunchCounter &lc, bool aliased)
 {
-    static FuncAttrOnce once;
-    const int smem = (int)(sizeof(ChunkSpaceT<PG_HB>) * PG_WARPS);
-    once.set(pack_grouped_kernel<Src>, smem);
     const u32 nchunks = (u32)((count + CH_RECORDS - 1) / CH_RECORDS);
-    const unsigned blocks = (nchunks + PG_WARPS - 1) / PG_WARPS;
-    pack_grouped_kernel<Src><<<blocks, PG_WARPS * 32, smem, stream>>>(src, count, nchunks, m, n, L, tid, flavour, out,
-                                                                      d_err, rt, chunk0, pos0, sf);
+    if (aliased)
+    { // the source IS the staging buffer (triplets copied there from the host): every warp reads its whole chunk first
+        static FuncAttrOnce once;
+        const int smem = (int)(sizeof(ChunkSpaceT<PG_HB>) * PG_WARPS);
+        once.set(pack_grouped_kernel<Src>, smem);
+        const unsigned blocks = (nchunks + PG_WARPS - 1) / PG_WARPS;
+        pack_grouped_kernel<Src><<<blocks, PG_WARPS * 32, smem, stream>>>(src, count, nchunks, m, n, L, tid, flavour, out,
+                                                                          d_err, rt, chunk0, pos0, sf);
+    }
+    else
+    {
+        static FuncAttrOnce once;
+        const int smem = (int)(sizeof(Pg2WarpSpace) * PG2_WARPS);
+        once.set(pack_grouped2_kernel<Src>, smem, true);
+        const unsigned blocks = (nchunks + PG2_WARPS - 1) / PG2_WARPS;
+        pack_grouped2_kernel<Src><<<blocks, PG2_WARPS * 32, smem, stream>>>(src, count, nchunks, m, n, L, tid, flavour, out,
+                                                                            d_err, rt, chunk0, pos0, sf);
+    }
     lc.add();
     XSB_CUDA(cudaGetLastError());
     return nchunks;
@@ -233,9 +438,9 @@ u32 pack_records_grouped(cudaStream_t stream, const void *I, const void *J, cons
         return 0;
     if (idx64)
         return launch_pack_grouped(stream, SrcIJV<int64_t>{(const int64_t *)I, (const int64_t *)J, V, (i64)base}, count, m,
-                                   n, L, tid, flavour, out, d_err, rt, chunk0, pos0, sf, lc);
+                                   n, L, tid, flavour, out, d_err, rt, chunk0, pos0, sf, lc, false);
     return launch_pack_grouped(stream, SrcIJV<int32_t>{(const int32_t *)I, (const int32_t *)J, V, (i64)base}, count, m, n,
-                               L, tid, flavour, out, d_err, rt, chunk0, pos0, sf, lc);
+                               L, tid, flavour, out, d_err, rt, chunk0, pos0, sf, lc, false);
 }
 
 u32 pack_triplets_grouped(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
@@ -245,7 +450,7 @@ u32 pack_triplets_grouped(cudaStream_t stream, const void *T, i64 count, int bas
     if (count <= 0)
         return 0;
     return launch_pack_grouped(stream, SrcTriplet{static_cast<const uint4 *>(T), (i64)base}, count, m, n, L, tid, flavour,
-                               out, d_err, rt, chunk0, pos0, sf, lc);
+                               out, d_err, rt, chunk0, pos0, sf, lc, static_cast<const void *>(T) == static_cast<const void *>(out));
 }
 
 template <typename Ti>
