@@ -132,6 +132,9 @@ struct xsb_matrix
     bool profiling = false;
     xsb_flush_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host triplets arrive in slices on a second stream while the slices before them are packed (xsb_insert_triplets)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_slice[3] = {nullptr, nullptr, nullptr};
 
     float alloc_ms = 0.f; // host time spent inside cudaMallocAsync (reset per flush)
     static constexpr size_t kBigBytes = (size_t)32 << 20;
@@ -1973,6 +1976,14 @@ int32_t xsb_destroy(xsb_matrix *h)
         cudaEventDestroy(h->ev0);
     if (h->ev1)
         cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->ev_slice)
+        if (e)
+            cudaEventDestroy(e);
+    if (h->copy_stream)
+    {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
     if (h->stream)
     {
         cudaStreamSynchronize(h->stream);
@@ -2143,22 +2154,54 @@ int32_t xsb_insert_triplets(xsb_matrix *h, int32_t tid, const xsb_triplet *T, in
         REQUIRE(T, XSB_EINVAL, "NULL array");
         REQUIRE((reinterpret_cast<uintptr_t>(T) & 15u) == 0, XSB_EINVAL, "triplet array must be 16-byte aligned");
         Rec *dst = begin_emit(h, tid, flavour, count);
-        const void *src = T;
-        if (!is_device_ptr(T))
-        { // PCIe straight into the staging buffer; the kernel below rewrites the records in place
-            XSB_CUDA(cudaMemcpyAsync(dst, T, sizeof(Rec) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
-            src = dst;
-        }
+        const bool from_host = !is_device_ptr(T);
         write_scalar(h, 1, ~0ull);
         RunTarget rt;
         u32 chunk0 = 0, pos0 = 0, chunks = 0;
         const bool grouped = runs_begin(h, tid, count, pack_chunks(count), &rt, &chunk0, &pos0);
-        if (grouped)
-            chunks = pack_triplets_grouped(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid,
-                                           (u32)flavour, dst, h->d_scal + 1, h->lc, rt, chunk0, pos0, h->stage_flags(tid));
-        else
-            pack_triplets(h->stream, src, count, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst,
-                          h->d_scal + 1, h->lc, h->stage_flags(tid));
+        // Host triplets go over PCIe straight into the staging buffer and are rewritten in place.  A large batch
+        // travels in slices on a second stream, and slice k is packed while slice k + 1 is on the wire: the packing
+        // (1.6 ms per 100 M records) disappears behind the transfer.
+        constexpr i64 kSlice = (i64)1 << 22; // 4 M records = 64 MB: a whole number of chunks (pack_chunks)
+        const bool sliced = from_host && count >= 3 * kSlice;
+        if (sliced && !h->copy_stream)
+        {
+            XSB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t &e : h->ev_slice)
+                XSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        if (sliced)
+        { // the transfers may not overtake what the handle's stream still does with the staging buffer
+            XSB_CUDA(cudaEventRecord(h->ev_slice[2], h->stream));
+            XSB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_slice[2], 0));
+        }
+        const i64 step = sliced ? kSlice : count;
+        int k = 0;
+        for (i64 off = 0; off < count; off += step, ++k)
+        {
+            const i64 cnt = std::min(step, count - off);
+            const void *src = static_cast<const Rec *>(static_cast<const void *>(T)) + off;
+            if (from_host)
+            {
+                cudaStream_t cs = sliced ? h->copy_stream : h->stream;
+                XSB_CUDA(cudaMemcpyAsync(dst + off, src, sizeof(Rec) * (size_t)cnt, cudaMemcpyHostToDevice, cs));
+                if (sliced)
+                {
+                    XSB_CUDA(cudaEventRecord(h->ev_slice[k & 1], cs));
+                    XSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_slice[k & 1], 0));
+                }
+                src = dst + off;
+            }
+            StageFlags sf = h->stage_flags(tid);
+            sf.pos0 += off;
+            if (grouped)
+                chunks += pack_triplets_grouped(h->stream, src, cnt, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour,
+                                                dst + off, h->d_scal + 1, h->lc, rt, chunk0 + pack_chunks(off),
+                                                pos0 + (u32)off, sf);
+            else
+                pack_triplets(h->stream, src, cnt, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst + off,
+                              h->d_scal + 1, h->lc, sf);
+        }
         const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)
         {

@@ -101,6 +101,68 @@ def test_two_flush_implementations_agree_bitwise(xsb, torch, case):
     assert torch.equal(nz.view(torch.int64), nz2.view(torch.int64)), "nzval differs between the two flush paths"
 
 
+def test_insertion_paths_agree_with_the_emitter(xsb, torch):
+    """The generic insertion paths at a size that exercises their large-batch machinery -- the FEM 80^3 stream
+    (59 M rawupdateindex! calls): (a) 16-byte triplets in HOST memory (xsb_insert_triplets: slices over PCIe on a
+    second stream, packed in place while the next slice travels), (b) the same triplets resident on the DEVICE
+    (grouped through shared-memory keys, re-read in destination order), (c) device (I,J,V) arrays, (d) host (I,J,V)
+    arrays -- all give the CSC of the stream generated on the device, bit for bit; a BoundsError in the LAST slice
+    rejects the whole batch."""
+    mesh = 80
+    n = mesh ** 3
+    ref = xsb.Handle(n, n)
+    ref.set_precount(False)  # the staged records in call order
+    ref.emit_p1fem(mesh, mesh, mesh, flavour=xsb.RAW)
+    cnt = ref.pending
+    assert cnt >= 3 * (1 << 22)
+    dI = torch.empty(cnt, dtype=torch.int64, device="cuda")
+    dJ = torch.empty_like(dI)
+    dV = torch.empty(cnt, dtype=torch.float64, device="cuda")
+    got = C.c_int64(0)
+    c = xsb.capi
+    c.check(c.lib().xsb_debug_fetch_staged(ref._h, 0, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), None, cnt,
+                                           C.byref(got)), ref._h)
+    ref.flush()
+    want = [t.clone() for t in device_csc(torch, ref)]
+    ref.close()
+    dT = torch.empty((cnt, 2), dtype=torch.int64, device="cuda")
+    dT[:, 0] = dI | (dJ << 32)
+    dT[:, 1] = dV.view(torch.int64)
+    hT = dT.cpu()
+
+    def same(h):
+        for a, b in zip(device_csc(torch, h), want):
+            assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+
+    h = xsb.Handle(n, n)
+    h.insert_triplets(hT, xsb.RAW, 0, cnt)  # (a)
+    h.flush()
+    assert h.flush_stats()["column_path"] == 4
+    same(h)
+    h.reset()
+    h.insert_triplets(dT, xsb.RAW, 0, cnt)  # (b)
+    h.flush()
+    same(h)
+    h.reset()
+    h.insert_batch(dI, dJ, dV, xsb.RAW)  # (c)
+    h.flush()
+    same(h)
+    h.reset()
+    h.insert_batch(dI.cpu().numpy(), dJ.cpu().numpy(), dV.cpu().numpy(), xsb.RAW)  # (d)
+    h.flush()
+    same(h)
+    h.reset()
+    bad = hT.clone()
+    bad[cnt - 7, 0] = (n + 1) | (1 << 32)  # row n + 1 in the last slice
+    with pytest.raises(IndexError):
+        h.insert_triplets(bad, xsb.RAW, 0, cnt)
+    assert h.pending == 0
+    h.insert_triplets(hT, xsb.RAW, 0, cnt)
+    h.flush()
+    same(h)
+    h.close()
+
+
 @pytest.mark.parametrize("preagg", [False, True])
 def test_fast_mode_full_size_fem(xsb, torch, preagg):
     n, mk, _, nnz_ref = CASES["cfg2_fem128"]
