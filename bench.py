@@ -651,9 +651,30 @@ def measure_e2e(args, xsb, local, mesh, n, mode, np, torch):
     hT = torch.empty((cnt, 2), dtype=torch.int64, pin_memory=True)
     hT.copy_(dT)
     torch.cuda.synchronize()
-    del dI, dJ, dV, dT
+    del dI, dJ, dV
     g.reset()
     g.set_precount(True)
+
+    # the generic insertion path with the stream RESIDENT in HBM (what a CUDA.jl kernel that wrote its triplets to a
+    # device array would call): xsb_insert_triplets on a device pointer + xsb_flush, nothing crosses PCIe
+    def step_dev():
+        g.reset()
+        g.insert_triplets(dT, xsb.RAW, 0, cnt)
+        return g.flush(mode)
+
+    for _ in range(2):
+        step_dev()
+    g.synchronize()
+    g.timer_start()
+    for _ in range(3):
+        step_dev()
+    ms_dev = g.timer_stop() / 3
+    g.set_profiling(True)
+    step_dev()
+    ms_dev_flush = g.flush_stats()["ms_total"]
+    g.set_profiling(False)
+    del dT
+    g.reset()
 
     # the extension object of the glue, its triplet buffer living in pinned host memory
     ext = dropin.SparseMatrixB200(en, en, buffer=hT.numpy().view(c.TRIPLET_DTYPE).reshape(-1))
@@ -723,6 +744,10 @@ def measure_e2e(args, xsb, local, mesh, n, mode, np, torch):
                        "d2h_bytes_per_step": 8 * (en + 1) + 16 * int(nnz_s),
                        "workload": "flush! with a resident matrix: old CSC uploaded through xsb_set_csc, 1 % new entries "
                                    "(xsb_insert_triplets), merged CSC read back"},
+            "device_triplets": {"value": cnt / (ms_dev / 1e3), "unit": UNIT, "ms_per_step": ms_dev,
+                                "ms_insert": ms_dev - ms_dev_flush, "ms_flush": ms_dev_flush,
+                                "workload": "same stream as 16-byte triplets resident in HBM: xsb_insert_triplets on a "
+                                            "device pointer (pack_grouped2_kernel) + xsb_flush; no PCIe"},
             "ijv": {"value": cnt / (ms_ijv / 1e3), "unit": UNIT, "h2d_bytes_per_step": 24 * cnt + 8 * (en + 1),
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_ijv,
                     "workload": "same stream as three pinned host arrays Int64 I, Int64 J, Float64 V "
