@@ -179,30 +179,60 @@ runpair_scan_kernel(const u32 *__restrict__ colpairs, i64 n, u32 *__restrict__ p
 // run descriptor: [region rank : 2][position of the run's first record : 32][records : 11]
 __device__ __forceinline__ u64 run_entry(u32 rank, u32 pos, u32 cnt) { return ((u64)rank << 43) | ((u64)pos << 11) | (u64)cnt; }
 
-// a warp per chunk: its pairs go into their columns' buckets.  colpairs counts DOWN: afterwards it is zero again.
+// A warp drops the pairs of RB_CHUNKS chunks into their columns' buckets; colpairs counts DOWN: afterwards it is zero
+// again.  The way of a pair is a chain of four dependent memory operations (chunk info -> column -> bucket start and
+// ticket -> store): the chunks of a warp travel it side by side (measured: one chunk per warp 0.103 ms for the FEM
+// matrix's 10.7 M pairs, latency-bound at 86 % occupancy).
+constexpr int RB_CHUNKS = 4;
 __global__ void __launch_bounds__(256)
 run_bucket_kernel(const uint2 *__restrict__ chunkinfo, const u32 *__restrict__ chunkstart, u32 nchunks,
                   const u32 *__restrict__ pcol, const u32 *__restrict__ pinfo, int colbits, u32 me, RunRegions reg,
                   const u32 *__restrict__ pstart, u32 *__restrict__ colpairs, u64 *__restrict__ bucket)
 {
     const int lane = threadIdx.x & 31;
-    const u32 c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c >= nchunks)
+    const u32 c0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RB_CHUNKS;
+    if (c0 >= nchunks)
         return;
-    const uint2 info = chunkinfo[c];
-    const u32 start = chunkstart[c];
-    const u32 rank = start < reg.own_end ? 1u : (start < reg.low_end ? 0u : 2u);
     const u32 cmask = (1u << colbits) - 1u;
-    for (u32 j = lane; j < info.y; j += 32)
+    uint2 info[RB_CHUNKS];
+    u32 start[RB_CHUNKS], most = 0;
+#pragma unroll
+    for (int u = 0; u < RB_CHUNKS; ++u)
     {
-        const u32 p = info.x + j;
-        const u32 g = pcol[p];
-        if ((g >> colbits) != me)
-            continue;
-        const u32 col = g & cmask;
-        const u32 pi = pinfo[p];
-        const u32 slot = pstart[col] + atomicSub(colpairs + col, 1u) - 1u;
-        bucket[slot] = run_entry(rank, start + (pi >> 16), pi & 0xffffu);
+        info[u] = make_uint2(0u, 0u);
+        start[u] = 0u;
+        if (c0 + u < nchunks)
+        {
+            info[u] = chunkinfo[c0 + u];
+            start[u] = chunkstart[c0 + u];
+        }
+        most = max(most, info[u].y);
+    }
+    for (u32 j = lane; j < most; j += 32)
+    {
+        u32 g[RB_CHUNKS], pi[RB_CHUNKS], slot[RB_CHUNKS];
+        bool mine[RB_CHUNKS];
+#pragma unroll
+        for (int u = 0; u < RB_CHUNKS; ++u)
+        {
+            g[u] = j < info[u].y ? pcol[info[u].x + j] : ~0u;
+            pi[u] = j < info[u].y ? pinfo[info[u].x + j] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < RB_CHUNKS; ++u)
+        { // records of other ranks (sent already) and padding are skipped
+            mine[u] = j < info[u].y && (g[u] >> colbits) == me;
+            slot[u] = 0u;
+            if (mine[u])
+                slot[u] = pstart[g[u] & cmask] + atomicSub(colpairs + (g[u] & cmask), 1u) - 1u;
+        }
+#pragma unroll
+        for (int u = 0; u < RB_CHUNKS; ++u)
+            if (mine[u])
+            {
+                const u32 rank = start[u] < reg.own_end ? 1u : (start[u] < reg.low_end ? 0u : 2u);
+                bucket[slot[u]] = run_entry(rank, start[u] + (pi[u] >> 16), pi[u] & 0xffffu);
+            }
     }
 }
 
@@ -772,7 +802,7 @@ void runs_bucket(cudaStream_t stream, const RunTarget &rt, u32 nchunks, u32 npai
     const unsigned stiles = (unsigned)(((u64)ncols + 1 + SC_TILE - 1) / SC_TILE);
     runpair_scan_kernel<<<stiles, SC_THREADS, 0, stream>>>(colpairs, ncols, pstart, status,
                                                            reinterpret_cast<u32 *>(status + stiles + 1));
-    run_bucket_kernel<<<(nchunks + 7) / 8, 256, 0, stream>>>(rt.chunkinfo, rt.chunkstart, nchunks, rt.pcol, rt.pinfo,
+    run_bucket_kernel<<<(nchunks + 8 * RB_CHUNKS - 1) / (8 * RB_CHUNKS), 256, 0, stream>>>(rt.chunkinfo, rt.chunkstart, nchunks, rt.pcol, rt.pinfo,
                                                              L.colbits, me, reg, pstart, colpairs, bucket);
     lc.add(3);
     XSB_CUDA(cudaGetLastError());
