@@ -673,47 +673,6 @@ struct FdWarpSpace
     ChunkSpaceT<FDG_HB> tab;
 };
 
-// one kind of visit: every valid lane holds a DIFFERENT grouping key.  Returns (slot << 16 | records of the column
-// before this visit); the column's count grows by `weight`.
-template <int HB>
-__device__ __forceinline__ u32 chunk_visit_batch(ChunkSpaceT<HB> &ws, u32 g, bool valid, u32 weight, u32 lt, u32 &d)
-{
-    constexpr u32 full = 0xffffffffu;
-    constexpr int H = ChunkSpaceT<HB>::H;
-    u32 slot = ch_hash(g, HB), old = 0;
-    bool fresh = false;
-    if (valid)
-    {
-        for (;;)
-        {
-            u32 k = ws.key[slot];
-            if (k == g)
-                break;
-            if (k == CH_EMPTY)
-            {
-                k = atomicCAS(&ws.key[slot], CH_EMPTY, g);
-                if (k == CH_EMPTY)
-                {
-                    fresh = true;
-                    break;
-                }
-            }
-            slot = (slot + 1) & (H - 1);
-        }
-        old = ws.cnt[slot]; // distinct keys: distinct slots
-        ws.cnt[slot] = (unsigned short)(old + weight);
-    }
-    const u32 rb = __ballot_sync(full, fresh);
-    if (rb)
-    {
-        if (fresh)
-            ws.cand[d + __popc(rb & lt)] = (unsigned short)slot;
-        d += __popc(rb);
-    }
-    __syncwarp();
-    return (slot << 16) | old;
-}
-
 __global__ void __launch_bounds__(FD_THREADS)
 emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour, i64 l_begin, i64 l_end,
                            i64 rec_begin, Rec *__restrict__ out, StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
@@ -793,35 +752,7 @@ emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u
     }
     __syncwarp();
     const i64 c0 = w_rec0 - rec_begin; // position of the chunk in this launch's output
-    { // the grouped chunk leaves shared memory as whole sectors
-        Rec *dst = out + c0;
-        const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) >> 4) & 1u; // dst[0] is the upper half of its sector
-        auto mark = [&](const Rec &r, u32 t) {
-            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
-                sf.flags[(sf.pos0 + c0 + (i64)t) >> kRouteTileShift] = 1; // benign race: same value
-        };
-        if (a && lane == 0 && len > 0)
-        {
-            const Rec r = sp.rec[0];
-            st_rec(dst, r);
-            mark(r, 0);
-        }
-        const u32 pairs = (len - min(a, len)) >> 1;
-        for (u32 q = lane; q < pairs; q += 32)
-        {
-            const u32 t = a + 2 * q;
-            const Rec r0 = sp.rec[t], r1 = sp.rec[t + 1];
-            st_v4_u64(dst + t, r0.key, (u64)__double_as_longlong(r0.val), r1.key, (u64)__double_as_longlong(r1.val));
-            mark(r0, t);
-            mark(r1, t + 1);
-        }
-        if (len > a && ((len - a) & 1u) && lane == 31)
-        {
-            const Rec r = sp.rec[len - 1];
-            st_rec(dst + len - 1, r);
-            mark(r, len - 1);
-        }
-    }
+    chunk_copy_out(sp.rec, len, out + c0, lane, L, sf.flags, sf.pos0 + c0);
     chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, true, lane);
 }
 
@@ -1283,6 +1214,7 @@ constexpr int RDG_NB = CH_RECORDS / 32;
 struct RdWarpSpace
 {
     Rec rec[CH_RECORDS];
+    u32 vis[4 * 32]; // visits [kind][lane]: (slot, records of the column before the visit)
     ChunkSpaceT<RDG_HB> tab;
 };
 __host__ __device__ inline i64 rd_node_rec(const RdGeom &g, i64 l0)
@@ -1303,11 +1235,20 @@ static int rd_nodes_per_warp(i64 ns)
     return (int)std::max<i64>(1, std::min<i64>(32 / ns2, CH_RECORDS / (13 * ns2)));
 }
 
+// Grouping by VISITS (see emit_fdrand_grouped_kernel): node l touches the ns columns of its own block row -- from every
+// edge pair it emits 2 ns records per column, plus ns reaction records -- and the ns columns of each far end (2 ns
+// records per column).  A warp holds npw nodes, so a kind of visit (z-ends, y-ends, x-ends, own) has npw * ns <= 32
+// (node, species) visitors with different columns; a column meets its visitors in node = call order.  Every
+// (node, a, b) item then computes its 13 records straight into their place of the grouped chunk in shared memory:
+//   far column (pair d, species b):  (-v, i_a, j_b) at 2 a, (v, j_a, j_b) at 2 a + 1
+//   own column b: pair d (the dd-th existing one): (-v, j_a, i_b) at 2 ns dd + 2 a, (v, i_a, i_b) one behind it;
+//                 reaction (i_a, i_b) at 2 ns nd + a
 __global__ void __launch_bounds__(RDG_WARPS * 32)
 emit_blockrd_grouped_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, int npw, Rec *__restrict__ out,
                             StageFlags sf, RunTarget rt, u32 chunk0, u32 pos_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr u32 full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RdWarpSpace &sp = reinterpret_cast<RdWarpSpace *>(smem_raw)[warp];
     const i64 N = g.nx * g.ny * g.nz;
@@ -1316,89 +1257,81 @@ emit_blockrd_grouped_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavou
     if (l_first >= N)
         return;
     const i64 l_last = min(l_first + npw, N);
-    const i64 ns2 = g.ns * g.ns;
+    const u32 ns = (u32)g.ns, ns2 = ns * ns;
     const i64 w_rec0 = rd_node_rec(g, l_first);
-    const u32 len = (u32)(rd_node_rec(g, l_last) - w_rec0);
     chunk_space_init(sp.tab, lane);
-    const i64 nitems = (l_last - l_first) * ns2;
-    for (i64 it = lane; it < nitems; it += 32)
+    const i64 step[3] = {1, g.nx, g.nx * g.ny};
+    auto gkey = [&](u64 col) { return (u32)(L.pack(col, 0, tid, flavour) >> rt.colshift) & rt.gmask; };
+    const u32 lt = lanemask_lt();
+    u32 d = 0, len = 0;
+    { // ---- the visits: lane v = (node v / ns, species v % ns)
+        const u32 nvis = (u32)(l_last - l_first) * ns; // <= 32
+        const bool have = (u32)lane < nvis;
+        const u32 vn = (u32)lane / ns, vb = (u32)lane - vn * ns;
+        const i64 l0 = l_first + (i64)vn;
+        i64 i = 1, j = 1, k = 1;
+        if (have)
+            node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
+        const bool has[3] = {have && i < g.nx, have && j < g.ny, have && k < g.nz};
+        const u32 nd = (u32)has[0] + (u32)has[1] + (u32)has[2];
+#pragma unroll
+        for (int dd = 2; dd >= 0; --dd) // z-ends, y-ends, x-ends
+            sp.vis[dd * 32 + lane] = chunk_visit_batch(sp.tab, has[dd] ? gkey((u64)ns * (u64)(l0 + step[dd]) + vb) : 0u,
+                                                       has[dd], 2u * ns, lt, d);
+        const u32 w_own = ns * (2u * nd + 1u);
+        sp.vis[3 * 32 + lane] = chunk_visit_batch(sp.tab, have ? gkey((u64)ns * (u64)l0 + vb) : 0u, have, w_own, lt, d);
+        len = have ? w_own + 2u * ns * nd : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            len += __shfl_xor_sync(full, len, o);
+    }
+    chunk_scan(sp.tab, d, lane);
+    const u32 nitems = (u32)(l_last - l_first) * ns2;
+    for (u32 it = lane; it < nitems; it += 32)
     {
-        const u32 nl = (u32)it / (u32)ns2; // items of a warp fit 32 bits: at most 32 nodes x ns^2
+        const u32 nl = it / ns2;
         const i64 l0 = l_first + (i64)nl;
-        const i64 ab = (i64)((u32)it - nl * (u32)ns2);
-        const u64 a = (u64)((u32)ab / (u32)g.ns), b = (u64)((u32)ab % (u32)g.ns);
+        const u32 ab = it - nl * ns2;
+        const u32 a = ab / ns, b = ab - a * ns;
         i64 i, j, k;
         node_ijk(l0, g.nx, g.ny, g.nz, i, j, k);
         const i64 eb = g.edges_before(i, j, k);
-        i64 rec = eb * 4 * ns2 + l0 * ns2 - w_rec0; // records of this chunk before this node
-        u64 call = (u64)(eb * ns2 + l0 * ns2);      // rand() calls before this node
-        const i64 step[3] = {1, g.nx, g.nx * g.ny};
+        u64 call = (u64)(eb * (i64)ns2 + l0 * (i64)ns2); // rand() calls before this node
         const bool has[3] = {i < g.nx, j < g.ny, k < g.nz};
-        const u64 ia = (u64)(g.ns * l0) + a, ib = (u64)(g.ns * l0) + b;
+        const u64 ia = (u64)((i64)ns * l0) + a, ib = (u64)((i64)ns * l0) + b;
+        const u32 v = nl * ns + b; // the visitor that speaks for this item's columns
+        Rec *own = sp.rec + chunk_dest(sp.tab.start, sp.vis[3 * 32 + v]) + 2u * a;
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
+        for (int dd = 0; dd < 3; ++dd)
         {
-            if (!has[d])
+            if (!has[dd])
                 continue;
-            const double v = philox_uniform(seed, call + (u64)ab);
-            const u64 l2 = (u64)(l0 + step[d]);
-            const u64 ja = (u64)g.ns * l2 + a, jb = (u64)g.ns * l2 + b;
-            Rec *dst = sp.rec + rec + ab * 4;
+            const double val = philox_uniform(seed, call + (u64)ab);
+            const u64 l2 = (u64)(l0 + step[dd]);
+            const u64 ja = (u64)ns * l2 + a, jb = (u64)ns * l2 + b;
+            Rec *far = sp.rec + chunk_dest(sp.tab.start, sp.vis[dd * 32 + v]) + 2u * a;
             Rec r;
-            r.val = -v;
+            r.val = -val;
             r.key = L.pack(jb, ia, tid, flavour); // (-v, i_a, j_b)
-            dst[0] = r;
+            far[0] = r;
             r.key = L.pack(ib, ja, tid, flavour); // (-v, j_a, i_b)
-            dst[1] = r;
-            r.val = v;
+            own[0] = r;
+            r.val = val;
             r.key = L.pack(ib, ia, tid, flavour); // ( v, i_a, i_b)
-            dst[2] = r;
+            own[1] = r;
             r.key = L.pack(jb, ja, tid, flavour); // ( v, j_a, j_b)
-            dst[3] = r;
-            rec += 4 * ns2;
+            far[1] = r;
+            own += 2u * ns;
             call += (u64)ns2;
         }
         Rec r;
         r.val = philox_uniform(seed, call + (u64)ab);
         r.key = L.pack(ib, ia, tid, flavour);
-        sp.rec[rec + ab] = r;
+        own[0 - (int)a] = r; // the reaction block follows the pairs: position 2 ns nd + a (own stands at ... + 2 a)
     }
     __syncwarp();
-    const u32 lt = lanemask_lt();
-    u32 rs[RDG_NB];
-    u32 d = 0;
-    bool grouped = true;
-#pragma unroll
-    for (int bb = 0; bb < RDG_NB; ++bb)
-    {
-        rs[bb] = 0;
-        if ((u32)(bb * 32) < len && grouped) // warp-uniform
-        {
-            const u32 q = bb * 32 + lane;
-            const u64 key = q < len ? sp.rec[q].key : 0ull;
-            if (d > ChunkSpaceT<RDG_HB>::DMAX - 32u)
-                grouped = false;
-            else
-                rs[bb] = chunk_count_batch(sp.tab, (u32)(key >> rt.colshift) & rt.gmask, q < len, lt, d);
-        }
-    }
-    if (grouped)
-        chunk_scan(sp.tab, d, lane);
-    Rec *dst = out + w_rec0;
-#pragma unroll
-    for (int bb = 0; bb < RDG_NB; ++bb)
-    {
-        const u32 q = bb * 32 + lane;
-        if (q < len)
-        {
-            const Rec r = sp.rec[q];
-            const u32 to = grouped ? chunk_dest(sp.tab.start, rs[bb]) : q;
-            st_rec(dst + to, r);
-            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
-                sf.flags[(sf.pos0 + w_rec0 + (i64)to) >> kRouteTileShift] = 1; // benign race: same value
-        }
-    }
-    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)w_rec0, d, grouped, lane);
+    chunk_copy_out(sp.rec, len, out + w_rec0, lane, L, sf.flags, sf.pos0 + w_rec0);
+    chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)w_rec0, d, true, lane);
 }
 
 // 0: this species count is emitted in stream order only (a node's records exceed a chunk)
