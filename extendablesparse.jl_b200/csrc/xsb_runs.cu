@@ -251,9 +251,10 @@ template <int HBITS> struct RfShape
     static constexpr int D = HBITS == 6 ? 32 : (HBITS == 5 ? 24 : (HBITS == 15 ? 16 : 12));
     // warps per block; blocks per SM that shared memory and the register file allow.  The largest shape takes
     // 544 B of shared memory per thread: one-warp blocks fit 12 warps per SM where four-warp blocks fit 8
-    // (measured on the block reaction-diffusion system: 2.65 -> 2.34 ms; the small shapes lose with tiny blocks)
-    static constexpr int kWarps = HBITS == 6 ? 1 : 4;
-    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 12 : (HBITS == 15 ? 6 : 5));
+    // (measured on the block reaction-diffusion system: 2.65 -> 2.34 ms; the small shapes lose with tiny blocks).
+    // The 32/16 shape takes 272 B per thread: five blocks of five warps = 25 warps per SM (four-warp blocks: 24).
+    static constexpr int kWarps = HBITS == 6 ? 1 : (HBITS == 15 ? 5 : 4);
+    static constexpr int kBlocks = HBITS == 4 ? 8 : (HBITS == 6 ? 12 : 5);
     static constexpr size_t kBytesPerWarp = 32 * (sizeof(u32) * H + (sizeof(double) + 1) * D);
 };
 
@@ -446,7 +447,10 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
             // place first (insertion sort: the descriptors arrive nearly in order) and reads it W at a time.
             // W descriptors in registers (8; the small table shape serves short columns met by few chunks: 4)
             constexpr int W = HBITS == 4 ? 4 : 8;
-            constexpr int DEPTH = (HBITS == 4 || HBITS == 15) ? 2 : 3; // sectors in flight ahead of the one being folded
+            // Sectors in flight ahead of the one being folded.  With 24 warps per SM the warps hide each other's loads:
+            // a deeper software pipeline only costs instructions and registers (FEM: depth 3 / 2 / 1 = 1.44 (at 20
+            // warps) / 1.30 / 1.24 ms); the 12 warps of the largest shape want one more (1.78 / 1.69 / 1.85 at 1 / 2 / 4)
+            constexpr int DEPTH = (HBITS == 4 || HBITS == 15) ? 1 : 2;
             u64 *b = bucket + ps;
             if (np > (u32)W)
             {
@@ -554,8 +558,8 @@ runfold_kernel(const Rec *__restrict__ buf, int low, int rowbits, u32 maxlen, co
                     const u32 take = (mm + 1u) >> 1;
                     const unsigned char *sec = base32 + (size_t)(pos >> 1) * 32u;
                     qq = ld_pair_stream(reinterpret_cast<const Rec *>(sec));
-                    if (rem >= 12u) // long run: pull the sector four steps ahead from HBM into L2 meanwhile
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(sec + 160));
+                    if (rem >= 8u) // long run: pull the sector some steps ahead from HBM into L2 meanwhile
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(sec + 96));
                     pos += take;
                     rem -= take;
                     left -= take;
