@@ -2197,10 +2197,10 @@ int32_t xsb_insert_triplets(xsb_matrix *h, int32_t tid, const xsb_triplet *T, in
             if (grouped)
                 chunks += pack_triplets_grouped(h->stream, src, cnt, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour,
                                                 dst + off, h->d_scal + 1, h->lc, rt, chunk0 + pack_chunks(off),
-                                                pos0 + (u32)off, sf);
+                                                pos0 + (u32)off, sf, off);
             else
                 pack_triplets(h->stream, src, cnt, h->base, h->m, h->n_global, h->Ls, (u32)tid, (u32)flavour, dst + off,
-                              h->d_scal + 1, h->lc, sf);
+                              h->d_scal + 1, h->lc, sf, off);
         }
         const u64 bad = read_scalar(h, 1);
         if (bad != ~0ull)

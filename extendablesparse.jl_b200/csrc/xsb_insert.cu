@@ -61,7 +61,7 @@ void pack_records(cudaStream_t stream, const void *I, const void *J, const doubl
 // its own 16 bytes), so neither pointer is __restrict__.
 __global__ void __launch_bounds__(256)
 pack_triplets_kernel(const uint4 *in, i64 count, u32 base, i64 m, i64 n, KeyLayout L, u32 tid, u32 flavour,
-                     Rec *out, u64 *__restrict__ d_err, StageFlags sf)
+                     Rec *out, u64 *__restrict__ d_err, StageFlags sf, i64 k0)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
@@ -70,7 +70,7 @@ pack_triplets_kernel(const uint4 *in, i64 count, u32 base, i64 m, i64 n, KeyLayo
         const i64 i = (i64)t.x - (i64)base, j = (i64)t.y - (i64)base;
         if (i < 0 || i >= m || j < 0 || j >= n)
         { // BoundsError: sparsematrixcsc.jl:8-10
-            atomicMin(d_err, (u64)k);
+            atomicMin(d_err, (u64)(k0 + k));
             continue;
         }
         Rec r;
@@ -81,14 +81,14 @@ pack_triplets_kernel(const uint4 *in, i64 count, u32 base, i64 m, i64 n, KeyLayo
 }
 
 void pack_triplets(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
-                   u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, StageFlags sf)
+                   u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, StageFlags sf, i64 k0)
 {
     if (count <= 0)
         return;
     const int threads = 256;
     const int blocks = (int)std::min<i64>((count + threads - 1) / threads, (i64)kNumSM * 16);
     pack_triplets_kernel<<<blocks, threads, 0, stream>>>(static_cast<const uint4 *>(T), count, (u32)base, m, n, L,
-                                                         tid, flavour, out, d_err, sf);
+                                                         tid, flavour, out, d_err, sf, k0);
     lc.add();
     XSB_CUDA(cudaGetLastError());
 }
@@ -103,6 +103,7 @@ template <typename Ti> struct SrcIJV
     const Ti *I, *J;
     const double *V;
     i64 base;
+    i64 k0 = 0; // position of entry 0 in the caller's batch (error reports)
     __device__ __forceinline__ void load(i64 k, i64 &i, i64 &j, double &v) const
     {
         i = (i64)I[k] - base;
@@ -119,6 +120,7 @@ struct SrcTriplet
 {
     const uint4 *T; // may alias the output: a warp reads its whole chunk before it writes any of it
     i64 base;
+    i64 k0 = 0; // position of entry 0 in the caller's batch (a large host batch arrives in slices)
     __device__ __forceinline__ void load(i64 k, i64 &i, i64 &j, double &v) const
     {
         const uint4 t = T[k];
@@ -168,7 +170,7 @@ pack_grouped_kernel(Src src, i64 count, u32 nchunks, i64 m, i64 n, KeyLayout L, 
             src.load(c0 + p, i, j, v);
             if (i < 0 || i >= m || j < 0 || j >= n)
             { // BoundsError (sparsematrixcsc.jl:8-10): the batch is rejected, whatever is written here is dropped
-                atomicMin(d_err, (u64)(c0 + p));
+                atomicMin(d_err, (u64)(src.k0 + c0 + p));
                 i = 0;
                 j = 0;
             }
@@ -277,7 +279,7 @@ pack_grouped2_kernel(Src src, i64 count, u32 nchunks, i64 m, i64 n, KeyLayout L,
             if (p < len)
             {
                 if (ii[u] < 0 || ii[u] >= m || jj[u] < 0 || jj[u] >= n)
-                    atomicMin(d_err, (u64)(c0 + p));
+                    atomicMin(d_err, (u64)(src.k0 + c0 + p));
                 sp.g[p] = (u32)(key_of(ii[u], jj[u]) >> rt.colshift) & rt.gmask;
             }
         }
@@ -445,11 +447,11 @@ u32 pack_records_grouped(cudaStream_t stream, const void *I, const void *J, cons
 
 u32 pack_triplets_grouped(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
                           u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0,
-                          StageFlags sf)
+                          StageFlags sf, i64 k0)
 {
     if (count <= 0)
         return 0;
-    return launch_pack_grouped(stream, SrcTriplet{static_cast<const uint4 *>(T), (i64)base}, count, m, n, L, tid, flavour,
+    return launch_pack_grouped(stream, SrcTriplet{static_cast<const uint4 *>(T), (i64)base, k0}, count, m, n, L, tid, flavour,
                                out, d_err, rt, chunk0, pos0, sf, lc, static_cast<const void *>(T) == static_cast<const void *>(out));
 }
 

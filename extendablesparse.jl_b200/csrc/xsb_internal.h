@@ -291,7 +291,7 @@ u32 pack_records_grouped(cudaStream_t stream, const void *I, const void *J, cons
                          LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0, StageFlags sf);
 u32 pack_triplets_grouped(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
                           u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, const RunTarget &rt, u32 chunk0, u32 pos0,
-                          StageFlags sf);
+                          StageFlags sf, i64 k0 = 0);
 u32 emit_fdrand_chunks(i64 l_begin, i64 l_end);
 u32 emit_fdrand_grouped(cudaStream_t stream, i64 nx, i64 ny, i64 nz, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavour,
                         i64 l_begin, i64 l_end, Rec *out, LaunchCounter &lc, StageFlags sf, const RunTarget &rt, u32 chunk0,
@@ -308,7 +308,7 @@ void pointblock_emit(cudaStream_t stream, const CscView &csc, i64 n, int idx64, 
 void pointblock_fill(cudaStream_t stream, const CscView &csc, i64 n, int idx64, int base, i64 bs,
                      const CscView &pattern, double *blocks, u64 *d_err, LaunchCounter &lc);
 void pack_triplets(cudaStream_t stream, const void *T, i64 count, int base, i64 m, i64 n, KeyLayout L, u32 tid,
-                   u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, StageFlags sf);
+                   u32 flavour, Rec *out, u64 *d_err, LaunchCounter &lc, StageFlags sf, i64 k0 = 0);
 void unpack_records(cudaStream_t stream, const Rec *in, i64 count, int idx64, int base, KeyLayout L, void *I,
                     void *J, double *V, int *flavour, LaunchCounter &lc);
 i64 fdrand_prefix(i64 nx, i64 ny, i64 nz, i64 l); // records emitted by nodes [0,l)

@@ -154,8 +154,9 @@ def test_insertion_paths_agree_with_the_emitter(xsb, torch):
     h.reset()
     bad = hT.clone()
     bad[cnt - 7, 0] = (n + 1) | (1 << 32)  # row n + 1 in the last slice
-    with pytest.raises(IndexError):
+    with pytest.raises(IndexError) as e:
         h.insert_triplets(bad, xsb.RAW, 0, cnt)
+    assert f"entry {cnt - 7} " in str(e.value)  # position in the caller's batch, not in the slice
     assert h.pending == 0
     h.insert_triplets(hT, xsb.RAW, 0, cnt)
     h.flush()
