@@ -190,6 +190,19 @@ mutable struct B200Assembler{Tv, Ti <: Integer}
                         y.handle = C_NULL), x)
         x
     end
+    # column slab of a matrix sharded over `nranks` processes: rank r owns columns col_splits[r+1]+1 : col_splits[r+2]
+    # (col_splits 0-based, nranks + 1 entries); insertions carry GLOBAL indices, the CSC is the slab's
+    function B200Assembler{Tv, Ti}(m, n, nranks::Integer, rank::Integer, col_splits::Vector{Int64}; device = 0) where {Tv, Ti}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:xsb_create_slab, libxsb), Int32,
+                   (Int64, Int64, Int32, Int32, Ptr{Int64}, Int32, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+                   m, n, nranks, rank, col_splits, XSB_F64, idxcode(Ti), 1, device, h)
+        check(Ptr{Cvoid}(C_NULL), rc)
+        x = new{Tv, Ti}(m, n, h[])
+        finalizer(y -> (y.handle == C_NULL || ccall((:xsb_destroy, libxsb), Int32, (Ptr{Cvoid},), y.handle);
+                        y.handle = C_NULL), x)
+        x
+    end
 end
 
 function set_csc!(a::B200Assembler{Tv, Ti}, csc::SparseMatrixCSC{Tv, Ti}) where {Tv, Ti}
@@ -271,6 +284,40 @@ function pattern_equal(a::B200Assembler, b::B200Assembler)
     eq[] != 0
 end
 
+# ---- multi-GPU: one Julia process (MPI rank) per GPU, column slabs, peer exchange over NVLink (INTEGRATION.md §4) ----
+"""
+    peer_exchange!(a, caps_in, allgather)
+
+Collective over the ranks of one node.  `caps_in[src+1]` = record slots this rank offers to rank `src` (0: the two
+ranks exchange nothing); `allgather(v::Vector)` concatenates every rank's `v` in rank order (e.g.
+`v -> MPI.Allgather(v, comm)`).  Afterwards every assembly step is `route_step!(a)`; `flush` follows as usual.
+"""
+function peer_exchange!(a::B200Assembler, caps_in::Vector{Int64}, allgather)
+    caps = allgather(caps_in)                       # caps[dst * n + src + 1]
+    handle = Vector{UInt8}(undef, 64)
+    check(a.handle, ccall((:xsb_peer_exchange_create, libxsb), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{UInt8}),
+                          a.handle, caps, handle))
+    handles = allgather(handle)
+    check(a.handle, ccall((:xsb_peer_exchange_connect, libxsb), Int32, (Ptr{Cvoid}, Ptr{UInt8}), a.handle, handles))
+    a
+end
+
+"what other ranks own leaves for their mailboxes, what they sent is taken (both stream-ordered, no host round trip)"
+function route_step!(a::B200Assembler)
+    check(a.handle, ccall((:xsb_route_pack_peer, libxsb), Int32, (Ptr{Cvoid},), a.handle))
+    check(a.handle, ccall((:xsb_route_unpack_peer, libxsb), Int32, (Ptr{Cvoid},), a.handle))
+    a
+end
+
+"teardown: every rank disconnects, `barrier()`, every rank frees its mailbox"
+function peer_exchange_close!(a::B200Assembler, barrier)
+    check(a.handle, ccall((:xsb_peer_exchange_disconnect, libxsb), Int32, (Ptr{Cvoid},), a.handle))
+    barrier()
+    check(a.handle, ccall((:xsb_peer_exchange_destroy, libxsb), Int32, (Ptr{Cvoid},), a.handle))
+    a
+end
+
+export peer_exchange!, route_step!, peer_exchange_close!
 export SparseMatrixB200, B200Assembler, pattern_equal, B200ExtendableSparseMatrixCSC, STB200ExtendableSparseMatrixCSC,
        set_csc!, insert!, fetch!, freeze!, reassemble!, pointblock, XsbTriplet
 

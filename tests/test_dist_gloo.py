@@ -125,6 +125,7 @@ def _worker(rank, world, port, m, n, splits, out_q):
             fl = splice  # update flavour, then raw
             D.insert_batch(I, J, V, fl)
             streams.append((I, J, V, fl))
+            D.exchange_begin()  # without the peer transport (this backend; counted steps): nothing to do
             if splice % 2 == 0:
                 nnz, changed = D.flush()
             else:  # offsets all-gather launched only; the global values are read on demand
@@ -132,6 +133,8 @@ def _worker(rank, world, port, m, n, splits, out_q):
                 changed = D.changed_any
             cp, rv, nz = backend.A.csc()
             results.append((nnz, changed, D.nnz_offset, D.nnz_global, cp, rv, nz, dict(D.last_exchange)))
+        assert D.transport_note == "" and D._peer is None  # the CPU double never leaves the counted exchange
+        D.recount()  # collective no-op here; the next flush counts (as every flush of this backend)
         out_q.put((rank, streams, results))
     finally:
         dist.destroy_process_group()
