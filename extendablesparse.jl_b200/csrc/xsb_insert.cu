@@ -1212,7 +1212,6 @@ emit_blockrd_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavour, Rec *
 // flush will read them.
 constexpr int RDG_WARPS = 4;
 constexpr int RDG_HB = 8;
-constexpr int RDG_NB = CH_RECORDS / 32;
 struct RdWarpSpace
 {
     Rec rec[CH_RECORDS];
