@@ -10,6 +10,13 @@ into the rank's CSC slab.  The fold meets the records of an entry as [resident C
 ranks | own | higher ranks], each in stream order -- the distributed result equals the serial
 reference applied to the rank-ordered concatenation of the ranks' streams.
 
+That is the COUNTED exchange of the first step.  An assembly loop repeats its step: from the second
+flush on the blocks have fixed capacities (twice what the counted step moved) and -- on one node --
+travel without any collective: the routing kernel stores every block straight into the receiving
+rank's mailbox over NVLink peer memory and raises a flag there (xsb_route_pack_peer /
+xsb_route_unpack_peer, mailboxes exchanged once through CUDA IPC); NCCL grouped send / receive is
+the fallback (XSB_EXCHANGE=nccl, ranks on several nodes, GPUs without peer access).
+
 Reference analogue: the per-partition buffers of GenericMTExtendableSparseMatrixCSC
 (genericmtextendablesparsematrixcsc.jl:45-51) summed in partition order
 (sparsematrixdilnkc.jl:416-426).  The reference itself is single-process.
