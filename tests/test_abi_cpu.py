@@ -35,6 +35,18 @@ def test_every_declared_symbol_is_exported(xsb):
     assert sorted(xsb.capi.SIGNATURES) == names
 
 
+def test_julia_glue_only_calls_declared_entry_points():
+    """The Julia glue cannot be executed in this image: at least every symbol it ccalls must exist in the header,
+    and the entry points of the drop-in sequence must be among them."""
+    glue = open(os.path.join(ROOT, "extendablesparse.jl_b200", "julia", "ExtendableSparseB200.jl")).read()
+    called = set(re.findall(r"ccall\(\(:(xsb_[a-z0-9_]+)", glue))
+    declared = set(header_functions())
+    assert called and called <= declared, sorted(called - declared)
+    for name in ("xsb_create", "xsb_set_csc", "xsb_insert_triplets", "xsb_flush", "xsb_fetch_csc", "xsb_destroy",
+                 "xsb_create_slab", "xsb_peer_exchange_create", "xsb_route_pack_peer", "xsb_route_unpack_peer"):
+        assert name in called, name
+
+
 def test_version(xsb):
     assert xsb.capi.lib().xsb_version() == 100
 
