@@ -666,12 +666,13 @@ emit_fdrand_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u32 flavo
 // these (node, column) VISITS through its table, weighted by their record counts, kind after kind: z-ends of all
 // nodes, y-ends, x-ends, own columns.  Inside one kind every lane holds a different column (no match.any, no
 // leader election), and a column meets its visitors in node = call order: l - nx*ny (z-end), l - nx (y-end),
-// l - 1 (x-end), l (own).  Then every lane computes its records straight into their place of the grouped chunk in
-// shared memory, and the chunk leaves as whole 32-byte sectors, consecutive lanes to consecutive sectors.
+// l - 1 (x-end), l (own).  Then every lane computes its records and stores them straight to their place of the grouped
+// chunk: a node's 6 .. 9 own-column records are neighbours there, and so are the two a far end receives, so they leave
+// as 256-bit stores wherever two share a sector.  (Staging the chunk in shared memory first -- 7.7 KB per warp --
+// left 30 % of the warp slots in use: 0.83 ms for 200^3; see profiles/r2_summary.md for this version.)
 constexpr int FDG_HB = 8; // 256 slots for at most 128 distinct columns
 struct FdWarpSpace
 {
-    Rec rec[32 * FD_MAXREC];
     ChunkSpaceT<FDG_HB> tab;
 };
 
@@ -710,13 +711,14 @@ emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u
     // position of the chunk in the stream: the records of the nodes before the warp's first one (lane 0 holds it)
     i64 w_rec0 = lane == 0 ? g.before<4>(i, j, k) : 0;
     w_rec0 = __shfl_sync(full, w_rec0, 0);
-    u32 len = w_own + 2u * ((u32)ex + (u32)ey + (u32)ez);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        len += __shfl_xor_sync(full, len, o);
+    const i64 c0 = w_rec0 - rec_begin; // position of the chunk in this launch's output
     if (have)
-    {
-        Rec *own = sp.rec + chunk_dest(sp.tab.start, vo);
+    { // records straight from registers to their place: the own column's 6 .. 9 records are neighbours, and so are the two
+      // a far end receives -- whole 32-byte sectors (STG.256) wherever two of them share one
+        Rec *const dst = out + c0;
+        Rec *own = dst + chunk_dest(sp.tab.start, vo);
+        Rec pend;
+        bool held = false; // pend waits for its sector's upper half
         u64 call = (u64)g.before<1>(i, j, k);
         const double hx = 1.0 / (double)g.nx, hy = 1.0 / (double)g.ny, hz = 1.0 / (double)g.nz;
         auto rnd = [&]() -> double {
@@ -724,37 +726,67 @@ emit_fdrand_grouped_kernel(FdGeom g, u64 seed, int ones, KeyLayout L, u32 tid, u
             ++call;
             return u;
         };
-        auto put = [&](Rec *p, double v, u64 row, u64 col) {
+        auto make = [&](double v, u64 row, u64 col) {
             Rec r;
             r.key = L.pack(col, row, tid, flavour);
             r.val = v;
-            *p = r;
+            return r;
+        };
+        auto mark = [&](const Rec *p, const Rec &r) {
+            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                sf.flags[(sf.pos0 + c0 + (i64)(p - dst)) >> kRouteTileShift] = 1; // benign race: same value
+        };
+        auto pair256 = [&](Rec *p, const Rec &a, const Rec &b) {
+            st_v4_u64(p, a.key, (u64)__double_as_longlong(a.val), b.key, (u64)__double_as_longlong(b.val));
+        };
+        auto put_own = [&](const Rec &r) {
+            mark(own, r);
+            if (held)
+            {
+                pair256(own - 1, pend, r);
+                held = false;
+            }
+            else if (reinterpret_cast<uintptr_t>(own) & 16u)
+                st_rec(own, r); // upper half of a sector whose lower half is somebody else's
+            else
+            {
+                pend = r;
+                held = true;
+            }
+            ++own;
         };
         // update_pair(v, a = l, b): (-v, a, b) (-v, b, a) (v, a, a) (v, b, b) in call order (sprand.jl:87-92):
         // the first and the last go to column b, the two in the middle to the node's own column
         auto pair = [&](double v, u64 b, u32 visit) {
-            Rec *far = sp.rec + chunk_dest(sp.tab.start, visit);
-            put(far, -v, l, b);
-            put(own++, -v, b, l);
-            put(own++, v, l, l);
-            put(far + 1, v, b, b);
+            Rec *far = dst + chunk_dest(sp.tab.start, visit);
+            const Rec f0 = make(-v, l, b), f1 = make(v, b, b);
+            mark(far, f0);
+            mark(far + 1, f1);
+            if (reinterpret_cast<uintptr_t>(far) & 16u)
+            {
+                st_rec(far, f0);
+                st_rec(far + 1, f1);
+            }
+            else
+                pair256(far, f0, f1);
+            put_own(make(-v, b, l));
+            put_own(make(v, l, l));
         };
         if (ex)
             pair(rnd() * hy * hz / hx, l + sx, vx);
         if (bx)
-            put(own++, rnd() * hy * hz, l, l);
+            put_own(make(rnd() * hy * hz, l, l));
         if (ey)
             pair(rnd() * hx * hz / hy, l + sy, vy);
         if (by)
-            put(own++, rnd() * hx * hz, l, l);
+            put_own(make(rnd() * hx * hz, l, l));
         if (ez)
             pair(rnd() * hx * hy / hz, l + sz, vz);
         if (bz)
-            put(own++, rnd() * hx * hy, l, l);
+            put_own(make(rnd() * hx * hy, l, l));
+        if (held)
+            st_rec(own - 1, pend);
     }
-    __syncwarp();
-    const i64 c0 = w_rec0 - rec_begin; // position of the chunk in this launch's output
-    chunk_copy_out(sp.rec, len, out + c0, lane, L, sf.flags, sf.pos0 + c0);
     chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)c0, d, true, lane);
 }
 
