@@ -1246,7 +1246,6 @@ constexpr int RDG_WARPS = 4;
 constexpr int RDG_HB = 8;
 struct RdWarpSpace
 {
-    Rec rec[CH_RECORDS];
     u32 vis[4 * 32]; // visits [kind][lane]: (slot, records of the column before the visit)
     ChunkSpaceT<RDG_HB> tab;
 };
@@ -1272,7 +1271,8 @@ static int rd_nodes_per_warp(i64 ns)
 // edge pair it emits 2 ns records per column, plus ns reaction records -- and the ns columns of each far end (2 ns
 // records per column).  A warp holds npw nodes, so a kind of visit (z-ends, y-ends, x-ends, own) has npw * ns <= 32
 // (node, species) visitors with different columns; a column meets its visitors in node = call order.  Every
-// (node, a, b) item then computes its 13 records straight into their place of the grouped chunk in shared memory:
+// (node, a, b) item then computes its 13 records and stores them straight to their place of the grouped chunk (the two
+// records a pair leaves in a column are neighbours: one 256-bit store where they share a sector):
 //   far column (pair d, species b):  (-v, i_a, j_b) at 2 a, (v, j_a, j_b) at 2 a + 1
 //   own column b: pair d (the dd-th existing one): (-v, j_a, i_b) at 2 ns dd + 2 a, (v, i_a, i_b) one behind it;
 //                 reaction (i_a, i_b) at 2 ns nd + a
@@ -1333,7 +1333,24 @@ emit_blockrd_grouped_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavou
         const bool has[3] = {i < g.nx, j < g.ny, k < g.nz};
         const u64 ia = (u64)((i64)ns * l0) + a, ib = (u64)((i64)ns * l0) + b;
         const u32 v = nl * ns + b; // the visitor that speaks for this item's columns
-        Rec *own = sp.rec + chunk_dest(sp.tab.start, sp.vis[3 * 32 + v]) + 2u * a;
+        Rec *const dst = out + w_rec0;
+        Rec *own = dst + chunk_dest(sp.tab.start, sp.vis[3 * 32 + v]) + 2u * a;
+        auto mark = [&](const Rec *p, const Rec &r) {
+            if (sf.flags != nullptr && L.owner(r.key) != (u32)L.self)
+                sf.flags[(sf.pos0 + w_rec0 + (i64)(p - dst)) >> kRouteTileShift] = 1; // benign race: same value
+        };
+        // two neighbouring records: one 256-bit store when they share a sector
+        auto put2 = [&](Rec *p, const Rec &r0, const Rec &r1) {
+            mark(p, r0);
+            mark(p + 1, r1);
+            if (reinterpret_cast<uintptr_t>(p) & 16u)
+            {
+                st_rec(p, r0);
+                st_rec(p + 1, r1);
+            }
+            else
+                st_v4_u64(p, r0.key, (u64)__double_as_longlong(r0.val), r1.key, (u64)__double_as_longlong(r1.val));
+        };
 #pragma unroll
         for (int dd = 0; dd < 3; ++dd)
         {
@@ -1342,28 +1359,28 @@ emit_blockrd_grouped_kernel(RdGeom g, u64 seed, KeyLayout L, u32 tid, u32 flavou
             const double val = philox_uniform(seed, call + (u64)ab);
             const u64 l2 = (u64)(l0 + step[dd]);
             const u64 ja = (u64)ns * l2 + a, jb = (u64)ns * l2 + b;
-            Rec *far = sp.rec + chunk_dest(sp.tab.start, sp.vis[dd * 32 + v]) + 2u * a;
-            Rec r;
-            r.val = -val;
-            r.key = L.pack(jb, ia, tid, flavour); // (-v, i_a, j_b)
-            far[0] = r;
-            r.key = L.pack(ib, ja, tid, flavour); // (-v, j_a, i_b)
-            own[0] = r;
-            r.val = val;
-            r.key = L.pack(ib, ia, tid, flavour); // ( v, i_a, i_b)
-            own[1] = r;
-            r.key = L.pack(jb, ja, tid, flavour); // ( v, j_a, j_b)
-            far[1] = r;
+            Rec *far = dst + chunk_dest(sp.tab.start, sp.vis[dd * 32 + v]) + 2u * a;
+            Rec f0, f1, o0, o1;
+            f0.val = -val;
+            f0.key = L.pack(jb, ia, tid, flavour); // (-v, i_a, j_b)
+            o0.val = -val;
+            o0.key = L.pack(ib, ja, tid, flavour); // (-v, j_a, i_b)
+            o1.val = val;
+            o1.key = L.pack(ib, ia, tid, flavour); // ( v, i_a, i_b)
+            f1.val = val;
+            f1.key = L.pack(jb, ja, tid, flavour); // ( v, j_a, j_b)
+            put2(far, f0, f1);
+            put2(own, o0, o1);
             own += 2u * ns;
             call += (u64)ns2;
         }
         Rec r;
         r.val = philox_uniform(seed, call + (u64)ab);
         r.key = L.pack(ib, ia, tid, flavour);
-        own[0 - (int)a] = r; // the reaction block follows the pairs: position 2 ns nd + a (own stands at ... + 2 a)
+        Rec *rp = own - (int)a; // the reaction block follows the pairs: position 2 ns nd + a (own stands at ... + 2 a)
+        mark(rp, r);
+        st_rec(rp, r);
     }
-    __syncwarp();
-    chunk_copy_out(sp.rec, len, out + w_rec0, lane, L, sf.flags, sf.pos0 + w_rec0);
     chunk_publish(sp.tab, rt, chunk0 + wchunk, pos_out + (u32)w_rec0, d, true, lane);
 }
 
