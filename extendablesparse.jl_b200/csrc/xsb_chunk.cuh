@@ -152,40 +152,6 @@ __device__ __forceinline__ u32 chunk_visit_batch(ChunkSpaceT<HB> &ws, u32 g, boo
     return (slot << 16) | old;
 }
 
-// A grouped chunk that was put together in shared memory leaves as whole 32-byte sectors (two records per 256-bit
-// store), consecutive lanes to consecutive sectors.  Slab handles: tiles that receive a record of another rank are
-// marked; pos = position of dst[0] in the staging buffer.
-__device__ __forceinline__ void chunk_copy_out(const Rec *src, u32 len, Rec *dst, int lane, const KeyLayout &L,
-                                               unsigned char *flags, i64 pos)
-{
-    const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) >> 4) & 1u; // dst[0] is the upper half of its sector
-    auto mark = [&](const Rec &r, u32 t) {
-        if (flags != nullptr && L.owner(r.key) != (u32)L.self)
-            flags[(pos + (i64)t) >> kRouteTileShift] = 1; // benign race: same value
-    };
-    if (a && lane == 0 && len > 0)
-    {
-        const Rec r = src[0];
-        st_rec(dst, r);
-        mark(r, 0);
-    }
-    const u32 pairs = (len - min(a, len)) >> 1;
-    for (u32 q = lane; q < pairs; q += 32)
-    {
-        const u32 t = a + 2 * q;
-        const Rec r0 = src[t], r1 = src[t + 1];
-        st_v4_u64(dst + t, r0.key, (u64)__double_as_longlong(r0.val), r1.key, (u64)__double_as_longlong(r1.val));
-        mark(r0, t);
-        mark(r1, t + 1);
-    }
-    if (len > a && ((len - a) & 1u) && lane == 31)
-    {
-        const Rec r = src[len - 1];
-        st_rec(dst + len - 1, r);
-        mark(r, len - 1);
-    }
-}
-
 // offsets of the runs: exclusive sum of the columns' record counts in order of first appearance.
 // MUL: every counted request stands for MUL records (a producer that knows that its records come in groups of
 // MUL per column counts the groups: emit_p1fem_grouped_kernel)
